@@ -1,0 +1,168 @@
+/*
+ * isr_b200.h -- C ABI of libisr_b200.so: the B200-native (sm_100a, FP64) implementation of
+ * ISRSolver's data-parallel hot path.
+ *
+ * The reference (sergeigribanov/ISRSolver) has no C ABI; its boundary for this path is the C++
+ * class API plus the PyISR CPython module.  Each entry point below names the reference interface it
+ * replaces (paths relative to the reference tree).  All pointers are HOST pointers unless the
+ * parameter name ends in _dev.  Matrices cross the ABI COLUMN-MAJOR (Eigen::MatrixXd storage, what
+ * extractIntOpMatrix / extractBCSCovMatrix hand to NumPy: src/ISRSolverSLE.cpp:19-25).  Every call
+ * returns 0 on success or an ISR_E* code; isr_last_error() gives the message.  No exceptions cross
+ * the ABI.  Calls on one isr_problem must not run concurrently; different problems may.
+ *
+ * There is no CPU fallback: without a CUDA device isr_ctx_create fails with ISR_ECUDA.
+ */
+#ifndef ISR_B200_H
+#define ISR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISR_OK 0
+#define ISR_EINVAL 1      /* bad argument */
+#define ISR_ERANGE 2      /* InterpRangeException (include/Interpolator.hpp:14-18) */
+#define ISR_ECUDA 3       /* CUDA / cuSOLVER / cuBLAS failure */
+#define ISR_ESTATE 4      /* call order violated (e.g. toy batch before factor) */
+#define ISR_ENUMERIC 5    /* singular matrix / non-SPD regulariser */
+#define ISR_EEFFDIM 6     /* EfficiencyDimensionException (include/BaseISRSolver.hpp:24-28) */
+
+typedef struct isr_ctx isr_ctx;         /* one CUDA device + stream + library handles */
+typedef struct isr_problem isr_problem; /* one solver instance: energies, basis, epsilon, G, factors */
+
+/* Detection efficiency.  Replaces std::function<double(double,double)> efficiency
+ * (include/BaseISRSolver.hpp:36-41) as built by BaseISRSolver::_setupEfficiency
+ * (src/BaseISRSolver.cpp:232-258) and BaseISRSolver2::_setupEfficiency (src/BaseISRSolver2.cpp:231-236).
+ * `values` include ROOT's underflow (index 0) and overflow (index nbins+1) cells. */
+enum {
+  ISR_EPS_ONE = 0,       /* efficiency == 1 (src/BaseISRSolver.cpp:140) */
+  ISR_EPS_ROW_TABLE = 1, /* v2: one TH1D in x per energy point; values[N][nx+2] */
+  ISR_EPS_TABLE_2D = 2,  /* TEfficiency 2-D in (x, E); values[(ne+2)][(nx+2)], global bin bx+(nx+2)*by */
+  ISR_EPS_E_ONLY = 3     /* TEfficiency 1-D: a function of E only; values[ne+2] */
+};
+typedef struct {
+  int kind;
+  int nx; double xlo, xhi; const double* xedges; /* xedges == NULL: nx fixed-width bins on [xlo,xhi) */
+  int ne; double elo, ehi; const double* eedges; /* same for the energy axis */
+  const double* values;
+} isr_eps_desc;
+
+/* ---- context ---------------------------------------------------------------------------------- */
+int isr_ctx_create(int device, isr_ctx** out);
+void isr_ctx_destroy(isr_ctx* ctx);
+const char* isr_last_error(void);
+/* cudaStream_t used by all launches of this context (as void*), for event timing by the caller. */
+void* isr_ctx_stream(isr_ctx* ctx);
+int isr_ctx_synchronize(isr_ctx* ctx);
+
+/* ---- problem ---------------------------------------------------------------------------------- */
+/* Replaces BaseISRSolver(n, energy, ...) + Interpolator(settings, ecm, threshold)
+ * (src/BaseISRSolver.cpp:77-129; src/Interpolator.cpp:34-83).  `ecm` must already be sorted ascending
+ * (the host class applies the reference's sort permutation).  ranges: nranges x {cubic?, firstSeg,
+ * lastSeg} as in the interpolation-settings JSON (README.md:177-188); nranges == 0 selects the default
+ * single linear range (src/Interpolator.cpp:356-360).  Invalid ranges -> ISR_ERANGE. */
+int isr_problem_create(isr_ctx* ctx, int n, const double* ecm, double threshold, int nranges,
+                       const int* ranges, const isr_eps_desc* eps, isr_problem** out);
+void isr_problem_destroy(isr_problem* p);
+/* ISRSolverSLE::setRangeInterpSettings (src/ISRSolverSLE.cpp:125-136) */
+int isr_problem_set_ranges(isr_problem* p, int nranges, const int* ranges);
+
+/* ISRSolverSLE::evalEqMatrix (src/ISRSolverSLE.cpp:138-149): G(i,j) = integral of F * basis_j * eps,
+ * optionally G <- G_spread * G (src/ISRSolverSLE.cpp:177-193) when ecm_err != NULL.
+ * G_out (N*N, column-major) may be NULL (matrix stays on the device). */
+int isr_assemble(isr_problem* p, const double* ecm_err, double* G_out);
+/* Inject a matrix instead of assembling it (tests of the solve path; column-major). */
+int isr_set_matrix(isr_problem* p, const double* G);
+/* Number of quadrature panels / integrand nodes of the last isr_assemble (roofline unit counts). */
+int isr_assemble_stats(isr_problem* p, int64_t* n_panels, int64_t* n_nodes);
+/* Debug/inspection: copy out the panel list of the last assembly.  Each panel = 4 doubles
+ * {a, b, eps, kind} and 2 ints {row, segment}.  Pass NULL to query the count only. */
+int isr_debug_panels(isr_problem* p, int64_t cap, double* ab_eps_kind, int* row_seg, int64_t* count);
+/* Debug/inspection: per-(row, segment) normalised moments M[i][k][0..3] (N*N*4, row-major). */
+int isr_debug_moments(isr_problem* p, double* M_out);
+
+/* kernelKuraevFadin(x, s) evaluated on the device (include/KuraevFadin.hpp:13; PyISR
+ * "kernelKuraevFadin", include/PyKuraevFadin.hpp:9-17). */
+int isr_kernel_kf(isr_ctx* ctx, int64_t n, const double* x, const double* s, double* out);
+
+/* Basis queries (Interpolator::basisEval / basisDerivEval / evalIntegralBasis,
+ * src/Interpolator.cpp:217-287, 459-473), evaluated from the device-resident coefficient tables. */
+int isr_basis_eval(isr_problem* p, int64_t n, const int* cs_index, const double* energy, int deriv, double* out);
+int isr_basis_integrals(isr_problem* p, double* w_out /* N */);
+/* ISRSolverSLE::interpEval (src/ISRSolverSLE.cpp:195-198) */
+int isr_interp_eval(isr_problem* p, const double* y, int64_t n, const double* energy, double* out);
+
+/* ---- solve ------------------------------------------------------------------------------------ */
+/* One-time factorisation for a given error vector: S = G^-1, R = W^(1/2) G, Cov = S W^-1 S^T
+ * (replaces the per-call COD + (G^T W G)^-1 of ISRSolverSLE::solve, src/ISRSolverSLE.cpp:91-94). */
+int isr_factor(isr_problem* p, const double* vcs_err);
+/* ISRSolverSLE::solve: bcs = G^-1 vcs; cov_out (N*N col-major) may be NULL. */
+int isr_solve(isr_problem* p, const double* vcs, double* bcs_out, double* cov_out);
+int isr_get_inverse(isr_problem* p, double* Ginv_out);         /* column-major */
+int isr_get_inv_cov(isr_problem* p, double* inv_cov_out);      /* G^T W G, column-major */
+/* ISRSolverSLE::evalConditionNumber (src/ISRSolverSLE.cpp:200-204) */
+int isr_cond_number(isr_problem* p, double* cond_out);
+
+/* ---- toy Monte-Carlo batch -------------------------------------------------------------------- */
+/* The loop bodies of chi2Test (src/Chi2Test.cpp:38-60), chi2TestData (:177-183) and ratioTestModel
+ * (src/RatioTest.cpp:38-45) over T toys at once:
+ *   b_k = S v_k ;  chi2_k = || R (b_k - bcs0) ||^2  (== (b_k-b0)^T Cov^-1 (b_k-b0))
+ *   sum_bcs[j] = sum_k b_k[j] ;  ratio_stats[j] = {count, sum r, sum r^2} of r = (b_k[j]-b0[j])/b0[j]
+ *   restricted to -2 <= r < 2 (TH1F(1024,-2,2) in-range statistics) ; ratio_hist[j][0..1025] counts.
+ * V is toy-major T x N.  Any output pointer may be NULL.  Uses the solver set by the last
+ * isr_factor / isr_tikhonov_select / isr_tsvd_select. */
+int isr_toy_batch(isr_problem* p, int64_t T, const double* V, const double* bcs0, double* chi2_out,
+                  double* sum_bcs_out, double* ratio_stats_out, uint32_t* ratio_hist_out, double* bcs_out);
+/* Same with device-resident V / outputs (accumulators are ADDED to, caller zeroes them). */
+int isr_toy_batch_dev(isr_problem* p, int64_t T, const double* V_dev, const double* bcs0,
+                      double* chi2_dev, double* sum_bcs_dev, double* ratio_stats_dev,
+                      uint32_t* ratio_hist_dev, double* bcs_dev);
+/* Kernel variant: 0 = auto, 1 = DMMA (mma.sync f64 tensor pipe), 2 = DFMA (CUDA cores). */
+int isr_set_toy_kernel(isr_problem* p, int variant);
+
+/* chi2 histogram, src/Chi2Test.cpp:64-78: TH1F(128, min, max) filled with every chi2 (ROOT bin
+ * arithmetic; the maximum lands in the overflow cell).  counts_out has nbins+2 entries. */
+int isr_minmax_dev(isr_ctx* ctx, int64_t n, const double* v_dev, double* min_out, double* max_out);
+int isr_histogram_dev(isr_ctx* ctx, int64_t n, const double* v_dev, int nbins, double lo, double hi,
+                      uint32_t* counts_out);
+int isr_chi2_histogram(isr_ctx* ctx, int64_t n, const double* chi2, int nbins, double* lo_out,
+                       double* hi_out, uint32_t* counts_out);
+
+/* ---- Tikhonov --------------------------------------------------------------------------------- */
+/* One decomposition shared by every lambda (replaces _evalProblemMatrices + two FullPivLU per lambda,
+ * src/ISRSolverTikhonov.cpp:139-155): F = D^T diag(w) D (deriv_reg != 0) or diag(w);
+ * generalised eigen-system (G^T W G) u = mu F u, U^T F U = I.  Needs isr_factor's vcs_err. */
+int isr_tikhonov_prepare(isr_problem* p, const double* vcs_err, int deriv_reg);
+/* For each lambda: solve (:61-72) + evalEqNorm2 (:106-109) + evalSmoothnessConstraintNorm2 (:111-113)
+ * + evalLCurveCurvature (:115-119) + evalLCurveCurvatureDerivative (:121-128).
+ * bcs_out: L x N row-major, may be NULL (as any other output). */
+int isr_tikhonov_scan(isr_problem* p, int64_t L, const double* lambda, const double* vcs,
+                      double* eq_norm2_out, double* smooth_norm2_out, double* curv_out,
+                      double* dcurv_out, double* bcs_out);
+/* Full solution for one lambda: bcs and Cov = A+ W^-1 A+^T (col-major; may be NULL). */
+int isr_tikhonov_solve(isr_problem* p, double lambda, const double* vcs, double* bcs_out, double* cov_out);
+/* chi2 of every (lambda, toy) pair: chi2_out[l*T + k]; the chi2Test loop of
+ * isrsolver-Tikhonov-chi2-test run for L lambdas at once.  V toy-major T x N (host). */
+int isr_tikhonov_toy_scan(isr_problem* p, int64_t L, const double* lambda, int64_t T, const double* V,
+                          const double* bcs0, double* chi2_out);
+int isr_tikhonov_toy_scan_dev(isr_problem* p, int64_t L, const double* lambda, int64_t T,
+                              const double* V_dev, const double* bcs0, double* chi2_dev);
+/* Make isr_toy_batch use the Tikhonov operator A+_lambda and its covariance. */
+int isr_tikhonov_select(isr_problem* p, double lambda);
+int isr_get_regulariser(isr_problem* p, double* F_out); /* column-major */
+
+/* ---- TSVD ------------------------------------------------------------------------------------- */
+/* ISRSolverTSVD::solve (src/ISRSolverTSVD.cpp:53-74): one SVD, rank-k (or keep-one) pseudo-inverse.
+ * cov_out is defined only for k == N and !keep_one (the reference inverts a singular matrix otherwise). */
+int isr_tsvd_solve(isr_problem* p, int k, int keep_one, const double* vcs, const double* vcs_err,
+                   double* bcs_out, double* cov_out);
+int isr_singular_values(isr_problem* p, double* sv_out /* N, descending */);
+int isr_tsvd_select(isr_problem* p, int k, int keep_one, const double* vcs_err);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISR_B200_H */

@@ -1,0 +1,138 @@
+"""ctypes binding of libisr_b200.so (the C ABI in include/isr_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or no B200 is visible when a context is
+created, the error is raised to the caller.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libisr_b200.so")
+
+ISR_OK, ISR_EINVAL, ISR_ERANGE, ISR_ECUDA, ISR_ESTATE, ISR_ENUMERIC, ISR_EEFFDIM = range(7)
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_up = C.POINTER(C.c_uint32)
+_i64 = C.c_int64
+_i64p = C.POINTER(C.c_int64)
+_vp = C.c_void_p
+
+
+class IsrGpuError(RuntimeError):
+    """CUDA / cuSOLVER / state errors reported by libisr_b200."""
+
+
+class InterpRangeException(ValueError):
+    """include/Interpolator.hpp:14-18 -- wrong interpolation ranges."""
+
+
+class EfficiencyDimensionException(ValueError):
+    """include/BaseISRSolver.hpp:24-28 -- wrong efficiency dimension."""
+
+
+class EpsDesc(C.Structure):
+    _fields_ = [("kind", C.c_int), ("nx", C.c_int), ("xlo", C.c_double), ("xhi", C.c_double),
+                ("xedges", _dp), ("ne", C.c_int), ("elo", C.c_double), ("ehi", C.c_double),
+                ("eedges", _dp), ("values", _dp)]
+
+
+# name -> (restype, argtypes); every symbol include/isr_b200.h declares
+SIGNATURES = {
+    "isr_ctx_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "isr_ctx_destroy": (None, [_vp]),
+    "isr_last_error": (C.c_char_p, []),
+    "isr_ctx_stream": (_vp, [_vp]),
+    "isr_ctx_synchronize": (C.c_int, [_vp]),
+    "isr_problem_create": (C.c_int, [_vp, C.c_int, _dp, C.c_double, C.c_int, _ip, C.POINTER(EpsDesc), C.POINTER(_vp)]),
+    "isr_problem_destroy": (None, [_vp]),
+    "isr_problem_set_ranges": (C.c_int, [_vp, C.c_int, _ip]),
+    "isr_assemble": (C.c_int, [_vp, _dp, _dp]),
+    "isr_set_matrix": (C.c_int, [_vp, _dp]),
+    "isr_assemble_stats": (C.c_int, [_vp, _i64p, _i64p]),
+    "isr_debug_panels": (C.c_int, [_vp, _i64, _dp, _ip, _i64p]),
+    "isr_debug_moments": (C.c_int, [_vp, _dp]),
+    "isr_kernel_kf": (C.c_int, [_vp, _i64, _dp, _dp, _dp]),
+    "isr_basis_eval": (C.c_int, [_vp, _i64, _ip, _dp, C.c_int, _dp]),
+    "isr_basis_integrals": (C.c_int, [_vp, _dp]),
+    "isr_interp_eval": (C.c_int, [_vp, _dp, _i64, _dp, _dp]),
+    "isr_factor": (C.c_int, [_vp, _dp]),
+    "isr_solve": (C.c_int, [_vp, _dp, _dp, _dp]),
+    "isr_get_inverse": (C.c_int, [_vp, _dp]),
+    "isr_get_inv_cov": (C.c_int, [_vp, _dp]),
+    "isr_cond_number": (C.c_int, [_vp, _dp]),
+    "isr_toy_batch": (C.c_int, [_vp, _i64, _dp, _dp, _dp, _dp, _dp, _up, _dp]),
+    "isr_toy_batch_dev": (C.c_int, [_vp, _i64, _vp, _dp, _vp, _vp, _vp, _vp, _vp]),
+    "isr_set_toy_kernel": (C.c_int, [_vp, C.c_int]),
+    "isr_minmax_dev": (C.c_int, [_vp, _i64, _vp, _dp, _dp]),
+    "isr_histogram_dev": (C.c_int, [_vp, _i64, _vp, C.c_int, C.c_double, C.c_double, _up]),
+    "isr_chi2_histogram": (C.c_int, [_vp, _i64, _dp, C.c_int, _dp, _dp, _up]),
+    "isr_tikhonov_prepare": (C.c_int, [_vp, _dp, C.c_int]),
+    "isr_tikhonov_scan": (C.c_int, [_vp, _i64, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "isr_tikhonov_solve": (C.c_int, [_vp, C.c_double, _dp, _dp, _dp]),
+    "isr_tikhonov_toy_scan": (C.c_int, [_vp, _i64, _dp, _i64, _dp, _dp, _dp]),
+    "isr_tikhonov_toy_scan_dev": (C.c_int, [_vp, _i64, _dp, _i64, _vp, _dp, _vp]),
+    "isr_tikhonov_select": (C.c_int, [_vp, C.c_double]),
+    "isr_get_regulariser": (C.c_int, [_vp, _dp]),
+    "isr_tsvd_solve": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp]),
+    "isr_singular_values": (C.c_int, [_vp, _dp]),
+    "isr_tsvd_select": (C.c_int, [_vp, C.c_int, C.c_int, _dp]),
+}
+
+_LIB = None
+
+
+def load():
+    """dlopen libisr_b200.so and bind every declared symbol.  Raises if the library is not built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise IsrGpuError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  isrsolver_b200 has no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = lib
+    return _LIB
+
+
+def check(rc: int):
+    if rc == ISR_OK:
+        return
+    msg = load().isr_last_error().decode("utf-8", "replace")
+    if rc == ISR_ERANGE:
+        raise InterpRangeException(msg)
+    if rc == ISR_EEFFDIM:
+        raise EfficiencyDimensionException(msg)
+    if rc == ISR_EINVAL:
+        raise ValueError(msg)
+    raise IsrGpuError(f"[isr rc={rc}] {msg}")
+
+
+def dptr(a):
+    """double* of a C-contiguous float64 ndarray (None -> NULL)."""
+    if a is None:
+        return None
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_dp)
+
+
+def iptr(a):
+    if a is None:
+        return None
+    assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_ip)
+
+
+def uptr(a):
+    if a is None:
+        return None
+    assert a.dtype == np.uint32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_up)

@@ -1,0 +1,747 @@
+// Matrix assembly: G(i,j) = int F(x, s_i) * eps_i(x) * basis_j(E_i sqrt(1-x)) dx.
+//
+// Replaces ISRSolverSLE::evalEqMatrix (src/ISRSolverSLE.cpp:138-149) and the N^2 adaptive GSL
+// integrations below it (src/Interpolator.cpp:437-453 -> src/LinearRangeInterpolator.cpp:57-101 /
+// src/CSplineRangeInterpolator.cpp:88-110 -> src/KuraevFadin.cpp:56-73 -> src/Integration.cpp:19-81).
+//
+// Design (DESIGN.md "Assembly"): per (row i, energy segment k <= i) the x-interval
+// [1-(ext[k+1]/E_i)^2, 1-(ext[k]/E_i)^2] is cut at the pair threshold x0 = 4 m_e / E_i, at the
+// efficiency bin edges and at a few geometric grading points; every resulting panel gets one
+// 16-point Gauss-Legendre rule -- in x (regular panels), in t = x^beta (panels in [0, x0]: removes
+// the x^(beta-1) and log(x) endpoint singularities) or in u = (x-x0)^beta (the panel touching x0 from
+// above: removes the (x-x0)^beta infinite slope of the pair term).  Each panel yields the four
+// normalised moments  M_p = int F eps ((E'-ext[k])/h_k)^p dx,  p = 0..3;  G is then the small dense
+// contraction  G(i,j) = sum_{k<=i} sum_p M[i,k,p] * C[j,k,p]  with C the per-segment polynomial
+// coefficients of basis j (hat functions or GSL-natural cardinal cubic splines).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "gl_tables.cuh"
+#include "kf_device.cuh"
+#include "problem.hpp"
+
+namespace isr {
+
+// =================================================================================================
+// Host: basis coefficient tables
+// =================================================================================================
+
+// Natural cubic spline second-derivative coefficients through (x_m, delta_{m,node}), m = 0..size-1,
+// by the symmetric-tridiagonal LDL^T recurrence (the algorithm GSL's gsl_interp_cspline uses, which
+// the reference instantiates once per cross-section point: src/CSplineRangeInterpolator.cpp:24-40).
+static void natural_spline_c(const std::vector<double>& x, int node, std::vector<double>& c) {
+  const int size = (int)x.size();
+  c.assign(size, 0.0);
+  const int m = size - 2;  // interior unknowns c[1..size-2]
+  if (m < 1) return;
+  std::vector<double> diag(m), off(m), rhs(m);
+  auto y = [node](int q) { return q == node ? 1.0 : 0.0; };
+  for (int q = 0; q < m; ++q) {
+    const double h0 = x[q + 1] - x[q], h1 = x[q + 2] - x[q + 1];
+    const double g0 = h0 != 0.0 ? 1.0 / h0 : 0.0, g1 = h1 != 0.0 ? 1.0 / h1 : 0.0;
+    off[q] = h1;
+    diag[q] = 2.0 * (h1 + h0);
+    rhs[q] = 3.0 * ((y(q + 2) - y(q + 1)) * g1 - (y(q + 1) - y(q)) * g0);
+  }
+  if (m == 1) {
+    c[1] = rhs[0] / diag[0];
+    return;
+  }
+  std::vector<double> alpha(m), gamma(m), z(m);
+  alpha[0] = diag[0];
+  gamma[0] = off[0] / alpha[0];
+  for (int q = 1; q < m - 1; ++q) {
+    alpha[q] = diag[q] - off[q - 1] * gamma[q - 1];
+    gamma[q] = off[q] / alpha[q];
+  }
+  alpha[m - 1] = diag[m - 1] - off[m - 2] * gamma[m - 2];
+  z[0] = rhs[0];
+  for (int q = 1; q < m; ++q) z[q] = rhs[q] - gamma[q - 1] * z[q - 1];
+  for (int q = 0; q < m; ++q) z[q] /= alpha[q];
+  c[m] = z[m - 1];
+  for (int q = m - 2; q >= 0; --q) c[q + 1] = z[q] - gamma[q] * c[q + 2];
+}
+
+// Validate + sort ranges exactly as Interpolator's constructor does (src/Interpolator.cpp:44-59,
+// checkRangeInterpSettings :90-147).
+static int normalise_ranges(int n, int nranges, const int* ranges, std::vector<int>& out) {
+  out.clear();
+  if (nranges <= 0) {  // defaultInterpRangeSettings, :356-360
+    out = {0, 0, n - 1};
+    return ISR_OK;
+  }
+  std::vector<int> idx(nranges);
+  for (int r = 0; r < nranges; ++r) idx[r] = r;
+  std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return ranges[3 * a + 1] < ranges[3 * b + 1]; });
+  if (ranges[3 * idx.front() + 1] != 0 || ranges[3 * idx.back() + 2] + 1 != n) {
+    set_error("[!] Wrong interpolation ranges: must start at segment 0 and end at segment n-1");
+    return ISR_ERANGE;
+  }
+  int pimax = -1;
+  for (int r : idx) {
+    const int imin = ranges[3 * r + 1], imax = ranges[3 * r + 2];
+    if (imin > imax || (pimax != -1 && pimax + 1 != imin)) {
+      set_error("[!] Wrong interpolation ranges: segments missed or taken twice");
+      return ISR_ERANGE;
+    }
+    pimax = imax;
+  }
+  for (int r : idx) {
+    out.push_back(ranges[3 * r] ? 1 : 0);
+    out.push_back(ranges[3 * r + 1]);
+    out.push_back(ranges[3 * r + 2]);
+  }
+  return ISR_OK;
+}
+
+int set_ranges(isr_problem* p, int nranges, const int* ranges) {
+  std::vector<int> sorted;
+  ISR_TRY(normalise_ranges(p->n, nranges, ranges, sorted));
+  p->ranges = sorted;
+  return build_basis_tables(p);
+}
+
+// Segment k = (ext[k], ext[k+1]] lies in exactly one range r (lo_r <= k <= hi_r).  That range decides
+// the polynomial piece of every basis function on the segment:
+//   linear range : rising edge of node j = k (delta/h), falling edge of node j = k-1 (1 - delta/h)
+//                  (src/LinearRangeInterpolator.cpp:25-39, 70-101 incl. the (min,max] guards :74-76, :92-94)
+//   cspline range: the cardinal natural spline of every node j in [max(lo-1,0), hi] -- hasCSIndex,
+//                  src/BaseRangeInterpolator.cpp:35-38, 80-100 -- restricted to the segment
+//                  (src/CSplineRangeInterpolator.cpp:88-110).
+int build_basis_tables(isr_problem* p) {
+  const int n = p->n;
+  const std::vector<double>& x = p->ext;
+  p->h_Ct.assign((size_t)n * 4 * n, 0.0);
+  p->h_klo.assign(n, n);
+  p->h_khi.assign(n, -1);
+  p->seg_range.assign(n, 0);
+  auto touch = [&](int j, int k) {
+    p->h_klo[j] = std::min(p->h_klo[j], k);
+    p->h_khi[j] = std::max(p->h_khi[j], k);
+  };
+  auto C = [&](int j, int k, int q) -> double& { return p->h_Ct[((size_t)k * 4 + q) * n + j]; };
+  const int R = (int)p->ranges.size() / 3;
+  std::vector<double> c;
+  for (int r = 0; r < R; ++r) {
+    const int cubic = p->ranges[3 * r], lo = p->ranges[3 * r + 1], hi = p->ranges[3 * r + 2];
+    for (int k = lo; k <= hi; ++k) p->seg_range[k] = r;
+    if (!cubic) {
+      for (int k = lo; k <= hi; ++k) {
+        C(k, k, 1) += 1.0;  // rising edge of node k
+        touch(k, k);
+        if (k >= 1) {       // falling edge of node k-1
+          C(k - 1, k, 0) += 1.0;
+          C(k - 1, k, 1) -= 1.0;
+          touch(k - 1, k);
+        }
+      }
+    } else {
+      const int jlo = lo > 0 ? lo - 1 : 0;
+      for (int j = jlo; j <= hi; ++j) {
+        natural_spline_c(x, j + 1, c);
+        for (int k = lo; k <= hi; ++k) {
+          const double h = x[k + 1] - x[k];
+          const double ylo = (k == j + 1) ? 1.0 : 0.0, yhi = (k + 1 == j + 1) ? 1.0 : 0.0;
+          const double bq = (yhi - ylo) / h - h * (c[k + 1] + 2.0 * c[k]) / 3.0;
+          const double dq = (c[k + 1] - c[k]) / (3.0 * h);
+          C(j, k, 0) += ylo;
+          C(j, k, 1) += bq * h;
+          C(j, k, 2) += c[k] * h * h;
+          C(j, k, 3) += dq * h * h * h;
+          touch(j, k);
+        }
+      }
+    }
+  }
+  std::vector<double> invh(n);
+  for (int k = 0; k < n; ++k) invh[k] = 1.0 / (x[k + 1] - x[k]);
+  cudaStream_t st = p->ctx->stream;
+  ISR_TRY(p->d_ext.reserve(n + 1));
+  ISR_TRY(p->d_invh.reserve(n));
+  ISR_TRY(p->d_Ct.reserve((size_t)n * 4 * n));
+  ISR_TRY(p->d_klo.reserve(n));
+  ISR_TRY(p->d_khi.reserve(n));
+  ISR_CUDA(cudaMemcpyAsync(p->d_ext.p, x.data(), sizeof(double) * (n + 1), cudaMemcpyHostToDevice, st));
+  ISR_CUDA(cudaMemcpyAsync(p->d_invh.p, invh.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  ISR_CUDA(cudaMemcpyAsync(p->d_Ct.p, p->h_Ct.data(), sizeof(double) * p->h_Ct.size(), cudaMemcpyHostToDevice, st));
+  ISR_CUDA(cudaMemcpyAsync(p->d_klo.p, p->h_klo.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+  ISR_CUDA(cudaMemcpyAsync(p->d_khi.p, p->h_khi.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+  ISR_CUDA(cudaStreamSynchronize(st));
+  p->has_G = false;
+  p->factored = false;
+  p->solver_selected = false;
+  p->tik_ready = false;
+  p->svd_ready = false;
+  return ISR_OK;
+}
+
+// =================================================================================================
+// Host: efficiency -> per-row device form
+// =================================================================================================
+
+// TAxis::FindBin on a non-extendable axis (ROOT): under/overflow aware; fixed or variable bins.
+static int host_find_bin(int nbins, double lo, double hi, const double* edges, double v) {
+  if (v < lo) return 0;
+  if (!(v < hi)) return nbins + 1;
+  if (!edges) return 1 + (int)(nbins * (v - lo) / (hi - lo));
+  int l = 0, h = nbins;
+  while (h - l > 1) {
+    const int m = (l + h) / 2;
+    if (edges[m] <= v) l = m; else h = m;
+  }
+  return 1 + l;
+}
+
+int upload_eps(isr_problem* p, const isr_eps_desc* e) {
+  const int n = p->n;
+  cudaStream_t st = p->ctx->stream;
+  p->eps = EpsDev{};
+  if (!e || e->kind == ISR_EPS_ONE) return ISR_OK;
+  if (e->kind < 0 || e->kind > ISR_EPS_E_ONLY) {
+    set_error("[!] Wrong efficiency dimension.");   // EfficiencyDimensionException
+    return ISR_EEFFDIM;
+  }
+  if (!e->values) { set_error("efficiency values == NULL"); return ISR_EINVAL; }
+  double elo = e->elo, ehi = e->ehi, xlo = e->xlo, xhi = e->xhi;
+  if (e->eedges) { elo = e->eedges[0]; ehi = e->eedges[e->ne]; }
+  if (e->xedges) { xlo = e->xedges[0]; xhi = e->xedges[e->nx]; }
+  if (e->kind == ISR_EPS_E_ONLY) {
+    // TEfficiency 1-D: efficiency(x, E) = eff[FindFixBin(E)] (src/BaseISRSolver.cpp:236-241)
+    if (e->ne < 1) { set_error("efficiency: ne < 1"); return ISR_EINVAL; }
+    std::vector<double> scale(n);
+    for (int i = 0; i < n; ++i) scale[i] = e->values[host_find_bin(e->ne, elo, ehi, e->eedges, p->ext[i + 1])];
+    ISR_TRY(p->d_eps_vals.reserve(n));
+    ISR_CUDA(cudaMemcpyAsync(p->d_eps_vals.p, scale.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    ISR_CUDA(cudaStreamSynchronize(st));
+    p->eps.kind = 1;
+    p->eps.values = p->d_eps_vals.p;
+    return ISR_OK;
+  }
+  if (e->nx < 1 || !(xhi > xlo)) { set_error("efficiency: bad x axis"); return ISR_EINVAL; }
+  const int w = e->nx + 2;
+  std::vector<double> vals((size_t)n * w);
+  if (e->kind == ISR_EPS_ROW_TABLE) {
+    // v2: eff(x, index) = hist[index]->GetBinContent(FindBin(x)) (src/BaseISRSolver2.cpp:231-236)
+    std::memcpy(vals.data(), e->values, sizeof(double) * vals.size());
+  } else {
+    // TEfficiency 2-D: global bin = bx + (nx+2)*by (src/BaseISRSolver.cpp:243-250)
+    if (e->ne < 1) { set_error("efficiency: ne < 1"); return ISR_EINVAL; }
+    for (int i = 0; i < n; ++i) {
+      const int by = host_find_bin(e->ne, elo, ehi, e->eedges, p->ext[i + 1]);
+      std::memcpy(&vals[(size_t)i * w], &e->values[(size_t)by * w], sizeof(double) * w);
+    }
+  }
+  ISR_TRY(p->d_eps_vals.reserve(vals.size()));
+  ISR_CUDA(cudaMemcpyAsync(p->d_eps_vals.p, vals.data(), sizeof(double) * vals.size(), cudaMemcpyHostToDevice, st));
+  p->eps.kind = 2;
+  p->eps.nx = e->nx;
+  p->eps.xlo = xlo;
+  p->eps.xhi = xhi;
+  p->eps.values = p->d_eps_vals.p;
+  p->eps.xedges = nullptr;
+  if (e->xedges) {
+    ISR_TRY(p->d_eps_edges.reserve(e->nx + 1));
+    ISR_CUDA(cudaMemcpyAsync(p->d_eps_edges.p, e->xedges, sizeof(double) * (e->nx + 1), cudaMemcpyHostToDevice, st));
+    p->eps.xedges = p->d_eps_edges.p;
+  }
+  ISR_CUDA(cudaStreamSynchronize(st));
+  return ISR_OK;
+}
+
+// =================================================================================================
+// Device: panel enumeration
+// =================================================================================================
+
+__global__ void row_setup_kernel(int n, const double* __restrict__ ext, RowConst* __restrict__ rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  RowConst rc;
+  row_const_init(rc, ext[i + 1], ext[0]);
+  // grading points: x0, x0 (1 + 4^m) for m = -2, -1, 0, 1, ... (ratio <= 4 to both singular points
+  // 0 and x0), then 1 - (1 - xmax) 4^m towards the pole of the pair term at x = 1.
+  int nb = 0;
+  rc.rb[nb++] = rc.x0;
+  double f = 1.0 / 16.0;
+  while (nb < kMaxRowBreaks - 6) {
+    const double v = rc.x0 * (1.0 + f);
+    if (!(v < rc.xmax)) break;
+    rc.rb[nb++] = v;
+    f *= 4.0;
+  }
+  const double d = 1.0 - rc.xmax;
+  double g = 4.0;
+  double tmp[6];
+  int nt = 0;
+  while (nt < 6) {
+    const double v = 1.0 - d * g;
+    if (!(v > 0.25) || !(v > rc.rb[nb - 1])) break;
+    tmp[nt++] = v;
+    g *= 4.0;
+  }
+  // tmp is descending; merge so rb stays ascending
+  for (int q = nt - 1; q >= 0; --q) rc.rb[nb++] = tmp[q];
+  // insertion sort (the two families can interleave)
+  for (int a = 1; a < nb; ++a) {
+    const double v = rc.rb[a];
+    int b = a - 1;
+    while (b >= 0 && rc.rb[b] > v) { rc.rb[b + 1] = rc.rb[b]; --b; }
+    rc.rb[b + 1] = v;
+  }
+  rc.nrb = nb;
+  rows[i] = rc;
+}
+
+// x-coordinate of energy node m seen from row i: x = 1 - (ext[m]/E_i)^2, exactly 0 at m = i+1.
+__device__ __forceinline__ double knot_x(const double* __restrict__ ext, double E, int i, int m) {
+  if (m == i + 1) return 0.0;
+  const double r = ext[m] / E;
+  return fmax(0.0, 1.0 - r * r);
+}
+
+// ROOT TAxis::FindBin arithmetic (bit-exact: no FMA contraction in the index expression).
+__device__ __forceinline__ int eps_find_bin(const EpsDev& e, double x) {
+  if (x < e.xlo) return 0;
+  if (!(x < e.xhi)) return e.nx + 1;
+  if (!e.xedges) {
+    const double t = __ddiv_rn(__dmul_rn((double)e.nx, __dsub_rn(x, e.xlo)), __dsub_rn(e.xhi, e.xlo));
+    return 1 + (int)t;
+  }
+  int l = 0, h = e.nx;
+  while (h - l > 1) {
+    const int m = (l + h) >> 1;
+    if (e.xedges[m] <= x) l = m; else h = m;
+  }
+  return 1 + l;
+}
+__device__ __forceinline__ double eps_edge(const EpsDev& e, int m) {
+  if (e.xedges) return e.xedges[m];
+  if (m == e.nx) return e.xhi;
+  return e.xlo + (double)m * ((e.xhi - e.xlo) / (double)e.nx);
+}
+// smallest edge index m in [0, nx] with edge(m) > v, or nx+1
+__device__ __forceinline__ int eps_first_edge_above(const EpsDev& e, double v) {
+  int m;
+  if (e.xedges) {
+    int l = -1, h = e.nx + 1;  // edge(l) <= v < edge(h)
+    while (h - l > 1) {
+      const int q = (l + h) >> 1;
+      if (e.xedges[q] <= v) l = q; else h = q;
+    }
+    return h;
+  }
+  const double w = (e.xhi - e.xlo) / (double)e.nx;
+  const double t = floor((v - e.xlo) / w) + 1.0;
+  m = t < 0.0 ? 0 : (t > (double)(e.nx + 1) ? e.nx + 1 : (int)t);
+  while (m > 0 && eps_edge(e, m - 1) > v) --m;
+  while (m <= e.nx && !(eps_edge(e, m) > v)) ++m;
+  return m;
+}
+
+// Walk the panels of item (row i, segment k).  Emit(a, b) is called for every panel in ascending x.
+template <typename Emit>
+__device__ __forceinline__ int walk_item(const RowConst& rc, const EpsDev& eps, const double* __restrict__ ext,
+                                         int i, int k, Emit emit) {
+  const double xa = knot_x(ext, rc.E, i, k + 1);
+  const double xb = knot_x(ext, rc.E, i, k);
+  int count = 0;
+  if (!(xb > xa)) return 0;
+  int ir = 0;
+  while (ir < rc.nrb && !(rc.rb[ir] > xa)) ++ir;
+  int ie = 0x7fffffff;
+  if (eps.kind == 2) ie = eps_first_edge_above(eps, xa);
+  double cur = xa;
+  for (;;) {
+    const double nr = ir < rc.nrb ? rc.rb[ir] : 2.0;
+    const double ne = (eps.kind == 2 && ie <= eps.nx) ? eps_edge(eps, ie) : 2.0;
+    const double nxt = fmin(nr, ne);
+    if (!(nxt < xb)) {
+      emit(cur, xb);
+      ++count;
+      break;
+    }
+    emit(cur, nxt);
+    ++count;
+    cur = nxt;
+    if (nr <= nxt) ++ir;
+    if (ne <= nxt) ++ie;
+  }
+  return count;
+}
+
+__device__ __forceinline__ void item_decode(int idx, int& i, int& k) {
+  int r = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
+  while ((long long)(r + 1) * (r + 2) / 2 <= idx) ++r;
+  while ((long long)r * (r + 1) / 2 > idx) --r;
+  i = r;
+  k = idx - r * (r + 1) / 2;
+}
+
+__global__ void count_kernel(int nitems, const RowConst* __restrict__ rows, EpsDev eps,
+                             const double* __restrict__ ext, int* __restrict__ cnt) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nitems) return;
+  int i, k;
+  item_decode(idx, i, k);
+  cnt[idx] = walk_item(rows[i], eps, ext, i, k, [](double, double) {});
+}
+
+// Single-block exclusive scan of cnt[0..n) into off[0..n], off[n] = total.
+__global__ void __launch_bounds__(1024) scan_kernel(int n, const int* __restrict__ cnt, int* __restrict__ off) {
+  __shared__ int part[1024];
+  const int t = threadIdx.x;
+  const int chunk = (n + 1023) / 1024;
+  const int b = t * chunk, e = min(n, b + chunk);
+  int s = 0;
+  for (int q = b; q < e; ++q) s += cnt[q];
+  part[t] = s;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {
+    int v = 0;
+    if (t >= d) v = part[t - d];
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  int run = t ? part[t - 1] : 0;
+  for (int q = b; q < e; ++q) {
+    off[q] = run;
+    run += cnt[q];
+  }
+  if (t == 1023) off[n] = part[1023];
+}
+
+// kind: 0 = regular (x), 1 = t = x^beta, 2 = u = (x - x0)^beta
+__global__ void fill_kernel(int nitems, const RowConst* __restrict__ rows, EpsDev eps,
+                            const double* __restrict__ ext, const int* __restrict__ off,
+                            double* __restrict__ pa, double* __restrict__ pb, double* __restrict__ peps,
+                            int* __restrict__ pitem, int* __restrict__ pkind) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nitems) return;
+  int i, k;
+  item_decode(idx, i, k);
+  const RowConst& rc = rows[i];
+  int o = off[idx];
+  double scale = 1.0;
+  if (eps.kind == 1) scale = eps.values[i];
+  walk_item(rc, eps, ext, i, k, [&](double a, double b) {
+    double ev = scale;
+    if (eps.kind == 2) ev = eps.values[(size_t)i * (eps.nx + 2) + eps_find_bin(eps, 0.5 * (a + b))];
+    int kind = 0;
+    if (!(b > rc.x0)) kind = 1;
+    else if (!(b > rc.xin)) kind = 2;
+    pa[o] = a;
+    pb[o] = b;
+    peps[o] = ev;
+    pitem[o] = idx;
+    pkind[o] = kind;
+    ++o;
+  });
+}
+
+// =================================================================================================
+// Device: panel evaluation (the hot kernel of the assembly)
+// =================================================================================================
+// One 16-lane group per panel, lane = Gauss-Legendre node; four moments reduced with warp shuffles.
+constexpr int kQ = 16;
+constexpr int kEvalThreads = 256;
+
+__global__ void __launch_bounds__(kEvalThreads)
+eval_kernel(const int* __restrict__ off_total, const RowConst* __restrict__ rows,
+            const double* __restrict__ ext, const double* __restrict__ invh,
+            const double* __restrict__ pa, const double* __restrict__ pb, const double* __restrict__ peps,
+            const int* __restrict__ pitem, const int* __restrict__ pkind, double* __restrict__ pm) {
+  __shared__ double s_x[kQ], s_w[kQ];
+  if (threadIdx.x < kQ) {
+    s_x[threadIdx.x] = kGL16_x[threadIdx.x];
+    s_w[threadIdx.x] = kGL16_w[threadIdx.x];
+  }
+  __syncthreads();
+  const int npanels = *off_total;
+  const int lane = threadIdx.x & (kQ - 1);
+  const int groups_per_block = kEvalThreads / kQ;
+  const int group = blockIdx.x * groups_per_block + (threadIdx.x / kQ);
+  const int ngroups = gridDim.x * groups_per_block;
+  const double t = s_x[lane], w = s_w[lane];
+  for (int pidx = group; pidx < npanels; pidx += ngroups) {
+    const double a = pa[pidx], b = pb[pidx], ev = peps[pidx];
+    const int item = pitem[pidx], kind = pkind[pidx];
+    int i, k;
+    item_decode(item, i, k);
+    const RowConst& rc = rows[i];
+    double x, lnx, wj, pw = -1.0;
+    if (kind == 0) {
+      const double half = 0.5 * (b - a);
+      x = fma(half, t, 0.5 * (a + b));
+      wj = half * w;
+      lnx = log(x);
+      pw = exp(rc.beta * log(x - rc.x0));
+    } else if (kind == 1) {
+      const double ta = a > 0.0 ? exp(rc.beta * log(a)) : 0.0;
+      const double tb = exp(rc.beta * log(b));
+      const double half = 0.5 * (tb - ta);
+      const double tt = fma(half, t, 0.5 * (ta + tb));
+      lnx = log(tt) * rc.inv_beta;
+      x = exp(lnx);
+      wj = half * w * rc.inv_beta * x / tt;
+    } else {
+      const double ya = a - rc.x0, yb = b - rc.x0;
+      const double ua = ya > 0.0 ? exp(rc.beta * log(ya)) : 0.0;
+      const double ub = exp(rc.beta * log(yb));
+      const double half = 0.5 * (ub - ua);
+      const double u = fma(half, t, 0.5 * (ua + ub));
+      const double y = exp(log(u) * rc.inv_beta);
+      x = rc.x0 + y;
+      lnx = log(x);
+      wj = half * w * rc.inv_beta * y / u;
+      pw = u;
+    }
+    const double f = kf_value(rc, x, lnx, pw) * wj * ev;
+    const double dn = (rc.E * sqrt(1.0 - x) - ext[k]) * invh[k];
+    double m0 = f, m1 = f * dn, m2 = m1 * dn, m3 = m2 * dn;
+#pragma unroll
+    for (int sft = kQ / 2; sft >= 1; sft >>= 1) {
+      m0 += __shfl_xor_sync(0xffffffffu, m0, sft);
+      m1 += __shfl_xor_sync(0xffffffffu, m1, sft);
+      m2 += __shfl_xor_sync(0xffffffffu, m2, sft);
+      m3 += __shfl_xor_sync(0xffffffffu, m3, sft);
+    }
+    if (lane == 0) {
+      double4 v = make_double4(m0, m1, m2, m3);
+      reinterpret_cast<double4*>(pm)[pidx] = v;
+    }
+  }
+}
+
+// Sum the panels of each item in panel order (deterministic) into M[i][k][0..3]; zero for k > i.
+__global__ void reduce_kernel(int n, const int* __restrict__ off, const double* __restrict__ pm,
+                              double* __restrict__ M) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over n*n (i,k)
+  if (idx >= n * n) return;
+  const int i = idx / n, k = idx % n;
+  double4 acc = make_double4(0, 0, 0, 0);
+  if (k <= i) {
+    const int item = i * (i + 1) / 2 + k;
+    for (int q = off[item]; q < off[item + 1]; ++q) {
+      const double4 v = reinterpret_cast<const double4*>(pm)[q];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  reinterpret_cast<double4*>(M)[idx] = acc;
+}
+
+// G(i,j) = sum_{k = klo_j}^{min(khi_j, i)} sum_p M[i][k][p] * Ct[k][p][j]   (column-major output).
+// Tile: 16 rows x 64 columns per block; M rows staged through shared memory in chunks of 32 segments.
+constexpr int kCtRows = 16, kCtCols = 64, kCtK = 32;
+__global__ void __launch_bounds__(256)
+contract_kernel(int n, const double* __restrict__ M, const double* __restrict__ Ct,
+                const int* __restrict__ klo, const int* __restrict__ khi, double* __restrict__ G) {
+  __shared__ double sM[kCtRows][kCtK * 4];
+  const int j = blockIdx.x * kCtCols + (threadIdx.x & (kCtCols - 1));
+  const int rsub = threadIdx.x / kCtCols;  // 0..3, each thread does 4 rows
+  const int i0 = blockIdx.y * kCtRows;
+  const int imax = min(n - 1, i0 + kCtRows - 1);
+  const int jl = j < n ? klo[j] : n, jh = j < n ? khi[j] : -1;
+  // block-wide segment range
+  __shared__ int s_lo, s_hi;
+  if (threadIdx.x == 0) { s_lo = n; s_hi = -1; }
+  __syncthreads();
+  if (j < n) { atomicMin(&s_lo, jl); atomicMax(&s_hi, jh); }
+  __syncthreads();
+  const int blo = s_lo, bhi = min(s_hi, imax);
+  double acc[4] = {0, 0, 0, 0};
+  for (int k0 = blo; k0 <= bhi; k0 += kCtK) {
+    __syncthreads();
+    for (int q = threadIdx.x; q < kCtRows * kCtK * 4; q += 256) {
+      const int r = q / (kCtK * 4), c = q % (kCtK * 4);
+      const int i = i0 + r, k = k0 + c / 4;
+      sM[r][c] = (i < n && k < n) ? M[((size_t)i * n + k) * 4 + (c & 3)] : 0.0;
+    }
+    __syncthreads();
+    if (j < n) {
+      const int ke = min(k0 + kCtK - 1, min(jh, bhi));
+      for (int k = max(k0, jl); k <= ke; ++k) {
+        const double c0 = Ct[((size_t)k * 4 + 0) * n + j], c1 = Ct[((size_t)k * 4 + 1) * n + j];
+        const double c2 = Ct[((size_t)k * 4 + 2) * n + j], c3 = Ct[((size_t)k * 4 + 3) * n + j];
+        const int c = (k - k0) * 4;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const double* m = &sM[rsub * 4 + r][c];   // M is zero for k > i
+          acc[r] = fma(m[0], c0, fma(m[1], c1, fma(m[2], c2, fma(m[3], c3, acc[r]))));
+        }
+      }
+    }
+  }
+  if (j < n) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = i0 + rsub * 4 + r;
+      if (i < n) G[(size_t)i + (size_t)n * j] = acc[r];
+    }
+  }
+}
+
+// =================================================================================================
+// Device: energy spread  G <- G_spread * G   (src/ISRSolverSLE.cpp:146-148, 177-193)
+// =================================================================================================
+// Segment lookup: k with ext[k] < E <= ext[k+1] (the (min, max] convention of
+// BaseRangeInterpolator::isEnergyInRange, src/BaseRangeInterpolator.cpp:45-47).
+__device__ __forceinline__ int segment_of(const double* __restrict__ ext, int n, double e) {
+  int l = 0, h = n;  // ext[l] < e <= ext[h]
+  while (h - l > 1) {
+    const int m = (l + h) >> 1;
+    if (ext[m] < e) l = m; else h = m;
+  }
+  return l;
+}
+// Interpolator::basisEval (src/Interpolator.cpp:217-258) / basisDerivEval (:266-287) from the tables.
+__device__ double basis_eval_dev(int n, const double* __restrict__ ext, const double* __restrict__ invh,
+                                 const double* __restrict__ Ct, int j, double e, int deriv) {
+  if (e <= ext[0]) return 0.0;
+  if (e > ext[n]) {
+    if (deriv) return 0.0;
+    return j == n - 1 ? 1.0 : 0.0;  // value at E_max of the last range's basis: delta_{j, n-1}
+  }
+  const int k = segment_of(ext, n, e);
+  const double dn = (e - ext[k]) * invh[k];
+  const double c0 = Ct[((size_t)k * 4 + 0) * n + j], c1 = Ct[((size_t)k * 4 + 1) * n + j];
+  const double c2 = Ct[((size_t)k * 4 + 2) * n + j], c3 = Ct[((size_t)k * 4 + 3) * n + j];
+  if (deriv) return (c1 + dn * (2.0 * c2 + 3.0 * c3 * dn)) * invh[k];
+  return c0 + dn * (c1 + dn * (c2 + dn * c3));
+}
+
+// S(i,j) = sum_m (w_m/sqrt(pi)) * basis_j(E_i + sqrt(2) sigma_i t_m): 6-point Gauss-Hermite
+// (gaussian_conv, src/Integration.cpp:86-100).  Column-major output.
+__global__ void spread_kernel(int n, const double* __restrict__ ext, const double* __restrict__ invh,
+                              const double* __restrict__ Ct, const double* __restrict__ sigE,
+                              double* __restrict__ S) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * n) return;
+  const int j = idx % n, i = idx / n;
+  const double e0 = ext[i + 1], sg = sigE[i] * 1.4142135623730951;
+  double acc = 0.0;
+#pragma unroll
+  for (int m = 0; m < 6; ++m)
+    acc += kGH6_w_over_sqrtpi[m] * basis_eval_dev(n, ext, invh, Ct, j, e0 + sg * kGH6_t[m], 0);
+  S[(size_t)i + (size_t)n * j] = acc;
+}
+
+// C = A * B, all n x n column-major, FP64; 32x32 tiles.  Used for the one-off spread product.
+__global__ void __launch_bounds__(256) gemm_nn_kernel(int n, const double* __restrict__ A,
+                                                       const double* __restrict__ B, double* __restrict__ C) {
+  __shared__ double sA[32][33], sB[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // ty 0..7, 4 rows each
+  const int row0 = blockIdx.y * 32, col0 = blockIdx.x * 32;
+  double acc[4] = {0, 0, 0, 0};
+  for (int k0 = 0; k0 < n; k0 += 32) {
+    for (int q = ty; q < 32; q += 8) {
+      const int ar = row0 + tx, ac = k0 + q;
+      sA[q][tx] = (ar < n && ac < n) ? A[(size_t)ar + (size_t)n * ac] : 0.0;   // sA[k][row]
+      const int br = k0 + tx, bc = col0 + q;
+      sB[q][tx] = (br < n && bc < n) ? B[(size_t)br + (size_t)n * bc] : 0.0;   // sB[col][k]
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      const double a = sA[k][tx];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r] = fma(a, sB[ty * 4 + r][k], acc[r]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int row = row0 + tx, col = col0 + ty * 4 + r;
+    if (row < n && col < n) C[(size_t)row + (size_t)n * col] = acc[r];
+  }
+}
+
+// =================================================================================================
+// Host driver
+// =================================================================================================
+static int64_t panel_upper_bound(const isr_problem* p) {
+  const int64_t n = p->n;
+  int64_t per_row_extra = kMaxRowBreaks + 2;
+  if (p->eps.kind == 2) per_row_extra += p->eps.nx + 2;
+  return n * (n + 1) / 2 + n * per_row_extra;
+}
+
+int assemble(isr_problem* p, const double* ecm_err) {
+  const int n = p->n;
+  cudaStream_t st = p->ctx->stream;
+  const int nitems = n * (n + 1) / 2;
+  const int64_t cap = panel_upper_bound(p);
+  if (cap > p->max_panels || !p->d_pa.p) {
+    ISR_TRY(p->d_pa.reserve(cap));
+    ISR_TRY(p->d_pb.reserve(cap));
+    ISR_TRY(p->d_peps.reserve(cap));
+    ISR_TRY(p->d_pitem.reserve(cap));
+    ISR_TRY(p->d_pkind.reserve(cap));
+    ISR_TRY(p->d_pm.reserve(cap * 4));
+    p->max_panels = cap;
+  }
+  ISR_TRY(p->d_row.reserve(n));
+  ISR_TRY(p->d_cnt.reserve(nitems));
+  ISR_TRY(p->d_off.reserve(nitems + 1));
+  ISR_TRY(p->d_M.reserve((size_t)n * n * 4));
+  ISR_TRY(p->d_G.reserve((size_t)n * n));
+
+  row_setup_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, p->d_ext.p, p->d_row.p);
+  count_kernel<<<(nitems + 127) / 128, 128, 0, st>>>(nitems, p->d_row.p, p->eps, p->d_ext.p, p->d_cnt.p);
+  scan_kernel<<<1, 1024, 0, st>>>(nitems, p->d_cnt.p, p->d_off.p);
+  fill_kernel<<<(nitems + 127) / 128, 128, 0, st>>>(nitems, p->d_row.p, p->eps, p->d_ext.p, p->d_off.p,
+                                                      p->d_pa.p, p->d_pb.p, p->d_peps.p, p->d_pitem.p, p->d_pkind.p);
+  const int eval_blocks = p->ctx->sm_count * 8;
+  eval_kernel<<<eval_blocks, kEvalThreads, 0, st>>>(p->d_off.p + nitems, p->d_row.p, p->d_ext.p, p->d_invh.p,
+                                                     p->d_pa.p, p->d_pb.p, p->d_peps.p, p->d_pitem.p,
+                                                     p->d_pkind.p, p->d_pm.p);
+  reduce_kernel<<<(n * n + 127) / 128, 128, 0, st>>>(n, p->d_off.p, p->d_pm.p, p->d_M.p);
+  dim3 cgrid((n + kCtCols - 1) / kCtCols, (n + kCtRows - 1) / kCtRows);
+  contract_kernel<<<cgrid, 256, 0, st>>>(n, p->d_M.p, p->d_Ct.p, p->d_klo.p, p->d_khi.p, p->d_G.p);
+  if (ecm_err) {
+    for (int i = 0; i < n; ++i)
+      if (!(ecm_err[i] > 0.0)) {
+        set_error("energy spread enabled but ecm_err[%d] = %g is not positive (src/Integration.cpp:89 divides by it)", i, ecm_err[i]);
+        return ISR_EINVAL;
+      }
+    ISR_TRY(p->d_sigE.reserve(n));
+    ISR_TRY(p->d_S.reserve((size_t)n * n));
+    ISR_TRY(p->d_tmp.reserve((size_t)n * n));
+    ISR_CUDA(cudaMemcpyAsync(p->d_sigE.p, ecm_err, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    spread_kernel<<<(n * n + 127) / 128, 128, 0, st>>>(n, p->d_ext.p, p->d_invh.p, p->d_Ct.p, p->d_sigE.p, p->d_S.p);
+    dim3 g((n + 31) / 32, (n + 31) / 32);
+    gemm_nn_kernel<<<g, 256, 0, st>>>(n, p->d_S.p, p->d_G.p, p->d_tmp.p);
+    ISR_CUDA(cudaMemcpyAsync(p->d_G.p, p->d_tmp.p, sizeof(double) * n * n, cudaMemcpyDeviceToDevice, st));
+  }
+  ISR_CUDA(cudaGetLastError());
+  p->has_G = true;
+  p->factored = false;
+  p->solver_selected = false;
+  p->tik_ready = false;
+  p->svd_ready = false;
+  p->last_panels = -1;  // fetched lazily by isr_assemble_stats
+  return ISR_OK;
+}
+
+// ---- device helpers exported to capi.cu ---------------------------------------------------------
+__global__ void kf_plain_kernel(int64_t n, const double* __restrict__ x, const double* __restrict__ s,
+                                double* __restrict__ out) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) out[q] = kf_plain(x[q], s[q]);
+}
+void launch_kf_plain(int64_t n, const double* x, const double* s, double* out, cudaStream_t st) {
+  kf_plain_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, x, s, out);
+}
+
+__global__ void basis_eval_kernel(int n, const double* __restrict__ ext, const double* __restrict__ invh,
+                                  const double* __restrict__ Ct, int64_t m, const int* __restrict__ js,
+                                  const double* __restrict__ es, int deriv, double* __restrict__ out) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < m) out[q] = basis_eval_dev(n, ext, invh, Ct, js[q], es[q], deriv);
+}
+void launch_basis_eval(const isr_problem* p, int64_t m, const int* js, const double* es, int deriv, double* out) {
+  basis_eval_kernel<<<(unsigned)((m + 255) / 256), 256, 0, p->ctx->stream>>>(p->n, p->d_ext.p, p->d_invh.p,
+                                                                             p->d_Ct.p, m, js, es, deriv, out);
+}
+
+}  // namespace isr

@@ -1,0 +1,111 @@
+// Shared declarations for libisr_b200.so (host + device).  sm_100a only, FP64 throughout.
+#pragma once
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include <cublas_v2.h>
+#include <cuda_runtime.h>
+#include <cusolverDn.h>
+
+#include "../../include/isr_b200.h"
+
+namespace isr {
+
+// ---- error plumbing: no exceptions cross the C ABI ---------------------------------------------
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define ISR_CUDA(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t e__ = (expr);                                                                \
+    if (e__ != cudaSuccess) {                                                                \
+      isr::set_error("CUDA error '%s' at %s:%d (%s)", cudaGetErrorString(e__), __FILE__,     \
+                     __LINE__, #expr);                                                       \
+      return ISR_ECUDA;                                                                      \
+    }                                                                                        \
+  } while (0)
+
+#define ISR_CUSOLVER(expr)                                                                   \
+  do {                                                                                       \
+    cusolverStatus_t s__ = (expr);                                                           \
+    if (s__ != CUSOLVER_STATUS_SUCCESS) {                                                    \
+      isr::set_error("cuSOLVER status %d at %s:%d (%s)", (int)s__, __FILE__, __LINE__, #expr); \
+      return ISR_ECUDA;                                                                      \
+    }                                                                                        \
+  } while (0)
+
+#define ISR_CUBLAS(expr)                                                                     \
+  do {                                                                                       \
+    cublasStatus_t s__ = (expr);                                                             \
+    if (s__ != CUBLAS_STATUS_SUCCESS) {                                                      \
+      isr::set_error("cuBLAS status %d at %s:%d (%s)", (int)s__, __FILE__, __LINE__, #expr); \
+      return ISR_ECUDA;                                                                      \
+    }                                                                                        \
+  } while (0)
+
+#define ISR_TRY(expr)              \
+  do {                             \
+    int rc__ = (expr);             \
+    if (rc__ != ISR_OK) return rc__; \
+  } while (0)
+
+// ---- physical constants (include/PhysicalConstants.hpp:7,11) -------------------------------------
+constexpr double kAlphaQED = 7.2973525698e-03;
+constexpr double kElectronM = 5.10998928e-04;
+constexpr double kPi = 3.14159265358979323846;
+
+// ---- device buffer with RAII (host side only) ----------------------------------------------------
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  // grow-only allocation
+  int reserve(size_t count) {
+    if (count <= n && p) return ISR_OK;
+    release();
+    if (count == 0) count = 1;
+    ISR_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    n = count;
+    return ISR_OK;
+  }
+};
+
+constexpr int kMaxRowBreaks = 24;
+
+// Per-row constants of the Kuraev-Fadin kernel and the row's quadrature grading points.
+struct RowConst {
+  double E, s, L, beta, inv_beta, C1, x0, xin, xmax;
+  int nrb;
+  double rb[kMaxRowBreaks];  // ascending: x0, x0(1+4^m), 1-(1-xmax)4^m
+};
+
+// Efficiency in the per-row form the device consumes.
+struct EpsDev {
+  int kind;             // 0: none, 1: per-row scale only, 2: per-row x table
+  int nx;
+  double xlo, xhi;
+  const double* xedges; // device, nx+1 entries, or nullptr for fixed-width bins
+  const double* values; // device: kind 1: [N]; kind 2: [N][nx+2]
+};
+
+}  // namespace isr
+
+struct isr_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cusolverDnHandle_t solver = nullptr;
+  cublasHandle_t blas = nullptr;
+};

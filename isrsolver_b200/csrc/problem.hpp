@@ -1,0 +1,71 @@
+// isr_problem: one solver instance (host mirror + device residency).
+#pragma once
+
+#include "common.cuh"
+
+struct isr_problem {
+  isr_ctx* ctx = nullptr;
+  int n = 0;
+  double threshold = 0;
+  std::vector<double> ext;   // n+1: threshold, E_0..E_{n-1}        (src/Interpolator.cpp:37-39)
+  std::vector<int> ranges;   // sorted by first segment, R x {cubic, lo, hi}
+  std::vector<int> seg_range;  // per segment k: index of the range that contains it
+
+  // ---- basis tables --------------------------------------------------------------------------
+  // Ct[(k*4 + p)*n + j]: coefficient of (delta/h_k)^p of basis j on segment k = (ext[k], ext[k+1]].
+  std::vector<double> h_Ct;
+  std::vector<int> h_klo, h_khi;  // per column j: first/last segment with non-zero coefficients
+  isr::DevBuf<double> d_ext, d_invh, d_Ct;
+  isr::DevBuf<int> d_klo, d_khi;
+
+  // ---- efficiency ----------------------------------------------------------------------------
+  isr::EpsDev eps{};
+  isr::DevBuf<double> d_eps_vals, d_eps_edges;
+
+  // ---- assembly workspaces -------------------------------------------------------------------
+  isr::DevBuf<isr::RowConst> d_row;
+  isr::DevBuf<int> d_cnt;        // panels per (row, segment) item, then exclusive scan (+1 entry)
+  isr::DevBuf<int> d_off;
+  isr::DevBuf<double> d_pa, d_pb, d_peps, d_pm;  // panel bounds, eps value, 4 moments per panel
+  isr::DevBuf<int> d_pitem, d_pkind;
+  isr::DevBuf<double> d_M;       // [i][k][4] normalised moments
+  isr::DevBuf<double> d_G;       // column-major N x N
+  isr::DevBuf<double> d_S, d_tmp, d_sigE;
+  int64_t max_panels = 0;
+  int64_t last_panels = 0;
+  bool has_G = false;
+
+  // ---- factorisation / selected solver -------------------------------------------------------
+  // All N x N, ROW-major on the device: Sop (solve operator: b = Sop v) and Rop (chi2 factor:
+  // chi2 = |Rop (b - b0)|^2).
+  isr::DevBuf<double> d_Ginv, d_R, d_Cov, d_InvCov, d_Sop, d_Rop, d_werr;
+  isr::DevBuf<double> d_work;
+  isr::DevBuf<int> d_ipiv, d_info;
+  std::vector<double> vcs_err;
+  bool factored = false;
+  bool solver_selected = false;
+  int toy_variant = 0;
+
+  // ---- toy batch workspaces ------------------------------------------------------------------
+  isr::DevBuf<double> d_V, d_chi2, d_acc, d_b0, d_B;
+  isr::DevBuf<uint32_t> d_rhist;
+
+  // ---- Tikhonov ------------------------------------------------------------------------------
+  bool tik_ready = false;
+  int tik_deriv = 1;
+  isr::DevBuf<double> d_F, d_U, d_mu, d_UtGtW, d_FU, d_lam, d_scan;
+  std::vector<double> h_F, h_U, h_mu, h_UtGtW;  // host mirrors (column-major)
+
+  // ---- SVD -----------------------------------------------------------------------------------
+  bool svd_ready = false;
+  std::vector<double> h_svU, h_svV, h_sv;  // column-major U, V; singular values descending
+};
+
+namespace isr {
+int build_basis_tables(isr_problem* p);
+int set_ranges(isr_problem* p, int nranges, const int* ranges);
+void launch_kf_plain(int64_t n, const double* x, const double* s, double* out, cudaStream_t st);
+void launch_basis_eval(const isr_problem* p, int64_t m, const int* js, const double* es, int deriv, double* out);
+int upload_eps(isr_problem* p, const isr_eps_desc* eps);
+int assemble(isr_problem* p, const double* ecm_err);
+}  // namespace isr
