@@ -744,4 +744,26 @@ void launch_basis_eval(const isr_problem* p, int64_t m, const int* js, const dou
                                                                              p->d_Ct.p, m, js, es, deriv, out);
 }
 
+// Interpolator::eval (src/Interpolator.cpp:295-323): sum_j y_j basis_j(E); the value at E_max beyond it.
+__global__ void interp_eval_kernel(int n, const double* __restrict__ ext, const double* __restrict__ invh,
+                                   const double* __restrict__ Ct, const double* __restrict__ y, int64_t m,
+                                   const double* __restrict__ es, double* __restrict__ out) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= m) return;
+  const double e = es[q];
+  double acc = 0.0;
+  if (e > ext[0]) {
+    if (e > ext[n]) {
+      acc = y[n - 1];
+    } else {
+      for (int j = 0; j < n; ++j) acc += y[j] * basis_eval_dev(n, ext, invh, Ct, j, e, 0);
+    }
+  }
+  out[q] = acc;
+}
+void launch_interp_eval(const isr_problem* p, const double* y, int64_t m, const double* es, double* out) {
+  interp_eval_kernel<<<(unsigned)((m + 127) / 128), 128, 0, p->ctx->stream>>>(p->n, p->d_ext.p, p->d_invh.p, p->d_Ct.p,
+                                                                               y, m, es, out);
+}
+
 }  // namespace isr

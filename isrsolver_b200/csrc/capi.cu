@@ -3,7 +3,11 @@
 #include <cstring>
 #include <new>
 
+#include "linalg.hpp"
 #include "problem.hpp"
+#include "solve.hpp"
+#include "tikhonov.hpp"
+#include "toy_batch.hpp"
 
 namespace isr {
 static thread_local char g_err[1024] = "";
@@ -207,6 +211,225 @@ int isr_basis_eval(isr_problem* p, int64_t m, const int* cs_index, const double*
   ISR_CUDA(cudaGetLastError());
   ISR_CUDA(cudaMemcpyAsync(out, dout.p, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
   ISR_CUDA(cudaStreamSynchronize(st));
+  return ISR_OK;
+}
+
+int isr_basis_integrals(isr_problem* p, double* w_out) {
+  if (!p || !w_out) { set_error("NULL argument"); return ISR_EINVAL; }
+  // exact integral of the per-segment polynomials: w_j = sum_k h_k sum_q C[j][k][q] / (q+1)
+  // (Interpolator::evalIntegralBasis, src/Interpolator.cpp:459-473, integrates the same pieces with QAG)
+  const int n = p->n;
+  for (int j = 0; j < n; ++j) {
+    double w = 0.0;
+    for (int k = p->h_klo[j]; k <= p->h_khi[j]; ++k) {
+      const double h = p->ext[k + 1] - p->ext[k];
+      double s = 0.0;
+      for (int q = 0; q < 4; ++q) s += p->h_Ct[((size_t)k * 4 + q) * n + j] / (q + 1);
+      w += h * s;
+    }
+    w_out[j] = w;
+  }
+  return ISR_OK;
+}
+
+int isr_interp_eval(isr_problem* p, const double* y, int64_t m, const double* energy, double* out) {
+  if (!p || !y || !energy || !out) { set_error("NULL argument"); return ISR_EINVAL; }
+  if (m <= 0) return ISR_OK;
+  ISR_CUDA(cudaSetDevice(p->ctx->device));
+  cudaStream_t st = p->ctx->stream;
+  DevBuf<double> dy, de, dout;
+  ISR_TRY(dy.reserve(p->n)); ISR_TRY(de.reserve(m)); ISR_TRY(dout.reserve(m));
+  ISR_CUDA(cudaMemcpyAsync(dy.p, y, sizeof(double) * p->n, cudaMemcpyHostToDevice, st));
+  ISR_CUDA(cudaMemcpyAsync(de.p, energy, sizeof(double) * m, cudaMemcpyHostToDevice, st));
+  launch_interp_eval(p, dy.p, m, de.p, dout.p);
+  ISR_CUDA(cudaGetLastError());
+  ISR_CUDA(cudaMemcpyAsync(out, dout.p, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+  ISR_CUDA(cudaStreamSynchronize(st));
+  return ISR_OK;
+}
+
+int isr_factor(isr_problem* p, const double* vcs_err) {
+  if (!p || !vcs_err) { set_error("NULL argument"); return ISR_EINVAL; }
+  ISR_CUDA(cudaSetDevice(p->ctx->device));
+  ISR_TRY(factor(p, vcs_err));
+  ISR_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  return ISR_OK;
+}
+
+int isr_solve(isr_problem* p, const double* vcs, double* bcs_out, double* cov_out) {
+  if (!p || !vcs || !bcs_out) { set_error("NULL argument"); return ISR_EINVAL; }
+  if (!p->factored) { set_error("isr_solve: call isr_factor first"); return ISR_ESTATE; }
+  ISR_CUDA(cudaSetDevice(p->ctx->device));
+  const int n = p->n;
+  cudaStream_t st = p->ctx->stream;
+  ISR_TRY(p->d_b0.reserve(n));
+  ISR_TRY(p->d_stat.reserve((size_t)4 * n));
+  ISR_CUDA(cudaMemcpyAsync(p->d_b0.p, vcs, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  ISR_TRY(gemv(p->ctx, false, n, p->d_Ginv.p, p->d_b0.p, p->d_stat.p));
+  ISR_CUDA(cudaMemcpyAsync(bcs_out, p->d_stat.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  if (cov_out) ISR_CUDA(cudaMemcpyAsync(cov_out, p->d_Cov.p, sizeof(double) * n * n, cudaMemcpyDeviceToHost, st));
+  ISR_CUDA(cudaStreamSynchronize(st));
+  return ISR_OK;
+}
+
+static int copy_out(isr_problem* p, const double* dev, double* host, const char* what) {
+  if (!p || !host) { set_error("NULL argument"); return ISR_EINVAL; }
+  if (!p->factored) { set_error("%s: call isr_factor first", what); return ISR_ESTATE; }
+  ISR_CUDA(cudaSetDevice(p->ctx->device));
+  ISR_CUDA(cudaMemcpyAsync(host, dev, sizeof(double) * p->n * p->n, cudaMemcpyDeviceToHost, p->ctx->stream));
+  ISR_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  return ISR_OK;
+}
+int isr_get_inverse(isr_problem* p, double* out) { return copy_out(p, p ? p->d_Ginv.p : nullptr, out, "isr_get_inverse"); }
+int isr_get_inv_cov(isr_problem* p, double* out) { return copy_out(p, p ? p->d_InvCov.p : nullptr, out, "isr_get_inv_cov"); }
+
+int isr_cond_number(isr_problem* p, double* cond_out) {
+  if (!p || !cond_out) { set_error("NULL argument"); return ISR_EINVAL; }
+  ISR_CUDA(cudaSetDevice(p->ctx->device));
+  ISR_TRY(ensure_svd(p));
+  *cond_out = p->h_sv.front() / p->h_sv.back();
+  return ISR_OK;
+}
+
+int isr_set_toy_kernel(isr_problem* p, int variant) {
+  if (!p || variant < 0 || variant > 2) { set_error("isr_set_toy_kernel: bad argument"); return ISR_EINVAL; }
+  p->toy_variant = variant;
+  return ISR_OK;
+}
+
+int isr_toy_batch(isr_problem* p, int64_t T, const double* V, const double* bcs0, double* chi2_out,
+                  double* sum_bcs_out, double* ratio_stats_out, uint32_t* ratio_hist_out, double* bcs_out) {
+  if (!p || (T > 0 && (!V || !bcs0))) { set_error("NULL argument"); return ISR_EINVAL; }
+  if (T < 0) { set_error("isr_toy_batch: T < 0"); return ISR_EINVAL; }
+  ISR_CUDA(cudaSetDevice(p->ctx->device));
+  if (T == 0) {
+    if (sum_bcs_out) std::memset(sum_bcs_out, 0, sizeof(double) * p->n);
+    if (ratio_stats_out) std::memset(ratio_stats_out, 0, sizeof(double) * 3 * p->n);
+    if (ratio_hist_out) std::memset(ratio_hist_out, 0, sizeof(uint32_t) * (size_t)p->n * 1026);
+    return ISR_OK;
+  }
+  return toy_batch_host(p, T, V, bcs0, chi2_out, sum_bcs_out, ratio_stats_out, ratio_hist_out, bcs_out);
+}
+
+int isr_toy_batch_dev(isr_problem* p, int64_t T, const double* V_dev, const double* bcs0, double* chi2_dev,
+                      double* sum_bcs_dev, double* ratio_stats_dev, uint32_t* ratio_hist_dev, double* bcs_dev) {
+  if (!p || (T > 0 && (!V_dev || !bcs0))) { set_error("NULL argument"); return ISR_EINVAL; }
+  if (T <= 0) return T == 0 ? ISR_OK : ISR_EINVAL;
+  ISR_CUDA(cudaSetDevice(p->ctx->device));
+  if (p->h_b0.size() != (size_t)p->n || std::memcmp(p->h_b0.data(), bcs0, sizeof(double) * p->n) != 0) {
+    ISR_TRY(p->d_b0.reserve(p->n));
+    // a stream-ordered copy from a stable host mirror: earlier launches that still read d_b0 finish first
+    p->h_b0.assign(bcs0, bcs0 + p->n);
+    ISR_CUDA(cudaMemcpyAsync(p->d_b0.p, p->h_b0.data(), sizeof(double) * p->n, cudaMemcpyHostToDevice, p->ctx->stream));
+    ISR_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  }
+  ToyOut o;
+  o.chi2 = chi2_dev; o.sum_bcs = sum_bcs_dev; o.ratio_stats = ratio_stats_dev; o.rhist = ratio_hist_dev; o.bcs = bcs_dev;
+  return toy_batch_device(p, T, V_dev, p->d_b0.p, o);
+}
+
+int isr_minmax_dev(isr_ctx* ctx, int64_t n, const double* v_dev, double* min_out, double* max_out) {
+  if (!ctx || !v_dev || !min_out || !max_out) { set_error("NULL argument"); return ISR_EINVAL; }
+  ISR_CUDA(cudaSetDevice(ctx->device));
+  return minmax_device(ctx, n, v_dev, min_out, max_out);
+}
+
+int isr_histogram_dev(isr_ctx* ctx, int64_t n, const double* v_dev, int nbins, double lo, double hi, uint32_t* counts_out) {
+  if (!ctx || (n > 0 && !v_dev) || !counts_out) { set_error("NULL argument"); return ISR_EINVAL; }
+  ISR_CUDA(cudaSetDevice(ctx->device));
+  return histogram_device(ctx, n, v_dev, nbins, lo, hi, counts_out);
+}
+
+int isr_chi2_histogram(isr_ctx* ctx, int64_t n, const double* chi2, int nbins, double* lo_out, double* hi_out, uint32_t* counts_out) {
+  if (!ctx || !chi2 || !lo_out || !hi_out || !counts_out) { set_error("NULL argument"); return ISR_EINVAL; }
+  if (n <= 0) { set_error("isr_chi2_histogram: empty input"); return ISR_EINVAL; }
+  ISR_CUDA(cudaSetDevice(ctx->device));
+  DevBuf<double> d;
+  ISR_TRY(d.reserve(n));
+  ISR_CUDA(cudaMemcpyAsync(d.p, chi2, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  ISR_TRY(minmax_device(ctx, n, d.p, lo_out, hi_out));
+  return histogram_device(ctx, n, d.p, nbins, *lo_out, *hi_out, counts_out);
+}
+
+int isr_tikhonov_prepare(isr_problem* p, const double* vcs_err, int deriv_reg) {
+  if (!p || !vcs_err) { set_error("NULL argument"); return ISR_EINVAL; }
+  ISR_CUDA(cudaSetDevice(p->ctx->device));
+  return tikhonov_prepare(p, vcs_err, deriv_reg);
+}
+
+int isr_tikhonov_scan(isr_problem* p, int64_t L, const double* lambda, const double* vcs, double* eq_norm2_out,
+                      double* smooth_norm2_out, double* curv_out, double* dcurv_out, double* bcs_out) {
+  if (!p || (L > 0 && (!lambda || !vcs))) { set_error("NULL argument"); return ISR_EINVAL; }
+  ISR_CUDA(cudaSetDevice(p->ctx->device));
+  return tikhonov_scan(p, L, lambda, vcs, eq_norm2_out, smooth_norm2_out, curv_out, dcurv_out, bcs_out);
+}
+
+int isr_tikhonov_solve(isr_problem* p, double lambda, const double* vcs, double* bcs_out, double* cov_out) {
+  if (!p || !vcs || !bcs_out) { set_error("NULL argument"); return ISR_EINVAL; }
+  ISR_CUDA(cudaSetDevice(p->ctx->device));
+  return tikhonov_solve(p, lambda, vcs, bcs_out, cov_out);
+}
+
+int isr_tikhonov_toy_scan_dev(isr_problem* p, int64_t L, const double* lambda, int64_t T, const double* V_dev,
+                              const double* bcs0, double* chi2_dev) {
+  if (!p || !lambda || !V_dev || !bcs0 || !chi2_dev) { set_error("NULL argument"); return ISR_EINVAL; }
+  ISR_CUDA(cudaSetDevice(p->ctx->device));
+  return tikhonov_toy_scan_device(p, L, lambda, T, V_dev, bcs0, chi2_dev);
+}
+
+int isr_tikhonov_toy_scan(isr_problem* p, int64_t L, const double* lambda, int64_t T, const double* V,
+                          const double* bcs0, double* chi2_out) {
+  if (!p || !lambda || !V || !bcs0 || !chi2_out) { set_error("NULL argument"); return ISR_EINVAL; }
+  if (L <= 0 || T <= 0) return ISR_OK;
+  ISR_CUDA(cudaSetDevice(p->ctx->device));
+  cudaStream_t st = p->ctx->stream;
+  DevBuf<double> dV, dchi;
+  ISR_TRY(dV.reserve((size_t)T * p->n));
+  ISR_TRY(dchi.reserve((size_t)L * T));
+  ISR_CUDA(cudaMemcpyAsync(dV.p, V, sizeof(double) * T * p->n, cudaMemcpyHostToDevice, st));
+  ISR_TRY(tikhonov_toy_scan_device(p, L, lambda, T, dV.p, bcs0, dchi.p));
+  ISR_CUDA(cudaMemcpyAsync(chi2_out, dchi.p, sizeof(double) * L * T, cudaMemcpyDeviceToHost, st));
+  ISR_CUDA(cudaStreamSynchronize(st));
+  return ISR_OK;
+}
+
+int isr_tikhonov_select(isr_problem* p, double lambda) {
+  if (!p) { set_error("NULL argument"); return ISR_EINVAL; }
+  ISR_CUDA(cudaSetDevice(p->ctx->device));
+  ISR_TRY(tikhonov_select(p, lambda));
+  ISR_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  return ISR_OK;
+}
+
+int isr_get_regulariser(isr_problem* p, double* F_out) {
+  if (!p || !F_out) { set_error("NULL argument"); return ISR_EINVAL; }
+  if (!p->tik_ready) { set_error("isr_get_regulariser: call isr_tikhonov_prepare first"); return ISR_ESTATE; }
+  ISR_CUDA(cudaSetDevice(p->ctx->device));
+  ISR_CUDA(cudaMemcpyAsync(F_out, p->d_F.p, sizeof(double) * p->n * p->n, cudaMemcpyDeviceToHost, p->ctx->stream));
+  ISR_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  return ISR_OK;
+}
+
+int isr_tsvd_solve(isr_problem* p, int k, int keep_one, const double* vcs, const double* vcs_err, double* bcs_out,
+                   double* cov_out) {
+  if (!p || !vcs || !bcs_out) { set_error("NULL argument"); return ISR_EINVAL; }
+  ISR_CUDA(cudaSetDevice(p->ctx->device));
+  return tsvd_solve(p, k, keep_one, vcs, vcs_err, bcs_out, cov_out);
+}
+
+int isr_singular_values(isr_problem* p, double* sv_out) {
+  if (!p || !sv_out) { set_error("NULL argument"); return ISR_EINVAL; }
+  ISR_CUDA(cudaSetDevice(p->ctx->device));
+  ISR_TRY(ensure_svd(p));
+  std::memcpy(sv_out, p->h_sv.data(), sizeof(double) * p->n);
+  return ISR_OK;
+}
+
+int isr_tsvd_select(isr_problem* p, int k, int keep_one, const double* vcs_err) {
+  if (!p || !vcs_err) { set_error("NULL argument"); return ISR_EINVAL; }
+  ISR_CUDA(cudaSetDevice(p->ctx->device));
+  ISR_TRY(tsvd_select(p, k, keep_one, vcs_err));
+  ISR_CUDA(cudaStreamSynchronize(p->ctx->stream));
   return ISR_OK;
 }
 

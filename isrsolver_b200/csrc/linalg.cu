@@ -1,0 +1,119 @@
+// One-off N x N dense linear algebra on the device (N <= a few hundred, once per problem):
+// LU inverse, SVD, symmetric-definite generalised eigen-system.  These are latency-bound library
+// calls (cuSOLVER / cuBLAS), not the hot path; the per-toy and per-lambda work is in toy_batch.cu and
+// tikhonov.cu.  All matrices here are column-major (Eigen / LAPACK convention).
+#include "linalg.hpp"
+
+namespace isr {
+
+__global__ void set_identity_kernel(int n, double* __restrict__ A) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n * n) A[idx] = (idx / n == idx % n) ? 1.0 : 0.0;
+}
+
+// out[r * ld + c] = (transpose ? in[c + n*r]... ) helpers -------------------------------------------
+// Row-major padded copy of a column-major matrix, optional row scaling: out[i][j] = s_i * A(i,j).
+__global__ void colmajor_to_rowmajor_kernel(int n, const double* __restrict__ A, const double* __restrict__ rowscale,
+                                            int invert_scale, double* __restrict__ out, int ld) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * ld) return;
+  const int i = idx / ld, j = idx % ld;
+  double v = 0.0;
+  if (j < n) {
+    v = A[(size_t)i + (size_t)n * j];
+    if (rowscale) v = invert_scale ? v / rowscale[i] : v * rowscale[i];
+  }
+  out[idx] = v;
+}
+void colmajor_to_rowmajor(cudaStream_t st, int n, const double* A, const double* rowscale, int invert_scale,
+                          double* out, int ld) {
+  colmajor_to_rowmajor_kernel<<<(n * ld + 255) / 256, 256, 0, st>>>(n, A, rowscale, invert_scale, out, ld);
+}
+
+// B(i,j) = A(i,j) * colscale_j (or / colscale_j), column-major.
+__global__ void scale_cols_kernel(int n, const double* __restrict__ A, const double* __restrict__ s, int invert,
+                                  double* __restrict__ B) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * n) return;
+  const int j = idx / n;
+  B[idx] = invert ? A[idx] / s[j] : A[idx] * s[j];
+}
+void scale_cols(cudaStream_t st, int n, const double* A, const double* s, int invert, double* B) {
+  scale_cols_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(n, A, s, invert, B);
+}
+// B(i,j) = A(i,j) * rowscale_i (or / rowscale_i), column-major.
+__global__ void scale_rows_kernel(int n, const double* __restrict__ A, const double* __restrict__ s, int invert,
+                                  double* __restrict__ B) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * n) return;
+  const int i = idx % n;
+  B[idx] = invert ? A[idx] / s[i] : A[idx] * s[i];
+}
+void scale_rows(cudaStream_t st, int n, const double* A, const double* s, int invert, double* B) {
+  scale_rows_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(n, A, s, invert, B);
+}
+
+int gemm(isr_ctx* c, bool ta, bool tb, int n, const double* A, const double* B, double* C) {
+  const double one = 1.0, zero = 0.0;
+  ISR_CUBLAS(cublasDgemm(c->blas, ta ? CUBLAS_OP_T : CUBLAS_OP_N, tb ? CUBLAS_OP_T : CUBLAS_OP_N, n, n, n, &one,
+                         A, n, B, n, &zero, C, n));
+  return ISR_OK;
+}
+int gemv(isr_ctx* c, bool ta, int n, const double* A, const double* x, double* y) {
+  const double one = 1.0, zero = 0.0;
+  ISR_CUBLAS(cublasDgemv(c->blas, ta ? CUBLAS_OP_T : CUBLAS_OP_N, n, n, &one, A, n, x, 1, &zero, y, 1));
+  return ISR_OK;
+}
+
+static int check_info(isr_ctx* c, const int* d_info, const char* what) {
+  int info = 0;
+  ISR_CUDA(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  ISR_CUDA(cudaStreamSynchronize(c->stream));
+  if (info != 0) {
+    set_error("%s failed: info = %d (singular or not positive definite matrix)", what, info);
+    return ISR_ENUMERIC;
+  }
+  return ISR_OK;
+}
+
+// Ainv = A^-1 by LU with partial pivoting (A is destroyed).
+int lu_inverse(isr_ctx* c, int n, double* A, double* Ainv, DevBuf<double>& work, DevBuf<int>& ipiv, DevBuf<int>& info) {
+  int lwork = 0;
+  ISR_CUSOLVER(cusolverDnDgetrf_bufferSize(c->solver, n, n, A, n, &lwork));
+  ISR_TRY(work.reserve(lwork));
+  ISR_TRY(ipiv.reserve(n));
+  ISR_TRY(info.reserve(1));
+  ISR_CUSOLVER(cusolverDnDgetrf(c->solver, n, n, A, n, work.p, ipiv.p, info.p));
+  ISR_TRY(check_info(c, info.p, "LU factorisation (getrf)"));
+  set_identity_kernel<<<(n * n + 255) / 256, 256, 0, c->stream>>>(n, Ainv);
+  ISR_CUSOLVER(cusolverDnDgetrs(c->solver, CUBLAS_OP_N, n, n, A, n, ipiv.p, Ainv, n, info.p));
+  ISR_TRY(check_info(c, info.p, "LU solve (getrs)"));
+  return ISR_OK;
+}
+
+// A = U diag(S) VT (A destroyed); U, VT n x n column-major, S descending.
+int svd(isr_ctx* c, int n, double* A, double* U, double* S, double* VT, DevBuf<double>& work, DevBuf<int>& info) {
+  int lwork = 0;
+  ISR_CUSOLVER(cusolverDnDgesvd_bufferSize(c->solver, n, n, &lwork));
+  ISR_TRY(work.reserve(lwork));
+  ISR_TRY(info.reserve(1));
+  ISR_CUSOLVER(cusolverDnDgesvd(c->solver, 'A', 'A', n, n, A, n, S, U, n, VT, n, work.p, lwork, nullptr, info.p));
+  ISR_TRY(check_info(c, info.p, "SVD (gesvd)"));
+  return ISR_OK;
+}
+
+// Generalised symmetric-definite eigen-system A u = mu B u with U^T B U = I (A <- U, B destroyed),
+// eigenvalues ascending in W.
+int sygvd(isr_ctx* c, int n, double* A, double* B, double* W, DevBuf<double>& work, DevBuf<int>& info) {
+  int lwork = 0;
+  ISR_CUSOLVER(cusolverDnDsygvd_bufferSize(c->solver, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR,
+                                           CUBLAS_FILL_MODE_LOWER, n, A, n, B, n, W, &lwork));
+  ISR_TRY(work.reserve(lwork));
+  ISR_TRY(info.reserve(1));
+  ISR_CUSOLVER(cusolverDnDsygvd(c->solver, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER,
+                                n, A, n, B, n, W, work.p, lwork, info.p));
+  ISR_TRY(check_info(c, info.p, "generalised eigen-system (sygvd; is the regulariser F positive definite?)"));
+  return ISR_OK;
+}
+
+}  // namespace isr

@@ -1,0 +1,15 @@
+// Declarations for linalg.cu (one-off N x N library calls, column-major).
+#pragma once
+#include "common.cuh"
+
+namespace isr {
+void colmajor_to_rowmajor(cudaStream_t st, int n, const double* A, const double* rowscale, int invert_scale,
+                          double* out, int ld);
+void scale_cols(cudaStream_t st, int n, const double* A, const double* s, int invert, double* B);
+void scale_rows(cudaStream_t st, int n, const double* A, const double* s, int invert, double* B);
+int gemm(isr_ctx* c, bool ta, bool tb, int n, const double* A, const double* B, double* C);
+int gemv(isr_ctx* c, bool ta, int n, const double* A, const double* x, double* y);
+int lu_inverse(isr_ctx* c, int n, double* A, double* Ainv, DevBuf<double>& work, DevBuf<int>& ipiv, DevBuf<int>& info);
+int svd(isr_ctx* c, int n, double* A, double* U, double* S, double* VT, DevBuf<double>& work, DevBuf<int>& info);
+int sygvd(isr_ctx* c, int n, double* A, double* B, double* W, DevBuf<double>& work, DevBuf<int>& info);
+}  // namespace isr

@@ -41,7 +41,7 @@ struct isr_problem {
   isr::DevBuf<double> d_Ginv, d_R, d_Cov, d_InvCov, d_Sop, d_Rop, d_werr;
   isr::DevBuf<double> d_work;
   isr::DevBuf<int> d_ipiv, d_info;
-  std::vector<double> vcs_err;
+  std::vector<double> vcs_err, h_b0;
   bool factored = false;
   bool solver_selected = false;
   int toy_variant = 0;
@@ -49,16 +49,28 @@ struct isr_problem {
   // ---- toy batch workspaces ------------------------------------------------------------------
   isr::DevBuf<double> d_V, d_chi2, d_acc, d_b0, d_B;
   isr::DevBuf<uint32_t> d_rhist;
+  // host-buffer pipeline (isr_toy_batch): two V slots, chi2 / statistics staging, copy stream
+  isr::DevBuf<double> d_Vh, d_chi2h, d_stat, d_Bh;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  ~isr_problem() {
+    for (int q = 0; q < 2; ++q) {
+      if (ev_copied[q]) cudaEventDestroy(ev_copied[q]);
+      if (ev_done[q]) cudaEventDestroy(ev_done[q]);
+    }
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+  }
 
   // ---- Tikhonov ------------------------------------------------------------------------------
   bool tik_ready = false;
   int tik_deriv = 1;
-  isr::DevBuf<double> d_F, d_U, d_mu, d_UtGtW, d_FU, d_lam, d_scan;
-  std::vector<double> h_F, h_U, h_mu, h_UtGtW;  // host mirrors (column-major)
+  isr::DevBuf<double> d_F, d_U, d_mu, d_P, d_FU, d_w, d_tmp2, d_E;
+  std::vector<double> h_mu;
 
   // ---- SVD -----------------------------------------------------------------------------------
   bool svd_ready = false;
-  std::vector<double> h_svU, h_svV, h_sv;  // column-major U, V; singular values descending
+  isr::DevBuf<double> d_svU, d_svVT, d_sv;  // column-major U, V^T; singular values descending
+  std::vector<double> h_sv;
 };
 
 namespace isr {
@@ -66,6 +78,8 @@ int build_basis_tables(isr_problem* p);
 int set_ranges(isr_problem* p, int nranges, const int* ranges);
 void launch_kf_plain(int64_t n, const double* x, const double* s, double* out, cudaStream_t st);
 void launch_basis_eval(const isr_problem* p, int64_t m, const int* js, const double* es, int deriv, double* out);
+void launch_interp_eval(const isr_problem* p, const double* y, int64_t m, const double* es, double* out);
+int ensure_svd(isr_problem* p);
 int upload_eps(isr_problem* p, const isr_eps_desc* eps);
 int assemble(isr_problem* p, const double* ecm_err);
 }  // namespace isr

@@ -1,0 +1,201 @@
+// ISRSolverSLE::solve pieces that run once per problem (src/ISRSolverSLE.cpp:86-95), the chi2 / ratio
+// histogramming of src/Chi2Test.cpp:64-78, and the host-buffer toy-batch pipeline.
+#include "linalg.hpp"
+#include "problem.hpp"
+#include "solve.hpp"
+#include "toy_batch.hpp"
+
+#include <algorithm>
+#include <cmath>
+
+namespace isr {
+
+// Factor for a given error vector (W = diag(err^-2), src/BaseISRSolver.cpp:355-357):
+//   Ginv = G^-1                      (b = Ginv v  ==  COD(G).solve(v) for a full-rank G)
+//   R    = W^(1/2) G                 (Cov^-1 = G^T W G = R^T R)
+//   Cov  = (Ginv W^(-1/2)) (Ginv W^(-1/2))^T  ==  (G^T W G)^-1, symmetric by construction
+int factor(isr_problem* p, const double* vcs_err) {
+  if (!p->has_G) { set_error("isr_factor: no matrix (call isr_assemble or isr_set_matrix first)"); return ISR_ESTATE; }
+  const int n = p->n, ld = (n + 1) & ~1;
+  for (int i = 0; i < n; ++i)
+    if (!(vcs_err[i] > 0.0) || !std::isfinite(vcs_err[i])) {
+      set_error("isr_factor: vcs_err[%d] = %g must be positive and finite", i, vcs_err[i]);
+      return ISR_EINVAL;
+    }
+  isr_ctx* c = p->ctx;
+  cudaStream_t st = c->stream;
+  const size_t nn = (size_t)n * n;
+  ISR_TRY(p->d_werr.reserve(n));
+  ISR_TRY(p->d_tmp.reserve(nn));
+  ISR_TRY(p->d_Ginv.reserve(nn));
+  ISR_TRY(p->d_R.reserve(nn));
+  ISR_TRY(p->d_Cov.reserve(nn));
+  ISR_TRY(p->d_InvCov.reserve(nn));
+  ISR_TRY(p->d_Sop.reserve((size_t)n * ld));
+  ISR_TRY(p->d_Rop.reserve((size_t)n * ld));
+  p->vcs_err.assign(vcs_err, vcs_err + n);
+  ISR_CUDA(cudaMemcpyAsync(p->d_werr.p, vcs_err, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  ISR_CUDA(cudaMemcpyAsync(p->d_tmp.p, p->d_G.p, sizeof(double) * nn, cudaMemcpyDeviceToDevice, st));
+  ISR_TRY(lu_inverse(c, n, p->d_tmp.p, p->d_Ginv.p, p->d_work, p->d_ipiv, p->d_info));
+  scale_rows(st, n, p->d_G.p, p->d_werr.p, 1, p->d_R.p);                  // R = diag(1/err) G
+  scale_cols(st, n, p->d_Ginv.p, p->d_werr.p, 0, p->d_tmp.p);             // Ginv diag(err)
+  ISR_TRY(gemm(c, false, true, n, p->d_tmp.p, p->d_tmp.p, p->d_Cov.p));   // Cov
+  ISR_TRY(gemm(c, true, false, n, p->d_R.p, p->d_R.p, p->d_InvCov.p));    // G^T W G
+  ISR_CUDA(cudaGetLastError());
+  p->factored = true;
+  return select_sle(p);
+}
+
+// Operators the toy kernel consumes: row-major, leading dimension padded to even, pad column zero.
+int select_sle(isr_problem* p) {
+  if (!p->factored) { set_error("select: isr_factor has not been called"); return ISR_ESTATE; }
+  const int n = p->n, ld = (n + 1) & ~1;
+  cudaStream_t st = p->ctx->stream;
+  colmajor_to_rowmajor(st, n, p->d_Ginv.p, nullptr, 0, p->d_Sop.p, ld);
+  colmajor_to_rowmajor(st, n, p->d_R.p, nullptr, 0, p->d_Rop.p, ld);
+  ISR_CUDA(cudaGetLastError());
+  p->solver_selected = true;
+  return ISR_OK;
+}
+
+// --------------------------------------------------------------------------------------------------
+// min / max and TH1-style histogram
+// --------------------------------------------------------------------------------------------------
+__global__ void minmax_kernel(int64_t n, const double* __restrict__ v, double* __restrict__ part) {
+  __shared__ double smin[32], smax[32];
+  double lo = INFINITY, hi = -INFINITY;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+    const double x = v[q];
+    lo = fmin(lo, x);
+    hi = fmax(hi, x);
+  }
+  for (int s = 16; s >= 1; s >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, s));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, s));
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { smin[w] = lo; smax[w] = hi; }
+  __syncthreads();
+  if (w == 0) {
+    lo = l < (blockDim.x >> 5) ? smin[l] : INFINITY;
+    hi = l < (blockDim.x >> 5) ? smax[l] : -INFINITY;
+    for (int s = 16; s >= 1; s >>= 1) {
+      lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, s));
+      hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, s));
+    }
+    if (l == 0) { part[2 * blockIdx.x] = lo; part[2 * blockIdx.x + 1] = hi; }
+  }
+}
+
+// TH1::Fill bin arithmetic (TAxis::FindBin, fixed bins): 0 = underflow, nbins+1 = overflow.
+__device__ __forceinline__ int th1_bin(int nbins, double lo, double hi, double x) {
+  if (x < lo) return 0;
+  if (!(x < hi)) return nbins + 1;
+  return 1 + (int)__ddiv_rn(__dmul_rn((double)nbins, __dsub_rn(x, lo)), __dsub_rn(hi, lo));
+}
+__global__ void hist_kernel(int64_t n, const double* __restrict__ v, int nbins, double lo, double hi,
+                            uint32_t* __restrict__ counts) {
+  extern __shared__ uint32_t sh[];
+  for (int q = threadIdx.x; q < nbins + 2; q += blockDim.x) sh[q] = 0;
+  __syncthreads();
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd(&sh[th1_bin(nbins, lo, hi, v[q])], 1u);
+  __syncthreads();
+  for (int q = threadIdx.x; q < nbins + 2; q += blockDim.x)
+    if (sh[q]) atomicAdd(&counts[q], sh[q]);
+}
+
+int minmax_device(isr_ctx* c, int64_t n, const double* v_dev, double* lo, double* hi) {
+  if (n <= 0) { set_error("minmax: empty input"); return ISR_EINVAL; }
+  const int blocks = (int)std::min<int64_t>(c->sm_count * 4, (n + 255) / 256);
+  DevBuf<double> part;
+  ISR_TRY(part.reserve(2 * blocks));
+  minmax_kernel<<<blocks, 256, 0, c->stream>>>(n, v_dev, part.p);
+  std::vector<double> h(2 * blocks);
+  ISR_CUDA(cudaMemcpyAsync(h.data(), part.p, sizeof(double) * 2 * blocks, cudaMemcpyDeviceToHost, c->stream));
+  ISR_CUDA(cudaStreamSynchronize(c->stream));
+  double a = INFINITY, b = -INFINITY;
+  for (int q = 0; q < blocks; ++q) { a = std::min(a, h[2 * q]); b = std::max(b, h[2 * q + 1]); }
+  *lo = a;
+  *hi = b;
+  return ISR_OK;
+}
+
+int histogram_device(isr_ctx* c, int64_t n, const double* v_dev, int nbins, double lo, double hi, uint32_t* counts_host) {
+  if (nbins < 1 || nbins > 8190) { set_error("histogram: nbins out of range"); return ISR_EINVAL; }
+  DevBuf<uint32_t> cnt;
+  ISR_TRY(cnt.reserve(nbins + 2));
+  ISR_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(uint32_t) * (nbins + 2), c->stream));
+  if (n > 0) {
+    const int blocks = (int)std::min<int64_t>(c->sm_count * 4, (n + 255) / 256);
+    hist_kernel<<<blocks, 256, sizeof(uint32_t) * (nbins + 2), c->stream>>>(n, v_dev, nbins, lo, hi, cnt.p);
+  }
+  ISR_CUDA(cudaMemcpyAsync(counts_host, cnt.p, sizeof(uint32_t) * (nbins + 2), cudaMemcpyDeviceToHost, c->stream));
+  ISR_CUDA(cudaStreamSynchronize(c->stream));
+  return ISR_OK;
+}
+
+// --------------------------------------------------------------------------------------------------
+// Host-buffer toy batch: H2D copies of V chunks overlap the kernels of the previous chunk.
+// --------------------------------------------------------------------------------------------------
+int toy_batch_host(isr_problem* p, int64_t T, const double* V, const double* bcs0, double* chi2_out,
+                   double* sum_bcs_out, double* ratio_stats_out, uint32_t* ratio_hist_out, double* bcs_out) {
+  const int n = p->n;
+  isr_ctx* c = p->ctx;
+  cudaStream_t st = c->stream;
+  if (!p->solver_selected) {
+    set_error("isr_toy_batch: no solver selected (call isr_factor first)");
+    return ISR_ESTATE;
+  }
+  if (T <= 0) return ISR_OK;
+  // two pipeline slots of up to 2^17 toys each
+  const int64_t slot = std::min<int64_t>(T, 1 << 17);
+  ISR_TRY(p->d_Vh.reserve((size_t)2 * slot * n));
+  ISR_TRY(p->d_chi2h.reserve((size_t)T));
+  ISR_TRY(p->d_b0.reserve(n));
+  ISR_TRY(p->d_stat.reserve((size_t)4 * n));
+  ISR_CUDA(cudaMemcpyAsync(p->d_b0.p, bcs0, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  ISR_CUDA(cudaMemsetAsync(p->d_stat.p, 0, sizeof(double) * 4 * n, st));
+  if (ratio_hist_out) {
+    ISR_TRY(p->d_rhist.reserve((size_t)n * 1026));
+    ISR_CUDA(cudaMemsetAsync(p->d_rhist.p, 0, sizeof(uint32_t) * (size_t)n * 1026, st));
+  }
+  if (bcs_out) ISR_TRY(p->d_Bh.reserve((size_t)2 * slot * n));
+  if (!p->copy_stream) {
+    ISR_CUDA(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+    for (int q = 0; q < 2; ++q) {
+      ISR_CUDA(cudaEventCreateWithFlags(&p->ev_copied[q], cudaEventDisableTiming));
+      ISR_CUDA(cudaEventCreateWithFlags(&p->ev_done[q], cudaEventDisableTiming));
+    }
+  }
+  int k = 0;
+  for (int64_t t0 = 0; t0 < T; t0 += slot, ++k) {
+    const int q = k & 1;
+    const int64_t tc = std::min<int64_t>(slot, T - t0);
+    double* dv = p->d_Vh.p + (size_t)q * slot * n;
+    if (k >= 2) ISR_CUDA(cudaStreamWaitEvent(p->copy_stream, p->ev_done[q], 0));   // slot free again
+    ISR_CUDA(cudaMemcpyAsync(dv, V + t0 * n, sizeof(double) * tc * n, cudaMemcpyHostToDevice, p->copy_stream));
+    ISR_CUDA(cudaEventRecord(p->ev_copied[q], p->copy_stream));
+    ISR_CUDA(cudaStreamWaitEvent(st, p->ev_copied[q], 0));
+    ToyOut o;
+    o.chi2 = chi2_out ? p->d_chi2h.p + t0 : nullptr;
+    o.sum_bcs = sum_bcs_out ? p->d_stat.p : nullptr;
+    o.ratio_stats = ratio_stats_out ? p->d_stat.p + n : nullptr;
+    o.rhist = ratio_hist_out ? p->d_rhist.p : nullptr;
+    o.bcs = bcs_out ? p->d_Bh.p + (size_t)q * slot * n : nullptr;
+    ISR_TRY(toy_batch_device(p, tc, dv, p->d_b0.p, o));
+    if (bcs_out)
+      ISR_CUDA(cudaMemcpyAsync(bcs_out + t0 * n, o.bcs, sizeof(double) * tc * n, cudaMemcpyDeviceToHost, st));
+    ISR_CUDA(cudaEventRecord(p->ev_done[q], st));
+  }
+  if (chi2_out) ISR_CUDA(cudaMemcpyAsync(chi2_out, p->d_chi2h.p, sizeof(double) * T, cudaMemcpyDeviceToHost, st));
+  if (sum_bcs_out) ISR_CUDA(cudaMemcpyAsync(sum_bcs_out, p->d_stat.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  if (ratio_stats_out)
+    ISR_CUDA(cudaMemcpyAsync(ratio_stats_out, p->d_stat.p + n, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, st));
+  if (ratio_hist_out)
+    ISR_CUDA(cudaMemcpyAsync(ratio_hist_out, p->d_rhist.p, sizeof(uint32_t) * (size_t)n * 1026, cudaMemcpyDeviceToHost, st));
+  ISR_CUDA(cudaStreamSynchronize(st));
+  return ISR_OK;
+}
+
+}  // namespace isr

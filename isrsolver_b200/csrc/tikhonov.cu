@@ -1,0 +1,406 @@
+// Tikhonov lambda-scan / L-curve and TSVD from ONE decomposition.
+//
+// Reference: every ISRSolverTikhonov::solve() call rebuilds F, T = G^T W G + lambda F,
+// L = F^-1 G^T W G + lambda I and two FullPivLU factorisations (src/ISRSolverTikhonov.cpp:139-155),
+// i.e. ~15 N^3 flop per lambda and per toy.  Here the generalised symmetric eigen-system
+//     (G^T W G) u_m = mu_m F u_m ,   U^T F U = I
+// is computed once (isr_tikhonov_prepare).  With  P = U^T G^T W  and  c = P v :
+//     b_lambda   = U (c / (mu + lambda))                                   (solve, :61-72)
+//     |W^1/2 (G b - v)|^2 = sum_m c_m^2 lambda^2 / (mu_m (mu_m + lambda)^2)  (evalEqNorm2, :106-109)
+//     b^T F b    = sum_m c_m^2 / (mu_m + lambda)^2                          (evalSmoothnessConstraintNorm2)
+//     xi'  = 2 b^T F b'  = -2 sum_m c_m^2 / (mu_m + lambda)^3 ,  b' = -L^-1 b   (:115-128)
+//     xi'' = 2 b'^T F b' + 2 b^T F b'' = 6 sum_m c_m^2 / (mu_m + lambda)^4 ,  b'' = -2 L^-1 b'
+//     Cov_lambda = A+ W^-1 A+^T = U diag(mu / (mu + lambda)^2) U^T
+//     chi2(lambda, toy k) = (b_k - b0)^T Cov_lambda^-1 (b_k - b0) = sum_m (e_km - lambda f_m)^2,
+//         e_km = (c_km - g_m mu_m) / sqrt(mu_m),  f_m = g_m / sqrt(mu_m),  g = U^T F b0
+// so every lambda is a diagonal rescaling: O(N) per lambda and per (lambda, toy) pair.
+#include "linalg.hpp"
+#include "problem.hpp"
+#include "solve.hpp"
+#include "tikhonov.hpp"
+#include "toy_batch.hpp"
+#include "toy_gemm.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+namespace isr {
+
+int ensure_svd(isr_problem* p) {
+  if (p->svd_ready) return ISR_OK;
+  if (!p->has_G) { set_error("SVD: no matrix (call isr_assemble first)"); return ISR_ESTATE; }
+  const int n = p->n;
+  const size_t nn = (size_t)n * n;
+  cudaStream_t st = p->ctx->stream;
+  ISR_TRY(p->d_tmp.reserve(nn));
+  ISR_TRY(p->d_svU.reserve(nn));
+  ISR_TRY(p->d_svVT.reserve(nn));
+  ISR_TRY(p->d_sv.reserve(n));
+  ISR_CUDA(cudaMemcpyAsync(p->d_tmp.p, p->d_G.p, sizeof(double) * nn, cudaMemcpyDeviceToDevice, st));
+  ISR_TRY(svd(p->ctx, n, p->d_tmp.p, p->d_svU.p, p->d_sv.p, p->d_svVT.p, p->d_work, p->d_info));
+  p->h_sv.resize(n);
+  ISR_CUDA(cudaMemcpyAsync(p->h_sv.data(), p->d_sv.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  ISR_CUDA(cudaStreamSynchronize(st));
+  p->svd_ready = true;
+  return ISR_OK;
+}
+
+// D(i,j) = basis_j'(E_i) (column-major): the point-wise derivative projector,
+// src/ISRSolverTikhonov.cpp:92-99.
+__global__ void deriv_pairs_kernel(int n, const double* __restrict__ ext, int* __restrict__ js, double* __restrict__ es) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * n) return;
+  const int i = idx % n, j = idx / n;  // column-major position idx = i + n j
+  js[idx] = j;
+  es[idx] = ext[i + 1];
+}
+
+int tikhonov_prepare(isr_problem* p, const double* vcs_err, int deriv_reg) {
+  if (!p->has_G) { set_error("isr_tikhonov_prepare: no matrix (call isr_assemble first)"); return ISR_ESTATE; }
+  const int n = p->n;
+  const size_t nn = (size_t)n * n;
+  isr_ctx* c = p->ctx;
+  cudaStream_t st = c->stream;
+  bool same = p->factored && p->vcs_err.size() == (size_t)n;
+  if (same) for (int i = 0; i < n; ++i) same = same && p->vcs_err[i] == vcs_err[i];
+  if (!same) ISR_TRY(factor(p, vcs_err));
+  // w_j = int basis_j dE (src/ISRSolverSLE.cpp:165-171), exact from the polynomial pieces
+  std::vector<double> w(n);
+  ISR_TRY(isr_basis_integrals(p, w.data()));
+  ISR_TRY(p->d_w.reserve(n));
+  ISR_CUDA(cudaMemcpyAsync(p->d_w.p, w.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  ISR_TRY(p->d_F.reserve(nn));
+  ISR_TRY(p->d_U.reserve(nn));
+  ISR_TRY(p->d_mu.reserve(n));
+  ISR_TRY(p->d_P.reserve(nn));
+  ISR_TRY(p->d_FU.reserve(nn));
+  ISR_TRY(p->d_tmp.reserve(nn));
+  ISR_TRY(p->d_tmp2.reserve(nn));
+  if (deriv_reg) {
+    // F = D^T diag(w) D  (:141-145)
+    DevBuf<int> js;
+    DevBuf<double> es;
+    ISR_TRY(js.reserve(nn));
+    ISR_TRY(es.reserve(nn));
+    deriv_pairs_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, st>>>(n, p->d_ext.p, js.p, es.p);
+    launch_basis_eval(p, (int64_t)nn, js.p, es.p, 1, p->d_tmp.p);           // tmp = D
+    scale_rows(st, n, p->d_tmp.p, p->d_w.p, 0, p->d_tmp2.p);                 // tmp2 = diag(w) D
+    ISR_TRY(gemm(c, true, false, n, p->d_tmp.p, p->d_tmp2.p, p->d_F.p));
+    ISR_CUDA(cudaStreamSynchronize(st));                                      // js/es go out of scope
+  } else {
+    // F = diag(w)  (:146-148)
+    ISR_CUDA(cudaMemsetAsync(p->d_F.p, 0, sizeof(double) * nn, st));
+    ISR_CUDA(cudaMemcpy2DAsync(p->d_F.p, sizeof(double) * (n + 1), p->d_w.p, sizeof(double), sizeof(double), n,
+                               cudaMemcpyDeviceToDevice, st));
+  }
+  // generalised eigen-system: U <- eigenvectors of (G^T W G, F), mu ascending
+  ISR_CUDA(cudaMemcpyAsync(p->d_U.p, p->d_InvCov.p, sizeof(double) * nn, cudaMemcpyDeviceToDevice, st));
+  ISR_CUDA(cudaMemcpyAsync(p->d_tmp.p, p->d_F.p, sizeof(double) * nn, cudaMemcpyDeviceToDevice, st));
+  ISR_TRY(sygvd(c, n, p->d_U.p, p->d_tmp.p, p->d_mu.p, p->d_work, p->d_info));
+  p->h_mu.resize(n);
+  ISR_CUDA(cudaMemcpyAsync(p->h_mu.data(), p->d_mu.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  // P = U^T G^T W = U^T (W G)^T ;  W G = diag(err^-2) G = diag(1/err) R
+  scale_rows(st, n, p->d_R.p, p->d_werr.p, 1, p->d_tmp.p);
+  ISR_TRY(gemm(c, true, true, n, p->d_U.p, p->d_tmp.p, p->d_P.p));
+  // FU = F U  (U^-1 = U^T F = (F U)^T)
+  ISR_TRY(gemm(c, false, false, n, p->d_F.p, p->d_U.p, p->d_FU.p));
+  ISR_CUDA(cudaStreamSynchronize(st));
+  for (int m = 0; m < n; ++m)
+    if (!(p->h_mu[m] > 0.0)) {
+      set_error("isr_tikhonov_prepare: generalised eigenvalue mu[%d] = %g is not positive", m, p->h_mu[m]);
+      return ISR_ENUMERIC;
+    }
+  p->tik_ready = true;
+  p->tik_deriv = deriv_reg;
+  return ISR_OK;
+}
+
+// One thread per lambda: the L-curve functionals (see the header comment).
+__global__ void lcurve_kernel(int n, int64_t L, const double* __restrict__ lam, const double* __restrict__ mu,
+                              const double* __restrict__ c, double* __restrict__ eqn, double* __restrict__ smooth,
+                              double* __restrict__ curv, double* __restrict__ dcurv, double* __restrict__ Z) {
+  const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= L) return;
+  const double la = lam[l];
+  double x = 0, y = 0, s3 = 0, s4 = 0;
+  for (int m = 0; m < n; ++m) {
+    const double cm = c[m], d = mu[m] + la, id = 1.0 / d, c2 = cm * cm;
+    const double q2 = c2 * id * id;
+    y += q2;
+    x += q2 * (la * la / mu[m]);
+    s3 += q2 * id;
+    s4 += q2 * id * id;
+    if (Z) Z[(size_t)l * n + m] = cm * id;   // row-major L x N: coefficients of b_lambda in the U basis
+  }
+  const double dksi = -2.0 * s3, d2ksi = 6.0 * s4;
+  const double q = 1.0 + la * la;
+  if (eqn) eqn[l] = x;
+  if (smooth) smooth[l] = y;
+  if (curv) curv[l] = -fabs(1.0 / dksi / pow(q, 1.5));                                         // :115-119
+  if (dcurv) dcurv[l] = -d2ksi * (1.0 / (dksi * dksi)) * pow(q, -1.5) + -3.0 * la / dksi * pow(q, -2.5);  // :121-128
+}
+
+int tikhonov_scan(isr_problem* p, int64_t L, const double* lambda, const double* vcs, double* eqn, double* smooth,
+                  double* curv, double* dcurv, double* bcs_out) {
+  if (!p->tik_ready) { set_error("isr_tikhonov_scan: call isr_tikhonov_prepare first"); return ISR_ESTATE; }
+  if (L <= 0) return ISR_OK;
+  const int n = p->n;
+  isr_ctx* c = p->ctx;
+  cudaStream_t st = c->stream;
+  DevBuf<double> dlam, dv, dc, dout, dZ, dB;
+  ISR_TRY(dlam.reserve(L)); ISR_TRY(dv.reserve(n)); ISR_TRY(dc.reserve(n)); ISR_TRY(dout.reserve(4 * L));
+  ISR_CUDA(cudaMemcpyAsync(dlam.p, lambda, sizeof(double) * L, cudaMemcpyHostToDevice, st));
+  ISR_CUDA(cudaMemcpyAsync(dv.p, vcs, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  ISR_TRY(gemv(c, false, n, p->d_P.p, dv.p, dc.p));
+  if (bcs_out) { ISR_TRY(dZ.reserve((size_t)L * n)); ISR_TRY(dB.reserve((size_t)L * n)); }
+  lcurve_kernel<<<(unsigned)((L + 127) / 128), 128, 0, st>>>(n, L, dlam.p, p->d_mu.p, dc.p, dout.p, dout.p + L,
+                                                              dout.p + 2 * L, dout.p + 3 * L, bcs_out ? dZ.p : nullptr);
+  ISR_CUDA(cudaGetLastError());
+  if (bcs_out) {
+    // B (row-major L x N) = Z U^T  <=>  column-major (N x L): B^T = U Z^T
+    const double one = 1.0, zero = 0.0;
+    ISR_CUBLAS(cublasDgemm(c->blas, CUBLAS_OP_N, CUBLAS_OP_N, n, (int)L, n, &one, p->d_U.p, n, dZ.p, n, &zero, dB.p, n));
+    ISR_CUDA(cudaMemcpyAsync(bcs_out, dB.p, sizeof(double) * L * n, cudaMemcpyDeviceToHost, st));
+  }
+  if (eqn) ISR_CUDA(cudaMemcpyAsync(eqn, dout.p, sizeof(double) * L, cudaMemcpyDeviceToHost, st));
+  if (smooth) ISR_CUDA(cudaMemcpyAsync(smooth, dout.p + L, sizeof(double) * L, cudaMemcpyDeviceToHost, st));
+  if (curv) ISR_CUDA(cudaMemcpyAsync(curv, dout.p + 2 * L, sizeof(double) * L, cudaMemcpyDeviceToHost, st));
+  if (dcurv) ISR_CUDA(cudaMemcpyAsync(dcurv, dout.p + 3 * L, sizeof(double) * L, cudaMemcpyDeviceToHost, st));
+  ISR_CUDA(cudaStreamSynchronize(st));
+  return ISR_OK;
+}
+
+// out(i, m) = U(i, m) * f(mu_m, lambda)   column-major; mode 0: 1/(mu+la), 1: sqrt(mu)/(mu+la)
+__global__ void scale_cols_mu_kernel(int n, const double* __restrict__ U, const double* __restrict__ mu, double la,
+                                     int mode, double* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * n) return;
+  const int m = idx / n;
+  const double d = mu[m] + la;
+  out[idx] = U[idx] * (mode == 0 ? 1.0 / d : sqrt(mu[m]) / d);
+}
+// Rop[m][i] (row-major, ld) = ((mu_m + la)/sqrt(mu_m)) * FU(i, m)
+__global__ void tik_rop_kernel(int n, int ld, const double* __restrict__ FU, const double* __restrict__ mu, double la,
+                               double* __restrict__ R) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * ld) return;
+  const int m = idx / ld, i = idx % ld;
+  R[idx] = i < n ? (mu[m] + la) / sqrt(mu[m]) * FU[(size_t)i + (size_t)n * m] : 0.0;
+}
+
+// A+ = U diag(1/(mu+la)) P (column-major into out)
+static int tik_operator(isr_problem* p, double la, double* out) {
+  const int n = p->n;
+  scale_cols_mu_kernel<<<(n * n + 255) / 256, 256, 0, p->ctx->stream>>>(n, p->d_U.p, p->d_mu.p, la, 0, p->d_tmp.p);
+  return gemm(p->ctx, false, false, n, p->d_tmp.p, p->d_P.p, out);
+}
+
+int tikhonov_solve(isr_problem* p, double la, const double* vcs, double* bcs_out, double* cov_out) {
+  if (!p->tik_ready) { set_error("isr_tikhonov_solve: call isr_tikhonov_prepare first"); return ISR_ESTATE; }
+  const int n = p->n;
+  const size_t nn = (size_t)n * n;
+  isr_ctx* c = p->ctx;
+  cudaStream_t st = c->stream;
+  ISR_TRY(p->d_tmp.reserve(nn));
+  ISR_TRY(p->d_tmp2.reserve(nn));
+  ISR_TRY(p->d_b0.reserve(n));
+  ISR_TRY(p->d_stat.reserve((size_t)4 * n));
+  ISR_CUDA(cudaMemcpyAsync(p->d_b0.p, vcs, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  ISR_TRY(tik_operator(p, la, p->d_tmp2.p));
+  ISR_TRY(gemv(c, false, n, p->d_tmp2.p, p->d_b0.p, p->d_stat.p));
+  ISR_CUDA(cudaMemcpyAsync(bcs_out, p->d_stat.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  if (cov_out) {
+    scale_cols_mu_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(n, p->d_U.p, p->d_mu.p, la, 1, p->d_tmp.p);
+    ISR_TRY(gemm(c, false, true, n, p->d_tmp.p, p->d_tmp.p, p->d_tmp2.p));
+    ISR_CUDA(cudaMemcpyAsync(cov_out, p->d_tmp2.p, sizeof(double) * nn, cudaMemcpyDeviceToHost, st));
+  }
+  ISR_CUDA(cudaStreamSynchronize(st));
+  return ISR_OK;
+}
+
+int tikhonov_select(isr_problem* p, double la) {
+  if (!p->tik_ready) { set_error("isr_tikhonov_select: call isr_tikhonov_prepare first"); return ISR_ESTATE; }
+  const int n = p->n, ld = (n + 1) & ~1;
+  cudaStream_t st = p->ctx->stream;
+  ISR_TRY(p->d_tmp2.reserve((size_t)n * n));
+  ISR_TRY(tik_operator(p, la, p->d_tmp2.p));
+  colmajor_to_rowmajor(st, n, p->d_tmp2.p, nullptr, 0, p->d_Sop.p, ld);
+  tik_rop_kernel<<<(n * ld + 255) / 256, 256, 0, st>>>(n, ld, p->d_FU.p, p->d_mu.p, la, p->d_Rop.p);
+  ISR_CUDA(cudaGetLastError());
+  p->solver_selected = true;
+  return ISR_OK;
+}
+
+// Pe[m][i] (row-major, ld) = P(m, i) / sqrt(mu_m) ;  gs[m] = g_m sqrt(mu_m) ; f[m] = g_m / sqrt(mu_m)
+__global__ void tik_proj_kernel(int n, int ld, const double* __restrict__ P, const double* __restrict__ mu,
+                                const double* __restrict__ g, double* __restrict__ Pe, double* __restrict__ gs,
+                                double* __restrict__ f) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n * ld) {
+    const int m = idx / ld, i = idx % ld;
+    Pe[idx] = i < n ? P[(size_t)m + (size_t)n * i] / sqrt(mu[m]) : 0.0;
+  }
+  if (idx < n) {
+    const double r = sqrt(mu[idx]);
+    gs[idx] = g[idx] * r;
+    f[idx] = g[idx] / r;
+  }
+}
+
+// chi2[l][k] = sum_m (e[k][m] - lambda_l f[m])^2.  One CTA: 32 toys (e tile in shared memory, odd
+// leading dimension => conflict-free), 8 warps striding over lambda, 4 lambdas per thread per sweep.
+constexpr int kScanToys = 32, kScanLam = 4;
+__global__ void __launch_bounds__(256) lambda_scan_kernel(int n, int ld, int64_t T, const double* __restrict__ E,
+                                                           const double* __restrict__ f, int64_t L,
+                                                           const double* __restrict__ lam, double* __restrict__ chi2,
+                                                           int64_t stride) {
+  extern __shared__ double sh[];
+  const int lds = n | 1;
+  double* se = sh;                    // [32][lds]
+  double* sf = sh + kScanToys * lds;  // [n]
+  const int64_t t0 = (int64_t)blockIdx.x * kScanToys;
+  for (int q = threadIdx.x; q < kScanToys * n; q += blockDim.x) {
+    const int r = q / n, m = q % n;
+    se[r * lds + m] = (t0 + r < T) ? E[(t0 + r) * ld + m] : 0.0;
+  }
+  for (int q = threadIdx.x; q < n; q += blockDim.x) sf[q] = f[q];
+  __syncthreads();
+  const int t = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const double* e = se + t * lds;
+  for (int64_t l0 = (int64_t)w * kScanLam; l0 < L; l0 += 8 * kScanLam) {
+    double la[kScanLam], acc[kScanLam];
+#pragma unroll
+    for (int q = 0; q < kScanLam; ++q) { la[q] = (l0 + q < L) ? lam[l0 + q] : 0.0; acc[q] = 0.0; }
+    for (int m = 0; m < n; ++m) {
+      const double ev = e[m], fv = sf[m];
+#pragma unroll
+      for (int q = 0; q < kScanLam; ++q) {
+        const double d = fma(-la[q], fv, ev);
+        acc[q] = fma(d, d, acc[q]);
+      }
+    }
+    if (t0 + t < T) {
+#pragma unroll
+      for (int q = 0; q < kScanLam; ++q)
+        if (l0 + q < L) chi2[(size_t)(l0 + q) * stride + t0 + t] = acc[q];
+    }
+  }
+}
+
+int tikhonov_toy_scan_device(isr_problem* p, int64_t L, const double* lambda, int64_t T, const double* V_dev,
+                             const double* bcs0, double* chi2_dev) {
+  if (!p->tik_ready) { set_error("isr_tikhonov_toy_scan: call isr_tikhonov_prepare first"); return ISR_ESTATE; }
+  if (L <= 0 || T <= 0) return ISR_OK;
+  const int n = p->n, ld = (n + 1) & ~1;
+  isr_ctx* c = p->ctx;
+  cudaStream_t st = c->stream;
+  DevBuf<double> dlam, db0, dg;
+  ISR_TRY(dlam.reserve(L)); ISR_TRY(db0.reserve(n)); ISR_TRY(dg.reserve(3 * (size_t)n));
+  ISR_CUDA(cudaMemcpyAsync(dlam.p, lambda, sizeof(double) * L, cudaMemcpyHostToDevice, st));
+  ISR_CUDA(cudaMemcpyAsync(db0.p, bcs0, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  ISR_TRY(gemv(c, true, n, p->d_FU.p, db0.p, dg.p));               // g = (F U)^T b0 = U^T F b0
+  // temporarily route the tile kernel: Sop <- Pe, "b0" <- g sqrt(mu); D then holds e
+  DevBuf<double> dPe;
+  ISR_TRY(dPe.reserve((size_t)n * ld));
+  tik_proj_kernel<<<(n * ld + 255) / 256, 256, 0, st>>>(n, ld, p->d_P.p, p->d_mu.p, dg.p, dPe.p, dg.p + n, dg.p + 2 * n);
+  ISR_CUDA(cudaGetLastError());
+  const size_t smem = sizeof(double) * ((size_t)kScanToys * (n | 1) + n);
+  ISR_CUDA(cudaFuncSetAttribute(lambda_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // chunk so that E (T x ld) stays modest; the scan reads E once per chunk
+  const int64_t Tc = std::min<int64_t>(T, 1 << 18);
+  ISR_TRY(p->d_E.reserve((size_t)Tc * ld));
+  for (int64_t t0 = 0; t0 < T; t0 += Tc) {
+    const int64_t tc = std::min<int64_t>(Tc, T - t0);
+    ISR_TRY(project_device(p, tc, V_dev + t0 * n, dPe.p, dg.p + n, p->d_E.p));
+    // output rows (one per lambda) have the full stride T; this chunk starts at column t0
+    lambda_scan_kernel<<<(unsigned)((tc + kScanToys - 1) / kScanToys), 256, smem, st>>>(
+        n, ld, tc, p->d_E.p, dg.p + 2 * n, L, dlam.p, chi2_dev + t0, T);
+  }
+  ISR_CUDA(cudaGetLastError());
+  ISR_CUDA(cudaStreamSynchronize(st));  // dlam / db0 / dg / dPe go out of scope
+  return ISR_OK;
+}
+
+// ---- TSVD (src/ISRSolverTSVD.cpp:53-74) -----------------------------------------------------------
+// z_m = (U^T v)_m / sigma_m for m in [first, first + count), 0 otherwise
+__global__ void tsvd_filter_kernel(int n, int first, int count, const double* __restrict__ sv, double* __restrict__ z) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n) return;
+  z[m] = (m >= first && m < first + count) ? z[m] / sv[m] : 0.0;
+}
+// out(i, m) = U(i, m) * (m in window ? scale_m : 0), column-major; mode 0: 1/sigma, mode 1: sigma
+__global__ void tsvd_window_kernel(int n, int first, int count, const double* __restrict__ U, const double* __restrict__ sv,
+                                   int mode, double* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * n) return;
+  const int m = idx / n;
+  const bool in = m >= first && m < first + count;
+  out[idx] = in ? U[idx] * (mode == 0 ? 1.0 / sv[m] : sv[m]) : 0.0;
+}
+
+static int tsvd_window(isr_problem* p, int k, int keep_one, int* first, int* count) {
+  if (k < 1 || k > p->n) { set_error("TSVD: upper index %d out of range [1, %d]", k, p->n); return ISR_EINVAL; }
+  *first = keep_one ? k - 1 : 0;   // :63-68
+  *count = keep_one ? 1 : k;
+  return ISR_OK;
+}
+
+int tsvd_solve(isr_problem* p, int k, int keep_one, const double* vcs, const double* vcs_err, double* bcs_out,
+               double* cov_out) {
+  int first, count;
+  ISR_TRY(tsvd_window(p, k, keep_one, &first, &count));
+  ISR_TRY(ensure_svd(p));
+  const int n = p->n;
+  isr_ctx* c = p->ctx;
+  cudaStream_t st = c->stream;
+  ISR_TRY(p->d_b0.reserve(n));
+  ISR_TRY(p->d_stat.reserve((size_t)4 * n));
+  ISR_CUDA(cudaMemcpyAsync(p->d_b0.p, vcs, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  // b = V_s Sigma_s^-1 U_s^T v  (minimum-norm least squares of K b = v, what COD(K).solve returns)
+  ISR_TRY(gemv(c, true, n, p->d_svU.p, p->d_b0.p, p->d_stat.p));
+  tsvd_filter_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, first, count, p->d_sv.p, p->d_stat.p);
+  ISR_TRY(gemv(c, true, n, p->d_svVT.p, p->d_stat.p, p->d_stat.p + n));
+  ISR_CUDA(cudaMemcpyAsync(bcs_out, p->d_stat.p + n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  ISR_CUDA(cudaStreamSynchronize(st));
+  if (cov_out) {
+    if (keep_one || k != n) {
+      set_error("isr_tsvd_solve: the covariance (K^T W K)^-1 is singular for a truncated K; request it only for k == N");
+      return ISR_ENUMERIC;
+    }
+    if (!vcs_err) { set_error("isr_tsvd_solve: vcs_err needed for the covariance"); return ISR_EINVAL; }
+    ISR_TRY(factor(p, vcs_err));
+    ISR_CUDA(cudaMemcpyAsync(cov_out, p->d_Cov.p, sizeof(double) * n * n, cudaMemcpyDeviceToHost, st));
+    ISR_CUDA(cudaStreamSynchronize(st));
+  }
+  return ISR_OK;
+}
+
+int tsvd_select(isr_problem* p, int k, int keep_one, const double* vcs_err) {
+  int first, count;
+  ISR_TRY(tsvd_window(p, k, keep_one, &first, &count));
+  ISR_TRY(ensure_svd(p));
+  const int n = p->n, ld = (n + 1) & ~1;
+  const size_t nn = (size_t)n * n;
+  isr_ctx* c = p->ctx;
+  cudaStream_t st = c->stream;
+  ISR_TRY(p->d_tmp.reserve(nn));
+  ISR_TRY(p->d_tmp2.reserve(nn));
+  ISR_TRY(p->d_werr.reserve(n));
+  ISR_TRY(p->d_Sop.reserve((size_t)n * ld));
+  ISR_TRY(p->d_Rop.reserve((size_t)n * ld));
+  ISR_CUDA(cudaMemcpyAsync(p->d_werr.p, vcs_err, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  // Sop = K^+ = V_s Sigma_s^-1 U_s^T = VT^T (U_window / sigma)^T
+  tsvd_window_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(n, first, count, p->d_svU.p, p->d_sv.p, 0, p->d_tmp.p);
+  ISR_TRY(gemm(c, true, true, n, p->d_svVT.p, p->d_tmp.p, p->d_tmp2.p));
+  colmajor_to_rowmajor(st, n, p->d_tmp2.p, nullptr, 0, p->d_Sop.p, ld);
+  // Rop = W^(1/2) K = diag(1/err) U_window Sigma VT   (chi2 = d^T K^T W K d)
+  tsvd_window_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(n, first, count, p->d_svU.p, p->d_sv.p, 1, p->d_tmp.p);
+  ISR_TRY(gemm(c, false, false, n, p->d_tmp.p, p->d_svVT.p, p->d_tmp2.p));
+  colmajor_to_rowmajor(st, n, p->d_tmp2.p, p->d_werr.p, 1, p->d_Rop.p, ld);
+  ISR_CUDA(cudaGetLastError());
+  p->factored = false;   // Sop/Rop no longer belong to the SLE factorisation
+  p->solver_selected = true;
+  return ISR_OK;
+}
+
+}  // namespace isr
