@@ -1,0 +1,339 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the ISRSolver hot path on B200.
+
+Metric (BASELINE.json): toy SLE solves/s for the N = 200 chi2 test, with the matrix-assembly time beside
+it.  One "step" is one complete chi2 test on one batch of synthetic input:
+    assemble the N x N integral-operator matrix  ->  factor  ->  T toys: b_k = G^-1 v_k, chi2_k
+    ->  (N > 1: one all_gather of the packed per-rank results)  ->  min/max + TH1F(128) histogram.
+Workload: N = 200 energy points on [1.18, 2.00] GeV, threshold 0.827 GeV, interpolation
+[[linear, 0, 0], [cubic, 1, N-1]] (dense G), efficiency 1, Breit-Wigner Born model, 5 % errors,
+T = 2^20 toys PER GPU (weak scaling), toys generated on the host side of the API contract
+(V = vcs + err * z) -- for the device-resident `value` they are produced once on the device before the
+timed region; for `e2e` they sit in pinned host memory and are copied inside the timed region.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--toys T] [--n N]
+For N > 1 launch through torch.distributed.run (one rank per GPU, NCCL).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+E_MIN, E_MAX, E_THR = 1.18, 2.00, 0.827
+BW_M, BW_G, BW_S0 = 1.50, 0.25, 4.0
+FP64_PEAK_TFLOPS = 37.1      # measured DMMA peak on this pool's B200 (profiles/fp64_peaks_r01.json)
+
+
+def bw_born(e):
+    """Relativistic Breit-Wigner x phase space: the synthetic Born cross section."""
+    e = np.asarray(e, dtype=np.float64)
+    ps = np.clip(1.0 - E_THR ** 2 / e ** 2, 0.0, None)
+    return BW_S0 * BW_M ** 2 * BW_G ** 2 / ((e * e - BW_M ** 2) ** 2 + BW_M ** 2 * BW_G ** 2) * ps ** 1.5
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        rows = [r for r in self.rows if len(r) >= 8]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in rows if r[0].replace(".", "").isdigit())
+        reasons = set()
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(rows[0][1]) if rows[0][1].replace(".", "").isdigit() else None,
+                "power_w_max": max((float(r[2]) for r in rows if r[2].replace(".", "").isdigit()), default=None),
+                "samples": len(rows), "reasons": sorted(reasons)}
+
+
+# =====================================================================================================
+# reference arm: the reference's own CPU algorithm (oracle port; the reference cannot be built here)
+# =====================================================================================================
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import isr_oracle as O
+    n = args.n
+    cores = os.cpu_count() or 1
+    ecm = np.linspace(E_MIN, E_MAX, n)
+    settings = [(False, 0, 0), (True, 1, n - 1)]
+    interp = O.Interp(ecm, E_THR, settings)
+    # bounded sample of the assembly: a few full rows of the N x N loop with the reference's adaptive quadrature
+    rows = (0, n // 2, n - 1)
+    t0 = time.perf_counter()
+    interp.eval_rows(rows, mode="faithful")
+    asm_row_s = (time.perf_counter() - t0) / len(rows)
+    # the toy loop needs a matrix; the converged back-end on all cores is the quickest way to get the real one
+    G = interp.eval_eq_matrix(mode="converged")
+    bcs0 = bw_born(ecm); vcs = G @ bcs0; err = 0.05 * vcs
+    per_step = args.ref_toys
+    V = O.draw_toys(vcs, err, per_step * (args.steps + args.warmup))
+    for w in range(args.warmup):
+        O.chi2_test_loop(G, V[w * per_step:(w + 1) * per_step], bcs0, err)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        b = (args.warmup + k) * per_step
+        O.chi2_test_loop(G, V[b:b + per_step], bcs0, err)
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    sample = (f"{per_step} toys per step of the faithful per-toy loop (COD solve + G^T W G + inverse every toy, "
+              f"src/Chi2Test.cpp:38-60) at N={n}; assembly sampled on rows {rows}: {asm_row_s * 1e3:.0f} ms/row "
+              f"=> {asm_row_s * n:.1f} s per matrix on 1 core")
+    line = {"impl": "reference", "metric": "toy SLE solves/s (N=200 chi2 test)", "value": value, "unit": "toys/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, world),
+            "cpu_baseline": {"value": value, "unit": "toys/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "toys/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "assembly_ms_cpu_1core_extrapolated": asm_row_s * n * 1e3}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"isrsolver-SLE-chi2-test: N={args.n} points, interp [[linear,0,0],[cubic,1,N-1]], eps=1, "
+                        f"{args.toys} toys per GPU, full matrix assembly + factor + toy batch + histogram per step",
+            "n_points": args.n, "toys_per_gpu": args.toys, "toys_total": args.toys * world,
+            "l2_policy": f"inputs larger than L2 (V = {args.toys * args.n * 8 / 2**20:.0f} MiB per GPU streams through the 126 MB L2 every step)",
+            "parallelism": f"toys sharded over {world} GPU(s), matrix replicated, one all_gather"}
+
+
+# =====================================================================================================
+# B200 arm
+# =====================================================================================================
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from isrsolver_b200 import _lib as L
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = L.load()
+    ctx = C.c_void_p()
+    L.check(lib.isr_ctx_create(local_rank, C.byref(ctx)))
+    stream = torch.cuda.ExternalStream(lib.isr_ctx_stream(ctx), device=dev)
+
+    n, T = args.n, args.toys
+    ecm = np.linspace(E_MIN, E_MAX, n)
+    st = np.ascontiguousarray([[0, 0, 0], [1, 1, n - 1]], dtype=np.int32)
+    prob = C.c_void_p()
+    L.check(lib.isr_problem_create(ctx, n, L.dptr(ecm), E_THR, len(st), L.iptr(st), None, C.byref(prob)))
+    G = np.empty((n, n))
+    L.check(lib.isr_assemble(prob, None, L.dptr(G)))          # also the first-touch allocation of all workspaces
+    G = G.T.copy()
+    bcs0 = bw_born(ecm)
+    vcs = G @ bcs0
+    err = 0.05 * vcs
+    L.check(lib.isr_factor(prob, L.dptr(err)))
+
+    # toys: per-rank stream of the documented generator shape (V = vcs + err * z); device copy for `value`,
+    # pinned host copy for `e2e`
+    gen = torch.Generator(device=dev); gen.manual_seed(20211103 + rank)
+    z = torch.randn((T, n), dtype=torch.float64, device=dev, generator=gen)
+    Vd = torch.from_numpy(vcs).to(dev)[None, :] + torch.from_numpy(err).to(dev)[None, :] * z
+    del z
+    Vh = torch.empty((T, n), dtype=torch.float64, pin_memory=True)
+    Vh.copy_(Vd)
+    gathered = torch.empty((world, T + 4 * n), dtype=torch.float64, device=dev)   # packed per-rank buffer
+    mine = gathered[rank] if world == 1 else torch.empty(T + 4 * n, dtype=torch.float64, device=dev)
+    chi2_host = np.empty(T)
+    sumb_host = np.zeros(n)
+    counts = np.zeros(130, dtype=np.uint32)
+    torch.cuda.synchronize()
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    asm_ev, toy_ev = [], []
+
+    def step_device(record):
+        """One chi2 test with V resident in HBM."""
+        with torch.cuda.stream(stream):
+            a0, a1, t0, t1 = ev(), ev(), ev(), ev()
+            a0.record(stream)
+            L.check(lib.isr_assemble(prob, None, None))
+            a1.record(stream)
+            L.check(lib.isr_factor(prob, L.dptr(err)))
+            mine[T:].zero_()
+            t0.record(stream)
+            L.check(lib.isr_toy_batch_dev(prob, T, Vd.data_ptr(), L.dptr(bcs0), mine.data_ptr(),
+                                          mine[T:].data_ptr(), None, None, None))
+            t1.record(stream)
+            if world > 1:
+                stream.synchronize()
+                dist.all_gather_into_tensor(gathered.view(-1), mine)      # the single collective
+                torch.cuda.current_stream().synchronize()
+            lo, hi = np.inf, -np.inf
+            for r in range(world):
+                a, b = C.c_double(), C.c_double()
+                L.check(lib.isr_minmax_dev(ctx, T, gathered[r].data_ptr(), C.byref(a), C.byref(b)))
+                lo, hi = min(lo, a.value), max(hi, b.value)
+            tot = np.zeros(130, dtype=np.uint64)
+            for r in range(world):
+                L.check(lib.isr_histogram_dev(ctx, T, gathered[r].data_ptr(), 128, lo, hi, L.uptr(counts)))
+                tot += counts
+            if record:
+                asm_ev.append((a0, a1)); toy_ev.append((t0, t1))
+            return tot
+
+    def step_e2e():
+        """The same test through the host-buffer C ABI: H2D of V and D2H of chi2 inside the call."""
+        L.check(lib.isr_assemble(prob, None, None))
+        L.check(lib.isr_factor(prob, L.dptr(err)))
+        L.check(lib.isr_toy_batch(prob, T, C.cast(Vh.data_ptr(), C.POINTER(C.c_double)), L.dptr(bcs0), L.dptr(chi2_host),
+                                  L.dptr(sumb_host), None, None, None))
+        lo, hi = C.c_double(), C.c_double()
+        L.check(lib.isr_chi2_histogram(ctx, T, L.dptr(chi2_host), 128, C.byref(lo), C.byref(hi), L.uptr(counts)))
+        return counts
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, record=False):
+        barrier()
+        e0, e1 = ev(), ev()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+        for _ in range(steps):
+            fn(record) if record is not None else fn()
+        with torch.cuda.stream(stream):
+            e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(args.warmup):
+        hist = step_device(False)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start(); time.sleep(0.3)
+    launches0 = lib.isr_launch_count()
+    ms_total = timed(step_device, args.steps, record=True)
+    launches = lib.isr_launch_count() - launches0
+    clocks = sampler.finish() if sampler else None
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    ms_e2e = timed(lambda: step_e2e(), args.steps, record=None)
+
+    assert int(hist.sum()) == T * world, "histogram lost entries"
+    if rank != 0:
+        return
+    ms_step = ms_total / args.steps
+    value = T * world / (ms_step * 1e-3)
+    asm_ms = float(np.mean([a.elapsed_time(b) for a, b in asm_ev]))
+    toy_ms = float(np.mean([a.elapsed_time(b) for a, b in toy_ev]))
+    flops = 4.0 * n * n * T          # 2N^2 for b = G^-1 v, 2N^2 for |W^(1/2) G (b - b0)|^2
+    achieved = flops / (toy_ms * 1e-3) * 1e-12
+    npan, nnode = C.c_int64(), C.c_int64()
+    L.check(lib.isr_assemble_stats(prob, C.byref(npan), C.byref(nnode)))
+    line = {
+        "metric": "toy SLE solves/s (N=200 chi2 test)", "value": value, "unit": "toys/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, world),
+        "assembly_ms": asm_ms, "toy_batch_ms": toy_ms,
+        "assembly": {"panels": npan.value, "nodes": nnode.value, "ms": asm_ms},
+        "roofline": {"bound": "tensor", "kernel": "toy_gemm_kernel (DMMA m8n8k4 f64; two passes per chunk)",
+                     "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
+                     "traffic": None, "flops_per_toy": 4 * n * n,
+                     "peak_source": "FP64 DMMA probe tools/fp64_peaks.cu -> profiles/fp64_peaks_r01.json "
+                                    "(MEASURED_PEAKS.json carries no FP64 figure; bf16 peak does not apply to an FP64 kernel)"},
+        "e2e": {"value": T * world / (ms_e2e / args.steps * 1e-3), "unit": "toys/s",
+                "h2d_bytes_per_step": T * n * 8, "d2h_bytes_per_step": T * 8 + n * 8 + 130 * 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(n, G, bcs0, vcs, err)
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(n, G, bcs0, vcs, err):
+    """The oracle (port of the reference's per-toy loop) on the box's host cores, bounded sample."""
+    from oracle import isr_oracle as O
+    V = O.draw_toys(vcs, err, 24)
+    t0 = time.perf_counter(); O.chi2_test_loop(G, V[:8], bcs0, err); per = (time.perf_counter() - t0) / 8
+    m = int(max(16, min(400, 12.0 / per)))
+    V = O.draw_toys(vcs, err, m)
+    t0 = time.perf_counter(); O.chi2_test_loop(G, V, bcs0, err); dt = time.perf_counter() - t0
+    Vf = O.draw_toys(vcs, err, 100000)
+    t1 = time.perf_counter(); O.chi2_test_fair(G, Vf, bcs0, err); dtf = time.perf_counter() - t1
+    return {"value": m / dt, "unit": "toys/s", "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": f"{m} toys of the faithful per-toy loop (COD + G^T W G + inverse per toy, src/Chi2Test.cpp:38-60) at N={n}, NumPy/LAPACK on all host cores",
+            "fair_value": 100000 / dtf,
+            "fair_sample": "100000 toys with the redundancy removed (factor once, two GEMMs; BASELINE.md B-fair), NumPy/OpenBLAS on all host cores"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=200)
+    ap.add_argument("--toys", type=int, default=1 << 20, help="toys per GPU")
+    ap.add_argument("--ref-toys", type=int, default=48, help="toys per step of the reference arm (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    elif args.gpus > 1:
+        raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    try:
+        run_b200(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

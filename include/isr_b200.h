@@ -57,6 +57,8 @@ const char* isr_last_error(void);
 /* cudaStream_t used by all launches of this context (as void*), for event timing by the caller. */
 void* isr_ctx_stream(isr_ctx* ctx);
 int isr_ctx_synchronize(isr_ctx* ctx);
+/* Number of kernels of THIS library launched by this process so far (diagnostic; bench.py's gpu_launches). */
+int64_t isr_launch_count(void);
 
 /* ---- problem ---------------------------------------------------------------------------------- */
 /* Replaces BaseISRSolver(n, energy, ...) + Interpolator(settings, ecm, threshold)

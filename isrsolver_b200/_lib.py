@@ -48,6 +48,7 @@ SIGNATURES = {
     "isr_last_error": (C.c_char_p, []),
     "isr_ctx_stream": (_vp, [_vp]),
     "isr_ctx_synchronize": (C.c_int, [_vp]),
+    "isr_launch_count": (_i64, []),
     "isr_problem_create": (C.c_int, [_vp, C.c_int, _dp, C.c_double, C.c_int, _ip, C.POINTER(EpsDesc), C.POINTER(_vp)]),
     "isr_problem_destroy": (None, [_vp]),
     "isr_problem_set_ranges": (C.c_int, [_vp, C.c_int, _ip]),

@@ -686,18 +686,18 @@ int assemble(isr_problem* p, const double* ecm_err) {
   ISR_TRY(p->d_M.reserve((size_t)n * n * 4));
   ISR_TRY(p->d_G.reserve((size_t)n * n));
 
-  row_setup_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, p->d_ext.p, p->d_row.p);
-  count_kernel<<<(nitems + 127) / 128, 128, 0, st>>>(nitems, p->d_row.p, p->eps, p->d_ext.p, p->d_cnt.p);
-  scan_kernel<<<1, 1024, 0, st>>>(nitems, p->d_cnt.p, p->d_off.p);
+  row_setup_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, p->d_ext.p, p->d_row.p); ISR_COUNT_LAUNCH();
+  count_kernel<<<(nitems + 127) / 128, 128, 0, st>>>(nitems, p->d_row.p, p->eps, p->d_ext.p, p->d_cnt.p); ISR_COUNT_LAUNCH();
+  scan_kernel<<<1, 1024, 0, st>>>(nitems, p->d_cnt.p, p->d_off.p); ISR_COUNT_LAUNCH();
   fill_kernel<<<(nitems + 127) / 128, 128, 0, st>>>(nitems, p->d_row.p, p->eps, p->d_ext.p, p->d_off.p,
-                                                      p->d_pa.p, p->d_pb.p, p->d_peps.p, p->d_pitem.p, p->d_pkind.p);
+                                                      p->d_pa.p, p->d_pb.p, p->d_peps.p, p->d_pitem.p, p->d_pkind.p); ISR_COUNT_LAUNCH();
   const int eval_blocks = p->ctx->sm_count * 8;
   eval_kernel<<<eval_blocks, kEvalThreads, 0, st>>>(p->d_off.p + nitems, p->d_row.p, p->d_ext.p, p->d_invh.p,
                                                      p->d_pa.p, p->d_pb.p, p->d_peps.p, p->d_pitem.p,
-                                                     p->d_pkind.p, p->d_pm.p);
-  reduce_kernel<<<(n * n + 127) / 128, 128, 0, st>>>(n, p->d_off.p, p->d_pm.p, p->d_M.p);
+                                                     p->d_pkind.p, p->d_pm.p); ISR_COUNT_LAUNCH();
+  reduce_kernel<<<(n * n + 127) / 128, 128, 0, st>>>(n, p->d_off.p, p->d_pm.p, p->d_M.p); ISR_COUNT_LAUNCH();
   dim3 cgrid((n + kCtCols - 1) / kCtCols, (n + kCtRows - 1) / kCtRows);
-  contract_kernel<<<cgrid, 256, 0, st>>>(n, p->d_M.p, p->d_Ct.p, p->d_klo.p, p->d_khi.p, p->d_G.p);
+  contract_kernel<<<cgrid, 256, 0, st>>>(n, p->d_M.p, p->d_Ct.p, p->d_klo.p, p->d_khi.p, p->d_G.p); ISR_COUNT_LAUNCH();
   if (ecm_err) {
     for (int i = 0; i < n; ++i)
       if (!(ecm_err[i] > 0.0)) {
@@ -708,9 +708,9 @@ int assemble(isr_problem* p, const double* ecm_err) {
     ISR_TRY(p->d_S.reserve((size_t)n * n));
     ISR_TRY(p->d_tmp.reserve((size_t)n * n));
     ISR_CUDA(cudaMemcpyAsync(p->d_sigE.p, ecm_err, sizeof(double) * n, cudaMemcpyHostToDevice, st));
-    spread_kernel<<<(n * n + 127) / 128, 128, 0, st>>>(n, p->d_ext.p, p->d_invh.p, p->d_Ct.p, p->d_sigE.p, p->d_S.p);
+    spread_kernel<<<(n * n + 127) / 128, 128, 0, st>>>(n, p->d_ext.p, p->d_invh.p, p->d_Ct.p, p->d_sigE.p, p->d_S.p); ISR_COUNT_LAUNCH();
     dim3 g((n + 31) / 32, (n + 31) / 32);
-    gemm_nn_kernel<<<g, 256, 0, st>>>(n, p->d_S.p, p->d_G.p, p->d_tmp.p);
+    gemm_nn_kernel<<<g, 256, 0, st>>>(n, p->d_S.p, p->d_G.p, p->d_tmp.p); ISR_COUNT_LAUNCH();
     ISR_CUDA(cudaMemcpyAsync(p->d_G.p, p->d_tmp.p, sizeof(double) * n * n, cudaMemcpyDeviceToDevice, st));
   }
   ISR_CUDA(cudaGetLastError());
@@ -730,7 +730,7 @@ __global__ void kf_plain_kernel(int64_t n, const double* __restrict__ x, const d
   if (q < n) out[q] = kf_plain(x[q], s[q]);
 }
 void launch_kf_plain(int64_t n, const double* x, const double* s, double* out, cudaStream_t st) {
-  kf_plain_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, x, s, out);
+  kf_plain_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, x, s, out); ISR_COUNT_LAUNCH();
 }
 
 __global__ void basis_eval_kernel(int n, const double* __restrict__ ext, const double* __restrict__ invh,
@@ -741,7 +741,7 @@ __global__ void basis_eval_kernel(int n, const double* __restrict__ ext, const d
 }
 void launch_basis_eval(const isr_problem* p, int64_t m, const int* js, const double* es, int deriv, double* out) {
   basis_eval_kernel<<<(unsigned)((m + 255) / 256), 256, 0, p->ctx->stream>>>(p->n, p->d_ext.p, p->d_invh.p,
-                                                                             p->d_Ct.p, m, js, es, deriv, out);
+                                                                             p->d_Ct.p, m, js, es, deriv, out); ISR_COUNT_LAUNCH();
 }
 
 // Interpolator::eval (src/Interpolator.cpp:295-323): sum_j y_j basis_j(E); the value at E_max beyond it.
@@ -763,7 +763,7 @@ __global__ void interp_eval_kernel(int n, const double* __restrict__ ext, const 
 }
 void launch_interp_eval(const isr_problem* p, const double* y, int64_t m, const double* es, double* out) {
   interp_eval_kernel<<<(unsigned)((m + 127) / 128), 128, 0, p->ctx->stream>>>(p->n, p->d_ext.p, p->d_invh.p, p->d_Ct.p,
-                                                                               y, m, es, out);
+                                                                               y, m, es, out); ISR_COUNT_LAUNCH();
 }
 
 }  // namespace isr

@@ -52,6 +52,10 @@ const char* get_error();
     if (rc__ != ISR_OK) return rc__; \
   } while (0)
 
+// ---- launch accounting (bench.py reports it as gpu_launches) -----------------------------------------
+extern long long g_launch_count;
+#define ISR_COUNT_LAUNCH() (++isr::g_launch_count)
+
 // ---- physical constants (include/PhysicalConstants.hpp:7,11) -------------------------------------
 constexpr double kAlphaQED = 7.2973525698e-03;
 constexpr double kElectronM = 5.10998928e-04;

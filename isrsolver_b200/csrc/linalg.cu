@@ -27,7 +27,7 @@ __global__ void colmajor_to_rowmajor_kernel(int n, const double* __restrict__ A,
 }
 void colmajor_to_rowmajor(cudaStream_t st, int n, const double* A, const double* rowscale, int invert_scale,
                           double* out, int ld) {
-  colmajor_to_rowmajor_kernel<<<(n * ld + 255) / 256, 256, 0, st>>>(n, A, rowscale, invert_scale, out, ld);
+  colmajor_to_rowmajor_kernel<<<(n * ld + 255) / 256, 256, 0, st>>>(n, A, rowscale, invert_scale, out, ld); ISR_COUNT_LAUNCH();
 }
 
 // B(i,j) = A(i,j) * colscale_j (or / colscale_j), column-major.
@@ -39,7 +39,7 @@ __global__ void scale_cols_kernel(int n, const double* __restrict__ A, const dou
   B[idx] = invert ? A[idx] / s[j] : A[idx] * s[j];
 }
 void scale_cols(cudaStream_t st, int n, const double* A, const double* s, int invert, double* B) {
-  scale_cols_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(n, A, s, invert, B);
+  scale_cols_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(n, A, s, invert, B); ISR_COUNT_LAUNCH();
 }
 // B(i,j) = A(i,j) * rowscale_i (or / rowscale_i), column-major.
 __global__ void scale_rows_kernel(int n, const double* __restrict__ A, const double* __restrict__ s, int invert,
@@ -50,7 +50,7 @@ __global__ void scale_rows_kernel(int n, const double* __restrict__ A, const dou
   B[idx] = invert ? A[idx] / s[i] : A[idx] * s[i];
 }
 void scale_rows(cudaStream_t st, int n, const double* A, const double* s, int invert, double* B) {
-  scale_rows_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(n, A, s, invert, B);
+  scale_rows_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(n, A, s, invert, B); ISR_COUNT_LAUNCH();
 }
 
 int gemm(isr_ctx* c, bool ta, bool tb, int n, const double* A, const double* B, double* C) {
@@ -85,7 +85,7 @@ int lu_inverse(isr_ctx* c, int n, double* A, double* Ainv, DevBuf<double>& work,
   ISR_TRY(info.reserve(1));
   ISR_CUSOLVER(cusolverDnDgetrf(c->solver, n, n, A, n, work.p, ipiv.p, info.p));
   ISR_TRY(check_info(c, info.p, "LU factorisation (getrf)"));
-  set_identity_kernel<<<(n * n + 255) / 256, 256, 0, c->stream>>>(n, Ainv);
+  set_identity_kernel<<<(n * n + 255) / 256, 256, 0, c->stream>>>(n, Ainv); ISR_COUNT_LAUNCH();
   ISR_CUSOLVER(cusolverDnDgetrs(c->solver, CUBLAS_OP_N, n, n, A, n, ipiv.p, Ainv, n, info.p));
   ISR_TRY(check_info(c, info.p, "LU solve (getrs)"));
   return ISR_OK;

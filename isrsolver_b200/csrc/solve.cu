@@ -110,7 +110,7 @@ int minmax_device(isr_ctx* c, int64_t n, const double* v_dev, double* lo, double
   const int blocks = (int)std::min<int64_t>(c->sm_count * 4, (n + 255) / 256);
   DevBuf<double> part;
   ISR_TRY(part.reserve(2 * blocks));
-  minmax_kernel<<<blocks, 256, 0, c->stream>>>(n, v_dev, part.p);
+  minmax_kernel<<<blocks, 256, 0, c->stream>>>(n, v_dev, part.p); ISR_COUNT_LAUNCH();
   std::vector<double> h(2 * blocks);
   ISR_CUDA(cudaMemcpyAsync(h.data(), part.p, sizeof(double) * 2 * blocks, cudaMemcpyDeviceToHost, c->stream));
   ISR_CUDA(cudaStreamSynchronize(c->stream));
@@ -128,7 +128,7 @@ int histogram_device(isr_ctx* c, int64_t n, const double* v_dev, int nbins, doub
   ISR_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(uint32_t) * (nbins + 2), c->stream));
   if (n > 0) {
     const int blocks = (int)std::min<int64_t>(c->sm_count * 4, (n + 255) / 256);
-    hist_kernel<<<blocks, 256, sizeof(uint32_t) * (nbins + 2), c->stream>>>(n, v_dev, nbins, lo, hi, cnt.p);
+    hist_kernel<<<blocks, 256, sizeof(uint32_t) * (nbins + 2), c->stream>>>(n, v_dev, nbins, lo, hi, cnt.p); ISR_COUNT_LAUNCH();
   }
   ISR_CUDA(cudaMemcpyAsync(counts_host, cnt.p, sizeof(uint32_t) * (nbins + 2), cudaMemcpyDeviceToHost, c->stream));
   ISR_CUDA(cudaStreamSynchronize(c->stream));

@@ -82,7 +82,7 @@ int tikhonov_prepare(isr_problem* p, const double* vcs_err, int deriv_reg) {
     DevBuf<double> es;
     ISR_TRY(js.reserve(nn));
     ISR_TRY(es.reserve(nn));
-    deriv_pairs_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, st>>>(n, p->d_ext.p, js.p, es.p);
+    deriv_pairs_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, st>>>(n, p->d_ext.p, js.p, es.p); ISR_COUNT_LAUNCH();
     launch_basis_eval(p, (int64_t)nn, js.p, es.p, 1, p->d_tmp.p);           // tmp = D
     scale_rows(st, n, p->d_tmp.p, p->d_w.p, 0, p->d_tmp2.p);                 // tmp2 = diag(w) D
     ISR_TRY(gemm(c, true, false, n, p->d_tmp.p, p->d_tmp2.p, p->d_F.p));
@@ -154,7 +154,7 @@ int tikhonov_scan(isr_problem* p, int64_t L, const double* lambda, const double*
   ISR_TRY(gemv(c, false, n, p->d_P.p, dv.p, dc.p));
   if (bcs_out) { ISR_TRY(dZ.reserve((size_t)L * n)); ISR_TRY(dB.reserve((size_t)L * n)); }
   lcurve_kernel<<<(unsigned)((L + 127) / 128), 128, 0, st>>>(n, L, dlam.p, p->d_mu.p, dc.p, dout.p, dout.p + L,
-                                                              dout.p + 2 * L, dout.p + 3 * L, bcs_out ? dZ.p : nullptr);
+                                                              dout.p + 2 * L, dout.p + 3 * L, bcs_out ? dZ.p : nullptr); ISR_COUNT_LAUNCH();
   ISR_CUDA(cudaGetLastError());
   if (bcs_out) {
     // B (row-major L x N) = Z U^T  <=>  column-major (N x L): B^T = U Z^T
@@ -191,7 +191,7 @@ __global__ void tik_rop_kernel(int n, int ld, const double* __restrict__ FU, con
 // A+ = U diag(1/(mu+la)) P (column-major into out)
 static int tik_operator(isr_problem* p, double la, double* out) {
   const int n = p->n;
-  scale_cols_mu_kernel<<<(n * n + 255) / 256, 256, 0, p->ctx->stream>>>(n, p->d_U.p, p->d_mu.p, la, 0, p->d_tmp.p);
+  scale_cols_mu_kernel<<<(n * n + 255) / 256, 256, 0, p->ctx->stream>>>(n, p->d_U.p, p->d_mu.p, la, 0, p->d_tmp.p); ISR_COUNT_LAUNCH();
   return gemm(p->ctx, false, false, n, p->d_tmp.p, p->d_P.p, out);
 }
 
@@ -210,7 +210,7 @@ int tikhonov_solve(isr_problem* p, double la, const double* vcs, double* bcs_out
   ISR_TRY(gemv(c, false, n, p->d_tmp2.p, p->d_b0.p, p->d_stat.p));
   ISR_CUDA(cudaMemcpyAsync(bcs_out, p->d_stat.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
   if (cov_out) {
-    scale_cols_mu_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(n, p->d_U.p, p->d_mu.p, la, 1, p->d_tmp.p);
+    scale_cols_mu_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(n, p->d_U.p, p->d_mu.p, la, 1, p->d_tmp.p); ISR_COUNT_LAUNCH();
     ISR_TRY(gemm(c, false, true, n, p->d_tmp.p, p->d_tmp.p, p->d_tmp2.p));
     ISR_CUDA(cudaMemcpyAsync(cov_out, p->d_tmp2.p, sizeof(double) * nn, cudaMemcpyDeviceToHost, st));
   }
@@ -225,7 +225,7 @@ int tikhonov_select(isr_problem* p, double la) {
   ISR_TRY(p->d_tmp2.reserve((size_t)n * n));
   ISR_TRY(tik_operator(p, la, p->d_tmp2.p));
   colmajor_to_rowmajor(st, n, p->d_tmp2.p, nullptr, 0, p->d_Sop.p, ld);
-  tik_rop_kernel<<<(n * ld + 255) / 256, 256, 0, st>>>(n, ld, p->d_FU.p, p->d_mu.p, la, p->d_Rop.p);
+  tik_rop_kernel<<<(n * ld + 255) / 256, 256, 0, st>>>(n, ld, p->d_FU.p, p->d_mu.p, la, p->d_Rop.p); ISR_COUNT_LAUNCH();
   ISR_CUDA(cudaGetLastError());
   p->solver_selected = true;
   return ISR_OK;
@@ -302,7 +302,7 @@ int tikhonov_toy_scan_device(isr_problem* p, int64_t L, const double* lambda, in
   // temporarily route the tile kernel: Sop <- Pe, "b0" <- g sqrt(mu); D then holds e
   DevBuf<double> dPe;
   ISR_TRY(dPe.reserve((size_t)n * ld));
-  tik_proj_kernel<<<(n * ld + 255) / 256, 256, 0, st>>>(n, ld, p->d_P.p, p->d_mu.p, dg.p, dPe.p, dg.p + n, dg.p + 2 * n);
+  tik_proj_kernel<<<(n * ld + 255) / 256, 256, 0, st>>>(n, ld, p->d_P.p, p->d_mu.p, dg.p, dPe.p, dg.p + n, dg.p + 2 * n); ISR_COUNT_LAUNCH();
   ISR_CUDA(cudaGetLastError());
   const size_t smem = sizeof(double) * ((size_t)kScanToys * (n | 1) + n);
   ISR_CUDA(cudaFuncSetAttribute(lambda_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -314,7 +314,7 @@ int tikhonov_toy_scan_device(isr_problem* p, int64_t L, const double* lambda, in
     ISR_TRY(project_device(p, tc, V_dev + t0 * n, dPe.p, dg.p + n, p->d_E.p));
     // output rows (one per lambda) have the full stride T; this chunk starts at column t0
     lambda_scan_kernel<<<(unsigned)((tc + kScanToys - 1) / kScanToys), 256, smem, st>>>(
-        n, ld, tc, p->d_E.p, dg.p + 2 * n, L, dlam.p, chi2_dev + t0, T);
+        n, ld, tc, p->d_E.p, dg.p + 2 * n, L, dlam.p, chi2_dev + t0, T); ISR_COUNT_LAUNCH();
   }
   ISR_CUDA(cudaGetLastError());
   ISR_CUDA(cudaStreamSynchronize(st));  // dlam / db0 / dg / dPe go out of scope
@@ -358,7 +358,7 @@ int tsvd_solve(isr_problem* p, int k, int keep_one, const double* vcs, const dou
   ISR_CUDA(cudaMemcpyAsync(p->d_b0.p, vcs, sizeof(double) * n, cudaMemcpyHostToDevice, st));
   // b = V_s Sigma_s^-1 U_s^T v  (minimum-norm least squares of K b = v, what COD(K).solve returns)
   ISR_TRY(gemv(c, true, n, p->d_svU.p, p->d_b0.p, p->d_stat.p));
-  tsvd_filter_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, first, count, p->d_sv.p, p->d_stat.p);
+  tsvd_filter_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, first, count, p->d_sv.p, p->d_stat.p); ISR_COUNT_LAUNCH();
   ISR_TRY(gemv(c, true, n, p->d_svVT.p, p->d_stat.p, p->d_stat.p + n));
   ISR_CUDA(cudaMemcpyAsync(bcs_out, p->d_stat.p + n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
   ISR_CUDA(cudaStreamSynchronize(st));
@@ -390,11 +390,11 @@ int tsvd_select(isr_problem* p, int k, int keep_one, const double* vcs_err) {
   ISR_TRY(p->d_Rop.reserve((size_t)n * ld));
   ISR_CUDA(cudaMemcpyAsync(p->d_werr.p, vcs_err, sizeof(double) * n, cudaMemcpyHostToDevice, st));
   // Sop = K^+ = V_s Sigma_s^-1 U_s^T = VT^T (U_window / sigma)^T
-  tsvd_window_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(n, first, count, p->d_svU.p, p->d_sv.p, 0, p->d_tmp.p);
+  tsvd_window_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(n, first, count, p->d_svU.p, p->d_sv.p, 0, p->d_tmp.p); ISR_COUNT_LAUNCH();
   ISR_TRY(gemm(c, true, true, n, p->d_svVT.p, p->d_tmp.p, p->d_tmp2.p));
   colmajor_to_rowmajor(st, n, p->d_tmp2.p, nullptr, 0, p->d_Sop.p, ld);
   // Rop = W^(1/2) K = diag(1/err) U_window Sigma VT   (chi2 = d^T K^T W K d)
-  tsvd_window_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(n, first, count, p->d_svU.p, p->d_sv.p, 1, p->d_tmp.p);
+  tsvd_window_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(n, first, count, p->d_svU.p, p->d_sv.p, 1, p->d_tmp.p); ISR_COUNT_LAUNCH();
   ISR_TRY(gemm(c, false, false, n, p->d_tmp.p, p->d_svVT.p, p->d_tmp2.p));
   colmajor_to_rowmajor(st, n, p->d_tmp2.p, p->d_werr.p, 1, p->d_Rop.p, ld);
   ISR_CUDA(cudaGetLastError());

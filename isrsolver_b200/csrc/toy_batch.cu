@@ -133,7 +133,7 @@ int toy_batch_device(isr_problem* p, int64_t T, const double* V_dev, const doubl
     const int64_t tc = std::min<int64_t>(Tc, T - t0);
     const double* A = V_dev + t0 * n;
     if (n != ld) {
-      repack_kernel<<<(unsigned)((tc * ld + 255) / 256), 256, 0, st>>>(tc, n, ld, A, p->d_V.p);
+      repack_kernel<<<(unsigned)((tc * ld + 255) / 256), 256, 0, st>>>(tc, n, ld, A, p->d_V.p); ISR_COUNT_LAUNCH();
       A = p->d_V.p;
     }
     const int64_t ntiles = (tc + cfg->tm - 1) / cfg->tm;
@@ -146,16 +146,16 @@ int toy_batch_device(isr_problem* p, int64_t T, const double* V_dev, const doubl
     g.part_ld = nblk * cfg->np;
     g.want_ratio = (out.ratio_stats || out.rhist) ? 1 : 0;
     g.rhist = out.rhist;
-    cfg->solve<<<grid, cfg->threads, cfg->smem, st>>>(g);
+    cfg->solve<<<grid, cfg->threads, cfg->smem, st>>>(g); ISR_COUNT_LAUNCH();
     if (want_stats)
-      reduce_part_kernel<<<(n + 127) / 128, 128, 0, st>>>((int)grid.x, g.part_ld, n, p->d_acc.p, out.sum_bcs, out.ratio_stats);
+      reduce_part_kernel<<<(n + 127) / 128, 128, 0, st>>>((int)grid.x, g.part_ld, n, p->d_acc.p, out.sum_bcs, out.ratio_stats); ISR_COUNT_LAUNCH();
     if (out.chi2) {
       GemmArgs h{};
       h.A = p->d_B.p; h.lda = ld; h.T = tc; h.B = p->d_Rop.p; h.ldb = ld; h.N = n; h.K = ld;
       h.chi2 = nblk > 1 ? p->d_chi2.p : out.chi2 + t0;
-      cfg->chi2<<<grid, cfg->threads, cfg->smem, st>>>(h);
+      cfg->chi2<<<grid, cfg->threads, cfg->smem, st>>>(h); ISR_COUNT_LAUNCH();
       if (nblk > 1)
-        sum_blocks_kernel<<<(unsigned)((tc + 255) / 256), 256, 0, st>>>(tc, nblk, p->d_chi2.p, out.chi2 + t0);
+        sum_blocks_kernel<<<(unsigned)((tc + 255) / 256), 256, 0, st>>>(tc, nblk, p->d_chi2.p, out.chi2 + t0); ISR_COUNT_LAUNCH();
     }
   }
   ISR_CUDA(cudaGetLastError());
@@ -173,7 +173,7 @@ int project_device(isr_problem* p, int64_t T, const double* V_dev, const double*
   const double* A = V_dev;
   if (n != ld) {
     ISR_TRY(p->d_V.reserve((size_t)T * ld));
-    repack_kernel<<<(unsigned)((T * ld + 255) / 256), 256, 0, st>>>(T, n, ld, V_dev, p->d_V.p);
+    repack_kernel<<<(unsigned)((T * ld + 255) / 256), 256, 0, st>>>(T, n, ld, V_dev, p->d_V.p); ISR_COUNT_LAUNCH();
     A = p->d_V.p;
     ISR_CUDA(cudaMemsetAsync(E_dev, 0, sizeof(double) * T * ld, st));   // zero pad column
   }
@@ -182,7 +182,7 @@ int project_device(isr_problem* p, int64_t T, const double* V_dev, const double*
   GemmArgs g{};
   g.A = A; g.lda = ld; g.T = T; g.B = op; g.ldb = ld; g.N = n; g.K = ld;
   g.b0 = shift_dev; g.D = E_dev; g.ldd = ld;
-  cfg->solve<<<grid, cfg->threads, cfg->smem, st>>>(g);
+  cfg->solve<<<grid, cfg->threads, cfg->smem, st>>>(g); ISR_COUNT_LAUNCH();
   ISR_CUDA(cudaGetLastError());
   return ISR_OK;
 }

@@ -1,0 +1,70 @@
+"""One-process-per-GPU sharding of toy campaigns (torch.distributed is plumbing only).
+
+The path shards with no data-path collective: every rank assembles and factors the same N x N problem
+(replicated: it is << 1 ms of GPU work) and processes a contiguous slice of the toys (or of the lambda
+grid).  The single exchange step is ONE all_gather of a packed per-rank buffer
+    [ chi2 shard (padded to the largest shard) | sum_bcs (N) | ratio {count, sum, sum2} (3N) ]
+after which every rank holds all chi2 values and computes the TH1F(128, min, max) histogram exactly as
+src/Chi2Test.cpp:64-78 does on one process -- the histogram range depends on the GLOBAL min/max, so
+binning must happen after the gather to stay bit-identical with the single-GPU result.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_bounds(total: int, world: int, rank: int):
+    """Contiguous [begin, end) slice of `total` units for `rank` (sizes differ by at most one)."""
+    base, rem = divmod(int(total), int(world))
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def pack(chi2, sum_bcs, ratio_stats, max_shard: int):
+    """Pack one rank's results into a flat float64 buffer of fixed length."""
+    n = len(sum_bcs)
+    buf = np.zeros(max_shard + 4 * n)
+    buf[: len(chi2)] = chi2
+    buf[max_shard: max_shard + n] = sum_bcs
+    buf[max_shard + n:] = np.asarray(ratio_stats).reshape(-1)
+    return buf
+
+
+def unpack(gathered, total: int, world: int, n: int):
+    """Inverse of pack over the gathered (world, len) array: all chi2 in toy order + summed statistics."""
+    max_shard = gathered.shape[1] - 4 * n
+    parts, sum_bcs, stats = [], np.zeros(n), np.zeros(3 * n)
+    for r in range(world):
+        b, e = shard_bounds(total, world, r)
+        parts.append(gathered[r, : e - b])
+        sum_bcs += gathered[r, max_shard: max_shard + n]      # fixed rank order => deterministic
+        stats += gathered[r, max_shard + n:]
+    return np.concatenate(parts), sum_bcs, stats.reshape(n, 3)
+
+
+def all_gather_results(chi2, sum_bcs, ratio_stats, total: int, device=None):
+    """The one collective of a toy campaign.  Works on NCCL (device tensors) and gloo (CPU tensors)."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(), dist.get_rank()
+    n = len(sum_bcs)
+    max_shard = max(shard_bounds(total, world, r)[1] - shard_bounds(total, world, r)[0] for r in range(world))
+    mine = torch.from_numpy(pack(chi2, sum_bcs, ratio_stats, max_shard))
+    if device is not None:
+        mine = mine.to(device)
+    out = torch.empty(world * mine.numel(), dtype=torch.float64, device=mine.device)
+    dist.all_gather_into_tensor(out, mine)       # the single collective
+    return unpack(out.view(world, mine.numel()).cpu().numpy(), total, world, n)
+
+
+def th1_counts(values, nbins: int, lo: float, hi: float):
+    """TH1F::Fill bin arithmetic on the host (used by the gloo tests and as the cross-check of the device
+    histogram): counts[nbins + 2] with under/overflow."""
+    v = np.asarray(values, dtype=np.float64)
+    idx = np.empty(v.shape, dtype=np.int64)
+    below, above = v < lo, ~(v < hi)
+    mid = ~(below | above)
+    idx[below], idx[above] = 0, nbins + 1
+    idx[mid] = 1 + (nbins * (v[mid] - lo) / (hi - lo)).astype(np.int64)
+    return np.bincount(idx, minlength=nbins + 2).astype(np.uint32)

@@ -1,0 +1,578 @@
+"""Host-side mirror of the reference's PyISR module for the hot path, on top of the C ABI.
+
+Reference surface mirrored here (paths relative to the reference tree):
+  module functions  kernelKuraevFadin                      src/PyISR.cpp:197-207, include/PyKuraevFadin.hpp:9-17
+  ISRSolverSLE      ctor kwargs + methods table            include/PyISRSolver.hpp:156-213, include/PyISRSolverSLE.hpp:183-215
+  ISRSolverSLE2     per-point efficiency histograms        src/BaseISRSolver2.cpp:151-160, 196-204, 231-236
+  ISRSolverTikhonov reg_param, make_LCurve, solve_LCurve   include/PyISRSolverTikhonov.hpp:44-146
+  ISRSolverTSVD     upper_TSVD_index, enable/disable_keepone include/PyISRSolverTSVD.hpp:30-81
+Method names, argument names and meaning follow the reference.  Differences forced by the environment
+(documented in INTEGRATION.md): ROOT files are replaced by .npz files holding arrays under the same object
+names; a Python-callable efficiency is replaced by an `Efficiency` table (the GPU cannot call back into
+the interpreter per integrand node as include/PyISRSolver.hpp:189-197 does); the toy generator is a
+seeded NumPy PCG64 stream instead of the unseeded global gRandom (src/Utils.cpp:6-13).
+
+All numerical work goes through libisr_b200.so; nothing here computes on the CPU beyond O(N)
+bookkeeping, and there is no fallback when the library or the GPU is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+from typing import Sequence
+
+import numpy as np
+
+from . import _lib as L
+from ._lib import (EfficiencyDimensionException, InterpRangeException, IsrGpuError)  # noqa: F401 (re-export)
+
+TOY_SEED = 20211103
+
+_CTX = {}
+
+
+def _ctx(device: int | None = None):
+    """One isr_ctx per (process, device); device defaults to LOCAL_RANK (one process per GPU) or 0."""
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    if device not in _CTX:
+        h = C.c_void_p()
+        L.check(L.load().isr_ctx_create(device, C.byref(h)))
+        _CTX[device] = h
+    return _CTX[device]
+
+
+def _f64(a, n=None, name="array"):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if n is not None and a.shape != (n,):
+        raise ValueError(f"{name}: expected shape ({n},), got {a.shape}")
+    return a
+
+
+class DifferentModelCrossSectionSizes(ValueError):
+    """include/Chi2Test.hpp:47-52"""
+
+
+# ---------------------------------------------------------------------------------------------------
+# module-level functions
+# ---------------------------------------------------------------------------------------------------
+def kernelKuraevFadin(x, s, device: int | None = None):
+    """Kuraev-Fadin radiator F(x, s) evaluated on the GPU (kernelKuraevFadin, src/KuraevFadin.cpp:14-49).
+    Scalars or arrays (broadcast)."""
+    xa, sa = np.broadcast_arrays(np.asarray(x, dtype=np.float64), np.asarray(s, dtype=np.float64))
+    xa, sa = np.ascontiguousarray(xa).ravel(), np.ascontiguousarray(sa).ravel()
+    out = np.empty_like(xa)
+    L.check(L.load().isr_kernel_kf(_ctx(device), xa.size, L.dptr(xa), L.dptr(sa), L.dptr(out)))
+    return float(out[0]) if np.ndim(x) == 0 and np.ndim(s) == 0 else out.reshape(np.broadcast(x, s).shape)
+
+
+# ---------------------------------------------------------------------------------------------------
+# efficiency tables
+# ---------------------------------------------------------------------------------------------------
+class Efficiency:
+    """Detection efficiency with ROOT histogram semantics (values include under/overflow cells).
+
+    kind = 'one'        efficiency = 1                         (src/BaseISRSolver.cpp:140)
+           'row_table'  one TH1D in x per energy point (v2)    (src/BaseISRSolver2.cpp:231-236)
+           'table_2d'   TEfficiency 2-D in (x, E)              (src/BaseISRSolver.cpp:243-250)
+           'e_only'     TEfficiency 1-D, a function of E only  (src/BaseISRSolver.cpp:236-241)
+    """
+    KINDS = {"one": 0, "row_table": 1, "table_2d": 2, "e_only": 3}
+
+    def __init__(self, kind="one", values=None, nx=0, xlo=0.0, xhi=1.0, xedges=None,
+                 ne=0, elo=0.0, ehi=1.0, eedges=None, dimension=None):
+        if dimension is not None and dimension > 2:
+            raise EfficiencyDimensionException("[!] Wrong efficiency dimension.")
+        if kind not in self.KINDS:
+            raise ValueError(f"unknown efficiency kind {kind!r}")
+        self.kind = kind
+        self.values = None if values is None else np.ascontiguousarray(values, dtype=np.float64)
+        self.xedges = None if xedges is None else _f64(xedges)
+        self.eedges = None if eedges is None else _f64(eedges)
+        self.nx = int(nx) if self.xedges is None else len(self.xedges) - 1
+        self.ne = int(ne) if self.eedges is None else len(self.eedges) - 1
+        self.xlo, self.xhi = (float(xlo), float(xhi)) if self.xedges is None else (float(self.xedges[0]), float(self.xedges[-1]))
+        self.elo, self.ehi = (float(elo), float(ehi)) if self.eedges is None else (float(self.eedges[0]), float(self.eedges[-1]))
+
+    def desc(self, n_points: int) -> L.EpsDesc:
+        d = L.EpsDesc()
+        d.kind = self.KINDS[self.kind]
+        d.nx, d.xlo, d.xhi, d.ne, d.elo, d.ehi = self.nx, self.xlo, self.xhi, self.ne, self.elo, self.ehi
+        d.xedges, d.eedges, d.values = L.dptr(self.xedges), L.dptr(self.eedges), L.dptr(self.values)
+        if self.kind == "row_table" and self.values.shape != (n_points, self.nx + 2):
+            raise ValueError(f"row_table efficiency: values must be ({n_points}, {self.nx + 2})")
+        if self.kind == "table_2d" and self.values.shape != (self.ne + 2, self.nx + 2):
+            raise ValueError(f"table_2d efficiency: values must be ({self.ne + 2}, {self.nx + 2})")
+        if self.kind == "e_only" and self.values.shape != (self.ne + 2,):
+            raise ValueError(f"e_only efficiency: values must be ({self.ne + 2},)")
+        return d
+
+
+def draw_toys(vcs, vcs_err, n: int, seed: int = TOY_SEED):
+    """n toy visible cross sections, toy-major (n, N): vcs + vcs_err * z, z ~ N(0,1) from PCG64(seed).
+    Stands in for randomDrawVisCS (src/Utils.cpp:6-13)."""
+    z = np.random.Generator(np.random.PCG64(seed)).standard_normal((int(n), len(vcs)))
+    return np.asarray(vcs)[None, :] + np.asarray(vcs_err)[None, :] * z
+
+
+# ---------------------------------------------------------------------------------------------------
+# solvers
+# ---------------------------------------------------------------------------------------------------
+class BaseISRSolver:
+    """BaseISRSolver (include/BaseISRSolver.hpp:30-120; array constructor src/BaseISRSolver.cpp:77-129)."""
+
+    def __init__(self, n, energy, vcs, energy_err, vcs_err, threshold, efficiency=None,
+                 enableEnergySpread=False, device: int | None = None):
+        n = int(n)
+        energy, vcs, vcs_err = _f64(energy, n, "energy"), _f64(vcs, n, "vcs"), _f64(vcs_err, n, "vcs_err")
+        energy_err = np.zeros(n) if energy_err is None else _f64(energy_err, n, "energy_err")
+        # sort by energy through an index permutation (src/BaseISRSolver.cpp:105-128)
+        idx = np.argsort(energy, kind="stable")
+        if np.any(np.diff(energy[idx]) <= 0):
+            raise ValueError("duplicate centre-of-mass energies (the reference's unstable std::sort makes their order undefined)")
+        self._perm = idx
+        self._ecm, self._vcs = energy[idx].copy(), vcs[idx].copy()
+        self._ecm_err, self._vcs_err = energy_err[idx].copy(), vcs_err[idx].copy()
+        self._n, self._thr = n, float(threshold)
+        self._spread = bool(enableEnergySpread)
+        if efficiency is not None and not isinstance(efficiency, Efficiency):
+            raise TypeError("efficiency must be an isrsolver_b200.Efficiency table (a Python callable cannot be "
+                            "evaluated inside a CUDA kernel); see INTEGRATION.md")
+        self._eff = efficiency
+        self._bcs = np.zeros(n)
+        self._lib = L.load()
+        self._ctxh = _ctx(device)
+        self._p = C.c_void_p()
+        self._settings = None
+        desc = efficiency.desc(n) if efficiency is not None else None
+        L.check(self._lib.isr_problem_create(self._ctxh, n, L.dptr(self._ecm), self._thr, 0, None,
+                                             C.byref(desc) if desc is not None else None, C.byref(self._p)))
+
+    def __del__(self):
+        p = getattr(self, "_p", None)
+        if p:
+            try:
+                self._lib.isr_problem_destroy(p)
+            except Exception:
+                pass
+            self._p = None
+
+    # getters (include/PyISRSolver.hpp:66-99 return views on solver-owned memory; so do these)
+    n = property(lambda self: self._n)
+    energy_spread_enabled = property(lambda self: self._spread)
+
+    def getN(self): return self._n
+    def ecm(self): return self._ecm
+    def ecm_err(self): return self._ecm_err
+    def vcs(self): return self._vcs
+    def vcs_err(self): return self._vcs_err
+    def bcs(self): return self._bcs
+    def getThresholdEnergy(self): return self._thr
+    def getMinEnergy(self): return float(self._ecm[0])
+    def getMaxEnergy(self): return float(self._ecm[-1])
+    def isEnergySpreadEnabled(self): return self._spread
+    def enableEnergySpread(self): self._spread = True; self._invalidate()
+    def disableEnergySpread(self): self._spread = False; self._invalidate()
+
+    def resetVisibleCS(self, vcs): self._vcs = _f64(vcs, self._n, "vcs").copy()
+    def resetVisibleCSErrors(self, vcs_err): self._vcs_err = _f64(vcs_err, self._n, "vcs_err").copy(); self._factored = False
+
+    def reset_ecm_err(self, energy_err):
+        """resetECMErrors (src/BaseISRSolver.cpp:448-450).  Unlike the reference (see its TO-DO at
+        include/BaseISRSolver.hpp:85) the cached matrix is invalidated."""
+        self._ecm_err = _f64(energy_err, self._n, "energy_err").copy()
+        self._invalidate()
+    resetECMErrors = reset_ecm_err
+
+    def _invalidate(self):
+        pass
+
+
+class ISRSolverSLE(BaseISRSolver):
+    """ISRSolverSLE -- the naive method (include/ISRSolverSLE.hpp; src/ISRSolverSLE.cpp)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self._eq_ready = False      # _isEqMatrixPrepared
+        self._factored = False
+        self._G = None              # column-major storage like Eigen; intop_matrix() returns the transposed view
+        self._cov = None
+
+    def _invalidate(self):
+        self._eq_ready = False
+        self._factored = False
+
+    # -- interpolation settings (src/ISRSolverSLE.cpp:125-136; JSON format README.md:177-188)
+    def set_interp_settings(self, settings: Sequence[Sequence]):
+        st = np.ascontiguousarray([[int(bool(a)), int(b), int(c)] for a, b, c in settings], dtype=np.int32)
+        L.check(self._lib.isr_problem_set_ranges(self._p, len(st), L.iptr(st)))
+        self._settings = [tuple(r) for r in st.tolist()]
+        self._invalidate()
+    setRangeInterpSettings = set_interp_settings
+
+    def setRangeInterpSettingsJSON(self, path_or_obj):
+        obj = path_or_obj
+        if isinstance(path_or_obj, (str, os.PathLike)):
+            with open(path_or_obj) as f:
+                obj = json.load(f)
+        self.set_interp_settings(obj)
+
+    # -- matrix
+    def eval_equation_matrix(self):
+        """evalEqMatrix (src/ISRSolverSLE.cpp:138-149)."""
+        G = np.empty((self._n, self._n))
+        L.check(self._lib.isr_assemble(self._p, L.dptr(self._ecm_err) if self._spread else None, L.dptr(G)))
+        self._G = G
+        self._eq_ready = True
+        self._factored = False
+        return 0
+    evalEqMatrix = eval_equation_matrix
+
+    def intop_matrix(self):
+        """getIntegralOperatorMatrix: logical [i, j] view over column-major storage
+        (include/PyISRSolverSLE.hpp:88-97)."""
+        return self._G.T
+
+    def set_matrix(self, G):
+        """Inject an operator matrix (logical [i, j]) instead of assembling it."""
+        self._G = np.ascontiguousarray(np.asarray(G, dtype=np.float64).T)
+        L.check(self._lib.isr_set_matrix(self._p, L.dptr(self._G)))
+        self._eq_ready = True
+        self._factored = False
+
+    def _ensure_factored(self):
+        if not self._eq_ready:
+            self.eval_equation_matrix()
+        if not self._factored:
+            L.check(self._lib.isr_factor(self._p, L.dptr(self._vcs_err)))
+            self._factored = True
+
+    def solve(self):
+        """solve (src/ISRSolverSLE.cpp:86-95)."""
+        self._ensure_factored()
+        cov = np.empty((self._n, self._n))
+        L.check(self._lib.isr_solve(self._p, L.dptr(self._vcs), L.dptr(self._bcs), L.dptr(cov)))
+        self._cov = cov
+        return 0
+
+    def bcs_cov_matrix(self): return self._cov.T
+    getBornCSCovMatrix = bcs_cov_matrix
+
+    def bcs_inv_cov_matrix(self):
+        """Inverse covariance G^T W G (the reference inverts Cov again: include/PyISRSolverSLE.hpp:72-86)."""
+        self._ensure_factored()
+        out = np.empty((self._n, self._n))
+        L.check(self._lib.isr_get_inv_cov(self._p, L.dptr(out)))
+        return out.T
+
+    def bcs_err(self): return np.sqrt(np.diag(self._cov))
+
+    def condnum_eval(self):
+        """evalConditionNumber (src/ISRSolverSLE.cpp:200-204)."""
+        if not self._eq_ready:
+            self.eval_equation_matrix()
+        c = C.c_double()
+        L.check(self._lib.isr_cond_number(self._p, C.byref(c)))
+        return c.value
+    evalConditionNumber = condnum_eval
+
+    def interp_eval(self, cm_energy):
+        """interpEval(bcs, energy) (src/ISRSolverSLE.cpp:195-198)."""
+        e = np.atleast_1d(np.asarray(cm_energy, dtype=np.float64)).ravel().copy()
+        out = np.empty_like(e)
+        L.check(self._lib.isr_interp_eval(self._p, L.dptr(self._bcs), e.size, L.dptr(e), L.dptr(out)))
+        return float(out[0]) if np.ndim(cm_energy) == 0 else out.reshape(np.shape(cm_energy))
+
+    def basis_eval(self, cs_index, energy, deriv=False):
+        j = np.ascontiguousarray(np.atleast_1d(cs_index), dtype=np.int32)
+        e = np.ascontiguousarray(np.atleast_1d(energy), dtype=np.float64)
+        j, e = np.broadcast_arrays(j, e)
+        j, e = np.ascontiguousarray(j), np.ascontiguousarray(e)
+        out = np.empty(e.shape)
+        L.check(self._lib.isr_basis_eval(self._p, e.size, L.iptr(j), L.dptr(e), int(deriv), L.dptr(out)))
+        return out
+
+    def save(self, output_path, vcs_name="vcs", bcs_name="bcs"):
+        """save (src/ISRSolverSLE.cpp:97-123) with the ROOT objects replaced by arrays of the same names."""
+        np.savez(output_path, **{
+            vcs_name: np.stack([self._ecm, self._vcs, self._ecm_err, self._vcs_err]),
+            bcs_name: np.stack([self._ecm, self._bcs, np.zeros(self._n), self.bcs_err()]),
+            "intergalOperatorMatrix": self.intop_matrix(),   # sic, the reference's object name
+            "covMatrixBornCS": self.bcs_cov_matrix(),
+            "invCovMatrixBornCS": self.bcs_inv_cov_matrix(),
+        })
+        return 0
+
+    # -- toy Monte-Carlo validation -------------------------------------------------------------------
+    def _select_for_toys(self):
+        self._ensure_factored()
+
+    def toy_batch(self, V, bcs0, want_chi2=True, want_sum=False, want_ratio=False, want_hist=False, want_bcs=False):
+        """The loop body of chi2Test / ratioTestModel over all rows of V (toy-major (T, N), host)."""
+        V = np.ascontiguousarray(V, dtype=np.float64)
+        T = V.shape[0]
+        if V.ndim != 2 or V.shape[1] != self._n:
+            raise ValueError(f"V must be (T, {self._n})")
+        bcs0 = _f64(bcs0, self._n, "bcs0")
+        self._select_for_toys()
+        out = {}
+        chi2 = np.empty(T) if want_chi2 else None
+        sb = np.zeros(self._n) if want_sum else None
+        rs = np.zeros(3 * self._n) if want_ratio else None
+        rh = np.zeros((self._n, 1026), dtype=np.uint32) if want_hist else None
+        B = np.empty((T, self._n)) if want_bcs else None
+        L.check(self._lib.isr_toy_batch(self._p, T, L.dptr(V), L.dptr(bcs0), L.dptr(chi2), L.dptr(sb), L.dptr(rs),
+                                        L.uptr(rh), L.dptr(B)))
+        if want_chi2: out["chi2"] = chi2
+        if want_sum: out["sum_bcs"] = sb
+        if want_ratio: out["ratio_stats"] = rs.reshape(self._n, 3)
+        if want_hist: out["ratio_hist"] = rh
+        if want_bcs: out["bcs"] = B
+        return out
+
+    def chi2_test(self, n, vcs, bcs0, vcs_err, seed=TOY_SEED, toys=None):
+        """chi2Test (src/Chi2Test.cpp:29-104) without the ROOT fit/file: returns the chi2 values and the
+        TH1F(128, min, max) counts (under/overflow included)."""
+        V = draw_toys(vcs, vcs_err, n, seed) if toys is None else toys
+        chi2 = self.toy_batch(V, bcs0)["chi2"]
+        lo, hi = C.c_double(), C.c_double()
+        counts = np.zeros(130, dtype=np.uint32)
+        L.check(self._lib.isr_chi2_histogram(self._ctxh, len(chi2), L.dptr(chi2), 128, C.byref(lo), C.byref(hi), L.uptr(counts)))
+        return {"chi2": chi2, "hist": counts.astype(np.float32), "lo": lo.value, "hi": hi.value}
+
+    @staticmethod
+    def _load_model(model_path, vcs_name, bcs_name):
+        with np.load(model_path) as f:
+            v, b = np.asarray(f[vcs_name], dtype=np.float64), np.asarray(f[bcs_name], dtype=np.float64)
+        v = v[1] if v.ndim == 2 else v      # graphs are stored as rows (x, y, ex, ey)
+        b = b[1] if b.ndim == 2 else b
+        if v.shape != b.shape:
+            raise DifferentModelCrossSectionSizes("[!] Model visible and Born cross sections have different sizes.")
+        return v, b
+
+    def chi2_test_model(self, n, initial_ampl, model_path, model_visible_cs_name, model_born_cs_name,
+                        output_path=None, seed=TOY_SEED):
+        """chi2TestModel (src/Chi2Test.cpp:113-151); kwargs as include/PyISRSolverSLE.hpp:125-153."""
+        self.solve()
+        vcs, bcs0 = self._load_model(model_path, model_visible_cs_name, model_born_cs_name)
+        res = self.chi2_test(n, vcs, bcs0, self._vcs_err, seed)
+        res["initial_ampl"] = float(initial_ampl)
+        if output_path:
+            np.savez(output_path, chi2Hist=res["hist"], chi2Min=res["lo"], chi2Max=res["hi"], chi2=res["chi2"])
+        return res
+
+    def chi2_test_data(self, n, initial_ampl=1e4, output_path=None, seed=TOY_SEED):
+        """chi2TestData (src/Chi2Test.cpp:160-195): reference = mean solution over n toys, then chi2Test."""
+        self.solve()
+        vcs = self._vcs.copy()
+        V = draw_toys(vcs, self._vcs_err, n, seed)
+        s = self.toy_batch(V, np.ones(self._n), want_chi2=False, want_sum=True)["sum_bcs"]
+        bcs0 = s / n
+        res = self.chi2_test(n, vcs, bcs0, self._vcs_err, seed + 1)
+        res["bcs0"] = bcs0
+        if output_path:
+            np.savez(output_path, chi2Hist=res["hist"], chi2Min=res["lo"], chi2Max=res["hi"], chi2=res["chi2"])
+        return res
+
+    def ratio_test_model(self, n, model_path, model_visible_cs_name, model_born_cs_name, output_path=None,
+                         seed=TOY_SEED, toys=None):
+        """ratioTestModel (src/RatioTest.cpp:13-62): per point TH1F(1024,-2,2) of (b - b0)/b0, GetMean and
+        GetMeanError of the in-range entries."""
+        self.solve()
+        vcs, bcs0 = self._load_model(model_path, model_visible_cs_name, model_born_cs_name)
+        V = draw_toys(vcs, self._vcs_err, n, seed) if toys is None else toys
+        r = self.toy_batch(V, bcs0, want_chi2=False, want_ratio=True, want_hist=True)
+        cnt, sx, sx2 = r["ratio_stats"].T
+        with np.errstate(divide="ignore", invalid="ignore"):
+            mean = np.where(cnt > 0, sx / cnt, 0.0)
+            rms = np.sqrt(np.abs(np.where(cnt > 0, sx2 / cnt, 0.0) - mean * mean))
+            err = np.where(cnt > 0, rms / np.sqrt(cnt), 0.0)
+        res = {"means": mean, "mean_errors": err, "hist": r["ratio_hist"].astype(np.float32), "ecm": self._ecm}
+        if output_path:
+            np.savez(output_path, means=np.stack([self._ecm, mean, np.zeros(self._n), err]),
+                     **{f"bias_pt_{i}": res["hist"][i] for i in range(self._n)})
+        return res
+
+
+class ISRSolverSLE2(ISRSolverSLE):
+    """ISRSolverSLE2: efficiency eps(x, energyIndex) from one x-histogram per energy point
+    (src/BaseISRSolver2.cpp:151-160, 196-204, 231-236; src/ISRSolverSLE2.cpp:142-153)."""
+
+    def __init__(self, n, energy, vcs, energy_err, vcs_err, threshold, eff_hists=None, nbins=None, xlo=0.0, xhi=1.0,
+                 xedges=None, enableEnergySpread=False, device=None):
+        eff = None
+        if eff_hists is not None:
+            vals = np.ascontiguousarray(eff_hists, dtype=np.float64)
+            order = np.argsort(np.asarray(energy, dtype=np.float64), kind="stable")
+            vals = vals[order]     # histograms follow their energy points through the sort
+            eff = Efficiency("row_table", values=vals, nx=(vals.shape[1] - 2 if nbins is None else nbins),
+                             xlo=xlo, xhi=xhi, xedges=xedges)
+        super().__init__(n, energy, vcs, energy_err, vcs_err, threshold, eff, enableEnergySpread, device)
+
+
+class ISRSolverTikhonov(ISRSolverSLE):
+    """ISRSolverTikhonov (include/ISRSolverTikhonov.hpp; src/ISRSolverTikhonov.cpp)."""
+
+    def __init__(self, *args, **kwargs):
+        lam = kwargs.pop("reg_param", 1.0)      # _lambda(1.), src/ISRSolverTikhonov.cpp:30
+        super().__init__(*args, **kwargs)
+        self._lambda = float(lam)
+        self._deriv_reg = True                  # _enabledDerivNorm2Reg(true), :29
+        self._tik_ready = False
+
+    def _invalidate(self):
+        super()._invalidate()
+        self._tik_ready = False
+
+    reg_param = property(lambda self: self._lambda, lambda self, v: self.setLambda(v))
+    def getLambda(self): return self._lambda
+    def setLambda(self, lam): self._lambda = float(lam)
+    def isDerivNorm2RegIsEnabled(self): return self._deriv_reg
+    def enableDerivNorm2Regularizator(self): self._deriv_reg = True; self._tik_ready = False
+    def disableDerivNorm2Regularizator(self): self._deriv_reg = False; self._tik_ready = False
+
+    def _ensure_tik(self):
+        if not self._eq_ready:
+            self.eval_equation_matrix()
+            self._tik_ready = False
+        if not self._tik_ready:
+            L.check(self._lib.isr_tikhonov_prepare(self._p, L.dptr(self._vcs_err), int(self._deriv_reg)))
+            self._tik_ready = True
+            self._factored = True
+
+    def resetVisibleCSErrors(self, vcs_err):
+        super().resetVisibleCSErrors(vcs_err)
+        self._tik_ready = False
+
+    def solve(self):
+        """solve (src/ISRSolverTikhonov.cpp:61-72)."""
+        self._ensure_tik()
+        cov = np.empty((self._n, self._n))
+        L.check(self._lib.isr_tikhonov_solve(self._p, self._lambda, L.dptr(self._vcs), L.dptr(self._bcs), L.dptr(cov)))
+        self._cov = cov
+        return 0
+
+    def bcs_inv_cov_matrix(self):
+        return np.linalg.inv(self.bcs_cov_matrix())
+
+    def _scan(self, lambdas, want_bcs=False):
+        self._ensure_tik()
+        lam = _f64(np.atleast_1d(lambdas))
+        Lm = lam.size
+        x, y, c, dc = (np.empty(Lm) for _ in range(4))
+        B = np.empty((Lm, self._n)) if want_bcs else None
+        L.check(self._lib.isr_tikhonov_scan(self._p, Lm, L.dptr(lam), L.dptr(self._vcs), L.dptr(x), L.dptr(y),
+                                            L.dptr(c), L.dptr(dc), L.dptr(B)))
+        return x, y, c, dc, B
+
+    def evalEqNorm2(self): return float(self._scan([self._lambda])[0][0])
+    def evalSmoothnessConstraintNorm2(self): return float(self._scan([self._lambda])[1][0])
+    def evalLCurveCurvature(self): return float(self._scan([self._lambda])[2][0])
+    def evalLCurveCurvatureDerivative(self): return float(self._scan([self._lambda])[3][0])
+
+    def make_LCurve(self, lambdas):
+        """make_LCurve (include/PyISRSolverTikhonov.hpp:44-79): x = |G b - v|^2_W, y = b^T F b, c = -curvature,
+        for every lambda, from one decomposition instead of one solve() per lambda.  Like the reference,
+        the solver is left at the last lambda."""
+        lam = np.asarray(lambdas, dtype=np.float64)
+        if lam.ndim != 1:
+            raise TypeError("Wrong dimension of the array with regularization parameter values. The array must be 1D array.")
+        x, y, c, _, _ = self._scan(lam)
+        if lam.size:
+            self._lambda = float(lam[-1])
+            self.solve()
+        return {"x": x, "y": y, "c": -c}
+
+    def solve_LCurve(self, initial_lambda, lo=1e-12, hi=None):
+        """solve_LCurve (include/PyISRSolverTikhonov.hpp:81-109): maximise the L-curve curvature over
+        lambda >= 0.  NLopt LD_MMA (absent here) is replaced by a dense log-grid scan of the O(N)-per-lambda
+        curvature followed by golden-section refinement to xtol_rel 1e-6."""
+        hi = max(10.0 * initial_lambda, 1.0) if hi is None else hi
+        grid = np.geomspace(lo, hi, 2048)
+        obj = self._scan(grid)[2]          # curvature = -|...| <= 0 ; NLopt minimises it
+        k = int(np.argmin(obj))
+        a, b = grid[max(k - 1, 0)], grid[min(k + 1, len(grid) - 1)]
+        gr = (np.sqrt(5.0) - 1.0) / 2.0
+        c_, d_ = b - gr * (b - a), a + gr * (b - a)
+        fc, fd = self._scan([c_])[2][0], self._scan([d_])[2][0]
+        while abs(b - a) > 1e-6 * abs(0.5 * (a + b)):
+            if fc < fd:
+                b, d_, fd = d_, c_, fc
+                c_ = b - gr * (b - a)
+                fc = self._scan([c_])[2][0]
+            else:
+                a, c_, fc = c_, d_, fd
+                d_ = a + gr * (b - a)
+                fd = self._scan([d_])[2][0]
+        lam = 0.5 * (a + b)
+        self._lambda = float(lam)
+        self.solve()
+        return {"lambda": float(lam), "max_curv": float(-self._scan([lam])[2][0])}
+
+    def _select_for_toys(self):
+        self._ensure_tik()
+        L.check(self._lib.isr_tikhonov_select(self._p, self._lambda))
+
+    def _ensure_factored(self):
+        self._ensure_tik()
+
+    def toy_scan(self, lambdas, V, bcs0):
+        """chi2 of every (lambda, toy) pair, (L, T): the chi2Test loop of isrsolver-Tikhonov-chi2-test for
+        all lambdas at once."""
+        self._ensure_tik()
+        lam = _f64(np.atleast_1d(lambdas))
+        V = np.ascontiguousarray(V, dtype=np.float64)
+        out = np.empty((lam.size, V.shape[0]))
+        L.check(self._lib.isr_tikhonov_toy_scan(self._p, lam.size, L.dptr(lam), V.shape[0], L.dptr(V),
+                                                L.dptr(_f64(bcs0, self._n)), L.dptr(out)))
+        return out
+
+    def regulariser(self):
+        self._ensure_tik()
+        F = np.empty((self._n, self._n))
+        L.check(self._lib.isr_get_regulariser(self._p, L.dptr(F)))
+        return F.T
+
+
+class ISRSolverTSVD(ISRSolverSLE):
+    """ISRSolverTSVD (include/ISRSolverTSVD.hpp; src/ISRSolverTSVD.cpp)."""
+
+    def __init__(self, *args, **kwargs):
+        k = kwargs.pop("upper_TSVD_index", None)
+        super().__init__(*args, **kwargs)
+        self._k = self._n if k is None else int(k)   # _upperTSVDIndex(numberOfPoints), src/ISRSolverTSVD.cpp:19
+        self._keep_one = False
+
+    upper_TSVD_index = property(lambda self: self._k, lambda self, v: self.setUpperTSVDIndex(v))
+    def getUpperTSVDIndex(self): return self._k
+    def setUpperTSVDIndex(self, k): self._k = int(k)
+    def enable_keepone(self): self._keep_one = True
+    def disable_keepone(self): self._keep_one = False
+    enableKeepOne, disableKeepOne = enable_keepone, disable_keepone
+
+    def solve(self):
+        """solve (src/ISRSolverTSVD.cpp:53-74).  Cov = (K^T W K)^-1 exists only for k == N; otherwise the
+        reference inverts a singular matrix and this implementation leaves bcs_cov_matrix() unset."""
+        if not self._eq_ready:
+            self.eval_equation_matrix()
+        full = (self._k == self._n) and not self._keep_one
+        cov = np.empty((self._n, self._n)) if full else None
+        L.check(self._lib.isr_tsvd_solve(self._p, self._k, int(self._keep_one), L.dptr(self._vcs),
+                                         L.dptr(self._vcs_err), L.dptr(self._bcs), L.dptr(cov)))
+        self._cov = cov
+        self._factored = False
+        return 0
+
+    def singular_values(self):
+        if not self._eq_ready:
+            self.eval_equation_matrix()
+        s = np.empty(self._n)
+        L.check(self._lib.isr_singular_values(self._p, L.dptr(s)))
+        return s
+
+    def _select_for_toys(self):
+        if not self._eq_ready:
+            self.eval_equation_matrix()
+        L.check(self._lib.isr_tsvd_select(self._p, self._k, int(self._keep_one), L.dptr(self._vcs_err)))
+        self._factored = False

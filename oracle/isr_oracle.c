@@ -740,6 +740,8 @@ static double conv_integrand(double x, void *vctx) {
   return fv * orc_kernel_kf(x, c->energy * c->energy) * eff_eval(c->eff, x, c->energy, c->row); /* :53,61 */
 }
 static double convolution_kf_faithful(conv_ctx *c, double min_x, double max_x);
+static double convolution_piece(conv_ctx *c, double a, double b);
+static double conv_integrand(double x, void *vctx);
 /* "Converged" back-end (NOT what the reference does): the same integrand and the same QUADPACK
  * routines, but the range is cut at every point where the integrand is not smooth (spline knots,
  * efficiency bin edges, x0), so that every adaptive call converges at its first tolerance instead of
@@ -754,11 +756,20 @@ static double convolution_kf(conv_ctx *c, double min_x, double max_x) {
     const double v = c->brk[q];
     if (!(v > lo)) continue;
     if (!(v < max_x)) break;
-    result += convolution_kf_faithful(c, lo, v);
+    result += convolution_piece(c, lo, v);
     lo = v;
   }
-  result += convolution_kf_faithful(c, lo, max_x);
+  result += convolution_piece(c, lo, max_x);
   return result;
+}
+/* one smooth piece: x0 is a break point, so the piece lies on one side of it.  (The reference's
+ * "[min,x0] forwards + [x0,max] backwards" evaluation for max < x0, src/KuraevFadin.cpp:64-68, is NOT
+ * reproduced here: it would re-cross the break points the piece was cut at.) */
+static double convolution_piece(conv_ctx *c, double a, double b) {
+  double error;
+  const double x0 = 4 * ELECTRON_M / c->energy;
+  if (b <= x0) return orc_integrateS(conv_integrand, c, a, b, &error);
+  return orc_integrate(conv_integrand, c, a, b, &error);
 }
 static double convolution_kf_faithful(conv_ctx *c, double min_x, double max_x) {   /* :56-73 */
   double error, result;

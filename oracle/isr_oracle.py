@@ -219,6 +219,17 @@ class Interp:
     def kf_basis_integral(self, i, j, eff: Efficiency | None = None):
         return lib().orc_kf_basis_integral(self._h, i, j, eff.ptr if eff else None)
 
+    def eval_rows(self, rows, eff: Efficiency | None = None, mode: str = "converged"):
+        """Selected rows of the equation matrix (full-size spot checks): returns (G[rows, :], Err[rows, :])."""
+        m = {"faithful": 0, "converged": 1}[mode]
+        G = np.zeros((len(rows), self.n)); E = np.zeros((len(rows), self.n))
+        for a, i in enumerate(rows):
+            for j in range(self.n):
+                e, r = C.c_double(), C.c_double()
+                G[a, j] = lib().orc_kf_basis_integral_ex(self._h, int(i), j, eff.ptr if eff else None, m, C.byref(e), C.byref(r))
+                E[a, j] = e.value
+        return G, E
+
     def integral_basis(self):
         """_evalDotProductOperator -- src/ISRSolverSLE.cpp:165-171."""
         return np.array([lib().orc_integral_basis(self._h, j) for j in range(self.n)])

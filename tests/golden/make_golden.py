@@ -1,0 +1,71 @@
+#!/usr/bin/env python3
+"""Generate the golden fixtures under tests/golden/ from the CPU oracle.
+
+The reference ships no golden vectors and cannot be built in this image, so these
+fixtures are outputs of oracle/ (the C restatement of the reference's QUADPACK-based assembly plus
+NumPy/LAPACK linear algebra), pinned in tests/test_oracle.py against SciPy QUADPACK, mpmath and analytic
+identities.  Run:  python tests/golden/make_golden.py   (about a minute on 8 cores).
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import isr_oracle as O  # noqa: E402
+
+
+def case(name, n, settings, eff=None, ecm_err=None, toys=64, tik=False):
+    ecm = np.linspace(O.E_MIN, O.E_MAX, n)
+    I = O.Interp(ecm, O.E_THR, settings)
+    Gf, Ef, Rf = I.eval_eq_matrix(eff=eff, with_errors=True)
+    Gc, Ec, Rc = I.eval_eq_matrix(eff=eff, mode="converged", with_errors=True)
+    out = dict(ecm=ecm, threshold=O.E_THR, settings=np.array(settings, dtype=np.int32),
+               G_faithful=Gf, G_faithful_err=Ef, G_faithful_relerr=Rf, G_converged=Gc, G_converged_err=Ec)
+    G = Gc
+    if ecm_err is not None:
+        S = I.energy_spread_matrix(ecm_err)
+        G = S @ Gc
+        out.update(ecm_err=ecm_err, S=S, G_spread=G)
+    bcs0 = O.bw_born(ecm)
+    vcs = O.bw_visible(ecm, eff=eff)
+    vcs_err = 0.05 * vcs
+    b, cov = O.sle_solve(G, vcs, vcs_err)
+    V = O.draw_toys(vcs, vcs_err, toys)
+    chi2_loop, B_loop = O.chi2_test_loop(G, V, bcs0, vcs_err)
+    chi2_fair, B_fair = O.chi2_test_fair(G, V, bcs0, vcs_err)
+    means, errs, counts, stats = O.ratio_test(B_fair, bcs0)
+    hist, idx, lo, hi = O.chi2_histogram(chi2_fair)
+    out.update(bcs0=bcs0, vcs=vcs, vcs_err=vcs_err, bcs=b, cov=cov, toys=V, chi2_loop=chi2_loop, chi2=chi2_fair,
+               B=B_fair, ratio_means=means, ratio_mean_errors=errs, ratio_stats=stats,
+               ratio_counts=counts.astype(np.uint16), chi2_hist=hist, chi2_lo=lo, chi2_hi=hi,
+               cond=O.cond_number(G), w=I.integral_basis(), D=I.deriv_projector())
+    if eff is not None:
+        out.update(eff_values=eff.values, eff_nx=eff.nx, eff_xlo=eff.xlo, eff_xhi=eff.xhi)
+    if tik:
+        lam = np.geomspace(1e-9, 1.0, 12)
+        F = O.tikhonov_F(out["D"], out["w"], True)
+        rows = [O.tikhonov_lcurve(G, vcs, vcs_err, F, l) for l in lam]
+        out.update(tik_lambda=lam, tik_F=F, tik_x=np.array([r["x"] for r in rows]), tik_y=np.array([r["y"] for r in rows]),
+                   tik_curv=np.array([r["curv"] for r in rows]), tik_dcurv=np.array([r["dcurv"] for r in rows]),
+                   tik_bcs=np.array([r["bcs"] for r in rows]), tik_cov3=rows[3]["cov"])
+        k = n // 2
+        out.update(tsvd_k=k, tsvd_bcs=O.tsvd_solve(G, vcs, vcs_err, k)[0], tsvd_bcs_keepone=O.tsvd_solve(G, vcs, vcs_err, k, True)[0],
+                   sv=np.linalg.svd(G, compute_uv=False))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "done; faithful-vs-converged max abs", np.abs(Gf - Gc).max(), "loosest faithful epsrel", Rf.max())
+
+
+if __name__ == "__main__":
+    n = 50
+    case("c1_sle_n50_linear", n, [(0, 0, n - 1)])                                     # BASELINE.json configs[0]
+    n = 40
+    case("c2_sle_n40_cspline", n, [(0, 0, 0), (1, 1, n - 1)], tik=False)              # configs[1] at test size
+    n = 24
+    ecm = np.linspace(O.E_MIN, O.E_MAX, n)
+    case("c3_sle2_n24_eps64", n, [(0, 0, n - 1)], eff=O.row_table_efficiency(ecm, 64))  # configs[2] at test size
+    n = 32
+    case("c4_tikhonov_n32_spread", n, [(0, 0, 0), (1, 1, n - 1)], ecm_err=np.full(n, 0.002), tik=True)  # configs[3]
+    n = 36
+    case("c5_mixed3_n36", n, [(1, 0, 11), (0, 12, 20), (1, 21, n - 1)])

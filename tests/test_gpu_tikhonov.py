@@ -1,0 +1,129 @@
+"""Tikhonov lambda-scan / L-curve and TSVD parity on the B200 (through the C ABI).
+
+The oracle is the literal matrix implementation of src/ISRSolverTikhonov.cpp / src/ISRSolverTSVD.cpp in
+NumPy.  The spread problem is ill-conditioned (that is what Tikhonov is for), so quantities that the
+reference itself obtains through LU factorisations of T = G^T W G + lambda F carry ~cond(T) * eps noise;
+tolerances below are 1e-8 where the conditioning allows and state the reason where it does not."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from test_gpu_assembly import make_solver
+
+pytestmark = pytest.mark.gpu
+
+
+def tik_solver(g):
+    import isrsolver_b200 as isr
+    s = make_solver(g, cls=isr.ISRSolverTikhonov, spread=True)
+    s.set_matrix(g["G_spread"])
+    return s
+
+
+def test_regulariser_and_basis_tables():
+    g = load_golden("c4_tikhonov_n32_spread")
+    s = tik_solver(g)
+    n = len(g["ecm"])
+    np.testing.assert_allclose(s.regulariser(), g["tik_F"], rtol=1e-8, atol=1e-10 * np.abs(g["tik_F"]).max())
+    # D(i,j) = basis_j'(E_i) and w_j = int basis_j
+    jj, ii = np.meshgrid(np.arange(n), np.arange(n))
+    D = s.basis_eval(jj.ravel(), g["ecm"][ii.ravel()], deriv=True).reshape(n, n)
+    np.testing.assert_allclose(D, g["D"], rtol=1e-9, atol=1e-9 * np.abs(g["D"]).max())
+    import ctypes as C
+    from isrsolver_b200 import _lib as L
+    w = np.empty(n); L.check(L.load().isr_basis_integrals(s._p, L.dptr(w)))
+    np.testing.assert_allclose(w, g["w"], rtol=1e-10)
+
+
+def test_lcurve_scan_vs_literal_matrices(oracle):
+    g = load_golden("c4_tikhonov_n32_spread")
+    s = tik_solver(g)
+    lam = g["tik_lambda"]
+    res = s.make_LCurve(lam)
+    np.testing.assert_allclose(res["y"], g["tik_y"], rtol=1e-8)
+    np.testing.assert_allclose(res["c"], -g["tik_curv"], rtol=1e-8)
+    # evalEqNorm2 is a residual: the reference forms G b - v (cancellation ~ eps |v| / |G b - v|)
+    np.testing.assert_allclose(res["x"], g["tik_x"], rtol=1e-6, atol=1e-9)
+    x, y, c, dc, B = s._scan(lam, want_bcs=True)
+    np.testing.assert_allclose(dc, g["tik_dcurv"], rtol=1e-7)
+    np.testing.assert_allclose(B, g["tik_bcs"], rtol=1e-8, atol=1e-8 * np.abs(g["tik_bcs"]).max())
+
+
+def test_single_lambda_solve_and_cov():
+    g = load_golden("c4_tikhonov_n32_spread")
+    s = tik_solver(g)
+    s.reg_param = float(g["tik_lambda"][3])
+    s.solve()
+    np.testing.assert_allclose(s.bcs(), g["tik_bcs"][3], rtol=1e-8, atol=1e-8 * np.abs(g["tik_bcs"][3]).max())
+    ref = g["tik_cov3"]
+    assert np.abs(s.bcs_cov_matrix() - ref).max() <= 1e-8 * np.abs(ref).max()
+    assert s.evalSmoothnessConstraintNorm2() == pytest.approx(float(g["tik_y"][3]), rel=1e-8)
+    assert s.evalLCurveCurvature() == pytest.approx(float(g["tik_curv"][3]), rel=1e-8)
+
+
+def test_diag_regulariser(oracle):
+    g = load_golden("c4_tikhonov_n32_spread")
+    s = tik_solver(g)
+    s.disableDerivNorm2Regularizator()
+    F = oracle.tikhonov_F(g["D"], g["w"], False)
+    np.testing.assert_allclose(s.regulariser(), F, rtol=1e-10, atol=1e-14)
+    lam = 1e-3
+    ref = oracle.tikhonov_lcurve(g["G_spread"], g["vcs"], g["vcs_err"], F, lam)
+    s.reg_param = lam; s.solve()
+    np.testing.assert_allclose(s.bcs(), ref["bcs"], rtol=1e-8, atol=1e-8 * np.abs(ref["bcs"]).max())
+    assert s.evalLCurveCurvature() == pytest.approx(ref["curv"], rel=1e-8)
+
+
+def test_toy_scan_vs_literal(oracle):
+    """chi2 of (lambda, toy) pairs: O(N) diagonal rescaling vs the literal A+ / Cov^-1 matrices."""
+    g = load_golden("c4_tikhonov_n32_spread")
+    s = tik_solver(g)
+    lam = np.array([1e-4, 1e-2, 0.3])
+    V, b0 = g["toys"][:48], g["bcs0"]
+    got = s.toy_scan(lam, V, b0)
+    for q, l in enumerate(lam):
+        t = oracle.tikhonov_solve(g["G_spread"], g["vcs"], g["vcs_err"], g["tik_F"], l)
+        D = V @ t["Ap"].T - b0[None, :]
+        ref = np.einsum("ij,ij->i", D, np.linalg.solve(t["cov"], D.T).T)
+        # Cov_lambda is ill-conditioned for small lambda; the literal solve loses ~cond(Cov) eps
+        np.testing.assert_allclose(got[q], ref, rtol=1e-6)
+    # the selected-operator path (isr_tikhonov_select + generic toy batch) agrees with the scan
+    s.reg_param = float(lam[1])
+    r = s.toy_batch(V, b0, want_bcs=True)
+    np.testing.assert_allclose(r["chi2"], got[1], rtol=1e-8)
+    t = oracle.tikhonov_solve(g["G_spread"], g["vcs"], g["vcs_err"], g["tik_F"], lam[1])
+    np.testing.assert_allclose(r["bcs"], V @ t["Ap"].T, rtol=1e-8, atol=1e-8 * np.abs(V).max())
+
+
+def test_solve_lcurve_finds_curvature_maximum():
+    g = load_golden("c4_tikhonov_n32_spread")
+    s = tik_solver(g)
+    res = s.solve_LCurve(1e-3)
+    grid = np.geomspace(1e-12, 1.0, 4001)
+    c = s.make_LCurve(grid)["c"]
+    assert res["max_curv"] >= c.max() * (1 - 1e-6)
+    assert res["lambda"] == pytest.approx(grid[np.argmax(c)], rel=2e-2)
+
+
+def test_tsvd(oracle):
+    import isrsolver_b200 as isr
+    g = load_golden("c4_tikhonov_n32_spread")
+    s = make_solver(g, cls=isr.ISRSolverTSVD, spread=True)
+    s.set_matrix(g["G_spread"])
+    np.testing.assert_allclose(s.singular_values(), g["sv"], rtol=1e-10)
+    k = int(g["tsvd_k"])
+    s.upper_TSVD_index = k
+    s.solve()
+    np.testing.assert_allclose(s.bcs(), g["tsvd_bcs"], rtol=1e-8, atol=1e-8 * np.abs(g["tsvd_bcs"]).max())
+    s.enable_keepone(); s.solve()
+    np.testing.assert_allclose(s.bcs(), g["tsvd_bcs_keepone"], rtol=1e-8, atol=1e-8 * np.abs(g["tsvd_bcs_keepone"]).max())
+    s.disable_keepone(); s.upper_TSVD_index = len(g["ecm"]); s.solve()
+    bo, covo = oracle.sle_solve(g["G_spread"], g["vcs"], g["vcs_err"])
+    np.testing.assert_allclose(s.bcs(), bo, rtol=1e-6)
+    assert np.abs(s.bcs_cov_matrix() - covo).max() <= 1e-6 * np.abs(covo).max()
+    # toy batch with the truncated operator: b_k = K^+ v_k
+    s.upper_TSVD_index = k
+    r = s.toy_batch(g["toys"][:16], g["bcs0"], want_bcs=True)
+    U, S, Vt = np.linalg.svd(g["G_spread"])
+    Kp = Vt[:k].T @ np.diag(1 / S[:k]) @ U[:, :k].T
+    np.testing.assert_allclose(r["bcs"], g["toys"][:16] @ Kp.T, rtol=1e-8, atol=1e-8 * np.abs(g["bcs0"]).max())

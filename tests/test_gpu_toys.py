@@ -1,0 +1,178 @@
+"""Solve / covariance / toy-batch / histogram parity on the B200 (through the C ABI).
+
+Tolerances (north star): Born cross section, covariance and per-toy chi2 within 1e-8 relative; histogram
+and bin indices bit-exact on identical chi2 inputs."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from test_gpu_assembly import make_solver
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-8
+
+
+@pytest.mark.parametrize("name", ["c1_sle_n50_linear", "c2_sle_n40_cspline", "c5_mixed3_n36"])
+def test_solve_and_covariance(name):
+    g = load_golden(name)
+    s = make_solver(g)
+    s.solve()
+    np.testing.assert_allclose(s.bcs(), g["bcs"], rtol=RTOL)
+    cov, ref = s.bcs_cov_matrix(), g["cov"]
+    scale = np.sqrt(np.outer(np.diag(ref), np.diag(ref)))
+    assert np.abs(cov - ref).max() <= RTOL * scale.max()
+    np.testing.assert_allclose(np.diag(cov), np.diag(ref), rtol=RTOL)
+    assert np.array_equal(cov, cov.T)
+    assert s.condnum_eval() == pytest.approx(float(g["cond"]), rel=1e-8)
+    inv = s.bcs_inv_cov_matrix()
+    np.testing.assert_allclose(inv @ ref, np.eye(len(ref)), atol=1e-7)
+    # interp_eval: the solution at the nodes and the reference's conventions outside the range
+    np.testing.assert_allclose(s.interp_eval(g["ecm"]), s.bcs(), rtol=1e-12)
+    assert s.interp_eval(float(g["threshold"])) == 0.0
+    assert s.interp_eval(g["ecm"][-1] + 0.5) == s.bcs()[-1]
+
+
+@pytest.mark.parametrize("name", ["c1_sle_n50_linear", "c2_sle_n40_cspline", "c3_sle2_n24_eps64"])
+def test_toy_batch_vs_golden(name):
+    import isrsolver_b200 as isr
+    g = load_golden(name)
+    eff = None
+    if "eff_values" in g:
+        eff = isr.Efficiency("row_table", values=g["eff_values"], nx=int(g["eff_nx"]), xlo=float(g["eff_xlo"]), xhi=float(g["eff_xhi"]))
+    s = make_solver(g, eff=eff)
+    # use the oracle's matrix so that this test isolates the solve path
+    s.set_matrix(g["G_converged"])
+    r = s.toy_batch(g["toys"], g["bcs0"], want_sum=True, want_ratio=True, want_hist=True, want_bcs=True)
+    np.testing.assert_allclose(r["chi2"], g["chi2"], rtol=RTOL)
+    np.testing.assert_allclose(r["chi2"], g["chi2_loop"], rtol=RTOL)        # the reference's per-toy O(N^3) loop
+    np.testing.assert_allclose(r["bcs"], g["B"], rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(r["sum_bcs"], g["B"].sum(0), rtol=RTOL)
+    np.testing.assert_allclose(r["ratio_stats"], g["ratio_stats"], rtol=RTOL, atol=1e-9)
+    np.testing.assert_array_equal(r["ratio_hist"], g["ratio_counts"].astype(np.uint32))   # bit-exact bins
+
+
+def test_toy_batch_with_assembled_matrix():
+    """End to end on the device: assemble -> factor -> toys; chi2 still within 1e-8 of the oracle."""
+    g = load_golden("c2_sle_n40_cspline")
+    s = make_solver(g)
+    r = s.toy_batch(g["toys"], g["bcs0"])
+    np.testing.assert_allclose(r["chi2"], g["chi2"], rtol=RTOL)
+
+
+def test_chi2_histogram_bit_exact(oracle):
+    from isrsolver_b200 import _lib as L
+    from isrsolver_b200.pyisr import _ctx
+    rng = np.random.default_rng(11)
+    chi2 = rng.chisquare(100, 200001)
+    lo, hi = C.c_double(), C.c_double(); cnt = np.zeros(130, dtype=np.uint32)
+    L.check(L.load().isr_chi2_histogram(_ctx(), len(chi2), L.dptr(chi2), 128, C.byref(lo), C.byref(hi), L.uptr(cnt)))
+    ref, idx, rlo, rhi = oracle.chi2_histogram(chi2)
+    assert (lo.value, hi.value) == (rlo, rhi)
+    np.testing.assert_array_equal(cnt, ref.astype(np.uint32))
+    assert cnt[129] >= 1 and cnt[0] == 0          # the maximum lands in the overflow cell
+
+
+@pytest.mark.parametrize("n,T", [(3, 1), (7, 5), (33, 129), (101, 1000), (64, 64), (199, 333)])
+def test_ragged_shapes(oracle, n, T):
+    """Odd N (padded leading dimension), T smaller than a tile, T not a multiple of the tile."""
+    import isrsolver_b200 as isr
+    rng = np.random.default_rng(n * 1000 + T)
+    ecm = np.sort(1.0 + rng.random(n)) ; ecm += np.arange(n) * 1e-3
+    G = np.tril(rng.random((n, n)) * 0.1) + np.eye(n) + (0.01 * rng.random((n, n)) if n % 2 else 0)
+    vcs_err = 0.05 + 0.1 * rng.random(n)
+    b0 = 1.0 + rng.random(n)
+    V = (G @ b0)[None, :] + vcs_err[None, :] * rng.standard_normal((T, n))
+    s = isr.ISRSolverSLE(n, ecm, G @ b0, None, vcs_err, 0.9)
+    s.set_matrix(G)
+    r = s.toy_batch(V, b0, want_sum=True, want_ratio=True, want_bcs=True)
+    c2, B = oracle.chi2_test_fair(G, V, b0, vcs_err)
+    np.testing.assert_allclose(r["chi2"], c2, rtol=RTOL)
+    np.testing.assert_allclose(r["bcs"], B, rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(r["sum_bcs"], B.sum(0), rtol=RTOL)
+    s.solve()
+    bo, covo = oracle.sle_solve(G, G @ b0, vcs_err)
+    np.testing.assert_allclose(s.bcs(), bo, rtol=RTOL)
+
+
+def test_empty_batch():
+    import isrsolver_b200 as isr
+    g = load_golden("c1_sle_n50_linear")
+    s = make_solver(g)
+    s.set_matrix(g["G_converged"])
+    r = s.toy_batch(np.empty((0, 50)), g["bcs0"], want_sum=True, want_ratio=True)
+    assert r["chi2"].shape == (0,) and np.all(r["sum_bcs"] == 0) and np.all(r["ratio_stats"] == 0)
+
+
+def test_call_order_errors():
+    import isrsolver_b200 as isr
+    from isrsolver_b200 import _lib as L
+    g = load_golden("c1_sle_n50_linear")
+    s = make_solver(g)
+    chi2 = np.empty(4)
+    rc = L.load().isr_toy_batch(s._p, 4, L.dptr(g["toys"][:4].copy()), L.dptr(g["bcs0"]), L.dptr(chi2), None, None, None, None)
+    assert rc == L.ISR_ESTATE
+    with pytest.raises(ValueError):
+        s2 = make_solver(g); s2._vcs_err[3] = 0.0; s2.solve()
+    sing = make_solver(g); sing.set_matrix(np.ones((50, 50)))
+    with pytest.raises(isr.IsrGpuError):
+        sing.solve()
+
+
+def test_deterministic_repeat():
+    """Same inputs -> bit-identical outputs (fixed-order reductions, no floating-point atomics)."""
+    g = load_golden("c2_sle_n40_cspline")
+    s = make_solver(g); s.set_matrix(g["G_converged"])
+    V = np.tile(g["toys"], (40, 1))
+    a = s.toy_batch(V, g["bcs0"], want_sum=True, want_ratio=True)
+    b = s.toy_batch(V, g["bcs0"], want_sum=True, want_ratio=True)
+    for k in a:
+        np.testing.assert_array_equal(a[k], b[k])
+
+
+def test_full_size_toy_properties(oracle):
+    """BASELINE size (N = 200, 2^18 toys here; the bench runs 2^20) through size-independent properties:
+    chi2_k = |W^(1/2)(v_k - G b0)|^2 (survey A.7), linearity of the solve, chi2 ~ chi2(N)."""
+    import isrsolver_b200 as isr
+    n, T = 200, 1 << 18
+    ecm = np.linspace(1.18, 2.0, n)
+    s = isr.ISRSolverSLE(n, ecm, np.ones(n), None, np.ones(n), 0.827)
+    s.set_interp_settings([(False, 0, 0), (True, 1, n - 1)])
+    s.eval_equation_matrix()
+    G = s.intop_matrix().copy()
+    b0 = oracle.bw_born(ecm); vcs = G @ b0; err = 0.05 * vcs
+    s.resetVisibleCS(vcs); s.resetVisibleCSErrors(err)
+    V = isr.draw_toys(vcs, err, T)
+    r = s.toy_batch(V, b0, want_sum=True)
+    z = (V - vcs[None, :]) / err[None, :]
+    np.testing.assert_allclose(r["chi2"], (z * z).sum(1), rtol=RTOL)
+    assert r["chi2"].mean() == pytest.approx(n, rel=5e-3)
+    # linearity: sum_k b_k = G^-1 sum_k v_k
+    np.testing.assert_allclose(r["sum_bcs"], np.linalg.solve(G, V.sum(0)), rtol=RTOL)
+    # first toys against the oracle loop
+    c2, B = oracle.chi2_test_fair(G, V[:512], b0, err)
+    np.testing.assert_allclose(r["chi2"][:512], c2, rtol=RTOL)
+
+
+def test_chi2_test_model_and_ratio_api(tmp_path, oracle):
+    """PyISR surface: chi2_test_model / ratio_test_model with .npz model files."""
+    g = load_golden("c2_sle_n40_cspline")
+    s = make_solver(g)
+    model = tmp_path / "model.npz"
+    np.savez(model, vcsBlured=np.stack([g["ecm"], g["vcs"], 0 * g["vcs"], g["vcs_err"]]),
+             bcsSRC=np.stack([g["ecm"], g["bcs0"], 0 * g["ecm"], 0 * g["ecm"]]))
+    out = tmp_path / "chi2.npz"
+    res = s.chi2_test_model(n=len(g["toys"]), initial_ampl=1e4, model_path=str(model), model_visible_cs_name="vcsBlured",
+                            model_born_cs_name="bcsSRC", output_path=str(out))
+    np.testing.assert_allclose(res["chi2"], g["chi2"], rtol=1e-7)     # assembled (not injected) matrix
+    h, idx, lo, hi = oracle.chi2_histogram(res["chi2"])
+    np.testing.assert_array_equal(res["hist"], h)
+    assert out.exists()
+    rr = s.ratio_test_model(n=len(g["toys"]), model_path=str(model), model_visible_cs_name="vcsBlured", model_born_cs_name="bcsSRC")
+    np.testing.assert_allclose(rr["means"], g["ratio_means"], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(rr["mean_errors"], g["ratio_mean_errors"], rtol=1e-6, atol=1e-9)
+    import isrsolver_b200 as isr
+    np.savez(model, vcsBlured=g["vcs"][:-1], bcsSRC=g["bcs0"])
+    with pytest.raises(isr.DifferentModelCrossSectionSizes):
+        s.chi2_test_model(8, 1e4, str(model), "vcsBlured", "bcsSRC")

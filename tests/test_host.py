@@ -1,0 +1,147 @@
+"""Host logic that needs no GPU: the C-ABI library loads and exports what include/isr_b200.h declares,
+error behaviour without a device, sharding/packing, and the world_size-2 gloo path of the one collective."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol():
+    from isrsolver_b200 import _lib as L
+    hdr = open(os.path.join(ROOT, "include", "isr_b200.h")).read()
+    declared = set(re.findall(r"\b(isr_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(L.SIGNATURES), declared ^ set(L.SIGNATURES)
+    lib = L.load()                     # dlopen + bind every symbol; raises if one is missing
+    for name in declared:
+        assert hasattr(lib, name)
+    out = subprocess.check_output(["nm", "-D", L.LIB_PATH]).decode()
+    exported = {l.split()[-1] for l in out.splitlines() if " T isr_" in l}
+    assert declared <= exported
+    # the product library must not link the oracle
+    assert "orc_" not in out
+
+
+def test_header_cites_reference_interfaces():
+    hdr = open(os.path.join(ROOT, "include", "isr_b200.h")).read()
+    for cite in ("src/ISRSolverSLE.cpp:138-149", "src/Chi2Test.cpp:38-60", "src/RatioTest.cpp:38-45",
+                 "src/ISRSolverTikhonov.cpp:139-155", "src/ISRSolverTSVD.cpp:53-74", "src/BaseISRSolver.cpp:232-258"):
+        assert cite in hdr
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-device failure mode")
+def test_no_cpu_fallback_without_device():
+    from isrsolver_b200 import _lib as L
+    lib = L.load()
+    h = C.c_void_p()
+    rc = lib.isr_ctx_create(0, C.byref(h))
+    assert rc == L.ISR_ECUDA and not h
+    assert b"no CPU fallback" in lib.isr_last_error()
+    import isrsolver_b200 as isr
+    with pytest.raises(isr.IsrGpuError):
+        isr.ISRSolverSLE(3, [1.0, 1.1, 1.2], [1, 1, 1], None, [0.1, 0.1, 0.1], 0.8)
+
+
+def test_product_does_not_import_oracle():
+    for root, _, files in os.walk(os.path.join(ROOT, "isrsolver_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
+                src = open(os.path.join(root, f)).read()
+                assert "isr_oracle" not in src and "libisr_oracle" not in src, f
+
+
+def test_efficiency_descriptor_validation():
+    import isrsolver_b200 as isr
+    with pytest.raises(isr.EfficiencyDimensionException):
+        isr.Efficiency("table_2d", dimension=3)
+    e = isr.Efficiency("row_table", values=np.ones((4, 10)), nx=8, xlo=0, xhi=1)
+    d = e.desc(4)
+    assert d.kind == 1 and d.nx == 8
+    with pytest.raises(ValueError):
+        e.desc(5)
+    e2 = isr.Efficiency("table_2d", values=np.ones((5, 6)), xedges=[0, .1, .3, .6, 1.0], eedges=[1.0, 1.5, 1.8, 2.5])
+    assert (e2.nx, e2.ne, e2.xhi, e2.elo) == (4, 3, 1.0, 1.0)
+    e2.desc(7)
+
+
+def test_shard_bounds_cover_exactly():
+    from isrsolver_b200.dist import shard_bounds
+    for total in (0, 1, 7, 8, 1000003):
+        for world in (1, 2, 3, 8):
+            b = [shard_bounds(total, world, r) for r in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == total
+            assert all(b[r][1] == b[r + 1][0] for r in range(world - 1))
+            sizes = [e - s for s, e in b]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_pack_unpack_roundtrip():
+    from isrsolver_b200.dist import pack, shard_bounds, unpack
+    rng = np.random.default_rng(0)
+    total, world, n = 11, 3, 4
+    chi2 = rng.random(total)
+    ms = max(shard_bounds(total, world, r)[1] - shard_bounds(total, world, r)[0] for r in range(world))
+    rows, sb, rs = [], np.zeros(n), np.zeros((n, 3))
+    for r in range(world):
+        b, e = shard_bounds(total, world, r)
+        s, t = rng.random(n), rng.random((n, 3))
+        sb += s; rs += t
+        rows.append(pack(chi2[b:e], s, t, ms))
+    c, s2, t2 = unpack(np.stack(rows), total, world, n)
+    np.testing.assert_array_equal(c, chi2)
+    np.testing.assert_allclose(s2, sb); np.testing.assert_allclose(t2, rs)
+
+
+def test_th1_counts_matches_oracle(oracle):
+    from isrsolver_b200.dist import th1_counts
+    rng = np.random.default_rng(3)
+    v = rng.chisquare(50, 5000)
+    lo, hi = v.min(), v.max()
+    ref, idx, *_ = oracle.th1_fill(v, 128, lo, hi)
+    np.testing.assert_array_equal(th1_counts(v, 128, lo, hi), ref.astype(np.uint32))
+
+
+_GLOO_WORKER = r"""
+import os, sys, numpy as np, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from isrsolver_b200.dist import all_gather_results, shard_bounds, th1_counts
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+total, n = 1001, 7
+rng = np.random.default_rng(42)
+chi2_all = rng.chisquare(n, total); B = rng.random((total, n))
+b, e = shard_bounds(total, world, rank)
+stats = np.stack([np.full(n, e - b), B[b:e].sum(0), (B[b:e] ** 2).sum(0)], 1)
+chi2, sb, rs = all_gather_results(chi2_all[b:e], B[b:e].sum(0), stats, total)
+assert np.array_equal(chi2, chi2_all)
+assert np.allclose(sb, B.sum(0), rtol=1e-13) and np.allclose(rs[:, 0], total) and np.allclose(rs[:, 2], (B ** 2).sum(0), rtol=1e-13)
+h = th1_counts(chi2, 128, chi2.min(), chi2.max())
+assert np.array_equal(h, th1_counts(chi2_all, 128, chi2_all.min(), chi2_all.max()))   # bit-identical with 1 process
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_gloo_world2_gather(tmp_path):
+    """The N>1 path on CPU: two gloo ranks shard 1001 toys, one all_gather, identical histogram."""
+    w = tmp_path / "worker.py"
+    w.write_text(_GLOO_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29631", str(w), ROOT],
+                         env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok") == 2
