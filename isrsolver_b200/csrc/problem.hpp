@@ -64,7 +64,7 @@ struct isr_problem {
   // ---- Tikhonov ------------------------------------------------------------------------------
   bool tik_ready = false;
   int tik_deriv = 1;
-  isr::DevBuf<double> d_F, d_U, d_mu, d_P, d_FU, d_w, d_tmp2, d_E;
+  isr::DevBuf<double> d_F, d_U, d_mu, d_P, d_FU, d_w, d_tmp2, d_E, d_E2;
   std::vector<double> h_mu;
 
   // ---- SVD -----------------------------------------------------------------------------------

@@ -308,13 +308,13 @@ int tikhonov_toy_scan_device(isr_problem* p, int64_t L, const double* lambda, in
   ISR_CUDA(cudaFuncSetAttribute(lambda_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // chunk so that E (T x ld) stays modest; the scan reads E once per chunk
   const int64_t Tc = std::min<int64_t>(T, 1 << 18);
-  ISR_TRY(p->d_E.reserve((size_t)Tc * ld));
+  ISR_TRY(p->d_E2.reserve((size_t)Tc * ld));
   for (int64_t t0 = 0; t0 < T; t0 += Tc) {
     const int64_t tc = std::min<int64_t>(Tc, T - t0);
-    ISR_TRY(project_device(p, tc, V_dev + t0 * n, dPe.p, dg.p + n, p->d_E.p));
+    ISR_TRY(project_device(p, tc, V_dev + t0 * n, dPe.p, dg.p + n, p->d_E2.p));
     // output rows (one per lambda) have the full stride T; this chunk starts at column t0
     lambda_scan_kernel<<<(unsigned)((tc + kScanToys - 1) / kScanToys), 256, smem, st>>>(
-        n, ld, tc, p->d_E.p, dg.p + 2 * n, L, dlam.p, chi2_dev + t0, T); ISR_COUNT_LAUNCH();
+        n, ld, tc, p->d_E2.p, dg.p + 2 * n, L, dlam.p, chi2_dev + t0, T); ISR_COUNT_LAUNCH();
   }
   ISR_CUDA(cudaGetLastError());
   ISR_CUDA(cudaStreamSynchronize(st));  // dlam / db0 / dg / dPe go out of scope

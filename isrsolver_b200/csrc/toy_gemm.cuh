@@ -1,131 +1,232 @@
-// FP64 tensor-pipe (DMMA, mma.sync.m8n8k4.f64) tile kernel behind the toy batch:
-//     C[t, n] = sum_k A[t, k] * B[n, k]          A: T x K (toy-major), B: N x K (row-major operator)
-// with fused epilogues.  The toy batch calls it twice (toy_batch.cu): pass 1 with B = S (solve
-// operator, b = S v), epilogue "solve"; pass 2 with B = R (chi2 factor) on D = b - b0, epilogue
-// "chi2".  North-star rule: DMMA is used because the probe in tools/fp64_peaks.cu measured 37.1
-// TFLOP/s for the tensor pipe against 33.3 TFLOP/s for DFMA on this B200 (profiles/fp64_peaks_r01.json);
-// the DFMA variant below stays selectable (isr_set_toy_kernel) for the ncu comparison.
+// Fused FP64 tensor-pipe (DMMA, mma.sync.m8n8k4.f64) kernel of the toy batch.  Per toy k:
+//     pass 1   b_k    = S v_k               (S: N x N solve operator)        2 N^2 flop
+//     pass 2   chi2_k = | R (b_k - b0) |^2  (R: N x N chi2 factor)           2 N^2 flop
+// Both passes are the same tile product  C[t, n] = sum_k A[t, k] * B[n, k]  (A toy-major, B row-major,
+// K contiguous in both) with different epilogues.  ONE persistent launch does both: a CTA owns tiles of
+// TM toys; for each tile it runs pass 1 (epilogue: d = b - b0 into a small per-CTA ring in global memory
+// that stays in L2, optional b output, column statistics) and later pass 2 on the same tile (epilogue:
+// row sums of squares -> chi2).  The passes of consecutive tiles are interleaved
+//     P1(0) P1(1) P2(0) P1(2) P2(1) ... P2(m-1)
+// so that the d-tile a pass 2 streams back was stored a whole tile-pass earlier.
 //
-// Tiling: one CTA = WM x WN warps, warp tile = (AT*8 toys) x (BT*8 columns); K streamed in chunks of
-// 24 doubles through a cp.async (LDGSTS) ring of STAGES buffers.  Rows are 24 doubles = 192 B, i.e.
-// stride = 8 (mod 16) doubles, which makes the 16-byte fragment loads below bank-conflict free with
-// no padding.  Each 16-byte load feeds two DMMAs: the k-permutation {2c, 2c+1} is applied to A and B
-// alike, so the contraction is unchanged.
+// TMA pipeline without a block-wide barrier: every K chunk is two cp.async.bulk.tensor (TMA) box loads
+// (A box TM x 24 doubles, B box NP x 24 doubles) into a ring of STAGES shared-memory buffers, completion
+// signalled on a "full" mbarrier per stage.  All WM x WN warps are consumers; when a warp is done with a
+// stage it bumps a shared counter, and the LAST warp to finish a stage immediately issues the TMA loads
+// of the chunk STAGES ahead into it (so there is no dedicated producer warp -- 21 warps would cap the
+// register file at 80 registers/thread on one SM sub-partition -- and no per-chunk __syncthreads: the
+// warps drift apart and the DMMA pipe stays fed while others sit in an epilogue).  Out-of-range rows /
+// columns are zero-filled by the TMA unit (no bounds code in the loop).
+//
+// North-star rule: DMMA is used because tools/fp64_peaks.cu measured 37.1 TFLOP/s for the tensor pipe
+// against 33.3 TFLOP/s for DFMA on this B200 (profiles/fp64_peaks_r01.json).
+//
+// Tiling: warp tile = (AT*8 toys) x (BT*8 columns), K chunks of 24 doubles.  Rows of 24 doubles = 192 B
+// have stride 8 (mod 16) doubles, which makes the 16-byte fragment loads conflict free without padding
+// or swizzle; each 16-byte load feeds two DMMAs (the k-permutation {2c, 2c+1} is applied to A and B
+// alike, so the contraction is unchanged).  Operators wider than one CTA tile (N > NP) are processed as
+// column blocks by the same CTA.
+// History (profiles/ncu_r01_toy_v*.txt): v1 two launches per chunk, per-tile drain: DMMA pipe 71 % busy
+// inside the kernels, 18.7 TFLOP/s overall; v2 fused cp.async version with a block barrier per chunk: 58 %
+// (every warp issued its share of the loads at the same moment, leaving the pipe idle).
 #pragma once
+
+#include <cuda.h>
 
 #include "common.cuh"
 
 namespace isr {
 
-constexpr int kKC = 24;  // K chunk (doubles); 24 = 8 (mod 16) keeps LDS.128 conflict-free
+constexpr int kKC = 24;        // K chunk (doubles); 24 = 8 (mod 16) keeps LDS.128 conflict-free
+constexpr int kRingSlots = 3;  // d-tiles alive per CTA (2 by schedule, +1 slack)
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+// L2 eviction-priority policies for TMA loads (same encodings CUTLASS uses for SM90+ cache hints)
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;   // toys: streamed once
+constexpr uint64_t kEvictLast = 0x14F0000000000000ull;    // operators and the d ring: reused by every tile
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;\n" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
 }
 
-enum { EPI_SOLVE = 0, EPI_CHI2 = 1 };
-
-struct GemmArgs {
-  const double* A;   // T x lda
-  const double* B;   // N x ldb (operator, row-major, K contiguous)
+struct ToyArgs {
+  const double* b0;   // N
   int64_t T;
-  int N, K, lda, ldb;
-  // EPI_SOLVE
-  const double* b0;  // N
-  double* D;         // T x ldd : b - b0 (input of pass 2)
-  int ldd;
-  double* Bout;      // T x N or nullptr : b
-  double* part;      // [gridDim.x][4][Npad_total] per-CTA partial sums {sum b, count, sum r, sum r^2} or nullptr
-  int part_ld;       // Npad_total
-  int want_ratio;    // accumulate ratio statistics
-  uint32_t* rhist;   // N x 1026 or nullptr
-  // EPI_CHI2
-  double* chi2;      // T (single column block) or partial [nblk][T]
+  int N, ld, nblk, do2;
+  double* Dring;      // [gridDim.x][kRingSlots][TM][ld]   (do2)
+  double* Dfull;      // T x ld                            (!do2: projection mode)
+  double* Bout;       // T x N or nullptr
+  double* chi2;       // T or nullptr
+  double* part;       // [gridDim.x][4][part_ld] per-CTA {sum b, count, sum r, sum r^2} or nullptr
+  int part_ld, nstat; // nstat = 1 (sum only) or 4
+  uint32_t* rhist;    // N x 1026 or nullptr
 };
 
-template <int WM, int WN, int AT, int BT, int STAGES, int EPI>
-__global__ void __launch_bounds__(WM* WN * 32, 1) toy_gemm_kernel(GemmArgs g) {
+// Position in the CTA's chunk stream.  Units: U1(i) = pass 1 of local tile i over all column blocks,
+// U2(i) = pass 2.  Interleaved order: U1(0) U1(1) U2(0) U1(2) U2(1) ... U2(m-1).  A d-tile must be complete
+// before the first loads of its pass 2 are issued, and loads run STAGES chunks ahead of the slowest warp:
+// at least STAGES-1 chunks must lie between the end of U1(i) and the start of U2(i).  When that does not
+// hold (a single tile, or an operator so small that a unit is shorter than STAGES-1 chunks) the
+// sequential order U1(i) NOP U2(i) is used instead, NOP being STAGES-1 empty chunks.
+enum { PH_P1 = 0, PH_P2 = 1, PH_NOP = 2 };
+struct Sched {
+  int m, u;        // local tiles, unit index
+  int nblk, nk, nop, do2, seq;
+  int cb, kc;
+  __device__ void init(int m_, int nblk_, int nk_, int nop_, int do2_) {
+    m = m_; nblk = nblk_; nk = nk_; nop = nop_; do2 = do2_; u = 0; cb = 0; kc = 0;
+    seq = (m == 1) || (nk * nblk < nop);
+  }
+  __device__ int units() const { return do2 ? (seq ? 3 * m : 2 * m) : m; }
+  __device__ bool done() const { return u >= units(); }
+  __device__ int kind() const {
+    if (!do2) return PH_P1;
+    if (seq) { const int r = u % 3; return r == 0 ? PH_P1 : (r == 1 ? PH_NOP : PH_P2); }
+    if (u == 0) return PH_P1;
+    if (u == 2 * m - 1) return PH_P2;
+    return (u & 1) ? PH_P1 : PH_P2;
+  }
+  __device__ int tile() const {   // local tile index
+    if (!do2) return u;
+    if (seq) return u / 3;
+    if (u == 0) return 0;
+    if (u == 2 * m - 1) return m - 1;
+    return (u & 1) ? (u + 1) / 2 : u / 2 - 1;
+  }
+  __device__ void advance() {
+    if (kind() == PH_NOP) {
+      if (++kc == nop) { kc = 0; ++u; }
+      return;
+    }
+    if (++kc == nk) {
+      kc = 0;
+      if (++cb == nblk) { cb = 0; ++u; }
+    }
+  }
+};
+
+template <int WM, int WN, int AT, int BT, int STAGES>
+__global__ void __launch_bounds__(WM * WN * 32, 1)
+toy_fused_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapS,
+                 const __grid_constant__ CUtensorMap mapR, const __grid_constant__ CUtensorMap mapD, ToyArgs g) {
   constexpr int TM = WM * AT * 8;
   constexpr int NP = WN * BT * 8;
-  constexpr int NTHREADS = WM * WN * 32;
+  constexpr int NCW = WM * WN;            // warps (all consumers)
+  constexpr int NCT = NCW * 32;
   constexpr int ROWS = TM + NP;
-  constexpr int PIECES = ROWS * (kKC / 2);  // 16-byte pieces per stage
-  extern __shared__ __align__(16) double smem[];
-  // layout: STAGES x [ROWS][kKC], then 4 x NP running column totals (EPI_SOLVE).  The epilogues
-  // reuse the stage buffers as scratch once the K loop has drained.
-  double* stage0 = smem;
-  double* scratch = smem + (size_t)STAGES * ROWS * kKC;
+  constexpr uint32_t STAGE_BYTES = ROWS * kKC * sizeof(double);
+  static_assert((TM * kKC * sizeof(double)) % 128 == 0 && STAGE_BYTES % 128 == 0, "TMA destinations must be 128-byte aligned");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // layout: STAGES x [ROWS][kKC] | full[STAGES] | done[STAGES] (int, padded) | sRow[2][WN][TM] | sAcc[WM][nstat][nblk*NP]
+  double* stage0 = reinterpret_cast<double*>(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * STAGE_BYTES);
+  uint64_t* full = bars;
+  int* done = reinterpret_cast<int*>(bars + STAGES);
+  double* sRowBase = reinterpret_cast<double*>(bars + 2 * STAGES + kRingSlots + 1);
+  double* sAcc = sRowBase + 2 * WN * TM;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nk = (g.ld + kKC - 1) / kKC;
+  const int64_t ntiles = (g.T + TM - 1) / TM;
+  const bool stats = g.part != nullptr;
+  const int accw = g.nblk * NP;
+
+  const int m = (int)(ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
+  const int ring_row0 = blockIdx.x * kRingSlots * TM;
+
+  // issue the TMA loads of the chunk at schedule position `p` into stage st (one thread)
+  auto issue = [&](const Sched& p, int st) {
+    const int kind = p.kind();
+    if (kind == PH_NOP) { mbar_arrive(&full[st]); return; }   // keeps the stage's phase in step
+    mbar_arrive_expect_tx(&full[st], STAGE_BYTES);
+    double* dst = stage0 + (size_t)st * ROWS * kKC;
+    const int k0 = p.kc * kKC;
+    const int lt = p.tile();
+    if (kind == PH_P1) {
+      const int64_t t0 = ((int64_t)blockIdx.x + (int64_t)lt * gridDim.x) * TM;
+      tma_load_2d(dst, &mapV, &full[st], k0, (int)t0, kEvictFirst);
+      tma_load_2d(dst + TM * kKC, &mapS, &full[st], k0, p.cb * NP, kEvictLast);
+    } else {
+      tma_load_2d(dst, &mapD, &full[st], k0, ring_row0 + (lt % kRingSlots) * TM, kEvictLast);
+      tma_load_2d(dst + TM * kKC, &mapR, &full[st], k0, p.cb * NP, kEvictLast);
+    }
+  };
+
+  Sched pf;   // schedule position of the chunk STAGES ahead of the one this warp consumes
+  pf.init(m, g.nblk, nk, STAGES - 1, g.do2);
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); done[s] = 0; }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (stats) {
+    for (int q = tid; q < WM * g.nstat * accw; q += NCT) sAcc[q] = 0.0;
+  }
+  __syncthreads();   // the only block-wide barrier
+  for (int s = 0; s < STAGES; ++s) {   // prologue: chunks 0 .. STAGES-1
+    if (!pf.done()) {
+      if (tid == 0) issue(pf, s);
+      pf.advance();
+    }
+  }
+
   const int wm = warp / WN, wn = warp % WN;
   const int gq = lane >> 2, c = lane & 3;
-  const int n0 = blockIdx.y * NP;
-  const int nk = (g.K + kKC - 1) / kKC;
-  const int64_t ntiles = (g.T + TM - 1) / TM;
+  double* ring = g.do2 ? g.Dring + (size_t)blockIdx.x * kRingSlots * TM * g.ld : nullptr;
+  auto consumer_barrier = [&]() { asm volatile("bar.sync 1, %0;\n" ::"n"(NCT) : "memory"); };
 
-  // per-CTA running column statistics (EPI_SOLVE): scratch[4][NP] totals + [WM][4][NP] per-tile partials
-  double* sTot = scratch;
-  double* sPart = stage0;   // [WM][4][NP], valid only inside the epilogue
-  if (EPI == EPI_SOLVE && g.part) {
-    for (int q = tid; q < 4 * NP; q += NTHREADS) sTot[q] = 0.0;
-  }
-  __syncthreads();
-
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t t0 = tile * TM;
+  if (m > 0) {
+    Sched q;
+    q.init(m, g.nblk, nk, STAGES - 1, g.do2);
+    int s = 0, parity = 0;
+    uint32_t ph = 0;
     double acc[AT][BT][2];
+    while (!q.done()) {
+      const int kind = q.kind();
+      mbar_wait(&full[s], ph);
+      if (kind != PH_NOP) {
+      if (q.kc == 0) {
 #pragma unroll
-    for (int i = 0; i < AT; ++i)
+        for (int i = 0; i < AT; ++i)
 #pragma unroll
-      for (int j = 0; j < BT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-    auto load_chunk = [&](int kc, int st) {
-      double* dst = stage0 + (size_t)st * ROWS * kKC;
-      const int k0 = kc * kKC;
-      for (int q = tid; q < PIECES; q += NTHREADS) {
-        const int row = q / (kKC / 2), pc = q % (kKC / 2);
-        const int k = k0 + pc * 2;
-        const double* src;
-        int bytes = 0;
-        if (row < TM) {
-          const int64_t t = t0 + row;
-          src = g.A;
-          if (t < g.T && k < g.K) { src = g.A + t * g.lda + k; bytes = 16; }
-        } else {
-          const int n = n0 + row - TM;
-          src = g.B;
-          if (n < g.N && k < g.K) { src = g.B + (size_t)n * g.ldb + k; bytes = 16; }
-        }
-        cp_async16(dst + row * kKC + pc * 2, src, bytes);
+          for (int j = 0; j < BT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
       }
-    };
-
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) {
-      if (s < nk) load_chunk(s, s);
-      cp_async_commit();
-    }
-    for (int kc = 0; kc < nk; ++kc) {
-      cp_async_wait<STAGES - 2>();
-      __syncthreads();
-      {  // prefetch chunk kc + STAGES - 1 into the buffer freed by iteration kc - 1
-        const int nxt = kc + STAGES - 1;
-        if (nxt < nk) load_chunk(nxt, nxt % STAGES);
-        cp_async_commit();
-      }
-      const double* sA = stage0 + (size_t)(kc % STAGES) * ROWS * kKC;
+      const double* sA = stage0 + (size_t)s * ROWS * kKC;
       const double* sB = sA + TM * kKC;
-      const int ksteps = min(kKC, g.K - kc * kKC + 7) / 8;  // 8 physical k per double-step
+      const int ksteps = min(kKC, g.ld - q.kc * kKC + 7) / 8;  // 8 physical k per double-step
 #pragma unroll
       for (int kp = 0; kp < kKC / 8; ++kp) {
         if (kp < ksteps) {
@@ -139,132 +240,154 @@ __global__ void __launch_bounds__(WM* WN * 32, 1) toy_gemm_kernel(GemmArgs g) {
 #pragma unroll
           for (int i = 0; i < AT; ++i)
 #pragma unroll
-            for (int j = 0; j < BT; ++j) {
-              dmma884(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
-              dmma884(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
-            }
+            for (int j = 0; j < BT; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
+#pragma unroll
+          for (int i = 0; i < AT; ++i)
+#pragma unroll
+            for (int j = 0; j < BT; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
         }
       }
-    }
-    cp_async_wait<0>();
-    __syncthreads();  // every warp is done with the last stage: the stage buffers become scratch
 
-    // ------------------------------------------------------------------ epilogues
-    if (EPI == EPI_SOLVE) {
-      const bool stats = g.part != nullptr;
+      if (q.kc == nk - 1) {
+        const int lt = q.tile();
+        const int64_t t0 = ((int64_t)blockIdx.x + (int64_t)lt * gridDim.x) * TM;
+        const int n0 = q.cb * NP;
+        if (kind == PH_P1) {
+          // ------------------------------------------------------------ pass-1 epilogue
+          double* Dt = g.do2 ? ring + (size_t)(lt % kRingSlots) * TM * g.ld : g.Dfull + t0 * g.ld;
 #pragma unroll
-      for (int j = 0; j < BT; ++j) {
-        const int col = n0 + (wn * BT + j) * 8 + 2 * c;
-        const bool ok0 = col < g.N, ok1 = col + 1 < g.N;
-        const double b00 = ok0 ? g.b0[col] : 0.0, b01 = ok1 ? g.b0[col + 1] : 0.0;
-        double cs[2] = {0, 0}, cn[2] = {0, 0}, cr[2] = {0, 0}, cq[2] = {0, 0};
+          for (int j = 0; j < BT; ++j) {
+            const int col = n0 + (wn * BT + j) * 8 + 2 * c;
+            const bool ok0 = col < g.N, ok1 = col + 1 < g.N;
+            const double b00 = ok0 ? g.b0[col] : 0.0, b01 = ok1 ? g.b0[col + 1] : 0.0;
+            double cs[2] = {0, 0}, cn[2] = {0, 0}, cr[2] = {0, 0}, cq[2] = {0, 0};
 #pragma unroll
-        for (int i = 0; i < AT; ++i) {
-          const int64_t t = t0 + (wm * AT + i) * 8 + gq;
-          if (t < g.T) {
-            const double v0 = acc[i][j][0], v1 = acc[i][j][1];
-            const double d0 = v0 - b00, d1 = v1 - b01;
-            if (ok1) {
-              *reinterpret_cast<double2*>(g.D + t * g.ldd + col) = make_double2(d0, d1);
-            } else if (ok0) {
-              g.D[t * g.ldd + col] = d0;
-            }
-            if (g.Bout) {
-              if (ok0) g.Bout[t * g.N + col] = v0;
-              if (ok1) g.Bout[t * g.N + col + 1] = v1;
-            }
-            cs[0] += v0;
-            cs[1] += v1;
-            if (g.want_ratio) {
-              // TH1F(1024, -2, 2)::Fill((b - b0)/b0): statistics of in-range entries only
-              // (src/RatioTest.cpp:36,43,51-52)
-              const double r0 = d0 / b00, r1 = d1 / b01;
-              if (ok0 && r0 >= -2.0 && r0 < 2.0) { cn[0] += 1.0; cr[0] += r0; cq[0] += r0 * r0; }
-              if (ok1 && r1 >= -2.0 && r1 < 2.0) { cn[1] += 1.0; cr[1] += r1; cq[1] += r1 * r1; }
-              if (g.rhist) {
-                if (ok0) {
-                  int bin = r0 < -2.0 ? 0 : (!(r0 < 2.0) ? 1025 : 1 + (int)__ddiv_rn(__dmul_rn(1024.0, __dsub_rn(r0, -2.0)), 4.0));
-                  atomicAdd(&g.rhist[(size_t)col * 1026 + bin], 1u);
-                }
+            for (int i = 0; i < AT; ++i) {
+              const int r = (wm * AT + i) * 8 + gq;
+              const int64_t t = t0 + r;
+              if (t < g.T) {
+                const double v0 = acc[i][j][0], v1 = acc[i][j][1];
+                const double d0 = v0 - b00, d1 = v1 - b01;
                 if (ok1) {
-                  int bin = r1 < -2.0 ? 0 : (!(r1 < 2.0) ? 1025 : 1 + (int)__ddiv_rn(__dmul_rn(1024.0, __dsub_rn(r1, -2.0)), 4.0));
-                  atomicAdd(&g.rhist[(size_t)(col + 1) * 1026 + bin], 1u);
+                  *reinterpret_cast<double2*>(Dt + (size_t)r * g.ld + col) = make_double2(d0, d1);
+                } else if (ok0) {
+                  Dt[(size_t)r * g.ld + col] = d0;
+                }
+                if (g.Bout) {
+                  if (ok0) g.Bout[t * g.N + col] = v0;
+                  if (ok1) g.Bout[t * g.N + col + 1] = v1;
+                }
+                cs[0] += v0;
+                cs[1] += v1;
+                if (g.nstat == 4) {
+                  // TH1F(1024, -2, 2)::Fill((b - b0)/b0): statistics of in-range entries only
+                  // (src/RatioTest.cpp:36,43,51-52)
+                  const double r0 = d0 / b00, r1 = d1 / b01;
+                  if (ok0 && r0 >= -2.0 && r0 < 2.0) { cn[0] += 1.0; cr[0] += r0; cq[0] += r0 * r0; }
+                  if (ok1 && r1 >= -2.0 && r1 < 2.0) { cn[1] += 1.0; cr[1] += r1; cq[1] += r1 * r1; }
+                  if (g.rhist) {
+                    if (ok0) {
+                      int bin = r0 < -2.0 ? 0 : (!(r0 < 2.0) ? 1025 : 1 + (int)__ddiv_rn(__dmul_rn(1024.0, __dsub_rn(r0, -2.0)), 4.0));
+                      atomicAdd(&g.rhist[(size_t)col * 1026 + bin], 1u);
+                    }
+                    if (ok1) {
+                      int bin = r1 < -2.0 ? 0 : (!(r1 < 2.0) ? 1025 : 1 + (int)__ddiv_rn(__dmul_rn(1024.0, __dsub_rn(r1, -2.0)), 4.0));
+                      atomicAdd(&g.rhist[(size_t)(col + 1) * 1026 + bin], 1u);
+                    }
+                  }
+                }
+              }
+            }
+            if (stats) {
+              // fixed-order reduction over the 8 toy lanes; lane gq == 0 owns slot (wm, stat, column): no
+              // other thread of the CTA ever touches it, so the running sum needs no barrier or atomic.
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+#pragma unroll
+                for (int sft = 4; sft <= 16; sft <<= 1) {
+                  cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], sft);
+                  if (g.nstat == 4) {
+                    cn[e] += __shfl_xor_sync(0xffffffffu, cn[e], sft);
+                    cr[e] += __shfl_xor_sync(0xffffffffu, cr[e], sft);
+                    cq[e] += __shfl_xor_sync(0xffffffffu, cq[e], sft);
+                  }
+                }
+                if (gq == 0) {
+                  const int lc = n0 + (wn * BT + j) * 8 + 2 * c + e;
+                  double* pp = sAcc + (size_t)wm * g.nstat * accw;
+                  pp[lc] += cs[e];
+                  if (g.nstat == 4) {
+                    pp[1 * accw + lc] += cn[e];
+                    pp[2 * accw + lc] += cr[e];
+                    pp[3 * accw + lc] += cq[e];
+                  }
                 }
               }
             }
           }
-        }
-        if (stats) {
-          // fixed-order reduction: the 8 toy lanes by shuffles here, the WM warps through smem below
+          // order this warp's generic-proxy stores of d before the TMA (async proxy) reads of pass 2; the
+          // stage hand-over below (fence + counter) then publishes them to whichever thread issues those loads
+          if (g.do2) asm volatile("fence.proxy.async;\n" ::: "memory");
+        } else {
+          // ------------------------------------------------------------ pass-2 epilogue
+          // chi2_t = sum_n C[t, n]^2: thread-local, then the 4 column lanes, then the WN warps (fixed order)
+          double* sRow = sRowBase + (size_t)parity * WN * TM;
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
+          for (int i = 0; i < AT; ++i) {
+            double sum = 0.0;
 #pragma unroll
-            for (int sft = 4; sft <= 16; sft <<= 1) {
-              cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], sft);
-              cn[e] += __shfl_xor_sync(0xffffffffu, cn[e], sft);
-              cr[e] += __shfl_xor_sync(0xffffffffu, cr[e], sft);
-              cq[e] += __shfl_xor_sync(0xffffffffu, cq[e], sft);
-            }
-            if (gq == 0) {
-              const int lc = (wn * BT + j) * 8 + 2 * c + e;
-              double* pp = sPart + (size_t)wm * 4 * NP;
-              pp[0 * NP + lc] = cs[e];
-              pp[1 * NP + lc] = cn[e];
-              pp[2 * NP + lc] = cr[e];
-              pp[3 * NP + lc] = cq[e];
+            for (int j = 0; j < BT; ++j) sum += acc[i][j][0] * acc[i][j][0] + acc[i][j][1] * acc[i][j][1];
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            if (c == 0) sRow[wn * TM + (wm * AT + i) * 8 + gq] = sum;
+          }
+          consumer_barrier();
+          for (int r = tid; r < TM; r += NCT) {
+            const int64_t t = t0 + r;
+            if (t < g.T) {
+              double sum = 0.0;
+#pragma unroll
+              for (int w = 0; w < WN; ++w) sum += sRow[w * TM + r];
+              if (q.cb == 0) g.chi2[t] = sum; else g.chi2[t] += sum;   // column blocks accumulate in order
             }
           }
+          parity ^= 1;   // the next tile writes the other buffer: no second barrier needed
         }
       }
-      if (stats) {
-        __syncthreads();
-        for (int q = tid; q < 4 * NP; q += NTHREADS) {
-          double s = sTot[q];
-#pragma unroll
-          for (int w = 0; w < WM; ++w) s += sPart[(size_t)w * 4 * NP + q];
-          sTot[q] = s;
+      }  // kind != PH_NOP
+
+      // hand the stage back: the last warp to finish it refills it with the chunk STAGES ahead
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence_block();
+        if (atomicAdd(&done[s], 1) == NCW - 1) {
+          done[s] = 0;
+          __threadfence_block();
+          if (!pf.done()) issue(pf, s);
         }
       }
-    } else {
-      // chi2_t = sum_n C[t, n]^2 : thread-local, then the 4 column lanes, then the WN warps (fixed order)
-      double* sRow = stage0;  // [WN][TM]
-#pragma unroll
-      for (int i = 0; i < AT; ++i) {
-        double s = 0.0;
-#pragma unroll
-        for (int j = 0; j < BT; ++j) s += acc[i][j][0] * acc[i][j][0] + acc[i][j][1] * acc[i][j][1];
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if (c == 0) sRow[wn * TM + (wm * AT + i) * 8 + gq] = s;
-      }
-      __syncthreads();
-      for (int r = tid; r < TM; r += NTHREADS) {
-        const int64_t t = t0 + r;
-        if (t < g.T) {
-          double s = 0.0;
-#pragma unroll
-          for (int w = 0; w < WN; ++w) s += sRow[w * TM + r];
-          g.chi2[(size_t)blockIdx.y * g.T + t] = s;
-        }
-      }
+      pf.advance();
+      q.advance();
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
     }
-    __syncthreads();  // smem stages and scratch are reused by the next tile
   }
 
-  if (EPI == EPI_SOLVE && g.part) {
-    for (int q = tid; q < 4 * NP; q += NTHREADS) {
-      const int stat = q / NP, lc = q % NP;
-      g.part[((size_t)blockIdx.x * 4 + stat) * g.part_ld + n0 + lc] = sTot[q];
+  if (stats) {
+    consumer_barrier();
+    for (int q = tid; q < g.nstat * accw; q += NCT) {
+      double sum = 0.0;
+#pragma unroll
+      for (int w = 0; w < WM; ++w) sum += sAcc[(size_t)w * g.nstat * accw + q];
+      g.part[((size_t)blockIdx.x * 4 + q / accw) * g.part_ld + q % accw] = sum;
     }
   }
 }
 
 template <int WM, int WN, int AT, int BT, int STAGES>
-constexpr size_t toy_gemm_smem() {
+constexpr size_t toy_fused_smem_base() {
   constexpr int TM = WM * AT * 8, NP = WN * BT * 8;
-  static_assert((size_t)WM * 4 * NP <= (size_t)STAGES * (TM + NP) * kKC, "epilogue scratch must fit the stage buffers");
-  static_assert((size_t)WN * TM <= (size_t)STAGES * (TM + NP) * kKC, "epilogue scratch must fit the stage buffers");
-  return (size_t)STAGES * (TM + NP) * kKC * sizeof(double) + (size_t)4 * NP * sizeof(double);
+  return (size_t)STAGES * (TM + NP) * kKC * sizeof(double) + (2 * STAGES + kRingSlots + 1) * sizeof(uint64_t) +
+         (size_t)2 * WN * TM * sizeof(double);
 }
 
 }  // namespace isr
