@@ -1,0 +1,293 @@
+// isr_b200.hpp -- header-only C++ mirror of the reference's solver classes for the hot path, on top of the
+// C ABI (isr_b200.h).  Same class and method names as the reference (include/BaseISRSolver.hpp,
+// include/ISRSolverSLE.hpp, include/ISRSolverTikhonov.hpp, include/ISRSolverTSVD.hpp, include/Chi2Test.hpp,
+// include/RatioTest.hpp); Eigen/ROOT types are replaced by std::vector and the small Matrix below
+// (column-major, like Eigen::MatrixXd).  Errors of the ABI are rethrown as the reference's exception types.
+//
+//   g++ -std=c++17 -Iinclude app.cpp -Lisrsolver_b200 -lisr_b200 -Wl,-rpath,$PWD/isrsolver_b200
+#ifndef ISR_B200_HPP
+#define ISR_B200_HPP
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <numeric>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "isr_b200.h"
+
+namespace isrb200 {
+
+struct InterpRangeException : std::exception {          // include/Interpolator.hpp:14-18
+  const char* what() const noexcept override { return "[!] Wrong interpolation ranges.\n"; }
+};
+struct EfficiencyDimensionException : std::exception {  // include/BaseISRSolver.hpp:24-28
+  const char* what() const noexcept override { return "[!] Wrong efficiency dimension.\n"; }
+};
+struct DifferentModelCrossSectionSizes : std::exception {  // include/Chi2Test.hpp:47-52
+  const char* what() const noexcept override { return "[!] Model visible and Born cross sections have different sizes.\n"; }
+};
+struct IsrGpuError : std::runtime_error { using std::runtime_error::runtime_error; };
+
+inline void check(int rc) {
+  if (rc == ISR_OK) return;
+  if (rc == ISR_ERANGE) throw InterpRangeException();
+  if (rc == ISR_EEFFDIM) throw EfficiencyDimensionException();
+  if (rc == ISR_EINVAL) throw std::invalid_argument(isr_last_error());
+  throw IsrGpuError(isr_last_error());
+}
+
+// Column-major dense matrix (Eigen::MatrixXd layout).
+struct Matrix {
+  int rows = 0, cols = 0;
+  std::vector<double> a;
+  Matrix() = default;
+  Matrix(int r, int c) : rows(r), cols(c), a((size_t)r * c, 0.0) {}
+  double& operator()(int i, int j) { return a[(size_t)i + (size_t)rows * j]; }
+  double operator()(int i, int j) const { return a[(size_t)i + (size_t)rows * j]; }
+  double* data() { return a.data(); }
+  const double* data() const { return a.data(); }
+};
+
+// Detection-efficiency table (what BaseISRSolver::_setupEfficiency wraps; src/BaseISRSolver.cpp:232-258).
+struct Efficiency {
+  int kind = ISR_EPS_ONE;
+  int nx = 0, ne = 0;
+  double xlo = 0, xhi = 1, elo = 0, ehi = 1;
+  std::vector<double> xedges, eedges, values;
+  isr_eps_desc desc() const {
+    isr_eps_desc d{};
+    d.kind = kind; d.nx = nx; d.xlo = xlo; d.xhi = xhi; d.ne = ne; d.elo = elo; d.ehi = ehi;
+    d.xedges = xedges.empty() ? nullptr : xedges.data();
+    d.eedges = eedges.empty() ? nullptr : eedges.data();
+    d.values = values.empty() ? nullptr : values.data();
+    return d;
+  }
+};
+
+class Context {
+ public:
+  static isr_ctx* get(int device = 0) {
+    static std::vector<isr_ctx*> ctxs(64, nullptr);
+    if (!ctxs.at(device)) check(isr_ctx_create(device, &ctxs[device]));
+    return ctxs[device];
+  }
+};
+
+struct Chi2TestArgs { int n; double initialChi2Ampl; std::string outputPath; };   // include/ISRSolverStructs.hpp
+struct Chi2TestResult { std::vector<double> chi2; std::vector<float> hist; double chi2Min, chi2Max; };
+struct RatioTestResult { std::vector<double> means, meanErrors; std::vector<uint32_t> hist; };
+
+class BaseISRSolver {   // include/BaseISRSolver.hpp:30-120
+ public:
+  // src/BaseISRSolver.cpp:77-129: copy, sort by energy through an index permutation; energyErr == nullptr
+  // switches the energy spread off.
+  BaseISRSolver(std::size_t numberOfPoints, const double* energy, const double* visibleCS, const double* energyErr,
+                const double* visibleCSErr, double thresholdEnergy, const Efficiency& efficiency = Efficiency(),
+                int device = 0)
+      : _n(numberOfPoints), _energyT(thresholdEnergy), _energySpread(energyErr != nullptr), _eff(efficiency) {
+    std::vector<int> index(_n);
+    std::iota(index.begin(), index.end(), 0);
+    std::sort(index.begin(), index.end(), [energy](int a, int b) { return energy[a] < energy[b]; });
+    _ecm.resize(_n); _ecmErr.assign(_n, 0.0); _vcs.resize(_n); _vcsErr.resize(_n); _bcs.assign(_n, 0.0);
+    for (std::size_t i = 0; i < _n; ++i) {
+      _ecm[i] = energy[index[i]]; _vcs[i] = visibleCS[index[i]]; _vcsErr[i] = visibleCSErr[index[i]];
+      if (energyErr) _ecmErr[i] = energyErr[index[i]];
+    }
+    _ctx = Context::get(device);
+    isr_eps_desc d = _eff.desc();
+    check(isr_problem_create(_ctx, (int)_n, _ecm.data(), _energyT, 0, nullptr, _eff.kind == ISR_EPS_ONE ? nullptr : &d, &_p));
+  }
+  BaseISRSolver(const BaseISRSolver&) = delete;
+  BaseISRSolver& operator=(const BaseISRSolver&) = delete;
+  virtual ~BaseISRSolver() { isr_problem_destroy(_p); }
+  virtual void solve() = 0;
+  std::size_t getN() const { return _n; }
+  double getThresholdEnergy() const { return _energyT; }
+  double getMinEnergy() const { return _ecm.front(); }
+  double getMaxEnergy() const { return _ecm.back(); }
+  const std::vector<double>& bcs() const { return _bcs; }
+  const std::vector<double>& ecm() const { return _ecm; }
+  const std::vector<double>& ecmErr() const { return _ecmErr; }
+  const std::vector<double>& vcs() const { return _vcs; }
+  const std::vector<double>& vcsErr() const { return _vcsErr; }
+  bool isEnergySpreadEnabled() const { return _energySpread; }
+  void enableEnergySpread() { _energySpread = true; invalidate(); }
+  void disableEnergySpread() { _energySpread = false; invalidate(); }
+  void resetVisibleCS(const std::vector<double>& v) { _vcs = v; }
+  void resetVisibleCSErrors(const std::vector<double>& e) { _vcsErr = e; _factored = false; }
+  void resetECMErrors(const std::vector<double>& e) { _ecmErr = e; invalidate(); }
+  isr_problem* gpuProblem() { return _p; }
+
+ protected:
+  virtual void invalidate() { _isEqMatrixPrepared = false; _factored = false; }
+  std::size_t _n;
+  double _energyT;
+  bool _energySpread;
+  Efficiency _eff;
+  std::vector<double> _ecm, _ecmErr, _vcs, _vcsErr, _bcs;
+  isr_ctx* _ctx = nullptr;
+  isr_problem* _p = nullptr;
+  bool _isEqMatrixPrepared = false, _factored = false;
+};
+
+class ISRSolverSLE : public BaseISRSolver {   // include/ISRSolverSLE.hpp
+ public:
+  using BaseISRSolver::BaseISRSolver;
+  void setRangeInterpSettings(const std::vector<std::tuple<bool, int, int>>& s) {   // src/ISRSolverSLE.cpp:125-128
+    std::vector<int> flat;
+    for (const auto& t : s) { flat.push_back(std::get<0>(t)); flat.push_back(std::get<1>(t)); flat.push_back(std::get<2>(t)); }
+    check(isr_problem_set_ranges(_p, (int)s.size(), flat.data()));
+    invalidate();
+  }
+  void evalEqMatrix() {   // src/ISRSolverSLE.cpp:138-149
+    _integralOperatorMatrix = Matrix((int)_n, (int)_n);
+    check(isr_assemble(_p, _energySpread ? _ecmErr.data() : nullptr, _integralOperatorMatrix.data()));
+    _isEqMatrixPrepared = true;
+    _factored = false;
+  }
+  void solve() override {   // src/ISRSolverSLE.cpp:86-95
+    ensureFactored();
+    _covMatrixBornCS = Matrix((int)_n, (int)_n);
+    check(isr_solve(_p, _vcs.data(), _bcs.data(), _covMatrixBornCS.data()));
+  }
+  const Matrix& getIntegralOperatorMatrix() const { return _integralOperatorMatrix; }
+  const Matrix& getBornCSCovMatrix() const { return _covMatrixBornCS; }
+  double interpEval(const std::vector<double>& y, double energy) const {   // :195-198
+    double out = 0;
+    check(isr_interp_eval(_p, y.data(), 1, &energy, &out));
+    return out;
+  }
+  double evalConditionNumber() {   // :200-204
+    if (!_isEqMatrixPrepared) evalEqMatrix();
+    double c = 0;
+    check(isr_cond_number(_p, &c));
+    return c;
+  }
+  // the toy loop body for T toys (toy-major V); any output may be nullptr
+  virtual void toyBatch(int64_t T, const double* V, const double* bcs0, double* chi2, double* sumBcs, double* ratioStats,
+                        uint32_t* ratioHist, double* bcsOut) {
+    selectForToys();
+    check(isr_toy_batch(_p, T, V, bcs0, chi2, sumBcs, ratioStats, ratioHist, bcsOut));
+  }
+
+ protected:
+  virtual void ensureFactored() {
+    if (!_isEqMatrixPrepared) evalEqMatrix();
+    if (!_factored) { check(isr_factor(_p, _vcsErr.data())); _factored = true; }
+  }
+  virtual void selectForToys() { ensureFactored(); }
+  Matrix _integralOperatorMatrix, _covMatrixBornCS;
+};
+
+class ISRSolverTikhonov : public ISRSolverSLE {   // include/ISRSolverTikhonov.hpp
+ public:
+  using ISRSolverSLE::ISRSolverSLE;
+  double getLambda() const { return _lambda; }
+  void setLambda(double l) { _lambda = l; }
+  bool isDerivNorm2RegIsEnabled() const { return _derivReg; }
+  void enableDerivNorm2Regularizator() { _derivReg = true; _tik = false; }
+  void disableDerivNorm2Regularizator() { _derivReg = false; _tik = false; }
+  void solve() override {   // src/ISRSolverTikhonov.cpp:61-72
+    ensureTik();
+    _covMatrixBornCS = Matrix((int)_n, (int)_n);
+    check(isr_tikhonov_solve(_p, _lambda, _vcs.data(), _bcs.data(), _covMatrixBornCS.data()));
+  }
+  double evalEqNorm2() { return scan1(0); }                      // :106-109
+  double evalSmoothnessConstraintNorm2() { return scan1(1); }    // :111-113
+  double evalLCurveCurvature() { return scan1(2); }              // :115-119
+  double evalLCurveCurvatureDerivative() { return scan1(3); }    // :121-128
+  // every lambda of an L-curve scan (src/isrsolver-LCurve-plot.cpp:131-151) from one decomposition
+  void scanLCurve(const std::vector<double>& lambdas, std::vector<double>& x, std::vector<double>& y,
+                  std::vector<double>& curv, std::vector<double>& dcurv) {
+    ensureTik();
+    const int64_t L = (int64_t)lambdas.size();
+    x.resize(L); y.resize(L); curv.resize(L); dcurv.resize(L);
+    check(isr_tikhonov_scan(_p, L, lambdas.data(), _vcs.data(), x.data(), y.data(), curv.data(), dcurv.data(), nullptr));
+  }
+
+ protected:
+  void invalidate() override { ISRSolverSLE::invalidate(); _tik = false; }
+  void ensureFactored() override { ensureTik(); }
+  void selectForToys() override { ensureTik(); check(isr_tikhonov_select(_p, _lambda)); }
+  void ensureTik() {
+    if (!_isEqMatrixPrepared) { evalEqMatrix(); _tik = false; }
+    if (!_tik) { check(isr_tikhonov_prepare(_p, _vcsErr.data(), _derivReg ? 1 : 0)); _tik = true; _factored = true; }
+  }
+  double scan1(int which) {
+    ensureTik();
+    double out[4];
+    check(isr_tikhonov_scan(_p, 1, &_lambda, _vcs.data(), &out[0], &out[1], &out[2], &out[3], nullptr));
+    return out[which];
+  }
+  double _lambda = 1.0;    // src/ISRSolverTikhonov.cpp:30
+  bool _derivReg = true;   // :29
+  bool _tik = false;
+};
+
+class ISRSolverTSVD : public ISRSolverSLE {   // include/ISRSolverTSVD.hpp
+ public:
+  ISRSolverTSVD(std::size_t n, const double* e, const double* v, const double* ee, const double* ve, double thr,
+                const Efficiency& eff = Efficiency(), int device = 0)
+      : ISRSolverSLE(n, e, v, ee, ve, thr, eff, device), _upperTSVDIndex((int)n) {}
+  void setUpperTSVDIndex(int k) { _upperTSVDIndex = k; }
+  int getUpperTSVDIndex() const { return _upperTSVDIndex; }
+  void enableKeepOne() { _keepOne = true; }
+  void disableKeepOne() { _keepOne = false; }
+  void solve() override {   // src/ISRSolverTSVD.cpp:53-74
+    if (!_isEqMatrixPrepared) evalEqMatrix();
+    const bool full = _upperTSVDIndex == (int)_n && !_keepOne;
+    if (full) _covMatrixBornCS = Matrix((int)_n, (int)_n);
+    check(isr_tsvd_solve(_p, _upperTSVDIndex, _keepOne ? 1 : 0, _vcs.data(), _vcsErr.data(), _bcs.data(),
+                         full ? _covMatrixBornCS.data() : nullptr));
+    _factored = false;
+  }
+
+ protected:
+  void selectForToys() override {
+    if (!_isEqMatrixPrepared) evalEqMatrix();
+    check(isr_tsvd_select(_p, _upperTSVDIndex, _keepOne ? 1 : 0, _vcsErr.data()));
+    _factored = false;
+  }
+  int _upperTSVDIndex;
+  bool _keepOne = false;
+};
+
+// chi2Test (src/Chi2Test.cpp:29-104) on caller-supplied toys (toy-major n x N); the ROOT fit/file are left to
+// the caller.  The histogram is TH1F(128, min, max) with under/overflow cells (130 floats).
+inline Chi2TestResult chi2Test(ISRSolverSLE* solver, const Chi2TestArgs& args, const std::vector<double>& toys,
+                               const std::vector<double>& bcs0) {
+  Chi2TestResult r;
+  r.chi2.resize(args.n);
+  solver->toyBatch(args.n, toys.data(), bcs0.data(), r.chi2.data(), nullptr, nullptr, nullptr, nullptr);
+  std::vector<uint32_t> counts(130);
+  check(isr_chi2_histogram(Context::get(), args.n, r.chi2.data(), 128, &r.chi2Min, &r.chi2Max, counts.data()));
+  r.hist.assign(counts.begin(), counts.end());
+  return r;
+}
+
+// ratioTestModel (src/RatioTest.cpp:13-62): mean and mean error of (b - b0)/b0 per point from TH1F(1024,-2,2).
+inline RatioTestResult ratioTestModel(ISRSolverSLE* solver, int n, const std::vector<double>& toys,
+                                      const std::vector<double>& bcs0) {
+  const std::size_t N = solver->getN();
+  if (bcs0.size() != N) throw DifferentModelCrossSectionSizes();
+  RatioTestResult r;
+  std::vector<double> stats(3 * N);
+  r.hist.assign(N * 1026, 0u);
+  solver->toyBatch(n, toys.data(), bcs0.data(), nullptr, nullptr, stats.data(), r.hist.data(), nullptr);
+  r.means.resize(N); r.meanErrors.resize(N);
+  for (std::size_t j = 0; j < N; ++j) {
+    const double c = stats[3 * j], sx = stats[3 * j + 1], sx2 = stats[3 * j + 2];
+    const double mean = c > 0 ? sx / c : 0.0;
+    const double rms = c > 0 ? std::sqrt(std::fabs(sx2 / c - mean * mean)) : 0.0;
+    r.means[j] = mean;
+    r.meanErrors[j] = c > 0 ? rms / std::sqrt(c) : 0.0;
+  }
+  return r;
+}
+
+}  // namespace isrb200
+#endif

@@ -532,30 +532,38 @@ __global__ void reduce_kernel(int n, const int* __restrict__ off, const double* 
 
 // G(i,j) = sum_{k = klo_j}^{min(khi_j, i)} sum_p M[i][k][p] * Ct[k][p][j]   (column-major output).
 // Tile: 16 rows x 64 columns per block; M rows staged through shared memory in chunks of 32 segments.
-constexpr int kCtRows = 16, kCtCols = 64, kCtK = 32;
+// The segment range is split over blockIdx.z (kCtSplit slices, partial sums combined in fixed order by
+// contract_sum_kernel) so that even N = 200 fills the machine.
+constexpr int kCtRows = 16, kCtCols = 64, kCtK = 32, kCtSplit = 4;
 __global__ void __launch_bounds__(256)
 contract_kernel(int n, const double* __restrict__ M, const double* __restrict__ Ct,
-                const int* __restrict__ klo, const int* __restrict__ khi, double* __restrict__ G) {
+                const int* __restrict__ klo, const int* __restrict__ khi, double* __restrict__ Gpart) {
   __shared__ double sM[kCtRows][kCtK * 4];
   const int j = blockIdx.x * kCtCols + (threadIdx.x & (kCtCols - 1));
   const int rsub = threadIdx.x / kCtCols;  // 0..3, each thread does 4 rows
   const int i0 = blockIdx.y * kCtRows;
   const int imax = min(n - 1, i0 + kCtRows - 1);
   const int jl = j < n ? klo[j] : n, jh = j < n ? khi[j] : -1;
-  // block-wide segment range
   __shared__ int s_lo, s_hi;
   if (threadIdx.x == 0) { s_lo = n; s_hi = -1; }
   __syncthreads();
   if (j < n) { atomicMin(&s_lo, jl); atomicMax(&s_hi, jh); }
   __syncthreads();
-  const int blo = s_lo, bhi = min(s_hi, imax);
+  // this block's slice of the block-wide segment range [blo, bhi]
+  int blo = s_lo, bhi = min(s_hi, imax);
+  {
+    const int len = max(0, bhi - blo + 1), per = (len + kCtSplit - 1) / kCtSplit;
+    const int a = blo + (int)blockIdx.z * per;
+    bhi = min(bhi, a + per - 1);
+    blo = a;
+  }
   double acc[4] = {0, 0, 0, 0};
   for (int k0 = blo; k0 <= bhi; k0 += kCtK) {
     __syncthreads();
     for (int q = threadIdx.x; q < kCtRows * kCtK * 4; q += 256) {
       const int r = q / (kCtK * 4), c = q % (kCtK * 4);
       const int i = i0 + r, k = k0 + c / 4;
-      sM[r][c] = (i < n && k < n) ? M[((size_t)i * n + k) * 4 + (c & 3)] : 0.0;
+      sM[r][c] = (i < n && k <= bhi) ? M[((size_t)i * n + k) * 4 + (c & 3)] : 0.0;
     }
     __syncthreads();
     if (j < n) {
@@ -576,9 +584,17 @@ contract_kernel(int n, const double* __restrict__ M, const double* __restrict__ 
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int i = i0 + rsub * 4 + r;
-      if (i < n) G[(size_t)i + (size_t)n * j] = acc[r];
+      if (i < n) Gpart[(size_t)blockIdx.z * n * n + (size_t)i + (size_t)n * j] = acc[r];
     }
   }
+}
+__global__ void contract_sum_kernel(int nn, const double* __restrict__ Gpart, double* __restrict__ G) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nn) return;
+  double s = 0.0;
+#pragma unroll
+  for (int z = 0; z < kCtSplit; ++z) s += Gpart[(size_t)z * nn + idx];
+  G[idx] = s;
 }
 
 // =================================================================================================
@@ -685,6 +701,7 @@ int assemble(isr_problem* p, const double* ecm_err) {
   ISR_TRY(p->d_off.reserve(nitems + 1));
   ISR_TRY(p->d_M.reserve((size_t)n * n * 4));
   ISR_TRY(p->d_G.reserve((size_t)n * n));
+  ISR_TRY(p->d_Gpart.reserve((size_t)kCtSplit * n * n));
 
   row_setup_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, p->d_ext.p, p->d_row.p); ISR_COUNT_LAUNCH();
   count_kernel<<<(nitems + 127) / 128, 128, 0, st>>>(nitems, p->d_row.p, p->eps, p->d_ext.p, p->d_cnt.p); ISR_COUNT_LAUNCH();
@@ -696,8 +713,9 @@ int assemble(isr_problem* p, const double* ecm_err) {
                                                      p->d_pa.p, p->d_pb.p, p->d_peps.p, p->d_pitem.p,
                                                      p->d_pkind.p, p->d_pm.p); ISR_COUNT_LAUNCH();
   reduce_kernel<<<(n * n + 127) / 128, 128, 0, st>>>(n, p->d_off.p, p->d_pm.p, p->d_M.p); ISR_COUNT_LAUNCH();
-  dim3 cgrid((n + kCtCols - 1) / kCtCols, (n + kCtRows - 1) / kCtRows);
-  contract_kernel<<<cgrid, 256, 0, st>>>(n, p->d_M.p, p->d_Ct.p, p->d_klo.p, p->d_khi.p, p->d_G.p); ISR_COUNT_LAUNCH();
+  dim3 cgrid((n + kCtCols - 1) / kCtCols, (n + kCtRows - 1) / kCtRows, kCtSplit);
+  contract_kernel<<<cgrid, 256, 0, st>>>(n, p->d_M.p, p->d_Ct.p, p->d_klo.p, p->d_khi.p, p->d_Gpart.p); ISR_COUNT_LAUNCH();
+  contract_sum_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(n * n, p->d_Gpart.p, p->d_G.p); ISR_COUNT_LAUNCH();
   if (ecm_err) {
     for (int i = 0; i < n; ++i)
       if (!(ecm_err[i] > 0.0)) {

@@ -347,7 +347,7 @@ int isr_chi2_histogram(isr_ctx* ctx, int64_t n, const double* chi2, int nbins, d
   if (!ctx || !chi2 || !lo_out || !hi_out || !counts_out) { set_error("NULL argument"); return ISR_EINVAL; }
   if (n <= 0) { set_error("isr_chi2_histogram: empty input"); return ISR_EINVAL; }
   ISR_CUDA(cudaSetDevice(ctx->device));
-  DevBuf<double> d;
+  DevBuf<double>& d = ctx->scratch_v;
   ISR_TRY(d.reserve(n));
   ISR_CUDA(cudaMemcpyAsync(d.p, chi2, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
   ISR_TRY(minmax_device(ctx, n, d.p, lo_out, hi_out));

@@ -112,4 +112,8 @@ struct isr_ctx {
   cudaStream_t stream = nullptr;
   cusolverDnHandle_t solver = nullptr;
   cublasHandle_t blas = nullptr;
+  // grow-only scratch for the reductions (min/max partials, histogram counters, staged chi2)
+  isr::DevBuf<double> scratch_d;
+  isr::DevBuf<uint32_t> scratch_u;
+  isr::DevBuf<double> scratch_v;
 };

@@ -30,6 +30,7 @@ struct isr_problem {
   isr::DevBuf<int> d_pitem, d_pkind;
   isr::DevBuf<double> d_M;       // [i][k][4] normalised moments
   isr::DevBuf<double> d_G;       // column-major N x N
+  isr::DevBuf<double> d_Gpart;   // split-K partials of the contraction
   isr::DevBuf<double> d_S, d_tmp, d_sigE;
   int64_t max_panels = 0;
   int64_t last_panels = 0;

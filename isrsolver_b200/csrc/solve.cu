@@ -108,11 +108,10 @@ __global__ void hist_kernel(int64_t n, const double* __restrict__ v, int nbins, 
 int minmax_device(isr_ctx* c, int64_t n, const double* v_dev, double* lo, double* hi) {
   if (n <= 0) { set_error("minmax: empty input"); return ISR_EINVAL; }
   const int blocks = (int)std::min<int64_t>(c->sm_count * 4, (n + 255) / 256);
-  DevBuf<double> part;
-  ISR_TRY(part.reserve(2 * blocks));
-  minmax_kernel<<<blocks, 256, 0, c->stream>>>(n, v_dev, part.p); ISR_COUNT_LAUNCH();
+  ISR_TRY(c->scratch_d.reserve(2 * blocks));
+  minmax_kernel<<<blocks, 256, 0, c->stream>>>(n, v_dev, c->scratch_d.p); ISR_COUNT_LAUNCH();
   std::vector<double> h(2 * blocks);
-  ISR_CUDA(cudaMemcpyAsync(h.data(), part.p, sizeof(double) * 2 * blocks, cudaMemcpyDeviceToHost, c->stream));
+  ISR_CUDA(cudaMemcpyAsync(h.data(), c->scratch_d.p, sizeof(double) * 2 * blocks, cudaMemcpyDeviceToHost, c->stream));
   ISR_CUDA(cudaStreamSynchronize(c->stream));
   double a = INFINITY, b = -INFINITY;
   for (int q = 0; q < blocks; ++q) { a = std::min(a, h[2 * q]); b = std::max(b, h[2 * q + 1]); }
@@ -123,7 +122,7 @@ int minmax_device(isr_ctx* c, int64_t n, const double* v_dev, double* lo, double
 
 int histogram_device(isr_ctx* c, int64_t n, const double* v_dev, int nbins, double lo, double hi, uint32_t* counts_host) {
   if (nbins < 1 || nbins > 8190) { set_error("histogram: nbins out of range"); return ISR_EINVAL; }
-  DevBuf<uint32_t> cnt;
+  DevBuf<uint32_t>& cnt = c->scratch_u;
   ISR_TRY(cnt.reserve(nbins + 2));
   ISR_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(uint32_t) * (nbins + 2), c->stream));
   if (n > 0) {

@@ -1,0 +1,51 @@
+"""The header-only C++ class mirror (include/isr_b200.hpp) compiled with g++ against libisr_b200.so."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+
+
+def _build(tmp_path):
+    exe = tmp_path / "test_classes"
+    lib_dir = os.path.join(ROOT, "isrsolver_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "test_classes.cpp"), "-L", lib_dir, "-lisr_b200",
+                           f"-Wl,-rpath,{lib_dir}", "-Wl,-rpath,/usr/local/cuda/lib64", "-o", str(exe)])
+    return exe
+
+
+def test_cpp_mirror_compiles_and_links(tmp_path):
+    """No GPU needed: the class mirror compiles against the header and links against the library."""
+    assert _build(tmp_path).exists()
+
+
+@pytest.mark.gpu
+def test_cpp_mirror_matches_oracle(tmp_path, oracle):
+    g = load_golden("c2_sle_n40_cspline")
+    exe = _build(tmp_path)
+    for k in ("ecm", "vcs", "vcs_err", "toys", "bcs0"):
+        np.ascontiguousarray(g[k], dtype=np.float64).tofile(tmp_path / f"{k}.bin")
+    out = subprocess.run([str(exe), str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "cpp ok" in out.stdout
+    n = len(g["ecm"])
+    rd = lambda name, shape=None: np.fromfile(tmp_path / name).reshape(shape) if shape else np.fromfile(tmp_path / name)
+    G = rd("out_G.bin", (n, n)).T                      # column-major on disk
+    assert np.all(np.abs(G - g["G_converged"]) <= 1e-9 * np.abs(g["G_converged"]) + 2e-12 + g["G_converged_err"])
+    np.testing.assert_allclose(rd("out_bcs.bin"), g["bcs"], rtol=1e-8)
+    cov = rd("out_cov.bin", (n, n)).T
+    assert np.abs(cov - g["cov"]).max() <= 1e-8 * np.abs(g["cov"]).max()
+    np.testing.assert_allclose(rd("out_chi2.bin"), g["chi2"], rtol=1e-7)
+    np.testing.assert_allclose(rd("out_means.bin"), g["ratio_means"], rtol=1e-6, atol=1e-9)
+    I = oracle.Interp(g["ecm"], 0.827)      # the Tikhonov/TSVD solvers in the C++ test keep the default linear basis
+    Gl = I.eval_eq_matrix(mode="converged")
+    F = oracle.tikhonov_F(I.deriv_projector(), I.integral_basis(), True)
+    ref = oracle.tikhonov_lcurve(Gl, g["vcs"], g["vcs_err"], F, 1e-3)
+    np.testing.assert_allclose(rd("out_tik_bcs.bin"), ref["bcs"], rtol=1e-7)
+    line = [l for l in out.stdout.splitlines() if l.startswith("tik")][0].split()
+    assert float(line[4]) == pytest.approx(ref["y"], rel=1e-7) and float(line[6]) == pytest.approx(ref["curv"], rel=1e-7)
+    np.testing.assert_allclose(rd("out_tsvd_bcs.bin"), oracle.tsvd_solve(Gl, g["vcs"], g["vcs_err"], n // 2)[0], rtol=1e-7)
+    assert f"hist_sum {len(g['toys'])}" in out.stdout
