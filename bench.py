@@ -273,7 +273,7 @@ def run_b200(args, rank, world, local_rank):
         "config": workload_config(args, world),
         "assembly_ms": asm_ms, "toy_batch_ms": toy_ms,
         "assembly": {"panels": npan.value, "nodes": nnode.value, "ms": asm_ms},
-        "roofline": {"bound": "tensor", "kernel": "toy_gemm_kernel (DMMA m8n8k4 f64; two passes per chunk)",
+        "roofline": {"bound": "tensor", "kernel": "toy_fused_kernel (one launch: TMA box loads -> DMMA m8n8k4 f64, pass 1 b = S v and pass 2 chi2 = |R(b-b0)|^2)",
                      "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
                      "traffic": None, "flops_per_toy": 4 * n * n,
                      "peak_source": "FP64 DMMA probe tools/fp64_peaks.cu -> profiles/fp64_peaks_r01.json "
