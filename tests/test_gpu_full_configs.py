@@ -1,0 +1,110 @@
+"""BASELINE.json configs C3-C5 at their full sizes, through size-independent properties (the oracle cannot
+finish these sizes in seconds; small-size parity is in the other test_gpu_* files)."""
+import time
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-8
+
+
+def _model(ecm, G):
+    from bench import bw_born
+    b0 = bw_born(ecm)
+    vcs = G @ b0
+    return b0, vcs, 0.05 * vcs
+
+
+def test_c4_tikhonov_1024_lambdas_10k_toys():
+    """C4: N = 200, cubic interpolation, 2 MeV energy spread, 1024 lambdas x 10k toys."""
+    import isrsolver_b200 as isr
+    n, T, L = 200, 10000, 1024
+    ecm = np.linspace(1.18, 2.0, n)
+    s = isr.ISRSolverTikhonov(n, ecm, np.ones(n), np.full(n, 0.002), np.ones(n), 0.827, enableEnergySpread=True)
+    s.set_interp_settings([(False, 0, 0), (True, 1, n - 1)])
+    s.eval_equation_matrix()
+    G = s.intop_matrix().copy()
+    b0, vcs, err = _model(ecm, G)
+    s.resetVisibleCS(vcs); s.resetVisibleCSErrors(err)
+    lam = 1e-9 * (1e9) ** (np.arange(L) / (L - 1))            # src/isrsolver-LCurve-plot.cpp:127-132
+    V = isr.draw_toys(vcs, err, T)
+    t0 = time.perf_counter()
+    chi2 = s.toy_scan(lam, V, b0)
+    dt = time.perf_counter() - t0
+    assert chi2.shape == (L, T) and np.all(np.isfinite(chi2)) and np.all(chi2 >= 0)
+    # the O(N)-per-pair scan against the generic operator path (A+_lambda, Cov_lambda^-1 through the tile kernel)
+    for q in (0, 400, 700, 1023):
+        s.reg_param = float(lam[q])
+        r = s.toy_batch(V[:2048], b0)
+        np.testing.assert_allclose(chi2[q, :2048], r["chi2"], rtol=1e-6)
+    # L-curve over the same grid: finite, and the residual norm grows / the smoothness norm falls with lambda
+    lc = s.make_LCurve(lam)
+    assert np.all(np.isfinite(lc["x"])) and np.all(np.isfinite(lc["y"])) and np.all(lc["c"] >= 0)
+    assert np.all(np.diff(lc["x"]) >= -1e-9 * lc["x"][1:]) and np.all(np.diff(lc["y"]) <= 1e-9 * lc["y"][:-1])
+    print(f"\nC4: {L} x {T} (lambda, toy) chi2 values through the host API in {dt * 1e3:.1f} ms")
+
+
+def test_c5_sle_ratio_and_chi2_n500():
+    """C5: N = 500, linear interpolation, 2^18 toys (the per-GPU share of 1M toys on 4 GPUs), ratio + chi2."""
+    import isrsolver_b200 as isr
+    n, T = 500, 1 << 18
+    ecm = np.linspace(1.18, 2.0, n)
+    s = isr.ISRSolverSLE(n, ecm, np.ones(n), None, np.ones(n), 0.827)
+    s.eval_equation_matrix()
+    G = s.intop_matrix().copy()
+    assert np.all(np.triu(G, 1) == 0)
+    b0, vcs, err = _model(ecm, G)
+    s.resetVisibleCS(vcs); s.resetVisibleCSErrors(err)
+    V = isr.draw_toys(vcs, err, T)
+    r = s.toy_batch(V, b0, want_sum=True, want_ratio=True, want_hist=True)
+    z = (V - vcs[None, :]) / err[None, :]
+    np.testing.assert_allclose(r["chi2"], (z * z).sum(1), rtol=RTOL)          # survey A.7 identity
+    assert r["chi2"].mean() == pytest.approx(n, rel=5e-3)
+    np.testing.assert_allclose(r["sum_bcs"], np.linalg.solve(G, V.sum(0)), rtol=RTOL)   # linearity
+    # ratio histograms: every toy lands in exactly one of the 1026 cells of its point; in-range count matches
+    hist = r["ratio_hist"]
+    assert np.all(hist.sum(1) == T)
+    np.testing.assert_array_equal(hist[:, 1:1025].sum(1), r["ratio_stats"][:, 0].astype(np.int64))
+    # means of (b - b0)/b0 are unbiased within 5 sigma of their own error
+    cnt, sx, sx2 = r["ratio_stats"].T
+    mean = sx / cnt
+    sig = np.sqrt(np.abs(sx2 / cnt - mean ** 2) / cnt)
+    assert np.all(np.abs(mean) < 6 * sig + 1e-12)
+    # first rows against NumPy
+    B = np.linalg.solve(G, V[:256].T).T
+    rr = (B - b0[None, :]) / b0[None, :]
+    s2 = s.toy_batch(V[:256], b0, want_ratio=True, want_bcs=True)
+    np.testing.assert_allclose(s2["bcs"], B, rtol=RTOL, atol=1e-12)
+    inr = (rr >= -2) & (rr < 2)
+    np.testing.assert_allclose(s2["ratio_stats"][:, 1], np.where(inr, rr, 0).sum(0), rtol=1e-7, atol=1e-9)
+
+
+def test_c3_sle2_matrix_assembly_timing():
+    """C3: N = 200 with a 512-bin efficiency histogram per point: assembly time and panel count."""
+    import ctypes as C
+    import isrsolver_b200 as isr
+    from isrsolver_b200 import _lib as L
+    n = 200
+    ecm = np.linspace(1.18, 2.0, n)
+    xc = (np.arange(512) + 0.5) / 512
+    vals = np.zeros((n, 514))
+    vals[:, 1:-1] = 0.25 + 0.5 * np.exp(-40.0 * xc)[None, :] * (1.0 - 0.1 * (ecm[:, None] - 1.5))
+    s = isr.ISRSolverSLE2(n, ecm, np.ones(n), None, np.ones(n), 0.827, eff_hists=vals, xlo=0.0, xhi=1.0)
+    s.eval_equation_matrix()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        s.eval_equation_matrix()
+    dt = (time.perf_counter() - t0) / 5
+    npan, nnode = C.c_int64(), C.c_int64()
+    L.check(L.load().isr_assemble_stats(s._p, C.byref(npan), C.byref(nnode)))
+    G = s.intop_matrix()
+    assert np.all(np.triu(G, 1) == 0) and np.all(G[np.tril_indices(n)] > 0)
+    # an efficiency <= 0.75 everywhere scales every entry below the eps = 1 matrix
+    s1 = isr.ISRSolverSLE(n, ecm, np.ones(n), None, np.ones(n), 0.827)
+    s1.eval_equation_matrix()
+    G1 = s1.intop_matrix()
+    tri = np.tril_indices(n)
+    assert np.all(G[tri] < 0.7501 * G1[tri]) and np.all(G[tri] > 0.2499 * G1[tri])
+    assert dt < 0.02
+    print(f"\nC3: N=200 eps 512xN assembly {dt * 1e3:.3f} ms wall per call incl. D2H of G, {npan.value} panels, {nnode.value} nodes")
