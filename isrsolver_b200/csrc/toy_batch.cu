@@ -105,7 +105,7 @@ static const std::vector<ToyCfg>& configs() {
       make_cfg<4, 2, 4, 4, 3>("m128n64w8"),   make_cfg<8, 1, 2, 13, 3>("m128n104w8"),
       make_cfg<4, 4, 2, 4, 3>("m64n128w16"),  make_cfg<4, 5, 2, 5, 3>("m64n200w20"),
       make_cfg<4, 2, 2, 13, 3>("m64n208w8"),  make_cfg<4, 4, 2, 8, 3>("m64n256w16"),
-      make_cfg<4, 4, 2, 8, 2>("m64n256w16s2"),
+      make_cfg<4, 4, 2, 8, 2>("m64n256w16s2"), make_cfg<8, 2, 2, 7, 3>("m128n112w16"),
   };
   return v;
 }
@@ -128,6 +128,7 @@ static const ToyCfg* pick_cfg(int n, int nstat) {
     // padded work, a mild preference for tall tiles and deeper pipelines
     double cost = (double)nblk * c.np * (1.0 + 2.0 / c.tm);
     if (std::string(c.name).find("s2") != std::string::npos) cost *= 1.05;
+    if (c.threads < 512) cost *= 1.10;   // 8-warp tiles hide latency worse (measured: N=100 25.8 vs 24.9 TFLOP/s)
     if (cost < best_cost) { best_cost = cost; best = &c; }
   }
   return best;
