@@ -175,14 +175,6 @@ def main():
         out.append(c_array(f"wgf{2 * n + 1}", wgg))   # full-length Gauss weights (0 at Kronrod-only nodes)
         out.append("\n")
         assert abs(sum(wk) - 2) < mp.mpf(10) ** (-60)
-        if n == 10:
-            try:
-                from scipy.integrate import _quad_vec
-                import numpy as np
-                x21 = np.array([float(v) for v in nodes])
-                ref = np.sort(np.asarray(_quad_vec._quadrature_gk21.__code__.co_consts, dtype=object)[0:0])
-            except Exception:
-                pass
     out.append("#endif\n")
     with open(os.path.join(HERE, "gk_tables.h"), "w") as f:
         f.write("".join(out))
@@ -196,6 +188,12 @@ def main():
         xs, ws = legendre_nodes(n)
         dev.append(c_array(f"kGL{n}_x", xs, "__device__ __constant__ double"))
         dev.append(c_array(f"kGL{n}_w", ws, "__device__ __constant__ double"))
+    # 15-point Gauss-Kronrod rule (7-point Gauss embedded) for the forward-convolution service: the
+    # Kronrod-minus-Gauss difference is reported back as the per-panel error estimate
+    kx, kw, kg = kronrod(7)
+    dev.append(c_array("kGK15_x", kx, "__device__ __constant__ double"))
+    dev.append(c_array("kGK15_wk", kw, "__device__ __constant__ double"))
+    dev.append(c_array("kGK15_wg", kg, "__device__ __constant__ double"))
     hx, hw = hermite_nodes(6)
     dev.append(c_array("kGH6_t", hx, "__device__ __constant__ double"))
     dev.append(c_array("kGH6_w_over_sqrtpi", [w / mp.sqrt(mp.pi) for w in hw], "__device__ __constant__ double"))
