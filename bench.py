@@ -92,14 +92,8 @@ def run_reference(args, rank, world):
     cores = os.cpu_count() or 1
     ecm = np.linspace(E_MIN, E_MAX, n)
     settings = [(False, 0, 0), (True, 1, n - 1)]
-    interp = O.Interp(ecm, E_THR, settings)
-    # bounded sample of the assembly: a few full rows of the N x N loop with the reference's adaptive quadrature
-    rows = (0, n // 2, n - 1)
-    t0 = time.perf_counter()
-    interp.eval_rows(rows, mode="faithful")
-    asm_row_s = (time.perf_counter() - t0) / len(rows)
-    # the toy loop needs a matrix; the converged back-end on all cores is the quickest way to get the real one
-    G = interp.eval_eq_matrix(mode="converged")
+    asm = reference_assembly(n, ecm, settings, cores)
+    G = asm.pop("G")
     bcs0 = bw_born(ecm); vcs = G @ bcs0; err = 0.05 * vcs
     per_step = args.ref_toys
     V = O.draw_toys(vcs, err, per_step * (args.steps + args.warmup))
@@ -112,16 +106,40 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     value = per_step * args.steps / dt
     sample = (f"{per_step} toys per step of the faithful per-toy loop (COD solve + G^T W G + inverse every toy, "
-              f"src/Chi2Test.cpp:38-60) at N={n}; assembly sampled on rows {rows}: {asm_row_s * 1e3:.0f} ms/row "
-              f"=> {asm_row_s * n:.1f} s per matrix on 1 core")
+              f"src/Chi2Test.cpp:38-60; NumPy/LAPACK port, Eigen + ROOT cannot be built) at N={n}; assembly: {asm['sample']}")
     line = {"impl": "reference", "metric": "toy SLE solves/s (N=200 chi2 test)", "value": value, "unit": "toys/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, world),
             "cpu_baseline": {"value": value, "unit": "toys/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "toys/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "assembly_ms_cpu_1core_extrapolated": asm_row_s * n * 1e3}
+            "assembly": asm}
     print(json.dumps(line), flush=True)
+
+
+def reference_assembly(n, ecm, settings, cores):
+    """Matrix assembly on the host cores: the reference's OWN compiled evalKuraevFadinBasisIntegral
+    (oracle/_ref/libisr_ref.so) when that prebuilt library travelled with the repo, else the oracle port.
+    Full matrix on all cores (the reference itself is single-threaded: 1-core time = cores x this, also
+    sampled directly on three rows)."""
+    from oracle import isr_oracle as O
+    from oracle import isr_ref as R
+    rows = (0, n // 2, n - 1)
+    if R.available():
+        ri = R.RefInterp(ecm, E_THR, settings)
+        t0 = time.perf_counter(); ri.eval_eq_matrix(rows=rows, nthreads=1); row_s = (time.perf_counter() - t0) / len(rows)
+        t0 = time.perf_counter(); G = ri.eval_eq_matrix(nthreads=cores); full_s = time.perf_counter() - t0
+        kind = "reference"
+    else:
+        oi = O.Interp(ecm, E_THR, settings)
+        t0 = time.perf_counter(); oi.eval_rows(rows, mode="faithful"); row_s = (time.perf_counter() - t0) / len(rows)
+        t0 = time.perf_counter(); G = oi.eval_eq_matrix(mode="faithful", nthreads=cores); full_s = time.perf_counter() - t0
+        kind = "port"
+    return {"G": G, "ms": full_s * 1e3, "unit": "ms per N x N matrix", "cores": cores, "kind": kind,
+            "ms_1core_from_rows": row_s * n * 1e3,
+            "sample": (f"full {n} x {n} matrix, adaptive GK21/GK61 at 1e-12 per entry (src/Integration.cpp:19-81), "
+                       f"{cores} threads: {full_s * 1e3:.0f} ms; rows {rows} on 1 thread: {row_s * 1e3:.0f} ms/row "
+                       f"=> {row_s * n:.1f} s per matrix single-threaded, as the reference runs it")}
 
 
 def workload_config(args, world):
@@ -300,7 +318,9 @@ def cpu_baseline(n, G, bcs0, vcs, err):
     t0 = time.perf_counter(); O.chi2_test_loop(G, V, bcs0, err); dt = time.perf_counter() - t0
     Vf = O.draw_toys(vcs, err, 100000)
     t1 = time.perf_counter(); O.chi2_test_fair(G, Vf, bcs0, err); dtf = time.perf_counter() - t1
-    return {"value": m / dt, "unit": "toys/s", "cores": os.cpu_count() or 1, "kind": "port",
+    asm = reference_assembly(n, np.linspace(E_MIN, E_MAX, n), [(False, 0, 0), (True, 1, n - 1)], os.cpu_count() or 1)
+    asm.pop("G")
+    return {"value": m / dt, "unit": "toys/s", "cores": os.cpu_count() or 1, "kind": "port", "assembly": asm,
             "sample": f"{m} toys of the faithful per-toy loop (COD + G^T W G + inverse per toy, src/Chi2Test.cpp:38-60) at N={n}, NumPy/LAPACK on all host cores",
             "fair_value": 100000 / dtf,
             "fair_sample": "100000 toys with the redundancy removed (factor once, two GEMMs; BASELINE.md B-fair), NumPy/OpenBLAS on all host cores"}

@@ -4,10 +4,14 @@
  * ORACLE / TEST INFRASTRUCTURE.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load this.  The product (libisr_b200.so) never links or calls it.
  *
- * PARITY UNPINNED BY THE REFERENCE: sergeigribanov/ISRSolver ships no tests, golden vectors or data
- * files, and cannot be built here (GSL, Eigen, ROOT, Boost, NLopt are absent), so this restatement is
- * pinned instead against (i) SciPy's QUADPACK (the algorithm GSL ports), (ii) mpmath high-precision
- * quadrature and (iii) analytic identities -- see tests/test_oracle.py.
+ * PINNING.  sergeigribanov/ISRSolver ships no tests, golden vectors or data files, and its own build
+ * (CMake + GSL + Eigen + ROOT + Boost + NLopt) cannot run here.  Its assembly-path SOURCES, however, are
+ * compiled unmodified into oracle/_ref/libisr_ref.so (oracle/Makefile) with the GSL entry points they call
+ * supplied by oracle/ref_shim on top of the QUADPACK / cspline routines of THIS file; every function of the
+ * restatement below (kernel, convolution split, retry loops, range bookkeeping, bases, N^2 loop, spread
+ * matrix) reproduces that compiled reference BIT FOR BIT (tests/test_ref_pin.py).  The GSL internals
+ * themselves, shared by both, are pinned against (i) SciPy's QUADPACK (identical evaluation counts),
+ * (ii) mpmath high-precision quadrature and (iii) analytic identities -- tests/test_oracle.py.
  *
  * Third-party algorithms restated here (not in /root/reference, versions unpinned by the reference:
  * Dockerfile:1,5, docker/install.sh:14-17):
@@ -564,6 +568,8 @@ static void cspline_natural_c(int size, const double *xa, const double *ya, doub
     free(g); free(diag); free(offdiag);
   }
 }
+/* exported for oracle/ref_shim/gsl_shim.c (the GSL-API shim the reference sources are compiled against) */
+void orc_cspline_natural_c(int size, const double *xa, const double *ya, double *c) { cspline_natural_c(size, xa, ya, c); }
 /* gsl_interp_bsearch(xa, x, 0, size-1) */
 int orc_bsearch(const double *xa, double x, int index_lo, int index_hi) {
   int ilo = index_lo, ihi = index_hi;

@@ -3,8 +3,11 @@
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
 this module.  The product path (isrsolver_b200 -> libisr_b200.so) never touches it.
 
-PARITY UNPINNED BY THE REFERENCE (it ships no golden vectors and cannot be built here; SURVEY.md F3,
-F5).  The restatement is pinned against SciPy's QUADPACK, mpmath and analytic identities instead
+PINNING.  The assembly layer (isr_oracle.c) reproduces the reference's own compiled sources bit for bit
+(oracle/_ref, oracle/isr_ref.py, tests/test_ref_pin.py).  The linear-algebra layer in THIS file (solve,
+covariance, toy loops, Tikhonov, TSVD) remains PARITY UNPINNED BY THE REFERENCE: those reference files need
+Eigen's decompositions and ROOT, which are absent, and the reference ships no golden vectors (SURVEY.md
+F3, F5); it is pinned against LAPACK identities and the literal matrix formulas instead
 (tests/test_oracle.py).
 
 Two layers:

@@ -1,10 +1,18 @@
 #!/usr/bin/env python3
-"""Generate the golden fixtures under tests/golden/ from the CPU oracle.
+"""Generate the golden fixtures under tests/golden/.
 
-The reference ships no golden vectors and cannot be built in this image, so these
-fixtures are outputs of oracle/ (the C restatement of the reference's QUADPACK-based assembly plus
-NumPy/LAPACK linear algebra), pinned in tests/test_oracle.py against SciPy QUADPACK, mpmath and analytic
-identities.  Run:  python tests/golden/make_golden.py   (about a minute on 8 cores).
+The reference ships no golden vectors.  Its assembly-path SOURCES are compiled here into
+oracle/_ref/libisr_ref.so (oracle/Makefile; GSL/Eigen resolved by oracle/ref_shim), and the fixtures
+carry that library's outputs under *_ref keys:
+    G_ref      evalEqMatrix fill loop over the reference's own Interpolator::evalKuraevFadinBasisIntegral
+    S_ref      _energySpreadMatrix over the reference's gaussian_conv + Interpolator::basisEval
+    vcs_ref    the reference's convolutionKuraevFadin of the Breit-Wigner Born model
+    w_ref, D_ref   Interpolator::evalIntegralBasis / basisDerivEval
+Everything else (solve, covariance, toys, Tikhonov, TSVD) is output of the restatement in oracle/
+(NumPy/LAPACK in place of Eigen; ROOT and Eigen's decompositions cannot be compiled here).  This script
+asserts that the restatement's faithful back-end reproduces the compiled reference BIT FOR BIT before
+writing anything.  Run in the container that has /root/reference:
+    python tests/golden/make_golden.py   (about a minute on 8 cores).
 """
 import os
 import sys
@@ -14,6 +22,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from oracle import isr_oracle as O  # noqa: E402
+from oracle import isr_ref as R     # noqa: E402
 
 
 def case(name, n, settings, eff=None, ecm_err=None, toys=64, tik=False):
@@ -23,13 +32,29 @@ def case(name, n, settings, eff=None, ecm_err=None, toys=64, tik=False):
     Gc, Ec, Rc = I.eval_eq_matrix(eff=eff, mode="converged", with_errors=True)
     out = dict(ecm=ecm, threshold=O.E_THR, settings=np.array(settings, dtype=np.int32),
                G_faithful=Gf, G_faithful_err=Ef, G_faithful_relerr=Rf, G_converged=Gc, G_converged_err=Ec)
+    # ---- the reference's own compiled code on the same inputs
+    v2 = eff is not None and eff.kind == "row_table"
+    RI = R.RefInterp(ecm, O.E_THR, settings, v2=v2)
+    G_ref = RI.eval_eq_matrix(eff=eff)
+    assert np.array_equal(G_ref, Gf), name + ": faithful restatement differs from the compiled reference"
+    w_ref = RI.integral_basis()
+    D_ref = np.array([[RI.basis_deriv_eval(j, ecm[i]) for j in range(n)] for i in range(n)])
+    born = lambda e: float(O.bw_born(e)[0])
+    vcs_ref = np.array([R.convolution_kf(e, born, 0.0, 1.0 - (O.E_THR / e) ** 2,
+                                         eff if (eff is not None and not v2) else None) for e in ecm]) if not v2 else None
+    out.update(G_ref=G_ref, w_ref=w_ref, D_ref=D_ref)
     G = Gc
     if ecm_err is not None:
+        S_ref = RI.energy_spread_matrix(ecm_err)
+        out.update(S_ref=S_ref)
         S = I.energy_spread_matrix(ecm_err)
         G = S @ Gc
         out.update(ecm_err=ecm_err, S=S, G_spread=G)
     bcs0 = O.bw_born(ecm)
     vcs = O.bw_visible(ecm, eff=eff)
+    if vcs_ref is not None:
+        assert np.array_equal(vcs_ref, vcs), name + ": visible cross section differs from the compiled reference"
+        out.update(vcs_ref=vcs_ref)
     vcs_err = 0.05 * vcs
     b, cov = O.sle_solve(G, vcs, vcs_err)
     V = O.draw_toys(vcs, vcs_err, toys)

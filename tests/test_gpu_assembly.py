@@ -4,7 +4,9 @@ Tolerance (north star): matrix entries within 1e-9 relative.  The comparison tar
 CONVERGED back-end; for structurally tiny entries the oracle's own absolute tolerance (epsabs = 1e-12 per
 adaptive call) is added as a floor.  Against the FAITHFUL back-end (the reference's call structure, whose
 loosen-until-success loop ends at epsrel up to 1e-3 for tabulated efficiencies) the gate is the same plus
-the faithful back-end's own reported error estimate."""
+the faithful back-end's own reported error estimate.  The fixtures' G_ref / S_ref / vcs_ref arrays are outputs
+of the reference's OWN compiled sources (oracle/_ref, see tests/golden/make_golden.py); the faithful back-end
+reproduces them bit for bit (tests/test_ref_pin.py), so the faithful gate is the gate against the reference."""
 import numpy as np
 import pytest
 
@@ -41,6 +43,7 @@ def test_matrix_vs_golden(name):
     G = s.intop_matrix()
     assert_matrix_parity(G, g["G_converged"], g["G_converged_err"], what=name + " vs converged oracle")
     assert_matrix_parity(G, g["G_faithful"], 3 * g["G_faithful_err"], row_rel=1e-9, what=name + " vs faithful oracle")
+    assert_matrix_parity(G, g["G_ref"], 3 * g["G_faithful_err"], row_rel=1e-9, what=name + " vs the compiled reference")
     if "linear" in name:
         assert np.all(np.triu(G, 1) == 0)       # structural zeros are exact (F1)
 
@@ -53,6 +56,7 @@ def test_matrix_with_row_table_efficiency():
     s.eval_equation_matrix()
     assert_matrix_parity(s.intop_matrix(), g["G_converged"], g["G_converged_err"], what="eps table vs converged")
     assert_matrix_parity(s.intop_matrix(), g["G_faithful"], 3 * g["G_faithful_err"], row_rel=1e-9, what="eps table vs faithful")
+    assert_matrix_parity(s.intop_matrix(), g["G_ref"], 3 * g["G_faithful_err"], row_rel=1e-9, what="eps table vs the compiled reference (Interpolator2)")
     # same through the v2 class (ISRSolverSLE2: histogram per energy point)
     s2 = isr.ISRSolverSLE2(len(g["ecm"]), g["ecm"], g["vcs"], None, g["vcs_err"], float(g["threshold"]),
                            eff_hists=g["eff_values"], xlo=0.0, xhi=1.0)
@@ -65,6 +69,9 @@ def test_matrix_with_energy_spread():
     s = make_solver(g, spread=True)
     s.eval_equation_matrix()
     assert_matrix_parity(s.intop_matrix(), g["G_spread"], 32 * g["G_converged_err"].max(), what="spread matrix")
+    # the compiled reference's _energySpreadMatrix times its own matrix
+    assert_matrix_parity(s.intop_matrix(), g["S_ref"] @ g["G_ref"], 32 * 3 * g["G_faithful_err"].max(), row_rel=1e-9,
+                         what="spread matrix vs the compiled reference")
 
 
 @pytest.mark.parametrize("kind", ["table_2d", "e_only", "row_var_edges"])
