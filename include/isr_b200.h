@@ -108,6 +108,12 @@ int isr_get_inv_cov(isr_problem* p, double* inv_cov_out);      /* G^T W G, colum
 /* ISRSolverSLE::evalConditionNumber (src/ISRSolverSLE.cpp:200-204) */
 int isr_cond_number(isr_problem* p, double* cond_out);
 
+/* Condition number versus beam-energy spread (src/isrsolver-condnum-test.cpp:88-140: resetECMErrors +
+ * evalEqMatrix + evalConditionNumber per point).  sigma: K common spreads (per_point == 0; 0 means "spread
+ * disabled") or K x N per-point spreads (row-major).  cond_out[K]; sv_out (K x N singular values,
+ * descending) may be NULL.  Leaves the problem holding the UNSPREAD matrix. */
+int isr_cond_spread_scan(isr_problem* p, int K, const double* sigma, int per_point, double* cond_out, double* sv_out);
+
 /* ---- toy Monte-Carlo batch -------------------------------------------------------------------- */
 /* The loop bodies of chi2Test (src/Chi2Test.cpp:38-60), chi2TestData (:177-183) and ratioTestModel
  * (src/RatioTest.cpp:38-45) over T toys at once:
@@ -163,6 +169,35 @@ int isr_tsvd_solve(isr_problem* p, int k, int keep_one, const double* vcs, const
                    double* bcs_out, double* cov_out);
 int isr_singular_values(isr_problem* p, double* sv_out /* N, descending */);
 int isr_tsvd_select(isr_problem* p, int k, int keep_one, const double* vcs_err);
+
+/* ---- forward convolution service ---------------------------------------------------------------- */
+/* convolutionKuraevFadin / convolutionKuraevFadin_1d (src/KuraevFadin.cpp:56-92; PyISR
+ * "convolutionKuraevFadin", include/PyKuraevFadin.hpp:19-62) for M energies at once:
+ *   result[m] = int_{min_x[m]}^{max_x[m]} F(x, E_m^2) eps(x, E_m) f(E_m sqrt(1 - x)) dx .
+ * The Born cross section f is a host callable, so the plan exposes its quadrature nodes: sample f at the
+ * node energies (isr_conv_plan_nodes), hand the values back (isr_conv_plan_feed), bisect the panels whose
+ * Gauss-Kronrod error estimate is too large (isr_conv_plan_refine) and repeat until no panel is split.
+ * Each pending panel exposes 16 node slots (15 Kronrod nodes + one duplicate with zero weight).
+ * eps may be NULL (== 1); for ISR_EPS_ROW_TABLE the table has one row per requested energy.
+ * break_energy: optional energies where f has a kink or a narrow peak (panels are cut there). */
+typedef struct isr_conv_plan isr_conv_plan;
+int isr_conv_plan_create(isr_ctx* ctx, int64_t M, const double* energy, const double* min_x, const double* max_x,
+                         const isr_eps_desc* eps, int nbreaks, const double* break_energy, isr_conv_plan** out);
+void isr_conv_plan_destroy(isr_conv_plan* plan);
+int isr_conv_plan_size(isr_conv_plan* plan, int64_t* n_panels, int64_t* n_pending_nodes);
+/* Nodes of the pending panels, n_pending_nodes entries each (any pointer may be NULL): E' = E sqrt(1 - x),
+ * x, the row index m, and the complete node weight w (so that sum w f(E') is the panel's Kronrod value). */
+int isr_conv_plan_nodes(isr_conv_plan* plan, double* energy_out, double* x_out, int* row_out, double* weight_out);
+int isr_conv_plan_feed(isr_conv_plan* plan, const double* fvals /* n_pending_nodes */);
+/* f = the interpolated Born cross section of a solver (Interpolator::eval, src/Interpolator.cpp:295-323),
+ * sampled on the device without a host round trip. */
+int isr_conv_plan_feed_interp(isr_conv_plan* plan, isr_problem* p, const double* bcs /* N */);
+/* Bisect every evaluated panel whose error estimate exceeds its share of max(abs_tol, rel_tol |result|);
+ * *n_split panels were replaced by two pending children each. */
+int isr_conv_plan_refine(isr_conv_plan* plan, double rel_tol, double abs_tol, int64_t* n_split);
+int isr_conv_plan_result(isr_conv_plan* plan, double* result /* M */, double* err_est /* M or NULL */);
+/* Keep the refined panel set, mark every panel pending again (same grid, new f). */
+int isr_conv_plan_reset(isr_conv_plan* plan);
 
 #ifdef __cplusplus
 }

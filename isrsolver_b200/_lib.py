@@ -66,6 +66,7 @@ SIGNATURES = {
     "isr_get_inverse": (C.c_int, [_vp, _dp]),
     "isr_get_inv_cov": (C.c_int, [_vp, _dp]),
     "isr_cond_number": (C.c_int, [_vp, _dp]),
+    "isr_cond_spread_scan": (C.c_int, [_vp, C.c_int, _dp, C.c_int, _dp, _dp]),
     "isr_toy_batch": (C.c_int, [_vp, _i64, _dp, _dp, _dp, _dp, _dp, _up, _dp]),
     "isr_toy_batch_dev": (C.c_int, [_vp, _i64, _vp, _dp, _vp, _vp, _vp, _vp, _vp]),
     "isr_set_toy_kernel": (C.c_int, [_vp, C.c_int]),
@@ -82,6 +83,15 @@ SIGNATURES = {
     "isr_tsvd_solve": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp]),
     "isr_singular_values": (C.c_int, [_vp, _dp]),
     "isr_tsvd_select": (C.c_int, [_vp, C.c_int, C.c_int, _dp]),
+    "isr_conv_plan_create": (C.c_int, [_vp, _i64, _dp, _dp, _dp, C.POINTER(EpsDesc), C.c_int, _dp, C.POINTER(_vp)]),
+    "isr_conv_plan_destroy": (None, [_vp]),
+    "isr_conv_plan_size": (C.c_int, [_vp, _i64p, _i64p]),
+    "isr_conv_plan_nodes": (C.c_int, [_vp, _dp, _dp, _ip, _dp]),
+    "isr_conv_plan_feed": (C.c_int, [_vp, _dp]),
+    "isr_conv_plan_feed_interp": (C.c_int, [_vp, _vp, _dp]),
+    "isr_conv_plan_refine": (C.c_int, [_vp, C.c_double, C.c_double, _i64p]),
+    "isr_conv_plan_result": (C.c_int, [_vp, _dp, _dp]),
+    "isr_conv_plan_reset": (C.c_int, [_vp]),
 }
 
 _LIB = None

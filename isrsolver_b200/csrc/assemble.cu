@@ -19,6 +19,7 @@
 
 #include "gl_tables.cuh"
 #include "kf_device.cuh"
+#include "panel_device.cuh"
 #include "problem.hpp"
 
 namespace isr {
@@ -193,10 +194,11 @@ static int host_find_bin(int nbins, double lo, double hi, const double* edges, d
   return 1 + l;
 }
 
-int upload_eps(isr_problem* p, const isr_eps_desc* e) {
-  const int n = p->n;
-  cudaStream_t st = p->ctx->stream;
-  p->eps = EpsDev{};
+// Reduce an efficiency descriptor to the per-row device form for `n` energies (rows): used by the
+// problem (rows = the energy points) and by the convolution plans (rows = the requested energies).
+int build_eps_rows(cudaStream_t st, int n, const double* energy, const isr_eps_desc* e, DevBuf<double>& d_vals,
+                   DevBuf<double>& d_edges, EpsDev& out) {
+  out = EpsDev{};
   if (!e || e->kind == ISR_EPS_ONE) return ISR_OK;
   if (e->kind < 0 || e->kind > ISR_EPS_E_ONLY) {
     set_error("[!] Wrong efficiency dimension.");   // EfficiencyDimensionException
@@ -210,12 +212,12 @@ int upload_eps(isr_problem* p, const isr_eps_desc* e) {
     // TEfficiency 1-D: efficiency(x, E) = eff[FindFixBin(E)] (src/BaseISRSolver.cpp:236-241)
     if (e->ne < 1) { set_error("efficiency: ne < 1"); return ISR_EINVAL; }
     std::vector<double> scale(n);
-    for (int i = 0; i < n; ++i) scale[i] = e->values[host_find_bin(e->ne, elo, ehi, e->eedges, p->ext[i + 1])];
-    ISR_TRY(p->d_eps_vals.reserve(n));
-    ISR_CUDA(cudaMemcpyAsync(p->d_eps_vals.p, scale.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    for (int i = 0; i < n; ++i) scale[i] = e->values[host_find_bin(e->ne, elo, ehi, e->eedges, energy[i])];
+    ISR_TRY(d_vals.reserve(n));
+    ISR_CUDA(cudaMemcpyAsync(d_vals.p, scale.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
     ISR_CUDA(cudaStreamSynchronize(st));
-    p->eps.kind = 1;
-    p->eps.values = p->d_eps_vals.p;
+    out.kind = 1;
+    out.values = d_vals.p;
     return ISR_OK;
   }
   if (e->nx < 1 || !(xhi > xlo)) { set_error("efficiency: bad x axis"); return ISR_EINVAL; }
@@ -228,25 +230,29 @@ int upload_eps(isr_problem* p, const isr_eps_desc* e) {
     // TEfficiency 2-D: global bin = bx + (nx+2)*by (src/BaseISRSolver.cpp:243-250)
     if (e->ne < 1) { set_error("efficiency: ne < 1"); return ISR_EINVAL; }
     for (int i = 0; i < n; ++i) {
-      const int by = host_find_bin(e->ne, elo, ehi, e->eedges, p->ext[i + 1]);
+      const int by = host_find_bin(e->ne, elo, ehi, e->eedges, energy[i]);
       std::memcpy(&vals[(size_t)i * w], &e->values[(size_t)by * w], sizeof(double) * w);
     }
   }
-  ISR_TRY(p->d_eps_vals.reserve(vals.size()));
-  ISR_CUDA(cudaMemcpyAsync(p->d_eps_vals.p, vals.data(), sizeof(double) * vals.size(), cudaMemcpyHostToDevice, st));
-  p->eps.kind = 2;
-  p->eps.nx = e->nx;
-  p->eps.xlo = xlo;
-  p->eps.xhi = xhi;
-  p->eps.values = p->d_eps_vals.p;
-  p->eps.xedges = nullptr;
+  ISR_TRY(d_vals.reserve(vals.size()));
+  ISR_CUDA(cudaMemcpyAsync(d_vals.p, vals.data(), sizeof(double) * vals.size(), cudaMemcpyHostToDevice, st));
+  out.kind = 2;
+  out.nx = e->nx;
+  out.xlo = xlo;
+  out.xhi = xhi;
+  out.values = d_vals.p;
+  out.xedges = nullptr;
   if (e->xedges) {
-    ISR_TRY(p->d_eps_edges.reserve(e->nx + 1));
-    ISR_CUDA(cudaMemcpyAsync(p->d_eps_edges.p, e->xedges, sizeof(double) * (e->nx + 1), cudaMemcpyHostToDevice, st));
-    p->eps.xedges = p->d_eps_edges.p;
+    ISR_TRY(d_edges.reserve(e->nx + 1));
+    ISR_CUDA(cudaMemcpyAsync(d_edges.p, e->xedges, sizeof(double) * (e->nx + 1), cudaMemcpyHostToDevice, st));
+    out.xedges = d_edges.p;
   }
   ISR_CUDA(cudaStreamSynchronize(st));
   return ISR_OK;
+}
+
+int upload_eps(isr_problem* p, const isr_eps_desc* e) {
+  return build_eps_rows(p->ctx->stream, p->n, p->ext.data() + 1, e, p->d_eps_vals, p->d_eps_edges, p->eps);
 }
 
 // =================================================================================================
@@ -258,37 +264,7 @@ __global__ void row_setup_kernel(int n, const double* __restrict__ ext, RowConst
   if (i >= n) return;
   RowConst rc;
   row_const_init(rc, ext[i + 1], ext[0]);
-  // grading points: x0, x0 (1 + 4^m) for m = -2, -1, 0, 1, ... (ratio <= 4 to both singular points
-  // 0 and x0), then 1 - (1 - xmax) 4^m towards the pole of the pair term at x = 1.
-  int nb = 0;
-  rc.rb[nb++] = rc.x0;
-  double f = 1.0 / 16.0;
-  while (nb < kMaxRowBreaks - 6) {
-    const double v = rc.x0 * (1.0 + f);
-    if (!(v < rc.xmax)) break;
-    rc.rb[nb++] = v;
-    f *= 4.0;
-  }
-  const double d = 1.0 - rc.xmax;
-  double g = 4.0;
-  double tmp[6];
-  int nt = 0;
-  while (nt < 6) {
-    const double v = 1.0 - d * g;
-    if (!(v > 0.25) || !(v > rc.rb[nb - 1])) break;
-    tmp[nt++] = v;
-    g *= 4.0;
-  }
-  // tmp is descending; merge so rb stays ascending
-  for (int q = nt - 1; q >= 0; --q) rc.rb[nb++] = tmp[q];
-  // insertion sort (the two families can interleave)
-  for (int a = 1; a < nb; ++a) {
-    const double v = rc.rb[a];
-    int b = a - 1;
-    while (b >= 0 && rc.rb[b] > v) { rc.rb[b + 1] = rc.rb[b]; --b; }
-    rc.rb[b + 1] = v;
-  }
-  rc.nrb = nb;
+  row_grading(rc);
   rows[i] = rc;
 }
 
@@ -297,45 +273,6 @@ __device__ __forceinline__ double knot_x(const double* __restrict__ ext, double 
   if (m == i + 1) return 0.0;
   const double r = ext[m] / E;
   return fmax(0.0, 1.0 - r * r);
-}
-
-// ROOT TAxis::FindBin arithmetic (bit-exact: no FMA contraction in the index expression).
-__device__ __forceinline__ int eps_find_bin(const EpsDev& e, double x) {
-  if (x < e.xlo) return 0;
-  if (!(x < e.xhi)) return e.nx + 1;
-  if (!e.xedges) {
-    const double t = __ddiv_rn(__dmul_rn((double)e.nx, __dsub_rn(x, e.xlo)), __dsub_rn(e.xhi, e.xlo));
-    return 1 + (int)t;
-  }
-  int l = 0, h = e.nx;
-  while (h - l > 1) {
-    const int m = (l + h) >> 1;
-    if (e.xedges[m] <= x) l = m; else h = m;
-  }
-  return 1 + l;
-}
-__device__ __forceinline__ double eps_edge(const EpsDev& e, int m) {
-  if (e.xedges) return e.xedges[m];
-  if (m == e.nx) return e.xhi;
-  return e.xlo + (double)m * ((e.xhi - e.xlo) / (double)e.nx);
-}
-// smallest edge index m in [0, nx] with edge(m) > v, or nx+1
-__device__ __forceinline__ int eps_first_edge_above(const EpsDev& e, double v) {
-  int m;
-  if (e.xedges) {
-    int l = -1, h = e.nx + 1;  // edge(l) <= v < edge(h)
-    while (h - l > 1) {
-      const int q = (l + h) >> 1;
-      if (e.xedges[q] <= v) l = q; else h = q;
-    }
-    return h;
-  }
-  const double w = (e.xhi - e.xlo) / (double)e.nx;
-  const double t = floor((v - e.xlo) / w) + 1.0;
-  m = t < 0.0 ? 0 : (t > (double)(e.nx + 1) ? e.nx + 1 : (int)t);
-  while (m > 0 && eps_edge(e, m - 1) > v) --m;
-  while (m <= e.nx && !(eps_edge(e, m) > v)) ++m;
-  return m;
 }
 
 // Walk the panels of item (row i, segment k).  Emit(a, b) is called for every panel in ascending x.
@@ -409,6 +346,12 @@ __global__ void __launch_bounds__(1024) scan_kernel(int n, const int* __restrict
     run += cnt[q];
   }
   if (t == 1023) off[n] = part[1023];
+}
+
+int exclusive_scan_int(cudaStream_t st, int n, const int* cnt_dev, int* off_dev) {
+  scan_kernel<<<1, 1024, 0, st>>>(n, cnt_dev, off_dev); ISR_COUNT_LAUNCH();
+  ISR_CUDA(cudaGetLastError());
+  return ISR_OK;
 }
 
 // kind: 0 = regular (x), 1 = t = x^beta, 2 = u = (x - x0)^beta
@@ -672,6 +615,17 @@ __global__ void __launch_bounds__(256) gemm_nn_kernel(int n, const double* __res
   }
 }
 
+// Gout = G_spread(sigE) * G0 (all column-major n x n on the device); S is scratch.
+int apply_spread(isr_problem* p, const double* sigE_dev, const double* G0, double* S, double* Gout) {
+  const int n = p->n;
+  cudaStream_t st = p->ctx->stream;
+  spread_kernel<<<(n * n + 127) / 128, 128, 0, st>>>(n, p->d_ext.p, p->d_invh.p, p->d_Ct.p, sigE_dev, S); ISR_COUNT_LAUNCH();
+  dim3 g((n + 31) / 32, (n + 31) / 32);
+  gemm_nn_kernel<<<g, 256, 0, st>>>(n, S, G0, Gout); ISR_COUNT_LAUNCH();
+  ISR_CUDA(cudaGetLastError());
+  return ISR_OK;
+}
+
 // =================================================================================================
 // Host driver
 // =================================================================================================
@@ -726,13 +680,12 @@ int assemble(isr_problem* p, const double* ecm_err) {
     ISR_TRY(p->d_S.reserve((size_t)n * n));
     ISR_TRY(p->d_tmp.reserve((size_t)n * n));
     ISR_CUDA(cudaMemcpyAsync(p->d_sigE.p, ecm_err, sizeof(double) * n, cudaMemcpyHostToDevice, st));
-    spread_kernel<<<(n * n + 127) / 128, 128, 0, st>>>(n, p->d_ext.p, p->d_invh.p, p->d_Ct.p, p->d_sigE.p, p->d_S.p); ISR_COUNT_LAUNCH();
-    dim3 g((n + 31) / 32, (n + 31) / 32);
-    gemm_nn_kernel<<<g, 256, 0, st>>>(n, p->d_S.p, p->d_G.p, p->d_tmp.p); ISR_COUNT_LAUNCH();
+    ISR_TRY(apply_spread(p, p->d_sigE.p, p->d_G.p, p->d_S.p, p->d_tmp.p));
     ISR_CUDA(cudaMemcpyAsync(p->d_G.p, p->d_tmp.p, sizeof(double) * n * n, cudaMemcpyDeviceToDevice, st));
   }
   ISR_CUDA(cudaGetLastError());
   p->has_G = true;
+  p->G_injected = false;
   p->factored = false;
   p->solver_selected = false;
   p->tik_ready = false;

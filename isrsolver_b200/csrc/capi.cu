@@ -1,4 +1,5 @@
 // extern "C" surface of libisr_b200.so (declared in include/isr_b200.h).
+#include <cmath>
 #include <cstdarg>
 #include <cstring>
 #include <new>
@@ -128,6 +129,7 @@ int isr_set_matrix(isr_problem* p, const double* G) {
   ISR_CUDA(cudaMemcpyAsync(p->d_G.p, G, sizeof(double) * p->n * p->n, cudaMemcpyHostToDevice, p->ctx->stream));
   ISR_CUDA(cudaStreamSynchronize(p->ctx->stream));
   p->has_G = true;
+  p->G_injected = true;
   p->factored = p->solver_selected = p->tik_ready = p->svd_ready = false;
   return ISR_OK;
 }
@@ -291,6 +293,53 @@ int isr_cond_number(isr_problem* p, double* cond_out) {
   ISR_CUDA(cudaSetDevice(p->ctx->device));
   ISR_TRY(ensure_svd(p));
   *cond_out = p->h_sv.front() / p->h_sv.back();
+  return ISR_OK;
+}
+
+// Condition number of G_spread(sigma_k) G for K beam-energy-spread settings: the loop of
+// src/isrsolver-condnum-test.cpp:88-140 (resetECMErrors + evalEqMatrix + JacobiSVD per point; also
+// notebooks/condnum_enspread.ipynb).  The reference re-integrates the whole matrix for every sigma; here the
+// unspread matrix is assembled once and only the 6-point Gauss-Hermite spread product and the SVD are redone.
+int isr_cond_spread_scan(isr_problem* p, int K, const double* sigma, int per_point, double* cond_out, double* sv_out) {
+  if (!p || !sigma || !cond_out || K < 0) { set_error("isr_cond_spread_scan: bad argument"); return ISR_EINVAL; }
+  if (K == 0) return ISR_OK;
+  ISR_CUDA(cudaSetDevice(p->ctx->device));
+  const int n = p->n;
+  const size_t nn = (size_t)n * n;
+  cudaStream_t st = p->ctx->stream;
+  for (int k = 0; k < K; ++k)
+    for (int i = 0; i < (per_point ? n : 1); ++i) {
+      const double v = sigma[per_point ? (size_t)k * n + i : k];
+      if (!(v >= 0.0) || !std::isfinite(v) || (per_point && v == 0.0)) {
+        set_error("isr_cond_spread_scan: sigma[%d] = %g (per-point spreads must be positive, common ones non-negative)", k, v);
+        return ISR_EINVAL;
+      }
+    }
+  if (!p->G_injected) ISR_TRY(assemble(p, nullptr));          // the unspread matrix
+  else if (!p->has_G) { set_error("isr_cond_spread_scan: no matrix"); return ISR_ESTATE; }
+  ISR_TRY(p->d_G0.reserve(nn));
+  ISR_TRY(p->d_S.reserve(nn));
+  ISR_TRY(p->d_tmp.reserve(nn));
+  ISR_TRY(p->d_sv.reserve(n));
+  ISR_TRY(p->d_sigK.reserve(n));
+  ISR_CUDA(cudaMemcpyAsync(p->d_G0.p, p->d_G.p, sizeof(double) * nn, cudaMemcpyDeviceToDevice, st));
+  std::vector<double> sg(n), sv(n);
+  for (int k = 0; k < K; ++k) {
+    const bool none = !per_point && sigma[k] == 0.0;    // first point of the reference's scan: spread disabled
+    if (none) {
+      ISR_CUDA(cudaMemcpyAsync(p->d_tmp.p, p->d_G0.p, sizeof(double) * nn, cudaMemcpyDeviceToDevice, st));
+    } else {
+      for (int i = 0; i < n; ++i) sg[i] = per_point ? sigma[(size_t)k * n + i] : sigma[k];
+      ISR_CUDA(cudaMemcpyAsync(p->d_sigK.p, sg.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
+      ISR_TRY(apply_spread(p, p->d_sigK.p, p->d_G0.p, p->d_S.p, p->d_tmp.p));
+    }
+    ISR_TRY(svd_values(p->ctx, n, p->d_tmp.p, p->d_sv.p, p->d_work, p->d_info));
+    ISR_CUDA(cudaMemcpyAsync(sv.data(), p->d_sv.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    ISR_CUDA(cudaStreamSynchronize(st));    // also protects sg before it is refilled
+    cond_out[k] = sv.front() / sv.back();
+    if (sv_out) std::memcpy(sv_out + (size_t)k * n, sv.data(), sizeof(double) * n);
+  }
+  p->svd_ready = false;    // d_sv no longer belongs to the problem's own matrix
   return ISR_OK;
 }
 

@@ -102,6 +102,17 @@ int svd(isr_ctx* c, int n, double* A, double* U, double* S, double* VT, DevBuf<d
   return ISR_OK;
 }
 
+// Singular values only (A destroyed), descending.
+int svd_values(isr_ctx* c, int n, double* A, double* S, DevBuf<double>& work, DevBuf<int>& info) {
+  int lwork = 0;
+  ISR_CUSOLVER(cusolverDnDgesvd_bufferSize(c->solver, n, n, &lwork));
+  ISR_TRY(work.reserve(lwork));
+  ISR_TRY(info.reserve(1));
+  ISR_CUSOLVER(cusolverDnDgesvd(c->solver, 'N', 'N', n, n, A, n, S, nullptr, n, nullptr, n, work.p, lwork, nullptr, info.p));
+  ISR_TRY(check_info(c, info.p, "SVD (gesvd, values only)"));
+  return ISR_OK;
+}
+
 // Generalised symmetric-definite eigen-system A u = mu B u with U^T B U = I (A <- U, B destroyed),
 // eigenvalues ascending in W.
 int sygvd(isr_ctx* c, int n, double* A, double* B, double* W, DevBuf<double>& work, DevBuf<int>& info) {

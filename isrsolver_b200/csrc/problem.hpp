@@ -35,6 +35,8 @@ struct isr_problem {
   int64_t max_panels = 0;
   int64_t last_panels = 0;
   bool has_G = false;
+  bool G_injected = false;   // matrix came from isr_set_matrix (cannot be re-assembled)
+  isr::DevBuf<double> d_G0, d_sigK;   // condition-number scan: unspread matrix, per-setting spreads
 
   // ---- factorisation / selected solver -------------------------------------------------------
   // All N x N, ROW-major on the device: Sop (solve operator: b = Sop v) and Rop (chi2 factor:
@@ -82,5 +84,9 @@ void launch_basis_eval(const isr_problem* p, int64_t m, const int* js, const dou
 void launch_interp_eval(const isr_problem* p, const double* y, int64_t m, const double* es, double* out);
 int ensure_svd(isr_problem* p);
 int upload_eps(isr_problem* p, const isr_eps_desc* eps);
+int build_eps_rows(cudaStream_t st, int n, const double* energy, const isr_eps_desc* e, DevBuf<double>& d_vals,
+                   DevBuf<double>& d_edges, EpsDev& out);
+int exclusive_scan_int(cudaStream_t st, int n, const int* cnt_dev, int* off_dev);   // off[n] = total
 int assemble(isr_problem* p, const double* ecm_err);
+int apply_spread(isr_problem* p, const double* sigE_dev, const double* G0, double* S, double* Gout);
 }  // namespace isr

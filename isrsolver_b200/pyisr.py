@@ -67,6 +67,157 @@ def kernelKuraevFadin(x, s, device: int | None = None):
     return float(out[0]) if np.ndim(x) == 0 and np.ndim(s) == 0 else out.reshape(np.broadcast(x, s).shape)
 
 
+def _call_vectorised(fcn, arr):
+    """Call a user function on an array; fall back to one call per element for scalar-only callables."""
+    try:
+        out = np.asarray(fcn(arr), dtype=np.float64)
+        if out.shape == arr.shape:
+            return np.ascontiguousarray(out)
+    except Exception:
+        pass
+    return np.ascontiguousarray([float(fcn(float(v))) for v in arr], dtype=np.float64)
+
+
+class ConvolutionPlan:
+    """Forward Kuraev-Fadin convolution of an arbitrary Born cross section for many energies at once
+    (convolutionKuraevFadin, src/KuraevFadin.cpp:56-73, looped over energies as
+    src/isrsolver-KuraevFadin-convolution.cpp:122-134 does).  The quadrature lives on the GPU; the Born
+    function is sampled on the host at the node energies the plan asks for.
+
+        plan = ConvolutionPlan(energies, threshold=0.827)         # min_x = 0, max_x = 1 - (thr/E)^2
+        vcs, err = plan.convolve(born)                            # adaptive, refines around narrow peaks
+        vcs2, _ = plan.convolve(born2, refine=False)              # same grid, another function
+    """
+
+    def __init__(self, energy, threshold=None, min_x=None, max_x=None, efficiency=None, breaks=None,
+                 device: int | None = None):
+        e = np.ascontiguousarray(np.atleast_1d(energy), dtype=np.float64).ravel()
+        self._m = e.size
+        if max_x is None:
+            if threshold is None:
+                raise ValueError("give either threshold or max_x")
+            max_x = 1.0 - (float(threshold) / e) ** 2
+        mn = np.ascontiguousarray(np.broadcast_to(0.0 if min_x is None else min_x, e.shape), dtype=np.float64)
+        mx = np.ascontiguousarray(np.broadcast_to(max_x, e.shape), dtype=np.float64)
+        self._eff_call = None
+        desc = None
+        if efficiency is not None:
+            if isinstance(efficiency, Efficiency):
+                desc = efficiency.desc(self._m)
+                self._keep_eff = efficiency
+            elif callable(efficiency):
+                self._eff_call = efficiency       # eps(x, E): sampled on the host at the plan's nodes
+            else:
+                raise TypeError("efficiency must be an Efficiency table or a callable eps(x, energy)")
+        br = None if breaks is None else np.ascontiguousarray(np.atleast_1d(breaks), dtype=np.float64)
+        self._lib = L.load()
+        self._p = C.c_void_p()
+        self._energy = e
+        L.check(self._lib.isr_conv_plan_create(_ctx(device), e.size, L.dptr(e), L.dptr(mn), L.dptr(mx),
+                                               C.byref(desc) if desc is not None else None,
+                                               0 if br is None else br.size, L.dptr(br), C.byref(self._p)))
+
+    def __del__(self):
+        p = getattr(self, "_p", None)
+        if p:
+            try:
+                self._lib.isr_conv_plan_destroy(p)
+            except Exception:
+                pass
+            self._p = None
+
+    def size(self):
+        a, b = C.c_int64(), C.c_int64()
+        L.check(self._lib.isr_conv_plan_size(self._p, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def nodes(self, want_weights=False):
+        """(E', x, row[, weight]) of the pending panels' node slots."""
+        n = self.size()[1]
+        e, x, r = np.empty(n), np.empty(n), np.empty(n, dtype=np.int32)
+        w = np.empty(n) if want_weights else None
+        L.check(self._lib.isr_conv_plan_nodes(self._p, L.dptr(e), L.dptr(x), L.iptr(r), L.dptr(w)))
+        return (e, x, r, w) if want_weights else (e, x, r)
+
+    def _sample(self, fcn):
+        e, x, r = self.nodes()
+        f = _call_vectorised(fcn, e)
+        if self._eff_call is not None:
+            en = self._energy[r]
+            try:
+                ev = np.asarray(self._eff_call(x, en), dtype=np.float64)
+                assert ev.shape == x.shape
+            except Exception:
+                ev = np.array([float(self._eff_call(float(a), float(b))) for a, b in zip(x, en)])
+            f = f * ev
+        return np.ascontiguousarray(f)
+
+    def convolve(self, fcn, rel_tol=1e-10, abs_tol=1e-12, refine=True, max_levels=40):
+        """Returns (result[M], error_estimate[M]).  refine=True bisects panels until every row meets
+        max(abs_tol, rel_tol |result|); refine=False evaluates f once on the current panel set."""
+        if self.size()[1] == 0:
+            L.check(self._lib.isr_conv_plan_reset(self._p))
+        for _ in range(max_levels):
+            if self.size()[1]:
+                L.check(self._lib.isr_conv_plan_feed(self._p, L.dptr(self._sample(fcn))))
+            if not refine:
+                break
+            ns = C.c_int64()
+            L.check(self._lib.isr_conv_plan_refine(self._p, float(rel_tol), float(abs_tol), C.byref(ns)))
+            if ns.value == 0:
+                break
+        if self.size()[1]:      # max_levels exhausted with children pending: evaluate them, report the error
+            L.check(self._lib.isr_conv_plan_feed(self._p, L.dptr(self._sample(fcn))))
+        res, err = np.empty(self._m), np.empty(self._m)
+        L.check(self._lib.isr_conv_plan_result(self._p, L.dptr(res), L.dptr(err)))
+        return res, err
+
+    def convolve_interp(self, solver, bcs=None):
+        """Convolve the interpolated Born cross section of `solver` (its bcs() by default) entirely on the
+        device: sigma_vis at the plan's energies, as ISRSolverVCSFitFunction / the radiative-correction
+        tools evaluate it."""
+        y = _f64(solver.bcs() if bcs is None else bcs, solver.n, "bcs")
+        L.check(self._lib.isr_conv_plan_reset(self._p))
+        L.check(self._lib.isr_conv_plan_feed_interp(self._p, solver._p, L.dptr(y)))
+        res, err = np.empty(self._m), np.empty(self._m)
+        L.check(self._lib.isr_conv_plan_result(self._p, L.dptr(res), L.dptr(err)))
+        return res, err
+
+
+def convolutionKuraevFadin(energy, fcn, min_x, max_x, efficiency=None, rel_tol=1e-10, abs_tol=1e-12, breaks=None,
+                           device: int | None = None):
+    """convolutionKuraevFadin(energy, fcn, min_x, max_x, efficiency) -- include/PyKuraevFadin.hpp:19-62,
+    src/KuraevFadin.cpp:56-73.  `energy`, `min_x`, `max_x` may be arrays (one integral per entry); `fcn` is
+    called with arrays of energies when it accepts them.  `efficiency` is an Efficiency table or a callable
+    eps(x, energy) as in the reference."""
+    scalar = np.ndim(energy) == 0
+    plan = ConvolutionPlan(energy, min_x=min_x, max_x=max_x, efficiency=efficiency, breaks=breaks, device=device)
+    res, _ = plan.convolve(fcn, rel_tol=rel_tol, abs_tol=abs_tol)
+    return float(res[0]) if scalar else res.reshape(np.shape(energy))
+
+
+def convolutionKuraevFadinBlurred(energy, fcn, threshold_energy, cm_energy_spread, efficiency=None, rel_tol=1e-10,
+                                  abs_tol=1e-12, breaks=None, device: int | None = None):
+    """convolutionKuraevFadinBlurred (include/PyKuraevFadin.hpp:64-116): the visible cross section
+    convolved with a Gaussian beam-energy spread by the 6-point Gauss-Hermite rule of gaussian_conv
+    (src/Integration.cpp:86-100)."""
+    t = np.array([-2.350604973674492222833922, -1.335849074013696949714895, -4.360774119276165086792159e-1,
+                  4.360774119276165086792159e-1, 1.335849074013696949714895, 2.350604973674492222833922])
+    w = np.array([4.530009905508845640857473e-3, 1.570673203228566439163116e-1, 7.246295952243925240919147e-1,
+                  7.246295952243925240919147e-1, 1.570673203228566439163116e-1, 4.530009905508845640857473e-3])
+    scalar = np.ndim(energy) == 0
+    e0 = np.atleast_1d(np.asarray(energy, dtype=np.float64)).ravel()
+    sg = np.broadcast_to(np.asarray(cm_energy_spread, dtype=np.float64), e0.shape)
+    en = (e0[:, None] + np.sqrt(2.0) * sg[:, None] * t[None, :]).ravel()
+    live = en > threshold_energy            # below threshold max_x < 0: the reference integrates an empty range
+    vis = np.zeros_like(en)
+    if live.any():
+        plan = ConvolutionPlan(en[live], threshold=threshold_energy, efficiency=efficiency, breaks=breaks, device=device)
+        vis[live] = plan.convolve(fcn, rel_tol=rel_tol, abs_tol=abs_tol)[0]
+    res = (vis.reshape(-1, 6) * (w / np.sqrt(np.pi))[None, :]).sum(1)
+    return float(res[0]) if scalar else res.reshape(np.shape(energy))
+
+
 # ---------------------------------------------------------------------------------------------------
 # efficiency tables
 # ---------------------------------------------------------------------------------------------------
@@ -276,6 +427,22 @@ class ISRSolverSLE(BaseISRSolver):
         L.check(self._lib.isr_cond_number(self._p, C.byref(c)))
         return c.value
     evalConditionNumber = condnum_eval
+
+    def condnum_spread_scan(self, sigmas, want_singular_values=False):
+        """Condition number of the operator matrix versus the beam-energy spread: the loop of
+        src/isrsolver-condnum-test.cpp:123-135 (`sigmas`: K common spreads, 0 = disabled) or K x N per-point
+        spreads.  One assembly + K Gauss-Hermite spread products and SVDs instead of K full assemblies.
+        The solver's cached matrix is invalidated."""
+        sg = np.ascontiguousarray(sigmas, dtype=np.float64)
+        per_point = sg.ndim == 2
+        if per_point and sg.shape[1] != self._n:
+            raise ValueError(f"per-point spreads must be (K, {self._n})")
+        K = sg.shape[0]
+        cond = np.empty(K)
+        sv = np.empty((K, self._n)) if want_singular_values else None
+        L.check(self._lib.isr_cond_spread_scan(self._p, K, L.dptr(sg), int(per_point), L.dptr(cond), L.dptr(sv)))
+        self._invalidate()
+        return (cond, sv) if want_singular_values else cond
 
     def interp_eval(self, cm_energy):
         """interpEval(bcs, energy) (src/ISRSolverSLE.cpp:195-198)."""

@@ -196,3 +196,34 @@ def test_full_size_eps_table_spot_rows(oracle):
     rows = (0, 101, 199)
     Gr, Er = oracle.Interp(ecm, 0.827).eval_rows(rows, eff=eo)
     assert_matrix_parity(s.intop_matrix()[list(rows)], Gr, Er, what="N=200 eps512 rows")
+
+
+def test_condition_number_vs_spread_scan(oracle):
+    """the loop of src/isrsolver-condnum-test.cpp:123-135 -- condition number of
+    G_spread(sigma) G for a list of beam-energy spreads, from ONE assembly."""
+    import isrsolver_b200 as isr
+    g = load_golden("c4_tikhonov_n32_spread")
+    n = len(g["ecm"])
+    s = make_solver(g)
+    sig = np.array([0.0, 0.0005, 0.002, 0.004])
+    cond, sv = s.condnum_spread_scan(sig, want_singular_values=True)
+    I = oracle.Interp(g["ecm"], float(g["threshold"]), [tuple(r) for r in g["settings"]])
+    for k, sg in enumerate(sig):
+        Gk = g["G_converged"] if sg == 0 else I.energy_spread_matrix(np.full(n, sg)) @ g["G_converged"]
+        ref = np.linalg.svd(Gk, compute_uv=False)
+        np.testing.assert_allclose(sv[k], ref, rtol=1e-8, atol=1e-12 * ref[0])
+        assert cond[k] == pytest.approx(ref[0] / ref[-1], rel=1e-8 * max(1.0, ref[0] / ref[-1] * 1e-4))
+    assert np.all(np.diff(cond) > 0)                 # smearing makes the problem worse conditioned
+    # the same numbers through the single-point API of the reference class
+    s2 = make_solver(g, spread=True)
+    assert s2.condnum_eval() == pytest.approx(cond[2], rel=1e-9)
+    s.eval_equation_matrix()
+    assert s.condnum_eval() == pytest.approx(cond[0], rel=1e-12)
+    # per-point spreads
+    pp = np.tile(np.linspace(0.001, 0.003, n), (2, 1)); pp[1] *= 2
+    c2 = s.condnum_spread_scan(pp)
+    for k in range(2):
+        ref = np.linalg.svd(I.energy_spread_matrix(pp[k]) @ g["G_converged"], compute_uv=False)
+        assert c2[k] == pytest.approx(ref[0] / ref[-1], rel=1e-7)
+    with pytest.raises(ValueError):
+        s.condnum_spread_scan([-0.001])
