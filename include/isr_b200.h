@@ -158,6 +158,14 @@ int isr_tikhonov_toy_scan(isr_problem* p, int64_t L, const double* lambda, int64
                           const double* bcs0, double* chi2_out);
 int isr_tikhonov_toy_scan_dev(isr_problem* p, int64_t L, const double* lambda, int64_t T,
                               const double* V_dev, const double* bcs0, double* chi2_dev);
+/* The chi2 test of isrsolver-Tikhonov-chi2-test (src/Chi2Test.cpp:38-78) for L lambdas at once, summarised on
+ * the device: stats_out[l] = {min, max, mean} of chi2 over the T toys, counts_out[l][0..nbins+1] = the
+ * TH1F(nbins, min_l, max_l) cells (under/overflow included).  The L x T chi2 matrix never leaves the GPU. */
+int isr_tikhonov_toy_scan_hist(isr_problem* p, int64_t L, const double* lambda, int64_t T, const double* V,
+                               const double* bcs0, int nbins, double* stats_out, uint32_t* counts_out);
+/* (lambda, toy) scan variant: 0 (default) = chi2 as a quadratic form in lambda from two dot products per toy
+ * (O(1) per pair, bound by writing the output); 1 = the direct O(N)-per-pair kernel (kept as a cross-check). */
+int isr_set_scan_kernel(isr_problem* p, int variant);
 /* Make isr_toy_batch use the Tikhonov operator A+_lambda and its covariance. */
 int isr_tikhonov_select(isr_problem* p, double lambda);
 int isr_get_regulariser(isr_problem* p, double* F_out); /* column-major */

@@ -11,7 +11,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <functional>
 #include <numeric>
+#include <random>
 #include <stdexcept>
 #include <string>
 #include <tuple>
@@ -167,6 +169,14 @@ class ISRSolverSLE : public BaseISRSolver {   // include/ISRSolverSLE.hpp
     check(isr_cond_number(_p, &c));
     return c;
   }
+  // Condition number versus beam-energy spread: the loop of src/isrsolver-condnum-test.cpp:123-135 (sigma = 0
+  // means "spread disabled") from ONE assembly.  Invalidates the cached matrix.
+  std::vector<double> evalConditionNumberSpreadScan(const std::vector<double>& sigmas) {
+    std::vector<double> cond(sigmas.size());
+    check(isr_cond_spread_scan(_p, (int)sigmas.size(), sigmas.data(), 0, cond.data(), nullptr));
+    invalidate();
+    return cond;
+  }
   // the toy loop body for T toys (toy-major V); any output may be nullptr
   virtual void toyBatch(int64_t T, const double* V, const double* bcs0, double* chi2, double* sumBcs, double* ratioStats,
                         uint32_t* ratioHist, double* bcsOut) {
@@ -181,6 +191,36 @@ class ISRSolverSLE : public BaseISRSolver {   // include/ISRSolverSLE.hpp
   }
   virtual void selectForToys() { ensureFactored(); }
   Matrix _integralOperatorMatrix, _covMatrixBornCS;
+};
+
+// ISRSolverSLE2 (include/ISRSolverSLE2.hpp; src/BaseISRSolver2.cpp:151-160, 231-236): the efficiency is one
+// x-histogram per energy point, effHists[point][0..nbins+1] with ROOT's under/overflow cells.
+class ISRSolverSLE2 : public ISRSolverSLE {
+ public:
+  ISRSolverSLE2(std::size_t n, const double* energy, const double* visibleCS, const double* energyErr,
+                const double* visibleCSErr, double thresholdEnergy, const std::vector<std::vector<double>>& effHists,
+                double xlo = 0.0, double xhi = 1.0, int device = 0)
+      : ISRSolverSLE(n, energy, visibleCS, energyErr, visibleCSErr, thresholdEnergy,
+                     rowTable(n, energy, effHists, xlo, xhi), device) {}
+
+ private:
+  static Efficiency rowTable(std::size_t n, const double* energy, const std::vector<std::vector<double>>& h, double xlo,
+                             double xhi) {
+    if (h.size() != n || h.empty() || h[0].size() < 3) throw std::invalid_argument("ISRSolverSLE2: one histogram per energy point");
+    std::vector<int> index(n);
+    std::iota(index.begin(), index.end(), 0);
+    std::sort(index.begin(), index.end(), [energy](int a, int b) { return energy[a] < energy[b]; });
+    Efficiency e;
+    e.kind = ISR_EPS_ROW_TABLE;
+    e.nx = (int)h[0].size() - 2;
+    e.xlo = xlo;
+    e.xhi = xhi;
+    for (std::size_t i = 0; i < n; ++i) {     // histograms follow their points through the energy sort
+      if (h[index[i]].size() != h[0].size()) throw std::invalid_argument("ISRSolverSLE2: histograms differ in size");
+      e.values.insert(e.values.end(), h[index[i]].begin(), h[index[i]].end());
+    }
+    return e;
+  }
 };
 
 class ISRSolverTikhonov : public ISRSolverSLE {   // include/ISRSolverTikhonov.hpp
@@ -207,6 +247,33 @@ class ISRSolverTikhonov : public ISRSolverSLE {   // include/ISRSolverTikhonov.h
     const int64_t L = (int64_t)lambdas.size();
     x.resize(L); y.resize(L); curv.resize(L); dcurv.resize(L);
     check(isr_tikhonov_scan(_p, L, lambdas.data(), _vcs.data(), x.data(), y.data(), curv.data(), dcurv.data(), nullptr));
+  }
+  // chi2 of every (lambda, toy) pair, row-major L x T: the chi2Test loop of isrsolver-Tikhonov-chi2-test for all
+  // lambdas at once
+  std::vector<double> toyScan(const std::vector<double>& lambdas, int64_t T, const double* V, const std::vector<double>& bcs0) {
+    ensureTik();
+    std::vector<double> chi2(lambdas.size() * (std::size_t)T);
+    check(isr_tikhonov_toy_scan(_p, (int64_t)lambdas.size(), lambdas.data(), T, V, bcs0.data(), chi2.data()));
+    return chi2;
+  }
+  // maximise the L-curve curvature (isrsolver-Tikhonov-LCurve, src/isrsolver-Tikhonov-LCurve.cpp:111-133; NLopt
+  // LD_MMA there): dense log-grid scan of the O(N)-per-lambda curvature + golden-section refinement
+  double solveLCurve(double lo = 1e-12, double hi = 1.0) {
+    std::vector<double> grid(2048), x, y, c, dc;
+    for (std::size_t q = 0; q < grid.size(); ++q) grid[q] = lo * std::pow(hi / lo, (double)q / (grid.size() - 1));
+    scanLCurve(grid, x, y, c, dc);
+    const std::size_t k = std::min_element(c.begin(), c.end()) - c.begin();   // curvature is stored as -|kappa|
+    double a = grid[k ? k - 1 : 0], b = grid[std::min(k + 1, grid.size() - 1)];
+    const double gr = (std::sqrt(5.0) - 1.0) / 2.0;
+    auto f = [this](double l) { const double keep = _lambda; _lambda = l; const double v = scan1(2); _lambda = keep; return v; };
+    double p1 = b - gr * (b - a), p2 = a + gr * (b - a), f1 = f(p1), f2 = f(p2);
+    while (std::fabs(b - a) > 1e-6 * std::fabs(0.5 * (a + b))) {
+      if (f1 < f2) { b = p2; p2 = p1; f2 = f1; p1 = b - gr * (b - a); f1 = f(p1); }
+      else { a = p1; p1 = p2; f1 = f2; p2 = a + gr * (b - a); f2 = f(p2); }
+    }
+    _lambda = 0.5 * (a + b);
+    solve();
+    return _lambda;
   }
 
  protected:
@@ -256,6 +323,75 @@ class ISRSolverTSVD : public ISRSolverSLE {   // include/ISRSolverTSVD.hpp
   bool _keepOne = false;
 };
 
+// kernelKuraevFadin(x, s) (include/KuraevFadin.hpp:13) evaluated on the device.
+inline double kernelKuraevFadin(double x, double s, int device = 0) {
+  double out = 0;
+  check(isr_kernel_kf(Context::get(device), 1, &x, &s, &out));
+  return out;
+}
+
+// convolutionKuraevFadin for many energies at once (src/KuraevFadin.cpp:56-73 looped as
+// src/isrsolver-KuraevFadin-convolution.cpp:122-134 does): the quadrature runs on the GPU, fcn is sampled on the
+// host at the node energies the plan asks for, panels are bisected until every energy meets
+// max(absTol, relTol |result|).  errEst (optional) receives the Gauss-Kronrod error estimates.
+inline std::vector<double> convolutionKuraevFadin(const std::vector<double>& energy, const std::function<double(double)>& fcn,
+                                                  const std::vector<double>& minX, const std::vector<double>& maxX,
+                                                  const Efficiency& efficiency = Efficiency(), double relTol = 1e-10,
+                                                  double absTol = 1e-12, std::vector<double>* errEst = nullptr,
+                                                  const std::vector<double>& breakEnergies = {}, int device = 0) {
+  if (minX.size() != energy.size() || maxX.size() != energy.size()) throw std::invalid_argument("convolutionKuraevFadin: sizes differ");
+  isr_eps_desc d = efficiency.desc();
+  isr_conv_plan* plan = nullptr;
+  check(isr_conv_plan_create(Context::get(device), (int64_t)energy.size(), energy.data(), minX.data(), maxX.data(),
+                             efficiency.kind == ISR_EPS_ONE ? nullptr : &d, (int)breakEnergies.size(),
+                             breakEnergies.empty() ? nullptr : breakEnergies.data(), &plan));
+  struct Guard { isr_conv_plan* p; ~Guard() { isr_conv_plan_destroy(p); } } guard{plan};
+  std::vector<double> nodes, f;
+  for (int level = 0; level < 40; ++level) {
+    int64_t npan = 0, nn = 0;
+    check(isr_conv_plan_size(plan, &npan, &nn));
+    if (nn) {
+      nodes.resize(nn); f.resize(nn);
+      check(isr_conv_plan_nodes(plan, nodes.data(), nullptr, nullptr, nullptr));
+      for (int64_t q = 0; q < nn; ++q) f[q] = fcn(nodes[q]);
+      check(isr_conv_plan_feed(plan, f.data()));
+    }
+    int64_t nsplit = 0;
+    check(isr_conv_plan_refine(plan, relTol, absTol, &nsplit));
+    if (!nsplit) break;
+  }
+  int64_t npan = 0, nn = 0;
+  check(isr_conv_plan_size(plan, &npan, &nn));
+  if (nn) {   // level cap reached with children pending: evaluate them and report the estimate
+    nodes.resize(nn); f.resize(nn);
+    check(isr_conv_plan_nodes(plan, nodes.data(), nullptr, nullptr, nullptr));
+    for (int64_t q = 0; q < nn; ++q) f[q] = fcn(nodes[q]);
+    check(isr_conv_plan_feed(plan, f.data()));
+  }
+  std::vector<double> res(energy.size());
+  if (errEst) errEst->resize(energy.size());
+  check(isr_conv_plan_result(plan, res.data(), errEst ? errEst->data() : nullptr));
+  return res;
+}
+// the reference's scalar signature (include/KuraevFadin.hpp:5-9)
+inline double convolutionKuraevFadin(double energy, const std::function<double(double)>& fcn, double min_x, double max_x,
+                                     const Efficiency& efficiency = Efficiency()) {
+  return convolutionKuraevFadin(std::vector<double>{energy}, fcn, {min_x}, {max_x}, efficiency)[0];
+}
+
+// randomDrawVisCS (src/Utils.cpp:6-13) for n toys at once, toy-major n x N.  The reference draws from the
+// unseeded global gRandom; here the stream is a seeded std::mt19937_64 so that campaigns are reproducible.
+inline std::vector<double> randomDrawVisCS(const std::vector<double>& vcs, const std::vector<double>& vcsErr, int n,
+                                           std::uint64_t seed = 20211103ull) {
+  std::mt19937_64 gen(seed);
+  std::normal_distribution<double> gaus(0.0, 1.0);
+  const std::size_t N = vcs.size();
+  std::vector<double> V((std::size_t)n * N);
+  for (int k = 0; k < n; ++k)
+    for (std::size_t i = 0; i < N; ++i) V[(std::size_t)k * N + i] = vcs[i] + vcsErr[i] * gaus(gen);
+  return V;
+}
+
 // chi2Test (src/Chi2Test.cpp:29-104) on caller-supplied toys (toy-major n x N); the ROOT fit/file are left to
 // the caller.  The histogram is TH1F(128, min, max) with under/overflow cells (130 floats).
 inline Chi2TestResult chi2Test(ISRSolverSLE* solver, const Chi2TestArgs& args, const std::vector<double>& toys,
@@ -267,6 +403,25 @@ inline Chi2TestResult chi2Test(ISRSolverSLE* solver, const Chi2TestArgs& args, c
   check(isr_chi2_histogram(Context::get(), args.n, r.chi2.data(), 128, &r.chi2Min, &r.chi2Max, counts.data()));
   r.hist.assign(counts.begin(), counts.end());
   return r;
+}
+
+// chi2TestModel (src/Chi2Test.cpp:113-151): solve, then chi2Test of toys drawn around the model visible cross
+// section against the model Born cross section (the reference reads both from a ROOT file).
+inline Chi2TestResult chi2TestModel(ISRSolverSLE* solver, const Chi2TestArgs& args, const std::vector<double>& modelVCS,
+                                    const std::vector<double>& modelBCS, std::uint64_t seed = 20211103ull) {
+  if (modelVCS.size() != modelBCS.size() || modelVCS.size() != solver->getN()) throw DifferentModelCrossSectionSizes();
+  solver->solve();
+  return chi2Test(solver, args, randomDrawVisCS(modelVCS, solver->vcsErr(), args.n, seed), modelBCS);
+}
+// chi2TestData (src/Chi2Test.cpp:160-195): the reference solution is the mean of the toy solutions around the data.
+inline Chi2TestResult chi2TestData(ISRSolverSLE* solver, const Chi2TestArgs& args, std::uint64_t seed = 20211103ull) {
+  solver->solve();
+  const std::size_t N = solver->getN();
+  std::vector<double> sum(N, 0.0), ones(N, 1.0);
+  solver->toyBatch(args.n, randomDrawVisCS(solver->vcs(), solver->vcsErr(), args.n, seed).data(), ones.data(), nullptr,
+                   sum.data(), nullptr, nullptr, nullptr);
+  for (double& v : sum) v /= args.n;
+  return chi2Test(solver, args, randomDrawVisCS(solver->vcs(), solver->vcsErr(), args.n, seed + 1), sum);
 }
 
 // ratioTestModel (src/RatioTest.cpp:13-62): mean and mean error of (b - b0)/b0 per point from TH1F(1024,-2,2).

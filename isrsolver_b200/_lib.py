@@ -78,6 +78,8 @@ SIGNATURES = {
     "isr_tikhonov_solve": (C.c_int, [_vp, C.c_double, _dp, _dp, _dp]),
     "isr_tikhonov_toy_scan": (C.c_int, [_vp, _i64, _dp, _i64, _dp, _dp, _dp]),
     "isr_tikhonov_toy_scan_dev": (C.c_int, [_vp, _i64, _dp, _i64, _vp, _dp, _vp]),
+    "isr_tikhonov_toy_scan_hist": (C.c_int, [_vp, _i64, _dp, _i64, _dp, _dp, C.c_int, _dp, _up]),
+    "isr_set_scan_kernel": (C.c_int, [_vp, C.c_int]),
     "isr_tikhonov_select": (C.c_int, [_vp, C.c_double]),
     "isr_get_regulariser": (C.c_int, [_vp, _dp]),
     "isr_tsvd_solve": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp]),

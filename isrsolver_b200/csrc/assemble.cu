@@ -616,9 +616,8 @@ __global__ void __launch_bounds__(256) gemm_nn_kernel(int n, const double* __res
 }
 
 // Gout = G_spread(sigE) * G0 (all column-major n x n on the device); S is scratch.
-int apply_spread(isr_problem* p, const double* sigE_dev, const double* G0, double* S, double* Gout) {
+int apply_spread(isr_problem* p, cudaStream_t st, const double* sigE_dev, const double* G0, double* S, double* Gout) {
   const int n = p->n;
-  cudaStream_t st = p->ctx->stream;
   spread_kernel<<<(n * n + 127) / 128, 128, 0, st>>>(n, p->d_ext.p, p->d_invh.p, p->d_Ct.p, sigE_dev, S); ISR_COUNT_LAUNCH();
   dim3 g((n + 31) / 32, (n + 31) / 32);
   gemm_nn_kernel<<<g, 256, 0, st>>>(n, S, G0, Gout); ISR_COUNT_LAUNCH();
@@ -680,7 +679,7 @@ int assemble(isr_problem* p, const double* ecm_err) {
     ISR_TRY(p->d_S.reserve((size_t)n * n));
     ISR_TRY(p->d_tmp.reserve((size_t)n * n));
     ISR_CUDA(cudaMemcpyAsync(p->d_sigE.p, ecm_err, sizeof(double) * n, cudaMemcpyHostToDevice, st));
-    ISR_TRY(apply_spread(p, p->d_sigE.p, p->d_G.p, p->d_S.p, p->d_tmp.p));
+    ISR_TRY(apply_spread(p, st, p->d_sigE.p, p->d_G.p, p->d_S.p, p->d_tmp.p));
     ISR_CUDA(cudaMemcpyAsync(p->d_G.p, p->d_tmp.p, sizeof(double) * n * n, cudaMemcpyDeviceToDevice, st));
   }
   ISR_CUDA(cudaGetLastError());

@@ -1,8 +1,10 @@
 // extern "C" surface of libisr_b200.so (declared in include/isr_b200.h).
 #include <cmath>
 #include <cstdarg>
+#include <algorithm>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "linalg.hpp"
 #include "problem.hpp"
@@ -318,27 +320,57 @@ int isr_cond_spread_scan(isr_problem* p, int K, const double* sigma, int per_poi
   if (!p->G_injected) ISR_TRY(assemble(p, nullptr));          // the unspread matrix
   else if (!p->has_G) { set_error("isr_cond_spread_scan: no matrix"); return ISR_ESTATE; }
   ISR_TRY(p->d_G0.reserve(nn));
-  ISR_TRY(p->d_S.reserve(nn));
-  ISR_TRY(p->d_tmp.reserve(nn));
-  ISR_TRY(p->d_sv.reserve(n));
-  ISR_TRY(p->d_sigK.reserve(n));
   ISR_CUDA(cudaMemcpyAsync(p->d_G0.p, p->d_G.p, sizeof(double) * nn, cudaMemcpyDeviceToDevice, st));
-  std::vector<double> sg(n), sv(n);
+  ISR_CUDA(cudaStreamSynchronize(st));
+  // The K decompositions are independent and each one is a chain of small latency-bound kernels, so they
+  // run on several lanes (stream + cuSOLVER handle + workspace each) at once.
+  struct Lane {
+    cudaStream_t st = nullptr;
+    cusolverDnHandle_t h = nullptr;
+    DevBuf<double> S, A, sig, sv, work;
+    DevBuf<int> info;
+    std::vector<double> h_sig, h_sv;
+    int h_info = 0, k = -1;
+    ~Lane() {
+      if (h) cusolverDnDestroy(h);
+      if (st) cudaStreamDestroy(st);
+    }
+  };
+  const int nlanes = std::min(K, 8);
+  std::vector<Lane> lanes(nlanes);
+  for (Lane& ln : lanes) {
+    ISR_CUDA(cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking));
+    ISR_CUSOLVER(cusolverDnCreate(&ln.h));
+    ISR_CUSOLVER(cusolverDnSetStream(ln.h, ln.st));
+    ISR_TRY(ln.S.reserve(nn)); ISR_TRY(ln.A.reserve(nn)); ISR_TRY(ln.sig.reserve(n)); ISR_TRY(ln.sv.reserve(n));
+    ln.h_sig.resize(n); ln.h_sv.resize(n);
+  }
+  auto collect = [&](Lane& ln) -> int {
+    if (ln.k < 0) return ISR_OK;
+    ISR_CUDA(cudaStreamSynchronize(ln.st));
+    if (ln.h_info != 0) { set_error("isr_cond_spread_scan: SVD failed for setting %d (info = %d)", ln.k, ln.h_info); return ISR_ENUMERIC; }
+    cond_out[ln.k] = ln.h_sv.front() / ln.h_sv.back();
+    if (sv_out) std::memcpy(sv_out + (size_t)ln.k * n, ln.h_sv.data(), sizeof(double) * n);
+    ln.k = -1;
+    return ISR_OK;
+  };
   for (int k = 0; k < K; ++k) {
+    Lane& ln = lanes[k % nlanes];
+    ISR_TRY(collect(ln));                               // the lane's previous setting (also frees h_sig)
     const bool none = !per_point && sigma[k] == 0.0;    // first point of the reference's scan: spread disabled
     if (none) {
-      ISR_CUDA(cudaMemcpyAsync(p->d_tmp.p, p->d_G0.p, sizeof(double) * nn, cudaMemcpyDeviceToDevice, st));
+      ISR_CUDA(cudaMemcpyAsync(ln.A.p, p->d_G0.p, sizeof(double) * nn, cudaMemcpyDeviceToDevice, ln.st));
     } else {
-      for (int i = 0; i < n; ++i) sg[i] = per_point ? sigma[(size_t)k * n + i] : sigma[k];
-      ISR_CUDA(cudaMemcpyAsync(p->d_sigK.p, sg.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
-      ISR_TRY(apply_spread(p, p->d_sigK.p, p->d_G0.p, p->d_S.p, p->d_tmp.p));
+      for (int i = 0; i < n; ++i) ln.h_sig[i] = per_point ? sigma[(size_t)k * n + i] : sigma[k];
+      ISR_CUDA(cudaMemcpyAsync(ln.sig.p, ln.h_sig.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ln.st));
+      ISR_TRY(apply_spread(p, ln.st, ln.sig.p, p->d_G0.p, ln.S.p, ln.A.p));
     }
-    ISR_TRY(svd_values(p->ctx, n, p->d_tmp.p, p->d_sv.p, p->d_work, p->d_info));
-    ISR_CUDA(cudaMemcpyAsync(sv.data(), p->d_sv.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-    ISR_CUDA(cudaStreamSynchronize(st));    // also protects sg before it is refilled
-    cond_out[k] = sv.front() / sv.back();
-    if (sv_out) std::memcpy(sv_out + (size_t)k * n, sv.data(), sizeof(double) * n);
+    ISR_TRY(svd_values_async(ln.h, n, ln.A.p, ln.sv.p, ln.work, ln.info));
+    ISR_CUDA(cudaMemcpyAsync(ln.h_sv.data(), ln.sv.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ln.st));
+    ISR_CUDA(cudaMemcpyAsync(&ln.h_info, ln.info.p, sizeof(int), cudaMemcpyDeviceToHost, ln.st));
+    ln.k = k;
   }
+  for (Lane& ln : lanes) ISR_TRY(collect(ln));
   p->svd_ready = false;    // d_sv no longer belongs to the problem's own matrix
   return ISR_OK;
 }
@@ -426,7 +458,9 @@ int isr_tikhonov_toy_scan_dev(isr_problem* p, int64_t L, const double* lambda, i
                               const double* bcs0, double* chi2_dev) {
   if (!p || !lambda || !V_dev || !bcs0 || !chi2_dev) { set_error("NULL argument"); return ISR_EINVAL; }
   ISR_CUDA(cudaSetDevice(p->ctx->device));
-  return tikhonov_toy_scan_device(p, L, lambda, T, V_dev, bcs0, chi2_dev);
+  ISR_TRY(tikhonov_toy_scan_device(p, L, lambda, T, V_dev, bcs0, chi2_dev));
+  ISR_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  return ISR_OK;
 }
 
 int isr_tikhonov_toy_scan(isr_problem* p, int64_t L, const double* lambda, int64_t T, const double* V,
@@ -435,13 +469,26 @@ int isr_tikhonov_toy_scan(isr_problem* p, int64_t L, const double* lambda, int64
   if (L <= 0 || T <= 0) return ISR_OK;
   ISR_CUDA(cudaSetDevice(p->ctx->device));
   cudaStream_t st = p->ctx->stream;
-  DevBuf<double> dV, dchi;
+  DevBuf<double>&dV = p->d_scan_V, &dchi = p->d_scan_chi;
   ISR_TRY(dV.reserve((size_t)T * p->n));
   ISR_TRY(dchi.reserve((size_t)L * T));
   ISR_CUDA(cudaMemcpyAsync(dV.p, V, sizeof(double) * T * p->n, cudaMemcpyHostToDevice, st));
   ISR_TRY(tikhonov_toy_scan_device(p, L, lambda, T, dV.p, bcs0, dchi.p));
   ISR_CUDA(cudaMemcpyAsync(chi2_out, dchi.p, sizeof(double) * L * T, cudaMemcpyDeviceToHost, st));
   ISR_CUDA(cudaStreamSynchronize(st));
+  return ISR_OK;
+}
+
+int isr_tikhonov_toy_scan_hist(isr_problem* p, int64_t L, const double* lambda, int64_t T, const double* V,
+                               const double* bcs0, int nbins, double* stats_out, uint32_t* counts_out) {
+  if (!p || !lambda || !V || !bcs0) { set_error("NULL argument"); return ISR_EINVAL; }
+  ISR_CUDA(cudaSetDevice(p->ctx->device));
+  return tikhonov_toy_scan_hist(p, L, lambda, T, V, bcs0, nbins, stats_out, counts_out);
+}
+
+int isr_set_scan_kernel(isr_problem* p, int variant) {
+  if (!p || variant < 0 || variant > 1) { set_error("isr_set_scan_kernel: bad argument"); return ISR_EINVAL; }
+  p->scan_variant = variant;
   return ISR_OK;
 }
 

@@ -102,14 +102,14 @@ int svd(isr_ctx* c, int n, double* A, double* U, double* S, double* VT, DevBuf<d
   return ISR_OK;
 }
 
-// Singular values only (A destroyed), descending.
-int svd_values(isr_ctx* c, int n, double* A, double* S, DevBuf<double>& work, DevBuf<int>& info) {
+// Singular values only (A destroyed), descending; asynchronous on the handle's stream -- the caller checks
+// *info after synchronising (several of these run concurrently on separate handles / streams).
+int svd_values_async(cusolverDnHandle_t h, int n, double* A, double* S, DevBuf<double>& work, DevBuf<int>& info) {
   int lwork = 0;
-  ISR_CUSOLVER(cusolverDnDgesvd_bufferSize(c->solver, n, n, &lwork));
+  ISR_CUSOLVER(cusolverDnDgesvd_bufferSize(h, n, n, &lwork));
   ISR_TRY(work.reserve(lwork));
   ISR_TRY(info.reserve(1));
-  ISR_CUSOLVER(cusolverDnDgesvd(c->solver, 'N', 'N', n, n, A, n, S, nullptr, n, nullptr, n, work.p, lwork, nullptr, info.p));
-  ISR_TRY(check_info(c, info.p, "SVD (gesvd, values only)"));
+  ISR_CUSOLVER(cusolverDnDgesvd(h, 'N', 'N', n, n, A, n, S, nullptr, n, nullptr, n, work.p, lwork, nullptr, info.p));
   return ISR_OK;
 }
 

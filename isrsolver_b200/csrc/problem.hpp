@@ -36,7 +36,7 @@ struct isr_problem {
   int64_t last_panels = 0;
   bool has_G = false;
   bool G_injected = false;   // matrix came from isr_set_matrix (cannot be re-assembled)
-  isr::DevBuf<double> d_G0, d_sigK;   // condition-number scan: unspread matrix, per-setting spreads
+  isr::DevBuf<double> d_G0;   // condition-number scan: the unspread matrix
 
   // ---- factorisation / selected solver -------------------------------------------------------
   // All N x N, ROW-major on the device: Sop (solve operator: b = Sop v) and Rop (chi2 factor:
@@ -67,8 +67,12 @@ struct isr_problem {
   // ---- Tikhonov ------------------------------------------------------------------------------
   bool tik_ready = false;
   int tik_deriv = 1;
+  int scan_variant = 0;   // (lambda, toy) scan: 0 = quadratic form in lambda, 1 = direct O(N)-per-pair kernel
   isr::DevBuf<double> d_F, d_U, d_mu, d_P, d_FU, d_w, d_tmp2, d_E, d_E2;
   std::vector<double> h_mu;
+  // (lambda, toy) scan scratch, grow-only
+  isr::DevBuf<double> d_scan_lam, d_scan_b0, d_scan_g, d_scan_Pe, d_scan_AB, d_scan_C, d_scan_V, d_scan_chi, d_scan_stats;
+  isr::DevBuf<uint32_t> d_scan_cnt;
 
   // ---- SVD -----------------------------------------------------------------------------------
   bool svd_ready = false;
@@ -88,5 +92,5 @@ int build_eps_rows(cudaStream_t st, int n, const double* energy, const isr_eps_d
                    DevBuf<double>& d_edges, EpsDev& out);
 int exclusive_scan_int(cudaStream_t st, int n, const int* cnt_dev, int* off_dev);   // off[n] = total
 int assemble(isr_problem* p, const double* ecm_err);
-int apply_spread(isr_problem* p, const double* sigE_dev, const double* G0, double* S, double* Gout);
+int apply_spread(isr_problem* p, cudaStream_t st, const double* sigE_dev, const double* G0, double* S, double* Gout);
 }  // namespace isr

@@ -287,6 +287,62 @@ __global__ void __launch_bounds__(256) lambda_scan_kernel(int n, int ld, int64_t
   }
 }
 
+// The (lambda, toy) scan collapses further: e is fixed per toy and f per problem, so
+//     chi2(lambda, k) = |e_k - lambda f|^2 = A_k - 2 lambda B_k + lambda^2 C,   A_k = |e_k|^2, B_k = e_k . f, C = |f|^2
+// -- two dot products per toy, then O(1) per pair: the scan is bound by WRITING chi2 (8 B per pair).
+// No catastrophic cancellation: e_k is unit-variance noise in every eigen-direction (the signal part
+// cancels exactly: U^T G^T W G b0 = mu (.) U^T F b0), so e_k is never aligned with the fixed vector f and
+// |e_k - lambda f|^2 >= (|e_k| - lambda |f|)^2 stays comparable to the larger of the two terms.
+// One warp per toy, lane-strided partial sums + fixed xor tree (deterministic).
+__global__ void __launch_bounds__(256) scan_coeff_kernel(int n, int ld, int64_t T, const double* __restrict__ E,
+                                                          const double* __restrict__ f, double* __restrict__ AB) {
+  const int64_t k = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (k >= T) return;
+  const double* e = E + k * ld;
+  double a = 0.0, b = 0.0;
+  for (int m = lane; m < n; m += 32) {
+    const double ev = e[m];
+    a = fma(ev, ev, a);
+    b = fma(ev, f[m], b);
+  }
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, s);
+    b += __shfl_xor_sync(0xffffffffu, b, s);
+  }
+  if (lane == 0) {
+    AB[2 * k] = a;
+    AB[2 * k + 1] = b;
+  }
+}
+// C = |f|^2 (one warp)
+__global__ void scan_fnorm_kernel(int n, const double* __restrict__ f, double* __restrict__ out) {
+  double c = 0.0;
+  for (int m = threadIdx.x; m < n; m += 32) c = fma(f[m], f[m], c);
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) c += __shfl_xor_sync(0xffffffffu, c, s);
+  if (threadIdx.x == 0) *out = c;
+}
+// chi2[l][t0 + k] = A_k - lambda_l (2 B_k - lambda_l C): thread = toy (coalesced row writes), 8 lambdas per thread
+constexpr int kPairLam = 8;
+__global__ void __launch_bounds__(256) scan_pair_kernel(int64_t T, const double* __restrict__ AB, const double* __restrict__ C,
+                                                         int64_t L, const double* __restrict__ lam, double* __restrict__ chi2,
+                                                         int64_t stride) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t l0 = (int64_t)blockIdx.y * kPairLam;
+  if (k >= T) return;
+  const double a = AB[2 * k], b2 = 2.0 * AB[2 * k + 1], c = *C;
+#pragma unroll
+  for (int q = 0; q < kPairLam; ++q) {
+    if (l0 + q < L) {
+      const double la = lam[l0 + q];
+      // streaming store: chi2 is written once and read by nobody on the device
+      __stcs(&chi2[(size_t)(l0 + q) * stride + k], fma(-la, fma(-la, c, b2), a));
+    }
+  }
+}
+
 int tikhonov_toy_scan_device(isr_problem* p, int64_t L, const double* lambda, int64_t T, const double* V_dev,
                              const double* bcs0, double* chi2_dev) {
   if (!p->tik_ready) { set_error("isr_tikhonov_toy_scan: call isr_tikhonov_prepare first"); return ISR_ESTATE; }
@@ -294,18 +350,23 @@ int tikhonov_toy_scan_device(isr_problem* p, int64_t L, const double* lambda, in
   const int n = p->n, ld = (n + 1) & ~1;
   isr_ctx* c = p->ctx;
   cudaStream_t st = c->stream;
-  DevBuf<double> dlam, db0, dg;
+  // persistent scratch (grow-only): repeated scans do not pay cudaMalloc / cudaFree
+  DevBuf<double>&dlam = p->d_scan_lam, &db0 = p->d_scan_b0, &dg = p->d_scan_g, &dPe = p->d_scan_Pe, &dAB = p->d_scan_AB, &dC = p->d_scan_C;
   ISR_TRY(dlam.reserve(L)); ISR_TRY(db0.reserve(n)); ISR_TRY(dg.reserve(3 * (size_t)n));
   ISR_CUDA(cudaMemcpyAsync(dlam.p, lambda, sizeof(double) * L, cudaMemcpyHostToDevice, st));
   ISR_CUDA(cudaMemcpyAsync(db0.p, bcs0, sizeof(double) * n, cudaMemcpyHostToDevice, st));
   ISR_TRY(gemv(c, true, n, p->d_FU.p, db0.p, dg.p));               // g = (F U)^T b0 = U^T F b0
   // temporarily route the tile kernel: Sop <- Pe, "b0" <- g sqrt(mu); D then holds e
-  DevBuf<double> dPe;
   ISR_TRY(dPe.reserve((size_t)n * ld));
   tik_proj_kernel<<<(n * ld + 255) / 256, 256, 0, st>>>(n, ld, p->d_P.p, p->d_mu.p, dg.p, dPe.p, dg.p + n, dg.p + 2 * n); ISR_COUNT_LAUNCH();
   ISR_CUDA(cudaGetLastError());
   const size_t smem = sizeof(double) * ((size_t)kScanToys * (n | 1) + n);
-  ISR_CUDA(cudaFuncSetAttribute(lambda_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const bool direct = p->scan_variant == 1;    // 1: O(N)-per-pair reference kernel, 0: quadratic form (default)
+  if (direct) ISR_CUDA(cudaFuncSetAttribute(lambda_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (!direct) {
+    ISR_TRY(dC.reserve(1));
+    scan_fnorm_kernel<<<1, 32, 0, st>>>(n, dg.p + 2 * n, dC.p); ISR_COUNT_LAUNCH();
+  }
   // chunk so that E (T x ld) stays modest; the scan reads E once per chunk
   const int64_t Tc = std::min<int64_t>(T, 1 << 18);
   ISR_TRY(p->d_E2.reserve((size_t)Tc * ld));
@@ -313,11 +374,86 @@ int tikhonov_toy_scan_device(isr_problem* p, int64_t L, const double* lambda, in
     const int64_t tc = std::min<int64_t>(Tc, T - t0);
     ISR_TRY(project_device(p, tc, V_dev + t0 * n, dPe.p, dg.p + n, p->d_E2.p));
     // output rows (one per lambda) have the full stride T; this chunk starts at column t0
-    lambda_scan_kernel<<<(unsigned)((tc + kScanToys - 1) / kScanToys), 256, smem, st>>>(
-        n, ld, tc, p->d_E2.p, dg.p + 2 * n, L, dlam.p, chi2_dev + t0, T); ISR_COUNT_LAUNCH();
+    if (direct) {
+      lambda_scan_kernel<<<(unsigned)((tc + kScanToys - 1) / kScanToys), 256, smem, st>>>(
+          n, ld, tc, p->d_E2.p, dg.p + 2 * n, L, dlam.p, chi2_dev + t0, T); ISR_COUNT_LAUNCH();
+    } else {
+      ISR_TRY(dAB.reserve((size_t)2 * Tc));
+      scan_coeff_kernel<<<(unsigned)((tc + 7) / 8), 256, 0, st>>>(n, ld, tc, p->d_E2.p, dg.p + 2 * n, dAB.p); ISR_COUNT_LAUNCH();
+      dim3 grid((unsigned)((tc + 255) / 256), (unsigned)((L + kPairLam - 1) / kPairLam));
+      scan_pair_kernel<<<grid, 256, 0, st>>>(tc, dAB.p, dC.p, L, dlam.p, chi2_dev + t0, T); ISR_COUNT_LAUNCH();
+    }
   }
   ISR_CUDA(cudaGetLastError());
-  ISR_CUDA(cudaStreamSynchronize(st));  // dlam / db0 / dg / dPe go out of scope
+  return ISR_OK;    // asynchronous on the context stream; lambda / bcs0 were staged from pageable memory (copied at call time)
+}
+
+// Per-lambda chi2 test summary without moving the L x T chi2 matrix to the host: one CTA per lambda computes
+// min / max / mean over the T toys (fixed-order tree: deterministic) and then fills TH1F(nbins, min, max)
+// with ROOT's bin arithmetic (src/Chi2Test.cpp:64-78 -- the maximum lands in the overflow cell).
+__global__ void __launch_bounds__(256) scan_hist_kernel(int64_t T, const double* __restrict__ chi2, int nbins,
+                                                         double* __restrict__ stats, uint32_t* __restrict__ counts) {
+  extern __shared__ uint32_t sh_cnt[];
+  __shared__ double s_lo[8], s_hi[8], s_sum[8];
+  __shared__ double b_lo, b_hi;
+  const double* row = chi2 + (size_t)blockIdx.x * T;
+  double lo = INFINITY, hi = -INFINITY, sum = 0.0;
+  for (int64_t k = threadIdx.x; k < T; k += blockDim.x) {
+    const double v = row[k];
+    lo = fmin(lo, v);
+    hi = fmax(hi, v);
+    sum += v;
+  }
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, s));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, s));
+    sum += __shfl_xor_sync(0xffffffffu, sum, s);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { s_lo[w] = lo; s_hi[w] = hi; s_sum[w] = sum; }
+  for (int q = threadIdx.x; q < nbins + 2; q += blockDim.x) sh_cnt[q] = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = s_lo[0], b = s_hi[0], c = s_sum[0];
+    for (int q = 1; q < 8; ++q) { a = fmin(a, s_lo[q]); b = fmax(b, s_hi[q]); c += s_sum[q]; }
+    b_lo = a; b_hi = b;
+    stats[3 * blockIdx.x + 0] = a;
+    stats[3 * blockIdx.x + 1] = b;
+    stats[3 * blockIdx.x + 2] = c / (double)T;
+  }
+  __syncthreads();
+  const double a = b_lo, b = b_hi;
+  for (int64_t k = threadIdx.x; k < T; k += blockDim.x) {
+    const double x = row[k];
+    int bin;
+    if (x < a) bin = 0;
+    else if (!(x < b)) bin = nbins + 1;
+    else bin = 1 + (int)__ddiv_rn(__dmul_rn((double)nbins, __dsub_rn(x, a)), __dsub_rn(b, a));
+    atomicAdd(&sh_cnt[bin], 1u);
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < nbins + 2; q += blockDim.x) counts[(size_t)blockIdx.x * (nbins + 2) + q] = sh_cnt[q];
+}
+
+int tikhonov_toy_scan_hist(isr_problem* p, int64_t L, const double* lambda, int64_t T, const double* V, const double* bcs0,
+                           int nbins, double* stats_out, uint32_t* counts_out) {
+  if (nbins < 1 || nbins > 8190) { set_error("isr_tikhonov_toy_scan_hist: nbins out of range"); return ISR_EINVAL; }
+  if (L <= 0 || T <= 0) return ISR_OK;
+  cudaStream_t st = p->ctx->stream;
+  DevBuf<double>&dV = p->d_scan_V, &dchi = p->d_scan_chi, &dstats = p->d_scan_stats;
+  DevBuf<uint32_t>& dcnt = p->d_scan_cnt;
+  ISR_TRY(dV.reserve((size_t)T * p->n));
+  ISR_TRY(dchi.reserve((size_t)L * T));
+  ISR_TRY(dstats.reserve(3 * (size_t)L));
+  ISR_TRY(dcnt.reserve((size_t)L * (nbins + 2)));
+  ISR_CUDA(cudaMemcpyAsync(dV.p, V, sizeof(double) * T * p->n, cudaMemcpyHostToDevice, st));
+  ISR_TRY(tikhonov_toy_scan_device(p, L, lambda, T, dV.p, bcs0, dchi.p));
+  scan_hist_kernel<<<(unsigned)L, 256, sizeof(uint32_t) * (nbins + 2), st>>>(T, dchi.p, nbins, dstats.p, dcnt.p); ISR_COUNT_LAUNCH();
+  ISR_CUDA(cudaGetLastError());
+  if (stats_out) ISR_CUDA(cudaMemcpyAsync(stats_out, dstats.p, sizeof(double) * 3 * L, cudaMemcpyDeviceToHost, st));
+  if (counts_out) ISR_CUDA(cudaMemcpyAsync(counts_out, dcnt.p, sizeof(uint32_t) * L * (nbins + 2), cudaMemcpyDeviceToHost, st));
+  ISR_CUDA(cudaStreamSynchronize(st));
   return ISR_OK;
 }
 

@@ -695,6 +695,19 @@ class ISRSolverTikhonov(ISRSolverSLE):
                                                 L.dptr(_f64(bcs0, self._n)), L.dptr(out)))
         return out
 
+    def toy_scan_hist(self, lambdas, V, bcs0, nbins=128):
+        """The chi2 test (chi2Test, src/Chi2Test.cpp:38-78) for every lambda at once, summarised on the GPU:
+        returns {"min", "max", "mean"} (L,) and "hist" (L, nbins + 2) float32 TH1F cells per lambda."""
+        self._ensure_tik()
+        lam = _f64(np.atleast_1d(lambdas))
+        V = np.ascontiguousarray(V, dtype=np.float64)
+        stats = np.empty((lam.size, 3))
+        counts = np.zeros((lam.size, nbins + 2), dtype=np.uint32)
+        L.check(self._lib.isr_tikhonov_toy_scan_hist(self._p, lam.size, L.dptr(lam), V.shape[0], L.dptr(V),
+                                                     L.dptr(_f64(bcs0, self._n)), int(nbins), L.dptr(stats), L.uptr(counts)))
+        return {"min": stats[:, 0].copy(), "max": stats[:, 1].copy(), "mean": stats[:, 2].copy(),
+                "hist": counts.astype(np.float32)}
+
     def regulariser(self):
         self._ensure_tik()
         F = np.empty((self._n, self._n))

@@ -56,6 +56,39 @@ int main(int argc, char** argv) {
     v.setUpperTSVDIndex((int)n / 2);
     v.solve();
     write_bin(d + "/out_tsvd_bcs.bin", v.bcs().data(), n);
+
+    // ---- additions: free functions, SLE2, scans -----------------------------------------------------
+    std::printf("kernel %.17g\n", kernelKuraevFadin(0.01, 2.25));
+    auto bw = [](double e) {
+      if (e <= 0.827) return 0.0;
+      const double m = 1.5, g = 0.25, ps = 1.0 - 0.827 * 0.827 / (e * e), d = e * e - m * m;
+      return 4.0 * m * m * g * g / (d * d + m * m * g * g) * ps * std::sqrt(ps);
+    };
+    std::vector<double> lo(n, 0.0), hi(n), er;
+    for (size_t i = 0; i < n; ++i) hi[i] = 1.0 - (0.827 / ecm[i]) * (0.827 / ecm[i]);
+    auto vis = convolutionKuraevFadin(ecm, bw, lo, hi, Efficiency(), 1e-10, 1e-12, &er);
+    write_bin(d + "/out_vis.bin", vis.data(), n);
+    std::printf("conv_scalar %.17g\n", convolutionKuraevFadin(ecm[3], bw, 0.0, hi[3]));
+    auto cond = s.evalConditionNumberSpreadScan({0.0, 0.002});
+    std::printf("condscan %.15g %.15g\n", cond[0], cond[1]);
+    auto tm = chi2TestModel(&s, {256, 1e4, ""}, vcs, bcs0);
+    double mean = 0; for (double c : tm.chi2) mean += c / tm.chi2.size();
+    std::printf("chi2model_mean %.6g\n", mean);
+    auto td = chi2TestData(&s, {256, 1e4, ""});
+    std::printf("chi2data_n %zu\n", td.chi2.size());
+    std::vector<std::vector<double>> hists(n, std::vector<double>(10, 0.5));
+    ISRSolverSLE2 s2(n, ecm.data(), vcs.data(), nullptr, err.data(), 0.827, hists);
+    s2.evalEqMatrix();
+    s.setRangeInterpSettings({});
+    s.evalEqMatrix();
+    double worst = 0;
+    for (size_t q = 0; q < n * n; ++q)
+      worst = std::max(worst, std::fabs(s2.getIntegralOperatorMatrix().a[q] - 0.5 * s.getIntegralOperatorMatrix().a[q]));
+    std::printf("sle2_half %.3g\n", worst);
+    t.setLambda(1e-3);
+    auto scan = t.toyScan({1e-4, 1e-3}, 8, toys.data(), bcs0);
+    std::printf("toyscan %zu %.15g\n", scan.size(), scan[8]);
+    std::printf("lcurve_lambda %.6g\n", t.solveLCurve());
   } catch (const std::exception& e) {
     std::cerr << "exception: " << e.what() << "\n";
     return 1;

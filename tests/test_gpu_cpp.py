@@ -49,3 +49,14 @@ def test_cpp_mirror_matches_oracle(tmp_path, oracle):
     assert float(line[4]) == pytest.approx(ref["y"], rel=1e-7) and float(line[6]) == pytest.approx(ref["curv"], rel=1e-7)
     np.testing.assert_allclose(rd("out_tsvd_bcs.bin"), oracle.tsvd_solve(Gl, g["vcs"], g["vcs_err"], n // 2)[0], rtol=1e-7)
     assert f"hist_sum {len(g['toys'])}" in out.stdout
+    # free functions, SLE2 and the scans added on top of the class mirror
+    val = lambda key: [l for l in out.stdout.splitlines() if l.startswith(key + " ")][0].split()[1:]
+    assert float(val("kernel")[0]) == pytest.approx(5.283686571158812, rel=1e-13)
+    np.testing.assert_allclose(rd("out_vis.bin"), g["vcs_ref"], rtol=1e-8)       # the compiled reference's convolution
+    assert float(val("conv_scalar")[0]) == pytest.approx(g["vcs_ref"][3], rel=1e-8)
+    c0, c1 = map(float, val("condscan"))
+    assert c0 == pytest.approx(np.linalg.cond(g["G_converged"]), rel=1e-8) and c1 > c0
+    assert float(val("chi2model_mean")[0]) == pytest.approx(n, rel=0.15)
+    assert int(val("chi2data_n")[0]) == 256
+    assert float(val("sle2_half")[0]) < 1e-15
+    assert int(val("toyscan")[0]) == 16 and float(val("lcurve_lambda")[0]) > 0

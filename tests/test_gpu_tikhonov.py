@@ -95,6 +95,40 @@ def test_toy_scan_vs_literal(oracle):
     np.testing.assert_allclose(r["bcs"], V @ t["Ap"].T, rtol=1e-8, atol=1e-8 * np.abs(V).max())
 
 
+def test_toy_scan_quadratic_form_equals_direct_kernel():
+    """chi2(lambda, k) = A_k - 2 lambda B_k + lambda^2 C (default) against the direct O(N)-per-pair kernel over
+    18 decades of lambda, including the bias-dominated end where lambda^2 C dwarfs A_k."""
+    from isrsolver_b200 import _lib as L
+    g = load_golden("c4_tikhonov_n32_spread")
+    s = tik_solver(g)
+    lam = np.geomspace(1e-12, 1e6, 73)
+    V, b0 = g["toys"], g["bcs0"]
+    quad = s.toy_scan(lam, V, b0)
+    L.check(L.load().isr_set_scan_kernel(s._p, 1))
+    direct = s.toy_scan(lam, V, b0)
+    L.check(L.load().isr_set_scan_kernel(s._p, 0))
+    assert np.all(direct > 0)
+    np.testing.assert_allclose(quad, direct, rtol=1e-10)
+    np.testing.assert_array_equal(quad, s.toy_scan(lam, V, b0))     # deterministic
+
+
+def test_toy_scan_hist_matches_host_binning(oracle):
+    """Per-lambda TH1F(128, min, max) filled on the device == ROOT bin arithmetic on the chi2 rows."""
+    from isrsolver_b200 import dist
+    g = load_golden("c4_tikhonov_n32_spread")
+    s = tik_solver(g)
+    lam = np.geomspace(1e-6, 1.0, 7)
+    V, b0 = g["toys"], g["bcs0"]
+    chi2 = s.toy_scan(lam, V, b0)
+    r = s.toy_scan_hist(lam, V, b0)
+    np.testing.assert_array_equal(r["min"], chi2.min(1))
+    np.testing.assert_array_equal(r["max"], chi2.max(1))
+    np.testing.assert_allclose(r["mean"], chi2.mean(1), rtol=1e-13)
+    for q in range(len(lam)):
+        np.testing.assert_array_equal(r["hist"][q], dist.th1_counts(chi2[q], 128, chi2[q].min(), chi2[q].max()).astype(np.float32))
+        assert r["hist"][q].sum() == V.shape[0] and r["hist"][q][129] >= 1      # the maximum is in the overflow cell
+
+
 def test_solve_lcurve_finds_curvature_maximum():
     g = load_golden("c4_tikhonov_n32_spread")
     s = tik_solver(g)
