@@ -238,6 +238,17 @@ def run_b200(args, rank, world, local_rank):
         L.check(lib.isr_chi2_histogram(ctx, T, L.dptr(chi2_host), 128, C.byref(lo), C.byref(hi), L.uptr(counts)))
         return counts
 
+    lohi = np.zeros(2)
+
+    def step_campaign():
+        """The same test asked for BY COUNT, as the reference's chi2Test(n, ...) is: toys drawn on the device
+        (Philox, csrc/rng.cu), chi2 histogrammed on the device; only vcs / err / bcs0 go in, 130 counters out."""
+        L.check(lib.isr_assemble(prob, None, None))
+        L.check(lib.isr_factor(prob, L.dptr(err)))
+        L.check(lib.isr_toy_campaign(prob, T, rank * T, 20211103, L.dptr(vcs), L.dptr(err), L.dptr(bcs0), None,
+                                     L.dptr(sumb_host), None, None, 128, L.dptr(lohi), L.uptr(counts)))
+        return counts
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -272,6 +283,9 @@ def run_b200(args, rank, world, local_rank):
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
     ms_e2e = timed(lambda: step_e2e(), args.steps, record=None)
+    step_campaign()
+    ms_rng = timed(lambda: step_campaign(), args.steps, record=None)
+    assert int(counts.sum()) == T
 
     assert int(hist.sum()) == T * world, "histogram lost entries"
     if rank != 0:
@@ -301,6 +315,11 @@ def run_b200(args, rank, world, local_rank):
                                     "(MEASURED_PEAKS.json carries no FP64 figure; bf16 peak does not apply to an FP64 kernel)"},
         "e2e": {"value": T * world / (ms_e2e / args.steps * 1e-3), "unit": "toys/s",
                 "h2d_bytes_per_step": T * n * 8, "d2h_bytes_per_step": T * 8 + n * 8 + 130 * 4, "ms_per_step": ms_e2e / args.steps},
+        "campaign_by_count": {"value": T * world / (ms_rng / args.steps * 1e-3), "unit": "toys/s", "ms_per_step": ms_rng / args.steps,
+                              "h2d_bytes_per_step": 3 * n * 8, "d2h_bytes_per_step": n * 8 + 130 * 4 + 16,
+                              "note": "same chi2 test through isr_toy_campaign: toys drawn on the device (Philox4x32-10 + Box-Muller, "
+                                      "as the reference's chi2Test(n) draws them internally), histogram on the device; NOT the e2e "
+                                      "figure -- its toy vectors never cross PCIe"},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:

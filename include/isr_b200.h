@@ -131,6 +131,25 @@ int isr_toy_batch_dev(isr_problem* p, int64_t T, const double* V_dev, const doub
 /* Kernel variant: 0 = auto, 1 = DMMA (mma.sync f64 tensor pipe), 2 = DFMA (CUDA cores). */
 int isr_set_toy_kernel(isr_problem* p, int variant);
 
+/* Toy campaigns by COUNT, as the reference's chi2Test / chi2TestData / ratioTestModel take them (src/Chi2Test.cpp:29-60,
+ * 160-195; src/RatioTest.cpp:13-45): toys first_toy .. first_toy + T - 1 of the stream `seed` are drawn on the device,
+ *   V[k][i] = vcs[i] + vcs_err[i] * z(seed, k, i)      (randomDrawVisCS, src/Utils.cpp:6-13)
+ * with z from counter-based Philox4x32-10 + Box-Muller (isrsolver_b200/csrc/rng.cu) -- a toy depends only on
+ * (seed, k, i), so a campaign sharded over ranks by first_toy reproduces the single-GPU campaign exactly.
+ * ROOT's unseeded global TRandom3 stream cannot be reproduced; isr_draw_toys returns the very vectors a campaign
+ * uses, for checking it against any other implementation.  Outputs as isr_toy_batch; additionally the
+ * TH1F(nbins, min, max) chi2 histogram of src/Chi2Test.cpp:64-78 (chi2_lo_hi_out[2], chi2_counts_out[nbins + 2])
+ * computed without moving chi2 to the host.  Any output pointer may be NULL. */
+int isr_toy_campaign(isr_problem* p, int64_t T, int64_t first_toy, uint64_t seed, const double* vcs, const double* vcs_err,
+                     const double* bcs0, double* chi2_out, double* sum_bcs_out, double* ratio_stats_out,
+                     uint32_t* ratio_hist_out, int nbins, double* chi2_lo_hi_out, uint32_t* chi2_counts_out);
+/* Same with device-resident outputs (accumulators are ADDED to); asynchronous on the context stream. */
+int isr_toy_campaign_dev(isr_problem* p, int64_t T, int64_t first_toy, uint64_t seed, const double* vcs, const double* vcs_err,
+                         const double* bcs0, double* chi2_dev, double* sum_bcs_dev, double* ratio_stats_dev,
+                         uint32_t* ratio_hist_dev);
+int isr_draw_toys(isr_ctx* ctx, int64_t T, int n, int64_t first_toy, uint64_t seed, const double* vcs, const double* vcs_err,
+                  double* V_out /* T x n toy-major, host */);
+
 /* chi2 histogram, src/Chi2Test.cpp:64-78: TH1F(128, min, max) filled with every chi2 (ROOT bin
  * arithmetic; the maximum lands in the overflow cell).  counts_out has nbins+2 entries. */
 int isr_minmax_dev(isr_ctx* ctx, int64_t n, const double* v_dev, double* min_out, double* max_out);

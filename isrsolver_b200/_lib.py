@@ -69,6 +69,9 @@ SIGNATURES = {
     "isr_cond_spread_scan": (C.c_int, [_vp, C.c_int, _dp, C.c_int, _dp, _dp]),
     "isr_toy_batch": (C.c_int, [_vp, _i64, _dp, _dp, _dp, _dp, _dp, _up, _dp]),
     "isr_toy_batch_dev": (C.c_int, [_vp, _i64, _vp, _dp, _vp, _vp, _vp, _vp, _vp]),
+    "isr_toy_campaign": (C.c_int, [_vp, _i64, _i64, C.c_uint64, _dp, _dp, _dp, _dp, _dp, _dp, _up, C.c_int, _dp, _up]),
+    "isr_toy_campaign_dev": (C.c_int, [_vp, _i64, _i64, C.c_uint64, _dp, _dp, _dp, _vp, _vp, _vp, _vp]),
+    "isr_draw_toys": (C.c_int, [_vp, _i64, C.c_int, _i64, C.c_uint64, _dp, _dp, _dp]),
     "isr_set_toy_kernel": (C.c_int, [_vp, C.c_int]),
     "isr_minmax_dev": (C.c_int, [_vp, _i64, _vp, _dp, _dp]),
     "isr_histogram_dev": (C.c_int, [_vp, _i64, _vp, C.c_int, C.c_double, C.c_double, _up]),

@@ -412,6 +412,70 @@ int isr_toy_batch_dev(isr_problem* p, int64_t T, const double* V_dev, const doub
   return toy_batch_device(p, T, V_dev, p->d_b0.p, o);
 }
 
+// ---- toy campaigns by count (toys drawn on the device) ----------------------------------------------
+int isr_draw_toys(isr_ctx* ctx, int64_t T, int n, int64_t first_toy, uint64_t seed, const double* vcs, const double* vcs_err,
+                  double* V_out) {
+  if (!ctx || !vcs || !vcs_err || !V_out || n < 1 || T < 0) { set_error("isr_draw_toys: bad argument"); return ISR_EINVAL; }
+  if (T == 0) return ISR_OK;
+  ISR_CUDA(cudaSetDevice(ctx->device));
+  DevBuf<double> dg, dV;
+  ISR_TRY(dg.reserve((size_t)2 * n));
+  ISR_TRY(dV.reserve((size_t)T * n));
+  ISR_CUDA(cudaMemcpyAsync(dg.p, vcs, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  ISR_CUDA(cudaMemcpyAsync(dg.p + n, vcs_err, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  ISR_TRY(draw_toys_device(ctx, T, n, first_toy, seed, dg.p, dg.p + n, dV.p));
+  ISR_CUDA(cudaMemcpyAsync(V_out, dV.p, sizeof(double) * T * n, cudaMemcpyDeviceToHost, ctx->stream));
+  ISR_CUDA(cudaStreamSynchronize(ctx->stream));
+  return ISR_OK;
+}
+
+int isr_toy_campaign_dev(isr_problem* p, int64_t T, int64_t first_toy, uint64_t seed, const double* vcs, const double* vcs_err,
+                         const double* bcs0, double* chi2_dev, double* sum_bcs_dev, double* ratio_stats_dev,
+                         uint32_t* ratio_hist_dev) {
+  if (!p || !vcs || !vcs_err || !bcs0 || T < 0) { set_error("isr_toy_campaign_dev: bad argument"); return ISR_EINVAL; }
+  ISR_CUDA(cudaSetDevice(p->ctx->device));
+  return toy_campaign_device(p, T, first_toy, seed, vcs, vcs_err, bcs0, chi2_dev, sum_bcs_dev, ratio_stats_dev, ratio_hist_dev);
+}
+
+int isr_toy_campaign(isr_problem* p, int64_t T, int64_t first_toy, uint64_t seed, const double* vcs, const double* vcs_err,
+                     const double* bcs0, double* chi2_out, double* sum_bcs_out, double* ratio_stats_out,
+                     uint32_t* ratio_hist_out, int nbins, double* chi2_lo_hi_out, uint32_t* chi2_counts_out) {
+  if (!p || !vcs || !vcs_err || !bcs0 || T < 0) { set_error("isr_toy_campaign: bad argument"); return ISR_EINVAL; }
+  if ((chi2_lo_hi_out || chi2_counts_out) && (nbins < 1 || nbins > 8190)) { set_error("isr_toy_campaign: nbins out of range"); return ISR_EINVAL; }
+  ISR_CUDA(cudaSetDevice(p->ctx->device));
+  const int n = p->n;
+  cudaStream_t st = p->ctx->stream;
+  if (T == 0) {
+    if (sum_bcs_out) std::memset(sum_bcs_out, 0, sizeof(double) * n);
+    if (ratio_stats_out) std::memset(ratio_stats_out, 0, sizeof(double) * 3 * n);
+    if (ratio_hist_out) std::memset(ratio_hist_out, 0, sizeof(uint32_t) * (size_t)n * 1026);
+    return ISR_OK;
+  }
+  const bool want_chi2 = chi2_out || chi2_lo_hi_out || chi2_counts_out;
+  if (want_chi2) ISR_TRY(p->d_chi2h.reserve((size_t)T));
+  ISR_TRY(p->d_stat.reserve((size_t)4 * n));
+  ISR_CUDA(cudaMemsetAsync(p->d_stat.p, 0, sizeof(double) * 4 * n, st));
+  if (ratio_hist_out) {
+    ISR_TRY(p->d_rhist.reserve((size_t)n * 1026));
+    ISR_CUDA(cudaMemsetAsync(p->d_rhist.p, 0, sizeof(uint32_t) * (size_t)n * 1026, st));
+  }
+  ISR_TRY(toy_campaign_device(p, T, first_toy, seed, vcs, vcs_err, bcs0, want_chi2 ? p->d_chi2h.p : nullptr,
+                              sum_bcs_out ? p->d_stat.p : nullptr, ratio_stats_out ? p->d_stat.p + n : nullptr,
+                              ratio_hist_out ? p->d_rhist.p : nullptr));
+  if (chi2_out) ISR_CUDA(cudaMemcpyAsync(chi2_out, p->d_chi2h.p, sizeof(double) * T, cudaMemcpyDeviceToHost, st));
+  if (sum_bcs_out) ISR_CUDA(cudaMemcpyAsync(sum_bcs_out, p->d_stat.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  if (ratio_stats_out) ISR_CUDA(cudaMemcpyAsync(ratio_stats_out, p->d_stat.p + n, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, st));
+  if (ratio_hist_out) ISR_CUDA(cudaMemcpyAsync(ratio_hist_out, p->d_rhist.p, sizeof(uint32_t) * (size_t)n * 1026, cudaMemcpyDeviceToHost, st));
+  if (chi2_lo_hi_out || chi2_counts_out) {
+    double lo = 0, hi = 0;
+    ISR_TRY(minmax_device(p->ctx, T, p->d_chi2h.p, &lo, &hi));
+    if (chi2_lo_hi_out) { chi2_lo_hi_out[0] = lo; chi2_lo_hi_out[1] = hi; }
+    if (chi2_counts_out) ISR_TRY(histogram_device(p->ctx, T, p->d_chi2h.p, nbins, lo, hi, chi2_counts_out));
+  }
+  ISR_CUDA(cudaStreamSynchronize(st));
+  return ISR_OK;
+}
+
 int isr_minmax_dev(isr_ctx* ctx, int64_t n, const double* v_dev, double* min_out, double* max_out) {
   if (!ctx || !v_dev || !min_out || !max_out) { set_error("NULL argument"); return ISR_EINVAL; }
   ISR_CUDA(cudaSetDevice(ctx->device));

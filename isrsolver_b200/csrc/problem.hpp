@@ -44,7 +44,8 @@ struct isr_problem {
   isr::DevBuf<double> d_Ginv, d_R, d_Cov, d_InvCov, d_Sop, d_Rop, d_werr;
   isr::DevBuf<double> d_work;
   isr::DevBuf<int> d_ipiv, d_info;
-  std::vector<double> vcs_err, h_b0;
+  std::vector<double> vcs_err, h_b0, h_gen;   // h_gen: {vcs, vcs_err} of the device toy generator (stable host mirror)
+  isr::DevBuf<double> d_gen;
   bool factored = false;
   bool solver_selected = false;
   int toy_variant = 0;

@@ -197,4 +197,43 @@ int toy_batch_host(isr_problem* p, int64_t T, const double* V, const double* bcs
   return ISR_OK;
 }
 
+// --------------------------------------------------------------------------------------------------
+// Toy campaign by count: toys drawn on the device (rng.cu), chunk by chunk through the fused kernel.
+// --------------------------------------------------------------------------------------------------
+int toy_campaign_device(isr_problem* p, int64_t T, int64_t first_toy, uint64_t seed, const double* vcs,
+                        const double* vcs_err, const double* bcs0, double* chi2_dev, double* sum_bcs_dev,
+                        double* ratio_stats_dev, uint32_t* rhist_dev) {
+  const int n = p->n;
+  isr_ctx* c = p->ctx;
+  cudaStream_t st = c->stream;
+  if (!p->solver_selected) { set_error("isr_toy_campaign: no solver selected (call isr_factor first)"); return ISR_ESTATE; }
+  if (T <= 0) return ISR_OK;
+  for (int i = 0; i < n; ++i)
+    if (!(vcs_err[i] >= 0.0) || !std::isfinite(vcs_err[i]) || !std::isfinite(vcs[i])) {
+      set_error("isr_toy_campaign: vcs / vcs_err[%d] not finite or negative", i);
+      return ISR_EINVAL;
+    }
+  // chunks of 2^16 toys: the generated block (105 MB at N = 200) is consumed from L2 by the next launch
+  const int64_t chunk = std::min<int64_t>(T, 1 << 16);
+  ISR_TRY(p->d_Vh.reserve((size_t)chunk * n));
+  ISR_TRY(p->d_b0.reserve(n));
+  ISR_TRY(p->d_gen.reserve((size_t)2 * n));
+  p->h_b0.assign(bcs0, bcs0 + n);
+  p->h_gen.assign(vcs, vcs + n);
+  p->h_gen.insert(p->h_gen.end(), vcs_err, vcs_err + n);
+  ISR_CUDA(cudaMemcpyAsync(p->d_b0.p, p->h_b0.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  ISR_CUDA(cudaMemcpyAsync(p->d_gen.p, p->h_gen.data(), sizeof(double) * 2 * n, cudaMemcpyHostToDevice, st));
+  for (int64_t t0 = 0; t0 < T; t0 += chunk) {
+    const int64_t tc = std::min<int64_t>(chunk, T - t0);
+    ISR_TRY(draw_toys_device(c, tc, n, first_toy + t0, seed, p->d_gen.p, p->d_gen.p + n, p->d_Vh.p));
+    ToyOut o;
+    o.chi2 = chi2_dev ? chi2_dev + t0 : nullptr;
+    o.sum_bcs = sum_bcs_dev;
+    o.ratio_stats = ratio_stats_dev;
+    o.rhist = rhist_dev;
+    ISR_TRY(toy_batch_device(p, tc, p->d_Vh.p, p->d_b0.p, o));
+  }
+  return ISR_OK;
+}
+
 }  // namespace isr

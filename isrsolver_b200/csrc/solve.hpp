@@ -8,4 +8,9 @@ int minmax_device(isr_ctx* c, int64_t n, const double* v_dev, double* lo, double
 int histogram_device(isr_ctx* c, int64_t n, const double* v_dev, int nbins, double lo, double hi, uint32_t* counts_host);
 int toy_batch_host(isr_problem* p, int64_t T, const double* V, const double* bcs0, double* chi2_out,
                    double* sum_bcs_out, double* ratio_stats_out, uint32_t* ratio_hist_out, double* bcs_out);
+int toy_campaign_device(isr_problem* p, int64_t T, int64_t first_toy, uint64_t seed, const double* vcs,
+                        const double* vcs_err, const double* bcs0, double* chi2_dev, double* sum_bcs_dev,
+                        double* ratio_stats_dev, uint32_t* rhist_dev);
+int draw_toys_device(isr_ctx* c, int64_t T, int n, int64_t first_toy, uint64_t seed, const double* vcs_dev,
+                     const double* err_dev, double* V_dev);
 }  // namespace isr

@@ -267,6 +267,15 @@ def draw_toys(vcs, vcs_err, n: int, seed: int = TOY_SEED):
     return np.asarray(vcs)[None, :] + np.asarray(vcs_err)[None, :] * z
 
 
+def draw_toys_device(vcs, vcs_err, n: int, seed: int = TOY_SEED, first_toy: int = 0, device: int | None = None):
+    """The toys a device-side campaign uses (isr_toy_campaign): toy k of stream `seed` is
+    vcs + vcs_err * z(seed, k, .), z from Philox4x32-10 + Box-Muller (csrc/rng.cu).  Returned toy-major (n, N)."""
+    vcs, vcs_err = _f64(vcs), _f64(vcs_err, len(vcs), "vcs_err")
+    V = np.empty((int(n), len(vcs)))
+    L.check(L.load().isr_draw_toys(_ctx(device), int(n), len(vcs), int(first_toy), int(seed), L.dptr(vcs), L.dptr(vcs_err), L.dptr(V)))
+    return V
+
+
 # ---------------------------------------------------------------------------------------------------
 # solvers
 # ---------------------------------------------------------------------------------------------------
@@ -498,9 +507,35 @@ class ISRSolverSLE(BaseISRSolver):
         if want_bcs: out["bcs"] = B
         return out
 
-    def chi2_test(self, n, vcs, bcs0, vcs_err, seed=TOY_SEED, toys=None):
+    def toy_campaign(self, n, vcs, vcs_err, bcs0, seed=TOY_SEED, first_toy=0, want_chi2=True, want_sum=False,
+                     want_ratio=False, want_hist=False, want_chi2_hist=True, nbins=128):
+        """A toy campaign by count with the toys drawn on the GPU (isr_toy_campaign): nothing but the results
+        crosses PCIe.  Toy k depends only on (seed, k): shard a campaign over ranks with `first_toy`."""
+        vcs, vcs_err, bcs0 = _f64(vcs, self._n, "vcs"), _f64(vcs_err, self._n, "vcs_err"), _f64(bcs0, self._n, "bcs0")
+        self._select_for_toys()
+        n = int(n)
+        chi2 = np.empty(n) if want_chi2 else None
+        sb = np.zeros(self._n) if want_sum else None
+        rs = np.zeros(3 * self._n) if want_ratio else None
+        rh = np.zeros((self._n, 1026), dtype=np.uint32) if want_hist else None
+        lohi = np.zeros(2) if want_chi2_hist else None
+        cnt = np.zeros(nbins + 2, dtype=np.uint32) if want_chi2_hist else None
+        L.check(self._lib.isr_toy_campaign(self._p, n, int(first_toy), int(seed), L.dptr(vcs), L.dptr(vcs_err), L.dptr(bcs0),
+                                           L.dptr(chi2), L.dptr(sb), L.dptr(rs), L.uptr(rh), int(nbins), L.dptr(lohi), L.uptr(cnt)))
+        out = {}
+        if want_chi2: out["chi2"] = chi2
+        if want_sum: out["sum_bcs"] = sb
+        if want_ratio: out["ratio_stats"] = rs.reshape(self._n, 3)
+        if want_hist: out["ratio_hist"] = rh
+        if want_chi2_hist: out.update(hist=cnt.astype(np.float32), lo=float(lohi[0]), hi=float(lohi[1]))
+        return out
+
+    def chi2_test(self, n, vcs, bcs0, vcs_err, seed=TOY_SEED, toys=None, rng="host"):
         """chi2Test (src/Chi2Test.cpp:29-104) without the ROOT fit/file: returns the chi2 values and the
-        TH1F(128, min, max) counts (under/overflow included)."""
+        TH1F(128, min, max) counts (under/overflow included).  rng="host": toys from the seeded NumPy stream
+        (or `toys`), copied to the GPU; rng="device": toys drawn on the GPU (toy_campaign), no bulk transfer."""
+        if rng == "device" and toys is None:
+            return self.toy_campaign(n, vcs, vcs_err, bcs0, seed)
         V = draw_toys(vcs, vcs_err, n, seed) if toys is None else toys
         chi2 = self.toy_batch(V, bcs0)["chi2"]
         lo, hi = C.c_double(), C.c_double()
@@ -519,37 +554,45 @@ class ISRSolverSLE(BaseISRSolver):
         return v, b
 
     def chi2_test_model(self, n, initial_ampl, model_path, model_visible_cs_name, model_born_cs_name,
-                        output_path=None, seed=TOY_SEED):
+                        output_path=None, seed=TOY_SEED, rng="host"):
         """chi2TestModel (src/Chi2Test.cpp:113-151); kwargs as include/PyISRSolverSLE.hpp:125-153."""
         self.solve()
         vcs, bcs0 = self._load_model(model_path, model_visible_cs_name, model_born_cs_name)
-        res = self.chi2_test(n, vcs, bcs0, self._vcs_err, seed)
+        res = self.chi2_test(n, vcs, bcs0, self._vcs_err, seed, rng=rng)
         res["initial_ampl"] = float(initial_ampl)
         if output_path:
             np.savez(output_path, chi2Hist=res["hist"], chi2Min=res["lo"], chi2Max=res["hi"], chi2=res["chi2"])
         return res
 
-    def chi2_test_data(self, n, initial_ampl=1e4, output_path=None, seed=TOY_SEED):
+    def chi2_test_data(self, n, initial_ampl=1e4, output_path=None, seed=TOY_SEED, rng="host"):
         """chi2TestData (src/Chi2Test.cpp:160-195): reference = mean solution over n toys, then chi2Test."""
         self.solve()
         vcs = self._vcs.copy()
-        V = draw_toys(vcs, self._vcs_err, n, seed)
-        s = self.toy_batch(V, np.ones(self._n), want_chi2=False, want_sum=True)["sum_bcs"]
+        if rng == "device":
+            s = self.toy_campaign(n, vcs, self._vcs_err, np.ones(self._n), seed, want_chi2=False, want_sum=True,
+                                  want_chi2_hist=False)["sum_bcs"]
+        else:
+            V = draw_toys(vcs, self._vcs_err, n, seed)
+            s = self.toy_batch(V, np.ones(self._n), want_chi2=False, want_sum=True)["sum_bcs"]
         bcs0 = s / n
-        res = self.chi2_test(n, vcs, bcs0, self._vcs_err, seed + 1)
+        res = self.chi2_test(n, vcs, bcs0, self._vcs_err, seed + 1, rng=rng)
         res["bcs0"] = bcs0
         if output_path:
             np.savez(output_path, chi2Hist=res["hist"], chi2Min=res["lo"], chi2Max=res["hi"], chi2=res["chi2"])
         return res
 
     def ratio_test_model(self, n, model_path, model_visible_cs_name, model_born_cs_name, output_path=None,
-                         seed=TOY_SEED, toys=None):
+                         seed=TOY_SEED, toys=None, rng="host"):
         """ratioTestModel (src/RatioTest.cpp:13-62): per point TH1F(1024,-2,2) of (b - b0)/b0, GetMean and
         GetMeanError of the in-range entries."""
         self.solve()
         vcs, bcs0 = self._load_model(model_path, model_visible_cs_name, model_born_cs_name)
-        V = draw_toys(vcs, self._vcs_err, n, seed) if toys is None else toys
-        r = self.toy_batch(V, bcs0, want_chi2=False, want_ratio=True, want_hist=True)
+        if rng == "device" and toys is None:
+            r = self.toy_campaign(n, vcs, self._vcs_err, bcs0, seed, want_chi2=False, want_ratio=True, want_hist=True,
+                                  want_chi2_hist=False)
+        else:
+            V = draw_toys(vcs, self._vcs_err, n, seed) if toys is None else toys
+            r = self.toy_batch(V, bcs0, want_chi2=False, want_ratio=True, want_hist=True)
         cnt, sx, sx2 = r["ratio_stats"].T
         with np.errstate(divide="ignore", invalid="ignore"):
             mean = np.where(cnt > 0, sx / cnt, 0.0)

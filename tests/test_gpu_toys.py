@@ -176,3 +176,66 @@ def test_chi2_test_model_and_ratio_api(tmp_path, oracle):
     np.savez(model, vcsBlured=g["vcs"][:-1], bcsSRC=g["bcs0"])
     with pytest.raises(isr.DifferentModelCrossSectionSizes):
         s.chi2_test_model(8, 1e4, str(model), "vcsBlured", "bcsSRC")
+
+
+# ---- toy campaigns by count: toys drawn on the device (csrc/rng.cu) ---------------------------------------
+def test_device_toys_are_standard_normal():
+    import isrsolver_b200 as isr
+    from scipy import stats
+    n, T = 40, 1 << 15
+    z = isr.draw_toys_device(np.zeros(n), np.ones(n), T, seed=12345)
+    assert z.shape == (T, n) and np.all(np.isfinite(z))
+    m = z.size
+    assert abs(z.mean()) < 5 / np.sqrt(m) and abs(z.var() - 1) < 5 * np.sqrt(2 / m)
+    assert abs(stats.skew(z.ravel())) < 5 * np.sqrt(6 / m) and abs(stats.kurtosis(z.ravel())) < 5 * np.sqrt(24 / m)
+    assert stats.kstest(z.ravel()[:200000], "norm").pvalue > 1e-4
+    # columns and toys are uncorrelated; even / odd columns (the cos / sin branches of a pair) both normal
+    c = np.corrcoef(z[:, :8].T)
+    assert np.abs(c - np.eye(8)).max() < 5 / np.sqrt(T)
+    assert stats.kstest(z[:, 0], "norm").pvalue > 1e-4 and stats.kstest(z[:, 1], "norm").pvalue > 1e-4
+    assert np.abs(np.corrcoef(z[:-1, 0], z[1:, 0])[0, 1]) < 5 / np.sqrt(T)
+    # a different seed is a different stream; scale and shift are applied per column
+    assert not np.array_equal(z, isr.draw_toys_device(np.zeros(n), np.ones(n), T, seed=12346))
+    v = isr.draw_toys_device(np.arange(n, dtype=float), 0.5 * np.ones(n), 16, seed=12345)
+    np.testing.assert_allclose(v, np.arange(n)[None, :] + 0.5 * z[:16], rtol=0, atol=1e-15 * n)
+
+
+@pytest.mark.parametrize("n", [36, 37])
+def test_device_toys_depend_only_on_seed_and_index(n):
+    """Sharding by first_toy reproduces the unsharded stream bit for bit (odd N included)."""
+    import isrsolver_b200 as isr
+    vcs, err = np.linspace(1, 2, n), np.linspace(0.1, 0.2, n)
+    full = isr.draw_toys_device(vcs, err, 1000, seed=7)
+    parts = [isr.draw_toys_device(vcs, err, c, seed=7, first_toy=f) for f, c in ((0, 400), (400, 1), (401, 599))]
+    np.testing.assert_array_equal(full, np.concatenate(parts))
+    big = isr.draw_toys_device(vcs, err, 3, seed=7, first_toy=(1 << 33) + 5)      # 64-bit toy indices
+    assert np.all(np.isfinite(big)) and not np.array_equal(big, full[:3])
+
+
+def test_toy_campaign_equals_batch_on_the_same_toys(oracle):
+    """isr_toy_campaign (device toys) == isr_toy_batch on isr_draw_toys' vectors == the oracle on them."""
+    import isrsolver_b200 as isr
+    g = load_golden("c2_sle_n40_cspline")
+    s = make_solver(g)
+    s.set_matrix(g["G_converged"])           # the oracle's matrix: this test isolates the toy path
+    T, seed = 70000, 99                      # more than one 2^16 chunk
+    r = s.toy_campaign(T, g["vcs"], g["vcs_err"], g["bcs0"], seed, want_sum=True, want_ratio=True, want_hist=True)
+    V = isr.draw_toys_device(g["vcs"], g["vcs_err"], T, seed)
+    rb = s.toy_batch(V, g["bcs0"], want_sum=True, want_ratio=True, want_hist=True)
+    np.testing.assert_array_equal(r["chi2"], rb["chi2"])
+    np.testing.assert_allclose(r["sum_bcs"], rb["sum_bcs"], rtol=1e-12)
+    np.testing.assert_array_equal(r["ratio_hist"], rb["ratio_hist"])
+    np.testing.assert_allclose(r["ratio_stats"], rb["ratio_stats"], rtol=1e-10, atol=1e-9)
+    c2, B = oracle.chi2_test_fair(g["G_converged"], V[:4096], g["bcs0"], g["vcs_err"])
+    np.testing.assert_allclose(r["chi2"][:4096], c2, rtol=1e-8)
+    hist, idx, lo, hi = oracle.chi2_histogram(r["chi2"])
+    assert (r["lo"], r["hi"]) == (lo, hi)
+    np.testing.assert_array_equal(r["hist"], hist)
+    assert r["chi2"].mean() == pytest.approx(len(g["ecm"]), rel=0.02)
+    # sharded campaign == unsharded campaign
+    a = s.toy_campaign(30000, g["vcs"], g["vcs_err"], g["bcs0"], seed, want_chi2_hist=False)["chi2"]
+    b = s.toy_campaign(40000, g["vcs"], g["vcs_err"], g["bcs0"], seed, first_toy=30000, want_chi2_hist=False)["chi2"]
+    np.testing.assert_array_equal(np.concatenate([a, b]), r["chi2"])
+    # the reference-style entry points with rng="device"
+    d = s.chi2_test_data(4096, rng="device")
+    assert d["chi2"].shape == (4096,) and d["hist"].sum() == 4096
