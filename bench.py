@@ -30,6 +30,13 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_STDOUT_FD = 1
+
+
+def emit(line: dict):
+    os.write(_STDOUT_FD, (json.dumps(line) + "\n").encode())
+
+
 E_MIN, E_MAX, E_THR = 1.18, 2.00, 0.827
 BW_M, BW_G, BW_S0 = 1.50, 0.25, 4.0
 FP64_PEAK_TFLOPS = 37.1      # measured DMMA peak on this pool's B200 (profiles/fp64_peaks_r01.json)
@@ -114,7 +121,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": "toys/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "toys/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "assembly": asm}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def reference_assembly(n, ecm, settings, cores):
@@ -147,7 +154,8 @@ def workload_config(args, world):
                         f"{args.toys} toys per GPU, full matrix assembly + factor + toy batch + histogram per step",
             "n_points": args.n, "toys_per_gpu": args.toys, "toys_total": args.toys * world,
             "l2_policy": f"inputs larger than L2 (V = {args.toys * args.n * 8 / 2**20:.0f} MiB per GPU streams through the 126 MB L2 every step)",
-            "parallelism": f"toys sharded over {world} GPU(s), matrix replicated, one all_gather"}
+            "parallelism": f"toys sharded over {world} GPU(s), matrix replicated; per step one all_gather of (min, max, sum_bcs) "
+                           f"and one all_reduce of the 130 histogram counters"}
 
 
 # =====================================================================================================
@@ -188,8 +196,10 @@ def run_b200(args, rank, world, local_rank):
     del z
     Vh = torch.empty((T, n), dtype=torch.float64, pin_memory=True)
     Vh.copy_(Vd)
-    gathered = torch.empty((world, T + 4 * n), dtype=torch.float64, device=dev)   # packed per-rank buffer
-    mine = gathered[rank] if world == 1 else torch.empty(T + 4 * n, dtype=torch.float64, device=dev)
+    mine = torch.empty(T + 4 * n, dtype=torch.float64, device=dev)      # [chi2 | sum_bcs | ratio stats]
+    small = torch.empty(2 + n, dtype=torch.float64, device=dev)         # packed per-rank summary: min, max, sum_bcs
+    small_all = torch.empty((world, 2 + n), dtype=torch.float64, device=dev)
+    cnt_dev = torch.empty(130, dtype=torch.int64, device=dev)
     chi2_host = np.empty(T)
     sumb_host = np.zeros(n)
     counts = np.zeros(130, dtype=np.uint32)
@@ -197,6 +207,22 @@ def run_b200(args, rank, world, local_rank):
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     asm_ev, toy_ev = [], []
+
+    def combine(lo, hi, local_counts, rehist):
+        """Global TH1F over all ranks: gather (min, max), re-bin locally against the global range when it differs,
+        all_reduce the integer counters.  world == 1: nothing to do."""
+        if world == 1:
+            return local_counts.astype(np.int64)
+        small[0], small[1] = lo, hi
+        small[2:] = mine[T:T + n]                       # sum of the toy solutions rides in the same gather
+        dist.all_gather_into_tensor(small_all.view(-1), small)
+        sa = small_all.cpu()
+        glo, ghi = float(sa[:, 0].min()), float(sa[:, 1].max())
+        if (glo, ghi) != (lo, hi):
+            local_counts = rehist(glo, ghi)
+        cnt_dev.copy_(torch.from_numpy(local_counts.astype(np.int64)))
+        dist.all_reduce(cnt_dev)
+        return cnt_dev.cpu().numpy()
 
     def step_device(record):
         """One chi2 test with V resident in HBM."""
@@ -211,19 +237,24 @@ def run_b200(args, rank, world, local_rank):
             L.check(lib.isr_toy_batch_dev(prob, T, Vd.data_ptr(), L.dptr(bcs0), mine.data_ptr(),
                                           mine[T:].data_ptr(), None, None, None))
             t1.record(stream)
+            # chi2 histogram over ALL ranks' toys without moving them: local min/max -> one tiny all_gather ->
+            # global range -> local TH1F counts -> one all_reduce of the 130 integer counters.  Binning against
+            # the GLOBAL range keeps the result bit-identical to one GPU.
+            a, b = C.c_double(), C.c_double()
+            L.check(lib.isr_minmax_dev(ctx, T, mine.data_ptr(), C.byref(a), C.byref(b)))      # synchronises the stream
+            lo, hi = a.value, b.value
             if world > 1:
-                stream.synchronize()
-                dist.all_gather_into_tensor(gathered.view(-1), mine)      # the single collective
-                torch.cuda.current_stream().synchronize()
-            lo, hi = np.inf, -np.inf
-            for r in range(world):
-                a, b = C.c_double(), C.c_double()
-                L.check(lib.isr_minmax_dev(ctx, T, gathered[r].data_ptr(), C.byref(a), C.byref(b)))
-                lo, hi = min(lo, a.value), max(hi, b.value)
-            tot = np.zeros(130, dtype=np.uint64)
-            for r in range(world):
-                L.check(lib.isr_histogram_dev(ctx, T, gathered[r].data_ptr(), 128, lo, hi, L.uptr(counts)))
-                tot += counts
+                small[0], small[1] = lo, hi
+                small[2:] = mine[T:T + n]
+                dist.all_gather_into_tensor(small_all.view(-1), small)
+                sa = small_all.cpu()
+                lo, hi = float(sa[:, 0].min()), float(sa[:, 1].max())
+            L.check(lib.isr_histogram_dev(ctx, T, mine.data_ptr(), 128, lo, hi, L.uptr(counts)))
+            tot = counts.astype(np.int64)
+            if world > 1:
+                cnt_dev.copy_(torch.from_numpy(tot))
+                dist.all_reduce(cnt_dev)
+                tot = cnt_dev.cpu().numpy()
             if record:
                 asm_ev.append((a0, a1)); toy_ev.append((t0, t1))
             return tot
@@ -236,7 +267,12 @@ def run_b200(args, rank, world, local_rank):
                                   L.dptr(sumb_host), None, None, None))
         lo, hi = C.c_double(), C.c_double()
         L.check(lib.isr_chi2_histogram(ctx, T, L.dptr(chi2_host), 128, C.byref(lo), C.byref(hi), L.uptr(counts)))
-        return counts
+
+        def rehist(glo, ghi):
+            L.check(lib.isr_last_chi2_histogram(prob, 128, glo, ghi, L.uptr(counts)))
+            return counts
+        with torch.cuda.stream(stream):
+            return combine(lo.value, hi.value, counts, rehist)
 
     lohi = np.zeros(2)
 
@@ -247,7 +283,12 @@ def run_b200(args, rank, world, local_rank):
         L.check(lib.isr_factor(prob, L.dptr(err)))
         L.check(lib.isr_toy_campaign(prob, T, rank * T, 20211103, L.dptr(vcs), L.dptr(err), L.dptr(bcs0), None,
                                      L.dptr(sumb_host), None, None, 128, L.dptr(lohi), L.uptr(counts)))
-        return counts
+
+        def rehist(glo, ghi):      # chi2 stayed on the device: re-bin it against the global range there
+            L.check(lib.isr_last_chi2_histogram(prob, 128, glo, ghi, L.uptr(counts)))
+            return counts
+        with torch.cuda.stream(stream):
+            return combine(float(lohi[0]), float(lohi[1]), counts, rehist)
 
     def barrier():
         if world > 1:
@@ -283,11 +324,11 @@ def run_b200(args, rank, world, local_rank):
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
     ms_e2e = timed(lambda: step_e2e(), args.steps, record=None)
-    step_campaign()
+    hist_c = step_campaign()
     ms_rng = timed(lambda: step_campaign(), args.steps, record=None)
-    assert int(counts.sum()) == T
+    assert int(np.asarray(hist_c).sum()) == T * world
 
-    assert int(hist.sum()) == T * world, "histogram lost entries"
+    assert int(np.asarray(hist).sum()) == T * world, "histogram lost entries"
     if rank != 0:
         return
     ms_step = ms_total / args.steps
@@ -324,7 +365,7 @@ def run_b200(args, rank, world, local_rank):
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(n, G, bcs0, vcs, err)
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline(n, G, bcs0, vcs, err):
@@ -358,11 +399,18 @@ def main():
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout must carry exactly ONE JSON line: libraries that print there (NCCL's version banner does) are sent to
+    # stderr for the whole run, and the line is written to the saved descriptor at the end
+    global _STDOUT_FD
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)

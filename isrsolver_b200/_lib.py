@@ -75,6 +75,8 @@ SIGNATURES = {
     "isr_set_toy_kernel": (C.c_int, [_vp, C.c_int]),
     "isr_minmax_dev": (C.c_int, [_vp, _i64, _vp, _dp, _dp]),
     "isr_histogram_dev": (C.c_int, [_vp, _i64, _vp, C.c_int, C.c_double, C.c_double, _up]),
+    "isr_last_chi2_histogram": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, _up]),
+    "isr_histogram": (C.c_int, [_vp, _i64, _dp, C.c_int, C.c_double, C.c_double, _up]),
     "isr_chi2_histogram": (C.c_int, [_vp, _i64, _dp, C.c_int, _dp, _dp, _up]),
     "isr_tikhonov_prepare": (C.c_int, [_vp, _dp, C.c_int]),
     "isr_tikhonov_scan": (C.c_int, [_vp, _i64, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),

@@ -459,6 +459,7 @@ int isr_toy_campaign(isr_problem* p, int64_t T, int64_t first_toy, uint64_t seed
     ISR_TRY(p->d_rhist.reserve((size_t)n * 1026));
     ISR_CUDA(cudaMemsetAsync(p->d_rhist.p, 0, sizeof(uint32_t) * (size_t)n * 1026, st));
   }
+  p->last_chi2_count = want_chi2 ? T : 0;
   ISR_TRY(toy_campaign_device(p, T, first_toy, seed, vcs, vcs_err, bcs0, want_chi2 ? p->d_chi2h.p : nullptr,
                               sum_bcs_out ? p->d_stat.p : nullptr, ratio_stats_out ? p->d_stat.p + n : nullptr,
                               ratio_hist_out ? p->d_rhist.p : nullptr));
@@ -476,6 +477,15 @@ int isr_toy_campaign(isr_problem* p, int64_t T, int64_t first_toy, uint64_t seed
   return ISR_OK;
 }
 
+// TH1F(nbins, lo, hi) of the chi2 values the LAST isr_toy_campaign / isr_toy_batch (host API) of this problem left
+// on the device -- the multi-GPU re-binning against the global range, without moving chi2.
+int isr_last_chi2_histogram(isr_problem* p, int nbins, double lo, double hi, uint32_t* counts_out) {
+  if (!p || !counts_out) { set_error("NULL argument"); return ISR_EINVAL; }
+  if (p->last_chi2_count <= 0 || !p->d_chi2h.p) { set_error("isr_last_chi2_histogram: no chi2 values on the device"); return ISR_ESTATE; }
+  ISR_CUDA(cudaSetDevice(p->ctx->device));
+  return histogram_device(p->ctx, p->last_chi2_count, p->d_chi2h.p, nbins, lo, hi, counts_out);
+}
+
 int isr_minmax_dev(isr_ctx* ctx, int64_t n, const double* v_dev, double* min_out, double* max_out) {
   if (!ctx || !v_dev || !min_out || !max_out) { set_error("NULL argument"); return ISR_EINVAL; }
   ISR_CUDA(cudaSetDevice(ctx->device));
@@ -486,6 +496,15 @@ int isr_histogram_dev(isr_ctx* ctx, int64_t n, const double* v_dev, int nbins, d
   if (!ctx || (n > 0 && !v_dev) || !counts_out) { set_error("NULL argument"); return ISR_EINVAL; }
   ISR_CUDA(cudaSetDevice(ctx->device));
   return histogram_device(ctx, n, v_dev, nbins, lo, hi, counts_out);
+}
+
+int isr_histogram(isr_ctx* ctx, int64_t n, const double* v, int nbins, double lo, double hi, uint32_t* counts_out) {
+  if (!ctx || (n > 0 && !v) || !counts_out) { set_error("NULL argument"); return ISR_EINVAL; }
+  ISR_CUDA(cudaSetDevice(ctx->device));
+  DevBuf<double>& d = ctx->scratch_v;
+  ISR_TRY(d.reserve(n > 0 ? n : 1));
+  if (n > 0) ISR_CUDA(cudaMemcpyAsync(d.p, v, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  return histogram_device(ctx, n, d.p, nbins, lo, hi, counts_out);
 }
 
 int isr_chi2_histogram(isr_ctx* ctx, int64_t n, const double* chi2, int nbins, double* lo_out, double* hi_out, uint32_t* counts_out) {

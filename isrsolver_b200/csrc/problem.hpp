@@ -49,6 +49,7 @@ struct isr_problem {
   bool factored = false;
   bool solver_selected = false;
   int toy_variant = 0;
+  int64_t last_chi2_count = 0;   // chi2 values the last host-API batch / campaign left in d_chi2h
 
   // ---- toy batch workspaces ------------------------------------------------------------------
   isr::DevBuf<double> d_V, d_chi2, d_acc, d_b0, d_B;

@@ -187,6 +187,7 @@ int toy_batch_host(isr_problem* p, int64_t T, const double* V, const double* bcs
       ISR_CUDA(cudaMemcpyAsync(bcs_out + t0 * n, o.bcs, sizeof(double) * tc * n, cudaMemcpyDeviceToHost, st));
     ISR_CUDA(cudaEventRecord(p->ev_done[q], st));
   }
+  p->last_chi2_count = chi2_out ? T : 0;
   if (chi2_out) ISR_CUDA(cudaMemcpyAsync(chi2_out, p->d_chi2h.p, sizeof(double) * T, cudaMemcpyDeviceToHost, st));
   if (sum_bcs_out) ISR_CUDA(cudaMemcpyAsync(sum_bcs_out, p->d_stat.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
   if (ratio_stats_out)

@@ -7,6 +7,11 @@ grid).  The single exchange step is ONE all_gather of a packed per-rank buffer
 after which every rank holds all chi2 values and computes the TH1F(128, min, max) histogram exactly as
 src/Chi2Test.cpp:64-78 does on one process -- the histogram range depends on the GLOBAL min/max, so
 binning must happen after the gather to stay bit-identical with the single-GPU result.
+
+When only the HISTOGRAM is wanted (the chi2 test itself), the chi2 values need not move at all
+(`histogram_sharded`): one all_gather of the packed per-rank summary [min, max | sum_bcs | ratio stats], local
+TH1F counts against the global range, one all_reduce of the integer counters -- what bench.py does per step.
+Device-drawn campaigns (isr_toy_campaign) shard by `first_toy`; lambda grids shard by slicing the grid.
 """
 from __future__ import annotations
 
@@ -56,6 +61,39 @@ def all_gather_results(chi2, sum_bcs, ratio_stats, total: int, device=None):
     out = torch.empty(world * mine.numel(), dtype=torch.float64, device=mine.device)
     dist.all_gather_into_tensor(out, mine)       # the single collective
     return unpack(out.view(world, mine.numel()).cpu().numpy(), total, world, n)
+
+
+def histogram_sharded(chi2_local, sum_bcs, ratio_stats, nbins: int = 128, count_fn=None, device=None):
+    """The chi2 test over all ranks' toys without gathering them.
+
+    Returns (counts[nbins + 2] int64 summed over ranks, lo, hi, sum_bcs, ratio_stats): bit-identical to the
+    single-process TH1F(nbins, min, max) of the concatenated values because every rank bins against the GLOBAL
+    range and integer counters add exactly.  count_fn(lo, hi) -> counts lets the caller bin on the GPU
+    (isr_histogram_dev); the default bins `chi2_local` on the host.  Two collectives, both O(N) bytes."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size()
+    chi2_local = np.asarray(chi2_local, dtype=np.float64)
+    n = len(sum_bcs)
+    lo = chi2_local.min() if chi2_local.size else np.inf
+    hi = chi2_local.max() if chi2_local.size else -np.inf
+    mine = torch.from_numpy(np.concatenate([[lo, hi], np.asarray(sum_bcs, dtype=np.float64),
+                                            np.asarray(ratio_stats, dtype=np.float64).reshape(-1)]))
+    if device is not None:
+        mine = mine.to(device)
+    allr = torch.empty(world * mine.numel(), dtype=torch.float64, device=mine.device)
+    dist.all_gather_into_tensor(allr, mine)                       # collective 1: per-rank summaries
+    a = allr.view(world, -1).cpu().numpy()
+    glo, ghi = float(a[:, 0].min()), float(a[:, 1].max())
+    sb = a[:, 2:2 + n].sum(0)                                     # fixed rank order => deterministic
+    rs = a[:, 2 + n:].sum(0).reshape(n, 3)
+    counts = count_fn(glo, ghi) if count_fn else th1_counts(chi2_local, nbins, glo, ghi)
+    c = torch.from_numpy(np.asarray(counts).astype(np.int64))
+    if device is not None:
+        c = c.to(device)
+    dist.all_reduce(c)                                            # collective 2: integer counters
+    return c.cpu().numpy(), glo, ghi, sb, rs
 
 
 def th1_counts(values, nbins: int, lo: float, hi: float):

@@ -117,7 +117,7 @@ def test_th1_counts_matches_oracle(oracle):
 _GLOO_WORKER = r"""
 import os, sys, numpy as np, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
-from isrsolver_b200.dist import all_gather_results, shard_bounds, th1_counts
+from isrsolver_b200.dist import all_gather_results, histogram_sharded, shard_bounds, th1_counts
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 total, n = 1001, 7
@@ -130,6 +130,10 @@ assert np.array_equal(chi2, chi2_all)
 assert np.allclose(sb, B.sum(0), rtol=1e-13) and np.allclose(rs[:, 0], total) and np.allclose(rs[:, 2], (B ** 2).sum(0), rtol=1e-13)
 h = th1_counts(chi2, 128, chi2.min(), chi2.max())
 assert np.array_equal(h, th1_counts(chi2_all, 128, chi2_all.min(), chi2_all.max()))   # bit-identical with 1 process
+# the histogram-only path: no chi2 movement, two O(N)-byte collectives, same counters bit for bit
+cnt, lo, hi, sb2, rs2 = histogram_sharded(chi2_all[b:e], B[b:e].sum(0), stats)
+assert (lo, hi) == (chi2_all.min(), chi2_all.max()) and np.array_equal(cnt, h.astype(np.int64))
+assert np.allclose(sb2, B.sum(0), rtol=1e-13) and np.allclose(rs2, rs, rtol=1e-13)
 dist.destroy_process_group()
 print("rank", rank, "ok")
 """
