@@ -530,6 +530,33 @@ class ISRSolverSLE(BaseISRSolver):
         if want_chi2_hist: out.update(hist=cnt.astype(np.float32), lo=float(lohi[0]), hi=float(lohi[1]))
         return out
 
+    def chi2_test_sharded(self, n, vcs, bcs0, vcs_err, seed=TOY_SEED, nbins=128):
+        """chi2Test over `n` toys sharded across the ranks of an initialised torch.distributed group (one
+        process per GPU): rank r draws and processes toys [begin_r, end_r) of the device stream `seed`
+        (toy k depends only on (seed, k)), then the TH1F(nbins, min, max) is combined with two O(N)-byte
+        collectives (dist.histogram_sharded) -- chi2 never leaves the GPUs.  Every rank returns the same
+        result, bit-identical to toy_campaign(n) on one GPU."""
+        import torch.distributed as td
+        from . import dist as D
+        rank, world = td.get_rank(), td.get_world_size()
+        b, e = D.shard_bounds(int(n), world, rank)
+        r = self.toy_campaign(e - b, vcs, vcs_err, bcs0, seed, first_toy=b, want_chi2=False, want_sum=True,
+                              want_ratio=True, want_chi2_hist=True, nbins=nbins)
+        counts = np.zeros(nbins + 2, dtype=np.uint32)
+
+        def rebin(lo, hi):
+            L.check(self._lib.isr_last_chi2_histogram(self._p, int(nbins), lo, hi, L.uptr(counts)))
+            return counts
+        dev = None
+        if td.get_backend() == "nccl":
+            import torch
+            dev = torch.device("cuda", torch.cuda.current_device())
+        lo = r["lo"] if e > b else np.inf
+        hi = r["hi"] if e > b else -np.inf
+        cnt, glo, ghi, sb, rs = D.histogram_sharded(np.array([lo, hi]), r["sum_bcs"], r["ratio_stats"], nbins,
+                                                    count_fn=rebin if e > b else (lambda lo, hi: counts), device=dev)
+        return {"hist": cnt.astype(np.float32), "lo": glo, "hi": ghi, "sum_bcs": sb, "ratio_stats": rs, "n": int(n)}
+
     def chi2_test(self, n, vcs, bcs0, vcs_err, seed=TOY_SEED, toys=None, rng="host"):
         """chi2Test (src/Chi2Test.cpp:29-104) without the ROOT fit/file: returns the chi2 values and the
         TH1F(128, min, max) counts (under/overflow included).  rng="host": toys from the seeded NumPy stream

@@ -239,3 +239,43 @@ def test_toy_campaign_equals_batch_on_the_same_toys(oracle):
     # the reference-style entry points with rng="device"
     d = s.chi2_test_data(4096, rng="device")
     assert d["chi2"].shape == (4096,) and d["hist"].sum() == 4096
+
+
+_SHARDED_WORKER = r"""
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+os.environ["LOCAL_RANK"] = str(int(os.environ["LOCAL_RANK"]) % torch.cuda.device_count())   # ranks may share a GPU here
+import isrsolver_b200 as isr
+dist.init_process_group("gloo")
+g = np.load(sys.argv[2])
+n = len(g["ecm"])
+s = isr.ISRSolverSLE(n, g["ecm"], g["vcs"], None, g["vcs_err"], 0.827)
+s.set_interp_settings([tuple(r) for r in g["settings"]])
+T = 100003
+r = s.chi2_test_sharded(T, g["vcs"], g["bcs0"], g["vcs_err"], seed=5)
+one = s.toy_campaign(T, g["vcs"], g["vcs_err"], g["bcs0"], seed=5, want_sum=True, want_ratio=True)
+assert (r["lo"], r["hi"]) == (one["lo"], one["hi"]), (r["lo"], r["hi"], one["lo"], one["hi"])
+assert np.array_equal(r["hist"], one["hist"]) and r["hist"].sum() == T
+assert np.allclose(r["sum_bcs"], one["sum_bcs"], rtol=1e-11) and np.allclose(r["ratio_stats"], one["ratio_stats"], rtol=1e-9, atol=1e-9)
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_chi2_test_equals_single_gpu(tmp_path, world):
+    """(e) multi-GPU on real kernels: `world` ranks (gloo for the two small collectives; the ranks share the
+    GPUs that exist) shard a device-drawn campaign; histogram bit-identical to the unsharded campaign."""
+    import os
+    import subprocess
+    import sys
+    from conftest import GOLDEN, ROOT
+    w = tmp_path / "worker.py"
+    w.write_text(_SHARDED_WORKER)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                          "--master-addr", "127.0.0.1", "--master-port", str(29640 + world), str(w), ROOT,
+                          os.path.join(GOLDEN, "c2_sle_n40_cspline.npz")],
+                         env=dict(os.environ, MASTER_ADDR="127.0.0.1"), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count("ok") == world
