@@ -778,6 +778,35 @@ class ISRSolverTikhonov(ISRSolverSLE):
         return {"min": stats[:, 0].copy(), "max": stats[:, 1].copy(), "mean": stats[:, 2].copy(),
                 "hist": counts.astype(np.float32)}
 
+    def toy_scan_hist_sharded(self, lambdas, V, bcs0, nbins=128):
+        """BASELINE config C4: the lambda grid sharded over the ranks of an initialised torch.distributed group
+        (lambdas are independent given the eigen-system, src/isrsolver-LCurve-plot.cpp:131-151); every rank
+        scans its contiguous slice against all toys and ONE all_gather of the per-lambda summaries
+        [min, max, mean, TH1F cells] follows.  Every rank returns the full grid."""
+        import torch
+        import torch.distributed as td
+        from . import dist as D
+        lam = _f64(np.atleast_1d(lambdas))
+        rank, world = td.get_rank(), td.get_world_size()
+        b, e = D.shard_bounds(lam.size, world, rank)
+        width = 3 + nbins + 2
+        per = max(D.shard_bounds(lam.size, world, r)[1] - D.shard_bounds(lam.size, world, r)[0] for r in range(world))
+        mine = np.zeros((per, width))
+        if e > b:
+            r = self.toy_scan_hist(lam[b:e], V, bcs0, nbins)
+            mine[: e - b, 0], mine[: e - b, 1], mine[: e - b, 2] = r["min"], r["max"], r["mean"]
+            mine[: e - b, 3:] = r["hist"]          # integer counts < 2^53: exact in float64
+        t = torch.from_numpy(mine)
+        if td.get_backend() == "nccl":
+            t = t.to(torch.device("cuda", torch.cuda.current_device()))
+        out = torch.empty((world,) + tuple(t.shape), dtype=torch.float64, device=t.device)
+        td.all_gather_into_tensor(out.view(-1), t.view(-1))        # the single collective
+        out = out.cpu().numpy()
+        rows = [out[r, : D.shard_bounds(lam.size, world, r)[1] - D.shard_bounds(lam.size, world, r)[0]] for r in range(world)]
+        full = np.concatenate(rows)
+        return {"min": full[:, 0].copy(), "max": full[:, 1].copy(), "mean": full[:, 2].copy(),
+                "hist": full[:, 3:].astype(np.float32)}
+
     def regulariser(self):
         self._ensure_tik()
         F = np.empty((self._n, self._n))

@@ -161,3 +161,40 @@ def test_tsvd(oracle):
     U, S, Vt = np.linalg.svd(g["G_spread"])
     Kp = Vt[:k].T @ np.diag(1 / S[:k]) @ U[:, :k].T
     np.testing.assert_allclose(r["bcs"], g["toys"][:16] @ Kp.T, rtol=1e-8, atol=1e-8 * np.abs(g["bcs0"]).max())
+
+
+_LAMBDA_WORKER = r"""
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+rank = int(os.environ["RANK"])
+os.environ["LOCAL_RANK"] = str(int(os.environ["LOCAL_RANK"]) % torch.cuda.device_count())
+import isrsolver_b200 as isr
+dist.init_process_group("gloo")
+g = np.load(sys.argv[2])
+n = len(g["ecm"])
+s = isr.ISRSolverTikhonov(n, g["ecm"], g["vcs"], g["ecm_err"], g["vcs_err"], 0.827, enableEnergySpread=True)
+s.set_interp_settings([tuple(r) for r in g["settings"]])
+lam = np.geomspace(1e-8, 1.0, 37)
+r = s.toy_scan_hist_sharded(lam, g["toys"], g["bcs0"])
+one = s.toy_scan_hist(lam, g["toys"], g["bcs0"])
+for k in ("min", "max", "mean", "hist"):
+    assert np.array_equal(r[k], one[k]), k
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_lambda_sharded_scan_equals_single_gpu(tmp_path):
+    """C4's lambda sharding on real kernels: 3 ranks, 37 lambdas (ragged slices), one all_gather."""
+    import os
+    import subprocess
+    import sys
+    from conftest import GOLDEN, ROOT
+    w = tmp_path / "worker.py"
+    w.write_text(_LAMBDA_WORKER)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=3",
+                          "--master-addr", "127.0.0.1", "--master-port", "29653", str(w), ROOT,
+                          os.path.join(GOLDEN, "c4_tikhonov_n32_spread.npz")],
+                         env=dict(os.environ, MASTER_ADDR="127.0.0.1"), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count("ok") == 3
