@@ -1,0 +1,121 @@
+"""Edge cases of the hot path on the B200: minimal and large N, energies hugging the threshold (x_max below the
+pair threshold x0), very unequal spacing, tiny and huge toy counts relative to the tile, odd N in every kernel."""
+import numpy as np
+import pytest
+
+from conftest import assert_matrix_parity
+
+pytestmark = pytest.mark.gpu
+THR = 0.827
+
+
+def _solver(ecm, settings=None, cls=None, **kw):
+    import isrsolver_b200 as isr
+    n = len(ecm)
+    s = (cls or isr.ISRSolverSLE)(n, ecm, np.ones(n), None, np.ones(n), THR, **kw)
+    if settings:
+        s.set_interp_settings(settings)
+    return s
+
+
+@pytest.mark.parametrize("n", [2, 3, 5])
+def test_minimal_sizes(oracle, n):
+    ecm = np.linspace(1.0, 1.3, n)
+    for st in (None, [(True, 0, n - 1)]):
+        s = _solver(ecm, st)
+        s.eval_equation_matrix()
+        Gc, Ec, _ = oracle.Interp(ecm, THR, st).eval_eq_matrix(mode="converged", with_errors=True)
+        assert_matrix_parity(s.intop_matrix(), Gc, Ec, what=f"N={n} {st}")
+        b0 = np.linspace(1.0, 2.0, n); vcs = Gc @ b0; err = 0.05 * vcs
+        s.resetVisibleCS(vcs); s.resetVisibleCSErrors(err)
+        s.solve()
+        np.testing.assert_allclose(s.bcs(), np.linalg.solve(s.intop_matrix(), vcs), rtol=1e-10)
+        V = oracle.draw_toys(vcs, err, 33)
+        c2, B = oracle.chi2_test_fair(s.intop_matrix(), V, b0, err)
+        r = s.toy_batch(V, b0, want_bcs=True)
+        np.testing.assert_allclose(r["chi2"], c2, rtol=1e-8)
+        np.testing.assert_allclose(r["bcs"], B, rtol=1e-8, atol=1e-12)
+
+
+def test_energies_hugging_the_threshold(oracle):
+    """x_max = 1 - (thr/E)^2 far below the pair threshold x0 = 4 m_e / E for the first points: only the
+    t = x^beta panels exist there; the matrix must still match the adaptive oracle."""
+    ecm = THR + np.array([1e-7, 1e-5, 5e-4, 2e-3, 0.05, 0.4])
+    for st in (None, [(False, 0, 1), (True, 2, 5)]):
+        s = _solver(ecm, st)
+        s.eval_equation_matrix()
+        Gc, Ec, _ = oracle.Interp(ecm, THR, st).eval_eq_matrix(mode="converged", with_errors=True)
+        assert_matrix_parity(s.intop_matrix(), Gc, Ec, what=f"threshold-hugging {st}")
+        assert np.all(np.isfinite(s.intop_matrix())) and np.all(np.diag(s.intop_matrix()) > 0)
+
+
+def test_very_unequal_spacing_and_high_energy(oracle):
+    rng = np.random.default_rng(17)
+    ecm = np.sort(np.concatenate([THR + 10.0 ** rng.uniform(-4, 0.5, 20), [10.58, 91.2]]))
+    st = [(False, 0, 4), (True, 5, len(ecm) - 1)]
+    s = _solver(ecm, st)
+    s.eval_equation_matrix()
+    Gc, Ec, _ = oracle.Interp(ecm, THR, st).eval_eq_matrix(mode="converged", with_errors=True)
+    assert_matrix_parity(s.intop_matrix(), Gc, Ec, rel=1e-9, what="unequal spacing up to 91 GeV")
+
+
+@pytest.mark.parametrize("n", [999, 1000])
+def test_large_n_rows_and_toys(oracle, n):
+    """N = 1000 (5x the headline size; odd N exercises the padded leading dimension): sampled rows against the
+    oracle, toys against NumPy."""
+    ecm = np.linspace(1.0, 3.0, n)
+    s = _solver(ecm)
+    s.eval_equation_matrix()
+    G = s.intop_matrix()
+    rows = [0, 1, n // 2, n - 1]
+    Gc, Ec = oracle.Interp(ecm, THR).eval_rows(rows, mode="converged")
+    assert_matrix_parity(G[rows], Gc, Ec, what=f"N={n} rows")
+    assert np.all(np.triu(G, 1) == 0)
+    b0 = 1.0 + np.sin(ecm); vcs = G @ b0; err = 0.03 * vcs
+    s.resetVisibleCS(vcs); s.resetVisibleCSErrors(err)
+    V = oracle.draw_toys(vcs, err, 777)
+    r = s.toy_batch(V, b0, want_sum=True, want_bcs=True)
+    B = np.linalg.solve(G, V.T).T
+    np.testing.assert_allclose(r["bcs"], B, rtol=1e-8, atol=1e-9 * np.abs(B).max())
+    z = (V - vcs) / err
+    np.testing.assert_allclose(r["chi2"], (z * z).sum(1), rtol=1e-8)
+    np.testing.assert_allclose(r["sum_bcs"], B.sum(0), rtol=1e-8, atol=1e-8 * np.abs(B.sum(0)).max())
+
+
+@pytest.mark.parametrize("T", [1, 7, 63, 64, 65, 148 * 64 - 1, 148 * 64 + 1])
+def test_toy_counts_around_the_tile_and_grid(oracle, T):
+    """T below one tile, exactly one tile, one more than a tile, and around one full wave of 148 CTAs."""
+    n = 31
+    ecm = np.linspace(1.0, 2.0, n)
+    s = _solver(ecm, [(False, 0, 0), (True, 1, n - 1)])
+    s.eval_equation_matrix()
+    G = s.intop_matrix()
+    b0 = oracle.bw_born(ecm); vcs = G @ b0; err = 0.05 * vcs
+    s.resetVisibleCS(vcs); s.resetVisibleCSErrors(err)
+    V = oracle.draw_toys(vcs, err, T)
+    r = s.toy_batch(V, b0, want_sum=True, want_ratio=True)
+    c2, B = oracle.chi2_test_fair(G, V, b0, err)
+    np.testing.assert_allclose(r["chi2"], c2, rtol=1e-8)
+    np.testing.assert_allclose(r["sum_bcs"], B.sum(0), rtol=1e-8)
+    assert r["ratio_stats"][:, 0].max() <= T
+
+
+def test_tikhonov_and_tsvd_minimal_and_odd(oracle):
+    import isrsolver_b200 as isr
+    for n in (3, 17):
+        ecm = np.linspace(1.0, 2.0, n)
+        I = oracle.Interp(ecm, THR)
+        G = I.eval_eq_matrix(mode="converged")
+        b0 = oracle.bw_born(ecm); vcs = G @ b0; err = 0.05 * vcs
+        t = isr.ISRSolverTikhonov(n, ecm, vcs, None, err, THR)
+        F = oracle.tikhonov_F(I.deriv_projector(), I.integral_basis(), True)
+        for lam in (1e-6, 1e-2):
+            ref = oracle.tikhonov_lcurve(G, vcs, err, F, lam)
+            t.reg_param = lam
+            t.solve()
+            np.testing.assert_allclose(t.bcs(), ref["bcs"], rtol=1e-7, atol=1e-9 * np.abs(ref["bcs"]).max())
+        V = oracle.draw_toys(vcs, err, 50)
+        assert t.toy_scan([1e-4, 1e-1], V, b0).shape == (2, 50)
+        v = isr.ISRSolverTSVD(n, ecm, vcs, None, err, THR, upper_TSVD_index=max(1, n - 1))
+        v.solve()
+        np.testing.assert_allclose(v.bcs(), oracle.tsvd_solve(G, vcs, err, max(1, n - 1))[0], rtol=1e-6, atol=1e-9)
