@@ -7,7 +7,8 @@ PINNING.  The assembly layer (isr_oracle.c) reproduces the reference's own compi
 (oracle/_ref, oracle/isr_ref.py, tests/test_ref_pin.py).  The linear-algebra layer in THIS file (solve,
 covariance, toy loops, Tikhonov, TSVD) remains PARITY UNPINNED BY THE REFERENCE: those reference files need
 Eigen's decompositions and ROOT, which are absent, and the reference ships no golden vectors (SURVEY.md
-F3, F5); it is pinned against LAPACK identities and the literal matrix formulas instead
+F3, F5); it is pinned instead against the same formulas evaluated in 60-digit mpmath arithmetic
+(test_linear_algebra_layer_against_exact_arithmetic), LAPACK identities and the eigen-form identities
 (tests/test_oracle.py).
 
 Two layers:

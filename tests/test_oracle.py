@@ -262,3 +262,69 @@ def test_histogram_semantics(oracle):
 def test_sort_points(oracle):
     e = np.array([1.5, 1.2, 1.9]); idx, es, vs, ee, ve = oracle.sort_points(e, [1, 2, 3], None, [4, 5, 6])
     assert list(idx) == [1, 0, 2] and list(vs) == [2, 1, 3] and ee is None and list(ve) == [5, 4, 6]
+
+
+def test_linear_algebra_layer_against_exact_arithmetic(oracle):
+    """The linear-algebra layer of the oracle (NumPy/LAPACK in place of Eigen -- the part of the reference that
+    cannot be compiled here) against the SAME formulas evaluated in 60-digit mpmath arithmetic: solve and
+    covariance (src/ISRSolverSLE.cpp:91-94), per-toy chi2 (src/Chi2Test.cpp:51-55), the Tikhonov matrices,
+    solution, covariance and L-curve functionals (src/ISRSolverTikhonov.cpp:61-72, 106-128, 139-155) and the TSVD
+    solution (src/ISRSolverTSVD.cpp:63-73)."""
+    import mpmath as mp
+    O = oracle
+    mp.mp.dps = 60
+    n = 10
+    ecm = np.linspace(O.E_MIN, O.E_MAX, n)
+    I = O.Interp(ecm, O.E_THR, [(False, 0, 0), (True, 1, n - 1)])
+    G = I.eval_eq_matrix(mode="converged")
+    b0 = O.bw_born(ecm); vcs = G @ b0; err = 0.05 * vcs
+    V = O.draw_toys(vcs, err, 4)
+    mG, mW = mp.matrix(G.tolist()), mp.diag([mp.mpf(float(e)) ** -2 for e in err])
+    f = lambda M: np.array(M.tolist(), dtype=float).reshape(M.rows, M.cols)
+    # --- SLE
+    mb = mp.lu_solve(mG, mp.matrix(vcs.tolist()))
+    mCovInv = mG.T * mW * mG
+    mCov = mp.inverse(mCovInv)
+    b, cov = O.sle_solve(G, vcs, err)
+    np.testing.assert_allclose(b, f(mb).ravel(), rtol=1e-11)
+    np.testing.assert_allclose(cov, f(mCov), rtol=1e-9, atol=1e-12 * np.abs(cov).max())
+    c2_loop, _ = O.chi2_test_loop(G, V, b0, err)
+    c2_fair, _ = O.chi2_test_fair(G, V, b0, err)
+    for k in range(len(V)):
+        d = mp.lu_solve(mG, mp.matrix(V[k].tolist())) - mp.matrix(b0.tolist())
+        exact = float((d.T * mCovInv * d)[0])
+        assert c2_loop[k] == pytest.approx(exact, rel=1e-9) and c2_fair[k] == pytest.approx(exact, rel=1e-11)
+    # --- Tikhonov
+    D, w = I.deriv_projector(), I.integral_basis()
+    F = O.tikhonov_F(D, w, True)
+    mF = mp.matrix(D.tolist()).T * mp.diag([mp.mpf(float(x)) for x in w]) * mp.matrix(D.tolist())
+    np.testing.assert_allclose(F, f(mF), rtol=1e-12, atol=1e-13 * np.abs(F).max())
+    lam = mp.mpf("1e-3")
+    mT = mCovInv + lam * mF
+    mL = mp.inverse(mF) * mCovInv + lam * mp.eye(n)
+    mAp = mp.inverse(mT) * mG.T * mW      # A+ = T^-1 G^T W
+    mbt = mAp * mp.matrix(vcs.tolist())
+    mCt = mAp * mp.inverse(mW) * mAp.T
+    dv = mG * mbt - mp.matrix(vcs.tolist())
+    x, y = (dv.T * mW * dv)[0], (mbt.T * mF * mbt)[0]
+    ds = -mp.lu_solve(mL, mbt)
+    d2s = -2 * mp.lu_solve(mL, ds)
+    dksi = 2 * (mbt.T * mF * ds)[0]
+    d2ksi = 2 * (ds.T * mF * ds)[0] + 2 * (mbt.T * mF * d2s)[0]
+    curv = -abs(1 / dksi / (1 + lam * lam) ** mp.mpf("1.5"))
+    dcurv = -d2ksi / dksi ** 2 * (1 + lam * lam) ** mp.mpf("-1.5") - 3 * lam / dksi * (1 + lam * lam) ** mp.mpf("-2.5")
+    r = O.tikhonov_lcurve(G, vcs, err, F, 1e-3)
+    np.testing.assert_allclose(r["bcs"], f(mbt).ravel(), rtol=1e-8)
+    np.testing.assert_allclose(r["cov"], f(mCt), rtol=1e-7, atol=1e-10 * np.abs(r["cov"]).max())
+    for got, exact, tol in ((r["x"], x, 1e-7), (r["y"], y, 1e-8), (r["curv"], curv, 1e-7), (r["dcurv"], dcurv, 1e-6)):
+        assert got == pytest.approx(float(exact), rel=tol)
+    # --- TSVD (k = n - 2): minimum-norm least squares through the exact SVD
+    U, S, Vt = mp.svd_r(mG)
+    k = n - 2
+    z = U.T * mp.matrix(vcs.tolist())
+    bt = mp.matrix(n, 1)
+    for m in range(k):
+        for i in range(n):
+            bt[i] += Vt[m, i] * z[m] / S[m]
+    np.testing.assert_allclose(O.tsvd_solve(G, vcs, err, k)[0], f(bt).ravel(), rtol=1e-8, atol=1e-10)
+    mp.mp.dps = 15
