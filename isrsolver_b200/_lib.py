@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libisr_b200.so")
+LIB_PATH = os.environ.get("ISR_B200_LIB") or os.path.join(_HERE, "libisr_b200.so")   # override: kernel experiments only
 
 ISR_OK, ISR_EINVAL, ISR_ERANGE, ISR_ECUDA, ISR_ESTATE, ISR_ENUMERIC, ISR_EEFFDIM = range(7)
 
