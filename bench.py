@@ -209,20 +209,26 @@ def run_b200(args, rank, world, local_rank):
     asm_ev, toy_ev = [], []
 
     def combine(lo, hi, local_counts, rehist):
-        """Global TH1F over all ranks: gather (min, max), re-bin locally against the global range when it differs,
-        all_reduce the integer counters.  world == 1: nothing to do."""
-        if world == 1:
-            return local_counts.astype(np.int64)
-        small[0], small[1] = lo, hi
-        small[2:] = mine[T:T + n]                       # sum of the toy solutions rides in the same gather
-        dist.all_gather_into_tensor(small_all.view(-1), small)
-        sa = small_all.cpu()
-        glo, ghi = float(sa[:, 0].min()), float(sa[:, 1].max())
-        if (glo, ghi) != (lo, hi):
-            local_counts = rehist(glo, ghi)
-        cnt_dev.copy_(torch.from_numpy(local_counts.astype(np.int64)))
-        dist.all_reduce(cnt_dev)
-        return cnt_dev.cpu().numpy()
+        """Global TH1F over all ranks: gather (min, max | sum_bcs), bin locally against the GLOBAL range (keeps the
+        result bit-identical to one GPU), all_reduce the integer counters.  local_counts: counters already binned
+        against (lo, hi), or None; rehist(lo, hi) bins this rank's chi2 (which stays on the device)."""
+        if world > 1:
+            small[0], small[1] = lo, hi
+            small[2:] = mine[T:T + n]                   # sum of the toy solutions rides in the same gather
+            dist.all_gather_into_tensor(small_all.view(-1), small)
+            sa = small_all.cpu()
+            glo, ghi = float(sa[:, 0].min()), float(sa[:, 1].max())
+            if (glo, ghi) != (lo, hi):
+                local_counts = None
+            lo, hi = glo, ghi
+        if local_counts is None:
+            local_counts = rehist(lo, hi)
+        tot = local_counts.astype(np.int64)
+        if world > 1:
+            cnt_dev.copy_(torch.from_numpy(tot))
+            dist.all_reduce(cnt_dev)
+            tot = cnt_dev.cpu().numpy()
+        return tot
 
     def step_device(record):
         """One chi2 test with V resident in HBM."""
@@ -237,24 +243,15 @@ def run_b200(args, rank, world, local_rank):
             L.check(lib.isr_toy_batch_dev(prob, T, Vd.data_ptr(), L.dptr(bcs0), mine.data_ptr(),
                                           mine[T:].data_ptr(), None, None, None))
             t1.record(stream)
-            # chi2 histogram over ALL ranks' toys without moving them: local min/max -> one tiny all_gather ->
-            # global range -> local TH1F counts -> one all_reduce of the 130 integer counters.  Binning against
-            # the GLOBAL range keeps the result bit-identical to one GPU.
+            # chi2 histogram over ALL ranks' toys without moving them (combine): local min/max -> one tiny all_gather
+            # -> global range -> local TH1F counts on the device -> one all_reduce of the 130 integer counters.
             a, b = C.c_double(), C.c_double()
             L.check(lib.isr_minmax_dev(ctx, T, mine.data_ptr(), C.byref(a), C.byref(b)))      # synchronises the stream
-            lo, hi = a.value, b.value
-            if world > 1:
-                small[0], small[1] = lo, hi
-                small[2:] = mine[T:T + n]
-                dist.all_gather_into_tensor(small_all.view(-1), small)
-                sa = small_all.cpu()
-                lo, hi = float(sa[:, 0].min()), float(sa[:, 1].max())
-            L.check(lib.isr_histogram_dev(ctx, T, mine.data_ptr(), 128, lo, hi, L.uptr(counts)))
-            tot = counts.astype(np.int64)
-            if world > 1:
-                cnt_dev.copy_(torch.from_numpy(tot))
-                dist.all_reduce(cnt_dev)
-                tot = cnt_dev.cpu().numpy()
+
+            def hist(lo, hi):
+                L.check(lib.isr_histogram_dev(ctx, T, mine.data_ptr(), 128, lo, hi, L.uptr(counts)))
+                return counts
+            tot = combine(a.value, b.value, None, hist)
             if record:
                 asm_ev.append((a0, a1)); toy_ev.append((t0, t1))
             return tot
@@ -363,9 +360,45 @@ def run_b200(args, rank, world, local_rank):
                                       "figure -- its toy vectors never cross PCIe"},
         "gpu_launches": int(launches), "clocks": clocks,
     }
+    line["assembly_other_configs"] = other_assemblies(lib, ctx, stream, torch)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(n, G, bcs0, vcs, err)
     emit(line)
+
+
+def other_assemblies(lib, ctx, stream, torch):
+    """Matrix-assembly ms (device-resident, CUDA events, mean of 10 after 2 warm-ups) for the other BASELINE.json
+    configurations: C1 N=50 linear, C2 N=100 cubic, C3 N=200 with a 512-bin efficiency histogram per point
+    (ISRSolverSLE2, 'matrix-assembly bound'), C5 N=500 linear."""
+    from isrsolver_b200 import _lib as L
+    out = {}
+    for name, n, cubic, nbins in (("c1_n50_linear", 50, False, 0), ("c2_n100_cubic", 100, True, 0),
+                                  ("c3_n200_eps512xN", 200, False, 512), ("c5_n500_linear", 500, False, 0)):
+        ecm = np.linspace(E_MIN, E_MAX, n)
+        st = np.ascontiguousarray([[0, 0, 0], [1, 1, n - 1]] if cubic else [[0, 0, n - 1]], dtype=np.int32)
+        desc = None
+        if nbins:
+            xc = (np.arange(nbins) + 0.5) / nbins
+            vals = np.zeros((n, nbins + 2))
+            vals[:, 1:-1] = 0.25 + 0.5 * np.exp(-40.0 * xc)[None, :] * (1.0 - 0.1 * (ecm[:, None] - 1.5))   # SURVEY.md 8d
+            desc = L.EpsDesc()
+            desc.kind, desc.nx, desc.xlo, desc.xhi, desc.values = 1, nbins, 0.0, 1.0, L.dptr(vals)
+        p = C.c_void_p()
+        L.check(lib.isr_problem_create(ctx, n, L.dptr(ecm), E_THR, len(st), L.iptr(st), C.byref(desc) if desc else None, C.byref(p)))
+        for _ in range(2):
+            L.check(lib.isr_assemble(p, None, None))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(10):
+                L.check(lib.isr_assemble(p, None, None))
+            e1.record(stream)
+        e1.synchronize()
+        npan, nnode = C.c_int64(), C.c_int64()
+        L.check(lib.isr_assemble_stats(p, C.byref(npan), C.byref(nnode)))
+        out[name] = {"ms": e0.elapsed_time(e1) / 10, "panels": npan.value, "nodes": nnode.value}
+        lib.isr_problem_destroy(p)
+    return out
 
 
 def cpu_baseline(n, G, bcs0, vcs, err):

@@ -21,7 +21,7 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* get_error() { return g_err; }
-long long g_launch_count = 0;
+std::atomic<long long> g_launch_count{0};
 }  // namespace isr
 
 using namespace isr;
@@ -30,7 +30,7 @@ extern "C" {
 
 const char* isr_last_error(void) { return isr::get_error(); }
 
-int64_t isr_launch_count(void) { return (int64_t)isr::g_launch_count; }
+int64_t isr_launch_count(void) { return (int64_t)isr::g_launch_count.load(); }
 
 int isr_ctx_create(int device, isr_ctx** out) {
   if (!out) { set_error("isr_ctx_create: out == NULL"); return ISR_EINVAL; }

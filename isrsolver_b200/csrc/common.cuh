@@ -1,6 +1,7 @@
 // Shared declarations for libisr_b200.so (host + device).  sm_100a only, FP64 throughout.
 #pragma once
 
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -53,8 +54,8 @@ const char* get_error();
   } while (0)
 
 // ---- launch accounting (bench.py reports it as gpu_launches) -----------------------------------------
-extern long long g_launch_count;
-#define ISR_COUNT_LAUNCH() (++isr::g_launch_count)
+extern std::atomic<long long> g_launch_count;   // problems on different host threads may launch concurrently
+#define ISR_COUNT_LAUNCH() (isr::g_launch_count.fetch_add(1, std::memory_order_relaxed))
 
 // ---- physical constants (include/PhysicalConstants.hpp:7,11) -------------------------------------
 constexpr double kAlphaQED = 7.2973525698e-03;
