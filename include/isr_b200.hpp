@@ -163,6 +163,18 @@ class ISRSolverSLE : public BaseISRSolver {   // include/ISRSolverSLE.hpp
     check(isr_interp_eval(_p, y.data(), 1, &energy, &out));
     return out;
   }
+  std::vector<double> interpEval(const std::vector<double>& y, const std::vector<double>& energies) const {
+    std::vector<double> out(energies.size());
+    if (!energies.empty()) check(isr_interp_eval(_p, y.data(), (int64_t)energies.size(), energies.data(), out.data()));
+    return out;
+  }
+  // inverse covariance G^T W G (PyISR bcs_inv_cov_matrix, include/PyISRSolverSLE.hpp:72-86)
+  virtual Matrix evalBornCSInvCovMatrix() {
+    ensureFactored();
+    Matrix m((int)_n, (int)_n);
+    check(isr_get_inv_cov(_p, m.data()));
+    return m;
+  }
   double evalConditionNumber() {   // :200-204
     if (!_isEqMatrixPrepared) evalEqMatrix();
     double c = 0;
