@@ -76,6 +76,14 @@ int isr_problem_set_ranges(isr_problem* p, int nranges, const int* ranges);
  * optionally G <- G_spread * G (src/ISRSolverSLE.cpp:177-193) when ecm_err != NULL.
  * G_out (N*N, column-major) may be NULL (matrix stays on the device). */
 int isr_assemble(isr_problem* p, const double* ecm_err, double* G_out);
+/* Host-sampled efficiency ("SAMPLED"): eps(x, E) is an arbitrary host callable, as the reference's
+ * std::function / Python callable is (include/BaseISRSolver.hpp:36-41, include/PyISRSolver.hpp:189-197).
+ * isr_assemble_nodes enumerates the quadrature panels of a problem created WITHOUT a tabulated efficiency and
+ * returns, for every node, x and the energy-point index i (evaluate eps(x, ecm[i]) there; pass NULL buffers to
+ * query *count only); isr_assemble_sampled then assembles G with those values entering the integrand node by
+ * node.  The callable must be smooth between the kernel's own break points: jumps are not resolved (use a table). */
+int isr_assemble_nodes(isr_problem* p, int64_t cap, double* x_out, int* row_out, int64_t* count);
+int isr_assemble_sampled(isr_problem* p, int64_t n_nodes, const double* eps_values, const double* ecm_err, double* G_out);
 /* Inject a matrix instead of assembling it (tests of the solve path; column-major). */
 int isr_set_matrix(isr_problem* p, const double* G);
 /* Number of quadrature panels / integrand nodes of the last isr_assemble (roofline unit counts). */

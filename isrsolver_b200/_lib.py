@@ -53,6 +53,8 @@ SIGNATURES = {
     "isr_problem_destroy": (None, [_vp]),
     "isr_problem_set_ranges": (C.c_int, [_vp, C.c_int, _ip]),
     "isr_assemble": (C.c_int, [_vp, _dp, _dp]),
+    "isr_assemble_nodes": (C.c_int, [_vp, _i64, _dp, _ip, _i64p]),
+    "isr_assemble_sampled": (C.c_int, [_vp, _i64, _dp, _dp, _dp]),
     "isr_set_matrix": (C.c_int, [_vp, _dp]),
     "isr_assemble_stats": (C.c_int, [_vp, _i64p, _i64p]),
     "isr_debug_panels": (C.c_int, [_vp, _i64, _dp, _ip, _i64p]),

@@ -389,11 +389,48 @@ __global__ void fill_kernel(int nitems, const RowConst* __restrict__ rows, EpsDe
 constexpr int kQ = 16;
 constexpr int kEvalThreads = 256;
 
+// Node `lane` of a panel: x, ln x, the pair-threshold power (x - x0)^beta (-1 below x0) and the quadrature
+// weight including dx/d(variable).  kind 0: x itself, 1: t = x^beta, 2: u = (x - x0)^beta.
+struct PanelNode { double x, lnx, pw, wj; };
+__device__ __forceinline__ PanelNode panel_node(const RowConst& rc, double a, double b, int kind, double t, double w) {
+  PanelNode q;
+  q.pw = -1.0;
+  if (kind == 0) {
+    const double half = 0.5 * (b - a);
+    q.x = fma(half, t, 0.5 * (a + b));
+    q.wj = half * w;
+    q.lnx = log(q.x);
+    q.pw = exp(rc.beta * log(q.x - rc.x0));
+  } else if (kind == 1) {
+    const double ta = a > 0.0 ? exp(rc.beta * log(a)) : 0.0;
+    const double tb = exp(rc.beta * log(b));
+    const double half = 0.5 * (tb - ta);
+    const double tt = fma(half, t, 0.5 * (ta + tb));
+    q.lnx = log(tt) * rc.inv_beta;
+    q.x = exp(q.lnx);
+    q.wj = half * w * rc.inv_beta * q.x / tt;
+  } else {
+    const double ya = a - rc.x0, yb = b - rc.x0;
+    const double ua = ya > 0.0 ? exp(rc.beta * log(ya)) : 0.0;
+    const double ub = exp(rc.beta * log(yb));
+    const double half = 0.5 * (ub - ua);
+    const double u = fma(half, t, 0.5 * (ua + ub));
+    const double y = exp(log(u) * rc.inv_beta);
+    q.x = rc.x0 + y;
+    q.lnx = log(q.x);
+    q.wj = half * w * rc.inv_beta * y / u;
+    q.pw = u;
+  }
+  return q;
+}
+
+// node_eps != nullptr: efficiency sampled by the host at every node (ISR_EPS_SAMPLED), [npanels][kQ]
 __global__ void __launch_bounds__(kEvalThreads)
 eval_kernel(const int* __restrict__ off_total, const RowConst* __restrict__ rows,
             const double* __restrict__ ext, const double* __restrict__ invh,
             const double* __restrict__ pa, const double* __restrict__ pb, const double* __restrict__ peps,
-            const int* __restrict__ pitem, const int* __restrict__ pkind, double* __restrict__ pm) {
+            const int* __restrict__ pitem, const int* __restrict__ pkind, const double* __restrict__ node_eps,
+            double* __restrict__ pm) {
   __shared__ double s_x[kQ], s_w[kQ];
   if (threadIdx.x < kQ) {
     s_x[threadIdx.x] = kGL16_x[threadIdx.x];
@@ -407,39 +444,16 @@ eval_kernel(const int* __restrict__ off_total, const RowConst* __restrict__ rows
   const int ngroups = gridDim.x * groups_per_block;
   const double t = s_x[lane], w = s_w[lane];
   for (int pidx = group; pidx < npanels; pidx += ngroups) {
-    const double a = pa[pidx], b = pb[pidx], ev = peps[pidx];
+    const double a = pa[pidx], b = pb[pidx];
+    double ev = peps[pidx];
+    if (node_eps) ev = node_eps[(size_t)pidx * kQ + lane];
     const int item = pitem[pidx], kind = pkind[pidx];
     int i, k;
     item_decode(item, i, k);
     const RowConst& rc = rows[i];
-    double x, lnx, wj, pw = -1.0;
-    if (kind == 0) {
-      const double half = 0.5 * (b - a);
-      x = fma(half, t, 0.5 * (a + b));
-      wj = half * w;
-      lnx = log(x);
-      pw = exp(rc.beta * log(x - rc.x0));
-    } else if (kind == 1) {
-      const double ta = a > 0.0 ? exp(rc.beta * log(a)) : 0.0;
-      const double tb = exp(rc.beta * log(b));
-      const double half = 0.5 * (tb - ta);
-      const double tt = fma(half, t, 0.5 * (ta + tb));
-      lnx = log(tt) * rc.inv_beta;
-      x = exp(lnx);
-      wj = half * w * rc.inv_beta * x / tt;
-    } else {
-      const double ya = a - rc.x0, yb = b - rc.x0;
-      const double ua = ya > 0.0 ? exp(rc.beta * log(ya)) : 0.0;
-      const double ub = exp(rc.beta * log(yb));
-      const double half = 0.5 * (ub - ua);
-      const double u = fma(half, t, 0.5 * (ua + ub));
-      const double y = exp(log(u) * rc.inv_beta);
-      x = rc.x0 + y;
-      lnx = log(x);
-      wj = half * w * rc.inv_beta * y / u;
-      pw = u;
-    }
-    const double f = kf_value(rc, x, lnx, pw) * wj * ev;
+    const PanelNode q = panel_node(rc, a, b, kind, t, w);
+    const double x = q.x;
+    const double f = kf_value(rc, x, q.lnx, q.pw) * q.wj * ev;
     const double dn = (rc.E * sqrt(1.0 - x) - ext[k]) * invh[k];
     double m0 = f, m1 = f * dn, m2 = m1 * dn, m3 = m2 * dn;
 #pragma unroll
@@ -454,6 +468,22 @@ eval_kernel(const int* __restrict__ off_total, const RowConst* __restrict__ rows
       reinterpret_cast<double4*>(pm)[pidx] = v;
     }
   }
+}
+
+// x and row index of every quadrature node of the current panel list (for host-sampled efficiencies)
+__global__ void __launch_bounds__(kEvalThreads)
+nodes_kernel(const int* __restrict__ off_total, const RowConst* __restrict__ rows, const double* __restrict__ pa,
+             const double* __restrict__ pb, const int* __restrict__ pitem, const int* __restrict__ pkind,
+             double* __restrict__ node_x, int* __restrict__ node_row) {
+  const int npanels = *off_total;
+  const int lane = threadIdx.x & (kQ - 1);
+  const int pidx = blockIdx.x * (kEvalThreads / kQ) + (threadIdx.x / kQ);
+  if (pidx >= npanels) return;
+  int i, k;
+  item_decode(pitem[pidx], i, k);
+  const PanelNode q = panel_node(rows[i], pa[pidx], pb[pidx], pkind[pidx], kGL16_x[lane], kGL16_w[lane]);
+  node_x[(size_t)pidx * kQ + lane] = q.x;
+  node_row[(size_t)pidx * kQ + lane] = i;
 }
 
 // Sum the panels of each item in panel order (deterministic) into M[i][k][0..3]; zero for k > i.
@@ -635,7 +665,8 @@ static int64_t panel_upper_bound(const isr_problem* p) {
   return n * (n + 1) / 2 + n * per_row_extra;
 }
 
-int assemble(isr_problem* p, const double* ecm_err) {
+// Panel enumeration (row constants, count, scan, fill): everything before the integrand is touched.
+static int enumerate_panels(isr_problem* p) {
   const int n = p->n;
   cudaStream_t st = p->ctx->stream;
   const int nitems = n * (n + 1) / 2;
@@ -652,19 +683,27 @@ int assemble(isr_problem* p, const double* ecm_err) {
   ISR_TRY(p->d_row.reserve(n));
   ISR_TRY(p->d_cnt.reserve(nitems));
   ISR_TRY(p->d_off.reserve(nitems + 1));
-  ISR_TRY(p->d_M.reserve((size_t)n * n * 4));
-  ISR_TRY(p->d_G.reserve((size_t)n * n));
-  ISR_TRY(p->d_Gpart.reserve((size_t)kCtSplit * n * n));
-
   row_setup_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, p->d_ext.p, p->d_row.p); ISR_COUNT_LAUNCH();
   count_kernel<<<(nitems + 127) / 128, 128, 0, st>>>(nitems, p->d_row.p, p->eps, p->d_ext.p, p->d_cnt.p); ISR_COUNT_LAUNCH();
   scan_kernel<<<1, 1024, 0, st>>>(nitems, p->d_cnt.p, p->d_off.p); ISR_COUNT_LAUNCH();
   fill_kernel<<<(nitems + 127) / 128, 128, 0, st>>>(nitems, p->d_row.p, p->eps, p->d_ext.p, p->d_off.p,
                                                       p->d_pa.p, p->d_pb.p, p->d_peps.p, p->d_pitem.p, p->d_pkind.p); ISR_COUNT_LAUNCH();
+  ISR_CUDA(cudaGetLastError());
+  return ISR_OK;
+}
+
+// Integrand evaluation, reduction, basis contraction and the optional spread product.
+static int finish_assembly(isr_problem* p, const double* ecm_err, const double* node_eps_dev) {
+  const int n = p->n;
+  cudaStream_t st = p->ctx->stream;
+  const int nitems = n * (n + 1) / 2;
+  ISR_TRY(p->d_M.reserve((size_t)n * n * 4));
+  ISR_TRY(p->d_G.reserve((size_t)n * n));
+  ISR_TRY(p->d_Gpart.reserve((size_t)kCtSplit * n * n));
   const int eval_blocks = p->ctx->sm_count * 8;
   eval_kernel<<<eval_blocks, kEvalThreads, 0, st>>>(p->d_off.p + nitems, p->d_row.p, p->d_ext.p, p->d_invh.p,
                                                      p->d_pa.p, p->d_pb.p, p->d_peps.p, p->d_pitem.p,
-                                                     p->d_pkind.p, p->d_pm.p); ISR_COUNT_LAUNCH();
+                                                     p->d_pkind.p, node_eps_dev, p->d_pm.p); ISR_COUNT_LAUNCH();
   reduce_kernel<<<(n * n + 127) / 128, 128, 0, st>>>(n, p->d_off.p, p->d_pm.p, p->d_M.p); ISR_COUNT_LAUNCH();
   dim3 cgrid((n + kCtCols - 1) / kCtCols, (n + kCtRows - 1) / kCtRows, kCtSplit);
   contract_kernel<<<cgrid, 256, 0, st>>>(n, p->d_M.p, p->d_Ct.p, p->d_klo.p, p->d_khi.p, p->d_Gpart.p); ISR_COUNT_LAUNCH();
@@ -691,6 +730,50 @@ int assemble(isr_problem* p, const double* ecm_err) {
   p->svd_ready = false;
   p->last_panels = -1;  // fetched lazily by isr_assemble_stats
   return ISR_OK;
+}
+
+int assemble(isr_problem* p, const double* ecm_err) {
+  ISR_TRY(enumerate_panels(p));
+  return finish_assembly(p, ecm_err, nullptr);
+}
+
+// ---- host-sampled efficiency (ISR_EPS_SAMPLED): eps(x, E_i) is an arbitrary host callable ------------------
+// Phase 1: enumerate the panels (cut at x0 and the grading points only -- a sampled efficiency has no bin edges)
+// and return x and the row of every node.  Phase 2: the caller's values enter the integrand node by node.
+int assemble_nodes(isr_problem* p, int64_t cap, double* x_out, int* row_out, int64_t* count) {
+  const int n = p->n;
+  cudaStream_t st = p->ctx->stream;
+  const int nitems = n * (n + 1) / 2;
+  if (p->eps.kind != 0) { set_error("isr_assemble_nodes: the problem already has a tabulated efficiency"); return ISR_ESTATE; }
+  ISR_TRY(enumerate_panels(p));
+  int total = 0;
+  ISR_CUDA(cudaMemcpyAsync(&total, p->d_off.p + nitems, sizeof(int), cudaMemcpyDeviceToHost, st));
+  ISR_CUDA(cudaStreamSynchronize(st));
+  const int64_t nn = (int64_t)total * kQ;
+  p->sampled_panels = total;
+  if (count) *count = nn;
+  if (!x_out && !row_out) return ISR_OK;
+  if (cap < nn) { set_error("isr_assemble_nodes: buffer holds %lld nodes, %lld needed", (long long)cap, (long long)nn); return ISR_EINVAL; }
+  ISR_TRY(p->d_node_x.reserve(nn));
+  ISR_TRY(p->d_node_row.reserve(nn));
+  nodes_kernel<<<(total + kEvalThreads / kQ - 1) / (kEvalThreads / kQ), kEvalThreads, 0, st>>>(
+      p->d_off.p + nitems, p->d_row.p, p->d_pa.p, p->d_pb.p, p->d_pitem.p, p->d_pkind.p, p->d_node_x.p, p->d_node_row.p); ISR_COUNT_LAUNCH();
+  ISR_CUDA(cudaGetLastError());
+  if (x_out) ISR_CUDA(cudaMemcpyAsync(x_out, p->d_node_x.p, sizeof(double) * nn, cudaMemcpyDeviceToHost, st));
+  if (row_out) ISR_CUDA(cudaMemcpyAsync(row_out, p->d_node_row.p, sizeof(int) * nn, cudaMemcpyDeviceToHost, st));
+  ISR_CUDA(cudaStreamSynchronize(st));
+  return ISR_OK;
+}
+
+int assemble_sampled(isr_problem* p, int64_t nn, const double* eps_values, const double* ecm_err) {
+  if (p->sampled_panels < 0 || nn != (int64_t)p->sampled_panels * kQ) {
+    set_error("isr_assemble_sampled: %lld values given, the node list of the last isr_assemble_nodes has %lld",
+              (long long)nn, (long long)(p->sampled_panels < 0 ? 0 : (int64_t)p->sampled_panels * kQ));
+    return ISR_ESTATE;
+  }
+  ISR_TRY(p->d_node_eps.reserve(nn > 0 ? nn : 1));
+  ISR_CUDA(cudaMemcpyAsync(p->d_node_eps.p, eps_values, sizeof(double) * nn, cudaMemcpyHostToDevice, p->ctx->stream));
+  return finish_assembly(p, ecm_err, p->d_node_eps.p);
 }
 
 // ---- device helpers exported to capi.cu ---------------------------------------------------------

@@ -124,6 +124,21 @@ int isr_assemble(isr_problem* p, const double* ecm_err, double* G_out) {
   return ISR_OK;
 }
 
+int isr_assemble_nodes(isr_problem* p, int64_t cap, double* x_out, int* row_out, int64_t* count) {
+  if (!p) { set_error("problem == NULL"); return ISR_EINVAL; }
+  ISR_CUDA(cudaSetDevice(p->ctx->device));
+  return assemble_nodes(p, cap, x_out, row_out, count);
+}
+
+int isr_assemble_sampled(isr_problem* p, int64_t n_nodes, const double* eps_values, const double* ecm_err, double* G_out) {
+  if (!p || (n_nodes > 0 && !eps_values)) { set_error("NULL argument"); return ISR_EINVAL; }
+  ISR_CUDA(cudaSetDevice(p->ctx->device));
+  ISR_TRY(assemble_sampled(p, n_nodes, eps_values, ecm_err));
+  if (G_out) ISR_CUDA(cudaMemcpyAsync(G_out, p->d_G.p, sizeof(double) * p->n * p->n, cudaMemcpyDeviceToHost, p->ctx->stream));
+  ISR_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  return ISR_OK;
+}
+
 int isr_set_matrix(isr_problem* p, const double* G) {
   if (!p || !G) { set_error("NULL argument"); return ISR_EINVAL; }
   ISR_CUDA(cudaSetDevice(p->ctx->device));

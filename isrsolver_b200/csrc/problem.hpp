@@ -33,6 +33,9 @@ struct isr_problem {
   isr::DevBuf<double> d_Gpart;   // split-K partials of the contraction
   isr::DevBuf<double> d_S, d_tmp, d_sigE;
   int64_t max_panels = 0;
+  int sampled_panels = -1;            // panel count of the last isr_assemble_nodes (host-sampled efficiency)
+  isr::DevBuf<double> d_node_x, d_node_eps;
+  isr::DevBuf<int> d_node_row;
   int64_t last_panels = 0;
   bool has_G = false;
   bool G_injected = false;   // matrix came from isr_set_matrix (cannot be re-assembled)
@@ -94,5 +97,7 @@ int build_eps_rows(cudaStream_t st, int n, const double* energy, const isr_eps_d
                    DevBuf<double>& d_edges, EpsDev& out);
 int exclusive_scan_int(cudaStream_t st, int n, const int* cnt_dev, int* off_dev);   // off[n] = total
 int assemble(isr_problem* p, const double* ecm_err);
+int assemble_nodes(isr_problem* p, int64_t cap, double* x_out, int* row_out, int64_t* count);
+int assemble_sampled(isr_problem* p, int64_t nn, const double* eps_values, const double* ecm_err);
 int apply_spread(isr_problem* p, cudaStream_t st, const double* sigE_dev, const double* G0, double* S, double* Gout);
 }  // namespace isr

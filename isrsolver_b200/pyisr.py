@@ -296,9 +296,14 @@ class BaseISRSolver:
         self._ecm_err, self._vcs_err = energy_err[idx].copy(), vcs_err[idx].copy()
         self._n, self._thr = n, float(threshold)
         self._spread = bool(enableEnergySpread)
+        # efficiency: an Efficiency table (binned, resolved exactly at its bin edges) or, as in the reference
+        # (include/PyISRSolver.hpp:189-197), a callable eps(x, energy) -- sampled by the host at the quadrature
+        # nodes the GPU asks for (isr_assemble_nodes / isr_assemble_sampled); it must be smooth in x
+        self._eff_call = None
         if efficiency is not None and not isinstance(efficiency, Efficiency):
-            raise TypeError("efficiency must be an isrsolver_b200.Efficiency table (a Python callable cannot be "
-                            "evaluated inside a CUDA kernel); see INTEGRATION.md")
+            if not callable(efficiency):
+                raise TypeError("efficiency must be an isrsolver_b200.Efficiency table or a callable eps(x, energy)")
+            self._eff_call, efficiency = efficiency, None
         self._eff = efficiency
         self._bcs = np.zeros(n)
         self._lib = L.load()
@@ -382,7 +387,21 @@ class ISRSolverSLE(BaseISRSolver):
     def eval_equation_matrix(self):
         """evalEqMatrix (src/ISRSolverSLE.cpp:138-149)."""
         G = np.empty((self._n, self._n))
-        L.check(self._lib.isr_assemble(self._p, L.dptr(self._ecm_err) if self._spread else None, L.dptr(G)))
+        spread = L.dptr(self._ecm_err) if self._spread else None
+        if self._eff_call is None:
+            L.check(self._lib.isr_assemble(self._p, spread, L.dptr(G)))
+        else:
+            cnt = C.c_int64()
+            L.check(self._lib.isr_assemble_nodes(self._p, 0, None, None, C.byref(cnt)))
+            x, row = np.empty(cnt.value), np.empty(cnt.value, dtype=np.int32)
+            L.check(self._lib.isr_assemble_nodes(self._p, cnt.value, L.dptr(x), L.iptr(row), C.byref(cnt)))
+            en = self._ecm[row]
+            try:
+                ev = np.asarray(self._eff_call(x, en), dtype=np.float64)
+                assert ev.shape == x.shape
+            except Exception:
+                ev = np.array([float(self._eff_call(float(a), float(b))) for a, b in zip(x, en)])
+            L.check(self._lib.isr_assemble_sampled(self._p, cnt.value, L.dptr(np.ascontiguousarray(ev)), spread, L.dptr(G)))
         self._G = G
         self._eq_ready = True
         self._factored = False

@@ -32,6 +32,7 @@ _LIB = None
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
 CALLBACK = C.CFUNCTYPE(C.c_double, C.c_double, C.c_void_p)
+EFF_CALLBACK = C.CFUNCTYPE(C.c_double, C.c_double, C.c_double, C.c_void_p)
 
 
 def build() -> bool:
@@ -60,6 +61,7 @@ def lib():
             getattr(L, nm).argtypes = [CALLBACK, C.c_void_p, C.c_double, C.c_double, _dp]
         L.ref_gaussian_conv.restype = C.c_double
         L.ref_gaussian_conv.argtypes = [C.c_double, C.c_double, CALLBACK, C.c_void_p]
+        L.ref_eval_eq_matrix_cb.argtypes = [C.c_void_p, EFF_CALLBACK, C.c_void_p, _dp, C.c_int, _ip]
         for pre in ("ref_", "ref2_"):
             f = lambda nm: getattr(L, pre + nm)
             f("interp_create").restype = C.c_void_p
@@ -168,6 +170,17 @@ class RefInterp:
         if ecm_err is not None:
             G = self.energy_spread_matrix(ecm_err) @ G
         return G
+
+    def eval_eq_matrix_callable(self, eff, rows=None):
+        """evalEqMatrix fill loop with the efficiency as a Python callable eps(x, energy), as PyISR passes it
+        (include/PyISRSolver.hpp:189-197).  v1 interpolator only; single-threaded."""
+        assert self._pre == "ref_"
+        cb = EFF_CALLBACK(lambda x, e, _ctx: float(eff(x, e)))
+        G = np.zeros((self.n, self.n), order="F")
+        ra = None if rows is None else np.ascontiguousarray(rows, dtype=np.int32)
+        lib().ref_eval_eq_matrix_cb(self._h, cb, None, G.ctypes.data_as(_dp), 0 if ra is None else len(ra),
+                                    None if ra is None else ra.ctypes.data_as(_ip))
+        return np.ascontiguousarray(G)
 
     def energy_spread_matrix(self, ecm_err):
         a = np.ascontiguousarray(ecm_err, dtype=np.float64)

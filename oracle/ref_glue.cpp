@@ -183,6 +183,22 @@ void REFN(eval_eq_matrix)(void* vh, const ref_eff* eff, double* G, int nrows, co
   });
 }
 
+#ifndef ISR_REF_V2
+// Same fill loop with the efficiency as a C callback eps(x, energy) -- the reference's std::function form
+// (include/BaseISRSolver.hpp:36-41; a Python callable in PyISR, include/PyISRSolver.hpp:189-197).  Single-threaded:
+// the callback may re-enter the interpreter.
+void ref_eval_eq_matrix_cb(void* vh, double (*eff)(double, double, void*), void* ctx, double* G, int nrows, const int* rows) {
+  auto* h = static_cast<RefInterp*>(vh);
+  const int n = h->n;
+  const EffFn ef = [eff, ctx](double x, double e) { return eff(x, e, ctx); };
+  const int nr = rows ? nrows : n;
+  for (int a = 0; a < nr; ++a) {
+    const int i = rows ? rows[a] : a;
+    for (int j = 0; j < n; ++j) G[(std::size_t)i + (std::size_t)n * j] = h->interp->evalKuraevFadinBasisIntegral(i, j, ef);
+  }
+}
+#endif
+
 // _energySpreadMatrix (src/ISRSolverSLE.cpp:177-193): S(i, j) = gaussian_conv(ecm_i, ecmErr_i^2, basis_j)
 void REFN(energy_spread_matrix)(void* vh, const double* ecm_err, double* S) {
   auto* h = static_cast<RefInterp*>(vh);

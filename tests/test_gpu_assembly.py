@@ -227,3 +227,37 @@ def test_condition_number_vs_spread_scan(oracle):
         assert c2[k] == pytest.approx(ref[0] / ref[-1], rel=1e-7)
     with pytest.raises(ValueError):
         s.condnum_spread_scan([-0.001])
+
+
+def test_callable_efficiency_sampled_at_the_nodes(oracle):
+    """SURVEY 8b `SAMPLED`: eps(x, E) as a Python callable, as the reference's PyISR constructor accepts it
+    (include/PyISRSolver.hpp:189-197) -- the host samples it at the GPU's quadrature nodes.  Compared with the
+    compiled reference running the SAME callable through its std::function, and with an equivalent fine table."""
+    import isrsolver_b200 as isr
+    from oracle import isr_ref as R
+    n = 12
+    ecm = np.linspace(1.18, 2.0, n); thr = 0.827
+    eff = lambda x, e: 0.3 + 0.5 * np.exp(-30.0 * x) * (1.0 - 0.1 * (e - 1.5))
+    st = [(False, 0, 2), (True, 3, n - 1)]
+    s = isr.ISRSolverSLE(n, ecm, np.ones(n), None, np.ones(n), thr, efficiency=eff)
+    s.set_interp_settings(st)
+    s.eval_equation_matrix()
+    G = s.intop_matrix()
+    s1 = isr.ISRSolverSLE(n, ecm, np.ones(n), None, np.ones(n), thr)
+    s1.set_interp_settings(st)
+    s1.eval_equation_matrix()
+    assert np.all(G[np.tril_indices(n)] < s1.intop_matrix()[np.tril_indices(n)])       # eps < 1 everywhere
+    if R.available():
+        Gr = R.RefInterp(ecm, thr, st).eval_eq_matrix_callable(eff)
+        assert_matrix_parity(G, Gr, None, rel=1e-9, abs_floor=2e-12, row_rel=1e-9, what="callable efficiency vs compiled reference")
+    # a scalar-only callable takes the element-wise path and gives the same matrix
+    s2 = isr.ISRSolverSLE(n, ecm, np.ones(n), None, np.ones(n), thr, efficiency=lambda x, e: float(eff(float(x), float(e))))
+    s2.set_interp_settings(st)
+    s2.eval_equation_matrix()
+    np.testing.assert_array_equal(s2.intop_matrix(), G)
+    # with the energy spread on top, and the solve path downstream of a sampled matrix
+    s3 = isr.ISRSolverSLE(n, ecm, G @ np.ones(n), np.full(n, 0.002), 0.05 * (G @ np.ones(n)), thr, efficiency=eff, enableEnergySpread=True)
+    s3.set_interp_settings(st)
+    s3.solve()
+    S = oracle.Interp(ecm, thr, st).energy_spread_matrix(np.full(n, 0.002))
+    np.testing.assert_allclose(s3.intop_matrix(), S @ G, rtol=1e-10, atol=1e-13)
