@@ -154,8 +154,8 @@ def workload_config(args, world):
                         f"{args.toys} toys per GPU, full matrix assembly + factor + toy batch + histogram per step",
             "n_points": args.n, "toys_per_gpu": args.toys, "toys_total": args.toys * world,
             "l2_policy": f"inputs larger than L2 (V = {args.toys * args.n * 8 / 2**20:.0f} MiB per GPU streams through the 126 MB L2 every step)",
-            "parallelism": f"toys sharded over {world} GPU(s), matrix replicated; per step one all_gather of (min, max, sum_bcs) "
-                           f"and one all_reduce of the 130 histogram counters"}
+            "parallelism": f"toys sharded over {world} GPU(s), matrix replicated; per step all_reduce(MIN) of (min, -max), "
+                           f"all_reduce(SUM) of the 130 histogram counters and of sum_bcs (N doubles), all device-resident"}
 
 
 # =====================================================================================================
@@ -200,6 +200,8 @@ def run_b200(args, rank, world, local_rank):
     small = torch.empty(2 + n, dtype=torch.float64, device=dev)         # packed per-rank summary: min, max, sum_bcs
     small_all = torch.empty((world, 2 + n), dtype=torch.float64, device=dev)
     cnt_dev = torch.empty(130, dtype=torch.int64, device=dev)
+    cnt32_dev = torch.empty(130, dtype=torch.int32, device=dev)
+    range_dev = torch.empty(2, dtype=torch.float64, device=dev)
     chi2_host = np.empty(T)
     sumb_host = np.zeros(n)
     counts = np.zeros(130, dtype=np.uint32)
@@ -243,15 +245,17 @@ def run_b200(args, rank, world, local_rank):
             L.check(lib.isr_toy_batch_dev(prob, T, Vd.data_ptr(), L.dptr(bcs0), mine.data_ptr(),
                                           mine[T:].data_ptr(), None, None, None))
             t1.record(stream)
-            # chi2 histogram over ALL ranks' toys without moving them (combine): local min/max -> one tiny all_gather
-            # -> global range -> local TH1F counts on the device -> one all_reduce of the 130 integer counters.
-            a, b = C.c_double(), C.c_double()
-            L.check(lib.isr_minmax_dev(ctx, T, mine.data_ptr(), C.byref(a), C.byref(b)))      # synchronises the stream
-
-            def hist(lo, hi):
-                L.check(lib.isr_histogram_dev(ctx, T, mine.data_ptr(), 128, lo, hi, L.uptr(counts)))
-                return counts
-            tot = combine(a.value, b.value, None, hist)
+            # chi2 histogram over ALL ranks' toys without moving them and without host round trips: {min, -max}
+            # on the device -> all_reduce(MIN) (N > 1) -> TH1F counts against the global range on the device ->
+            # all_reduce(SUM) of the 130 integer counters (N > 1) -> ONE device-to-host read of the result.
+            L.check(lib.isr_minmax_to_dev(ctx, T, mine.data_ptr(), range_dev.data_ptr()))
+            if world > 1:
+                dist.all_reduce(range_dev, op=dist.ReduceOp.MIN)
+            L.check(lib.isr_histogram_range_dev(ctx, T, mine.data_ptr(), 128, range_dev.data_ptr(), cnt32_dev.data_ptr()))
+            if world > 1:
+                dist.all_reduce(cnt32_dev)
+                dist.all_reduce(mine[T:T + n])              # sum of the toy solutions (covariance partial sums)
+            tot = cnt32_dev.cpu().numpy().astype(np.int64)   # synchronises
             if record:
                 asm_ev.append((a0, a1)); toy_ev.append((t0, t1))
             return tot

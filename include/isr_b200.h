@@ -161,6 +161,11 @@ int isr_draw_toys(isr_ctx* ctx, int64_t T, int n, int64_t first_toy, uint64_t se
 /* chi2 histogram, src/Chi2Test.cpp:64-78: TH1F(128, min, max) filled with every chi2 (ROOT bin
  * arithmetic; the maximum lands in the overflow cell).  counts_out has nbins+2 entries. */
 int isr_minmax_dev(isr_ctx* ctx, int64_t n, const double* v_dev, double* min_out, double* max_out);
+/* Fully device-resident, asynchronous forms for multi-GPU pipelines: out_dev = {min, -max}, so that ONE
+ * all_reduce(MIN) over the ranks yields the global range in the same layout; isr_histogram_range_dev bins
+ * against a range stored that way in device memory into int32 counters (overwritten) ready for an all_reduce(SUM). */
+int isr_minmax_to_dev(isr_ctx* ctx, int64_t n, const double* v_dev, double* out_dev);
+int isr_histogram_range_dev(isr_ctx* ctx, int64_t n, const double* v_dev, int nbins, const double* range_dev, int32_t* counts_dev);
 int isr_histogram_dev(isr_ctx* ctx, int64_t n, const double* v_dev, int nbins, double lo, double hi,
                       uint32_t* counts_out);
 /* TH1F(nbins, lo, hi) of the chi2 values the last isr_toy_batch / isr_toy_campaign of this problem left on the

@@ -76,6 +76,8 @@ SIGNATURES = {
     "isr_draw_toys": (C.c_int, [_vp, _i64, C.c_int, _i64, C.c_uint64, _dp, _dp, _dp]),
     "isr_set_toy_kernel": (C.c_int, [_vp, C.c_int]),
     "isr_minmax_dev": (C.c_int, [_vp, _i64, _vp, _dp, _dp]),
+    "isr_minmax_to_dev": (C.c_int, [_vp, _i64, _vp, _vp]),
+    "isr_histogram_range_dev": (C.c_int, [_vp, _i64, _vp, C.c_int, _vp, _vp]),
     "isr_histogram_dev": (C.c_int, [_vp, _i64, _vp, C.c_int, C.c_double, C.c_double, _up]),
     "isr_last_chi2_histogram": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, _up]),
     "isr_histogram": (C.c_int, [_vp, _i64, _dp, C.c_int, C.c_double, C.c_double, _up]),

@@ -507,6 +507,18 @@ int isr_minmax_dev(isr_ctx* ctx, int64_t n, const double* v_dev, double* min_out
   return minmax_device(ctx, n, v_dev, min_out, max_out);
 }
 
+int isr_minmax_to_dev(isr_ctx* ctx, int64_t n, const double* v_dev, double* out_dev) {
+  if (!ctx || !v_dev || !out_dev) { set_error("NULL argument"); return ISR_EINVAL; }
+  ISR_CUDA(cudaSetDevice(ctx->device));
+  return minmax_to_device(ctx, n, v_dev, out_dev);
+}
+
+int isr_histogram_range_dev(isr_ctx* ctx, int64_t n, const double* v_dev, int nbins, const double* range_dev, int32_t* counts_dev) {
+  if (!ctx || (n > 0 && !v_dev) || !range_dev || !counts_dev) { set_error("NULL argument"); return ISR_EINVAL; }
+  ISR_CUDA(cudaSetDevice(ctx->device));
+  return histogram_range_device(ctx, n, v_dev, nbins, range_dev, counts_dev);
+}
+
 int isr_histogram_dev(isr_ctx* ctx, int64_t n, const double* v_dev, int nbins, double lo, double hi, uint32_t* counts_out) {
   if (!ctx || (n > 0 && !v_dev) || !counts_out) { set_error("NULL argument"); return ISR_EINVAL; }
   ISR_CUDA(cudaSetDevice(ctx->device));

@@ -105,6 +105,51 @@ __global__ void hist_kernel(int64_t n, const double* __restrict__ v, int nbins, 
     if (sh[q]) atomicAdd(&counts[q], sh[q]);
 }
 
+// Device-resident variants for multi-GPU pipelines (no host round trip, asynchronous on the context stream):
+// out_dev[0] = min, out_dev[1] = -max, so that ONE all_reduce(MIN) over ranks yields the global range.
+__global__ void minmax_final_kernel(int blocks, const double* __restrict__ part, double* __restrict__ out) {
+  double lo = INFINITY, hi = -INFINITY;
+  for (int q = threadIdx.x; q < blocks; q += 32) { lo = fmin(lo, part[2 * q]); hi = fmax(hi, part[2 * q + 1]); }
+  for (int s = 16; s >= 1; s >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, s));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, s));
+  }
+  if (threadIdx.x == 0) { out[0] = lo; out[1] = -hi; }
+}
+int minmax_to_device(isr_ctx* c, int64_t n, const double* v_dev, double* out_dev) {
+  if (n <= 0) { set_error("minmax: empty input"); return ISR_EINVAL; }
+  const int blocks = (int)std::min<int64_t>(c->sm_count * 4, (n + 255) / 256);
+  ISR_TRY(c->scratch_d.reserve(2 * blocks));
+  minmax_kernel<<<blocks, 256, 0, c->stream>>>(n, v_dev, c->scratch_d.p); ISR_COUNT_LAUNCH();
+  minmax_final_kernel<<<1, 32, 0, c->stream>>>(blocks, c->scratch_d.p, out_dev); ISR_COUNT_LAUNCH();
+  ISR_CUDA(cudaGetLastError());
+  return ISR_OK;
+}
+// TH1 counts with the range read from device memory ({lo, -hi} as minmax_to_device / the all_reduce leave it);
+// counts_dev[nbins + 2] int32 is overwritten.
+__global__ void hist_range_dev_kernel(int64_t n, const double* __restrict__ v, int nbins, const double* __restrict__ range,
+                                      int* __restrict__ counts) {
+  extern __shared__ uint32_t sh[];
+  const double lo = range[0], hi = -range[1];
+  for (int q = threadIdx.x; q < nbins + 2; q += blockDim.x) sh[q] = 0;
+  __syncthreads();
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd(&sh[th1_bin(nbins, lo, hi, v[q])], 1u);
+  __syncthreads();
+  for (int q = threadIdx.x; q < nbins + 2; q += blockDim.x)
+    if (sh[q]) atomicAdd(&counts[q], (int)sh[q]);
+}
+int histogram_range_device(isr_ctx* c, int64_t n, const double* v_dev, int nbins, const double* range_dev, int* counts_dev) {
+  if (nbins < 1 || nbins > 8190) { set_error("histogram: nbins out of range"); return ISR_EINVAL; }
+  ISR_CUDA(cudaMemsetAsync(counts_dev, 0, sizeof(int) * (nbins + 2), c->stream));
+  if (n > 0) {
+    const int blocks = (int)std::min<int64_t>(c->sm_count * 4, (n + 255) / 256);
+    hist_range_dev_kernel<<<blocks, 256, sizeof(uint32_t) * (nbins + 2), c->stream>>>(n, v_dev, nbins, range_dev, counts_dev); ISR_COUNT_LAUNCH();
+  }
+  ISR_CUDA(cudaGetLastError());
+  return ISR_OK;
+}
+
 int minmax_device(isr_ctx* c, int64_t n, const double* v_dev, double* lo, double* hi) {
   if (n <= 0) { set_error("minmax: empty input"); return ISR_EINVAL; }
   const int blocks = (int)std::min<int64_t>(c->sm_count * 4, (n + 255) / 256);

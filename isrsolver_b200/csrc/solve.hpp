@@ -6,6 +6,8 @@ int factor(isr_problem* p, const double* vcs_err);
 int select_sle(isr_problem* p);
 int minmax_device(isr_ctx* c, int64_t n, const double* v_dev, double* lo, double* hi);
 int histogram_device(isr_ctx* c, int64_t n, const double* v_dev, int nbins, double lo, double hi, uint32_t* counts_host);
+int minmax_to_device(isr_ctx* c, int64_t n, const double* v_dev, double* out_dev);
+int histogram_range_device(isr_ctx* c, int64_t n, const double* v_dev, int nbins, const double* range_dev, int* counts_dev);
 int toy_batch_host(isr_problem* p, int64_t T, const double* V, const double* bcs0, double* chi2_out,
                    double* sum_bcs_out, double* ratio_stats_out, uint32_t* ratio_hist_out, double* bcs_out);
 int toy_campaign_device(isr_problem* p, int64_t T, int64_t first_toy, uint64_t seed, const double* vcs,

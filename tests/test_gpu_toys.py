@@ -279,3 +279,21 @@ def test_sharded_chi2_test_equals_single_gpu(tmp_path, world):
                          env=dict(os.environ, MASTER_ADDR="127.0.0.1"), capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count("ok") == world
+
+
+def test_device_resident_minmax_and_histogram(oracle):
+    """isr_minmax_to_dev / isr_histogram_range_dev (the multi-GPU pipeline's forms) == the host-range forms."""
+    import torch
+    from isrsolver_b200 import _lib as L
+    from isrsolver_b200.pyisr import _ctx
+    lib, ctx = L.load(), _ctx()
+    v = torch.from_numpy(np.random.default_rng(4).chisquare(40, 100003)).cuda()
+    rng, cnt = torch.empty(2, dtype=torch.float64, device="cuda"), torch.full((130,), 7, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    L.check(lib.isr_minmax_to_dev(ctx, v.numel(), v.data_ptr(), rng.data_ptr()))
+    L.check(lib.isr_histogram_range_dev(ctx, v.numel(), v.data_ptr(), 128, rng.data_ptr(), cnt.data_ptr()))
+    L.check(lib.isr_ctx_synchronize(ctx))
+    lo, hi = float(rng[0]), -float(rng[1])
+    assert (lo, hi) == (float(v.min()), float(v.max()))
+    ref, *_ = oracle.chi2_histogram(v.cpu().numpy())
+    np.testing.assert_array_equal(cnt.cpu().numpy(), ref.astype(np.int32))
