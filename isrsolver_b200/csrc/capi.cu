@@ -289,7 +289,10 @@ int isr_solve(isr_problem* p, const double* vcs, double* bcs_out, double* cov_ou
   ISR_CUDA(cudaMemcpyAsync(p->d_b0.p, vcs, sizeof(double) * n, cudaMemcpyHostToDevice, st));
   ISR_TRY(gemv(p->ctx, false, n, p->d_Ginv.p, p->d_b0.p, p->d_stat.p));
   ISR_CUDA(cudaMemcpyAsync(bcs_out, p->d_stat.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-  if (cov_out) ISR_CUDA(cudaMemcpyAsync(cov_out, p->d_Cov.p, sizeof(double) * n * n, cudaMemcpyDeviceToHost, st));
+  if (cov_out) {
+    ISR_TRY(ensure_cov(p));
+    ISR_CUDA(cudaMemcpyAsync(cov_out, p->d_Cov.p, sizeof(double) * n * n, cudaMemcpyDeviceToHost, st));
+  }
   ISR_CUDA(cudaStreamSynchronize(st));
   return ISR_OK;
 }
@@ -303,7 +306,13 @@ static int copy_out(isr_problem* p, const double* dev, double* host, const char*
   return ISR_OK;
 }
 int isr_get_inverse(isr_problem* p, double* out) { return copy_out(p, p ? p->d_Ginv.p : nullptr, out, "isr_get_inverse"); }
-int isr_get_inv_cov(isr_problem* p, double* out) { return copy_out(p, p ? p->d_InvCov.p : nullptr, out, "isr_get_inv_cov"); }
+int isr_get_inv_cov(isr_problem* p, double* out) {
+  if (p && p->factored) {
+    ISR_CUDA(cudaSetDevice(p->ctx->device));
+    ISR_TRY(ensure_cov(p));
+  }
+  return copy_out(p, p ? p->d_InvCov.p : nullptr, out, "isr_get_inv_cov");
+}
 
 int isr_cond_number(isr_problem* p, double* cond_out) {
   if (!p || !cond_out) { set_error("NULL argument"); return ISR_EINVAL; }

@@ -50,6 +50,7 @@ struct isr_problem {
   std::vector<double> vcs_err, h_b0, h_gen;   // h_gen: {vcs, vcs_err} of the device toy generator (stable host mirror)
   isr::DevBuf<double> d_gen;
   bool factored = false;
+  bool cov_ready = false;      // d_Cov / d_InvCov match the current factorisation
   bool solver_selected = false;
   int toy_variant = 0;
   int64_t last_chi2_count = 0;   // chi2 values the last host-API batch / campaign left in d_chi2h

@@ -38,12 +38,25 @@ int factor(isr_problem* p, const double* vcs_err) {
   ISR_CUDA(cudaMemcpyAsync(p->d_tmp.p, p->d_G.p, sizeof(double) * nn, cudaMemcpyDeviceToDevice, st));
   ISR_TRY(lu_inverse(c, n, p->d_tmp.p, p->d_Ginv.p, p->d_work, p->d_ipiv, p->d_info));
   scale_rows(st, n, p->d_G.p, p->d_werr.p, 1, p->d_R.p);                  // R = diag(1/err) G
-  scale_cols(st, n, p->d_Ginv.p, p->d_werr.p, 0, p->d_tmp.p);             // Ginv diag(err)
+  ISR_CUDA(cudaGetLastError());
+  p->factored = true;
+  p->cov_ready = false;      // Cov / G^T W G are formed on first use (ensure_cov): the toy path never reads them
+  return select_sle(p);
+}
+
+// Cov = (Ginv W^(-1/2)) (Ginv W^(-1/2))^T and InvCov = R^T R, once per factorisation and only when asked for.
+int ensure_cov(isr_problem* p) {
+  if (!p->factored) { set_error("covariance: isr_factor has not been called"); return ISR_ESTATE; }
+  if (p->cov_ready) return ISR_OK;
+  const int n = p->n;
+  isr_ctx* c = p->ctx;
+  ISR_TRY(p->d_tmp.reserve((size_t)n * n));
+  scale_cols(c->stream, n, p->d_Ginv.p, p->d_werr.p, 0, p->d_tmp.p);      // Ginv diag(err)
   ISR_TRY(gemm(c, false, true, n, p->d_tmp.p, p->d_tmp.p, p->d_Cov.p));   // Cov
   ISR_TRY(gemm(c, true, false, n, p->d_R.p, p->d_R.p, p->d_InvCov.p));    // G^T W G
   ISR_CUDA(cudaGetLastError());
-  p->factored = true;
-  return select_sle(p);
+  p->cov_ready = true;
+  return ISR_OK;
 }
 
 // Operators the toy kernel consumes: row-major, leading dimension padded to even, pad column zero.

@@ -64,6 +64,7 @@ int tikhonov_prepare(isr_problem* p, const double* vcs_err, int deriv_reg) {
   bool same = p->factored && p->vcs_err.size() == (size_t)n;
   if (same) for (int i = 0; i < n; ++i) same = same && p->vcs_err[i] == vcs_err[i];
   if (!same) ISR_TRY(factor(p, vcs_err));
+  ISR_TRY(ensure_cov(p));      // G^T W G below
   // w_j = int basis_j dE (src/ISRSolverSLE.cpp:165-171), exact from the polynomial pieces
   std::vector<double> w(n);
   ISR_TRY(isr_basis_integrals(p, w.data()));
@@ -505,6 +506,7 @@ int tsvd_solve(isr_problem* p, int k, int keep_one, const double* vcs, const dou
     }
     if (!vcs_err) { set_error("isr_tsvd_solve: vcs_err needed for the covariance"); return ISR_EINVAL; }
     ISR_TRY(factor(p, vcs_err));
+    ISR_TRY(ensure_cov(p));
     ISR_CUDA(cudaMemcpyAsync(cov_out, p->d_Cov.p, sizeof(double) * n * n, cudaMemcpyDeviceToHost, st));
     ISR_CUDA(cudaStreamSynchronize(st));
   }
