@@ -48,7 +48,7 @@ __global__ void repack_kernel(int64_t T, int n, int ld, const double* __restrict
 }
 
 struct ToyCfg {
-  int tm, np, threads, wm;
+  int tm, np, threads, wm, kc, stages;
   size_t smem_base;   // stages + barriers + chi2 row scratch; statistics scratch is added per launch
   void (*kernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, ToyArgs);
   const char* name;
@@ -69,43 +69,51 @@ static EncodeTiledFn encode_fn() {
   }
   return fn;
 }
-// 2-D FP64 map over a row-major [rows][ld] matrix, box = box_rows x kKC, no swizzle, zero OOB fill
-static int make_map(CUtensorMap* m, const double* base, int64_t rows, int ld, int box_rows) {
+// 2-D FP64 map over a row-major [rows][ld] matrix, box = box_rows x kc, no swizzle, zero OOB fill
+static int make_map(CUtensorMap* m, const double* base, int64_t rows, int ld, int box_rows, int kc) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return ISR_ECUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
-  cuuint32_t box[2] = {(cuuint32_t)kKC, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (%d) for a %lld x %d matrix, box %d x %d", (int)r, (long long)rows, ld, box_rows, kKC);
+    set_error("cuTensorMapEncodeTiled failed (%d) for a %lld x %d matrix, box %d x %d", (int)r, (long long)rows, ld, box_rows, kc);
     return ISR_ECUDA;
   }
   return ISR_OK;
 }
 
-template <int WM, int WN, int AT, int BT, int ST>
+template <int WM, int WN, int AT, int BT, int ST, int KC = 24>
 static ToyCfg make_cfg(const char* name) {
   ToyCfg c;
   c.tm = WM * AT * 8;
   c.np = WN * BT * 8;
   c.threads = WM * WN * 32;
   c.wm = WM;
-  c.smem_base = toy_fused_smem_base<WM, WN, AT, BT, ST>();
-  c.kernel = toy_fused_kernel<WM, WN, AT, BT, ST>;
+  c.kc = KC;
+  c.stages = ST;
+  c.smem_base = toy_fused_smem_base<WM, WN, AT, BT, ST, KC>();
+  c.kernel = toy_fused_kernel<WM, WN, AT, BT, ST, KC>;
   c.name = name;
   return c;
 }
 
 static const std::vector<ToyCfg>& configs() {
+  // name = m<TM>n<NP>w<warps>[s<stages>][k<KC>]; defaults 3 stages, KC = 24.  The k40 variants trade the third
+  // pipeline stage for 40-double chunks (fewer chunk boundaries); they are preferred whenever they fit.
   static const std::vector<ToyCfg> v = {
-      make_cfg<4, 2, 4, 4, 3>("m128n64w8"),   make_cfg<8, 1, 2, 13, 3>("m128n104w8"),
-      make_cfg<4, 4, 2, 4, 3>("m64n128w16"),  make_cfg<4, 5, 2, 5, 3>("m64n200w20"),
-      make_cfg<4, 2, 2, 13, 3>("m64n208w8"),  make_cfg<4, 4, 2, 8, 3>("m64n256w16"),
+      make_cfg<4, 2, 4, 4, 3>("m128n64w8"),    make_cfg<8, 1, 2, 13, 3>("m128n104w8"),
+      make_cfg<4, 4, 2, 4, 3>("m64n128w16"),   make_cfg<4, 5, 2, 5, 3>("m64n200w20"),
+      make_cfg<4, 2, 2, 13, 3>("m64n208w8"),   make_cfg<4, 4, 2, 8, 3>("m64n256w16"),
       make_cfg<4, 4, 2, 8, 2>("m64n256w16s2"), make_cfg<8, 2, 2, 7, 3>("m128n112w16"),
+      make_cfg<4, 5, 2, 5, 2>("m64n200w20s2"),
+      make_cfg<4, 5, 2, 5, 2, 40>("m64n200w20s2k40"),  make_cfg<4, 4, 2, 8, 2, 40>("m64n256w16s2k40"),
+      make_cfg<8, 2, 2, 7, 2, 40>("m128n112w16s2k40"), make_cfg<4, 4, 2, 4, 2, 40>("m64n128w16s2k40"),
+      make_cfg<4, 4, 2, 4, 3, 40>("m64n128w16k40"),
   };
   return v;
 }
@@ -121,14 +129,17 @@ static const ToyCfg* pick_cfg(int n, int nstat) {
   const char* force = std::getenv("ISR_TOY_CFG");
   const ToyCfg* best = nullptr;
   double best_cost = 1e300;
+  const int ld = (n + 1) & ~1;
   for (const ToyCfg& c : configs()) {
     if (cfg_smem(c, n, nstat) > kSmemLimit) continue;
     if (force && std::string(force) == c.name) return &c;
     const int nblk = (n + c.np - 1) / c.np;
-    // padded work, a mild preference for tall tiles and deeper pipelines
-    double cost = (double)nblk * c.np * (1.0 + 2.0 / c.tm);
-    if (std::string(c.name).find("s2") != std::string::npos) cost *= 1.05;
-    if (c.threads < 512) cost *= 1.10;   // 8-warp tiles hide latency worse (measured: N=100 25.8 vs 24.9 TFLOP/s)
+    // cost model (fitted to the B200 measurements in DESIGN.md K5): DMMA work of the padded tile in 8-deep k-steps
+    // plus ~0.3 k-step per chunk boundary; a mild preference for tall tiles; 8-warp tiles hide latency worse
+    const int nk = (ld + c.kc - 1) / c.kc;
+    double cost = (double)nblk * c.np * ((ld + 7) / 8 + 0.31 * nk) * (1.0 + 2.0 / c.tm);
+    if (c.threads < 512) cost *= 1.10;   // measured: N=100 25.8 vs 24.9 TFLOP/s
+    if (c.stages < 3 && c.kc == 24) cost *= 1.001;   // tie-break: the deeper ring when nothing else differs
     if (cost < best_cost) { best_cost = cost; best = &c; }
   }
   return best;
@@ -158,8 +169,8 @@ static int launch_fused(isr_problem* p, int64_t T, const double* V_dev, const do
   ToyArgs g{};
   g.b0 = b0_dev; g.T = T; g.N = n; g.ld = ld; g.nblk = nblk; g.do2 = Rop ? 1 : 0;
   CUtensorMap mapV, mapS, mapR, mapD;
-  ISR_TRY(make_map(&mapV, A, T, ld, cfg->tm));
-  ISR_TRY(make_map(&mapS, Sop, n, ld, cfg->np));
+  ISR_TRY(make_map(&mapV, A, T, ld, cfg->tm, cfg->kc));
+  ISR_TRY(make_map(&mapS, Sop, n, ld, cfg->np, cfg->kc));
   if (Rop) {
     const size_t ring = (size_t)p->ctx->sm_count * kRingSlots * cfg->tm * ld;
     if (p->d_B.n < ring) {
@@ -167,8 +178,8 @@ static int launch_fused(isr_problem* p, int64_t T, const double* V_dev, const do
       ISR_CUDA(cudaMemsetAsync(p->d_B.p, 0, ring * sizeof(double), st));   // pad column stays zero
     }
     g.Dring = p->d_B.p;
-    ISR_TRY(make_map(&mapR, Rop, n, ld, cfg->np));
-    ISR_TRY(make_map(&mapD, p->d_B.p, (int64_t)p->ctx->sm_count * kRingSlots * cfg->tm, ld, cfg->tm));
+    ISR_TRY(make_map(&mapR, Rop, n, ld, cfg->np, cfg->kc));
+    ISR_TRY(make_map(&mapD, p->d_B.p, (int64_t)p->ctx->sm_count * kRingSlots * cfg->tm, ld, cfg->tm, cfg->kc));
   } else {
     g.Dfull = Dfull;
     mapR = mapS;

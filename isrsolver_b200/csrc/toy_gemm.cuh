@@ -10,7 +10,7 @@
 // so that the d-tile a pass 2 streams back was stored a whole tile-pass earlier.
 //
 // TMA pipeline without a block-wide barrier: every K chunk is two cp.async.bulk.tensor (TMA) box loads
-// (A box TM x 24 doubles, B box NP x 24 doubles) into a ring of STAGES shared-memory buffers, completion
+// (A box TM x KC doubles, B box NP x KC doubles) into a ring of STAGES shared-memory buffers, completion
 // signalled on a "full" mbarrier per stage.  All WM x WN warps are consumers; when a warp is done with a
 // stage it bumps a shared counter, and the LAST warp to finish a stage immediately issues the TMA loads
 // of the chunk STAGES ahead into it (so there is no dedicated producer warp -- 21 warps would cap the
@@ -21,8 +21,8 @@
 // North-star rule: DMMA is used because tools/fp64_peaks.cu measured 37.1 TFLOP/s for the tensor pipe
 // against 33.3 TFLOP/s for DFMA on this B200 (profiles/fp64_peaks_r01.json).
 //
-// Tiling: warp tile = (AT*8 toys) x (BT*8 columns), K chunks of 24 doubles.  Rows of 24 doubles = 192 B
-// have stride 8 (mod 16) doubles, which makes the 16-byte fragment loads conflict free without padding
+// Tiling: warp tile = (AT*8 toys) x (BT*8 columns), K chunks of KC = 24 / 40 / 56 doubles.  Rows of KC doubles
+// (192 / 320 / 448 B) have stride 8 (mod 16) doubles, which makes the 16-byte fragment loads conflict free without padding
 // or swizzle; each 16-byte load feeds two DMMAs (the k-permutation {2c, 2c+1} is applied to A and B
 // alike, so the contraction is unchanged).  Operators wider than one CTA tile (N > NP) are processed as
 // column blocks by the same CTA.
@@ -37,7 +37,10 @@
 
 namespace isr {
 
-constexpr int kKC = 24;        // K chunk (doubles); 24 = 8 (mod 16) keeps LDS.128 conflict-free
+// K chunk KC (doubles, template parameter): rows of KC doubles must have stride 8 (mod 16) doubles -- 24, 40, 56 --
+// to keep the 16-byte fragment loads conflict-free.  Fewer, fuller chunks are faster: every chunk boundary costs a
+// barrier wait, a stage hand-over and a TMA issue (measured at N = 200: KC = 24 -> 9 chunks, the last one a third
+// full, 31.8 TFLOP/s; KC = 40 -> 5 full chunks, 33.4 TFLOP/s), but the stage ring has to fit 227 KB.
 constexpr int kRingSlots = 3;  // d-tiles alive per CTA (2 by schedule, +1 slack)
 
 // L2 eviction-priority policies for TMA loads (same encodings CUTLASS uses for SM90+ cache hints)
@@ -139,10 +142,12 @@ struct Sched {
   }
 };
 
-template <int WM, int WN, int AT, int BT, int STAGES>
+template <int WM, int WN, int AT, int BT, int STAGES, int KC>
 __global__ void __launch_bounds__(WM * WN * 32, 1)
 toy_fused_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapS,
                  const __grid_constant__ CUtensorMap mapR, const __grid_constant__ CUtensorMap mapD, ToyArgs g) {
+  constexpr int kKC = KC;
+  static_assert(KC % 16 == 8, "KC must be 8 (mod 16) doubles");
   constexpr int TM = WM * AT * 8;
   constexpr int NP = WN * BT * 8;
   constexpr int NCW = WM * WN;            // warps (all consumers)
@@ -383,8 +388,9 @@ toy_fused_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant
   }
 }
 
-template <int WM, int WN, int AT, int BT, int STAGES>
+template <int WM, int WN, int AT, int BT, int STAGES, int KC>
 constexpr size_t toy_fused_smem_base() {
+  constexpr int kKC = KC;
   constexpr int TM = WM * AT * 8, NP = WN * BT * 8;
   return (size_t)STAGES * (TM + NP) * kKC * sizeof(double) + (2 * STAGES + kRingSlots + 1) * sizeof(uint64_t) +
          (size_t)2 * WN * TM * sizeof(double);

@@ -45,7 +45,7 @@ for n in (100, 200, 500):
     Vd = torch.from_numpy(vcs)[None,:].cuda() + torch.from_numpy(err)[None,:].cuda()*torch.randn(T, n, dtype=torch.float64, device='cuda')
     chi2d = torch.empty(T, dtype=torch.float64, device='cuda'); sbd = torch.zeros(n, dtype=torch.float64, device='cuda')
     torch.cuda.synchronize()
-    for cfgname in ({100: [None, "m128n112w16"], 200: [None, "m64n200w20s4", None], 500: [None]}[n]):
+    for cfgname in ({100: [None, "m128n112w16", "m128n112w16s2k40"], 200: [None, "m64n200w20", "m64n200w20s2k40"], 500: [None, "m64n256w16", "m64n256w16s2k40"]}[n]):
         if cfgname: os.environ["ISR_TOY_CFG"] = cfgname
         else: os.environ.pop("ISR_TOY_CFG", None)
         for modes in ("chi2+sum", "chi2"):
