@@ -80,6 +80,13 @@ def test_large_n_rows_and_toys(oracle, n):
     z = (V - vcs) / err
     np.testing.assert_allclose(r["chi2"], (z * z).sum(1), rtol=1e-8)
     np.testing.assert_allclose(r["sum_bcs"], B.sum(0), rtol=1e-8, atol=1e-8 * np.abs(B.sum(0)).max())
+    # ratio statistics at this size need the smallest stage ring (the per-CTA accumulators take 128 KB)
+    r4 = s.toy_batch(V[:300], b0, want_chi2=False, want_ratio=True, want_hist=True)
+    rr = (B[:300] - b0[None, :]) / b0[None, :]
+    inr = (rr >= -2) & (rr < 2)
+    np.testing.assert_array_equal(r4["ratio_stats"][:, 0], inr.sum(0))
+    np.testing.assert_allclose(r4["ratio_stats"][:, 1], np.where(inr, rr, 0).sum(0), rtol=1e-7, atol=1e-9)
+    assert np.all(r4["ratio_hist"].sum(1) == 300)
 
 
 @pytest.mark.parametrize("T", [1, 7, 63, 64, 65, 148 * 64 - 1, 148 * 64 + 1])
