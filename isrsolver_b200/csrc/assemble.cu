@@ -275,35 +275,68 @@ __device__ __forceinline__ double knot_x(const double* __restrict__ ext, double 
   return fmax(0.0, 1.0 - r * r);
 }
 
-// Walk the panels of item (row i, segment k).  Emit(a, b) is called for every panel in ascending x.
-template <typename Emit>
-__device__ __forceinline__ int walk_item(const RowConst& rc, const EpsDev& eps, const double* __restrict__ ext,
-                                         int i, int k, Emit emit) {
-  const double xa = knot_x(ext, rc.E, i, k + 1);
-  const double xb = knot_x(ext, rc.E, i, k);
-  int count = 0;
-  if (!(xb > xa)) return 0;
-  int ir = 0;
-  while (ir < rc.nrb && !(rc.rb[ir] > xa)) ++ir;
-  int ie = 0x7fffffff;
-  if (eps.kind == 2) ie = eps_first_edge_above(eps, xa);
-  double cur = xa;
-  for (;;) {
-    const double nr = ir < rc.nrb ? rc.rb[ir] : 2.0;
-    const double ne = (eps.kind == 2 && ie <= eps.nx) ? eps_edge(eps, ie) : 2.0;
-    const double nxt = fmin(nr, ne);
-    if (!(nxt < xb)) {
-      emit(cur, xb);
-      ++count;
-      break;
-    }
-    emit(cur, nxt);
-    ++count;
-    cur = nxt;
-    if (nr <= nxt) ++ir;
-    if (ne <= nxt) ++ie;
+// Panels of item (row i, segment k): the x-interval (xa, xb) of the segment seen from row i, cut at the row's
+// grading points R = {rb[r] in (xa, xb)} and at the efficiency bin edges E = {edge(m) in (xa, xb)}.  The interior
+// cuts are the stable merge of the two ascending sets (R first on a tie; a tie leaves a zero-width panel, which
+// integrates to zero), so the panel count is analytic -- 1 + |R| + |E| -- and the q-th cut can be selected directly:
+// no serial walk over hundreds of bins for the items that span most of a tabulated efficiency.
+struct ItemCuts {
+  double xa, xb;
+  int r0, nR;     // rb[r0 .. r0 + nR) lie strictly inside (xa, xb)
+  int e0, nE;     // edges e0 .. e0 + nE - 1 lie strictly inside (xa, xb)
+  __device__ int count() const { return xb > xa ? 1 + nR + nE : 0; }
+};
+__device__ __forceinline__ ItemCuts item_cuts(const RowConst& rc, const EpsDev& eps, const double* __restrict__ ext,
+                                              int i, int k) {
+  ItemCuts c;
+  c.xa = knot_x(ext, rc.E, i, k + 1);
+  c.xb = knot_x(ext, rc.E, i, k);
+  c.r0 = c.nR = c.e0 = c.nE = 0;
+  if (!(c.xb > c.xa)) return c;
+  int r = 0;
+  while (r < rc.nrb && !(rc.rb[r] > c.xa)) ++r;
+  c.r0 = r;
+  while (r < rc.nrb && rc.rb[r] < c.xb) ++r;
+  c.nR = r - c.r0;
+  if (eps.kind == 2) {
+    c.e0 = eps_first_edge_above(eps, c.xa);
+    const int e1 = min(eps_first_edge_ge(eps, c.xb), eps.nx + 1);
+    c.nE = max(0, e1 - c.e0);
   }
-  return count;
+  return c;
+}
+// Merge state after the first t interior cuts have been consumed: ir grading points and ie = t - ir edges.
+__device__ __forceinline__ void cuts_state_at(const ItemCuts& c, const RowConst& rc, const EpsDev& eps, int t, int& ir, int& ie) {
+  int used = 0;                 // grading points whose merged position is below t
+  for (int r = 0; r < c.nR; ++r) {
+    int before = 0;             // edges of E strictly below rb[r] (they precede it; equal ones follow)
+    if (c.nE > 0) before = min(max(eps_first_edge_ge(eps, rc.rb[c.r0 + r]) - c.e0, 0), c.nE);
+    if (r + before < t) ++used; else break;
+  }
+  ir = used;
+  ie = t - used;
+}
+// Emit panels [q0, q1) of the item in ascending x: incremental merge from the state at cut q0 - 1.
+template <typename Emit>
+__device__ __forceinline__ void walk_panels(const ItemCuts& c, const RowConst& rc, const EpsDev& eps, int q0, int q1, Emit emit) {
+  const int count = c.count();
+  if (q0 >= q1 || q0 >= count) return;
+  int ir = 0, ie = 0;
+  double cur = c.xa;
+  if (q0 > 0) {
+    cuts_state_at(c, rc, eps, q0 - 1, ir, ie);       // state before cut number q0 - 1 ...
+    const double nr = ir < c.nR ? rc.rb[c.r0 + ir] : 2.0, ne = ie < c.nE ? eps_edge(eps, c.e0 + ie) : 2.0;
+    if (nr <= ne) { cur = nr; ++ir; } else { cur = ne; ++ie; }   // ... and past it: cur = left edge of panel q0
+  }
+  for (int q = q0; q < q1; ++q) {
+    double nxt = c.xb;
+    if (q < count - 1) {
+      const double nr = ir < c.nR ? rc.rb[c.r0 + ir] : 2.0, ne = ie < c.nE ? eps_edge(eps, c.e0 + ie) : 2.0;
+      if (nr <= ne) { nxt = nr; ++ir; } else { nxt = ne; ++ie; }
+    }
+    emit(q, cur, nxt);
+    cur = nxt;
+  }
 }
 
 __device__ __forceinline__ void item_decode(int idx, int& i, int& k) {
@@ -314,38 +347,127 @@ __device__ __forceinline__ void item_decode(int idx, int& i, int& k) {
   k = idx - r * (r + 1) / 2;
 }
 
-__global__ void count_kernel(int nitems, const RowConst* __restrict__ rows, EpsDev eps,
-                             const double* __restrict__ ext, int* __restrict__ cnt) {
+// Panel count of every item + exclusive scan WITHIN the block (local[]) + the block's total (blocksum[]): the
+// global offsets follow from a scan over the few hundred block totals (blockscan_kernel), so no kernel ever walks
+// all N(N+1)/2 counts serially.
+constexpr int kCountThreads = 256;
+__global__ void __launch_bounds__(kCountThreads)
+count_kernel(int nitems, const RowConst* __restrict__ rows, EpsDev eps, const double* __restrict__ ext,
+             int* __restrict__ cnt, int* __restrict__ local, int* __restrict__ blocksum) {
+  __shared__ int wsum[kCountThreads / 32];
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= nitems) return;
-  int i, k;
-  item_decode(idx, i, k);
-  cnt[idx] = walk_item(rows[i], eps, ext, i, k, [](double, double) {});
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int c = 0;
+  if (idx < nitems) {
+    int i, k;
+    item_decode(idx, i, k);
+    c = item_cuts(rows[i], eps, ext, i, k).count();
+    cnt[idx] = c;
+  }
+  int incl = c;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += u;
+  }
+  if (lane == 31) wsum[w] = incl;
+  __syncthreads();
+  int before = 0;
+#pragma unroll
+  for (int q = 0; q < kCountThreads / 32; ++q) before += q < w ? wsum[q] : 0;
+  if (idx < nitems) local[idx] = before + incl - c;
+  if (threadIdx.x == kCountThreads - 1) blocksum[blockIdx.x] = before + incl;
+}
+// Exclusive scan of the block totals (one block, carry across tiles of 1024) -> blockoff[]; *total = grand total.
+__global__ void __launch_bounds__(1024) blockscan_kernel(int nb, const int* __restrict__ blocksum, int* __restrict__ blockoff,
+                                                          int* __restrict__ total) {
+  __shared__ int wsum[32];
+  __shared__ int carry_s;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  if (t == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < nb; base += 1024) {
+    const int v = base + t < nb ? blocksum[base + t] : 0;
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += u;
+    }
+    if (lane == 31) wsum[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+      int x = wsum[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x += u;
+      }
+      wsum[lane] = x;
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    if (base + t < nb) blockoff[base + t] = carry + (w ? wsum[w - 1] : 0) + incl - v;
+    __syncthreads();
+    if (t == 1023) carry_s = carry + wsum[31];
+    __syncthreads();
+  }
+  if (t == 0) *total = carry_s;
 }
 
-// Single-block exclusive scan of cnt[0..n) into off[0..n], off[n] = total.
+// Single-block exclusive scan of cnt[0..n) into off[0..n], off[n] = total.  Tiles of 8 x 1024 elements go
+// through shared memory: coalesced loads, an 8-element serial scan per thread out of shared memory, a
+// shuffle-based block scan of the 1024 thread totals, coalesced stores (no dependent global-load chains).
+constexpr int kScanPer = 8, kScanTile = kScanPer * 1024;
 __global__ void __launch_bounds__(1024) scan_kernel(int n, const int* __restrict__ cnt, int* __restrict__ off) {
-  __shared__ int part[1024];
-  const int t = threadIdx.x;
-  const int chunk = (n + 1023) / 1024;
-  const int b = t * chunk, e = min(n, b + chunk);
-  int s = 0;
-  for (int q = b; q < e; ++q) s += cnt[q];
-  part[t] = s;
+  __shared__ int tile[kScanTile];
+  __shared__ int wsum[32];
+  __shared__ int carry_s;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  if (t == 0) carry_s = 0;
   __syncthreads();
-  for (int d = 1; d < 1024; d <<= 1) {
-    int v = 0;
-    if (t >= d) v = part[t - d];
+  for (int base = 0; base < n; base += kScanTile) {
+#pragma unroll
+    for (int q = 0; q < kScanPer; ++q) {
+      const int idx = base + q * 1024 + t;
+      tile[q * 1024 + t] = idx < n ? cnt[idx] : 0;
+    }
     __syncthreads();
-    part[t] += v;
+    int v[kScanPer], sum = 0;
+#pragma unroll
+    for (int q = 0; q < kScanPer; ++q) { v[q] = tile[t * kScanPer + q]; sum += v[q]; }
+    int incl = sum;                      // inclusive scan of the thread totals
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += u;
+    }
+    if (lane == 31) wsum[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+      int x = wsum[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x += u;
+      }
+      wsum[lane] = x;                    // inclusive scan of the warp totals
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    int run = carry + (w ? wsum[w - 1] : 0) + incl - sum;   // exclusive prefix of this thread's first element
+#pragma unroll
+    for (int q = 0; q < kScanPer; ++q) { tile[t * kScanPer + q] = run; run += v[q]; }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kScanPer; ++q) {
+      const int idx = base + q * 1024 + t;
+      if (idx < n) off[idx] = tile[q * 1024 + t];
+    }
+    if (t == 1023) carry_s = carry + wsum[31];
     __syncthreads();
   }
-  int run = t ? part[t - 1] : 0;
-  for (int q = b; q < e; ++q) {
-    off[q] = run;
-    run += cnt[q];
-  }
-  if (t == 1023) off[n] = part[1023];
+  if (t == 0) off[n] = carry_s;
 }
 
 int exclusive_scan_int(cudaStream_t st, int n, const int* cnt_dev, int* off_dev) {
@@ -355,30 +477,57 @@ int exclusive_scan_int(cudaStream_t st, int n, const int* cnt_dev, int* off_dev)
 }
 
 // kind: 0 = regular (x), 1 = t = x^beta, 2 = u = (x - x0)^beta
-__global__ void fill_kernel(int nitems, const RowConst* __restrict__ rows, EpsDev eps,
-                            const double* __restrict__ ext, const int* __restrict__ off,
-                            double* __restrict__ pa, double* __restrict__ pb, double* __restrict__ peps,
-                            int* __restrict__ pitem, int* __restrict__ pkind) {
+__device__ __forceinline__ int panel_kind(const RowConst& rc, double b) {
+  if (!(b > rc.x0)) return 1;
+  if (!(b > rc.xin)) return 2;
+  return 0;
+}
+constexpr int kHeavyItem = 32;   // items with more panels than this are filled by a whole warp
+// Thread per item: global offset off[idx] = local prefix + block offset (written for EVERY item), then the item's
+// panels by a serial merge -- one to three for most items.  Items with more than kHeavyItem panels (the wide
+// segments of a row under a finely binned efficiency) are left to fill_heavy_kernel.
+__global__ void __launch_bounds__(kCountThreads)
+fill_kernel(int nitems, const RowConst* __restrict__ rows, EpsDev eps, const double* __restrict__ ext,
+            const int* __restrict__ cnt, const int* __restrict__ local, const int* __restrict__ blockoff, int* __restrict__ off,
+            double* __restrict__ pa, double* __restrict__ pb, int* __restrict__ pitem, int* __restrict__ pkind, int skip_heavy) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nitems) return;
+  const int o = local[idx] + blockoff[blockIdx.x];
+  off[idx] = o;
+  const int count = cnt[idx];
+  if (count == 0 || (skip_heavy && count > kHeavyItem)) return;
   int i, k;
   item_decode(idx, i, k);
   const RowConst& rc = rows[i];
-  int o = off[idx];
-  double scale = 1.0;
-  if (eps.kind == 1) scale = eps.values[i];
-  walk_item(rc, eps, ext, i, k, [&](double a, double b) {
-    double ev = scale;
-    if (eps.kind == 2) ev = eps.values[(size_t)i * (eps.nx + 2) + eps_find_bin(eps, 0.5 * (a + b))];
-    int kind = 0;
-    if (!(b > rc.x0)) kind = 1;
-    else if (!(b > rc.xin)) kind = 2;
-    pa[o] = a;
-    pb[o] = b;
-    peps[o] = ev;
-    pitem[o] = idx;
-    pkind[o] = kind;
-    ++o;
+  const ItemCuts c = item_cuts(rc, eps, ext, i, k);
+  walk_panels(c, rc, eps, 0, count, [&](int q, double a, double b) {
+    pa[o + q] = a;
+    pb[o + q] = b;
+    pitem[o + q] = idx;
+    pkind[o + q] = panel_kind(rc, b);
+  });
+}
+// Warp per item, only for the heavy ones: each lane fills a contiguous run of panels, starting from the merge
+// state selected directly at its first cut.
+__global__ void __launch_bounds__(256)
+fill_heavy_kernel(int nitems, const RowConst* __restrict__ rows, EpsDev eps, const double* __restrict__ ext,
+                  const int* __restrict__ cnt, const int* __restrict__ off, double* __restrict__ pa, double* __restrict__ pb,
+                  int* __restrict__ pitem, int* __restrict__ pkind) {
+  const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (idx >= nitems) return;
+  const int count = cnt[idx];
+  if (count <= kHeavyItem) return;
+  int i, k;
+  item_decode(idx, i, k);
+  const RowConst& rc = rows[i];
+  const ItemCuts c = item_cuts(rc, eps, ext, i, k);
+  const int o = off[idx], per = (count + 31) / 32;
+  walk_panels(c, rc, eps, lane * per, min(count, (lane + 1) * per), [&](int q, double a, double b) {
+    pa[o + q] = a;
+    pb[o + q] = b;
+    pitem[o + q] = idx;
+    pkind[o + q] = panel_kind(rc, b);
   });
 }
 
@@ -426,9 +575,9 @@ __device__ __forceinline__ PanelNode panel_node(const RowConst& rc, double a, do
 
 // node_eps != nullptr: efficiency sampled by the host at every node (ISR_EPS_SAMPLED), [npanels][kQ]
 __global__ void __launch_bounds__(kEvalThreads)
-eval_kernel(const int* __restrict__ off_total, const RowConst* __restrict__ rows,
+eval_kernel(const int* __restrict__ off_total, const RowConst* __restrict__ rows, EpsDev eps,
             const double* __restrict__ ext, const double* __restrict__ invh,
-            const double* __restrict__ pa, const double* __restrict__ pb, const double* __restrict__ peps,
+            const double* __restrict__ pa, const double* __restrict__ pb, double* __restrict__ peps,
             const int* __restrict__ pitem, const int* __restrict__ pkind, const double* __restrict__ node_eps,
             double* __restrict__ pm) {
   __shared__ double s_x[kQ], s_w[kQ];
@@ -445,12 +594,16 @@ eval_kernel(const int* __restrict__ off_total, const RowConst* __restrict__ rows
   const double t = s_x[lane], w = s_w[lane];
   for (int pidx = group; pidx < npanels; pidx += ngroups) {
     const double a = pa[pidx], b = pb[pidx];
-    double ev = peps[pidx];
-    if (node_eps) ev = node_eps[(size_t)pidx * kQ + lane];
     const int item = pitem[pidx], kind = pkind[pidx];
     int i, k;
     item_decode(item, i, k);
     const RowConst& rc = rows[i];
+    // efficiency: constant on a panel (ROOT bin of its midpoint / the row's scale), or sampled per node by the host
+    double ev = 1.0;
+    if (eps.kind == 2) ev = eps.values[(size_t)i * (eps.nx + 2) + eps_find_bin(eps, 0.5 * (a + b))];
+    else if (eps.kind == 1) ev = eps.values[i];
+    if (lane == 0) peps[pidx] = ev;      // kept for isr_debug_panels
+    if (node_eps) ev = node_eps[(size_t)pidx * kQ + lane];
     const PanelNode q = panel_node(rc, a, b, kind, t, w);
     const double x = q.x;
     const double f = kf_value(rc, x, q.lnx, q.pw) * q.wj * ev;
@@ -486,78 +639,110 @@ nodes_kernel(const int* __restrict__ off_total, const RowConst* __restrict__ row
   node_row[(size_t)pidx * kQ + lane] = i;
 }
 
-// Sum the panels of each item in panel order (deterministic) into M[i][k][0..3]; zero for k > i.
-__global__ void reduce_kernel(int n, const int* __restrict__ off, const double* __restrict__ pm,
-                              double* __restrict__ M) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over n*n (i,k)
+// M[i][k][0..3] = sum of the item's panel moments; zero for k > i.  One warp per (i, k): lanes stride over the
+// panels, fixed xor tree => deterministic whatever the panel count.
+__global__ void __launch_bounds__(256) reduce_kernel(int n, const int* __restrict__ off, const double* __restrict__ pm,
+                                                      double* __restrict__ M) {
+  const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // over n*n (i,k)
+  const int lane = threadIdx.x & 31;
   if (idx >= n * n) return;
   const int i = idx / n, k = idx % n;
   double4 acc = make_double4(0, 0, 0, 0);
   if (k <= i) {
     const int item = i * (i + 1) / 2 + k;
-    for (int q = off[item]; q < off[item + 1]; ++q) {
+    for (int q = off[item] + lane; q < off[item + 1]; q += 32) {
       const double4 v = reinterpret_cast<const double4*>(pm)[q];
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, s);
+      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, s);
+      acc.z += __shfl_xor_sync(0xffffffffu, acc.z, s);
+      acc.w += __shfl_xor_sync(0xffffffffu, acc.w, s);
+    }
   }
-  reinterpret_cast<double4*>(M)[idx] = acc;
+  if (lane == 0) reinterpret_cast<double4*>(M)[idx] = acc;
 }
 
-// G(i,j) = sum_{k = klo_j}^{min(khi_j, i)} sum_p M[i][k][p] * Ct[k][p][j]   (column-major output).
-// Tile: 16 rows x 64 columns per block; M rows staged through shared memory in chunks of 32 segments.
-// The segment range is split over blockIdx.z (kCtSplit slices, partial sums combined in fixed order by
-// contract_sum_kernel) so that even N = 200 fills the machine.
-constexpr int kCtRows = 16, kCtCols = 64, kCtK = 32, kCtSplit = 4;
+// G(i,j) = sum_{k = klo_j}^{min(khi_j, i)} sum_p M[i][k][p] * Ct[k][p][j]   (column-major output), with the panel
+// reduction fused in: M[i][k][p] = sum of the item's panel moments pm[q][p], q in [off[item], off[item+1]) in panel
+// order (deterministic).  One block = 16 rows x 64 columns, 256 threads (thread = column x 4 rows).  Segments are
+// processed in chunks of 16: the chunk's moments (16 x 64 doubles) and coefficients (64 x 64 doubles) are staged in
+// shared memory with independent coalesced loads, then a fully unrolled 64-deep FMA loop runs out of shared memory
+// (Ct is zero outside a column's band, so no per-column bounds are needed inside the chunk).  Only the segment range
+// the block's columns actually touch ([min klo, min(max khi, last row)]) is visited: a purely linear matrix costs two
+// chunks per block, a cubic one N/16 -- split over blockIdx.z (kCtSplit slices of the segment range, partial sums
+// combined in fixed order by contract_sum_kernel) so that N = 200 still fills the machine.
+constexpr int kCtRows = 16, kCtCols = 64, kCtK = 16, kCtSplit = 4;
+// FUSED = false: the moments were reduced beforehand by reduce_kernel into pm = M[i][k][4] (tabulated efficiencies:
+// dozens of panels per item, which every column tile would otherwise re-reduce).
+template <bool FUSED>
 __global__ void __launch_bounds__(256)
-contract_kernel(int n, const double* __restrict__ M, const double* __restrict__ Ct,
-                const int* __restrict__ klo, const int* __restrict__ khi, double* __restrict__ Gpart) {
+contract_kernel(int n, const int* __restrict__ off, const double* __restrict__ pm, const double* __restrict__ Ct,
+                const int* __restrict__ klo, const int* __restrict__ khi, double* __restrict__ G) {
   __shared__ double sM[kCtRows][kCtK * 4];
-  const int j = blockIdx.x * kCtCols + (threadIdx.x & (kCtCols - 1));
+  __shared__ double sC[kCtK * 4][kCtCols];
+  __shared__ int s_lo, s_hi;
+  const int tx = threadIdx.x & (kCtCols - 1);
+  const int j = blockIdx.x * kCtCols + tx;
   const int rsub = threadIdx.x / kCtCols;  // 0..3, each thread does 4 rows
   const int i0 = blockIdx.y * kCtRows;
   const int imax = min(n - 1, i0 + kCtRows - 1);
-  const int jl = j < n ? klo[j] : n, jh = j < n ? khi[j] : -1;
-  __shared__ int s_lo, s_hi;
   if (threadIdx.x == 0) { s_lo = n; s_hi = -1; }
   __syncthreads();
-  if (j < n) { atomicMin(&s_lo, jl); atomicMax(&s_hi, jh); }
+  if (j < n) { atomicMin(&s_lo, klo[j]); atomicMax(&s_hi, khi[j]); }
   __syncthreads();
-  // this block's slice of the block-wide segment range [blo, bhi]
+  // this block's slice of the block-wide segment range, in whole chunks
   int blo = s_lo, bhi = min(s_hi, imax);
   {
-    const int len = max(0, bhi - blo + 1), per = (len + kCtSplit - 1) / kCtSplit;
-    const int a = blo + (int)blockIdx.z * per;
-    bhi = min(bhi, a + per - 1);
+    const int nchunks = bhi >= blo ? (bhi - blo) / kCtK + 1 : 0, per = (nchunks + kCtSplit - 1) / kCtSplit;
+    const int a = blo + (int)blockIdx.z * per * kCtK;
+    bhi = min(bhi, a + per * kCtK - 1);
     blo = a;
   }
   double acc[4] = {0, 0, 0, 0};
   for (int k0 = blo; k0 <= bhi; k0 += kCtK) {
     __syncthreads();
-    for (int q = threadIdx.x; q < kCtRows * kCtK * 4; q += 256) {
-      const int r = q / (kCtK * 4), c = q % (kCtK * 4);
-      const int i = i0 + r, k = k0 + c / 4;
-      sM[r][c] = (i < n && k <= bhi) ? M[((size_t)i * n + k) * 4 + (c & 3)] : 0.0;
-    }
-    __syncthreads();
-    if (j < n) {
-      const int ke = min(k0 + kCtK - 1, min(jh, bhi));
-      for (int k = max(k0, jl); k <= ke; ++k) {
-        const double c0 = Ct[((size_t)k * 4 + 0) * n + j], c1 = Ct[((size_t)k * 4 + 1) * n + j];
-        const double c2 = Ct[((size_t)k * 4 + 2) * n + j], c3 = Ct[((size_t)k * 4 + 3) * n + j];
-        const int c = (k - k0) * 4;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const double* m = &sM[rsub * 4 + r][c];   // M is zero for k > i
-          acc[r] = fma(m[0], c0, fma(m[1], c1, fma(m[2], c2, fma(m[3], c3, acc[r]))));
+    // moments of (row, segment) pairs of this chunk: 16 rows x 16 segments, one thread each
+    {
+      const int r = threadIdx.x / kCtK, kk = threadIdx.x % kCtK;
+      const int i = i0 + r, k = k0 + kk;
+      double4 m = make_double4(0, 0, 0, 0);
+      if (i < n && k <= i && k <= bhi) {
+        if (FUSED) {
+          const int item = i * (i + 1) / 2 + k;
+          for (int q = off[item]; q < off[item + 1]; ++q) {
+            const double4 v = reinterpret_cast<const double4*>(pm)[q];
+            m.x += v.x; m.y += v.y; m.z += v.z; m.w += v.w;
+          }
+        } else {
+          m = reinterpret_cast<const double4*>(pm)[(size_t)i * n + k];
         }
       }
+      sM[r][kk * 4 + 0] = m.x; sM[r][kk * 4 + 1] = m.y; sM[r][kk * 4 + 2] = m.z; sM[r][kk * 4 + 3] = m.w;
+    }
+    // coefficients: rows q = (k - k0) * 4 + p of Ct, 64 columns (coalesced along j)
+#pragma unroll
+    for (int it = 0; it < (kCtK * 4 * kCtCols) / 256; ++it) {
+      const int e = it * 256 + threadIdx.x;
+      const int q = e / kCtCols, c = e % kCtCols;
+      const int k = k0 + q / 4, jj = blockIdx.x * kCtCols + c;
+      sC[q][c] = (k <= bhi && jj < n) ? Ct[((size_t)k * 4 + (q & 3)) * n + jj] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 16
+    for (int q = 0; q < kCtK * 4; ++q) {
+      const double cv = sC[q][tx];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r] = fma(sM[rsub * 4 + r][q], cv, acc[r]);
     }
   }
   if (j < n) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int i = i0 + rsub * 4 + r;
-      if (i < n) Gpart[(size_t)blockIdx.z * n * n + (size_t)i + (size_t)n * j] = acc[r];
+      if (i < n) G[(size_t)blockIdx.z * n * n + (size_t)i + (size_t)n * j] = acc[r];
     }
   }
 }
@@ -665,6 +850,16 @@ static int64_t panel_upper_bound(const isr_problem* p) {
   return n * (n + 1) / 2 + n * per_row_extra;
 }
 
+// Per-(row, segment) moments M[i][k][4] = sum of the item's panel moments: used when items have many panels (tabulated
+// efficiency) and by isr_debug_moments; otherwise the contraction sums the panels on the fly.
+int reduce_moments(isr_problem* p) {
+  const int n = p->n;
+  ISR_TRY(p->d_M.reserve((size_t)n * n * 4));
+  reduce_kernel<<<(n * n + 7) / 8, 256, 0, p->ctx->stream>>>(n, p->d_off.p, p->d_pm.p, p->d_M.p); ISR_COUNT_LAUNCH();
+  ISR_CUDA(cudaGetLastError());
+  return ISR_OK;
+}
+
 // Panel enumeration (row constants, count, scan, fill): everything before the integrand is touched.
 static int enumerate_panels(isr_problem* p) {
   const int n = p->n;
@@ -680,14 +875,23 @@ static int enumerate_panels(isr_problem* p) {
     ISR_TRY(p->d_pm.reserve(cap * 4));
     p->max_panels = cap;
   }
+  const int nb = (nitems + kCountThreads - 1) / kCountThreads;
   ISR_TRY(p->d_row.reserve(n));
   ISR_TRY(p->d_cnt.reserve(nitems));
   ISR_TRY(p->d_off.reserve(nitems + 1));
+  ISR_TRY(p->d_local.reserve(nitems));
+  ISR_TRY(p->d_blocksum.reserve(nb));
+  ISR_TRY(p->d_blockoff.reserve(nb));
   row_setup_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, p->d_ext.p, p->d_row.p); ISR_COUNT_LAUNCH();
-  count_kernel<<<(nitems + 127) / 128, 128, 0, st>>>(nitems, p->d_row.p, p->eps, p->d_ext.p, p->d_cnt.p); ISR_COUNT_LAUNCH();
-  scan_kernel<<<1, 1024, 0, st>>>(nitems, p->d_cnt.p, p->d_off.p); ISR_COUNT_LAUNCH();
-  fill_kernel<<<(nitems + 127) / 128, 128, 0, st>>>(nitems, p->d_row.p, p->eps, p->d_ext.p, p->d_off.p,
-                                                      p->d_pa.p, p->d_pb.p, p->d_peps.p, p->d_pitem.p, p->d_pkind.p); ISR_COUNT_LAUNCH();
+  count_kernel<<<nb, kCountThreads, 0, st>>>(nitems, p->d_row.p, p->eps, p->d_ext.p, p->d_cnt.p, p->d_local.p, p->d_blocksum.p); ISR_COUNT_LAUNCH();
+  blockscan_kernel<<<1, 1024, 0, st>>>(nb, p->d_blocksum.p, p->d_blockoff.p, p->d_off.p + nitems); ISR_COUNT_LAUNCH();
+  const int heavy = p->eps.kind == 2;     // only a tabulated efficiency can give an item more than 1 + kMaxRowBreaks panels
+  fill_kernel<<<nb, kCountThreads, 0, st>>>(nitems, p->d_row.p, p->eps, p->d_ext.p, p->d_cnt.p, p->d_local.p, p->d_blockoff.p,
+                                            p->d_off.p, p->d_pa.p, p->d_pb.p, p->d_pitem.p, p->d_pkind.p, heavy); ISR_COUNT_LAUNCH();
+  if (heavy) {
+    fill_heavy_kernel<<<(nitems + 7) / 8, 256, 0, st>>>(nitems, p->d_row.p, p->eps, p->d_ext.p, p->d_cnt.p, p->d_off.p,
+                                                        p->d_pa.p, p->d_pb.p, p->d_pitem.p, p->d_pkind.p); ISR_COUNT_LAUNCH();
+  }
   ISR_CUDA(cudaGetLastError());
   return ISR_OK;
 }
@@ -697,16 +901,19 @@ static int finish_assembly(isr_problem* p, const double* ecm_err, const double* 
   const int n = p->n;
   cudaStream_t st = p->ctx->stream;
   const int nitems = n * (n + 1) / 2;
-  ISR_TRY(p->d_M.reserve((size_t)n * n * 4));
   ISR_TRY(p->d_G.reserve((size_t)n * n));
   ISR_TRY(p->d_Gpart.reserve((size_t)kCtSplit * n * n));
   const int eval_blocks = p->ctx->sm_count * 8;
-  eval_kernel<<<eval_blocks, kEvalThreads, 0, st>>>(p->d_off.p + nitems, p->d_row.p, p->d_ext.p, p->d_invh.p,
+  eval_kernel<<<eval_blocks, kEvalThreads, 0, st>>>(p->d_off.p + nitems, p->d_row.p, p->eps, p->d_ext.p, p->d_invh.p,
                                                      p->d_pa.p, p->d_pb.p, p->d_peps.p, p->d_pitem.p,
                                                      p->d_pkind.p, node_eps_dev, p->d_pm.p); ISR_COUNT_LAUNCH();
-  reduce_kernel<<<(n * n + 127) / 128, 128, 0, st>>>(n, p->d_off.p, p->d_pm.p, p->d_M.p); ISR_COUNT_LAUNCH();
   dim3 cgrid((n + kCtCols - 1) / kCtCols, (n + kCtRows - 1) / kCtRows, kCtSplit);
-  contract_kernel<<<cgrid, 256, 0, st>>>(n, p->d_M.p, p->d_Ct.p, p->d_klo.p, p->d_khi.p, p->d_Gpart.p); ISR_COUNT_LAUNCH();
+  if (p->eps.kind == 2) {   // many panels per item: reduce once, then contract
+    ISR_TRY(reduce_moments(p));
+    contract_kernel<false><<<cgrid, 256, 0, st>>>(n, p->d_off.p, p->d_M.p, p->d_Ct.p, p->d_klo.p, p->d_khi.p, p->d_Gpart.p); ISR_COUNT_LAUNCH();
+  } else {
+    contract_kernel<true><<<cgrid, 256, 0, st>>>(n, p->d_off.p, p->d_pm.p, p->d_Ct.p, p->d_klo.p, p->d_khi.p, p->d_Gpart.p); ISR_COUNT_LAUNCH();
+  }
   contract_sum_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(n * n, p->d_Gpart.p, p->d_G.p); ISR_COUNT_LAUNCH();
   if (ecm_err) {
     for (int i = 0; i < n; ++i)

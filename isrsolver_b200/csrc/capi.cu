@@ -196,8 +196,9 @@ int isr_debug_panels(isr_problem* p, int64_t cap, double* abek, int* row_seg, in
 
 int isr_debug_moments(isr_problem* p, double* M_out) {
   if (!p || !M_out) { set_error("NULL argument"); return ISR_EINVAL; }
-  if (!p->has_G || !p->d_M.p) { set_error("isr_debug_moments: no assembly yet"); return ISR_ESTATE; }
+  if (!p->has_G || p->G_injected || !p->d_pm.p) { set_error("isr_debug_moments: no assembly yet"); return ISR_ESTATE; }
   ISR_CUDA(cudaSetDevice(p->ctx->device));
+  ISR_TRY(reduce_moments(p));
   ISR_CUDA(cudaMemcpyAsync(M_out, p->d_M.p, sizeof(double) * p->n * p->n * 4, cudaMemcpyDeviceToHost, p->ctx->stream));
   ISR_CUDA(cudaStreamSynchronize(p->ctx->stream));
   return ISR_OK;

@@ -81,4 +81,11 @@ __device__ __forceinline__ int eps_first_edge_above(const EpsDev& e, double v) {
   return m;
 }
 
+// smallest edge index m in [0, nx] with edge(m) >= v, or nx+1
+__device__ __forceinline__ int eps_first_edge_ge(const EpsDev& e, double v) {
+  int m = eps_first_edge_above(e, v);          // edge(m) > v, edge(m-1) <= v
+  if (m > 0 && eps_edge(e, m - 1) == v) --m;   // an edge exactly at v
+  return m;
+}
+
 }  // namespace isr

@@ -26,9 +26,10 @@ struct isr_problem {
   isr::DevBuf<isr::RowConst> d_row;
   isr::DevBuf<int> d_cnt;        // panels per (row, segment) item, then exclusive scan (+1 entry)
   isr::DevBuf<int> d_off;
+  isr::DevBuf<int> d_local, d_blocksum, d_blockoff;   // block-local prefixes and block totals / offsets of the panel counts
   isr::DevBuf<double> d_pa, d_pb, d_peps, d_pm;  // panel bounds, eps value, 4 moments per panel
   isr::DevBuf<int> d_pitem, d_pkind;
-  isr::DevBuf<double> d_M;       // [i][k][4] normalised moments
+  isr::DevBuf<double> d_M;       // [i][k][4] normalised moments (filled on demand by isr_debug_moments)
   isr::DevBuf<double> d_G;       // column-major N x N
   isr::DevBuf<double> d_Gpart;   // split-K partials of the contraction
   isr::DevBuf<double> d_S, d_tmp, d_sigE;
@@ -98,6 +99,7 @@ int build_eps_rows(cudaStream_t st, int n, const double* energy, const isr_eps_d
                    DevBuf<double>& d_edges, EpsDev& out);
 int exclusive_scan_int(cudaStream_t st, int n, const int* cnt_dev, int* off_dev);   // off[n] = total
 int assemble(isr_problem* p, const double* ecm_err);
+int reduce_moments(isr_problem* p);
 int assemble_nodes(isr_problem* p, int64_t cap, double* x_out, int* row_out, int64_t* count);
 int assemble_sampled(isr_problem* p, int64_t nn, const double* eps_values, const double* ecm_err);
 int apply_spread(isr_problem* p, cudaStream_t st, const double* sigE_dev, const double* G0, double* S, double* Gout);
