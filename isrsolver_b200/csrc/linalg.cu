@@ -76,17 +76,61 @@ static int check_info(isr_ctx* c, const int* d_info, const char* what) {
   return ISR_OK;
 }
 
-// Ainv = A^-1 by LU with partial pivoting (A is destroyed).
-int lu_inverse(isr_ctx* c, int n, double* A, double* Ainv, DevBuf<double>& work, DevBuf<int>& ipiv, DevBuf<int>& info) {
+// out[0] = max |(A X)(i, j) - delta_ij| over the n x n product P = A X (column-major): one block, fixed order.
+__global__ void __launch_bounds__(1024) inverse_residual_kernel(int n, const double* __restrict__ P, double* __restrict__ out) {
+  __shared__ double smax[32];
+  double m = 0.0;
+  for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+    const double v = P[idx] - ((idx / n == idx % n) ? 1.0 : 0.0);
+    m = fmax(m, fabs(v));          // NaN-safe below: a NaN product fails the !(r <= tol) test on the host
+    if (v != v) m = INFINITY;
+  }
+  for (int s = 16; s >= 1; s >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, s));
+  if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = smax[threadIdx.x];
+    for (int s = 16; s >= 1; s >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, s));
+    if (threadIdx.x == 0) out[0] = m;
+  }
+}
+
+// Ainv = A^-1.  A (column-major, preserved) is factored in `lu` (n x n scratch, destroyed); `prod` is n x n scratch.
+//
+// cuSOLVER's LU without pivoting is about twice as fast as the pivoted one at these sizes (N = 200: 0.26 vs 0.56 ms,
+// tools/inv_probe.cu) because the pivot search and row swaps serialise its single-CTA panel kernel.  The operator
+// matrices of this problem are lower-triangular-dominated and need no row exchanges, but nothing guarantees that for
+// an injected or ill-conditioned matrix, so the fast path is CERTIFIED a posteriori: X is accepted only if
+// max |A X - I| <= 1e-12 n (then |X - A^-1| <= |A^-1| |A X - I|, i.e. 2e-10 relative at N = 200, typically 1e-13);
+// otherwise -- zero pivot, growth, NaN -- the partially pivoted factorisation is used, exactly as before.
+int lu_inverse(isr_ctx* c, int n, const double* A, double* lu, double* prod, double* Ainv, DevBuf<double>& work,
+               DevBuf<int>& ipiv, DevBuf<int>& info) {
   int lwork = 0;
-  ISR_CUSOLVER(cusolverDnDgetrf_bufferSize(c->solver, n, n, A, n, &lwork));
-  ISR_TRY(work.reserve(lwork));
+  const size_t bytes = sizeof(double) * (size_t)n * n;
+  ISR_CUSOLVER(cusolverDnDgetrf_bufferSize(c->solver, n, n, lu, n, &lwork));
+  ISR_TRY(work.reserve((size_t)lwork + 1));      // +1: the residual scalar lives behind the LAPACK workspace
   ISR_TRY(ipiv.reserve(n));
-  ISR_TRY(info.reserve(1));
-  ISR_CUSOLVER(cusolverDnDgetrf(c->solver, n, n, A, n, work.p, ipiv.p, info.p));
+  ISR_TRY(info.reserve(2));
+  double* resid_dev = work.p + lwork;
+  // ---- fast path: no pivoting, certified by the residual
+  ISR_CUDA(cudaMemcpyAsync(lu, A, bytes, cudaMemcpyDeviceToDevice, c->stream));
+  ISR_CUSOLVER(cusolverDnDgetrf(c->solver, n, n, lu, n, work.p, nullptr, info.p));
+  set_identity_kernel<<<(n * n + 255) / 256, 256, 0, c->stream>>>(n, Ainv); ISR_COUNT_LAUNCH();
+  ISR_CUSOLVER(cusolverDnDgetrs(c->solver, CUBLAS_OP_N, n, n, lu, n, nullptr, Ainv, n, info.p + 1));
+  ISR_TRY(gemm(c, false, false, n, A, Ainv, prod));
+  inverse_residual_kernel<<<1, 1024, 0, c->stream>>>(n, prod, resid_dev); ISR_COUNT_LAUNCH();
+  int h_info[2] = {0, 0};
+  double resid = INFINITY;
+  ISR_CUDA(cudaMemcpyAsync(h_info, info.p, sizeof(int) * 2, cudaMemcpyDeviceToHost, c->stream));
+  ISR_CUDA(cudaMemcpyAsync(&resid, resid_dev, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  ISR_CUDA(cudaStreamSynchronize(c->stream));
+  if (h_info[0] == 0 && h_info[1] == 0 && resid <= 1e-12 * n) return ISR_OK;
+  // ---- certified path failed: LU with partial pivoting
+  ISR_CUDA(cudaMemcpyAsync(lu, A, bytes, cudaMemcpyDeviceToDevice, c->stream));
+  ISR_CUSOLVER(cusolverDnDgetrf(c->solver, n, n, lu, n, work.p, ipiv.p, info.p));
   ISR_TRY(check_info(c, info.p, "LU factorisation (getrf)"));
   set_identity_kernel<<<(n * n + 255) / 256, 256, 0, c->stream>>>(n, Ainv); ISR_COUNT_LAUNCH();
-  ISR_CUSOLVER(cusolverDnDgetrs(c->solver, CUBLAS_OP_N, n, n, A, n, ipiv.p, Ainv, n, info.p));
+  ISR_CUSOLVER(cusolverDnDgetrs(c->solver, CUBLAS_OP_N, n, n, lu, n, ipiv.p, Ainv, n, info.p));
   ISR_TRY(check_info(c, info.p, "LU solve (getrs)"));
   return ISR_OK;
 }

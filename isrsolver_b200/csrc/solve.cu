@@ -35,8 +35,8 @@ int factor(isr_problem* p, const double* vcs_err) {
   ISR_TRY(p->d_Rop.reserve((size_t)n * ld));
   p->vcs_err.assign(vcs_err, vcs_err + n);
   ISR_CUDA(cudaMemcpyAsync(p->d_werr.p, vcs_err, sizeof(double) * n, cudaMemcpyHostToDevice, st));
-  ISR_CUDA(cudaMemcpyAsync(p->d_tmp.p, p->d_G.p, sizeof(double) * nn, cudaMemcpyDeviceToDevice, st));
-  ISR_TRY(lu_inverse(c, n, p->d_tmp.p, p->d_Ginv.p, p->d_work, p->d_ipiv, p->d_info));
+  ISR_TRY(p->d_tmp2.reserve(nn));
+  ISR_TRY(lu_inverse(c, n, p->d_G.p, p->d_tmp.p, p->d_tmp2.p, p->d_Ginv.p, p->d_work, p->d_ipiv, p->d_info));
   scale_rows(st, n, p->d_G.p, p->d_werr.p, 1, p->d_R.p);                  // R = diag(1/err) G
   ISR_CUDA(cudaGetLastError());
   p->factored = true;

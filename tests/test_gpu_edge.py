@@ -126,3 +126,36 @@ def test_tikhonov_and_tsvd_minimal_and_odd(oracle):
         v = isr.ISRSolverTSVD(n, ecm, vcs, None, err, THR, upper_TSVD_index=max(1, n - 1))
         v.solve()
         np.testing.assert_allclose(v.bcs(), oracle.tsvd_solve(G, vcs, err, max(1, n - 1))[0], rtol=1e-6, atol=1e-9)
+
+
+def test_factor_falls_back_to_pivoting_and_rejects_singular(oracle):
+    """isr_factor tries cuSOLVER's LU without pivoting first and accepts it only if max |G X - I| is tiny; matrices
+    that need row exchanges (zero or tiny leading pivots), or are badly conditioned, must come out right through
+    the pivoted path, and a singular matrix must be reported."""
+    import isrsolver_b200 as isr
+    from isrsolver_b200 import IsrGpuError
+    rng = np.random.default_rng(12)
+    n = 23
+    ecm = np.linspace(1.0, 2.0, n)
+    cases = {
+        "zero leading pivot": np.roll(np.eye(n), 1, axis=0) * 2.0 + 0.01 * rng.random((n, n)),
+        "tiny pivots (growth without exchanges)": np.triu(rng.random((n, n)), 1) + np.diag(np.full(n, 1e-9)) + np.tril(rng.random((n, n)), -1),
+        "ill-conditioned (cond 1e9)": (lambda u, v: u @ np.diag(np.geomspace(1, 1e-9, n)) @ v)(*[np.linalg.qr(rng.random((n, n)))[0] for _ in range(2)]),
+        "well conditioned dense": np.eye(n) * 3 + rng.random((n, n)),
+    }
+    for name, G in cases.items():
+        s = isr.ISRSolverSLE(n, ecm, np.ones(n), None, np.ones(n), THR)
+        s.set_matrix(G)
+        b0 = 1.0 + rng.random(n); vcs = G @ b0; err = 0.05 * np.abs(vcs) + 1e-3
+        s.resetVisibleCS(vcs); s.resetVisibleCSErrors(err)
+        s.solve()
+        cond = np.linalg.cond(G)
+        np.testing.assert_allclose(s.bcs(), b0, rtol=1e-13 * cond + 1e-9, atol=1e-12 * cond, err_msg=name)
+        V = oracle.draw_toys(vcs, err, 64)
+        r = s.toy_batch(V, b0, want_bcs=True)
+        np.testing.assert_allclose(r["bcs"], np.linalg.solve(G, V.T).T, rtol=1e-12 * cond + 1e-8, atol=1e-11 * cond, err_msg=name)
+    s = isr.ISRSolverSLE(n, ecm, np.ones(n), None, np.ones(n), THR)
+    G = rng.random((n, n)); G[5] = G[3]               # exactly singular
+    s.set_matrix(G)
+    with pytest.raises(IsrGpuError):
+        s.solve()

@@ -41,6 +41,18 @@ int main() {
     }
     cudaEventRecord(e1, st); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms2, e0, e1); ms2 /= 10;
     std::vector<double> r2((size_t)n * n); CK(cudaMemcpy(r2.data(), C, sizeof(double) * n * n, cudaMemcpyDeviceToHost));
+    float ms3 = 0;
+    for (int rep = 0; rep < 12; ++rep) {
+      if (rep == 2) cudaEventRecord(e0, st);
+      CK(cudaMemcpyAsync(B, A, sizeof(double) * n * n, cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(C, I, sizeof(double) * n * n, cudaMemcpyDeviceToDevice, st));
+      CK(cusolverDnDgetrf(sh, n, n, B, n, work, nullptr, info));                 // no pivoting
+      CK(cusolverDnDgetrs(sh, CUBLAS_OP_N, n, n, B, n, nullptr, C, n, info));
+    }
+    cudaEventRecord(e1, st); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms3, e0, e1); ms3 /= 10;
+    std::vector<double> r3((size_t)n * n); CK(cudaMemcpy(r3.data(), C, sizeof(double) * n * n, cudaMemcpyDeviceToHost));
+    double d3 = 0; for (size_t q = 0; q < r1.size(); ++q) d3 = fmax(d3, fabs(r1[q] - r3[q]));
+    printf("n=%d  cusolver getrf+getrs WITHOUT pivoting %.3f ms  max|diff| %.2e\n", n, ms3, d3);
     double d = 0, s = 0; for (size_t q = 0; q < r1.size(); ++q) { d = fmax(d, fabs(r1[q] - r2[q])); s = fmax(s, fabs(r1[q])); }
     printf("n=%d  cusolver getrf+getrs %.3f ms   cublas getrfBatched+getriBatched %.3f ms   max|diff|/max %.2e\n", n, ms1, ms2, d / s);
   }
