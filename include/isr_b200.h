@@ -111,6 +111,10 @@ int isr_interp_eval(isr_problem* p, const double* y, int64_t n, const double* en
 int isr_factor(isr_problem* p, const double* vcs_err);
 /* ISRSolverSLE::solve: bcs = G^-1 vcs; cov_out (N*N col-major) may be NULL. */
 int isr_solve(isr_problem* p, const double* vcs, double* bcs_out, double* cov_out);
+/* IterISRInterpSolver::solve (src/IterISRInterpSolver.cpp:45-57) on the assembled operator: b <- vcs, then niter
+ * times  radcorr = (G b) / b,  b <- vcs / radcorr.  radcorr_out (N) may be NULL; the covariance of that method is
+ * diag((vcs_err / radcorr)^2), formed by the caller. */
+int isr_iterative_solve(isr_problem* p, int niter, const double* vcs, double* bcs_out, double* radcorr_out);
 int isr_get_inverse(isr_problem* p, double* Ginv_out);         /* column-major */
 int isr_get_inv_cov(isr_problem* p, double* inv_cov_out);      /* G^T W G, column-major */
 /* ISRSolverSLE::evalConditionNumber (src/ISRSolverSLE.cpp:200-204) */

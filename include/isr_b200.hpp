@@ -205,6 +205,33 @@ class ISRSolverSLE : public BaseISRSolver {   // include/ISRSolverSLE.hpp
   Matrix _integralOperatorMatrix, _covMatrixBornCS;
 };
 
+// IterISRInterpSolver (include/IterISRInterpSolver.hpp; src/IterISRInterpSolver.cpp:45-65): the iterative
+// radiative-correction method on the same operator matrix; Cov = diag((vcsErr / radcorr)^2).
+class IterISRInterpSolver : public ISRSolverSLE {
+ public:
+  using ISRSolverSLE::ISRSolverSLE;
+  void setNumOfIters(std::size_t n) { _nIter = n; }
+  std::size_t getNumOfIters() const { return _nIter; }
+  const std::vector<double>& getRadCorr() const { return _radcorr; }
+  void solve() override {
+    if (!_isEqMatrixPrepared) evalEqMatrix();
+    _radcorr.assign(_n, 0.0);
+    check(isr_iterative_solve(_p, (int)_nIter, _vcs.data(), _bcs.data(), _radcorr.data()));
+    _covMatrixBornCS = Matrix((int)_n, (int)_n);
+    if (_nIter > 0)
+      for (std::size_t i = 0; i < _n; ++i) _covMatrixBornCS((int)i, (int)i) = (_vcsErr[i] / _radcorr[i]) * (_vcsErr[i] / _radcorr[i]);
+  }
+  Matrix evalBornCSInvCovMatrix() override {
+    Matrix m((int)_n, (int)_n);
+    for (std::size_t i = 0; i < _n; ++i) m((int)i, (int)i) = 1.0 / _covMatrixBornCS((int)i, (int)i);
+    return m;
+  }
+
+ private:
+  std::size_t _nIter = 10;   // src/IterISRInterpSolver.cpp:19
+  std::vector<double> _radcorr;
+};
+
 // ISRSolverSLE2 (include/ISRSolverSLE2.hpp; src/BaseISRSolver2.cpp:151-160, 231-236): the efficiency is one
 // x-histogram per energy point, effHists[point][0..nbins+1] with ROOT's under/overflow cells.
 class ISRSolverSLE2 : public ISRSolverSLE {

@@ -7,9 +7,9 @@ solver or kernel call does, and fails loudly if it is not built or no B200 is vi
 """
 from .pyisr import (DifferentModelCrossSectionSizes, Efficiency, EfficiencyDimensionException,  # noqa: F401
                     InterpRangeException, IsrGpuError, ISRSolverSLE, ISRSolverSLE2, ISRSolverTikhonov,
-                    ISRSolverTSVD, ConvolutionPlan, convolutionKuraevFadin, convolutionKuraevFadinBlurred,
+                    ISRSolverTSVD, IterISRInterpSolver, ConvolutionPlan, convolutionKuraevFadin, convolutionKuraevFadinBlurred,
                     draw_toys, draw_toys_device, kernelKuraevFadin)
 
-__all__ = ["ISRSolverSLE", "ISRSolverSLE2", "ISRSolverTikhonov", "ISRSolverTSVD", "Efficiency",
+__all__ = ["ISRSolverSLE", "ISRSolverSLE2", "ISRSolverTikhonov", "ISRSolverTSVD", "IterISRInterpSolver", "Efficiency",
            "kernelKuraevFadin", "convolutionKuraevFadin", "convolutionKuraevFadinBlurred", "ConvolutionPlan", "draw_toys", "draw_toys_device", "InterpRangeException", "EfficiencyDimensionException",
            "DifferentModelCrossSectionSizes", "IsrGpuError"]

@@ -65,6 +65,7 @@ SIGNATURES = {
     "isr_interp_eval": (C.c_int, [_vp, _dp, _i64, _dp, _dp]),
     "isr_factor": (C.c_int, [_vp, _dp]),
     "isr_solve": (C.c_int, [_vp, _dp, _dp, _dp]),
+    "isr_iterative_solve": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp]),
     "isr_get_inverse": (C.c_int, [_vp, _dp]),
     "isr_get_inv_cov": (C.c_int, [_vp, _dp]),
     "isr_cond_number": (C.c_int, [_vp, _dp]),

@@ -298,6 +298,12 @@ int isr_solve(isr_problem* p, const double* vcs, double* bcs_out, double* cov_ou
   return ISR_OK;
 }
 
+int isr_iterative_solve(isr_problem* p, int niter, const double* vcs, double* bcs_out, double* radcorr_out) {
+  if (!p || !vcs || !bcs_out) { set_error("NULL argument"); return ISR_EINVAL; }
+  ISR_CUDA(cudaSetDevice(p->ctx->device));
+  return iterative_solve(p, niter, vcs, bcs_out, radcorr_out);
+}
+
 static int copy_out(isr_problem* p, const double* dev, double* host, const char* what) {
   if (!p || !host) { set_error("NULL argument"); return ISR_EINVAL; }
   if (!p->factored) { set_error("%s: call isr_factor first", what); return ISR_ESTATE; }

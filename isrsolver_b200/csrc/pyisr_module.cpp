@@ -271,6 +271,14 @@ PYBIND11_MODULE(PyISR, m) {
            },
            py::arg("initial_lambda"), "Find the regularization parameter of maximum L-curve curvature and solve");
 
+  py::class_<IterISRInterpSolver> iter(m, "IterISRInterpSolver", kCtorDoc);   // include/PyIterISRInterpSolver.hpp
+  iter.def(py::init(&make_solver<IterISRInterpSolver>), CTOR_ARGS);
+  bind_common<IterISRInterpSolver>(iter);
+  iter.def("eval_equation_matrix", [](IterISRInterpSolver& s) { s.evalEqMatrix(); return 0; }, "Eval equation matrix")
+      .def_property("n_iter", [](IterISRInterpSolver& s) { return s.getNumOfIters(); },
+                    [](IterISRInterpSolver& s, std::size_t n) { s.setNumOfIters(n); }, "Number of iterations")
+      .def("radcorr", [](IterISRInterpSolver& s) { return view1(s.getRadCorr(), s); }, "Radiative correction 1 + delta");
+
   py::class_<ISRSolverTSVD> tsvd(m, "ISRSolverTSVD", kCtorDoc);
   tsvd.def(py::init([](int n, const py::object& energy, const py::object& vcs, const py::object& energy_err, const py::object& vcs_err,
                        double threshold, const py::object& efficiency, bool enableEnergySpread, const py::object& upper_TSVD_index) {

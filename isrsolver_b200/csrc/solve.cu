@@ -257,6 +257,49 @@ int toy_batch_host(isr_problem* p, int64_t T, const double* V, const double* bcs
 }
 
 // --------------------------------------------------------------------------------------------------
+// IterISRInterpSolver::solve (src/IterISRInterpSolver.cpp:45-57): the iterative radiative-correction method on
+// the assembled operator:  b <- v;  repeat nIter times:  delta = (G b) / b,  b <- v / delta;
+// Cov = diag((err / delta)^2).  One block; the matrix-vector product is a warp per row (fixed order).
+// --------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) iterative_kernel(int n, int niter, const double* __restrict__ G /* col-major */,
+                                                          const double* __restrict__ vcs, double* __restrict__ bcs,
+                                                          double* __restrict__ radcorr) {
+  extern __shared__ double sb[];      // current b
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) sb[j] = vcs[j];
+  __syncthreads();
+  for (int it = 0; it < niter; ++it) {
+    for (int i = w; i < n; i += nw) {
+      double acc = 0.0;
+      for (int j = lane; j < n; j += 32) acc = fma(G[(size_t)i + (size_t)n * j], sb[j], acc);
+      for (int s = 16; s >= 1; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+      if (lane == 0) radcorr[i] = acc / sb[i];
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += blockDim.x) sb[j] = vcs[j] / radcorr[j];
+    __syncthreads();
+  }
+  for (int j = threadIdx.x; j < n; j += blockDim.x) bcs[j] = sb[j];
+}
+
+int iterative_solve(isr_problem* p, int niter, const double* vcs, double* bcs_out, double* radcorr_out) {
+  if (!p->has_G) { set_error("isr_iterative_solve: no matrix (call isr_assemble first)"); return ISR_ESTATE; }
+  if (niter < 0) { set_error("isr_iterative_solve: niter < 0"); return ISR_EINVAL; }
+  const int n = p->n;
+  cudaStream_t st = p->ctx->stream;
+  ISR_TRY(p->d_stat.reserve((size_t)4 * n));
+  double *dv = p->d_stat.p, *db = p->d_stat.p + n, *dr = p->d_stat.p + 2 * n;
+  ISR_CUDA(cudaMemcpyAsync(dv, vcs, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  ISR_CUDA(cudaMemsetAsync(dr, 0, sizeof(double) * n, st));
+  iterative_kernel<<<1, 1024, sizeof(double) * n, st>>>(n, niter, p->d_G.p, dv, db, dr); ISR_COUNT_LAUNCH();
+  ISR_CUDA(cudaGetLastError());
+  ISR_CUDA(cudaMemcpyAsync(bcs_out, db, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  if (radcorr_out) ISR_CUDA(cudaMemcpyAsync(radcorr_out, dr, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  ISR_CUDA(cudaStreamSynchronize(st));
+  return ISR_OK;
+}
+
+// --------------------------------------------------------------------------------------------------
 // Toy campaign by count: toys drawn on the device (rng.cu), chunk by chunk through the fused kernel.
 // --------------------------------------------------------------------------------------------------
 int toy_campaign_device(isr_problem* p, int64_t T, int64_t first_toy, uint64_t seed, const double* vcs,

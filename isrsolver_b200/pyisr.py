@@ -651,6 +651,41 @@ class ISRSolverSLE(BaseISRSolver):
         return res
 
 
+class IterISRInterpSolver(ISRSolverSLE):
+    """IterISRInterpSolver (include/IterISRInterpSolver.hpp; src/IterISRInterpSolver.cpp:45-65; PyISR
+    "IterISRInterpSolver", include/PyIterISRInterpSolver.hpp): the iterative radiative-correction method on the
+    same operator matrix.  bcs_cov_matrix() is diag((vcs_err / radcorr)^2) as in the reference."""
+
+    def __init__(self, *args, **kwargs):
+        self._n_iter = int(kwargs.pop("n_iter", 10))      # _nIter(10), src/IterISRInterpSolver.cpp:19
+        super().__init__(*args, **kwargs)
+        self._radcorr = np.zeros(self._n)
+
+    n_iter = property(lambda self: self._n_iter, lambda self, v: self.setNumOfIters(v))
+    def getNumOfIters(self): return self._n_iter
+    def setNumOfIters(self, n): self._n_iter = int(n)
+    def radcorr(self): return self._radcorr
+
+    def solve(self):
+        if not self._eq_ready:
+            self.eval_equation_matrix()
+        L.check(self._lib.isr_iterative_solve(self._p, self._n_iter, L.dptr(self._vcs), L.dptr(self._bcs), L.dptr(self._radcorr)))
+        self._cov = np.diag((self._vcs_err / self._radcorr) ** 2) if self._n_iter > 0 else np.zeros((self._n, self._n))
+        return 0
+
+    def bcs_inv_cov_matrix(self):
+        return np.diag(1.0 / np.diag(self._cov))
+
+    def save(self, output_path, vcs_name="vcs", bcs_name="bcs"):
+        np.savez(output_path, **{
+            vcs_name: np.stack([self._ecm, self._vcs, self._ecm_err, self._vcs_err]),
+            bcs_name: np.stack([self._ecm, self._bcs, np.zeros(self._n), self.bcs_err()]),
+            "radiative_correction": np.stack([self._ecm, self._radcorr]),
+            "intergalOperatorMatrix": self.intop_matrix(), "covMatrixBornCS": self.bcs_cov_matrix(),
+            "invCovMatrixBornCS": self.bcs_inv_cov_matrix()})
+        return 0
+
+
 class ISRSolverSLE2(ISRSolverSLE):
     """ISRSolverSLE2: efficiency eps(x, energyIndex) from one x-histogram per energy point
     (src/BaseISRSolver2.cpp:151-160, 196-204, 231-236; src/ISRSolverSLE2.cpp:142-153)."""
