@@ -365,6 +365,7 @@ def run_b200(args, rank, world, local_rank):
         "gpu_launches": int(launches), "clocks": clocks,
     }
     line["assembly_other_configs"] = other_assemblies(lib, ctx, stream, torch)
+    line["chi2_test_other_configs"] = other_chi2_tests(lib, ctx, stream, torch, dev)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(n, G, bcs0, vcs, err)
     emit(line)
@@ -401,6 +402,53 @@ def other_assemblies(lib, ctx, stream, torch):
         npan, nnode = C.c_int64(), C.c_int64()
         L.check(lib.isr_assemble_stats(p, C.byref(npan), C.byref(nnode)))
         out[name] = {"ms": e0.elapsed_time(e1) / 10, "panels": npan.value, "nodes": nnode.value}
+        lib.isr_problem_destroy(p)
+    return out
+
+
+def other_chi2_tests(lib, ctx, stream, torch, dev):
+    """The same step (assemble + factor + toys + min/max + TH1F) at the other BASELINE.json chi2-test sizes, V resident,
+    this rank only: C2 = N 100, cubic, 100k toys (configs[1]); C5 = N 500, linear, 2^17 toys (the per-GPU share of
+    1M toys on 8 GPUs) with the ratio statistics on top.  CUDA events, mean of 5 after 2 warm-ups."""
+    from isrsolver_b200 import _lib as L
+    out = {}
+    for name, n, cubic, T, ratio in (("c2_n100_cubic_100k_toys", 100, True, 100000, False),
+                                     ("c5_n500_linear_131072_toys_ratio", 500, False, 1 << 17, True)):
+        ecm = np.linspace(E_MIN, E_MAX, n)
+        st = np.ascontiguousarray([[0, 0, 0], [1, 1, n - 1]] if cubic else [[0, 0, n - 1]], dtype=np.int32)
+        p = C.c_void_p()
+        L.check(lib.isr_problem_create(ctx, n, L.dptr(ecm), E_THR, len(st), L.iptr(st), None, C.byref(p)))
+        G = np.empty((n, n))
+        L.check(lib.isr_assemble(p, None, L.dptr(G)))
+        bcs0 = bw_born(ecm); vcs = G.T @ bcs0; err = 0.05 * vcs
+        gen = torch.Generator(device=dev); gen.manual_seed(7)
+        Vd = torch.from_numpy(vcs).to(dev)[None, :] + torch.from_numpy(err).to(dev)[None, :] * torch.randn((T, n), dtype=torch.float64, device=dev, generator=gen)
+        chi2 = torch.empty(T, dtype=torch.float64, device=dev)
+        acc = torch.zeros(4 * n, dtype=torch.float64, device=dev)
+        rng2, cnt = torch.empty(2, dtype=torch.float64, device=dev), torch.empty(130, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+
+        def step():
+            L.check(lib.isr_assemble(p, None, None))
+            L.check(lib.isr_factor(p, L.dptr(err)))
+            acc.zero_()
+            L.check(lib.isr_toy_batch_dev(p, T, Vd.data_ptr(), L.dptr(bcs0), chi2.data_ptr(), acc.data_ptr(),
+                                          acc[n:].data_ptr() if ratio else None, None, None))
+            L.check(lib.isr_minmax_to_dev(ctx, T, chi2.data_ptr(), rng2.data_ptr()))
+            L.check(lib.isr_histogram_range_dev(ctx, T, chi2.data_ptr(), 128, rng2.data_ptr(), cnt.data_ptr()))
+            return cnt.cpu()
+        with torch.cuda.stream(stream):
+            for _ in range(2):
+                h = step()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(5):
+                h = step()
+            e1.record(stream)
+        e1.synchronize()
+        assert int(h.sum()) == T
+        ms = e0.elapsed_time(e1) / 5
+        out[name] = {"ms_per_test": ms, "toys_per_s": T / (ms * 1e-3), "n_points": n, "toys": T}
         lib.isr_problem_destroy(p)
     return out
 

@@ -14,12 +14,14 @@ for n in (200,):
     T = 1 << 20
     Vd = torch.from_numpy(vcs)[None,:].cuda() + torch.from_numpy(err)[None,:].cuda()*torch.randn(T, n, dtype=torch.float64, device='cuda')
     chi2d = torch.empty(T, dtype=torch.float64, device='cuda')
+    sbd = torch.zeros(n, dtype=torch.float64, device='cuda')
+    sb = sbd.data_ptr() if os.environ.get('SUM') else None
     torch.cuda.synchronize()
     with torch.cuda.stream(stream):
-        for _ in range(2): L.check(lib.isr_toy_batch_dev(p, T, Vd.data_ptr(), L.dptr(bcs0), chi2d.data_ptr(), None, None, None, None))
+        for _ in range(2): L.check(lib.isr_toy_batch_dev(p, T, Vd.data_ptr(), L.dptr(bcs0), chi2d.data_ptr(), sb, None, None, None))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for _ in range(5): L.check(lib.isr_toy_batch_dev(p, T, Vd.data_ptr(), L.dptr(bcs0), chi2d.data_ptr(), None, None, None, None))
+        for _ in range(5): L.check(lib.isr_toy_batch_dev(p, T, Vd.data_ptr(), L.dptr(bcs0), chi2d.data_ptr(), sb, None, None, None))
         e1.record(stream)
     e1.synchronize(); ms = e0.elapsed_time(e1)/5
     print(f"{os.environ.get('TAG','')} N={n}: {ms:.3f} ms {4*n*n*T/ms*1e-9:.2f} TFLOP/s mean chi2 {chi2d.mean().item():.3f}")
