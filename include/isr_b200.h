@@ -78,10 +78,12 @@ int isr_problem_set_ranges(isr_problem* p, int nranges, const int* ranges);
 int isr_assemble(isr_problem* p, const double* ecm_err, double* G_out);
 /* Host-sampled efficiency ("SAMPLED"): eps(x, E) is an arbitrary host callable, as the reference's
  * std::function / Python callable is (include/BaseISRSolver.hpp:36-41, include/PyISRSolver.hpp:189-197).
- * isr_assemble_nodes enumerates the quadrature panels of a problem created WITHOUT a tabulated efficiency and
+ * isr_assemble_nodes enumerates the quadrature panels of a problem and
  * returns, for every node, x and the energy-point index i (evaluate eps(x, ecm[i]) there; pass NULL buffers to
  * query *count only); isr_assemble_sampled then assembles G with those values entering the integrand node by
- * node.  The callable must be smooth between the kernel's own break points: jumps are not resolved (use a table). */
+ * node.  The callable must be smooth between break points: besides the kernel's own (x0, grading), the bin edges of an
+ * ISR_EPS_ROW_TABLE / ISR_EPS_TABLE_2D given at problem creation are honoured (its values are then ignored) -- pass a
+ * table whose edges are the callable's discontinuities. */
 int isr_assemble_nodes(isr_problem* p, int64_t cap, double* x_out, int* row_out, int64_t* count);
 int isr_assemble_sampled(isr_problem* p, int64_t n_nodes, const double* eps_values, const double* ecm_err, double* G_out);
 /* Inject a matrix instead of assembling it (tests of the solve path; column-major). */

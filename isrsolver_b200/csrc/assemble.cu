@@ -945,13 +945,14 @@ int assemble(isr_problem* p, const double* ecm_err) {
 }
 
 // ---- host-sampled efficiency (ISR_EPS_SAMPLED): eps(x, E_i) is an arbitrary host callable ------------------
-// Phase 1: enumerate the panels (cut at x0 and the grading points only -- a sampled efficiency has no bin edges)
-// and return x and the row of every node.  Phase 2: the caller's values enter the integrand node by node.
+// Phase 1: enumerate the panels (cut at x0 and the grading points, plus the bin edges of a table given at problem
+// creation -- the way to tell the quadrature where a sampled efficiency jumps) and return x and the row of every node.  Phase 2: the caller's values enter the integrand node by node.
 int assemble_nodes(isr_problem* p, int64_t cap, double* x_out, int* row_out, int64_t* count) {
   const int n = p->n;
   cudaStream_t st = p->ctx->stream;
   const int nitems = n * (n + 1) / 2;
-  if (p->eps.kind != 0) { set_error("isr_assemble_nodes: the problem already has a tabulated efficiency"); return ISR_ESTATE; }
+  // a tabulated efficiency may be present: its bin edges then serve as break points of the sampled one (the sampled
+  // values replace the table's; pass a table of ones whose edges are the callable's discontinuities)
   ISR_TRY(enumerate_panels(p));
   int total = 0;
   ISR_CUDA(cudaMemcpyAsync(&total, p->d_off.p + nitems, sizeof(int), cudaMemcpyDeviceToHost, st));

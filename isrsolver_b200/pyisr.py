@@ -283,7 +283,7 @@ class BaseISRSolver:
     """BaseISRSolver (include/BaseISRSolver.hpp:30-120; array constructor src/BaseISRSolver.cpp:77-129)."""
 
     def __init__(self, n, energy, vcs, energy_err, vcs_err, threshold, efficiency=None,
-                 enableEnergySpread=False, device: int | None = None):
+                 enableEnergySpread=False, device: int | None = None, efficiency_breaks=None):
         n = int(n)
         energy, vcs, vcs_err = _f64(energy, n, "energy"), _f64(vcs, n, "vcs"), _f64(vcs_err, n, "vcs_err")
         energy_err = np.zeros(n) if energy_err is None else _f64(energy_err, n, "energy_err")
@@ -304,6 +304,11 @@ class BaseISRSolver:
             if not callable(efficiency):
                 raise TypeError("efficiency must be an isrsolver_b200.Efficiency table or a callable eps(x, energy)")
             self._eff_call, efficiency = efficiency, None
+            if efficiency_breaks is not None and len(efficiency_breaks):
+                # x values where the callable jumps: handed to the quadrature as the edges of a table of ones
+                br = np.unique(np.clip(np.asarray(efficiency_breaks, dtype=np.float64), 0.0, 1.0))
+                edges = np.unique(np.concatenate([[0.0], br, [1.0]]))
+                efficiency = Efficiency("row_table", values=np.ones((n, len(edges) + 1)), xedges=edges)
         self._eff = efficiency
         self._bcs = np.zeros(n)
         self._lib = L.load()

@@ -261,3 +261,26 @@ def test_callable_efficiency_sampled_at_the_nodes(oracle):
     s3.solve()
     S = oracle.Interp(ecm, thr, st).energy_spread_matrix(np.full(n, 0.002))
     np.testing.assert_allclose(s3.intop_matrix(), S @ G, rtol=1e-10, atol=1e-13)
+
+
+def test_callable_efficiency_with_declared_jumps():
+    """A step efficiency given as a callable plus its break points == the same efficiency given as a two-bin table."""
+    import isrsolver_b200 as isr
+    n = 14
+    ecm = np.linspace(1.18, 2.0, n); thr = 0.827
+    step = lambda x, e: np.where(x < 0.1, 0.8, 0.4) * (1.0 + 0.05 * (e - 1.5))
+    st = [(False, 0, 3), (True, 4, n - 1)]
+    s = isr.ISRSolverSLE(n, ecm, np.ones(n), None, np.ones(n), thr, efficiency=step, efficiency_breaks=[0.1])
+    s.set_interp_settings(st)
+    s.eval_equation_matrix()
+    vals = np.zeros((n, 4))
+    vals[:, 1], vals[:, 2] = 0.8 * (1.0 + 0.05 * (ecm - 1.5)), 0.4 * (1.0 + 0.05 * (ecm - 1.5))
+    t = isr.ISRSolverSLE2(n, ecm, np.ones(n), None, np.ones(n), thr, eff_hists=vals, xedges=[0.0, 0.1, 1.0])
+    t.set_interp_settings(st)
+    t.eval_equation_matrix()
+    np.testing.assert_allclose(s.intop_matrix(), t.intop_matrix(), rtol=1e-13, atol=1e-16)
+    # without the declared jump the panels straddle it and the result is visibly off
+    u = isr.ISRSolverSLE(n, ecm, np.ones(n), None, np.ones(n), thr, efficiency=step)
+    u.set_interp_settings(st)
+    u.eval_equation_matrix()
+    assert np.abs(u.intop_matrix() - t.intop_matrix()).max() > 1e-6
