@@ -142,7 +142,12 @@ int isr_toy_batch(isr_problem* p, int64_t T, const double* V, const double* bcs0
 int isr_toy_batch_dev(isr_problem* p, int64_t T, const double* V_dev, const double* bcs0,
                       double* chi2_dev, double* sum_bcs_dev, double* ratio_stats_dev,
                       uint32_t* ratio_hist_dev, double* bcs_dev);
-/* Kernel variant: 0 = auto, 1 = DMMA (mma.sync f64 tensor pipe), 2 = DFMA (CUDA cores). */
+/* Toy-kernel schedule.  0 (default): operators that are exactly lower triangular -- G^-1 and W^(1/2) G of linear
+ * interpolation without energy spread -- skip their structural zeros (bit-identical results, about 2 N^2 instead of
+ * 4 N^2 flop per toy).  1: dense schedule on the operators as given (cross-check).  2: as 0, and a dense chi2 factor R is
+ * replaced at the first chi2 batch by the lower-triangular factor L of its QL decomposition (L^T L = R^T R, so
+ * |L d|^2 = |R d|^2 = d^T Cov^-1 d of src/Chi2Test.cpp:51-55 up to rounding): 3 N^2 flop per toy, for campaigns long
+ * enough (about 10^6 toys) to repay the Householder QR. */
 int isr_set_toy_kernel(isr_problem* p, int variant);
 
 /* Toy campaigns by COUNT, as the reference's chi2Test / chi2TestData / ratioTestModel take them (src/Chi2Test.cpp:29-60,

@@ -613,7 +613,7 @@ int isr_tikhonov_toy_scan_hist(isr_problem* p, int64_t L, const double* lambda, 
 }
 
 int isr_set_scan_kernel(isr_problem* p, int variant) {
-  if (!p || variant < 0 || variant > 1) { set_error("isr_set_scan_kernel: bad argument"); return ISR_EINVAL; }
+  if (!p || variant < 0 || variant > 2) { set_error("isr_set_scan_kernel: bad argument"); return ISR_EINVAL; }
   p->scan_variant = variant;
   return ISR_OK;
 }

@@ -135,6 +135,36 @@ int lu_inverse(isr_ctx* c, int n, const double* A, double* lu, double* prod, dou
   return ISR_OK;
 }
 
+// B(i, k') = A[i][n-1-k']: column-major copy of a row-major operator with its columns reversed
+__global__ void reverse_cols_kernel(int n, int ld, const double* __restrict__ A, double* __restrict__ B) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * n) return;
+  const int i = idx % n, k = idx / n;
+  B[idx] = A[(size_t)i * ld + (n - 1 - k)];
+}
+// L[i][k] = R'(n-1-i, n-1-k) for k <= i, exact zeros above the diagonal and in the pad column
+__global__ void ql_writeback_kernel(int n, int ld, const double* __restrict__ QR, double* __restrict__ L) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * ld) return;
+  const int i = idx / ld, k = idx % ld;
+  L[idx] = (k <= i) ? QR[(size_t)(n - 1 - i) + (size_t)n * (n - 1 - k)] : 0.0;
+}
+// Replace the row-major operator A (n x n, leading dimension ld) by a LOWER-TRIANGULAR L with L^T L = A^T A, so that
+// |L d|^2 == |A d|^2 for every d: the triangular factor of the QL decomposition A = Q L.  Computed as the Householder QR
+// (cuSOLVER geqrf; backward stable, no squaring of the condition number, rank-deficient A allowed) of A with its
+// columns reversed, A J = Q R'  =>  A = (Q J)(J R' J), and J R' J is lower triangular.  `scratch` holds n x n doubles.
+int ql_factor_rowmajor(isr_ctx* c, int n, int ld, double* A, double* scratch, DevBuf<double>& work, DevBuf<int>& info) {
+  int lwork = 0;
+  ISR_CUSOLVER(cusolverDnDgeqrf_bufferSize(c->solver, n, n, scratch, n, &lwork));
+  ISR_TRY(work.reserve((size_t)lwork + n));      // tau lives behind the LAPACK workspace
+  ISR_TRY(info.reserve(1));
+  reverse_cols_kernel<<<(n * n + 255) / 256, 256, 0, c->stream>>>(n, ld, A, scratch); ISR_COUNT_LAUNCH();
+  ISR_CUSOLVER(cusolverDnDgeqrf(c->solver, n, n, scratch, n, work.p + lwork, work.p, lwork, info.p));
+  ql_writeback_kernel<<<(n * ld + 255) / 256, 256, 0, c->stream>>>(n, ld, scratch, A); ISR_COUNT_LAUNCH();
+  ISR_CUDA(cudaGetLastError());
+  return ISR_OK;
+}
+
 // A = U diag(S) VT (A destroyed); U, VT n x n column-major, S descending.
 int svd(isr_ctx* c, int n, double* A, double* U, double* S, double* VT, DevBuf<double>& work, DevBuf<int>& info) {
   int lwork = 0;

@@ -67,6 +67,7 @@ int select_sle(isr_problem* p) {
   colmajor_to_rowmajor(st, n, p->d_Ginv.p, nullptr, 0, p->d_Sop.p, ld);
   colmajor_to_rowmajor(st, n, p->d_R.p, nullptr, 0, p->d_Rop.p, ld);
   ISR_CUDA(cudaGetLastError());
+  ISR_TRY(update_tri_flag(p));
   p->solver_selected = true;
   return ISR_OK;
 }

@@ -8,6 +8,7 @@
 #include "problem.hpp"
 #include "tikhonov.hpp"
 #include "toy_batch.hpp"
+#include "linalg.hpp"
 #include "toy_gemm.cuh"
 
 #include <cstdlib>
@@ -36,6 +37,30 @@ __global__ void reduce_part_kernel(int nctas, int ld, int n, int nstat, const do
       ratio_stats[3 * j + 2] += s[3];
     }
   }
+}
+
+// flag[0] / flag[1] = 1 iff the row-major operator S / R (leading dimension ld) is exactly lower triangular
+__global__ void tri_check_kernel(int n, int ld, const double* __restrict__ S, const double* __restrict__ R, int* __restrict__ flag) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * n) return;
+  const int i = idx / n, j = idx % n;
+  if (j > i) {
+    if (S[(size_t)i * ld + j] != 0.0) flag[0] = 0;
+    if (R[(size_t)i * ld + j] != 0.0) flag[1] = 0;
+  }
+}
+// Called whenever d_Sop / d_Rop change (isr_factor, isr_tikhonov_select, isr_tsvd_select): asynchronous, the toy
+// kernel reads the flags from device memory.
+int update_tri_flag(isr_problem* p) {
+  const int n = p->n, ld = (n + 1) & ~1;
+  cudaStream_t st = p->ctx->stream;
+  ISR_TRY(p->d_tri.reserve(2));
+  static const int ones[2] = {1, 1};
+  ISR_CUDA(cudaMemcpyAsync(p->d_tri.p, ones, sizeof(ones), cudaMemcpyHostToDevice, st));
+  tri_check_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(n, ld, p->d_Sop.p, p->d_Rop.p, p->d_tri.p); ISR_COUNT_LAUNCH();
+  ISR_CUDA(cudaGetLastError());
+  p->rop_tri_known = false;
+  return ISR_OK;
 }
 
 // repack T x N (odd N) into T x ld with a zero pad column
@@ -194,11 +219,35 @@ static int launch_fused(isr_problem* p, int64_t T, const double* V_dev, const do
   }
   g.nstat = nstat;
   g.rhist = out.rhist;
+  g.tri = (Sop == p->d_Sop.p && (!Rop || Rop == p->d_Rop.p)) ? p->d_tri.p : nullptr;   // the flag describes the selected pair only
+  if (p->toy_variant == 1) g.tri = nullptr;   // cross-check variant: dense schedule, operators as given
   cfg->kernel<<<ctas, cfg->threads, smem, st>>>(mapV, mapS, mapR, mapD, g); ISR_COUNT_LAUNCH();
   if (want_stats) {
     reduce_part_kernel<<<(n + 3) / 4, 128, 0, st>>>(ctas, g.part_ld, n, nstat, p->d_acc.p, out.sum_bcs, out.ratio_stats); ISR_COUNT_LAUNCH();
   }
   ISR_CUDA(cudaGetLastError());
+  return ISR_OK;
+}
+
+// Schedule 2 (isr_set_toy_kernel): chi2 = |R d|^2 only depends on R^T R, so a dense chi2 factor is replaced -- once
+// per selection, at the first toy batch that asks for chi2 -- by the lower-triangular factor L of its QL decomposition
+// (|L d| == |R d| for every d): pass 2 then skips the structural zeros, N^2 instead of 2 N^2 flop per toy.  Already
+// triangular factors (linear interpolation without energy spread) are left as they are.  Opt-in, because cuSOLVER's
+// Householder QR costs 0.6 ms at N = 200 (1.8 ms at N = 500): it pays from about 10^6 toys per factorisation.
+static int ensure_rop_triangular(isr_problem* p) {
+  if (p->rop_tri_known) return ISR_OK;
+  const int n = p->n, ld = (n + 1) & ~1;
+  cudaStream_t st = p->ctx->stream;
+  int flags[2] = {0, 0};
+  ISR_CUDA(cudaMemcpyAsync(flags, p->d_tri.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
+  ISR_CUDA(cudaStreamSynchronize(st));
+  if (!flags[1] && n >= 16) {
+    ISR_TRY(p->d_tmp.reserve((size_t)n * n));
+    ISR_TRY(ql_factor_rowmajor(p->ctx, n, ld, p->d_Rop.p, p->d_tmp.p, p->d_work, p->d_info));
+    static const int one = 1;
+    ISR_CUDA(cudaMemcpyAsync(p->d_tri.p + 1, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+  }
+  p->rop_tri_known = true;
   return ISR_OK;
 }
 
@@ -208,6 +257,7 @@ int toy_batch_device(isr_problem* p, int64_t T, const double* V_dev, const doubl
     return ISR_ESTATE;
   }
   if (T <= 0) return ISR_OK;
+  if (out.chi2 && p->toy_variant == 2) ISR_TRY(ensure_rop_triangular(p));
   // pass 2 is skipped when no chi2 is requested (e.g. the mean-solution loop of chi2TestData)
   return launch_fused(p, T, V_dev, p->d_Sop.p, out.chi2 ? p->d_Rop.p : nullptr, b0_dev,
                       out.chi2 ? nullptr : scratch_dfull(p, T), out);

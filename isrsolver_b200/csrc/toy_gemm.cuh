@@ -97,6 +97,7 @@ struct ToyArgs {
   double* part;       // [gridDim.x][4][part_ld] per-CTA {sum b, count, sum r, sum r^2} or nullptr
   int part_ld, nstat; // nstat = 1 (sum only) or 4
   uint32_t* rhist;    // N x 1026 or nullptr
+  const int* tri;     // device flags {S, R}: operator is exactly lower triangular (B[n][k] == 0 for k > n), or nullptr
 };
 
 // Position in the CTA's chunk stream.  Units: U1(i) = pass 1 of local tile i over all column blocks,
@@ -106,13 +107,26 @@ struct ToyArgs {
 // hold (a single tile, or an operator so small that a unit is shorter than STAGES-1 chunks) the
 // sequential order U1(i) NOP U2(i) is used instead, NOP being STAGES-1 empty chunks.
 enum { PH_P1 = 0, PH_P2 = 1, PH_NOP = 2 };
+template <int NP_, int KC_>
 struct Sched {
+  static constexpr int np = NP_, kcs = KC_;   // compile-time: the chunk count of a triangular column block is a division
   int m, u;        // local tiles, unit index
   int nblk, nk, nop, do2, seq;
   int cb, kc;
-  __device__ void init(int m_, int nblk_, int nk_, int nop_, int do2_) {
+  int tri, ld;   // tri: bit 0 = pass-1 operator lower triangular, bit 1 = pass-2 operator.  Column block cb of a
+                          // triangular operator only has non-zero K below (cb + 1) * np: the chunks beyond are not loaded
+  __device__ int nk_tri(int b, int pass2) const {
+    if (!((tri >> pass2) & 1)) return nk;
+    const int lim = min(ld, (b + 1) * np);
+    return (lim + kcs - 1) / kcs;
+  }
+  __device__ int nk_of(int b) const { return nk_tri(b, kind() == PH_P2); }
+  __device__ void init(int m_, int nblk_, int nk_, int nop_, int do2_, int tri_, int ld_) {
     m = m_; nblk = nblk_; nk = nk_; nop = nop_; do2 = do2_; u = 0; cb = 0; kc = 0;
-    seq = (m == 1) || (nk * nblk < nop);
+    tri = tri_; ld = ld_;
+    int t1 = 0, t2 = 0;
+    for (int b = 0; b < nblk; ++b) { t1 += nk_tri(b, 0); t2 += nk_tri(b, 1); }
+    seq = (m == 1) || (min(t1, t2) < nop);
   }
   __device__ int units() const { return do2 ? (seq ? 3 * m : 2 * m) : m; }
   __device__ bool done() const { return u >= units(); }
@@ -135,12 +149,22 @@ struct Sched {
       if (++kc == nop) { kc = 0; ++u; }
       return;
     }
-    if (++kc == nk) {
+    if (++kc == nk_of(cb)) {
       kc = 0;
       if (++cb == nblk) { cb = 0; ++u; }
     }
   }
 };
+
+template <int J> struct IntC { static constexpr int value = J; };
+// f(IntC<jmin>) for a run-time jmin in [0, BT): a chain of compares ending in a compile-time specialised body
+template <int J, int BT, class F>
+__device__ __forceinline__ void dispatch_jmin(int jmin, F&& f) {
+  if constexpr (J < BT) {
+    if (jmin == J) f(IntC<J>{});
+    else dispatch_jmin<J + 1, BT>(jmin, f);
+  }
+}
 
 template <int WM, int WN, int AT, int BT, int STAGES, int KC>
 __global__ void __launch_bounds__(WM * WN * 32, 1)
@@ -174,7 +198,7 @@ toy_fused_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant
   const int ring_row0 = blockIdx.x * kRingSlots * TM;
 
   // issue the TMA loads of the chunk at schedule position `p` into stage st (one thread)
-  auto issue = [&](const Sched& p, int st) {
+  auto issue = [&](const Sched<NP, kKC>& p, int st) {
     const int kind = p.kind();
     if (kind == PH_NOP) { mbar_arrive(&full[st]); return; }   // keeps the stage's phase in step
     mbar_arrive_expect_tx(&full[st], STAGE_BYTES);
@@ -191,8 +215,9 @@ toy_fused_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant
     }
   };
 
-  Sched pf;   // schedule position of the chunk STAGES ahead of the one this warp consumes
-  pf.init(m, g.nblk, nk, STAGES - 1, g.do2);
+  Sched<NP, kKC> pf;   // schedule position of the chunk STAGES ahead of the one this warp consumes
+  const int tri = g.tri ? (g.tri[0] | (g.tri[1] << 1)) : 0;
+  pf.init(m, g.nblk, nk, STAGES - 1, g.do2, tri, g.ld);
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); done[s] = 0; }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -214,8 +239,8 @@ toy_fused_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant
   auto consumer_barrier = [&]() { asm volatile("bar.sync 1, %0;\n" ::"n"(NCT) : "memory"); };
 
   if (m > 0) {
-    Sched q;
-    q.init(m, g.nblk, nk, STAGES - 1, g.do2);
+    Sched<NP, kKC> q;
+    q.init(m, g.nblk, nk, STAGES - 1, g.do2, tri, g.ld);
     int s = 0, parity = 0;
     uint32_t ph = 0;
     double acc[AT][BT][2];
@@ -232,28 +257,42 @@ toy_fused_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant
       const double* sA = stage0 + (size_t)s * ROWS * kKC;
       const double* sB = sA + TM * kKC;
       const int ksteps = min(kKC, g.ld - q.kc * kKC + 7) / 8;  // 8 physical k per double-step
-#pragma unroll
-      for (int kp = 0; kp < kKC / 8; ++kp) {
-        if (kp < ksteps) {
-          double2 a[AT], b[BT];
-#pragma unroll
-          for (int i = 0; i < AT; ++i)
-            a[i] = *reinterpret_cast<const double2*>(sA + ((wm * AT + i) * 8 + gq) * kKC + kp * 8 + 2 * c);
-#pragma unroll
-          for (int j = 0; j < BT; ++j)
-            b[j] = *reinterpret_cast<const double2*>(sB + ((wn * BT + j) * 8 + gq) * kKC + kp * 8 + 2 * c);
-#pragma unroll
-          for (int i = 0; i < AT; ++i)
-#pragma unroll
-            for (int j = 0; j < BT; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
-#pragma unroll
-          for (int i = 0; i < AT; ++i)
-#pragma unroll
-            for (int j = 0; j < BT; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
-        }
+      // Lower-triangular operator (B[n][k] == 0 for k > n): column tile j of this warp, columns
+      // n0 + (j * WN + wn) * 8 .. + 8, has non-zeros in this chunk (k >= kc * KC) only if j * WN + wn >= kt0, the chunk's
+      // first k-tile counted from column n0.  The fragment loads and DMMAs of the tiles j < jm are skipped -- by real
+      // branches into a body specialised for jm: a predicated-off DMMA still occupies the pipe (measured, no gain) and
+      // a per-k-step test costs more instructions than the zeros it saves (ncu: 60 % DMMA-busy against 75 %).  The
+      // column tiles are dealt to the warps cyclically so that every warp keeps the same share of the work.
+      int jm = 0;
+      if ((tri >> (kind == PH_P2)) & 1) {
+        const int need = (q.kc * kKC - q.cb * NP) / 8 - wn;
+        jm = need <= 0 ? 0 : (need + WN - 1) / WN;
       }
+      dispatch_jmin<0, BT>(jm, [&](auto jmc) {
+        constexpr int JM = decltype(jmc)::value;
+#pragma unroll
+        for (int kp = 0; kp < kKC / 8; ++kp) {
+          if (kp < ksteps) {
+            double2 a[AT], b[BT];
+#pragma unroll
+            for (int i = 0; i < AT; ++i)
+              a[i] = *reinterpret_cast<const double2*>(sA + ((wm * AT + i) * 8 + gq) * kKC + kp * 8 + 2 * c);
+#pragma unroll
+            for (int j = JM; j < BT; ++j)
+              b[j] = *reinterpret_cast<const double2*>(sB + ((j * WN + wn) * 8 + gq) * kKC + kp * 8 + 2 * c);
+#pragma unroll
+            for (int i = 0; i < AT; ++i)
+#pragma unroll
+              for (int j = JM; j < BT; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
+#pragma unroll
+            for (int i = 0; i < AT; ++i)
+#pragma unroll
+              for (int j = JM; j < BT; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
+          }
+        }
+      });
 
-      if (q.kc == nk - 1) {
+      if (q.kc == q.nk_of(q.cb) - 1) {
         const int lt = q.tile();
         const int64_t t0 = ((int64_t)blockIdx.x + (int64_t)lt * gridDim.x) * TM;
         const int n0 = q.cb * NP;
@@ -262,7 +301,7 @@ toy_fused_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant
           double* Dt = g.do2 ? ring + (size_t)(lt % kRingSlots) * TM * g.ld : g.Dfull + t0 * g.ld;
 #pragma unroll
           for (int j = 0; j < BT; ++j) {
-            const int col = n0 + (wn * BT + j) * 8 + 2 * c;
+            const int col = n0 + (j * WN + wn) * 8 + 2 * c;
             const bool ok0 = col < g.N, ok1 = col + 1 < g.N;
             const double b00 = ok0 ? g.b0[col] : 0.0, b01 = ok1 ? g.b0[col + 1] : 0.0;
             double cs[2] = {0, 0}, cn[2] = {0, 0}, cr[2] = {0, 0}, cq[2] = {0, 0};
@@ -318,7 +357,7 @@ toy_fused_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant
                   }
                 }
                 if (gq == 0) {
-                  const int lc = n0 + (wn * BT + j) * 8 + 2 * c + e;
+                  const int lc = n0 + (j * WN + wn) * 8 + 2 * c + e;
                   double* pp = sAcc + (size_t)wm * g.nstat * accw;
                   pp[lc] += cs[e];
                   if (g.nstat == 4) {

@@ -508,6 +508,12 @@ class ISRSolverSLE(BaseISRSolver):
     def _select_for_toys(self):
         self._ensure_factored()
 
+    def set_toy_schedule(self, variant: int):
+        """0 (default): exactly lower-triangular operators skip their zeros; 1: dense schedule on the operators as
+        given (cross-check); 2: as 0, and a dense chi2 factor is replaced by its triangular QL factor (long campaigns).
+        See isr_set_toy_kernel."""
+        L.check(self._lib.isr_set_toy_kernel(self._p, int(variant)))
+
     def toy_batch(self, V, bcs0, want_chi2=True, want_sum=False, want_ratio=False, want_hist=False, want_bcs=False):
         """The loop body of chi2Test / ratioTestModel over all rows of V (toy-major (T, N), host)."""
         V = np.ascontiguousarray(V, dtype=np.float64)

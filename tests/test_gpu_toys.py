@@ -96,6 +96,68 @@ def test_ragged_shapes(oracle, n, T):
     np.testing.assert_allclose(s.bcs(), bo, rtol=RTOL)
 
 
+@pytest.mark.parametrize("n", [5, 16, 23, 100, 200, 257, 500])
+@pytest.mark.parametrize("shape", ["lower", "dense"])
+def test_triangular_schedule_equals_dense_schedule_and_oracle(oracle, n, shape):
+    """Lower-triangular operators (linear interpolation, no spread) skip their structural zeros -- bit-identical
+    to the dense schedule, the skipped products are exact zeros; under schedule 2 a dense chi2 factor is replaced by
+    its QL factor (|L d| = |R d|): chi2 within rounding of the dense schedule; all within 1e-8 of the oracle.  N around the
+    K chunk (24 / 40), the column tile (128 / 200 / 256) and two column blocks (257, 500)."""
+    import isrsolver_b200 as isr
+    rng = np.random.default_rng(977 + n)
+    T = 777
+    ecm = np.sort(1.0 + rng.random(n)); ecm += np.arange(n) * 1e-3
+    G = np.tril(rng.random((n, n)) * 0.1) + np.eye(n)
+    if shape == "dense":
+        G += 0.02 * rng.random((n, n))
+    vcs_err = 0.05 + 0.1 * rng.random(n)
+    b0 = 1.0 + rng.random(n)
+    V = (G @ b0)[None, :] + vcs_err[None, :] * rng.standard_normal((T, n))
+    c2, B = oracle.chi2_test_fair(G, V, b0, vcs_err)
+    res = {}
+    for variant in (0, 1, 2):
+        s = isr.ISRSolverSLE(n, ecm, G @ b0, None, vcs_err, 0.9)
+        s.set_matrix(G)
+        s.set_toy_schedule(variant)
+        r = s.toy_batch(V, b0, want_sum=True, want_ratio=True, want_bcs=True)
+        np.testing.assert_allclose(r["chi2"], c2, rtol=RTOL)
+        np.testing.assert_allclose(r["bcs"], B, rtol=RTOL, atol=1e-12)
+        np.testing.assert_allclose(r["sum_bcs"], B.sum(0), rtol=RTOL)
+        r2 = s.toy_batch(V, b0, want_sum=True, want_ratio=True)   # second batch on the already triangularised factor
+        np.testing.assert_array_equal(r2["chi2"], r["chi2"])
+        res[variant] = r
+    for v in (0, 2):
+        np.testing.assert_array_equal(res[v]["bcs"], res[1]["bcs"])
+        np.testing.assert_array_equal(res[v]["ratio_stats"], res[1]["ratio_stats"])
+    np.testing.assert_array_equal(res[0]["chi2"], res[1]["chi2"])
+    if shape == "lower":
+        np.testing.assert_array_equal(res[2]["chi2"], res[1]["chi2"])
+    else:
+        np.testing.assert_allclose(res[2]["chi2"], res[1]["chi2"], rtol=1e-12)
+
+
+def test_qr_chi2_factor_of_rank_deficient_and_ill_conditioned_operators(oracle):
+    """TSVD with k < N selects a rank-deficient chi2 factor, a tiny lambda a badly conditioned one: the Householder
+    QL replacement must reproduce the dense schedule there too."""
+    import isrsolver_b200 as isr
+    n, T = 48, 300
+    rng = np.random.default_rng(5)
+    ecm = np.linspace(1.2, 2.0, n)
+    G = np.tril(rng.random((n, n)) * 0.3) + np.eye(n) + 0.05 * rng.random((n, n))
+    vcs_err = 0.05 + 0.1 * rng.random(n)
+    b0 = 1.0 + rng.random(n)
+    V = (G @ b0)[None, :] + vcs_err[None, :] * rng.standard_normal((T, n))
+    out = {}
+    for variant in (2, 1):
+        t = isr.ISRSolverTSVD(n, ecm, G @ b0, None, vcs_err, 0.9)
+        t.set_matrix(G); t.setUpperTSVDIndex(n - 7); t.set_toy_schedule(variant)
+        k = isr.ISRSolverTikhonov(n, ecm, G @ b0, None, vcs_err, 0.9)
+        k.set_matrix(G); k.setLambda(1e-10); k.set_toy_schedule(variant)
+        out[variant] = (t.toy_batch(V, b0)["chi2"], k.toy_batch(V, b0)["chi2"])
+    np.testing.assert_allclose(out[2][0], out[1][0], rtol=1e-10)
+    np.testing.assert_allclose(out[2][1], out[1][1], rtol=1e-10)
+
+
 def test_empty_batch():
     import isrsolver_b200 as isr
     g = load_golden("c1_sle_n50_linear")
