@@ -48,8 +48,9 @@ struct isr_problem {
   isr::DevBuf<double> d_Ginv, d_R, d_Cov, d_InvCov, d_Sop, d_Rop, d_werr;
   isr::DevBuf<double> d_work;
   isr::DevBuf<int> d_ipiv, d_info;
-  isr::DevBuf<int> d_tri;      // {S, R}: 1 iff d_Sop / d_Rop is exactly lower triangular (the toy kernel skips the zeros)
-  bool rop_tri_known = false;  // d_Rop has been brought to lower-triangular form for the current selection (toy_batch.cu)
+  int tri_sel[2] = {0, 0};     // {S, R}: d_Sop / d_Rop of the current selection is exactly lower triangular (the toy kernel
+                               // skips the zeros); known on the host without a synchronisation of its own (lu_inverse)
+  int tri_sle[2] = {0, 0};     // the same for the SLE factorisation {Ginv, R}, restored by select_sle
   std::vector<double> vcs_err, h_b0, h_gen;   // h_gen: {vcs, vcs_err} of the device toy generator (stable host mirror)
   isr::DevBuf<double> d_gen;
   bool factored = false;

@@ -36,7 +36,7 @@ int factor(isr_problem* p, const double* vcs_err) {
   p->vcs_err.assign(vcs_err, vcs_err + n);
   ISR_CUDA(cudaMemcpyAsync(p->d_werr.p, vcs_err, sizeof(double) * n, cudaMemcpyHostToDevice, st));
   ISR_TRY(p->d_tmp2.reserve(nn));
-  ISR_TRY(lu_inverse(c, n, p->d_G.p, p->d_tmp.p, p->d_tmp2.p, p->d_Ginv.p, p->d_work, p->d_ipiv, p->d_info));
+  ISR_TRY(lu_inverse(c, n, p->d_G.p, p->d_tmp.p, p->d_tmp2.p, p->d_Ginv.p, p->d_work, p->d_ipiv, p->d_info, p->tri_sle));
   scale_rows(st, n, p->d_G.p, p->d_werr.p, 1, p->d_R.p);                  // R = diag(1/err) G
   ISR_CUDA(cudaGetLastError());
   p->factored = true;
@@ -67,7 +67,8 @@ int select_sle(isr_problem* p) {
   colmajor_to_rowmajor(st, n, p->d_Ginv.p, nullptr, 0, p->d_Sop.p, ld);
   colmajor_to_rowmajor(st, n, p->d_R.p, nullptr, 0, p->d_Rop.p, ld);
   ISR_CUDA(cudaGetLastError());
-  ISR_TRY(update_tri_flag(p));
+  p->tri_sel[0] = p->tri_sle[0];
+  p->tri_sel[1] = p->tri_sle[1];
   p->solver_selected = true;
   return ISR_OK;
 }

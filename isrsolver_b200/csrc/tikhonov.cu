@@ -228,7 +228,7 @@ int tikhonov_select(isr_problem* p, double la) {
   colmajor_to_rowmajor(st, n, p->d_tmp2.p, nullptr, 0, p->d_Sop.p, ld);
   tik_rop_kernel<<<(n * ld + 255) / 256, 256, 0, st>>>(n, ld, p->d_FU.p, p->d_mu.p, la, p->d_Rop.p); ISR_COUNT_LAUNCH();
   ISR_CUDA(cudaGetLastError());
-  ISR_TRY(update_tri_flag(p));
+  p->tri_sel[0] = p->tri_sel[1] = 0;
   p->solver_selected = true;
   return ISR_OK;
 }
@@ -537,7 +537,7 @@ int tsvd_select(isr_problem* p, int k, int keep_one, const double* vcs_err) {
   ISR_TRY(gemm(c, false, false, n, p->d_tmp.p, p->d_svVT.p, p->d_tmp2.p));
   colmajor_to_rowmajor(st, n, p->d_tmp2.p, p->d_werr.p, 1, p->d_Rop.p, ld);
   ISR_CUDA(cudaGetLastError());
-  ISR_TRY(update_tri_flag(p));
+  p->tri_sel[0] = p->tri_sel[1] = 0;
   p->factored = false;   // Sop/Rop no longer belong to the SLE factorisation
   p->solver_selected = true;
   return ISR_OK;

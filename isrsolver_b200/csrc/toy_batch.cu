@@ -39,30 +39,6 @@ __global__ void reduce_part_kernel(int nctas, int ld, int n, int nstat, const do
   }
 }
 
-// flag[0] / flag[1] = 1 iff the row-major operator S / R (leading dimension ld) is exactly lower triangular
-__global__ void tri_check_kernel(int n, int ld, const double* __restrict__ S, const double* __restrict__ R, int* __restrict__ flag) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n * n) return;
-  const int i = idx / n, j = idx % n;
-  if (j > i) {
-    if (S[(size_t)i * ld + j] != 0.0) flag[0] = 0;
-    if (R[(size_t)i * ld + j] != 0.0) flag[1] = 0;
-  }
-}
-// Called whenever d_Sop / d_Rop change (isr_factor, isr_tikhonov_select, isr_tsvd_select): asynchronous, the toy
-// kernel reads the flags from device memory.
-int update_tri_flag(isr_problem* p) {
-  const int n = p->n, ld = (n + 1) & ~1;
-  cudaStream_t st = p->ctx->stream;
-  ISR_TRY(p->d_tri.reserve(2));
-  static const int ones[2] = {1, 1};
-  ISR_CUDA(cudaMemcpyAsync(p->d_tri.p, ones, sizeof(ones), cudaMemcpyHostToDevice, st));
-  tri_check_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(n, ld, p->d_Sop.p, p->d_Rop.p, p->d_tri.p); ISR_COUNT_LAUNCH();
-  ISR_CUDA(cudaGetLastError());
-  p->rop_tri_known = false;
-  return ISR_OK;
-}
-
 // repack T x N (odd N) into T x ld with a zero pad column
 __global__ void repack_kernel(int64_t T, int n, int ld, const double* __restrict__ in, double* __restrict__ out) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -76,6 +52,7 @@ struct ToyCfg {
   int tm, np, threads, wm, kc, stages;
   size_t smem_base;   // stages + barriers + chi2 row scratch; statistics scratch is added per launch
   void (*kernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, ToyArgs);
+  void (*kernel_tri)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, ToyArgs);   // triangular schedule
   const char* name;
 };
 
@@ -122,7 +99,8 @@ static ToyCfg make_cfg(const char* name) {
   c.kc = KC;
   c.stages = ST;
   c.smem_base = toy_fused_smem_base<WM, WN, AT, BT, ST, KC>();
-  c.kernel = toy_fused_kernel<WM, WN, AT, BT, ST, KC>;
+  c.kernel = toy_fused_kernel<WM, WN, AT, BT, ST, KC, false>;
+  c.kernel_tri = toy_fused_kernel<WM, WN, AT, BT, ST, KC, true>;
   c.name = name;
   return c;
 }
@@ -181,7 +159,6 @@ static int launch_fused(isr_problem* p, int64_t T, const double* V_dev, const do
   const ToyCfg* cfg = pick_cfg(n, want_stats ? nstat : 0);
   if (!cfg) { set_error("toy batch: N = %d does not fit any kernel configuration", n); return ISR_EINVAL; }
   const size_t smem = cfg_smem(*cfg, n, want_stats ? nstat : 0);
-  ISR_CUDA(cudaFuncSetAttribute(cfg->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nblk = (n + cfg->np - 1) / cfg->np;
   const int64_t ntiles = (T + cfg->tm - 1) / cfg->tm;
   const int ctas = (int)std::min<int64_t>(p->ctx->sm_count, ntiles);
@@ -219,9 +196,13 @@ static int launch_fused(isr_problem* p, int64_t T, const double* V_dev, const do
   }
   g.nstat = nstat;
   g.rhist = out.rhist;
-  g.tri = (Sop == p->d_Sop.p && (!Rop || Rop == p->d_Rop.p)) ? p->d_tri.p : nullptr;   // the flag describes the selected pair only
-  if (p->toy_variant == 1) g.tri = nullptr;   // cross-check variant: dense schedule, operators as given
-  cfg->kernel<<<ctas, cfg->threads, smem, st>>>(mapV, mapS, mapR, mapD, g); ISR_COUNT_LAUNCH();
+  // a kernel PARAMETER, so that the schedule arithmetic stays in the uniform datapath (read from device memory it cost
+  // the dense schedule 1.2 %); the flags describe the selected pair only
+  g.tri = 0;
+  if (p->toy_variant != 1) g.tri = (Sop == p->d_Sop.p ? p->tri_sel[0] : 0) | ((Rop && Rop == p->d_Rop.p) ? p->tri_sel[1] << 1 : 0);
+  auto kernel = g.tri ? cfg->kernel_tri : cfg->kernel;
+  ISR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kernel<<<ctas, cfg->threads, smem, st>>>(mapV, mapS, mapR, mapD, g); ISR_COUNT_LAUNCH();
   if (want_stats) {
     reduce_part_kernel<<<(n + 3) / 4, 128, 0, st>>>(ctas, g.part_ld, n, nstat, p->d_acc.p, out.sum_bcs, out.ratio_stats); ISR_COUNT_LAUNCH();
   }
@@ -235,19 +216,11 @@ static int launch_fused(isr_problem* p, int64_t T, const double* V_dev, const do
 // triangular factors (linear interpolation without energy spread) are left as they are.  Opt-in, because cuSOLVER's
 // Householder QR costs 0.6 ms at N = 200 (1.8 ms at N = 500): it pays from about 10^6 toys per factorisation.
 static int ensure_rop_triangular(isr_problem* p) {
-  if (p->rop_tri_known) return ISR_OK;
   const int n = p->n, ld = (n + 1) & ~1;
-  cudaStream_t st = p->ctx->stream;
-  int flags[2] = {0, 0};
-  ISR_CUDA(cudaMemcpyAsync(flags, p->d_tri.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
-  ISR_CUDA(cudaStreamSynchronize(st));
-  if (!flags[1] && n >= 16) {
-    ISR_TRY(p->d_tmp.reserve((size_t)n * n));
-    ISR_TRY(ql_factor_rowmajor(p->ctx, n, ld, p->d_Rop.p, p->d_tmp.p, p->d_work, p->d_info));
-    static const int one = 1;
-    ISR_CUDA(cudaMemcpyAsync(p->d_tri.p + 1, &one, sizeof(int), cudaMemcpyHostToDevice, st));
-  }
-  p->rop_tri_known = true;
+  if (p->tri_sel[1] || n < 16) return ISR_OK;
+  ISR_TRY(p->d_tmp.reserve((size_t)n * n));
+  ISR_TRY(ql_factor_rowmajor(p->ctx, n, ld, p->d_Rop.p, p->d_tmp.p, p->d_work, p->d_info));
+  p->tri_sel[1] = 1;
   return ISR_OK;
 }
 

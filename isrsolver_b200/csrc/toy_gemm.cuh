@@ -33,6 +33,8 @@
 
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace isr {
@@ -80,10 +82,19 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       : "memory");
 }
 
+// TAG: the chunk body specialised for TAG skipped column tiles carries it as a PTX comment, which keeps the compiler
+// from merging the tails of the specialised bodies into one another (that splits the k loop of a body in two and
+// re-loads the A fragments: measured 33.4 -> 30.7 TFLOP/s on the dense schedule)
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
       : "+d"(c0), "+d"(c1)
       : "d"(a), "d"(b));
+}
+template <int TAG>
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1}; // body %4\n"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b), "n"(TAG));
 }
 
 struct ToyArgs {
@@ -97,7 +108,7 @@ struct ToyArgs {
   double* part;       // [gridDim.x][4][part_ld] per-CTA {sum b, count, sum r, sum r^2} or nullptr
   int part_ld, nstat; // nstat = 1 (sum only) or 4
   uint32_t* rhist;    // N x 1026 or nullptr
-  const int* tri;     // device flags {S, R}: operator is exactly lower triangular (B[n][k] == 0 for k > n), or nullptr
+  int tri;            // bit 0 / bit 1: the pass-1 / pass-2 operator is exactly lower triangular (B[n][k] == 0 for k > n)
 };
 
 // Position in the CTA's chunk stream.  Units: U1(i) = pass 1 of local tile i over all column blocks,
@@ -107,26 +118,14 @@ struct ToyArgs {
 // hold (a single tile, or an operator so small that a unit is shorter than STAGES-1 chunks) the
 // sequential order U1(i) NOP U2(i) is used instead, NOP being STAGES-1 empty chunks.
 enum { PH_P1 = 0, PH_P2 = 1, PH_NOP = 2 };
-template <int NP_, int KC_>
-struct Sched {
-  static constexpr int np = NP_, kcs = KC_;   // compile-time: the chunk count of a triangular column block is a division
+// Dense schedule: every column block has all nk chunks.
+struct SchedDense {
   int m, u;        // local tiles, unit index
   int nblk, nk, nop, do2, seq;
   int cb, kc;
-  int tri, ld;   // tri: bit 0 = pass-1 operator lower triangular, bit 1 = pass-2 operator.  Column block cb of a
-                          // triangular operator only has non-zero K below (cb + 1) * np: the chunks beyond are not loaded
-  __device__ int nk_tri(int b, int pass2) const {
-    if (!((tri >> pass2) & 1)) return nk;
-    const int lim = min(ld, (b + 1) * np);
-    return (lim + kcs - 1) / kcs;
-  }
-  __device__ int nk_of(int b) const { return nk_tri(b, kind() == PH_P2); }
-  __device__ void init(int m_, int nblk_, int nk_, int nop_, int do2_, int tri_, int ld_) {
+  __device__ void init(int m_, int nblk_, int nk_, int nop_, int do2_, int, int) {
     m = m_; nblk = nblk_; nk = nk_; nop = nop_; do2 = do2_; u = 0; cb = 0; kc = 0;
-    tri = tri_; ld = ld_;
-    int t1 = 0, t2 = 0;
-    for (int b = 0; b < nblk; ++b) { t1 += nk_tri(b, 0); t2 += nk_tri(b, 1); }
-    seq = (m == 1) || (min(t1, t2) < nop);
+    seq = (m == 1) || (nk * nblk < nop);
   }
   __device__ int units() const { return do2 ? (seq ? 3 * m : 2 * m) : m; }
   __device__ bool done() const { return u >= units(); }
@@ -144,14 +143,69 @@ struct Sched {
     if (u == 2 * m - 1) return m - 1;
     return (u & 1) ? (u + 1) / 2 : u / 2 - 1;
   }
+  __device__ bool last_chunk() const { return kc == nk - 1; }   // of the current column block
   __device__ void advance() {
     if (kind() == PH_NOP) {
       if (++kc == nop) { kc = 0; ++u; }
       return;
     }
-    if (++kc == nk_of(cb)) {
+    if (++kc == nk) {
       kc = 0;
       if (++cb == nblk) { cb = 0; ++u; }
+    }
+  }
+};
+// Triangular schedule (at least one operator exactly lower triangular): the chunk count depends on the pass and the
+// column block.
+template <int NP_, int KC_>
+struct SchedTri {
+  static constexpr int np = NP_, kcs = KC_;   // compile-time: the chunk count of a triangular column block is a division
+  int m, u;        // local tiles, unit index
+  int nblk, nk, nop, do2, seq;
+  int cb, kc;
+  int tri, ld;   // tri: bit 0 = pass-1 operator lower triangular, bit 1 = pass-2 operator.  Column block cb of a
+                          // triangular operator only has non-zero K below (cb + 1) * np: the chunks beyond are not loaded
+  __device__ int nk_tri(int b, int pass2) const {
+    if (!((tri >> pass2) & 1)) return nk;
+    const int lim = min(ld, (b + 1) * np);
+    return (lim + kcs - 1) / kcs;
+  }
+  int knd, cnk;   // kind and chunk count of the current (unit, column block): refreshed on transitions only
+  __device__ void refresh() {
+    knd = kind_of_unit();
+    cnk = knd == PH_NOP ? nop : nk_tri(cb, knd == PH_P2);
+  }
+  __device__ void init(int m_, int nblk_, int nk_, int nop_, int do2_, int tri_, int ld_) {
+    m = m_; nblk = nblk_; nk = nk_; nop = nop_; do2 = do2_; u = 0; cb = 0; kc = 0;
+    tri = tri_; ld = ld_;
+    int t1 = 0, t2 = 0;
+    for (int b = 0; b < nblk; ++b) { t1 += nk_tri(b, 0); t2 += nk_tri(b, 1); }
+    seq = (m == 1) || (min(t1, t2) < nop);
+    refresh();
+  }
+  __device__ int units() const { return do2 ? (seq ? 3 * m : 2 * m) : m; }
+  __device__ bool done() const { return u >= units(); }
+  __device__ int kind() const { return knd; }
+  __device__ int kind_of_unit() const {
+    if (!do2) return PH_P1;
+    if (seq) { const int r = u % 3; return r == 0 ? PH_P1 : (r == 1 ? PH_NOP : PH_P2); }
+    if (u == 0) return PH_P1;
+    if (u == 2 * m - 1) return PH_P2;
+    return (u & 1) ? PH_P1 : PH_P2;
+  }
+  __device__ int tile() const {   // local tile index
+    if (!do2) return u;
+    if (seq) return u / 3;
+    if (u == 0) return 0;
+    if (u == 2 * m - 1) return m - 1;
+    return (u & 1) ? (u + 1) / 2 : u / 2 - 1;
+  }
+  __device__ bool last_chunk() const { return kc == cnk - 1; }   // of the current column block
+  __device__ void advance() {
+    if (++kc == cnk) {
+      kc = 0;
+      if (knd == PH_NOP || ++cb == nblk) { cb = 0; ++u; }
+      refresh();
     }
   }
 };
@@ -166,7 +220,9 @@ __device__ __forceinline__ void dispatch_jmin(int jmin, F&& f) {
   }
 }
 
-template <int WM, int WN, int AT, int BT, int STAGES, int KC>
+// TRI = false is the dense kernel (every structure of the triangular schedule compiled out: it costs the dense schedule
+// 1.6 % when merely present -- measured, tools/exp_time.py); TRI = true is launched when an operator is triangular.
+template <int WM, int WN, int AT, int BT, int STAGES, int KC, bool TRI = false>
 __global__ void __launch_bounds__(WM * WN * 32, 1)
 toy_fused_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapS,
                  const __grid_constant__ CUtensorMap mapR, const __grid_constant__ CUtensorMap mapD, ToyArgs g) {
@@ -188,7 +244,10 @@ toy_fused_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant
   double* sRowBase = reinterpret_cast<double*>(bars + 2 * STAGES + kRingSlots + 1);
   double* sAcc = sRowBase + 2 * WN * TM;
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // TRI: broadcast from lane 0 so that the compiler knows the warp index -- and the triangular-schedule branches that
+  // depend on it -- to be warp-uniform (otherwise every mma.sync behind such a branch gets a WARPSYNC)
+  const int warp = TRI ? __shfl_sync(0xffffffffu, tid >> 5, 0) : tid >> 5;
   const int nk = (g.ld + kKC - 1) / kKC;
   const int64_t ntiles = (g.T + TM - 1) / TM;
   const bool stats = g.part != nullptr;
@@ -198,7 +257,8 @@ toy_fused_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant
   const int ring_row0 = blockIdx.x * kRingSlots * TM;
 
   // issue the TMA loads of the chunk at schedule position `p` into stage st (one thread)
-  auto issue = [&](const Sched<NP, kKC>& p, int st) {
+  using SchedT = std::conditional_t<TRI, SchedTri<NP, kKC>, SchedDense>;
+  auto issue = [&](const SchedT& p, int st) {
     const int kind = p.kind();
     if (kind == PH_NOP) { mbar_arrive(&full[st]); return; }   // keeps the stage's phase in step
     mbar_arrive_expect_tx(&full[st], STAGE_BYTES);
@@ -215,9 +275,8 @@ toy_fused_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant
     }
   };
 
-  Sched<NP, kKC> pf;   // schedule position of the chunk STAGES ahead of the one this warp consumes
-  const int tri = g.tri ? (g.tri[0] | (g.tri[1] << 1)) : 0;
-  pf.init(m, g.nblk, nk, STAGES - 1, g.do2, tri, g.ld);
+  SchedT pf;   // schedule position of the chunk STAGES ahead of the one this warp consumes
+  pf.init(m, g.nblk, nk, STAGES - 1, g.do2, g.tri, g.ld);
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); done[s] = 0; }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -235,12 +294,16 @@ toy_fused_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant
 
   const int wm = warp / WN, wn = warp % WN;
   const int gq = lane >> 2, c = lane & 3;
+  // column tile j of this warp within the CTA's column block: dealt cyclically, so that under the triangular schedule
+  // every warp keeps the same share of the work below the diagonal (the dense kernel uses the same map: the two
+  // schedules then sum in the same order and agree bit for bit)
+  auto ctile = [&](int j) { return j * WN + wn; };
   double* ring = g.do2 ? g.Dring + (size_t)blockIdx.x * kRingSlots * TM * g.ld : nullptr;
   auto consumer_barrier = [&]() { asm volatile("bar.sync 1, %0;\n" ::"n"(NCT) : "memory"); };
 
   if (m > 0) {
-    Sched<NP, kKC> q;
-    q.init(m, g.nblk, nk, STAGES - 1, g.do2, tri, g.ld);
+    SchedT q;
+    q.init(m, g.nblk, nk, STAGES - 1, g.do2, g.tri, g.ld);
     int s = 0, parity = 0;
     uint32_t ph = 0;
     double acc[AT][BT][2];
@@ -257,19 +320,7 @@ toy_fused_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant
       const double* sA = stage0 + (size_t)s * ROWS * kKC;
       const double* sB = sA + TM * kKC;
       const int ksteps = min(kKC, g.ld - q.kc * kKC + 7) / 8;  // 8 physical k per double-step
-      // Lower-triangular operator (B[n][k] == 0 for k > n): column tile j of this warp, columns
-      // n0 + (j * WN + wn) * 8 .. + 8, has non-zeros in this chunk (k >= kc * KC) only if j * WN + wn >= kt0, the chunk's
-      // first k-tile counted from column n0.  The fragment loads and DMMAs of the tiles j < jm are skipped -- by real
-      // branches into a body specialised for jm: a predicated-off DMMA still occupies the pipe (measured, no gain) and
-      // a per-k-step test costs more instructions than the zeros it saves (ncu: 60 % DMMA-busy against 75 %).  The
-      // column tiles are dealt to the warps cyclically so that every warp keeps the same share of the work.
-      int jm = 0;
-      if ((tri >> (kind == PH_P2)) & 1) {
-        const int need = (q.kc * kKC - q.cb * NP) / 8 - wn;
-        jm = need <= 0 ? 0 : (need + WN - 1) / WN;
-      }
-      dispatch_jmin<0, BT>(jm, [&](auto jmc) {
-        constexpr int JM = decltype(jmc)::value;
+      if constexpr (!TRI) {
 #pragma unroll
         for (int kp = 0; kp < kKC / 8; ++kp) {
           if (kp < ksteps) {
@@ -278,21 +329,57 @@ toy_fused_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant
             for (int i = 0; i < AT; ++i)
               a[i] = *reinterpret_cast<const double2*>(sA + ((wm * AT + i) * 8 + gq) * kKC + kp * 8 + 2 * c);
 #pragma unroll
-            for (int j = JM; j < BT; ++j)
+            for (int j = 0; j < BT; ++j)
               b[j] = *reinterpret_cast<const double2*>(sB + ((j * WN + wn) * 8 + gq) * kKC + kp * 8 + 2 * c);
 #pragma unroll
             for (int i = 0; i < AT; ++i)
 #pragma unroll
-              for (int j = JM; j < BT; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
+              for (int j = 0; j < BT; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
 #pragma unroll
             for (int i = 0; i < AT; ++i)
 #pragma unroll
-              for (int j = JM; j < BT; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
+              for (int j = 0; j < BT; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
           }
         }
-      });
+      } else {
+        // Lower-triangular operator (B[n][k] == 0 for k > n): column tile j of this warp, columns
+        // n0 + (j * WN + wn) * 8 .. + 8, has non-zeros in this chunk (k >= kc * KC) only if j * WN + wn >= kt0, the
+        // chunk's first k-tile counted from column n0.  The fragment loads and DMMAs of the tiles j < jm are skipped -- by
+        // real branches into a body specialised for jm: a predicated-off DMMA still occupies the pipe (measured, no gain)
+        // and a per-k-step test costs more instructions than the zeros it saves (ncu: 60 % DMMA-busy against 75 %).
+        int jm = 0;
+        if ((g.tri >> (kind == PH_P2)) & 1) {
+          const int need = (q.kc * kKC - q.cb * NP) / 8 - wn;
+          jm = need <= 0 ? 0 : (need + WN - 1) / WN;
+        }
+        auto body = [&](auto jmc) {
+          constexpr int JM = decltype(jmc)::value;
+#pragma unroll
+          for (int kp = 0; kp < kKC / 8; ++kp) {
+            if (kp < ksteps) {
+              double2 a[AT], b[BT];
+#pragma unroll
+              for (int i = 0; i < AT; ++i)
+                a[i] = *reinterpret_cast<const double2*>(sA + ((wm * AT + i) * 8 + gq) * kKC + kp * 8 + 2 * c);
+#pragma unroll
+              for (int j = JM; j < BT; ++j)
+                b[j] = *reinterpret_cast<const double2*>(sB + ((j * WN + wn) * 8 + gq) * kKC + kp * 8 + 2 * c);
+#pragma unroll
+              for (int i = 0; i < AT; ++i)
+#pragma unroll
+                for (int j = JM; j < BT; ++j) dmma884<JM>(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
+#pragma unroll
+              for (int i = 0; i < AT; ++i)
+#pragma unroll
+                for (int j = JM; j < BT; ++j) dmma884<JM>(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
+            }
+          }
+        };
+        if (jm == 0) body(IntC<0>{});   // a dense pass of a half-triangular pair never reaches the jump table below
+        else dispatch_jmin<1, BT>(jm, body);
+      }
 
-      if (q.kc == q.nk_of(q.cb) - 1) {
+      if (q.last_chunk()) {
         const int lt = q.tile();
         const int64_t t0 = ((int64_t)blockIdx.x + (int64_t)lt * gridDim.x) * TM;
         const int n0 = q.cb * NP;
@@ -301,7 +388,7 @@ toy_fused_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant
           double* Dt = g.do2 ? ring + (size_t)(lt % kRingSlots) * TM * g.ld : g.Dfull + t0 * g.ld;
 #pragma unroll
           for (int j = 0; j < BT; ++j) {
-            const int col = n0 + (j * WN + wn) * 8 + 2 * c;
+            const int col = n0 + ctile(j) * 8 + 2 * c;
             const bool ok0 = col < g.N, ok1 = col + 1 < g.N;
             const double b00 = ok0 ? g.b0[col] : 0.0, b01 = ok1 ? g.b0[col + 1] : 0.0;
             double cs[2] = {0, 0}, cn[2] = {0, 0}, cr[2] = {0, 0}, cq[2] = {0, 0};
@@ -357,7 +444,7 @@ toy_fused_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant
                   }
                 }
                 if (gq == 0) {
-                  const int lc = n0 + (j * WN + wn) * 8 + 2 * c + e;
+                  const int lc = n0 + ctile(j) * 8 + 2 * c + e;
                   double* pp = sAcc + (size_t)wm * g.nstat * accw;
                   pp[lc] += cs[e];
                   if (g.nstat == 4) {
