@@ -409,11 +409,15 @@ def other_assemblies(lib, ctx, stream, torch):
 def other_chi2_tests(lib, ctx, stream, torch, dev):
     """The same step (assemble + factor + toys + min/max + TH1F) at the other BASELINE.json chi2-test sizes, V resident,
     this rank only: C2 = N 100, cubic, 100k toys (configs[1]); C5 = N 500, linear, 2^17 toys (the per-GPU share of
-    1M toys on 8 GPUs) with the ratio statistics on top.  CUDA events, mean of 5 after 2 warm-ups."""
+    1M toys on 8 GPUs) with the ratio statistics on top -- lower-triangular operators, so the toy kernel runs its
+    triangular schedule (about 2 N^2 flop per toy executed); and the north-star target's per-GPU share: N 200, cubic,
+    2^17 toys (1M toys on 8 GPUs), with the fraction of the FP64 roofline the WHOLE test reaches (4 N^2 T flop over the
+    time of assembly + factorisation + toys + histogram).  CUDA events, mean of 5 after 2 warm-ups."""
     from isrsolver_b200 import _lib as L
     out = {}
     for name, n, cubic, T, ratio in (("c2_n100_cubic_100k_toys", 100, True, 100000, False),
-                                     ("c5_n500_linear_131072_toys_ratio", 500, False, 1 << 17, True)):
+                                     ("c5_n500_linear_131072_toys_ratio", 500, False, 1 << 17, True),
+                                     ("target_n200_cubic_131072_toys", 200, True, 1 << 17, False)):
         ecm = np.linspace(E_MIN, E_MAX, n)
         st = np.ascontiguousarray([[0, 0, 0], [1, 1, n - 1]] if cubic else [[0, 0, n - 1]], dtype=np.int32)
         p = C.c_void_p()
@@ -448,7 +452,10 @@ def other_chi2_tests(lib, ctx, stream, torch, dev):
         e1.synchronize()
         assert int(h.sum()) == T
         ms = e0.elapsed_time(e1) / 5
-        out[name] = {"ms_per_test": ms, "toys_per_s": T / (ms * 1e-3), "n_points": n, "toys": T}
+        out[name] = {"ms_per_test": ms, "toys_per_s": T / (ms * 1e-3), "n_points": n, "toys": T,
+                     "toy_schedule": "dense (4 N^2 flop/toy)" if cubic else "triangular (about 2 N^2 flop/toy executed)"}
+        if cubic:
+            out[name]["whole_test_frac_of_fp64_peak"] = 4.0 * n * n * T / (ms * 1e-3) * 1e-12 / FP64_PEAK_TFLOPS
         lib.isr_problem_destroy(p)
     return out
 

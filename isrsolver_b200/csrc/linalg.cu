@@ -4,6 +4,7 @@
 // tikhonov.cu.  All matrices here are column-major (Eigen / LAPACK convention).
 #include "linalg.hpp"
 
+
 namespace isr {
 
 __global__ void set_identity_kernel(int n, double* __restrict__ A) {
@@ -76,18 +77,20 @@ static int check_info(isr_ctx* c, const int* d_info, const char* what) {
   return ISR_OK;
 }
 
-// out[0] = max |(A X)(i, j) - delta_ij| over the n x n product P = A X (column-major): one block, fixed order.
-// out[1] / out[2] = max |X(i, j)| / max |A(i, j)| over j > i: both zero iff X / A is exactly lower triangular.
-__global__ void __launch_bounds__(1024) inverse_residual_kernel(int n, const double* __restrict__ P, const double* __restrict__ X,
-                                                                const double* __restrict__ A, double* __restrict__ out) {
-  __shared__ double smax[3][32];
+// out[0] = max |(A X)(i, j) - delta_ij| over the n x n product P = A X (column-major); out[1] / out[2] = +inf unless
+// X / A is exactly lower triangular.  `out` is zeroed by the caller; non-negative doubles order like their bit patterns,
+// so the blocks combine with an integer atomicMax (the maximum does not depend on the order).
+__global__ void __launch_bounds__(256) inverse_residual_kernel(int n, const double* __restrict__ P, const double* __restrict__ X,
+                                                               const double* __restrict__ A, double* __restrict__ out) {
+  __shared__ double smax[3][8];
   double m = 0.0, ux = 0.0, ua = 0.0;
-  for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
-    const int i = idx % n, j = idx / n;
+  const int j = blockIdx.x;   // one column per block
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const size_t idx = (size_t)i + (size_t)n * j;
     if (P) {
       const double v = P[idx] - ((i == j) ? 1.0 : 0.0);
-      m = fmax(m, fabs(v));          // NaN-safe below: a NaN product fails the !(r <= tol) test on the host
-      if (v != v) m = INFINITY;
+      m = fmax(m, fabs(v));
+      if (v != v) m = INFINITY;           // a NaN product must fail the (r <= tol) test on the host
     }
     if (j > i) {
       if (X[idx] != 0.0) ux = INFINITY;   // (NaN != 0 too)
@@ -101,15 +104,211 @@ __global__ void __launch_bounds__(1024) inverse_residual_kernel(int n, const dou
   }
   if ((threadIdx.x & 31) == 0) { smax[0][threadIdx.x >> 5] = m; smax[1][threadIdx.x >> 5] = ux; smax[2][threadIdx.x >> 5] = ua; }
   __syncthreads();
-  if (threadIdx.x < 32) {
-    m = smax[0][threadIdx.x]; ux = smax[1][threadIdx.x]; ua = smax[2][threadIdx.x];
-    for (int s = 16; s >= 1; s >>= 1) {
-      m = fmax(m, __shfl_xor_sync(0xffffffffu, m, s));
-      ux = fmax(ux, __shfl_xor_sync(0xffffffffu, ux, s));
-      ua = fmax(ua, __shfl_xor_sync(0xffffffffu, ua, s));
-    }
-    if (threadIdx.x == 0) { out[0] = m; out[1] = ux; out[2] = ua; }
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { m = fmax(m, smax[0][w]); ux = fmax(ux, smax[1][w]); ua = fmax(ua, smax[2][w]); }
+    unsigned long long* o = reinterpret_cast<unsigned long long*>(out);
+    atomicMax(o, (unsigned long long)__double_as_longlong(m));
+    if (ux != 0.0) atomicMax(o + 1, (unsigned long long)__double_as_longlong(ux));
+    if (ua != 0.0) atomicMax(o + 2, (unsigned long long)__double_as_longlong(ua));
   }
+}
+
+// --------------------------------------------------------------------------------------------------
+// X = A^-1 by in-place Gauss-Jordan elimination without pivoting, the matrix resident in the REGISTER FILES of a
+// 4-CTA thread-block cluster (N <= 256).  cuSOLVER's getrf + getrs need 0.3 ms at N = 200 -- almost all of it the
+// latency of two dozen dependent panel / trsm launches -- which is a third of a 131k-toy chi2 test; here one launch
+// does the N dependent rank-1 steps.
+//
+// CTA c owns rows [c R, (c+1) R), R = ceil(N / 4); thread (i, s) holds the 32-column strip s of row i in registers,
+// the 8 strips of a row in 8 consecutive lanes (4 rows per warp); the row buffers interleave the strips ([column pair]
+// [strip][2]) so that those 8 lanes read and write 128 contiguous bytes (strip-major they collide 8-way: 3.5 us per
+// step at N = 200).  Step k:
+//   * the multiplier a_ik comes from lane s = k / 32 of the row by a warp shuffle;
+//   * the 8 lanes that own row k store its raw strips to a staging buffer and ONE lane sends them to the row buffer of
+//     every CTA with a bulk shared->distributed-shared copy (cp.async.bulk.shared::cluster.shared::cta) that completes
+//     tx-bytes on the destination's `full` mbarrier: no cluster barrier and no cluster-scope fence on the critical path.
+//     Measured per step at N = 200: cluster.sync() per step 1.85 us (it carries a MEMBAR.ALL.GPU, and so does every
+//     .release.cluster / .acquire.cluster mbarrier operation); st.async 16-byte stores from registers 1.25 us; this
+//     version 1.07 us, of which about 0.8 us is the latency of the copy + remote completion itself (N = 50: 0.84 us);
+//   * every thread waits on its CTA's `full` barrier and updates its strip from registers:
+//       pivot row:  a_kj <- a_kj / p,  a_kk <- 1 / p        other rows:  a_ij <- a_ij - (a_ik / p) a_kj,  a_ik <- -a_ik / p
+//   * the two row buffers alternate with the parity of k; a warp that has consumed step k arrives on its CTA's `done`
+//     barrier, and one extra warp per CTA forwards each completed `done` phase as ONE credit (remote mbarrier arrive) to
+//     the `empty` barrier of the CTA that owns row k + 2, whose owner warp waits for the four credits before it
+//     overwrites the buffer.  (Remote arrives serialise at about 60 ns each at the target: one per warp instead of one
+//     per CTA made a step 3.5 us at N = 200.)
+// A lower-triangular A yields an exactly lower-triangular inverse (the updates above the diagonal subtract exact
+// zeros).  No pivoting: the caller certifies the result (lu_inverse) and falls back to the pivoted LU otherwise.
+// --------------------------------------------------------------------------------------------------
+constexpr int kGjCtas = 4, kGjMaxN = 256, kGjColsPerLane = kGjMaxN / 32;   // 8 columns (4 pairs) per lane
+constexpr int kGjMaxRows = 240;   // 15 arithmetic warps + the forwarder = 512 threads per CTA: 128 registers each
+namespace gj {
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(s32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(s32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "GJ_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra GJ_DONE;\n"
+      "bra GJ_WAIT;\n"
+      "GJ_DONE:\n"
+      "}\n" ::"r"(s32(bar)), "r"(parity) : "memory");
+}
+// Default semantics (release at CTA scope), as in CUTLASS's ClusterBarrier::arrive(cta_id): what the credit protects is
+// a later async-proxy overwrite of a buffer this warp has finished reading.  The .release.cluster / .acquire.cluster forms
+// compile to MEMBAR.ALL.GPU / CCTL.IVALL and cost 1.8 us per step (measured: slower than cuSOLVER).
+__device__ __forceinline__ void mbar_remote_arrive(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_smem_to_cluster(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t mbar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(mbar_cluster) : "memory");
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+}  // namespace gj
+
+__global__ void __cluster_dims__(kGjCtas, 1, 1) __launch_bounds__(512, 1)
+gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, double* __restrict__ cert) {
+  constexpr int kRowDoubles = kGjMaxN;                         // one pivot row, columns in natural order
+  constexpr uint32_t kRowBytes = kRowDoubles * sizeof(double);
+  __shared__ __align__(128) double rowbuf[2][4][kRowDoubles];  // the 4 pivot rows of a block, as received
+  __shared__ __align__(128) double stage[2][4][kRowDoubles];   // the same, as produced by the owner warp
+  __shared__ __align__(8) uint64_t full[2], empty[2], done[2];
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(rank));
+  const int R = 4 * ((n + 4 * kGjCtas - 1) / (4 * kGjCtas));   // rows per CTA: whole warps
+  const int NB = (n + 3) / 4;                                  // pivot blocks
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int nwarps = (blockDim.x >> 5) - 1;   // arithmetic warps; the last warp forwards the credits
+  const int row0 = (int)rank * R, wrow = row0 + 4 * warp;      // first of this warp's four rows
+  auto block_bytes = [&](int B) { return (uint32_t)min(4, n - 4 * B) * kRowBytes; };
+  if (tid == 0) {
+    if (rank == 0) cert[0] = cert[1] = cert[2] = 0.0;   // the certificate scalars inverse_residual_kernel maximises into
+    for (int b = 0; b < 2; ++b) { gj::mbar_init(&full[b], 1); gj::mbar_init(&empty[b], kGjCtas); gj::mbar_init(&done[b], nwarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    gj::mbar_expect_tx(&full[0], block_bytes(0));           // blocks 0 and 1
+    if (NB > 1) gj::mbar_expect_tx(&full[1], block_bytes(1));
+  }
+  // a[r][2 i + e] = A(wrow + r, 2 (lane + 32 i) + e): four rows x four column pairs per lane
+  double a[4][kGjColsPerLane];
+  if (warp < nwarps) {
+#pragma unroll
+    for (int j = 0; j < kGjColsPerLane; ++j) {
+      const int col = 2 * (lane + 32 * (j >> 1)) + (j & 1);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) a[r][j] = (wrow + r < n && col < n) ? A[(size_t)(wrow + r) + (size_t)n * col] : 0.0;
+    }
+  }
+  gj::cluster_sync();   // barriers initialised and every CTA resident before the first remote access
+
+  if (warp == nwarps) {
+    // ---- credit forwarder: block B consumed by every arithmetic warp of this CTA -> one credit to the owner of block B + 2
+    for (int B = 0; B + 2 < NB; ++B) {
+      gj::mbar_wait(&done[B & 1], (uint32_t)(B >> 1) & 1u);
+      if (lane == 0) gj::mbar_remote_arrive(gj::mapa(gj::s32(&empty[B & 1]), (uint32_t)(4 * (B + 2) / R)));
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < kGjColsPerLane / 2; ++i) {
+      for (int q = 0; q < 16; ++q) {
+        const int k0 = 64 * i + 4 * q, B = k0 >> 2;   // pivots k0 .. k0 + 3: column pairs of lanes 2 q and 2 q + 1
+        if (k0 >= n) break;
+        const int b = B & 1;
+        const bool owner = k0 == wrow;                 // this warp's four rows ARE the pivot rows
+        if (owner) {
+          if (B >= 2) {   // wait until every warp of the cluster has consumed block B - 2 out of this buffer
+            int B0 = max(2, row0 >> 2);
+            if ((B0 ^ b) & 1) ++B0;
+            gj::mbar_wait(&empty[b], (uint32_t)((B - B0) >> 1) & 1u);
+          }
+        } else {
+          gj::mbar_wait(&full[b], (uint32_t)(B >> 1) & 1u);
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          if (k0 + t >= n) break;
+          const int j = 2 * i + (t & 1), lk = 2 * q + (t >> 1);   // column k0 + t is element j of lane lk
+          double m[4];                                             // a_ik of the four rows, before the step
+#pragma unroll
+          for (int r = 0; r < 4; ++r) m[r] = __shfl_sync(0xffffffffu, a[r][j], lk);
+          if (owner) {
+            // pivot row = this warp's row t: scale it (a_kj / p, a_kk <- 1 / p), eliminate it from the warp's other three
+            // rows straight from registers (every lane holds the same columns of all four rows), and stage it
+            const double pinv = 1.0 / m[t];
+#pragma unroll
+            for (int jj = 0; jj < kGjColsPerLane; ++jj) a[t][jj] *= pinv;
+            if (lane == lk) a[t][j] = pinv;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              if (r == t) continue;
+#pragma unroll
+              for (int jj = 0; jj < kGjColsPerLane; ++jj) a[r][jj] = fma(-m[r], a[t][jj], a[r][jj]);
+              if (lane == lk) a[r][j] = -m[r] * pinv;
+            }
+            double2* dst = reinterpret_cast<double2*>(&stage[b][t][0]) + lane;
+#pragma unroll
+            for (int ii = 0; ii < kGjColsPerLane / 2; ++ii) dst[32 * ii] = make_double2(a[t][2 * ii], a[t][2 * ii + 1]);
+          } else {
+            // a_ij <- a_ij - a_ik a'_kj (a' the scaled pivot row), a_ik <- -a_ik / p = -a_ik a'_kk
+            const double2* rk = reinterpret_cast<const double2*>(&rowbuf[b][t][0]) + lane;
+            double2 pr[kGjColsPerLane / 2];
+#pragma unroll
+            for (int ii = 0; ii < kGjColsPerLane / 2; ++ii) pr[ii] = rk[32 * ii];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+#pragma unroll
+              for (int ii = 0; ii < kGjColsPerLane / 2; ++ii) {
+                a[r][2 * ii] = fma(-m[r], pr[ii].x, a[r][2 * ii]);
+                a[r][2 * ii + 1] = fma(-m[r], pr[ii].y, a[r][2 * ii + 1]);
+              }
+              if (lane == lk) a[r][j] = -m[r] * ((t & 1) ? pr[i].y : pr[i].x);
+            }
+          }
+        }
+        if (owner) {
+          // the four scaled pivot rows, each as it was at its own step, to every CTA (this one included)
+          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < kGjCtas; ++c)
+              gj::bulk_smem_to_cluster(gj::mapa(gj::s32(&rowbuf[b][0][0]), c), gj::s32(&stage[b][0][0]), block_bytes(B),
+                                       gj::mapa(gj::s32(&full[b]), c));
+          }
+          gj::mbar_wait(&full[b], (uint32_t)(B >> 1) & 1u);   // keeps this warp in step with the buffer's phases
+        }
+        if (tid == 0 && B + 2 < NB) gj::mbar_expect_tx(&full[b], block_bytes(B + 2));   // this buffer's next use
+        // ---- this warp is done with the buffer (the forwarder turns the CTA's arrivals into one credit)
+        __syncwarp();
+        if (lane == 0 && B + 2 < NB) gj::mbar_arrive(&done[b]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kGjColsPerLane; ++j) {
+      const int col = 2 * (lane + 32 * (j >> 1)) + (j & 1);
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (wrow + r < n && col < n) X[(size_t)(wrow + r) + (size_t)n * col] = a[r][j];
+    }
+  }
+  gj::cluster_sync();   // no CTA may exit while its shared memory can still be the target of a remote copy or arrive
 }
 
 // Ainv = A^-1.  A (column-major, preserved) is factored in `lu` (n x n scratch, destroyed); `prod` is n x n scratch.
@@ -132,15 +331,21 @@ int lu_inverse(isr_ctx* c, int n, const double* A, double* lu, double* prod, dou
   ISR_TRY(info.reserve(2));
   double* resid_dev = work.p + lwork;
   // ---- fast path: no pivoting, certified by the residual
-  ISR_CUDA(cudaMemcpyAsync(lu, A, bytes, cudaMemcpyDeviceToDevice, c->stream));
-  ISR_CUSOLVER(cusolverDnDgetrf(c->solver, n, n, lu, n, work.p, nullptr, info.p));
-  set_identity_kernel<<<(n * n + 255) / 256, 256, 0, c->stream>>>(n, Ainv); ISR_COUNT_LAUNCH();
-  ISR_CUSOLVER(cusolverDnDgetrs(c->solver, CUBLAS_OP_N, n, n, lu, n, nullptr, Ainv, n, info.p + 1));
-  ISR_TRY(gemm(c, false, false, n, A, Ainv, prod));
-  inverse_residual_kernel<<<1, 1024, 0, c->stream>>>(n, prod, Ainv, A, resid_dev); ISR_COUNT_LAUNCH();
   int h_info[2] = {0, 0};
+  if (n <= kGjMaxRows) {
+    const int warps = (n + 4 * kGjCtas - 1) / (4 * kGjCtas);   // four rows per warp, whole warps per CTA
+    gj_inverse_kernel<<<kGjCtas, 32 * warps + 32, 0, c->stream>>>(n, A, Ainv, resid_dev); ISR_COUNT_LAUNCH();
+  } else {
+    ISR_CUDA(cudaMemsetAsync(resid_dev, 0, 3 * sizeof(double), c->stream));
+    ISR_CUDA(cudaMemcpyAsync(lu, A, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    ISR_CUSOLVER(cusolverDnDgetrf(c->solver, n, n, lu, n, work.p, nullptr, info.p));
+    set_identity_kernel<<<(n * n + 255) / 256, 256, 0, c->stream>>>(n, Ainv); ISR_COUNT_LAUNCH();
+    ISR_CUSOLVER(cusolverDnDgetrs(c->solver, CUBLAS_OP_N, n, n, lu, n, nullptr, Ainv, n, info.p + 1));
+    ISR_CUDA(cudaMemcpyAsync(h_info, info.p, sizeof(int) * 2, cudaMemcpyDeviceToHost, c->stream));
+  }
+  ISR_TRY(gemm(c, false, false, n, A, Ainv, prod));
+  inverse_residual_kernel<<<n, 256, 0, c->stream>>>(n, prod, Ainv, A, resid_dev); ISR_COUNT_LAUNCH();
   double resid[3] = {INFINITY, INFINITY, INFINITY};
-  ISR_CUDA(cudaMemcpyAsync(h_info, info.p, sizeof(int) * 2, cudaMemcpyDeviceToHost, c->stream));
   ISR_CUDA(cudaMemcpyAsync(resid, resid_dev, sizeof(resid), cudaMemcpyDeviceToHost, c->stream));
   ISR_CUDA(cudaStreamSynchronize(c->stream));
   tri[0] = resid[1] == 0.0;
@@ -152,7 +357,8 @@ int lu_inverse(isr_ctx* c, int n, const double* A, double* lu, double* prod, dou
   ISR_TRY(check_info(c, info.p, "LU factorisation (getrf)"));
   set_identity_kernel<<<(n * n + 255) / 256, 256, 0, c->stream>>>(n, Ainv); ISR_COUNT_LAUNCH();
   ISR_CUSOLVER(cusolverDnDgetrs(c->solver, CUBLAS_OP_N, n, n, lu, n, ipiv.p, Ainv, n, info.p));
-  inverse_residual_kernel<<<1, 1024, 0, c->stream>>>(n, nullptr, Ainv, A, resid_dev); ISR_COUNT_LAUNCH();
+  ISR_CUDA(cudaMemsetAsync(resid_dev, 0, 3 * sizeof(double), c->stream));
+  inverse_residual_kernel<<<n, 256, 0, c->stream>>>(n, nullptr, Ainv, A, resid_dev); ISR_COUNT_LAUNCH();
   ISR_CUDA(cudaMemcpyAsync(resid, resid_dev, sizeof(resid), cudaMemcpyDeviceToHost, c->stream));
   ISR_TRY(check_info(c, info.p, "LU solve (getrs)"));    // synchronises
   tri[0] = resid[1] == 0.0;     // row exchanges usually leave rounding residue above the diagonal

@@ -37,8 +37,6 @@ int factor(isr_problem* p, const double* vcs_err) {
   ISR_CUDA(cudaMemcpyAsync(p->d_werr.p, vcs_err, sizeof(double) * n, cudaMemcpyHostToDevice, st));
   ISR_TRY(p->d_tmp2.reserve(nn));
   ISR_TRY(lu_inverse(c, n, p->d_G.p, p->d_tmp.p, p->d_tmp2.p, p->d_Ginv.p, p->d_work, p->d_ipiv, p->d_info, p->tri_sle));
-  scale_rows(st, n, p->d_G.p, p->d_werr.p, 1, p->d_R.p);                  // R = diag(1/err) G
-  ISR_CUDA(cudaGetLastError());
   p->factored = true;
   p->cov_ready = false;      // Cov / G^T W G are formed on first use (ensure_cov): the toy path never reads them
   return select_sle(p);
@@ -59,13 +57,31 @@ int ensure_cov(isr_problem* p) {
   return ISR_OK;
 }
 
+// R = diag(1/err) G (column-major, as the covariance / Tikhonov code reads it) and the two operators the toy kernel
+// consumes, Sop = G^-1 and Rop = R, row-major with the leading dimension padded to even and a zero pad column: one launch.
+__global__ void sle_operators_kernel(int n, int ld, const double* __restrict__ G, const double* __restrict__ Ginv,
+                                     const double* __restrict__ err, double* __restrict__ R, double* __restrict__ Sop,
+                                     double* __restrict__ Rop) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * ld) return;
+  const int i = idx / ld, j = idx % ld;
+  double sv = 0.0, rv = 0.0;
+  if (j < n) {
+    const size_t cm = (size_t)i + (size_t)n * j;
+    sv = Ginv[cm];
+    rv = G[cm] / err[i];
+    R[cm] = rv;
+  }
+  Sop[idx] = sv;
+  Rop[idx] = rv;
+}
+
 // Operators the toy kernel consumes: row-major, leading dimension padded to even, pad column zero.
 int select_sle(isr_problem* p) {
   if (!p->factored) { set_error("select: isr_factor has not been called"); return ISR_ESTATE; }
   const int n = p->n, ld = (n + 1) & ~1;
   cudaStream_t st = p->ctx->stream;
-  colmajor_to_rowmajor(st, n, p->d_Ginv.p, nullptr, 0, p->d_Sop.p, ld);
-  colmajor_to_rowmajor(st, n, p->d_R.p, nullptr, 0, p->d_Rop.p, ld);
+  sle_operators_kernel<<<(n * ld + 255) / 256, 256, 0, st>>>(n, ld, p->d_G.p, p->d_Ginv.p, p->d_werr.p, p->d_R.p, p->d_Sop.p, p->d_Rop.p); ISR_COUNT_LAUNCH();
   ISR_CUDA(cudaGetLastError());
   p->tri_sel[0] = p->tri_sle[0];
   p->tri_sel[1] = p->tri_sle[1];

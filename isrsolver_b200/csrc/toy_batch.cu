@@ -116,7 +116,8 @@ static const std::vector<ToyCfg>& configs() {
       make_cfg<4, 5, 2, 5, 2>("m64n200w20s2"),         make_cfg<4, 4, 2, 4, 2>("m64n128w16s2"),   // smallest ring: large N with ratio statistics
       make_cfg<4, 5, 2, 5, 2, 40>("m64n200w20s2k40"),  make_cfg<4, 4, 2, 8, 2, 40>("m64n256w16s2k40"),
       make_cfg<8, 2, 2, 7, 2, 40>("m128n112w16s2k40"), make_cfg<4, 4, 2, 4, 2, 40>("m64n128w16s2k40"),
-      make_cfg<4, 4, 2, 4, 3, 40>("m64n128w16k40"),
+      make_cfg<4, 4, 2, 4, 3, 40>("m64n128w16k40"),   make_cfg<16, 1, 1, 13, 2, 40>("m128n104w16s2k40"),
+      make_cfg<16, 1, 1, 13, 3, 40>("m128n104w16k40"),
   };
   return v;
 }

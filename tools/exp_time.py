@@ -5,7 +5,7 @@ from isrsolver_b200 import _lib as L
 lib = L.load()
 ctx = C.c_void_p(); L.check(lib.isr_ctx_create(0, C.byref(ctx)))
 stream = torch.cuda.ExternalStream(lib.isr_ctx_stream(ctx))
-for n in (200,):
+for n in [int(a) for a in os.environ.get("N", "200").split(",")]:
     ecm = np.linspace(1.18, 2.0, n); st = np.ascontiguousarray([[0,0,0],[1,1,n-1]], dtype=np.int32); p = C.c_void_p()
     L.check(lib.isr_problem_create(ctx, n, L.dptr(ecm), 0.827, 2, L.iptr(st), None, C.byref(p)))
     G = np.empty((n,n)); L.check(lib.isr_assemble(p, None, L.dptr(G))); G = G.T.copy()
