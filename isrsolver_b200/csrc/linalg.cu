@@ -184,27 +184,46 @@ __device__ __forceinline__ void cluster_sync() {
 }
 }  // namespace gj
 
+constexpr int kGjSlots = 4;   // pivot blocks in flight: the owner chain runs ahead of the remote consumers by up to 4 blocks
+struct GjSmem {
+  double stage[kGjSlots][4][kGjMaxN];    // pivot blocks produced by this CTA (read by its own warps, source of the copies)
+  double rowbuf[kGjSlots][4][kGjMaxN];   // pivot blocks received from the other CTAs
+  uint64_t rfull[kGjSlots], lfull[kGjSlots], empty[kGjSlots], done[kGjSlots];
+};
+
 __global__ void __cluster_dims__(kGjCtas, 1, 1) __launch_bounds__(512, 1)
 gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, double* __restrict__ cert) {
-  constexpr int kRowDoubles = kGjMaxN;                         // one pivot row, columns in natural order
-  constexpr uint32_t kRowBytes = kRowDoubles * sizeof(double);
-  __shared__ __align__(128) double rowbuf[2][4][kRowDoubles];  // the 4 pivot rows of a block, as received
-  __shared__ __align__(128) double stage[2][4][kRowDoubles];   // the same, as produced by the owner warp
-  __shared__ __align__(8) uint64_t full[2], empty[2], done[2];
+  constexpr uint32_t kRowBytes = kGjMaxN * sizeof(double);
+  extern __shared__ __align__(128) unsigned char gj_smem_raw[];
+  GjSmem& sm = *reinterpret_cast<GjSmem*>(gj_smem_raw);
   uint32_t rank;
   asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(rank));
   const int R = 4 * ((n + 4 * kGjCtas - 1) / (4 * kGjCtas));   // rows per CTA: whole warps
-  const int NB = (n + 3) / 4;                                  // pivot blocks
+  const int NB = (n + 3) / 4;                                  // pivot blocks; block B = rows / pivots 4 B .. 4 B + 3
   const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int nwarps = (blockDim.x >> 5) - 1;   // arithmetic warps; the last warp forwards the credits
   const int row0 = (int)rank * R, wrow = row0 + 4 * warp;      // first of this warp's four rows
+  const int Bs = row0 >> 2, Be = min(NB, Bs + (R >> 2));       // blocks whose pivot rows this CTA owns
   auto block_bytes = [&](int B) { return (uint32_t)min(4, n - 4 * B) * kRowBytes; };
+  auto owned = [&](int B) { return B >= Bs && B < Be; };
+  auto below = [&](int x, int slot) { return x <= 0 ? 0 : (x + kGjSlots - 1 - slot) / kGjSlots; };   // #{y in [0, x): y = slot mod 4}
+  // next block after B in the same slot that arrives from another CTA (its rfull phase needs an expect_tx), or -1
+  auto next_remote = [&](int B) {
+    for (B += kGjSlots; B < NB; B += kGjSlots)
+      if (!owned(B)) return B;
+    return -1;
+  };
   if (tid == 0) {
     if (rank == 0) cert[0] = cert[1] = cert[2] = 0.0;   // the certificate scalars inverse_residual_kernel maximises into
-    for (int b = 0; b < 2; ++b) { gj::mbar_init(&full[b], 1); gj::mbar_init(&empty[b], kGjCtas); gj::mbar_init(&done[b], nwarps); }
+    for (int q = 0; q < kGjSlots; ++q) {
+      gj::mbar_init(&sm.rfull[q], 1); gj::mbar_init(&sm.lfull[q], 1);
+      gj::mbar_init(&sm.empty[q], kGjCtas); gj::mbar_init(&sm.done[q], nwarps);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    gj::mbar_expect_tx(&full[0], block_bytes(0));           // blocks 0 and 1
-    if (NB > 1) gj::mbar_expect_tx(&full[1], block_bytes(1));
+    for (int q = 0; q < kGjSlots; ++q) {    // first block of every slot that comes from another CTA
+      const int B = (q < NB && !owned(q)) ? q : next_remote(q);
+      if (B >= 0 && B < NB) gj::mbar_expect_tx(&sm.rfull[q], block_bytes(B));
+    }
   }
   // a[r][2 i + e] = A(wrow + r, 2 (lane + 32 i) + e): four rows x four column pairs per lane
   double a[4][kGjColsPerLane];
@@ -219,32 +238,43 @@ gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, d
   gj::cluster_sync();   // barriers initialised and every CTA resident before the first remote access
 
   if (warp == nwarps) {
-    // ---- credit forwarder: block B consumed by every arithmetic warp of this CTA -> one credit to the owner of block B + 2
-    for (int B = 0; B + 2 < NB; ++B) {
-      gj::mbar_wait(&done[B & 1], (uint32_t)(B >> 1) & 1u);
-      if (lane == 0) gj::mbar_remote_arrive(gj::mapa(gj::s32(&empty[B & 1]), (uint32_t)(4 * (B + 2) / R)));
+    // ---- credit forwarder: block B consumed by every arithmetic warp of this CTA -> one credit to the owner of block B + 4
+    for (int B = 0; B < NB; ++B) {
+      const int q = B & (kGjSlots - 1);
+      gj::mbar_wait(&sm.done[q], (uint32_t)(B / kGjSlots) & 1u);
+      if (lane == 0 && B + kGjSlots < NB)
+        gj::mbar_remote_arrive(gj::mapa(gj::s32(&sm.empty[q]), (uint32_t)(4 * (B + kGjSlots) / R)));
     }
   } else {
 #pragma unroll
     for (int i = 0; i < kGjColsPerLane / 2; ++i) {
-      for (int q = 0; q < 16; ++q) {
-        const int k0 = 64 * i + 4 * q, B = k0 >> 2;   // pivots k0 .. k0 + 3: column pairs of lanes 2 q and 2 q + 1
+      for (int qq = 0; qq < 16; ++qq) {
+        const int k0 = 64 * i + 4 * qq, B = k0 >> 2;   // pivots k0 .. k0 + 3: column pairs of lanes 2 qq and 2 qq + 1
         if (k0 >= n) break;
-        const int b = B & 1;
+        const int q = B & (kGjSlots - 1);
+        const bool local = owned(B);                   // produced by a warp of this CTA: read from `stage`
         const bool owner = k0 == wrow;                 // this warp's four rows ARE the pivot rows
+        const double* src = local ? &sm.stage[q][0][0] : &sm.rowbuf[q][0][0];
         if (owner) {
-          if (B >= 2) {   // wait until every warp of the cluster has consumed block B - 2 out of this buffer
-            int B0 = max(2, row0 >> 2);
-            if ((B0 ^ b) & 1) ++B0;
-            gj::mbar_wait(&empty[b], (uint32_t)((B - B0) >> 1) & 1u);
+          if (B >= kGjSlots) {   // every warp of the cluster has consumed block B - 4 out of this slot
+            int B0 = max(kGjSlots, Bs);
+            B0 += (q - B0) & (kGjSlots - 1);
+            gj::mbar_wait(&sm.empty[q], (uint32_t)((B - B0) / kGjSlots) & 1u);
           }
+        } else if (local) {
+          gj::mbar_wait(&sm.lfull[q], (uint32_t)(below(B, q) - below(Bs, q)) & 1u);
         } else {
-          gj::mbar_wait(&full[b], (uint32_t)(B >> 1) & 1u);
+          const int mine_before = B < Bs ? 0 : below(Be, q) - below(Bs, q);
+          gj::mbar_wait(&sm.rfull[q], (uint32_t)(below(B, q) - mine_before) & 1u);
+          if (tid == 0) {                                // this slot's next block from another CTA
+            const int Bn = next_remote(B);
+            if (Bn >= 0) gj::mbar_expect_tx(&sm.rfull[q], block_bytes(Bn));
+          }
         }
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           if (k0 + t >= n) break;
-          const int j = 2 * i + (t & 1), lk = 2 * q + (t >> 1);   // column k0 + t is element j of lane lk
+          const int j = 2 * i + (t & 1), lk = 2 * qq + (t >> 1);   // column k0 + t is element j of lane lk
           double m[4];                                             // a_ik of the four rows, before the step
 #pragma unroll
           for (int r = 0; r < 4; ++r) m[r] = __shfl_sync(0xffffffffu, a[r][j], lk);
@@ -262,12 +292,12 @@ gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, d
               for (int jj = 0; jj < kGjColsPerLane; ++jj) a[r][jj] = fma(-m[r], a[t][jj], a[r][jj]);
               if (lane == lk) a[r][j] = -m[r] * pinv;
             }
-            double2* dst = reinterpret_cast<double2*>(&stage[b][t][0]) + lane;
+            double2* dst = reinterpret_cast<double2*>(&sm.stage[q][t][0]) + lane;
 #pragma unroll
             for (int ii = 0; ii < kGjColsPerLane / 2; ++ii) dst[32 * ii] = make_double2(a[t][2 * ii], a[t][2 * ii + 1]);
           } else {
             // a_ij <- a_ij - a_ik a'_kj (a' the scaled pivot row), a_ik <- -a_ik / p = -a_ik a'_kk
-            const double2* rk = reinterpret_cast<const double2*>(&rowbuf[b][t][0]) + lane;
+            const double2* rk = reinterpret_cast<const double2*>(src + t * kGjMaxN) + lane;
             double2 pr[kGjColsPerLane / 2];
 #pragma unroll
             for (int ii = 0; ii < kGjColsPerLane / 2; ++ii) pr[ii] = rk[32 * ii];
@@ -283,21 +313,23 @@ gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, d
           }
         }
         if (owner) {
-          // the four scaled pivot rows, each as it was at its own step, to every CTA (this one included)
+          // the four scaled pivot rows, each as it was at its own step: first to the warps of this CTA (the next owner
+          // is almost always one of them -- the critical chain never waits for a copy), then to the other CTAs
+          __syncwarp();
+          if (lane == 0) gj::mbar_arrive(&sm.lfull[q]);
           asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
           __syncwarp();
           if (lane == 0) {
 #pragma unroll
             for (int c = 0; c < kGjCtas; ++c)
-              gj::bulk_smem_to_cluster(gj::mapa(gj::s32(&rowbuf[b][0][0]), c), gj::s32(&stage[b][0][0]), block_bytes(B),
-                                       gj::mapa(gj::s32(&full[b]), c));
+              if (c != (int)rank)
+                gj::bulk_smem_to_cluster(gj::mapa(gj::s32(&sm.rowbuf[q][0][0]), c), gj::s32(&sm.stage[q][0][0]), block_bytes(B),
+                                         gj::mapa(gj::s32(&sm.rfull[q]), c));
           }
-          gj::mbar_wait(&full[b], (uint32_t)(B >> 1) & 1u);   // keeps this warp in step with the buffer's phases
         }
-        if (tid == 0 && B + 2 < NB) gj::mbar_expect_tx(&full[b], block_bytes(B + 2));   // this buffer's next use
-        // ---- this warp is done with the buffer (the forwarder turns the CTA's arrivals into one credit)
+        // ---- this warp is done with the slot (the forwarder turns the CTA's arrivals into one credit)
         __syncwarp();
-        if (lane == 0 && B + 2 < NB) gj::mbar_arrive(&done[b]);
+        if (lane == 0) gj::mbar_arrive(&sm.done[q]);
       }
     }
 #pragma unroll
@@ -334,7 +366,8 @@ int lu_inverse(isr_ctx* c, int n, const double* A, double* lu, double* prod, dou
   int h_info[2] = {0, 0};
   if (n <= kGjMaxRows) {
     const int warps = (n + 4 * kGjCtas - 1) / (4 * kGjCtas);   // four rows per warp, whole warps per CTA
-    gj_inverse_kernel<<<kGjCtas, 32 * warps + 32, 0, c->stream>>>(n, A, Ainv, resid_dev); ISR_COUNT_LAUNCH();
+    ISR_CUDA(cudaFuncSetAttribute(gj_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GjSmem)));   // per device
+    gj_inverse_kernel<<<kGjCtas, 32 * warps + 32, sizeof(GjSmem), c->stream>>>(n, A, Ainv, resid_dev); ISR_COUNT_LAUNCH();
   } else {
     ISR_CUDA(cudaMemsetAsync(resid_dev, 0, 3 * sizeof(double), c->stream));
     ISR_CUDA(cudaMemcpyAsync(lu, A, bytes, cudaMemcpyDeviceToDevice, c->stream));
