@@ -350,8 +350,8 @@ def run_b200(args, rank, world, local_rank):
         "roofline": {"bound": "tensor", "kernel": "toy_fused_kernel<4,5,2,5,2,40> (one launch: TMA box loads -> DMMA m8n8k4 f64, pass 1 b = S v and pass 2 chi2 = |R(b-b0)|^2)",
                      "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
                      # dram__bytes_read + dram__bytes_write of the fused launch from the ncu --set full capture
-                     # in profiles/ncu_r01_toy_k40.txt (420.45 + 81.20 MB for 262144 toys at N=200), scaled to this T
-                     "traffic": (501.66e6 / 262144) * T if n == 200 else None,
+                     # in profiles/ncu_r01_toy_dense_final.txt (840.00 + 176.71 MB for 524288 toys at N=200), scaled to this T
+                     "traffic": (1016.71e6 / 524288) * T if n == 200 else None,
                      "algorithmic_bytes": (8 * n + 8) * T, "flops_per_toy": 4 * n * n,
                      "peak_source": "FP64 DMMA probe tools/fp64_peaks.cu -> profiles/fp64_peaks_r01.json "
                                     "(MEASURED_PEAKS.json carries no FP64 figure; bf16 peak does not apply to an FP64 kernel)"},
