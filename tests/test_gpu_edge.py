@@ -129,7 +129,8 @@ def test_tikhonov_and_tsvd_minimal_and_odd(oracle):
 
 
 def test_factor_falls_back_to_pivoting_and_rejects_singular(oracle):
-    """isr_factor tries cuSOLVER's LU without pivoting first and accepts it only if max |G X - I| is tiny; matrices
+    """isr_factor tries an inverse without pivoting first (the cluster Gauss-Jordan kernel for N <= 240, cuSOLVER's
+    LU above) and accepts it only if max |G X - I| is tiny; matrices
     that need row exchanges (zero or tiny leading pivots), or are badly conditioned, must come out right through
     the pivoted path, and a singular matrix must be reported."""
     import isrsolver_b200 as isr
@@ -159,3 +160,35 @@ def test_factor_falls_back_to_pivoting_and_rejects_singular(oracle):
     s.set_matrix(G)
     with pytest.raises(IsrGpuError):
         s.solve()
+
+
+@pytest.mark.parametrize("n", [2, 4, 15, 16, 17, 63, 64, 65, 128, 129, 236, 239, 240, 241, 256])
+def test_inverse_sizes_around_the_cluster_kernel_limits(n):
+    """The register-resident Gauss-Jordan inverse (4 CTAs x warps of 4 rows, pivot blocks of 4, 64-column pair groups,
+    N <= 240) against NumPy on dense and on lower-triangular matrices, at sizes around every one of those boundaries
+    and across the hand-over to cuSOLVER; a lower-triangular matrix must come back exactly lower triangular
+    (the toy kernel's triangular schedule relies on it)."""
+    import isrsolver_b200 as isr
+    rng = np.random.default_rng(3100 + n)
+    ecm = np.linspace(1.0, 2.0, n) if n > 1 else np.array([1.5])
+    for shape in ("dense", "lower"):
+        G = np.eye(n) * 2.0 + np.tril(rng.random((n, n))) * 0.3
+        if shape == "dense":
+            G += 0.05 * rng.random((n, n))
+        b0 = 1.0 + rng.random(n); vcs = G @ b0; err = 0.05 + 0.1 * rng.random(n)
+        s = isr.ISRSolverSLE(n, ecm, vcs, None, err, THR)
+        s.set_matrix(G)
+        s.solve()
+        np.testing.assert_allclose(s.bcs(), b0, rtol=1e-12)
+        Ginv = np.linalg.inv(G)
+        cov = (Ginv * err[None, :]) @ (Ginv * err[None, :]).T
+        np.testing.assert_allclose(s.bcs_cov_matrix(), cov, rtol=1e-10, atol=1e-13 * np.abs(cov).max())
+        V = vcs[None, :] + err[None, :] * rng.standard_normal((37, n))
+        r = s.toy_batch(V, b0, want_bcs=True)
+        np.testing.assert_allclose(r["bcs"], V @ Ginv.T, rtol=1e-11, atol=1e-12)
+        if shape == "lower":
+            # v = e_0 scaled: b must vanish exactly nowhere above ... equivalently a toy with only the LAST point excited
+            # leaves every earlier b exactly untouched iff G^-1 is exactly lower triangular
+            e = np.zeros((1, n)); e[0, -1] = 1.0
+            be = s.toy_batch(e, np.zeros(n), want_bcs=True)["bcs"][0]
+            assert np.all(be[:-1] == 0.0)
