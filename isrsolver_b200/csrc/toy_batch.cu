@@ -5,6 +5,7 @@
 // factored once (isr_factor) and a toy costs 4 N^2 flop in ONE fused launch (toy_gemm.cuh):
 //   pass 1  b_k = Sop v_k ; d_k = b_k - b0 ; column statistics
 //   pass 2  chi2_k = | Rop d_k |^2
+// (about 2 N^2 when both operators are exactly lower triangular: the triangular schedule skips the structural zeros).
 #include "problem.hpp"
 #include "tikhonov.hpp"
 #include "toy_batch.hpp"

@@ -25,7 +25,13 @@
 // (192 / 320 / 448 B) have stride 8 (mod 16) doubles, which makes the 16-byte fragment loads conflict free without padding
 // or swizzle; each 16-byte load feeds two DMMAs (the k-permutation {2c, 2c+1} is applied to A and B
 // alike, so the contraction is unchanged).  Operators wider than one CTA tile (N > NP) are processed as
-// column blocks by the same CTA.
+// column blocks by the same CTA.  The BT column tiles of a warp are dealt cyclically (tile j of warp wn = j WN + wn).
+//
+// Two instantiations per tile shape: TRI = false, the dense kernel; TRI = true for operator pairs of which at least
+// one is EXACTLY lower triangular (linear interpolation without energy spread: G^-1 and W^(1/2) G; or a chi2 factor
+// replaced by its QL factor) -- column blocks then load only the K chunks below their last row and a warp skips the
+// column tiles entirely above the diagonal, through branches into chunk bodies specialised for the number of skipped
+// tiles.  The skipped products are exact zeros, so both instantiations return the same bits.
 // History (profiles/ncu_r01_toy_v*.txt): v1 two launches per chunk, per-tile drain: DMMA pipe 71 % busy
 // inside the kernels, 18.7 TFLOP/s overall; v2 fused cp.async version with a block barrier per chunk: 58 %
 // (every warp issued its share of the loads at the same moment, leaving the pipe idle).
