@@ -115,28 +115,31 @@ __global__ void __launch_bounds__(256) inverse_residual_kernel(int n, const doub
 
 // --------------------------------------------------------------------------------------------------
 // X = A^-1 by in-place Gauss-Jordan elimination without pivoting, the matrix resident in the REGISTER FILES of a
-// 4-CTA thread-block cluster (N <= 256).  cuSOLVER's getrf + getrs need 0.3 ms at N = 200 -- almost all of it the
+// 4-CTA thread-block cluster (N <= 240).  cuSOLVER's getrf + getrs need 0.3 ms at N = 200 -- almost all of it the
 // latency of two dozen dependent panel / trsm launches -- which is a third of a 131k-toy chi2 test; here one launch
-// does the N dependent rank-1 steps.
+// does the N dependent rank-1 steps in 0.1 ms.
 //
-// CTA c owns rows [c R, (c+1) R), R = ceil(N / 4); thread (i, s) holds the 32-column strip s of row i in registers,
-// the 8 strips of a row in 8 consecutive lanes (4 rows per warp); the row buffers interleave the strips ([column pair]
-// [strip][2]) so that those 8 lanes read and write 128 contiguous bytes (strip-major they collide 8-way: 3.5 us per
-// step at N = 200).  Step k:
-//   * the multiplier a_ik comes from lane s = k / 32 of the row by a warp shuffle;
-//   * the 8 lanes that own row k store its raw strips to a staging buffer and ONE lane sends them to the row buffer of
-//     every CTA with a bulk shared->distributed-shared copy (cp.async.bulk.shared::cluster.shared::cta) that completes
-//     tx-bytes on the destination's `full` mbarrier: no cluster barrier and no cluster-scope fence on the critical path.
-//     Measured per step at N = 200: cluster.sync() per step 1.85 us (it carries a MEMBAR.ALL.GPU, and so does every
-//     .release.cluster / .acquire.cluster mbarrier operation); st.async 16-byte stores from registers 1.25 us; this
-//     version 1.07 us, of which about 0.8 us is the latency of the copy + remote completion itself (N = 50: 0.84 us);
-//   * every thread waits on its CTA's `full` barrier and updates its strip from registers:
-//       pivot row:  a_kj <- a_kj / p,  a_kk <- 1 / p        other rows:  a_ij <- a_ij - (a_ik / p) a_kj,  a_ik <- -a_ik / p
-//   * the two row buffers alternate with the parity of k; a warp that has consumed step k arrives on its CTA's `done`
-//     barrier, and one extra warp per CTA forwards each completed `done` phase as ONE credit (remote mbarrier arrive) to
-//     the `empty` barrier of the CTA that owns row k + 2, whose owner warp waits for the four credits before it
-//     overwrites the buffer.  (Remote arrives serialise at about 60 ns each at the target: one per warp instead of one
-//     per CTA made a step 3.5 us at N = 200.)
+// CTA c owns rows [c R, (c+1) R), R = 4 ceil(N / 16); a warp owns four consecutive rows and lane l holds the column
+// pairs {l + 32 i, i = 0..3} of those four rows (32 doubles), so that one conflict-free 512-byte LDS.128 sweep of a
+// pivot row serves four matrix rows.  Pivots are processed in blocks of four = the four rows of one warp, the owner:
+//   * the owner eliminates its four rows against each other out of its own registers (multipliers a_ik and the pivot
+//     by warp shuffle; pivot row: a_kj <- a_kj / p, a_kk <- 1 / p; other rows: a_ij <- a_ij - a_ik a'_kj, a_ik <- -a_ik a'_kk)
+//     and stores the four scaled pivot rows, each as it was at its own step, to a slot of `stage`;
+//   * it flips the slot's local `lfull` mbarrier -- the other warps of its CTA, among them (almost always) the next
+//     owner, read `stage` directly, so the critical chain never waits for a copy -- and ONE lane sends the block to the
+//     `rowbuf` slot of the three other CTAs with cp.async.bulk.shared::cluster.shared::cta, which completes tx-bytes on
+//     their `rfull` mbarriers: no cluster barrier and no cluster-scope fence anywhere in the loop;
+//   * every other warp applies the four rank-1 updates from registers;
+//   * a ring of four slots lets the owner chain run ahead of the remote consumers.  A warp that is done with a slot
+//     arrives on its CTA's `done` barrier; one extra warp per CTA forwards each completed `done` phase as ONE credit
+//     (remote mbarrier arrive) to the `empty` barrier of the CTA that owns the block four ahead, whose owner waits for
+//     the four credits before it overwrites the slot.
+// What the measurements said on the way (per pivot, N = 200): cluster.sync() per pivot 1.85 us -- it carries a
+// MEMBAR.ALL.GPU, and so does every .release.cluster / .acquire.cluster mbarrier operation; one remote credit per warp
+// instead of per CTA: no better (remote arrives serialise at the target); one row per 8-lane group with strip-major
+// buffers 3.5 us (8-way bank conflicts), conflict-free 1.07 us; st.async stores from registers instead of the bulk
+// copy 1.25 us; four pivots per exchange, one row per lane group 1.15 us (each LDS sweep served one row); four rows
+// per lane 0.6 us; local fast path + four slots 0.5 us.
 // A lower-triangular A yields an exactly lower-triangular inverse (the updates above the diagonal subtract exact
 // zeros).  No pivoting: the caller certifies the result (lu_inverse) and falls back to the pivoted LU otherwise.
 // --------------------------------------------------------------------------------------------------
