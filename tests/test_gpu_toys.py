@@ -136,6 +136,29 @@ def test_triangular_schedule_equals_dense_schedule_and_oracle(oracle, n, shape):
         np.testing.assert_allclose(res[2]["chi2"], res[1]["chi2"], rtol=1e-12)
 
 
+@pytest.mark.parametrize("n,T", [(40, 3), (200, 70), (333, 1000)])
+def test_triangular_schedule_without_chi2_pass(oracle, n, T):
+    """Pass 1 alone (no chi2 requested: the mean-solution loop of chi2TestData, src/Chi2Test.cpp:177-183) on
+    lower-triangular operators, including a single tile per CTA and two column blocks."""
+    import isrsolver_b200 as isr
+    rng = np.random.default_rng(4400 + n)
+    ecm = np.linspace(1.0, 2.0, n)
+    G = np.tril(rng.random((n, n)) * 0.1) + np.eye(n)
+    vcs_err = 0.05 + 0.1 * rng.random(n)
+    b0 = 1.0 + rng.random(n)
+    V = (G @ b0)[None, :] + vcs_err[None, :] * rng.standard_normal((T, n))
+    _, B = oracle.chi2_test_fair(G, V, b0, vcs_err)
+    out = {}
+    for variant in (0, 1):
+        s = isr.ISRSolverSLE(n, ecm, G @ b0, None, vcs_err, 0.9)
+        s.set_matrix(G); s.set_toy_schedule(variant)
+        out[variant] = s.toy_batch(V, b0, want_chi2=False, want_sum=True, want_ratio=True, want_bcs=True)
+        np.testing.assert_allclose(out[variant]["bcs"], B, rtol=RTOL, atol=1e-12)
+        np.testing.assert_allclose(out[variant]["sum_bcs"], B.sum(0), rtol=RTOL)
+    for key in ("bcs", "sum_bcs", "ratio_stats"):
+        np.testing.assert_array_equal(out[0][key], out[1][key])
+
+
 def test_qr_chi2_factor_of_rank_deficient_and_ill_conditioned_operators(oracle):
     """TSVD with k < N selects a rank-deficient chi2 factor, a tiny lambda a badly conditioned one: the Householder
     QL replacement must reproduce the dense schedule there too."""
