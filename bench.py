@@ -202,7 +202,8 @@ def run_b200(args, rank, world, local_rank):
     cnt_dev = torch.empty(130, dtype=torch.int64, device=dev)
     cnt32_dev = torch.empty(130, dtype=torch.int32, device=dev)
     range_dev = torch.empty(2, dtype=torch.float64, device=dev)
-    chi2_host = np.empty(T)
+    chi2_pin = torch.empty(T, dtype=torch.float64, pin_memory=True)     # the caller's chi2 buffer of the e2e step, pinned like V
+    chi2_host = chi2_pin.numpy()
     sumb_host = np.zeros(n)
     counts = np.zeros(130, dtype=np.uint32)
     torch.cuda.synchronize()
@@ -266,14 +267,15 @@ def run_b200(args, rank, world, local_rank):
         L.check(lib.isr_factor(prob, L.dptr(err)))
         L.check(lib.isr_toy_batch(prob, T, C.cast(Vh.data_ptr(), C.POINTER(C.c_double)), L.dptr(bcs0), L.dptr(chi2_host),
                                   L.dptr(sumb_host), None, None, None))
+        # the chi2 values are in the caller's buffer now AND still on the device: range and TH1F from there
         lo, hi = C.c_double(), C.c_double()
-        L.check(lib.isr_chi2_histogram(ctx, T, L.dptr(chi2_host), 128, C.byref(lo), C.byref(hi), L.uptr(counts)))
+        L.check(lib.isr_last_chi2_minmax(prob, C.byref(lo), C.byref(hi)))
 
         def rehist(glo, ghi):
             L.check(lib.isr_last_chi2_histogram(prob, 128, glo, ghi, L.uptr(counts)))
             return counts
         with torch.cuda.stream(stream):
-            return combine(lo.value, hi.value, counts, rehist)
+            return combine(lo.value, hi.value, None, rehist)
 
     lohi = np.zeros(2)
 

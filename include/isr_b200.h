@@ -182,6 +182,8 @@ int isr_histogram_dev(isr_ctx* ctx, int64_t n, const double* v_dev, int nbins, d
 /* TH1F(nbins, lo, hi) of the chi2 values the last isr_toy_batch / isr_toy_campaign of this problem left on the
  * device (multi-GPU: re-bin against the GLOBAL range without moving chi2). */
 int isr_last_chi2_histogram(isr_problem* p, int nbins, double lo, double hi, uint32_t* counts_out);
+/* min / max of the same device-resident values (the range src/Chi2Test.cpp:64-71 takes from the toy loop). */
+int isr_last_chi2_minmax(isr_problem* p, double* min_out, double* max_out);
 /* TH1F(nbins, lo, hi) of a host array with a caller-supplied range (multi-GPU: the GLOBAL min / max). */
 int isr_histogram(isr_ctx* ctx, int64_t n, const double* v, int nbins, double lo, double hi, uint32_t* counts_out);
 int isr_chi2_histogram(isr_ctx* ctx, int64_t n, const double* chi2, int nbins, double* lo_out,

@@ -81,6 +81,7 @@ SIGNATURES = {
     "isr_histogram_range_dev": (C.c_int, [_vp, _i64, _vp, C.c_int, _vp, _vp]),
     "isr_histogram_dev": (C.c_int, [_vp, _i64, _vp, C.c_int, C.c_double, C.c_double, _up]),
     "isr_last_chi2_histogram": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, _up]),
+    "isr_last_chi2_minmax": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "isr_histogram": (C.c_int, [_vp, _i64, _dp, C.c_int, C.c_double, C.c_double, _up]),
     "isr_chi2_histogram": (C.c_int, [_vp, _i64, _dp, C.c_int, _dp, _dp, _up]),
     "isr_tikhonov_prepare": (C.c_int, [_vp, _dp, C.c_int]),

@@ -517,6 +517,15 @@ int isr_last_chi2_histogram(isr_problem* p, int nbins, double lo, double hi, uin
   return histogram_device(p->ctx, p->last_chi2_count, p->d_chi2h.p, nbins, lo, hi, counts_out);
 }
 
+// min / max of the same device-resident chi2 values: with isr_last_chi2_histogram the whole chi2 test of a host-fed
+// batch is summarised without uploading the chi2 array again.
+int isr_last_chi2_minmax(isr_problem* p, double* min_out, double* max_out) {
+  if (!p || !min_out || !max_out) { set_error("NULL argument"); return ISR_EINVAL; }
+  if (p->last_chi2_count <= 0 || !p->d_chi2h.p) { set_error("isr_last_chi2_minmax: no chi2 values on the device"); return ISR_ESTATE; }
+  ISR_CUDA(cudaSetDevice(p->ctx->device));
+  return minmax_device(p->ctx, p->last_chi2_count, p->d_chi2h.p, min_out, max_out);
+}
+
 int isr_minmax_dev(isr_ctx* ctx, int64_t n, const double* v_dev, double* min_out, double* max_out) {
   if (!ctx || !v_dev || !min_out || !max_out) { set_error("NULL argument"); return ISR_EINVAL; }
   ISR_CUDA(cudaSetDevice(ctx->device));

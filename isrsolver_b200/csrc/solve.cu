@@ -262,9 +262,11 @@ int toy_batch_host(isr_problem* p, int64_t T, const double* V, const double* bcs
     if (bcs_out)
       ISR_CUDA(cudaMemcpyAsync(bcs_out + t0 * n, o.bcs, sizeof(double) * tc * n, cudaMemcpyDeviceToHost, st));
     ISR_CUDA(cudaEventRecord(p->ev_done[q], st));
+    // this chunk's chi2 goes back while the next chunk's toys are still coming in (the two directions have their own
+    // copy engines); the values also stay on the device for isr_last_chi2_minmax / isr_last_chi2_histogram
+    if (chi2_out) ISR_CUDA(cudaMemcpyAsync(chi2_out + t0, o.chi2, sizeof(double) * tc, cudaMemcpyDeviceToHost, st));
   }
   p->last_chi2_count = chi2_out ? T : 0;
-  if (chi2_out) ISR_CUDA(cudaMemcpyAsync(chi2_out, p->d_chi2h.p, sizeof(double) * T, cudaMemcpyDeviceToHost, st));
   if (sum_bcs_out) ISR_CUDA(cudaMemcpyAsync(sum_bcs_out, p->d_stat.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
   if (ratio_stats_out)
     ISR_CUDA(cudaMemcpyAsync(ratio_stats_out, p->d_stat.p + n, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, st));

@@ -181,6 +181,23 @@ def test_qr_chi2_factor_of_rank_deficient_and_ill_conditioned_operators(oracle):
     np.testing.assert_allclose(out[2][1], out[1][1], rtol=1e-10)
 
 
+def test_last_chi2_range_and_histogram_from_the_device(oracle):
+    """After a host-fed batch the chi2 values are also still on the device: their range and TH1F must equal what the
+    reference's loop derives from the returned array (src/Chi2Test.cpp:64-78), bit for bit, without re-uploading it."""
+    from isrsolver_b200 import _lib as L
+    g = load_golden("c2_sle_n40_cspline")
+    s = make_solver(g)
+    r = s.toy_batch(g["toys"], g["bcs0"])
+    lo, hi = C.c_double(), C.c_double()
+    L.check(L.load().isr_last_chi2_minmax(s._p, C.byref(lo), C.byref(hi)))
+    assert (lo.value, hi.value) == (r["chi2"].min(), r["chi2"].max())
+    cnt = np.zeros(130, dtype=np.uint32)
+    L.check(L.load().isr_last_chi2_histogram(s._p, 128, lo.value, hi.value, L.uptr(cnt)))
+    ref, _, rlo, rhi = oracle.chi2_histogram(r["chi2"])
+    assert (rlo, rhi) == (lo.value, hi.value)
+    np.testing.assert_array_equal(cnt, ref.astype(np.uint32))
+
+
 def test_empty_batch():
     import isrsolver_b200 as isr
     g = load_golden("c1_sle_n50_linear")
