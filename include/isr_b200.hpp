@@ -439,7 +439,9 @@ inline Chi2TestResult chi2Test(ISRSolverSLE* solver, const Chi2TestArgs& args, c
   r.chi2.resize(args.n);
   solver->toyBatch(args.n, toys.data(), bcs0.data(), r.chi2.data(), nullptr, nullptr, nullptr, nullptr);
   std::vector<uint32_t> counts(130);
-  check(isr_chi2_histogram(Context::get(), args.n, r.chi2.data(), 128, &r.chi2Min, &r.chi2Max, counts.data()));
+  // range and TH1F from the chi2 values the batch left on the device (no second upload)
+  check(isr_last_chi2_minmax(solver->gpuProblem(), &r.chi2Min, &r.chi2Max));
+  check(isr_last_chi2_histogram(solver->gpuProblem(), 128, r.chi2Min, r.chi2Max, counts.data()));
   r.hist.assign(counts.begin(), counts.end());
   return r;
 }

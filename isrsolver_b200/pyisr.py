@@ -597,7 +597,9 @@ class ISRSolverSLE(BaseISRSolver):
         chi2 = self.toy_batch(V, bcs0)["chi2"]
         lo, hi = C.c_double(), C.c_double()
         counts = np.zeros(130, dtype=np.uint32)
-        L.check(self._lib.isr_chi2_histogram(self._ctxh, len(chi2), L.dptr(chi2), 128, C.byref(lo), C.byref(hi), L.uptr(counts)))
+        # range and TH1F from the chi2 values the batch left on the device (no second upload)
+        L.check(self._lib.isr_last_chi2_minmax(self._p, C.byref(lo), C.byref(hi)))
+        L.check(self._lib.isr_last_chi2_histogram(self._p, 128, lo.value, hi.value, L.uptr(counts)))
         return {"chi2": chi2, "hist": counts.astype(np.float32), "lo": lo.value, "hi": hi.value}
 
     @staticmethod
