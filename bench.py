@@ -368,6 +368,7 @@ def run_b200(args, rank, world, local_rank):
     }
     line["assembly_other_configs"] = other_assemblies(lib, ctx, stream, torch)
     line["chi2_test_other_configs"] = other_chi2_tests(lib, ctx, stream, torch, dev)
+    line["tikhonov_c4"] = tikhonov_c4(lib, ctx, torch)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(n, G, bcs0, vcs, err)
     emit(line)
@@ -460,6 +461,50 @@ def other_chi2_tests(lib, ctx, stream, torch, dev):
             out[name]["whole_test_frac_of_fp64_peak"] = 4.0 * n * n * T / (ms * 1e-3) * 1e-12 / FP64_PEAK_TFLOPS
         lib.isr_problem_destroy(p)
     return out
+
+
+def tikhonov_c4(lib, ctx, torch):
+    """BASELINE config C4 on this rank: ISRSolverTikhonov, N = 200, cubic, 2 MeV energy spread, derivative regulariser;
+    the generalised eigen-system once (isr_tikhonov_prepare), then the chi2 test of 10k toys for 1024 lambdas -- the
+    whole grid, and the 128-lambda slice one of 8 GPUs gets -- through the host-buffer ABI with the toys in pinned
+    memory (H2D of V and D2H of the per-lambda summaries inside the timed call; wall clock around synchronous calls,
+    mean of 5 after 2 warm-ups)."""
+    from isrsolver_b200 import _lib as L
+    n, T, Lm = 200, 10000, 1024
+    ecm = np.linspace(E_MIN, E_MAX, n)
+    st = np.ascontiguousarray([[0, 0, 0], [1, 1, n - 1]], dtype=np.int32)
+    p = C.c_void_p()
+    L.check(lib.isr_problem_create(ctx, n, L.dptr(ecm), E_THR, len(st), L.iptr(st), None, C.byref(p)))
+    sig = np.full(n, 0.002)
+    G = np.empty((n, n))
+    L.check(lib.isr_assemble(p, L.dptr(sig), L.dptr(G)))
+    bcs0 = bw_born(ecm); vcs = G.T @ bcs0; err = 0.05 * vcs
+    lam = 1e-9 * (1e9) ** (np.arange(Lm) / (Lm - 1))          # src/isrsolver-LCurve-plot.cpp:127-132
+    rng = np.random.default_rng(20211103)
+    Vp = torch.empty((T, n), dtype=torch.float64, pin_memory=True)
+    Vp.copy_(torch.from_numpy(vcs[None, :] + err[None, :] * rng.standard_normal((T, n))))
+    Vptr = C.cast(Vp.data_ptr(), C.POINTER(C.c_double))
+    stats = np.empty((Lm, 3)); counts = np.zeros((Lm, 130), dtype=np.uint32)
+
+    def wall(fn, reps=5):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps * 1e3
+    prep = wall(lambda: L.check(lib.isr_tikhonov_prepare(p, L.dptr(err), 1)))
+    full = wall(lambda: L.check(lib.isr_tikhonov_toy_scan_hist(p, Lm, L.dptr(lam), T, Vptr, L.dptr(bcs0), 128, L.dptr(stats), L.uptr(counts))))
+    assert int(counts.sum()) == Lm * T
+    part = wall(lambda: L.check(lib.isr_tikhonov_toy_scan_hist(p, Lm // 8, L.dptr(lam), T, Vptr, L.dptr(bcs0), 128, L.dptr(stats), L.uptr(counts))))
+    lc = [np.empty(Lm) for _ in range(4)]
+    lcurve = wall(lambda: L.check(lib.isr_tikhonov_scan(p, Lm, L.dptr(lam), L.dptr(vcs), L.dptr(lc[0]), L.dptr(lc[1]), L.dptr(lc[2]), L.dptr(lc[3]), None)))
+    lib.isr_problem_destroy(p)
+    return {"n_points": n, "lambdas": Lm, "toys_per_lambda": T, "prepare_ms": prep, "lcurve_1024_lambdas_ms": lcurve,
+            "chi2_test_1024_lambdas_ms": full, "pairs_per_s": Lm * T / (full * 1e-3),
+            "chi2_test_128_lambdas_ms": part, "note": "128 lambdas = the slice of one of 8 GPUs (toy_scan_hist_sharded)"}
 
 
 def cpu_baseline(n, G, bcs0, vcs, err):
