@@ -931,6 +931,8 @@ static int finish_assembly(isr_problem* p, const double* ecm_err, const double* 
   ISR_CUDA(cudaGetLastError());
   p->has_G = true;
   p->G_injected = false;
+  p->G_lower = !ecm_err;   // linear ranges only (LinearRangeInterpolator returns 0 for j > i, src/LinearRangeInterpolator.cpp:60-62), no spread product
+  for (size_t r = 0; r + 2 < p->ranges.size() && p->G_lower; r += 3) p->G_lower = p->ranges[r] == 0;
   p->factored = false;
   p->solver_selected = false;
   p->tik_ready = false;

@@ -147,6 +147,10 @@ int isr_set_matrix(isr_problem* p, const double* G) {
   ISR_CUDA(cudaStreamSynchronize(p->ctx->stream));
   p->has_G = true;
   p->G_injected = true;
+  p->G_lower = true;
+  for (int j = 1; j < p->n && p->G_lower; ++j)
+    for (int i = 0; i < j; ++i)
+      if (G[(size_t)i + (size_t)p->n * j] != 0.0) { p->G_lower = false; break; }
   p->factored = p->solver_selected = p->tik_ready = p->svd_ready = false;
   return ISR_OK;
 }
@@ -352,6 +356,7 @@ int isr_cond_spread_scan(isr_problem* p, int K, const double* sigma, int per_poi
   else if (!p->has_G) { set_error("isr_cond_spread_scan: no matrix"); return ISR_ESTATE; }
   ISR_TRY(p->d_G0.reserve(nn));
   ISR_CUDA(cudaMemcpyAsync(p->d_G0.p, p->d_G.p, sizeof(double) * nn, cudaMemcpyDeviceToDevice, st));
+  p->G_lower = false;
   ISR_CUDA(cudaStreamSynchronize(st));
   // The K decompositions are independent and each one is a chain of small latency-bound kernels, so they
   // run on several lanes (stream + cuSOLVER handle + workspace each) at once.

@@ -354,10 +354,11 @@ gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, d
 // an injected or ill-conditioned matrix, so the fast path is CERTIFIED a posteriori: X is accepted only if
 // max |A X - I| <= 1e-12 n (then |X - A^-1| <= |A^-1| |A X - I|, i.e. 2e-10 relative at N = 200, typically 1e-13);
 // otherwise -- zero pivot, growth, NaN -- the partially pivoted factorisation is used, exactly as before.
+// lower_hint: the caller knows A to be lower triangular (used for N > 240 only).
 // tri[0] / tri[1] = 1 iff Ainv / A came out exactly lower triangular (linear interpolation without energy spread: the
 // toy kernel then skips the structural zeros); read back with the certificate, no extra synchronisation.
 int lu_inverse(isr_ctx* c, int n, const double* A, double* lu, double* prod, double* Ainv, DevBuf<double>& work,
-               DevBuf<int>& ipiv, DevBuf<int>& info, int* tri) {
+               DevBuf<int>& ipiv, DevBuf<int>& info, bool lower_hint, int* tri) {
   int lwork = 0;
   const size_t bytes = sizeof(double) * (size_t)n * n;
   ISR_CUSOLVER(cusolverDnDgetrf_bufferSize(c->solver, n, n, lu, n, &lwork));
@@ -371,6 +372,13 @@ int lu_inverse(isr_ctx* c, int n, const double* A, double* lu, double* prod, dou
     const int warps = (n + 4 * kGjCtas - 1) / (4 * kGjCtas);   // four rows per warp, whole warps per CTA
     ISR_CUDA(cudaFuncSetAttribute(gj_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GjSmem)));   // per device
     gj_inverse_kernel<<<kGjCtas, 32 * warps + 32, sizeof(GjSmem), c->stream>>>(n, A, Ainv, resid_dev); ISR_COUNT_LAUNCH();
+  } else if (lower_hint) {
+    // the caller knows A to be lower triangular (linear interpolation without spread): one triangular solve L X = I
+    // instead of getrf + two of them; a wrong hint fails the certificate below like any other bad inverse
+    ISR_CUDA(cudaMemsetAsync(resid_dev, 0, 3 * sizeof(double), c->stream));
+    set_identity_kernel<<<(n * n + 255) / 256, 256, 0, c->stream>>>(n, Ainv); ISR_COUNT_LAUNCH();
+    const double one = 1.0;
+    ISR_CUBLAS(cublasDtrsm(c->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, n, n, &one, A, n, Ainv, n));
   } else {
     ISR_CUDA(cudaMemsetAsync(resid_dev, 0, 3 * sizeof(double), c->stream));
     ISR_CUDA(cudaMemcpyAsync(lu, A, bytes, cudaMemcpyDeviceToDevice, c->stream));

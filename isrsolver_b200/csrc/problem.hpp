@@ -40,6 +40,8 @@ struct isr_problem {
   int64_t last_panels = 0;
   bool has_G = false;
   bool G_injected = false;   // matrix came from isr_set_matrix (cannot be re-assembled)
+  bool G_lower = false;      // known on the host to be lower triangular (all ranges linear and no spread, or an injected
+                             // matrix that was checked): lets isr_factor pick the triangular solve for N > 240
   isr::DevBuf<double> d_G0;   // condition-number scan: the unspread matrix
 
   // ---- factorisation / selected solver -------------------------------------------------------

@@ -36,7 +36,7 @@ int factor(isr_problem* p, const double* vcs_err) {
   p->vcs_err.assign(vcs_err, vcs_err + n);
   ISR_CUDA(cudaMemcpyAsync(p->d_werr.p, vcs_err, sizeof(double) * n, cudaMemcpyHostToDevice, st));
   ISR_TRY(p->d_tmp2.reserve(nn));
-  ISR_TRY(lu_inverse(c, n, p->d_G.p, p->d_tmp.p, p->d_tmp2.p, p->d_Ginv.p, p->d_work, p->d_ipiv, p->d_info, p->tri_sle));
+  ISR_TRY(lu_inverse(c, n, p->d_G.p, p->d_tmp.p, p->d_tmp2.p, p->d_Ginv.p, p->d_work, p->d_ipiv, p->d_info, p->G_lower, p->tri_sle));
   p->factored = true;
   p->cov_ready = false;      // Cov / G^T W G are formed on first use (ensure_cov): the toy path never reads them
   return select_sle(p);
