@@ -672,9 +672,18 @@ __global__ void __launch_bounds__(256) reduce_kernel(int n, const int* __restric
 // shared memory with independent coalesced loads, then a fully unrolled 64-deep FMA loop runs out of shared memory
 // (Ct is zero outside a column's band, so no per-column bounds are needed inside the chunk).  Only the segment range
 // the block's columns actually touch ([min klo, min(max khi, last row)]) is visited: a purely linear matrix costs two
-// chunks per block, a cubic one N/16 -- split over blockIdx.z (kCtSplit slices of the segment range, partial sums
+// chunks per block, a cubic one N/16 -- split over blockIdx.z (contract_slices() slices of the segment range, partial sums
 // combined in fixed order by contract_sum_kernel) so that N = 200 still fills the machine.
-constexpr int kCtRows = 16, kCtCols = 64, kCtK = 16, kCtSplit = 4;
+constexpr int kCtRows = 16, kCtCols = 64, kCtK = 16, kCtMaxSplit = 16;
+// Slices of the segment range (gridDim.z): about four blocks per SM in all, at most one slice per 16-segment chunk --
+// a block that handles a single chunk pays the latency of its dependent loads (panel offsets -> moments, coefficients)
+// once, and the slices run side by side (N = 200 cubic: 12 slices, 624 blocks; 4 slices took 20 us).
+static int contract_slices(int n, int sm_count, bool all_linear) {
+  // a block of 64 hat-function columns touches 65 segments (5 chunks), one with a spline column all of them
+  const int tiles = ((n + kCtCols - 1) / kCtCols) * ((n + kCtRows - 1) / kCtRows);
+  const int nchunks = all_linear ? std::min(5, (n + kCtK - 1) / kCtK) : (n + kCtK - 1) / kCtK;
+  return std::max(1, std::min({kCtMaxSplit, nchunks, (4 * sm_count + tiles - 1) / tiles}));
+}
 // FUSED = false: the moments were reduced beforehand by reduce_kernel into pm = M[i][k][4] (tabulated efficiencies:
 // dozens of panels per item, which every column tile would otherwise re-reduce).
 template <bool FUSED>
@@ -696,7 +705,7 @@ contract_kernel(int n, const int* __restrict__ off, const double* __restrict__ p
   // this block's slice of the block-wide segment range, in whole chunks
   int blo = s_lo, bhi = min(s_hi, imax);
   {
-    const int nchunks = bhi >= blo ? (bhi - blo) / kCtK + 1 : 0, per = (nchunks + kCtSplit - 1) / kCtSplit;
+    const int nchunks = bhi >= blo ? (bhi - blo) / kCtK + 1 : 0, per = (nchunks + (int)gridDim.z - 1) / (int)gridDim.z;
     const int a = blo + (int)blockIdx.z * per * kCtK;
     bhi = min(bhi, a + per * kCtK - 1);
     blo = a;
@@ -746,12 +755,11 @@ contract_kernel(int n, const int* __restrict__ off, const double* __restrict__ p
     }
   }
 }
-__global__ void contract_sum_kernel(int nn, const double* __restrict__ Gpart, double* __restrict__ G) {
+__global__ void contract_sum_kernel(int nn, int nslices, const double* __restrict__ Gpart, double* __restrict__ G) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nn) return;
   double s = 0.0;
-#pragma unroll
-  for (int z = 0; z < kCtSplit; ++z) s += Gpart[(size_t)z * nn + idx];
+  for (int z = 0; z < nslices; ++z) s += Gpart[(size_t)z * nn + idx];   // fixed order
   G[idx] = s;
 }
 
@@ -902,19 +910,22 @@ static int finish_assembly(isr_problem* p, const double* ecm_err, const double* 
   cudaStream_t st = p->ctx->stream;
   const int nitems = n * (n + 1) / 2;
   ISR_TRY(p->d_G.reserve((size_t)n * n));
-  ISR_TRY(p->d_Gpart.reserve((size_t)kCtSplit * n * n));
+  bool all_linear = true;
+  for (size_t r = 0; r + 2 < p->ranges.size(); r += 3) all_linear = all_linear && p->ranges[r] == 0;
+  const int nslices = contract_slices(n, p->ctx->sm_count, all_linear);
+  ISR_TRY(p->d_Gpart.reserve((size_t)nslices * n * n));
   const int eval_blocks = p->ctx->sm_count * 8;
   eval_kernel<<<eval_blocks, kEvalThreads, 0, st>>>(p->d_off.p + nitems, p->d_row.p, p->eps, p->d_ext.p, p->d_invh.p,
                                                      p->d_pa.p, p->d_pb.p, p->d_peps.p, p->d_pitem.p,
                                                      p->d_pkind.p, node_eps_dev, p->d_pm.p); ISR_COUNT_LAUNCH();
-  dim3 cgrid((n + kCtCols - 1) / kCtCols, (n + kCtRows - 1) / kCtRows, kCtSplit);
+  dim3 cgrid((n + kCtCols - 1) / kCtCols, (n + kCtRows - 1) / kCtRows, nslices);
   if (p->eps.kind == 2) {   // many panels per item: reduce once, then contract
     ISR_TRY(reduce_moments(p));
     contract_kernel<false><<<cgrid, 256, 0, st>>>(n, p->d_off.p, p->d_M.p, p->d_Ct.p, p->d_klo.p, p->d_khi.p, p->d_Gpart.p); ISR_COUNT_LAUNCH();
   } else {
     contract_kernel<true><<<cgrid, 256, 0, st>>>(n, p->d_off.p, p->d_pm.p, p->d_Ct.p, p->d_klo.p, p->d_khi.p, p->d_Gpart.p); ISR_COUNT_LAUNCH();
   }
-  contract_sum_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(n * n, p->d_Gpart.p, p->d_G.p); ISR_COUNT_LAUNCH();
+  contract_sum_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(n * n, nslices, p->d_Gpart.p, p->d_G.p); ISR_COUNT_LAUNCH();
   if (ecm_err) {
     for (int i = 0; i < n; ++i)
       if (!(ecm_err[i] > 0.0)) {
