@@ -348,8 +348,8 @@ __device__ __forceinline__ void item_decode(int idx, int& i, int& k) {
 }
 
 // Panel count of every item + exclusive scan WITHIN the block (local[]) + the block's total (blocksum[]): the
-// global offsets follow from a scan over the few hundred block totals (blockscan_kernel), so no kernel ever walks
-// all N(N+1)/2 counts serially.
+// global offsets follow from the few hundred block totals (every fill_kernel block sums the prefix it needs), so no
+// kernel ever walks all N(N+1)/2 counts serially.
 constexpr int kCountThreads = 256;
 __global__ void __launch_bounds__(kCountThreads)
 count_kernel(int nitems, const RowConst* __restrict__ rows, EpsDev eps, const double* __restrict__ ext,
@@ -378,43 +378,6 @@ count_kernel(int nitems, const RowConst* __restrict__ rows, EpsDev eps, const do
   if (idx < nitems) local[idx] = before + incl - c;
   if (threadIdx.x == kCountThreads - 1) blocksum[blockIdx.x] = before + incl;
 }
-// Exclusive scan of the block totals (one block, carry across tiles of 1024) -> blockoff[]; *total = grand total.
-__global__ void __launch_bounds__(1024) blockscan_kernel(int nb, const int* __restrict__ blocksum, int* __restrict__ blockoff,
-                                                          int* __restrict__ total) {
-  __shared__ int wsum[32];
-  __shared__ int carry_s;
-  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  if (t == 0) carry_s = 0;
-  __syncthreads();
-  for (int base = 0; base < nb; base += 1024) {
-    const int v = base + t < nb ? blocksum[base + t] : 0;
-    int incl = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int u = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += u;
-    }
-    if (lane == 31) wsum[w] = incl;
-    __syncthreads();
-    if (w == 0) {
-      int x = wsum[lane];
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int u = __shfl_up_sync(0xffffffffu, x, d);
-        if (lane >= d) x += u;
-      }
-      wsum[lane] = x;
-    }
-    __syncthreads();
-    const int carry = carry_s;
-    if (base + t < nb) blockoff[base + t] = carry + (w ? wsum[w - 1] : 0) + incl - v;
-    __syncthreads();
-    if (t == 1023) carry_s = carry + wsum[31];
-    __syncthreads();
-  }
-  if (t == 0) *total = carry_s;
-}
-
 // Single-block exclusive scan of cnt[0..n) into off[0..n], off[n] = total.  Tiles of 8 x 1024 elements go
 // through shared memory: coalesced loads, an 8-element serial scan per thread out of shared memory, a
 // shuffle-based block scan of the 1024 thread totals, coalesced stores (no dependent global-load chains).
@@ -488,11 +451,31 @@ constexpr int kHeavyItem = 32;   // items with more panels than this are filled 
 // segments of a row under a finely binned efficiency) are left to fill_heavy_kernel.
 __global__ void __launch_bounds__(kCountThreads)
 fill_kernel(int nitems, const RowConst* __restrict__ rows, EpsDev eps, const double* __restrict__ ext,
-            const int* __restrict__ cnt, const int* __restrict__ local, const int* __restrict__ blockoff, int* __restrict__ off,
+            const int* __restrict__ cnt, const int* __restrict__ local, const int* __restrict__ blocksum, int* __restrict__ off,
             double* __restrict__ pa, double* __restrict__ pb, int* __restrict__ pitem, int* __restrict__ pkind, int skip_heavy) {
+  // offset of this block's items = sum of the totals of the blocks before it: every block adds up that prefix of the
+  // few hundred block totals itself (integer sum, any order), which saves the separate scan launch
+  __shared__ int s_part[kCountThreads / 32];
+  __shared__ int s_blockoff;
+  {
+    int acc = 0;
+    for (int b = threadIdx.x; b < (int)blockIdx.x; b += kCountThreads) acc += blocksum[b];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+#pragma unroll
+      for (int q = 0; q < kCountThreads / 32; ++q) t += s_part[q];
+      s_blockoff = t;
+      if (blockIdx.x == gridDim.x - 1) off[nitems] = t + blocksum[blockIdx.x];   // grand total
+    }
+    __syncthreads();
+  }
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nitems) return;
-  const int o = local[idx] + blockoff[blockIdx.x];
+  const int o = local[idx] + s_blockoff;
   off[idx] = o;
   const int count = cnt[idx];
   if (count == 0 || (skip_heavy && count > kHeavyItem)) return;
@@ -689,7 +672,7 @@ static int contract_slices(int n, int sm_count, bool all_linear) {
 template <bool FUSED>
 __global__ void __launch_bounds__(256)
 contract_kernel(int n, const int* __restrict__ off, const double* __restrict__ pm, const double* __restrict__ Ct,
-                const int* __restrict__ klo, const int* __restrict__ khi, double* __restrict__ G) {
+                const int* __restrict__ klo, const int* __restrict__ khi, double* __restrict__ Gpart) {
   __shared__ double sM[kCtRows][kCtK * 4];
   __shared__ double sC[kCtK * 4][kCtCols];
   __shared__ int s_lo, s_hi;
@@ -751,10 +734,13 @@ contract_kernel(int n, const int* __restrict__ off, const double* __restrict__ p
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int i = i0 + rsub * 4 + r;
-      if (i < n) G[(size_t)blockIdx.z * n * n + (size_t)i + (size_t)n * j] = acc[r];
+      if (i < n) Gpart[(size_t)blockIdx.z * n * n + (size_t)i + (size_t)n * j] = acc[r];
     }
   }
 }
+// G = sum of the slices' partial results, in slice order.  (Letting the slice block that arrives last at a tile do
+// this -- __threadfence + arrival counter -- was measured: the fences make the contraction 18 us slower than this
+// 4 us launch.)
 __global__ void contract_sum_kernel(int nn, int nslices, const double* __restrict__ Gpart, double* __restrict__ G) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nn) return;
@@ -889,12 +875,10 @@ static int enumerate_panels(isr_problem* p) {
   ISR_TRY(p->d_off.reserve(nitems + 1));
   ISR_TRY(p->d_local.reserve(nitems));
   ISR_TRY(p->d_blocksum.reserve(nb));
-  ISR_TRY(p->d_blockoff.reserve(nb));
   row_setup_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, p->d_ext.p, p->d_row.p); ISR_COUNT_LAUNCH();
   count_kernel<<<nb, kCountThreads, 0, st>>>(nitems, p->d_row.p, p->eps, p->d_ext.p, p->d_cnt.p, p->d_local.p, p->d_blocksum.p); ISR_COUNT_LAUNCH();
-  blockscan_kernel<<<1, 1024, 0, st>>>(nb, p->d_blocksum.p, p->d_blockoff.p, p->d_off.p + nitems); ISR_COUNT_LAUNCH();
   const int heavy = p->eps.kind == 2;     // only a tabulated efficiency can give an item more than 1 + kMaxRowBreaks panels
-  fill_kernel<<<nb, kCountThreads, 0, st>>>(nitems, p->d_row.p, p->eps, p->d_ext.p, p->d_cnt.p, p->d_local.p, p->d_blockoff.p,
+  fill_kernel<<<nb, kCountThreads, 0, st>>>(nitems, p->d_row.p, p->eps, p->d_ext.p, p->d_cnt.p, p->d_local.p, p->d_blocksum.p,
                                             p->d_off.p, p->d_pa.p, p->d_pb.p, p->d_pitem.p, p->d_pkind.p, heavy); ISR_COUNT_LAUNCH();
   if (heavy) {
     fill_heavy_kernel<<<(nitems + 7) / 8, 256, 0, st>>>(nitems, p->d_row.p, p->eps, p->d_ext.p, p->d_cnt.p, p->d_off.p,
@@ -919,13 +903,14 @@ static int finish_assembly(isr_problem* p, const double* ecm_err, const double* 
                                                      p->d_pa.p, p->d_pb.p, p->d_peps.p, p->d_pitem.p,
                                                      p->d_pkind.p, node_eps_dev, p->d_pm.p); ISR_COUNT_LAUNCH();
   dim3 cgrid((n + kCtCols - 1) / kCtCols, (n + kCtRows - 1) / kCtRows, nslices);
+  double* part = nslices == 1 ? p->d_G.p : p->d_Gpart.p;   // a single slice is the result itself
   if (p->eps.kind == 2) {   // many panels per item: reduce once, then contract
     ISR_TRY(reduce_moments(p));
-    contract_kernel<false><<<cgrid, 256, 0, st>>>(n, p->d_off.p, p->d_M.p, p->d_Ct.p, p->d_klo.p, p->d_khi.p, p->d_Gpart.p); ISR_COUNT_LAUNCH();
+    contract_kernel<false><<<cgrid, 256, 0, st>>>(n, p->d_off.p, p->d_M.p, p->d_Ct.p, p->d_klo.p, p->d_khi.p, part); ISR_COUNT_LAUNCH();
   } else {
-    contract_kernel<true><<<cgrid, 256, 0, st>>>(n, p->d_off.p, p->d_pm.p, p->d_Ct.p, p->d_klo.p, p->d_khi.p, p->d_Gpart.p); ISR_COUNT_LAUNCH();
+    contract_kernel<true><<<cgrid, 256, 0, st>>>(n, p->d_off.p, p->d_pm.p, p->d_Ct.p, p->d_klo.p, p->d_khi.p, part); ISR_COUNT_LAUNCH();
   }
-  contract_sum_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(n * n, nslices, p->d_Gpart.p, p->d_G.p); ISR_COUNT_LAUNCH();
+  if (nslices > 1) { contract_sum_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(n * n, nslices, p->d_Gpart.p, p->d_G.p); ISR_COUNT_LAUNCH(); }
   if (ecm_err) {
     for (int i = 0; i < n; ++i)
       if (!(ecm_err[i] > 0.0)) {

@@ -26,7 +26,7 @@ struct isr_problem {
   isr::DevBuf<isr::RowConst> d_row;
   isr::DevBuf<int> d_cnt;        // panels per (row, segment) item, then exclusive scan (+1 entry)
   isr::DevBuf<int> d_off;
-  isr::DevBuf<int> d_local, d_blocksum, d_blockoff;   // block-local prefixes and block totals / offsets of the panel counts
+  isr::DevBuf<int> d_local, d_blocksum;   // block-local prefixes and block totals of the panel counts
   isr::DevBuf<double> d_pa, d_pb, d_peps, d_pm;  // panel bounds, eps value, 4 moments per panel
   isr::DevBuf<int> d_pitem, d_pkind;
   isr::DevBuf<double> d_M;       // [i][k][4] normalised moments (filled on demand by isr_debug_moments)
