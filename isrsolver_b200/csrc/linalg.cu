@@ -355,10 +355,12 @@ gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, d
 // max |A X - I| <= 1e-12 n (then |X - A^-1| <= |A^-1| |A X - I|, i.e. 2e-10 relative at N = 200, typically 1e-13);
 // otherwise -- zero pivot, growth, NaN -- the partially pivoted factorisation is used, exactly as before.
 // lower_hint: the caller knows A to be lower triangular (used for N > 240 only).
+// enqueue_dependents: launches of the caller that only read Ainv; they are enqueued BEFORE the host waits for the
+// certificate, so that the GPU works on while the host wakes up (and once more if the pivoted fall-back replaces Ainv).
 // tri[0] / tri[1] = 1 iff Ainv / A came out exactly lower triangular (linear interpolation without energy spread: the
 // toy kernel then skips the structural zeros); read back with the certificate, no extra synchronisation.
 int lu_inverse(isr_ctx* c, int n, const double* A, double* lu, double* prod, double* Ainv, DevBuf<double>& work,
-               DevBuf<int>& ipiv, DevBuf<int>& info, bool lower_hint, int* tri) {
+               DevBuf<int>& ipiv, DevBuf<int>& info, bool lower_hint, int* tri, const std::function<int()>& enqueue_dependents) {
   int lwork = 0;
   const size_t bytes = sizeof(double) * (size_t)n * n;
   ISR_CUSOLVER(cusolverDnDgetrf_bufferSize(c->solver, n, n, lu, n, &lwork));
@@ -391,6 +393,7 @@ int lu_inverse(isr_ctx* c, int n, const double* A, double* lu, double* prod, dou
   inverse_residual_kernel<<<n, 256, 0, c->stream>>>(n, prod, Ainv, A, resid_dev); ISR_COUNT_LAUNCH();
   double resid[3] = {INFINITY, INFINITY, INFINITY};
   ISR_CUDA(cudaMemcpyAsync(resid, resid_dev, sizeof(resid), cudaMemcpyDeviceToHost, c->stream));
+  ISR_TRY(enqueue_dependents());
   ISR_CUDA(cudaStreamSynchronize(c->stream));
   tri[0] = resid[1] == 0.0;
   tri[1] = resid[2] == 0.0;
@@ -407,7 +410,7 @@ int lu_inverse(isr_ctx* c, int n, const double* A, double* lu, double* prod, dou
   ISR_TRY(check_info(c, info.p, "LU solve (getrs)"));    // synchronises
   tri[0] = resid[1] == 0.0;     // row exchanges usually leave rounding residue above the diagonal
   tri[1] = resid[2] == 0.0;
-  return ISR_OK;
+  return enqueue_dependents();
 }
 
 // B(i, k') = A[i][n-1-k']: column-major copy of a row-major operator with its columns reversed

@@ -2,6 +2,8 @@
 #pragma once
 #include "common.cuh"
 
+#include <functional>
+
 namespace isr {
 void colmajor_to_rowmajor(cudaStream_t st, int n, const double* A, const double* rowscale, int invert_scale,
                           double* out, int ld);
@@ -10,7 +12,7 @@ void scale_rows(cudaStream_t st, int n, const double* A, const double* s, int in
 int gemm(isr_ctx* c, bool ta, bool tb, int n, const double* A, const double* B, double* C);
 int gemv(isr_ctx* c, bool ta, int n, const double* A, const double* x, double* y);
 int lu_inverse(isr_ctx* c, int n, const double* A, double* lu, double* prod, double* Ainv, DevBuf<double>& work,
-               DevBuf<int>& ipiv, DevBuf<int>& info, bool lower_hint, int* tri);
+               DevBuf<int>& ipiv, DevBuf<int>& info, bool lower_hint, int* tri, const std::function<int()>& enqueue_dependents);
 int ql_factor_rowmajor(isr_ctx* c, int n, int ld, double* A, double* scratch, DevBuf<double>& work, DevBuf<int>& info);
 int svd(isr_ctx* c, int n, double* A, double* U, double* S, double* VT, DevBuf<double>& work, DevBuf<int>& info);
 int svd_values_async(cusolverDnHandle_t h, int n, double* A, double* S, DevBuf<double>& work, DevBuf<int>& info);

@@ -36,10 +36,15 @@ int factor(isr_problem* p, const double* vcs_err) {
   p->vcs_err.assign(vcs_err, vcs_err + n);
   ISR_CUDA(cudaMemcpyAsync(p->d_werr.p, vcs_err, sizeof(double) * n, cudaMemcpyHostToDevice, st));
   ISR_TRY(p->d_tmp2.reserve(nn));
-  ISR_TRY(lu_inverse(c, n, p->d_G.p, p->d_tmp.p, p->d_tmp2.p, p->d_Ginv.p, p->d_work, p->d_ipiv, p->d_info, p->G_lower, p->tri_sle));
+  // the operator set-up only reads G^-1: it is enqueued before the host waits for the inverse's certificate
+  ISR_TRY(lu_inverse(c, n, p->d_G.p, p->d_tmp.p, p->d_tmp2.p, p->d_Ginv.p, p->d_work, p->d_ipiv, p->d_info, p->G_lower, p->tri_sle,
+                     [p]() { return launch_sle_operators(p); }));
   p->factored = true;
   p->cov_ready = false;      // Cov / G^T W G are formed on first use (ensure_cov): the toy path never reads them
-  return select_sle(p);
+  p->tri_sel[0] = p->tri_sle[0];
+  p->tri_sel[1] = p->tri_sle[1];
+  p->solver_selected = true;
+  return ISR_OK;
 }
 
 // Cov = (Ginv W^(-1/2)) (Ginv W^(-1/2))^T and InvCov = R^T R, once per factorisation and only when asked for.
@@ -77,12 +82,16 @@ __global__ void sle_operators_kernel(int n, int ld, const double* __restrict__ G
 }
 
 // Operators the toy kernel consumes: row-major, leading dimension padded to even, pad column zero.
-int select_sle(isr_problem* p) {
-  if (!p->factored) { set_error("select: isr_factor has not been called"); return ISR_ESTATE; }
+int launch_sle_operators(isr_problem* p) {
   const int n = p->n, ld = (n + 1) & ~1;
   cudaStream_t st = p->ctx->stream;
   sle_operators_kernel<<<(n * ld + 255) / 256, 256, 0, st>>>(n, ld, p->d_G.p, p->d_Ginv.p, p->d_werr.p, p->d_R.p, p->d_Sop.p, p->d_Rop.p); ISR_COUNT_LAUNCH();
   ISR_CUDA(cudaGetLastError());
+  return ISR_OK;
+}
+int select_sle(isr_problem* p) {
+  if (!p->factored) { set_error("select: isr_factor has not been called"); return ISR_ESTATE; }
+  ISR_TRY(launch_sle_operators(p));
   p->tri_sel[0] = p->tri_sle[0];
   p->tri_sel[1] = p->tri_sle[1];
   p->solver_selected = true;

@@ -4,6 +4,7 @@ struct isr_problem;
 namespace isr {
 int factor(isr_problem* p, const double* vcs_err);
 int select_sle(isr_problem* p);
+int launch_sle_operators(isr_problem* p);
 int ensure_cov(isr_problem* p);
 int iterative_solve(isr_problem* p, int niter, const double* vcs, double* bcs_out, double* radcorr_out);
 int minmax_device(isr_ctx* c, int64_t n, const double* v_dev, double* lo, double* hi);

@@ -13,6 +13,9 @@
 #include "toy_gemm.cuh"
 
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <utility>
 
 namespace isr {
 
@@ -152,6 +155,20 @@ static const ToyCfg* pick_cfg(int n, int nstat) {
 
 const char* toy_cfg_name(int n) { return pick_cfg(n, 1)->name; }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel) and size: it is a driver call on the path
+// between the factorisation's certificate and the toy launch, where the GPU waits for the host
+static int ensure_dynamic_smem(int device, const void* kernel, size_t smem) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> done;
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& have = done[{device, kernel}];
+  if (smem > have) {
+    ISR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    have = smem;
+  }
+  return ISR_OK;
+}
+
 static int launch_fused(isr_problem* p, int64_t T, const double* V_dev, const double* Sop, const double* Rop,
                         const double* b0_dev, double* Dfull, const ToyOut& out) {
   const int n = p->n, ld = (n + 1) & ~1;
@@ -203,7 +220,7 @@ static int launch_fused(isr_problem* p, int64_t T, const double* V_dev, const do
   g.tri = 0;
   if (p->toy_variant != 1) g.tri = (Sop == p->d_Sop.p ? p->tri_sel[0] : 0) | ((Rop && Rop == p->d_Rop.p) ? p->tri_sel[1] << 1 : 0);
   auto kernel = g.tri ? cfg->kernel_tri : cfg->kernel;
-  ISR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ISR_TRY(ensure_dynamic_smem(p->ctx->device, (const void*)kernel, smem));
   kernel<<<ctas, cfg->threads, smem, st>>>(mapV, mapS, mapR, mapD, g); ISR_COUNT_LAUNCH();
   if (want_stats) {
     reduce_part_kernel<<<(n + 3) / 4, 128, 0, st>>>(ctas, g.part_ld, n, nstat, p->d_acc.p, out.sum_bcs, out.ratio_stats); ISR_COUNT_LAUNCH();
