@@ -211,13 +211,14 @@ def run_b200(args, rank, world, local_rank):
     ev = lambda: torch.cuda.Event(enable_timing=True)
     asm_ev, toy_ev = [], []
 
-    def combine(lo, hi, local_counts, rehist):
+    def combine(lo, hi, local_counts, rehist, sum_bcs):
         """Global TH1F over all ranks: gather (min, max | sum_bcs), bin locally against the GLOBAL range (keeps the
         result bit-identical to one GPU), all_reduce the integer counters.  local_counts: counters already binned
-        against (lo, hi), or None; rehist(lo, hi) bins this rank's chi2 (which stays on the device)."""
+        against (lo, hi), or None; rehist(lo, hi) bins this rank's chi2 (which stays on the device); sum_bcs: this
+        rank's sum of the toy solutions (host array of the call that produced it)."""
         if world > 1:
             small[0], small[1] = lo, hi
-            small[2:] = mine[T:T + n]                   # sum of the toy solutions rides in the same gather
+            small[2:] = torch.from_numpy(sum_bcs)       # sum of the toy solutions rides in the same gather
             dist.all_gather_into_tensor(small_all.view(-1), small)
             sa = small_all.cpu()
             glo, ghi = float(sa[:, 0].min()), float(sa[:, 1].max())
@@ -275,7 +276,7 @@ def run_b200(args, rank, world, local_rank):
             L.check(lib.isr_last_chi2_histogram(prob, 128, glo, ghi, L.uptr(counts)))
             return counts
         with torch.cuda.stream(stream):
-            return combine(lo.value, hi.value, None, rehist)
+            return combine(lo.value, hi.value, None, rehist, sumb_host)
 
     lohi = np.zeros(2)
 
@@ -291,7 +292,7 @@ def run_b200(args, rank, world, local_rank):
             L.check(lib.isr_last_chi2_histogram(prob, 128, glo, ghi, L.uptr(counts)))
             return counts
         with torch.cuda.stream(stream):
-            return combine(float(lohi[0]), float(lohi[1]), counts, rehist)
+            return combine(float(lohi[0]), float(lohi[1]), counts, rehist, sumb_host)
 
     def barrier():
         if world > 1:
