@@ -189,6 +189,8 @@ class ISRSolverSLE : public BaseISRSolver {   // include/ISRSolverSLE.hpp
     invalidate();
     return cond;
   }
+  // toy-kernel schedule (isr_set_toy_kernel): 0 default, 1 dense cross-check, 2 triangularised chi2 factor
+  void setToySchedule(int variant) { check(isr_set_toy_kernel(_p, variant)); }
   // the toy loop body for T toys (toy-major V); any output may be nullptr
   virtual void toyBatch(int64_t T, const double* V, const double* bcs0, double* chi2, double* sumBcs, double* ratioStats,
                         uint32_t* ratioHist, double* bcsOut) {
