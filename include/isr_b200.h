@@ -56,6 +56,10 @@ void isr_ctx_destroy(isr_ctx* ctx);
 const char* isr_last_error(void);
 /* cudaStream_t used by all launches of this context (as void*), for event timing by the caller. */
 void* isr_ctx_stream(isr_ctx* ctx);
+/* Page-locked host memory for the arrays the host-buffer calls move in bulk (the toys of isr_toy_batch, the chi2 array):
+ * from pageable memory such a copy runs at a fraction of the PCIe rate.  Plain cudaMallocHost / cudaFreeHost. */
+int isr_host_alloc(isr_ctx* ctx, size_t bytes, void** out);
+void isr_host_free(void* ptr);
 int isr_ctx_synchronize(isr_ctx* ctx);
 /* Number of kernels of THIS library launched by this process so far (diagnostic; bench.py's gpu_launches). */
 int64_t isr_launch_count(void);

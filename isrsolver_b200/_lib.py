@@ -47,6 +47,8 @@ SIGNATURES = {
     "isr_ctx_destroy": (None, [_vp]),
     "isr_last_error": (C.c_char_p, []),
     "isr_ctx_stream": (_vp, [_vp]),
+    "isr_host_alloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "isr_host_free": (None, [C.c_void_p]),
     "isr_ctx_synchronize": (C.c_int, [_vp]),
     "isr_launch_count": (_i64, []),
     "isr_problem_create": (C.c_int, [_vp, C.c_int, _dp, C.c_double, C.c_int, _ip, C.POINTER(EpsDesc), C.POINTER(_vp)]),

@@ -73,6 +73,18 @@ void isr_ctx_destroy(isr_ctx* c) {
 
 void* isr_ctx_stream(isr_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
+int isr_host_alloc(isr_ctx* c, size_t bytes, void** out) {
+  if (!c || !out) { set_error("isr_host_alloc: NULL argument"); return ISR_EINVAL; }
+  *out = nullptr;
+  if (bytes == 0) return ISR_OK;
+  ISR_CUDA(cudaSetDevice(c->device));
+  ISR_CUDA(cudaMallocHost(out, bytes));
+  return ISR_OK;
+}
+void isr_host_free(void* ptr) {
+  if (ptr) cudaFreeHost(ptr);
+}
+
 int isr_ctx_synchronize(isr_ctx* c) {
   if (!c) { set_error("ctx == NULL"); return ISR_EINVAL; }
   ISR_CUDA(cudaStreamSynchronize(c->stream));

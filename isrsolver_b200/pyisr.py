@@ -260,11 +260,35 @@ class Efficiency:
         return d
 
 
-def draw_toys(vcs, vcs_err, n: int, seed: int = TOY_SEED):
+def pinned_empty(shape, device: int | None = None):
+    """An uninitialised float64 array in page-locked host memory (isr_host_alloc): what isr_toy_batch copies from at
+    the PCIe rate.  Freed when the array (and every view of it) is gone."""
+    import weakref
+    shape = tuple(int(s) for s in np.atleast_1d(shape))
+    count = int(np.prod(shape))
+    if count == 0:
+        return np.empty(shape)
+    lib = L.load()
+    ptr = C.c_void_p()
+    L.check(lib.isr_host_alloc(_ctx(device), count * 8, C.byref(ptr)))
+    buf = (C.c_double * count).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=np.float64).reshape(shape)
+    weakref.finalize(buf, lib.isr_host_free, C.c_void_p(ptr.value))   # arr.base chain keeps buf alive
+    return arr
+
+
+def draw_toys(vcs, vcs_err, n: int, seed: int = TOY_SEED, pinned: bool = False):
     """n toy visible cross sections, toy-major (n, N): vcs + vcs_err * z, z ~ N(0,1) from PCG64(seed).
-    Stands in for randomDrawVisCS (src/Utils.cpp:6-13)."""
-    z = np.random.Generator(np.random.PCG64(seed)).standard_normal((int(n), len(vcs)))
-    return np.asarray(vcs)[None, :] + np.asarray(vcs_err)[None, :] * z
+    Stands in for randomDrawVisCS (src/Utils.cpp:6-13).  pinned=True: the same values in page-locked memory."""
+    gen = np.random.Generator(np.random.PCG64(seed))
+    if not pinned:
+        z = gen.standard_normal((int(n), len(vcs)))
+        return np.asarray(vcs)[None, :] + np.asarray(vcs_err)[None, :] * z
+    V = pinned_empty((int(n), len(vcs)))
+    gen.standard_normal(out=V)
+    V *= np.asarray(vcs_err)[None, :]
+    V += np.asarray(vcs)[None, :]
+    return V
 
 
 def draw_toys_device(vcs, vcs_err, n: int, seed: int = TOY_SEED, first_toy: int = 0, device: int | None = None):
@@ -593,7 +617,7 @@ class ISRSolverSLE(BaseISRSolver):
         (or `toys`), copied to the GPU; rng="device": toys drawn on the GPU (toy_campaign), no bulk transfer."""
         if rng == "device" and toys is None:
             return self.toy_campaign(n, vcs, vcs_err, bcs0, seed)
-        V = draw_toys(vcs, vcs_err, n, seed) if toys is None else toys
+        V = draw_toys(vcs, vcs_err, n, seed, pinned=True) if toys is None else toys   # pinned: H2D at the PCIe rate
         chi2 = self.toy_batch(V, bcs0)["chi2"]
         lo, hi = C.c_double(), C.c_double()
         counts = np.zeros(130, dtype=np.uint32)

@@ -198,6 +198,29 @@ def test_last_chi2_range_and_histogram_from_the_device(oracle):
     np.testing.assert_array_equal(cnt, ref.astype(np.uint32))
 
 
+def test_pinned_toys_are_the_same_toys(oracle):
+    """draw_toys(pinned=True) fills page-locked memory (isr_host_alloc) with exactly the values of the pageable
+    stream; a batch fed from it returns the same bits; the memory is released with the array."""
+    import gc
+    import isrsolver_b200 as isr
+    from isrsolver_b200.pyisr import pinned_empty
+    g = load_golden("c2_sle_n40_cspline")
+    s = make_solver(g)
+    vcs, err = g["G_converged"] @ g["bcs0"], np.full(len(g["bcs0"]), 0.03)
+    Vp = isr.draw_toys(vcs, err, 300, seed=5, pinned=True)
+    Vn = isr.draw_toys(vcs, err, 300, seed=5)
+    np.testing.assert_allclose(Vp, Vn, rtol=0, atol=1e-15)      # (a * z + b in two steps vs one expression)
+    r1, r2 = s.toy_batch(Vp, g["bcs0"]), s.toy_batch(np.array(Vp), g["bcs0"])
+    np.testing.assert_array_equal(r1["chi2"], r2["chi2"])
+    a = pinned_empty((3, 4)); a[:] = 7.0
+    assert a.shape == (3, 4) and a.sum() == 84.0
+    del a, Vp; gc.collect()
+    assert pinned_empty(0).size == 0
+    res = s.chi2_test(500, vcs, g["bcs0"], err, seed=11)          # draws its toys into pinned memory
+    ref = s.toy_batch(isr.draw_toys(vcs, err, 500, seed=11), g["bcs0"])["chi2"]
+    np.testing.assert_allclose(res["chi2"], ref, rtol=1e-12)
+
+
 def test_empty_batch():
     import isrsolver_b200 as isr
     g = load_golden("c1_sle_n50_linear")
