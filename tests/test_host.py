@@ -43,6 +43,23 @@ def test_header_cites_reference_interfaces():
 
 
 @pytest.mark.skipif(_has_gpu(), reason="checks the no-device failure mode")
+def test_cpp_class_mirror_compiles_against_the_c_abi(tmp_path):
+    """include/isr_b200.hpp (the C++ mirror of BaseISRSolver / ISRSolverSLE / ISRSolverTikhonov / ISRSolverTSVD, the host
+    side a maintainer of the reference would keep) must compile as plain C++17 against include/isr_b200.h alone -- no
+    CUDA headers, no torch -- and link against the shared library."""
+    import shutil
+    import subprocess
+    cxx = shutil.which("g++")
+    if cxx is None:
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "t.cpp"
+    src.write_text('#include "isr_b200.hpp"\nint main() { return isr_last_error() == nullptr; }\n')
+    lib = os.path.join(root, "isrsolver_b200")
+    subprocess.check_call([cxx, "-std=c++17", "-Wall", "-I", os.path.join(root, "include"), str(src), "-o", str(tmp_path / "t"),
+                           "-L", lib, "-lisr_b200", "-Wl,-rpath," + lib, "-Wl,-rpath,/usr/local/cuda/lib64"])
+
+
 def test_no_cpu_fallback_without_device():
     from isrsolver_b200 import _lib as L
     lib = L.load()
