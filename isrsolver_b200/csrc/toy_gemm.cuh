@@ -124,33 +124,35 @@ struct ToyArgs {
 // hold (a single tile, or an operator so small that a unit is shorter than STAGES-1 chunks) the
 // sequential order U1(i) NOP U2(i) is used instead, NOP being STAGES-1 empty chunks.
 enum { PH_P1 = 0, PH_P2 = 1, PH_NOP = 2 };
+// (The schedule structs are __host__ __device__: tests/cpp/test_sched.cu walks them on the CPU and checks the
+// invariants stated above for every tile shape, chunk count and triangularity.)
 // Dense schedule: every column block has all nk chunks.
 struct SchedDense {
   int m, u;        // local tiles, unit index
   int nblk, nk, nop, do2, seq;
   int cb, kc;
-  __device__ void init(int m_, int nblk_, int nk_, int nop_, int do2_, int, int) {
+  __host__ __device__ void init(int m_, int nblk_, int nk_, int nop_, int do2_, int, int) {
     m = m_; nblk = nblk_; nk = nk_; nop = nop_; do2 = do2_; u = 0; cb = 0; kc = 0;
     seq = (m == 1) || (nk * nblk < nop);
   }
-  __device__ int units() const { return do2 ? (seq ? 3 * m : 2 * m) : m; }
-  __device__ bool done() const { return u >= units(); }
-  __device__ int kind() const {
+  __host__ __device__ int units() const { return do2 ? (seq ? 3 * m : 2 * m) : m; }
+  __host__ __device__ bool done() const { return u >= units(); }
+  __host__ __device__ int kind() const {
     if (!do2) return PH_P1;
     if (seq) { const int r = u % 3; return r == 0 ? PH_P1 : (r == 1 ? PH_NOP : PH_P2); }
     if (u == 0) return PH_P1;
     if (u == 2 * m - 1) return PH_P2;
     return (u & 1) ? PH_P1 : PH_P2;
   }
-  __device__ int tile() const {   // local tile index
+  __host__ __device__ int tile() const {   // local tile index
     if (!do2) return u;
     if (seq) return u / 3;
     if (u == 0) return 0;
     if (u == 2 * m - 1) return m - 1;
     return (u & 1) ? (u + 1) / 2 : u / 2 - 1;
   }
-  __device__ bool last_chunk() const { return kc == nk - 1; }   // of the current column block
-  __device__ void advance() {
+  __host__ __device__ bool last_chunk() const { return kc == nk - 1; }   // of the current column block
+  __host__ __device__ void advance() {
     if (kind() == PH_NOP) {
       if (++kc == nop) { kc = 0; ++u; }
       return;
@@ -171,17 +173,17 @@ struct SchedTri {
   int cb, kc;
   int tri, ld;   // tri: bit 0 = pass-1 operator lower triangular, bit 1 = pass-2 operator.  Column block cb of a
                           // triangular operator only has non-zero K below (cb + 1) * np: the chunks beyond are not loaded
-  __device__ int nk_tri(int b, int pass2) const {
+  __host__ __device__ int nk_tri(int b, int pass2) const {
     if (!((tri >> pass2) & 1)) return nk;
     const int lim = min(ld, (b + 1) * np);
     return (lim + kcs - 1) / kcs;
   }
   int knd, cnk;   // kind and chunk count of the current (unit, column block): refreshed on transitions only
-  __device__ void refresh() {
+  __host__ __device__ void refresh() {
     knd = kind_of_unit();
     cnk = knd == PH_NOP ? nop : nk_tri(cb, knd == PH_P2);
   }
-  __device__ void init(int m_, int nblk_, int nk_, int nop_, int do2_, int tri_, int ld_) {
+  __host__ __device__ void init(int m_, int nblk_, int nk_, int nop_, int do2_, int tri_, int ld_) {
     m = m_; nblk = nblk_; nk = nk_; nop = nop_; do2 = do2_; u = 0; cb = 0; kc = 0;
     tri = tri_; ld = ld_;
     int t1 = 0, t2 = 0;
@@ -189,25 +191,25 @@ struct SchedTri {
     seq = (m == 1) || (min(t1, t2) < nop);
     refresh();
   }
-  __device__ int units() const { return do2 ? (seq ? 3 * m : 2 * m) : m; }
-  __device__ bool done() const { return u >= units(); }
-  __device__ int kind() const { return knd; }
-  __device__ int kind_of_unit() const {
+  __host__ __device__ int units() const { return do2 ? (seq ? 3 * m : 2 * m) : m; }
+  __host__ __device__ bool done() const { return u >= units(); }
+  __host__ __device__ int kind() const { return knd; }
+  __host__ __device__ int kind_of_unit() const {
     if (!do2) return PH_P1;
     if (seq) { const int r = u % 3; return r == 0 ? PH_P1 : (r == 1 ? PH_NOP : PH_P2); }
     if (u == 0) return PH_P1;
     if (u == 2 * m - 1) return PH_P2;
     return (u & 1) ? PH_P1 : PH_P2;
   }
-  __device__ int tile() const {   // local tile index
+  __host__ __device__ int tile() const {   // local tile index
     if (!do2) return u;
     if (seq) return u / 3;
     if (u == 0) return 0;
     if (u == 2 * m - 1) return m - 1;
     return (u & 1) ? (u + 1) / 2 : u / 2 - 1;
   }
-  __device__ bool last_chunk() const { return kc == cnk - 1; }   // of the current column block
-  __device__ void advance() {
+  __host__ __device__ bool last_chunk() const { return kc == cnk - 1; }   // of the current column block
+  __host__ __device__ void advance() {
     if (++kc == cnk) {
       kc = 0;
       if (knd == PH_NOP || ++cb == nblk) { cb = 0; ++u; }

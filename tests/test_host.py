@@ -60,6 +60,24 @@ def test_cpp_class_mirror_compiles_against_the_c_abi(tmp_path):
                            "-L", lib, "-lisr_b200", "-Wl,-rpath," + lib, "-Wl,-rpath,/usr/local/cuda/lib64"])
 
 
+def test_toy_kernel_chunk_schedules_on_the_cpu(tmp_path):
+    """tests/cpp/test_sched.cu walks the toy kernel's own chunk schedules (SchedDense / SchedTri of
+    csrc/toy_gemm.cuh, __host__ __device__) on the host: every (tile, pass, column block, chunk) exactly once and in
+    order, triangular chunk counts, and the pipeline-safety distance between pass 1 and pass 2 of a tile."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("no nvcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "test_sched")
+    subprocess.check_call([nvcc, "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a", "--expt-relaxed-constexpr",
+                           "--extended-lambda", "-I", os.path.join(root, "isrsolver_b200", "csrc"), "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp", "test_sched.cu"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "schedule walk ok" in out.stdout, out.stdout + out.stderr
+
+
 def test_no_cpu_fallback_without_device():
     from isrsolver_b200 import _lib as L
     lib = L.load()
