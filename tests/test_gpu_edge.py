@@ -192,3 +192,25 @@ def test_inverse_sizes_around_the_cluster_kernel_limits(n):
             e = np.zeros((1, n)); e[0, -1] = 1.0
             be = s.toy_batch(e, np.zeros(n), want_bcs=True)["bcs"][0]
             assert np.all(be[:-1] == 0.0)
+
+
+def test_inverse_every_size_through_the_cluster_kernel():
+    """Every N from 2 to 260: the Gauss-Jordan kernel's slot / parity bookkeeping depends on N through the number of
+    pivot blocks, the rows per CTA and which CTA owns which block -- a wrong phase would hang or corrupt, so each size
+    is factored (dense and lower triangular) and checked against NumPy."""
+    import isrsolver_b200 as isr
+    rng = np.random.default_rng(77)
+    for n in range(2, 261):
+        ecm = np.linspace(1.0, 2.0, n)
+        for lower in (False, True):
+            G = np.eye(n) * 2.0 + np.tril(rng.random((n, n))) * 0.3
+            if not lower:
+                G += 0.05 * rng.random((n, n))
+            b0 = 1.0 + rng.random(n); err = 0.05 + 0.1 * rng.random(n)
+            s = isr.ISRSolverSLE(n, ecm, G @ b0, None, err, THR)
+            s.set_matrix(G)
+            s.solve()
+            assert np.allclose(s.bcs(), b0, rtol=1e-12, atol=0), (n, lower)
+            Ginv = np.linalg.inv(G)
+            cov = (Ginv * err[None, :]) @ (Ginv * err[None, :]).T
+            assert np.abs(s.bcs_cov_matrix() - cov).max() <= 1e-10 * np.abs(cov).max(), (n, lower)
