@@ -159,6 +159,29 @@ def test_triangular_schedule_without_chi2_pass(oracle, n, T):
         np.testing.assert_array_equal(out[0][key], out[1][key])
 
 
+def test_triangular_schedule_every_size():
+    """Every N from 2 to 300 (all tile shapes, chunk counts and odd / even paddings on the way): the triangular
+    schedule must return the bits of the dense one on lower-triangular operators, chi2 and solutions alike."""
+    import isrsolver_b200 as isr
+    rng = np.random.default_rng(808)
+    T = 70
+    for n in range(2, 301):
+        ecm = np.linspace(1.0, 2.0, n)
+        G = np.tril(rng.random((n, n)) * 0.1) + np.eye(n)
+        err = 0.05 + 0.1 * rng.random(n)
+        b0 = 1.0 + rng.random(n)
+        V = (G @ b0)[None, :] + err[None, :] * rng.standard_normal((T, n))
+        out = []
+        for variant in (0, 1):
+            s = isr.ISRSolverSLE(n, ecm, G @ b0, None, err, 0.9)
+            s.set_matrix(G); s.set_toy_schedule(variant)
+            out.append(s.toy_batch(V, b0, want_sum=True, want_bcs=True))
+        assert np.array_equal(out[0]["chi2"], out[1]["chi2"]) and np.array_equal(out[0]["bcs"], out[1]["bcs"]), n
+        assert np.array_equal(out[0]["sum_bcs"], out[1]["sum_bcs"]), n
+        ref = np.linalg.solve(G, V.T).T
+        assert np.allclose(out[0]["bcs"], ref, rtol=1e-10, atol=1e-12), n
+
+
 def test_qr_chi2_factor_of_rank_deficient_and_ill_conditioned_operators(oracle):
     """TSVD with k < N selects a rank-deficient chi2 factor, a tiny lambda a badly conditioned one: the Householder
     QL replacement must reproduce the dense schedule there too."""
