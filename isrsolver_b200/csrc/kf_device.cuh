@@ -1,4 +1,6 @@
-// Device-side Kuraev-Fadin radiator F(x, s) and the per-row constants it needs.
+// Device-side Kuraev-Fadin radiator F(x, s) and the per-row constants it needs.  (__host__ __device__: the same
+// source is compiled for the host by tests/cpp/test_kf_host.cu and checked against the reference formula's known values
+// without a GPU.)
 // Reference formula: kernelKuraevFadin, src/KuraevFadin.cpp:14-49 (fLog :10, fBeta :12).
 #pragma once
 
@@ -26,7 +28,7 @@ __host__ __device__ inline void row_const_init(RowConst& rc, double E, double th
 
 // F(x, s) given ln(x) and the pair-threshold power (x - x0)^beta (pass pow_y < 0 below threshold).
 // log1p(-x) replaces log(1-x): identical to rounding for the x range of the path, better for tiny x.
-__device__ __forceinline__ double kf_value(const RowConst& rc, double x, double lnx, double pow_y) {
+__host__ __device__ __forceinline__ double kf_value(const RowConst& rc, double x, double lnx, double pow_y) {
   const double b = rc.beta;
   const double mx = 1.0 - x;
   const double lnm = log1p(-x);
@@ -47,7 +49,7 @@ __device__ __forceinline__ double kf_value(const RowConst& rc, double x, double 
 }
 
 // Plain (x, s) evaluation with the reference's own threshold test, for isr_kernel_kf.
-__device__ inline double kf_plain(double x, double s) {
+__host__ __device__ inline double kf_plain(double x, double s) {
   RowConst rc;
   const double E = sqrt(s);
   row_const_init(rc, E, 0.0);

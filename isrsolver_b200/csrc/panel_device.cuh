@@ -6,11 +6,23 @@
 
 namespace isr {
 
+// Round-to-nearest products / quotients that must not be contracted into FMAs (bit-exact ROOT bin arithmetic): the
+// intrinsics on the device, plain operators in the host compilation of the same source (tests/cpp/test_kf_host.cu).
+#ifdef __CUDA_ARCH__
+#define ISR_DMUL_RN(a, b) __dmul_rn((a), (b))
+#define ISR_DDIV_RN(a, b) __ddiv_rn((a), (b))
+#define ISR_DSUB_RN(a, b) __dsub_rn((a), (b))
+#else
+#define ISR_DMUL_RN(a, b) ((a) * (b))
+#define ISR_DDIV_RN(a, b) ((a) / (b))
+#define ISR_DSUB_RN(a, b) ((a) - (b))
+#endif
+
 // Grading points of the x-interval (0, rc.xmax] of a row whose constants are already set: x0, then
 // x0 (1 + 4^m) for m = -2, -1, 0, 1, ... (ratio <= 4 to both singular points 0 and x0), then
 // 1 - (1 - xmax) 4^m towards the pole of the pair term at x = 1.  Every panel between consecutive points is
 // then analytic with Bernstein parameter rho >= 3 in its integration variable.
-__device__ __forceinline__ void row_grading(RowConst& rc) {
+__host__ __device__ __forceinline__ void row_grading(RowConst& rc) {
   int nb = 0;
   rc.rb[nb++] = rc.x0;
   double f = 1.0 / 16.0;
@@ -43,11 +55,11 @@ __device__ __forceinline__ void row_grading(RowConst& rc) {
 }
 
 // ROOT TAxis::FindBin arithmetic (bit-exact: no FMA contraction in the index expression).
-__device__ __forceinline__ int eps_find_bin(const EpsDev& e, double x) {
+__host__ __device__ __forceinline__ int eps_find_bin(const EpsDev& e, double x) {
   if (x < e.xlo) return 0;
   if (!(x < e.xhi)) return e.nx + 1;
   if (!e.xedges) {
-    const double t = __ddiv_rn(__dmul_rn((double)e.nx, __dsub_rn(x, e.xlo)), __dsub_rn(e.xhi, e.xlo));
+    const double t = ISR_DDIV_RN(ISR_DMUL_RN((double)e.nx, ISR_DSUB_RN(x, e.xlo)), ISR_DSUB_RN(e.xhi, e.xlo));
     return 1 + (int)t;
   }
   int l = 0, h = e.nx;
@@ -57,13 +69,13 @@ __device__ __forceinline__ int eps_find_bin(const EpsDev& e, double x) {
   }
   return 1 + l;
 }
-__device__ __forceinline__ double eps_edge(const EpsDev& e, int m) {
+__host__ __device__ __forceinline__ double eps_edge(const EpsDev& e, int m) {
   if (e.xedges) return e.xedges[m];
   if (m == e.nx) return e.xhi;
   return e.xlo + (double)m * ((e.xhi - e.xlo) / (double)e.nx);
 }
 // smallest edge index m in [0, nx] with edge(m) > v, or nx+1
-__device__ __forceinline__ int eps_first_edge_above(const EpsDev& e, double v) {
+__host__ __device__ __forceinline__ int eps_first_edge_above(const EpsDev& e, double v) {
   int m;
   if (e.xedges) {
     int l = -1, h = e.nx + 1;  // edge(l) <= v < edge(h)
@@ -82,7 +94,7 @@ __device__ __forceinline__ int eps_first_edge_above(const EpsDev& e, double v) {
 }
 
 // smallest edge index m in [0, nx] with edge(m) >= v, or nx+1
-__device__ __forceinline__ int eps_first_edge_ge(const EpsDev& e, double v) {
+__host__ __device__ __forceinline__ int eps_first_edge_ge(const EpsDev& e, double v) {
   int m = eps_first_edge_above(e, v);          // edge(m) > v, edge(m-1) <= v
   if (m > 0 && eps_edge(e, m - 1) == v) --m;   // an edge exactly at v
   return m;

@@ -78,6 +78,26 @@ def test_toy_kernel_chunk_schedules_on_the_cpu(tmp_path):
     assert out.returncode == 0 and "schedule walk ok" in out.stdout, out.stdout + out.stderr
 
 
+def test_integrand_source_on_the_cpu(tmp_path, oracle):
+    """tests/cpp/test_kf_host.cu compiles the product's own integrand headers (kf_device.cuh, panel_device.cuh:
+    __host__ __device__) for the host and compares kf_plain / kf_value / the ROOT bin arithmetic with the oracle's
+    restatement of the reference (and SURVEY 8c's known values) -- the only product arithmetic that can run without a GPU."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("no nvcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    orc = os.path.join(root, "oracle")
+    exe = str(tmp_path / "test_kf_host")
+    subprocess.check_call([nvcc, "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a", "--expt-relaxed-constexpr",
+                           "-I", os.path.join(root, "isrsolver_b200", "csrc"), "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp", "test_kf_host.cu"), "-o", exe, "-L", orc, "-lisr_oracle",
+                           "-Xlinker", "-rpath=" + orc])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "integrand source ok" in out.stdout, out.stdout + out.stderr
+
+
 def test_no_cpu_fallback_without_device():
     from isrsolver_b200 import _lib as L
     lib = L.load()
