@@ -98,6 +98,23 @@ def test_integrand_source_on_the_cpu(tmp_path, oracle):
     assert out.returncode == 0 and "integrand source ok" in out.stdout, out.stdout + out.stderr
 
 
+def test_philox_known_answers_on_the_cpu(tmp_path):
+    """The bit source of the device toy generator (csrc/rng_device.cuh, __host__ __device__) reproduces the
+    Philox4x32-10 known-answer vectors published with Random123 -- run on the host, no GPU."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("no nvcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "test_philox_host")
+    subprocess.check_call([nvcc, "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a",
+                           "-I", os.path.join(root, "isrsolver_b200", "csrc"),
+                           os.path.join(root, "tests", "cpp", "test_philox_host.cu"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "known answers ok" in out.stdout, out.stdout + out.stderr
+
+
 def test_no_cpu_fallback_without_device():
     from isrsolver_b200 import _lib as L
     lib = L.load()
