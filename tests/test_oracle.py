@@ -328,3 +328,38 @@ def test_linear_algebra_layer_against_exact_arithmetic(oracle):
             bt[i] += Vt[m, i] * z[m] / S[m]
     np.testing.assert_allclose(O.tsvd_solve(G, vcs, err, k)[0], f(bt).ravel(), rtol=1e-8, atol=1e-10)
     mp.mp.dps = 15
+
+
+def test_device_quadrature_tables_against_numpy_and_scipy():
+    """The constants the CUDA kernels integrate with (isrsolver_b200/csrc/gl_tables.cuh, generated at 80 digits) parsed
+    back from the header and checked independently of the generator: Gauss-Legendre nodes / weights against
+    numpy.polynomial.legendre.leggauss, the 6-point Gauss-Hermite rule against numpy.polynomial.hermite.hermgauss, the
+    15-point Kronrod rule with its embedded 7-point Gauss weights against the exactness conditions (Kronrod: degree 22,
+    Gauss: degree 13) -- every table to 1e-15."""
+    import os
+    import re
+    hdr = open(os.path.join(os.path.dirname(__file__), "..", "isrsolver_b200", "csrc", "gl_tables.cuh")).read()
+    tabs = {m.group(1): np.array([float(v) for v in m.group(3).replace("\n", " ").split(",") if v.strip()])
+            for m in re.finditer(r"double (k\w+)\[(\d+)\] = \{(.*?)\};", hdr, re.S)}
+    assert tabs, "no tables parsed"
+    for n in (8, 16, 32):
+        x, w = np.polynomial.legendre.leggauss(n)
+        np.testing.assert_allclose(tabs[f"kGL{n}_x"], x, rtol=0, atol=1e-15)
+        np.testing.assert_allclose(tabs[f"kGL{n}_w"], w, rtol=2e-13, atol=1e-16)   # (numpy's own weights are good to ~1e-13)
+        for p in range(0, 2 * n, max(1, n // 4)):      # exactness through degree 2n - 1: the sharper check
+            exact = 0.0 if p % 2 else 2.0 / (p + 1)
+            assert abs(np.dot(tabs[f"kGL{n}_w"], tabs[f"kGL{n}_x"] ** p) - exact) < 2e-15, (n, p)
+    t, w = np.polynomial.hermite.hermgauss(6)                  # physicists' rule, as gsl_integration_fixed_hermite
+    order = np.argsort(tabs["kGH6_t"])
+    np.testing.assert_allclose(tabs["kGH6_t"][order], t, rtol=0, atol=1e-15)
+    np.testing.assert_allclose(tabs["kGH6_w_over_sqrtpi"][order], w / np.sqrt(np.pi), rtol=1e-14)
+    x, wk, wg = tabs["kGK15_x"], tabs["kGK15_wk"], tabs["kGK15_wg"]
+    assert len(x) == 15 and np.count_nonzero(wg) == 7
+    for p in range(0, 23):          # Kronrod: exact through degree 22
+        exact = 0.0 if p % 2 else 2.0 / (p + 1)
+        assert abs(np.dot(wk, x ** p) - exact) < 2e-15, p
+    for p in range(0, 14):          # embedded 7-point Gauss rule: exact through degree 13
+        exact = 0.0 if p % 2 else 2.0 / (p + 1)
+        assert abs(np.dot(wg, x ** p) - exact) < 2e-15, p
+    xg, wgl = np.polynomial.legendre.leggauss(7)
+    np.testing.assert_allclose(np.sort(x[wg != 0]), xg, rtol=0, atol=1e-15)
