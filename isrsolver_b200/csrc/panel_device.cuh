@@ -1,5 +1,6 @@
 // Device helpers shared by the matrix assembly (assemble.cu) and the forward-convolution service (conv.cu):
-// grading points of a row's x-interval, ROOT bin arithmetic for the efficiency tables.
+// grading points of a row's x-interval, ROOT bin arithmetic for the efficiency tables, the panels of a (row, segment)
+// item and the quadrature nodes of a panel in its singularity-removing variable.
 #pragma once
 
 #include "kf_device.cuh"
@@ -98,6 +99,129 @@ __host__ __device__ __forceinline__ int eps_first_edge_ge(const EpsDev& e, doubl
   int m = eps_first_edge_above(e, v);          // edge(m) > v, edge(m-1) <= v
   if (m > 0 && eps_edge(e, m - 1) == v) --m;   // an edge exactly at v
   return m;
+}
+
+// ---- panel enumeration and quadrature nodes (used by assemble.cu; __host__ __device__ so that tests/cpp/test_panels_host.cu
+// can integrate matrix moments with this very source on the CPU and compare them with the oracle) ----------------------
+
+// x-coordinate of energy node m seen from row i: x = 1 - (ext[m]/E_i)^2, exactly 0 at m = i+1.
+__host__ __device__ __forceinline__ double knot_x(const double* __restrict__ ext, double E, int i, int m) {
+  if (m == i + 1) return 0.0;
+  const double r = ext[m] / E;
+  return fmax(0.0, 1.0 - r * r);
+}
+
+// Panels of item (row i, segment k): the x-interval (xa, xb) of the segment seen from row i, cut at the row's
+// grading points R = {rb[r] in (xa, xb)} and at the efficiency bin edges E = {edge(m) in (xa, xb)}.  The interior
+// cuts are the stable merge of the two ascending sets (R first on a tie; a tie leaves a zero-width panel, which
+// integrates to zero), so the panel count is analytic -- 1 + |R| + |E| -- and the q-th cut can be selected directly:
+// no serial walk over hundreds of bins for the items that span most of a tabulated efficiency.
+struct ItemCuts {
+  double xa, xb;
+  int r0, nR;     // rb[r0 .. r0 + nR) lie strictly inside (xa, xb)
+  int e0, nE;     // edges e0 .. e0 + nE - 1 lie strictly inside (xa, xb)
+  __host__ __device__ int count() const { return xb > xa ? 1 + nR + nE : 0; }
+};
+__host__ __device__ __forceinline__ ItemCuts item_cuts(const RowConst& rc, const EpsDev& eps, const double* __restrict__ ext,
+                                              int i, int k) {
+  ItemCuts c;
+  c.xa = knot_x(ext, rc.E, i, k + 1);
+  c.xb = knot_x(ext, rc.E, i, k);
+  c.r0 = c.nR = c.e0 = c.nE = 0;
+  if (!(c.xb > c.xa)) return c;
+  int r = 0;
+  while (r < rc.nrb && !(rc.rb[r] > c.xa)) ++r;
+  c.r0 = r;
+  while (r < rc.nrb && rc.rb[r] < c.xb) ++r;
+  c.nR = r - c.r0;
+  if (eps.kind == 2) {
+    c.e0 = eps_first_edge_above(eps, c.xa);
+    const int e1 = min(eps_first_edge_ge(eps, c.xb), eps.nx + 1);
+    c.nE = max(0, e1 - c.e0);
+  }
+  return c;
+}
+// Merge state after the first t interior cuts have been consumed: ir grading points and ie = t - ir edges.
+__host__ __device__ __forceinline__ void cuts_state_at(const ItemCuts& c, const RowConst& rc, const EpsDev& eps, int t, int& ir, int& ie) {
+  int used = 0;                 // grading points whose merged position is below t
+  for (int r = 0; r < c.nR; ++r) {
+    int before = 0;             // edges of E strictly below rb[r] (they precede it; equal ones follow)
+    if (c.nE > 0) before = min(max(eps_first_edge_ge(eps, rc.rb[c.r0 + r]) - c.e0, 0), c.nE);
+    if (r + before < t) ++used; else break;
+  }
+  ir = used;
+  ie = t - used;
+}
+// Emit panels [q0, q1) of the item in ascending x: incremental merge from the state at cut q0 - 1.
+template <typename Emit>
+__host__ __device__ __forceinline__ void walk_panels(const ItemCuts& c, const RowConst& rc, const EpsDev& eps, int q0, int q1, Emit emit) {
+  const int count = c.count();
+  if (q0 >= q1 || q0 >= count) return;
+  int ir = 0, ie = 0;
+  double cur = c.xa;
+  if (q0 > 0) {
+    cuts_state_at(c, rc, eps, q0 - 1, ir, ie);       // state before cut number q0 - 1 ...
+    const double nr = ir < c.nR ? rc.rb[c.r0 + ir] : 2.0, ne = ie < c.nE ? eps_edge(eps, c.e0 + ie) : 2.0;
+    if (nr <= ne) { cur = nr; ++ir; } else { cur = ne; ++ie; }   // ... and past it: cur = left edge of panel q0
+  }
+  for (int q = q0; q < q1; ++q) {
+    double nxt = c.xb;
+    if (q < count - 1) {
+      const double nr = ir < c.nR ? rc.rb[c.r0 + ir] : 2.0, ne = ie < c.nE ? eps_edge(eps, c.e0 + ie) : 2.0;
+      if (nr <= ne) { nxt = nr; ++ir; } else { nxt = ne; ++ie; }
+    }
+    emit(q, cur, nxt);
+    cur = nxt;
+  }
+}
+
+__host__ __device__ __forceinline__ void item_decode(int idx, int& i, int& k) {
+  int r = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
+  while ((long long)(r + 1) * (r + 2) / 2 <= idx) ++r;
+  while ((long long)r * (r + 1) / 2 > idx) --r;
+  i = r;
+  k = idx - r * (r + 1) / 2;
+}
+
+// kind: 0 = regular (x), 1 = t = x^beta, 2 = u = (x - x0)^beta
+__host__ __device__ __forceinline__ int panel_kind(const RowConst& rc, double b) {
+  if (!(b > rc.x0)) return 1;
+  if (!(b > rc.xin)) return 2;
+  return 0;
+}
+// Node `lane` of a panel: x, ln x, the pair-threshold power (x - x0)^beta (-1 below x0) and the quadrature
+// weight including dx/d(variable).  kind 0: x itself, 1: t = x^beta, 2: u = (x - x0)^beta.
+struct PanelNode { double x, lnx, pw, wj; };
+__host__ __device__ __forceinline__ PanelNode panel_node(const RowConst& rc, double a, double b, int kind, double t, double w) {
+  PanelNode q;
+  q.pw = -1.0;
+  if (kind == 0) {
+    const double half = 0.5 * (b - a);
+    q.x = fma(half, t, 0.5 * (a + b));
+    q.wj = half * w;
+    q.lnx = log(q.x);
+    q.pw = exp(rc.beta * log(q.x - rc.x0));
+  } else if (kind == 1) {
+    const double ta = a > 0.0 ? exp(rc.beta * log(a)) : 0.0;
+    const double tb = exp(rc.beta * log(b));
+    const double half = 0.5 * (tb - ta);
+    const double tt = fma(half, t, 0.5 * (ta + tb));
+    q.lnx = log(tt) * rc.inv_beta;
+    q.x = exp(q.lnx);
+    q.wj = half * w * rc.inv_beta * q.x / tt;
+  } else {
+    const double ya = a - rc.x0, yb = b - rc.x0;
+    const double ua = ya > 0.0 ? exp(rc.beta * log(ya)) : 0.0;
+    const double ub = exp(rc.beta * log(yb));
+    const double half = 0.5 * (ub - ua);
+    const double u = fma(half, t, 0.5 * (ua + ub));
+    const double y = exp(log(u) * rc.inv_beta);
+    q.x = rc.x0 + y;
+    q.lnx = log(q.x);
+    q.wj = half * w * rc.inv_beta * y / u;
+    q.pw = u;
+  }
+  return q;
 }
 
 }  // namespace isr

@@ -98,6 +98,28 @@ def test_integrand_source_on_the_cpu(tmp_path, oracle):
     assert out.returncode == 0 and "integrand source ok" in out.stdout, out.stdout + out.stderr
 
 
+def test_panel_quadrature_on_the_cpu(tmp_path, oracle):
+    """tests/cpp/test_panels_host.cu: the product's own panel enumeration, singularity-removing substitutions and
+    integrand (csrc/panel_device.cuh, __host__ __device__), compiled for the host, integrate the four moments of every
+    (row, segment) item of a 14-point problem -- eps = 1 and a tabulated efficiency -- and must agree with the oracle's
+    adaptive QUADPACK integration of the reference integrand to 1e-10 of the item's zeroth moment.  The assembly's
+    numerical core checked against the reference algorithm without a GPU."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("no nvcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    orc = os.path.join(root, "oracle")
+    exe = str(tmp_path / "test_panels_host")
+    subprocess.check_call([nvcc, "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a", "--expt-relaxed-constexpr",
+                           "--extended-lambda", "-I", os.path.join(root, "isrsolver_b200", "csrc"), "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp", "test_panels_host.cu"), "-o", exe, "-L", orc, "-lisr_oracle",
+                           "-Xlinker", "-rpath=" + orc])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "panel quadrature ok" in out.stdout, out.stdout + out.stderr
+
+
 def test_philox_known_answers_on_the_cpu(tmp_path):
     """The bit source of the device toy generator (csrc/rng_device.cuh, __host__ __device__) reproduces the
     Philox4x32-10 known-answer vectors published with Random123 -- run on the host, no GPU."""
