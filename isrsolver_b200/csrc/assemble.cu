@@ -20,6 +20,7 @@
 #include "gl_tables.cuh"
 #include "kf_device.cuh"
 #include "panel_device.cuh"
+#include "basis_host.hpp"
 #include "problem.hpp"
 
 namespace isr {
@@ -27,74 +28,6 @@ namespace isr {
 // =================================================================================================
 // Host: basis coefficient tables
 // =================================================================================================
-
-// Natural cubic spline second-derivative coefficients through (x_m, delta_{m,node}), m = 0..size-1,
-// by the symmetric-tridiagonal LDL^T recurrence (the algorithm GSL's gsl_interp_cspline uses, which
-// the reference instantiates once per cross-section point: src/CSplineRangeInterpolator.cpp:24-40).
-static void natural_spline_c(const std::vector<double>& x, int node, std::vector<double>& c) {
-  const int size = (int)x.size();
-  c.assign(size, 0.0);
-  const int m = size - 2;  // interior unknowns c[1..size-2]
-  if (m < 1) return;
-  std::vector<double> diag(m), off(m), rhs(m);
-  auto y = [node](int q) { return q == node ? 1.0 : 0.0; };
-  for (int q = 0; q < m; ++q) {
-    const double h0 = x[q + 1] - x[q], h1 = x[q + 2] - x[q + 1];
-    const double g0 = h0 != 0.0 ? 1.0 / h0 : 0.0, g1 = h1 != 0.0 ? 1.0 / h1 : 0.0;
-    off[q] = h1;
-    diag[q] = 2.0 * (h1 + h0);
-    rhs[q] = 3.0 * ((y(q + 2) - y(q + 1)) * g1 - (y(q + 1) - y(q)) * g0);
-  }
-  if (m == 1) {
-    c[1] = rhs[0] / diag[0];
-    return;
-  }
-  std::vector<double> alpha(m), gamma(m), z(m);
-  alpha[0] = diag[0];
-  gamma[0] = off[0] / alpha[0];
-  for (int q = 1; q < m - 1; ++q) {
-    alpha[q] = diag[q] - off[q - 1] * gamma[q - 1];
-    gamma[q] = off[q] / alpha[q];
-  }
-  alpha[m - 1] = diag[m - 1] - off[m - 2] * gamma[m - 2];
-  z[0] = rhs[0];
-  for (int q = 1; q < m; ++q) z[q] = rhs[q] - gamma[q - 1] * z[q - 1];
-  for (int q = 0; q < m; ++q) z[q] /= alpha[q];
-  c[m] = z[m - 1];
-  for (int q = m - 2; q >= 0; --q) c[q + 1] = z[q] - gamma[q] * c[q + 2];
-}
-
-// Validate + sort ranges exactly as Interpolator's constructor does (src/Interpolator.cpp:44-59,
-// checkRangeInterpSettings :90-147).
-static int normalise_ranges(int n, int nranges, const int* ranges, std::vector<int>& out) {
-  out.clear();
-  if (nranges <= 0) {  // defaultInterpRangeSettings, :356-360
-    out = {0, 0, n - 1};
-    return ISR_OK;
-  }
-  std::vector<int> idx(nranges);
-  for (int r = 0; r < nranges; ++r) idx[r] = r;
-  std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return ranges[3 * a + 1] < ranges[3 * b + 1]; });
-  if (ranges[3 * idx.front() + 1] != 0 || ranges[3 * idx.back() + 2] + 1 != n) {
-    set_error("[!] Wrong interpolation ranges: must start at segment 0 and end at segment n-1");
-    return ISR_ERANGE;
-  }
-  int pimax = -1;
-  for (int r : idx) {
-    const int imin = ranges[3 * r + 1], imax = ranges[3 * r + 2];
-    if (imin > imax || (pimax != -1 && pimax + 1 != imin)) {
-      set_error("[!] Wrong interpolation ranges: segments missed or taken twice");
-      return ISR_ERANGE;
-    }
-    pimax = imax;
-  }
-  for (int r : idx) {
-    out.push_back(ranges[3 * r] ? 1 : 0);
-    out.push_back(ranges[3 * r + 1]);
-    out.push_back(ranges[3 * r + 2]);
-  }
-  return ISR_OK;
-}
 
 int set_ranges(isr_problem* p, int nranges, const int* ranges) {
   std::vector<int> sorted;
@@ -113,48 +46,7 @@ int set_ranges(isr_problem* p, int nranges, const int* ranges) {
 int build_basis_tables(isr_problem* p) {
   const int n = p->n;
   const std::vector<double>& x = p->ext;
-  p->h_Ct.assign((size_t)n * 4 * n, 0.0);
-  p->h_klo.assign(n, n);
-  p->h_khi.assign(n, -1);
-  p->seg_range.assign(n, 0);
-  auto touch = [&](int j, int k) {
-    p->h_klo[j] = std::min(p->h_klo[j], k);
-    p->h_khi[j] = std::max(p->h_khi[j], k);
-  };
-  auto C = [&](int j, int k, int q) -> double& { return p->h_Ct[((size_t)k * 4 + q) * n + j]; };
-  const int R = (int)p->ranges.size() / 3;
-  std::vector<double> c;
-  for (int r = 0; r < R; ++r) {
-    const int cubic = p->ranges[3 * r], lo = p->ranges[3 * r + 1], hi = p->ranges[3 * r + 2];
-    for (int k = lo; k <= hi; ++k) p->seg_range[k] = r;
-    if (!cubic) {
-      for (int k = lo; k <= hi; ++k) {
-        C(k, k, 1) += 1.0;  // rising edge of node k
-        touch(k, k);
-        if (k >= 1) {       // falling edge of node k-1
-          C(k - 1, k, 0) += 1.0;
-          C(k - 1, k, 1) -= 1.0;
-          touch(k - 1, k);
-        }
-      }
-    } else {
-      const int jlo = lo > 0 ? lo - 1 : 0;
-      for (int j = jlo; j <= hi; ++j) {
-        natural_spline_c(x, j + 1, c);
-        for (int k = lo; k <= hi; ++k) {
-          const double h = x[k + 1] - x[k];
-          const double ylo = (k == j + 1) ? 1.0 : 0.0, yhi = (k + 1 == j + 1) ? 1.0 : 0.0;
-          const double bq = (yhi - ylo) / h - h * (c[k + 1] + 2.0 * c[k]) / 3.0;
-          const double dq = (c[k + 1] - c[k]) / (3.0 * h);
-          C(j, k, 0) += ylo;
-          C(j, k, 1) += bq * h;
-          C(j, k, 2) += c[k] * h * h;
-          C(j, k, 3) += dq * h * h * h;
-          touch(j, k);
-        }
-      }
-    }
-  }
+  compute_basis_tables(n, x, p->ranges, p->h_Ct, p->h_klo, p->h_khi, p->seg_range);
   std::vector<double> invh(n);
   for (int k = 0; k < n; ++k) invh[k] = 1.0 / (x[k + 1] - x[k]);
   cudaStream_t st = p->ctx->stream;

@@ -120,6 +120,43 @@ def test_panel_quadrature_on_the_cpu(tmp_path, oracle):
     assert out.returncode == 0 and "panel quadrature ok" in out.stdout, out.stdout + out.stderr
 
 
+def test_whole_matrices_from_the_product_source_on_the_cpu(tmp_path):
+    """tests/cpp/test_matrix_host.cu assembles whole matrices on the CPU from the product's own source -- range
+    normalisation + basis tables (csrc/basis_host.hpp, the host code behind isr_problem_set_ranges) and the panel
+    quadrature the kernels run (csrc/panel_device.cuh compiled for the host).  The golden fixtures' problems must pass
+    the SAME gates as on the GPU (tests/test_gpu_assembly.py::test_matrix_vs_golden): 1e-9 against the converged oracle
+    and against the reference's own compiled code; invalid ranges must be refused."""
+    import shutil
+    import subprocess
+    from conftest import assert_matrix_parity, load_golden
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("no nvcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "test_matrix_host")
+    subprocess.check_call([nvcc, "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a", "--expt-relaxed-constexpr",
+                           "--extended-lambda", "-I", os.path.join(root, "isrsolver_b200", "csrc"), "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp", "test_matrix_host.cu"), "-o", exe])
+
+    def run(ecm, thr, settings):
+        inp = (f"{len(ecm)} {float(thr)!r} {len(settings)}\n" + " ".join(repr(float(e)) for e in ecm) + "\n" +
+               "\n".join(" ".join(str(int(v)) for v in r) for r in settings) + "\n")
+        return subprocess.run([exe], input=inp, capture_output=True, text=True)
+    for name in ("c1_sle_n50_linear", "c2_sle_n40_cspline", "c5_mixed3_n36"):
+        g = load_golden(name)
+        out = run(g["ecm"], g["threshold"], g["settings"])
+        assert out.returncode == 0, out.stderr
+        G = np.array([[float(v) for v in line.split()] for line in out.stdout.strip().splitlines()])
+        assert_matrix_parity(G, g["G_converged"], g["G_converged_err"], what=name + " (CPU build of the product source) vs converged oracle")
+        assert_matrix_parity(G, g["G_ref"], 3 * g["G_faithful_err"], row_rel=1e-9, what=name + " vs the compiled reference")
+        if "linear" in name:
+            assert np.all(np.triu(G, 1) == 0)
+    g = load_golden("c1_sle_n50_linear")
+    n = len(g["ecm"])
+    assert run(g["ecm"], g["threshold"], [(0, 0, 10), (1, 12, n - 1)]).returncode == 3      # segment 11 missed -> ISR_ERANGE
+    assert run(g["ecm"], g["threshold"], [(0, 0, 20), (1, 15, n - 1)]).returncode == 3      # overlap
+
+
 def test_philox_known_answers_on_the_cpu(tmp_path):
     """The bit source of the device toy generator (csrc/rng_device.cuh, __host__ __device__) reproduces the
     Philox4x32-10 known-answer vectors published with Random123 -- run on the host, no GPU."""
