@@ -524,32 +524,6 @@ __global__ void contract_sum_kernel(int nn, int nslices, const double* __restric
 // =================================================================================================
 // Device: energy spread  G <- G_spread * G   (src/ISRSolverSLE.cpp:146-148, 177-193)
 // =================================================================================================
-// Segment lookup: k with ext[k] < E <= ext[k+1] (the (min, max] convention of
-// BaseRangeInterpolator::isEnergyInRange, src/BaseRangeInterpolator.cpp:45-47).
-__device__ __forceinline__ int segment_of(const double* __restrict__ ext, int n, double e) {
-  int l = 0, h = n;  // ext[l] < e <= ext[h]
-  while (h - l > 1) {
-    const int m = (l + h) >> 1;
-    if (ext[m] < e) l = m; else h = m;
-  }
-  return l;
-}
-// Interpolator::basisEval (src/Interpolator.cpp:217-258) / basisDerivEval (:266-287) from the tables.
-__device__ double basis_eval_dev(int n, const double* __restrict__ ext, const double* __restrict__ invh,
-                                 const double* __restrict__ Ct, int j, double e, int deriv) {
-  if (e <= ext[0]) return 0.0;
-  if (e > ext[n]) {
-    if (deriv) return 0.0;
-    return j == n - 1 ? 1.0 : 0.0;  // value at E_max of the last range's basis: delta_{j, n-1}
-  }
-  const int k = segment_of(ext, n, e);
-  const double dn = (e - ext[k]) * invh[k];
-  const double c0 = Ct[((size_t)k * 4 + 0) * n + j], c1 = Ct[((size_t)k * 4 + 1) * n + j];
-  const double c2 = Ct[((size_t)k * 4 + 2) * n + j], c3 = Ct[((size_t)k * 4 + 3) * n + j];
-  if (deriv) return (c1 + dn * (2.0 * c2 + 3.0 * c3 * dn)) * invh[k];
-  return c0 + dn * (c1 + dn * (c2 + dn * c3));
-}
-
 // S(i,j) = sum_m (w_m/sqrt(pi)) * basis_j(E_i + sqrt(2) sigma_i t_m): 6-point Gauss-Hermite
 // (gaussian_conv, src/Integration.cpp:86-100).  Column-major output.
 __global__ void spread_kernel(int n, const double* __restrict__ ext, const double* __restrict__ invh,

@@ -224,4 +224,31 @@ __host__ __device__ __forceinline__ PanelNode panel_node(const RowConst& rc, dou
   return q;
 }
 
+// ---- basis functions from the coefficient tables (energy spread, isr_basis_eval, isr_interp_eval) ---------------------
+// Segment lookup: k with ext[k] < E <= ext[k+1] (the (min, max] convention of
+// BaseRangeInterpolator::isEnergyInRange, src/BaseRangeInterpolator.cpp:45-47).
+__host__ __device__ __forceinline__ int segment_of(const double* __restrict__ ext, int n, double e) {
+  int l = 0, h = n;  // ext[l] < e <= ext[h]
+  while (h - l > 1) {
+    const int m = (l + h) >> 1;
+    if (ext[m] < e) l = m; else h = m;
+  }
+  return l;
+}
+// Interpolator::basisEval (src/Interpolator.cpp:217-258) / basisDerivEval (:266-287) from the tables.
+__host__ __device__ inline double basis_eval_dev(int n, const double* __restrict__ ext, const double* __restrict__ invh,
+                                 const double* __restrict__ Ct, int j, double e, int deriv) {
+  if (e <= ext[0]) return 0.0;
+  if (e > ext[n]) {
+    if (deriv) return 0.0;
+    return j == n - 1 ? 1.0 : 0.0;  // value at E_max of the last range's basis: delta_{j, n-1}
+  }
+  const int k = segment_of(ext, n, e);
+  const double dn = (e - ext[k]) * invh[k];
+  const double c0 = Ct[((size_t)k * 4 + 0) * n + j], c1 = Ct[((size_t)k * 4 + 1) * n + j];
+  const double c2 = Ct[((size_t)k * 4 + 2) * n + j], c3 = Ct[((size_t)k * 4 + 3) * n + j];
+  if (deriv) return (c1 + dn * (2.0 * c2 + 3.0 * c3 * dn)) * invh[k];
+  return c0 + dn * (c1 + dn * (c2 + dn * c3));
+}
+
 }  // namespace isr

@@ -138,19 +138,37 @@ def test_whole_matrices_from_the_product_source_on_the_cpu(tmp_path):
                            "--extended-lambda", "-I", os.path.join(root, "isrsolver_b200", "csrc"), "-I", os.path.join(root, "include"),
                            os.path.join(root, "tests", "cpp", "test_matrix_host.cu"), "-o", exe])
 
-    def run(ecm, thr, settings):
+    def run(ecm, thr, settings, eff=None, sigma=None):
         inp = (f"{len(ecm)} {float(thr)!r} {len(settings)}\n" + " ".join(repr(float(e)) for e in ecm) + "\n" +
                "\n".join(" ".join(str(int(v)) for v in r) for r in settings) + "\n")
+        if eff is None:
+            inp += "0 0.0 1.0\n"
+        else:
+            vals, nx, xlo, xhi = eff
+            inp += f"{int(nx)} {float(xlo)!r} {float(xhi)!r}\n" + " ".join(repr(float(v)) for v in np.asarray(vals).ravel()) + "\n"
+        inp += "0\n" if sigma is None else "1\n" + " ".join(repr(float(v)) for v in sigma) + "\n"
         return subprocess.run([exe], input=inp, capture_output=True, text=True)
+
+    def matrix(out):
+        assert out.returncode == 0, out.stderr
+        return np.array([[float(v) for v in line.split()] for line in out.stdout.strip().splitlines()])
     for name in ("c1_sle_n50_linear", "c2_sle_n40_cspline", "c5_mixed3_n36"):
         g = load_golden(name)
-        out = run(g["ecm"], g["threshold"], g["settings"])
-        assert out.returncode == 0, out.stderr
-        G = np.array([[float(v) for v in line.split()] for line in out.stdout.strip().splitlines()])
+        G = matrix(run(g["ecm"], g["threshold"], g["settings"]))
         assert_matrix_parity(G, g["G_converged"], g["G_converged_err"], what=name + " (CPU build of the product source) vs converged oracle")
         assert_matrix_parity(G, g["G_ref"], 3 * g["G_faithful_err"], row_rel=1e-9, what=name + " vs the compiled reference")
         if "linear" in name:
             assert np.all(np.triu(G, 1) == 0)
+    # tabulated efficiency (ISRSolverSLE2, 64 bins per energy point) and beam-energy spread: gates of
+    # test_matrix_with_row_table_efficiency / test_matrix_with_energy_spread
+    g = load_golden("c3_sle2_n24_eps64")
+    G = matrix(run(g["ecm"], g["threshold"], g["settings"], eff=(g["eff_values"], g["eff_nx"], g["eff_xlo"], g["eff_xhi"])))
+    assert_matrix_parity(G, g["G_converged"], g["G_converged_err"], what="eps table vs converged")
+    assert_matrix_parity(G, g["G_ref"], 3 * g["G_faithful_err"], row_rel=1e-9, what="eps table vs the compiled reference")
+    g = load_golden("c4_tikhonov_n32_spread")
+    G = matrix(run(g["ecm"], g["threshold"], g["settings"], sigma=g["ecm_err"]))
+    assert_matrix_parity(G, g["G_spread"], 32 * g["G_converged_err"].max(), what="spread matrix")
+    assert_matrix_parity(G, g["S_ref"] @ g["G_ref"], 32 * 3 * g["G_faithful_err"].max(), row_rel=1e-9, what="spread matrix vs the compiled reference")
     g = load_golden("c1_sle_n50_linear")
     n = len(g["ecm"])
     assert run(g["ecm"], g["threshold"], [(0, 0, 10), (1, 12, n - 1)]).returncode == 3      # segment 11 missed -> ISR_ERANGE
