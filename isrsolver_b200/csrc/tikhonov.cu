@@ -18,6 +18,7 @@
 #include "problem.hpp"
 #include "solve.hpp"
 #include "tikhonov.hpp"
+#include "tikhonov_device.cuh"
 #include "toy_batch.hpp"
 #include "toy_gemm.cuh"
 
@@ -116,29 +117,18 @@ int tikhonov_prepare(isr_problem* p, const double* vcs_err, int deriv_reg) {
   return ISR_OK;
 }
 
-// One thread per lambda: the L-curve functionals (see the header comment).
+// One thread per lambda: the L-curve functionals (tikhonov_device.cuh).
 __global__ void lcurve_kernel(int n, int64_t L, const double* __restrict__ lam, const double* __restrict__ mu,
                               const double* __restrict__ c, double* __restrict__ eqn, double* __restrict__ smooth,
                               double* __restrict__ curv, double* __restrict__ dcurv, double* __restrict__ Z) {
   const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= L) return;
-  const double la = lam[l];
-  double x = 0, y = 0, s3 = 0, s4 = 0;
-  for (int m = 0; m < n; ++m) {
-    const double cm = c[m], d = mu[m] + la, id = 1.0 / d, c2 = cm * cm;
-    const double q2 = c2 * id * id;
-    y += q2;
-    x += q2 * (la * la / mu[m]);
-    s3 += q2 * id;
-    s4 += q2 * id * id;
-    if (Z) Z[(size_t)l * n + m] = cm * id;   // row-major L x N: coefficients of b_lambda in the U basis
-  }
-  const double dksi = -2.0 * s3, d2ksi = 6.0 * s4;
-  const double q = 1.0 + la * la;
+  double x, y, cv, dcv;
+  lcurve_point(n, lam[l], mu, c, x, y, cv, dcv, Z ? Z + (size_t)l * n : nullptr);
   if (eqn) eqn[l] = x;
   if (smooth) smooth[l] = y;
-  if (curv) curv[l] = -fabs(1.0 / dksi / pow(q, 1.5));                                         // :115-119
-  if (dcurv) dcurv[l] = -d2ksi * (1.0 / (dksi * dksi)) * pow(q, -1.5) + -3.0 * la / dksi * pow(q, -2.5);  // :121-128
+  if (curv) curv[l] = cv;
+  if (dcurv) dcurv[l] = dcv;
 }
 
 int tikhonov_scan(isr_problem* p, int64_t L, const double* lambda, const double* vcs, double* eqn, double* smooth,

@@ -175,6 +175,44 @@ def test_whole_matrices_from_the_product_source_on_the_cpu(tmp_path):
     assert run(g["ecm"], g["threshold"], [(0, 0, 20), (1, 15, n - 1)]).returncode == 3      # overlap
 
 
+def test_tikhonov_lcurve_arithmetic_on_the_cpu(tmp_path):
+    """tests/cpp/test_lcurve_host.cu runs the product's per-lambda Tikhonov arithmetic (csrc/tikhonov_device.cuh, the body
+    of lcurve_kernel) on the host.  With (mu, U) from SciPy's generalised eigen-solver for the golden C4-like problem it
+    must reproduce the literal matrix evaluation of src/ISRSolverTikhonov.cpp:61-128 stored in the fixture: solution,
+    residual norm, smoothness norm, L-curve curvature and its derivative."""
+    import shutil
+    import subprocess
+    import scipy.linalg as sla
+    from conftest import load_golden
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("no nvcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "test_lcurve_host")
+    subprocess.check_call([nvcc, "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a",
+                           "-I", os.path.join(root, "isrsolver_b200", "csrc"),
+                           os.path.join(root, "tests", "cpp", "test_lcurve_host.cu"), "-o", exe])
+    g = load_golden("c4_tikhonov_n32_spread")
+    G, F, v, err = g["G_spread"], g["tik_F"], g["vcs"], g["vcs_err"]
+    W = np.diag(err ** -2.0)
+    mu, U = sla.eigh(G.T @ W @ G, F)
+    c = U.T @ G.T @ W @ v
+    lam = np.asarray(g["tik_lambda"], dtype=float)
+    inp = (f"{len(mu)} {len(lam)}\n" + " ".join(repr(float(x)) for x in mu) + "\n" + " ".join(repr(float(x)) for x in c) + "\n" +
+           " ".join(repr(float(x)) for x in lam) + "\n")
+    out = subprocess.run([exe], input=inp, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    rows = np.array([[float(t) for t in line.split()] for line in out.stdout.strip().splitlines()])
+    for q in range(len(lam)):
+        x, y, curv, dcurv, z = rows[q, 0], rows[q, 1], rows[q, 2], rows[q, 3], rows[q, 4:]
+        np.testing.assert_allclose(U @ z, g["tik_bcs"][q], rtol=1e-6)
+        assert y == pytest.approx(g["tik_y"][q], rel=1e-6)
+        assert x == pytest.approx(g["tik_x"][q], rel=1e-5, abs=1e-9)
+        assert curv == pytest.approx(g["tik_curv"][q], rel=1e-5)
+        if "tik_dcurv" in g:
+            assert dcurv == pytest.approx(g["tik_dcurv"][q], rel=1e-4)
+
+
 def test_philox_known_answers_on_the_cpu(tmp_path):
     """The bit source of the device toy generator (csrc/rng_device.cuh, __host__ __device__) reproduces the
     Philox4x32-10 known-answer vectors published with Random123 -- run on the host, no GPU."""
