@@ -19,6 +19,14 @@ namespace isr {
 #define ISR_DSUB_RN(a, b) ((a) - (b))
 #endif
 
+// TH1::Fill bin arithmetic (TAxis::FindBin, fixed bins): 0 = underflow, nbins+1 = overflow.  __host__ __device__ (the
+// round-to-nearest macros of panel_device.cuh): tests/cpp/test_kf_host.cu checks it against the oracle on the CPU.
+__host__ __device__ __forceinline__ int th1_bin(int nbins, double lo, double hi, double x) {
+  if (x < lo) return 0;
+  if (!(x < hi)) return nbins + 1;
+  return 1 + (int)ISR_DDIV_RN(ISR_DMUL_RN((double)nbins, ISR_DSUB_RN(x, lo)), ISR_DSUB_RN(hi, lo));
+}
+
 // Grading points of the x-interval (0, rc.xmax] of a row whose constants are already set: x0, then
 // x0 (1 + 4^m) for m = -2, -1, 0, 1, ... (ratio <= 4 to both singular points 0 and x0), then
 // 1 - (1 - xmax) 4^m towards the pole of the pair term at x = 1.  Every panel between consecutive points is

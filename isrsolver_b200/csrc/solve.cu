@@ -1,6 +1,7 @@
 // ISRSolverSLE::solve pieces that run once per problem (src/ISRSolverSLE.cpp:86-95), the chi2 / ratio
 // histogramming of src/Chi2Test.cpp:64-78, and the host-buffer toy-batch pipeline.
 #include "linalg.hpp"
+#include "panel_device.cuh"
 #include "problem.hpp"
 #include "solve.hpp"
 #include "toy_batch.hpp"
@@ -127,12 +128,6 @@ __global__ void minmax_kernel(int64_t n, const double* __restrict__ v, double* _
   }
 }
 
-// TH1::Fill bin arithmetic (TAxis::FindBin, fixed bins): 0 = underflow, nbins+1 = overflow.
-__device__ __forceinline__ int th1_bin(int nbins, double lo, double hi, double x) {
-  if (x < lo) return 0;
-  if (!(x < hi)) return nbins + 1;
-  return 1 + (int)__ddiv_rn(__dmul_rn((double)nbins, __dsub_rn(x, lo)), __dsub_rn(hi, lo));
-}
 __global__ void hist_kernel(int64_t n, const double* __restrict__ v, int nbins, double lo, double hi,
                             uint32_t* __restrict__ counts) {
   extern __shared__ uint32_t sh[];

@@ -73,6 +73,20 @@ int main() {
       ++n;
     }
   }
+  // ---- TH1 bin arithmetic of the chi2 / ratio histograms (th1_bin; fixed bins) against the same oracle routine
+  {
+    unsigned long long st = 1234567ull;
+    for (int nb : {128, 1024}) {
+      const double lo = nb == 1024 ? -2.0 : 151.73, hi = nb == 1024 ? 2.0 : 268.4;
+      for (int q = 0; q < 50000; ++q) {
+        st ^= st << 13; st ^= st >> 7; st ^= st << 17;
+        double x = lo - 0.05 * (hi - lo) + 1.1 * (hi - lo) * (double)(st >> 11) / 9007199254740992.0;
+        if (q <= nb) x = lo + (hi - lo) * (double)q / nb;     // on the edges
+        CHECK(th1_bin(nb, lo, hi, x) == orc_find_bin(nb, lo, hi, nullptr, x), "th1_bin nbins = %d x = %.17g", nb, x);
+        ++n;
+      }
+    }
+  }
   std::printf("integrand source ok on the host: %ld comparisons\n", n);
   return 0;
 }
