@@ -350,7 +350,8 @@ def run_b200(args, rank, world, local_rank):
         "config": workload_config(args, world),
         "assembly_ms": asm_ms, "toy_batch_ms": toy_ms,
         "assembly": {"panels": npan.value, "nodes": nnode.value, "ms": asm_ms},
-        "roofline": {"bound": "tensor", "kernel": "toy_fused_kernel<4,5,2,5,2,40> (one launch: TMA box loads -> DMMA m8n8k4 f64, pass 1 b = S v and pass 2 chi2 = |R(b-b0)|^2)",
+        "roofline": {"bound": "tensor", "kernel": "toy_fused_kernel, tile " + (lib.isr_toy_tile_name(n, 1) or b"?").decode() +
+                               " (one launch: TMA box loads -> DMMA m8n8k4 f64, pass 1 b = S v and pass 2 chi2 = |R(b-b0)|^2)",
                      "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
                      # dram__bytes_read + dram__bytes_write of the fused launch from the ncu --set full capture
                      # in profiles/ncu_r01_toy_dense_final.txt (840.00 + 176.71 MB for 524288 toys at N=200), scaled to this T

@@ -153,6 +153,10 @@ int isr_toy_batch_dev(isr_problem* p, int64_t T, const double* V_dev, const doub
  * |L d|^2 = |R d|^2 = d^T Cov^-1 d of src/Chi2Test.cpp:51-55 up to rounding): 3 N^2 flop per toy, for campaigns long
  * enough (about 10^6 toys) to repay the Householder QR. */
 int isr_set_toy_kernel(isr_problem* p, int variant);
+/* Name of the tile shape the fused toy kernel uses at N points -- m<toys per tile>n<columns per block>w<warps>[s<stages>]
+ * [k<K chunk>] -- with no column statistics (nstat 0), the sum of solutions (1) or the ratio statistics (4); NULL if no
+ * shape fits the 227 KB of shared memory.  Pure host logic (no device needed): diagnostics and bench labels. */
+const char* isr_toy_tile_name(int n, int nstat);
 
 /* Toy campaigns by COUNT, as the reference's chi2Test / chi2TestData / ratioTestModel take them (src/Chi2Test.cpp:29-60,
  * 160-195; src/RatioTest.cpp:13-45): toys first_toy .. first_toy + T - 1 of the stream `seed` are drawn on the device,

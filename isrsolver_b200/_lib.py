@@ -78,6 +78,7 @@ SIGNATURES = {
     "isr_toy_campaign_dev": (C.c_int, [_vp, _i64, _i64, C.c_uint64, _dp, _dp, _dp, _vp, _vp, _vp, _vp]),
     "isr_draw_toys": (C.c_int, [_vp, _i64, C.c_int, _i64, C.c_uint64, _dp, _dp, _dp]),
     "isr_set_toy_kernel": (C.c_int, [_vp, C.c_int]),
+    "isr_toy_tile_name": (C.c_char_p, [C.c_int, C.c_int]),
     "isr_minmax_dev": (C.c_int, [_vp, _i64, _vp, _dp, _dp]),
     "isr_minmax_to_dev": (C.c_int, [_vp, _i64, _vp, _vp]),
     "isr_histogram_range_dev": (C.c_int, [_vp, _i64, _vp, C.c_int, _vp, _vp]),

@@ -423,6 +423,11 @@ int isr_cond_spread_scan(isr_problem* p, int K, const double* sigma, int per_poi
   return ISR_OK;
 }
 
+const char* isr_toy_tile_name(int n, int nstat) {
+  if (n < 1 || (nstat != 0 && nstat != 1 && nstat != 4)) return nullptr;
+  return toy_cfg_name(n, nstat);
+}
+
 int isr_set_toy_kernel(isr_problem* p, int variant) {
   if (!p || variant < 0 || variant > 2) { set_error("isr_set_toy_kernel: bad argument"); return ISR_EINVAL; }
   p->toy_variant = variant;

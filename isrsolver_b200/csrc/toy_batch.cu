@@ -153,7 +153,10 @@ static const ToyCfg* pick_cfg(int n, int nstat) {
   return best;
 }
 
-const char* toy_cfg_name(int n) { return pick_cfg(n, 1)->name; }
+const char* toy_cfg_name(int n, int nstat) {
+  const ToyCfg* c = pick_cfg(n, nstat);
+  return c ? c->name : nullptr;
+}
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel) and size: it is a driver call on the path
 // between the factorisation's certificate and the toy launch, where the GPU waits for the host

@@ -11,6 +11,6 @@ struct ToyOut {
 };
 // All pointers are device pointers; launches go to the problem's context stream.
 int toy_batch_device(isr_problem* p, int64_t T, const double* V_dev, const double* b0_dev, const ToyOut& out);
-const char* toy_cfg_name(int n);
+const char* toy_cfg_name(int n, int nstat);   // nstat: 0 none, 1 sum of solutions, 4 ratio statistics; nullptr: no tile fits
 double* scratch_dfull(isr_problem* p, int64_t T);
 }  // namespace isr

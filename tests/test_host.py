@@ -213,6 +213,22 @@ def test_tikhonov_lcurve_arithmetic_on_the_cpu(tmp_path):
             assert dcurv == pytest.approx(g["tik_dcurv"][q], rel=1e-4)
 
 
+def test_toy_tile_chooser_without_a_device():
+    """isr_toy_tile_name is pure host logic: every N the tests and BASELINE configs use gets a tile shape that fits the
+    227 KB of shared memory, the measured winners are the ones chosen (DESIGN K5), and impossible requests return NULL."""
+    from isrsolver_b200 import _lib as L
+    lib = L.load()
+    assert lib.isr_toy_tile_name(200, 1) == b"m64n200w20s2k40"      # bench / C4 size: 5 full 40-double chunks, 20 warps
+    assert lib.isr_toy_tile_name(100, 1) == b"m128n104w16s2k40"     # C2
+    assert lib.isr_toy_tile_name(500, 1) == b"m64n256w16s2k40"      # C5 chi2 only
+    assert lib.isr_toy_tile_name(500, 4) == b"m64n128w16s2k40"      # C5 with ratio statistics: smaller column block
+    for n in range(1, 1001):
+        for nstat in (0, 1, 4):
+            assert lib.isr_toy_tile_name(n, nstat) is not None, (n, nstat)
+    assert lib.isr_toy_tile_name(0, 1) is None and lib.isr_toy_tile_name(200, 3) is None
+    assert lib.isr_toy_tile_name(3000, 4) is None                   # ratio statistics of 3000 points do not fit
+
+
 def test_philox_known_answers_on_the_cpu(tmp_path):
     """The bit source of the device toy generator (csrc/rng_device.cuh, __host__ __device__) reproduces the
     Philox4x32-10 known-answer vectors published with Random123 -- run on the host, no GPU."""
