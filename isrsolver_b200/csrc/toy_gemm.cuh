@@ -218,6 +218,16 @@ struct SchedTri {
   }
 };
 
+// Triangular schedule: first column tile j of warp wn (tile j covers columns (j WN + wn) 8 .. + 8 of the column block) that
+// has a non-zero in a chunk whose first K index lies k_rel columns past the block's first column: B[n][k] == 0 for k > n,
+// so the tile is live iff its last column (j WN + wn) 8 + 7 >= k_rel.  __host__ __device__: tests/cpp/test_sched.cu checks
+// on the CPU that exactly the all-zero tiles are skipped.
+template <int WN>
+__host__ __device__ __forceinline__ int tri_first_live_tile(int k_rel, int wn) {
+  const int need = k_rel / 8 - wn;
+  return need <= 0 ? 0 : (need + WN - 1) / WN;
+}
+
 template <int J> struct IntC { static constexpr int value = J; };
 // f(IntC<jmin>) for a run-time jmin in [0, BT): a chain of compares ending in a compile-time specialised body
 template <int J, int BT, class F>
@@ -356,10 +366,7 @@ toy_fused_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant
         // real branches into a body specialised for jm: a predicated-off DMMA still occupies the pipe (measured, no gain)
         // and a per-k-step test costs more instructions than the zeros it saves (ncu: 60 % DMMA-busy against 75 %).
         int jm = 0;
-        if ((g.tri >> (kind == PH_P2)) & 1) {
-          const int need = (q.kc * kKC - q.cb * NP) / 8 - wn;
-          jm = need <= 0 ? 0 : (need + WN - 1) / WN;
-        }
+        if ((g.tri >> (kind == PH_P2)) & 1) jm = tri_first_live_tile<WN>(q.kc * kKC - q.cb * NP, wn);
         auto body = [&](auto jmc) {
           constexpr int JM = decltype(jmc)::value;
 #pragma unroll

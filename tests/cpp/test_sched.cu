@@ -6,7 +6,9 @@
 //       in order, and a triangular column block b has exactly ceil(min(ld, (b + 1) NP) / KC) chunks;
 //   (2) pass 2 of a tile starts at least STAGES - 1 chunks after the last chunk of its pass 1 (the d-tile is complete
 //       before the first loads of its pass 2 are issued, loads running STAGES chunks ahead);
-//   (3) NOP chunks appear only in the sequential order and the walk terminates after exactly the expected number of chunks.
+//   (3) NOP chunks appear only in the sequential order and the walk terminates after exactly the expected number of chunks;
+//   (4) the triangular schedule (tri_first_live_tile, nk_tri) skips exactly the column tiles / chunks that hold nothing but
+//       structural zeros of a lower-triangular operator, for every shipped tile shape.
 #include <cstdio>
 #include <cstdlib>
 #include <map>
@@ -93,7 +95,41 @@ static void sweep() {
         }
 }
 
+// Triangular skipping: with B[n][k] == 0 for k > n, (a) the chunks a column block does not load (kc >= nk_tri) hold only
+// zeros for it, and (b) within a loaded chunk warp wn skips exactly the column tiles that are all zero there.
+template <int WN, int BT, int KC>
+static void tri_tiles(int nblk) {
+  constexpr int NP = WN * BT * 8;
+  const int m = 1, nk = 0, stages = 2, do2 = 1, tri = 3;   // (context of the CHECK message)
+  for (int ld = (nblk - 1) * NP + 2; ld <= nblk * NP; ld += 2) {
+    const int nk_all = (ld + KC - 1) / KC;
+    SchedTri<NP, KC> q;
+    q.init(1, nblk, nk_all, 1, 1, 3, ld);
+    for (int cb = 0; cb < nblk; ++cb) {
+      const int loaded = q.nk_tri(cb, 0);
+      for (int kc = 0; kc < nk_all; ++kc) {
+        const int k0 = kc * KC, n_first = cb * NP, n_last_blk = (cb + 1) * NP - 1 < ld - 1 ? (cb + 1) * NP - 1 : ld - 1;
+        if (kc >= loaded) { CHECK(k0 > n_last_blk); continue; }           // (a): every k of the chunk is beyond every column
+        for (int wn = 0; wn < WN; ++wn) {
+          const int jm = tri_first_live_tile<WN>(k0 - n_first, wn);
+          for (int j = 0; j < BT; ++j) {
+            const int n_last = n_first + (j * WN + wn) * 8 + 7;           // last column of the tile
+            if (j < jm) CHECK(n_last < k0);                               // skipped => all zero in this chunk
+            else CHECK(n_last >= k0);                                     // live => it has a k <= n (nothing more could go)
+          }
+        }
+        ++g_cases;
+      }
+    }
+  }
+}
+
 int main() {
+  tri_tiles<5, 5, 40>(1); tri_tiles<5, 5, 40>(3);      // m64n200w20
+  tri_tiles<4, 8, 40>(1); tri_tiles<4, 8, 40>(2);      // m64n256w16 (N = 500: two column blocks)
+  tri_tiles<4, 4, 24>(4); tri_tiles<4, 4, 40>(4);      // m64n128w16
+  tri_tiles<1, 13, 40>(2);                             // m128n104w16
+  tri_tiles<2, 7, 40>(2); tri_tiles<2, 13, 24>(1);     // m128n112w16, m64n208w8
   sweep<200, 40>();
   sweep<256, 40>();
   sweep<128, 24>();

@@ -63,7 +63,8 @@ def test_cpp_class_mirror_compiles_against_the_c_abi(tmp_path):
 def test_toy_kernel_chunk_schedules_on_the_cpu(tmp_path):
     """tests/cpp/test_sched.cu walks the toy kernel's own chunk schedules (SchedDense / SchedTri of
     csrc/toy_gemm.cuh, __host__ __device__) on the host: every (tile, pass, column block, chunk) exactly once and in
-    order, triangular chunk counts, and the pipeline-safety distance between pass 1 and pass 2 of a tile."""
+    order, triangular chunk counts, the pipeline-safety distance between pass 1 and pass 2 of a tile, and -- for every shipped
+    tile shape -- that the triangular schedule skips exactly the column tiles and chunks that hold only structural zeros."""
     import shutil
     import subprocess
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
