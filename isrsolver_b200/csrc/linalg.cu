@@ -3,6 +3,7 @@
 // calls (cuSOLVER / cuBLAS), not the hot path; the per-toy and per-lambda work is in toy_batch.cu and
 // tikhonov.cu.  All matrices here are column-major (Eigen / LAPACK convention).
 #include "linalg.hpp"
+#include "gj_phases.cuh"
 
 
 namespace isr {
@@ -187,7 +188,7 @@ __device__ __forceinline__ void cluster_sync() {
 }
 }  // namespace gj
 
-constexpr int kGjSlots = 4;   // pivot blocks in flight: the owner chain runs ahead of the remote consumers by up to 4 blocks
+
 struct GjSmem {
   double stage[kGjSlots][4][kGjMaxN];    // pivot blocks produced by this CTA (read by its own warps, source of the copies)
   double rowbuf[kGjSlots][4][kGjMaxN];   // pivot blocks received from the other CTAs
@@ -208,14 +209,9 @@ gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, d
   const int row0 = (int)rank * R, wrow = row0 + 4 * warp;      // first of this warp's four rows
   const int Bs = row0 >> 2, Be = min(NB, Bs + (R >> 2));       // blocks whose pivot rows this CTA owns
   auto block_bytes = [&](int B) { return (uint32_t)min(4, n - 4 * B) * kRowBytes; };
-  auto owned = [&](int B) { return B >= Bs && B < Be; };
-  auto below = [&](int x, int slot) { return x <= 0 ? 0 : (x + kGjSlots - 1 - slot) / kGjSlots; };   // #{y in [0, x): y = slot mod 4}
-  // next block after B in the same slot that arrives from another CTA (its rfull phase needs an expect_tx), or -1
-  auto next_remote = [&](int B) {
-    for (B += kGjSlots; B < NB; B += kGjSlots)
-      if (!owned(B)) return B;
-    return -1;
-  };
+  const GjPhases ph{NB, Bs, Be};
+  auto owned = [&](int B) { return ph.owned(B); };
+  auto next_remote = [&](int B) { return ph.next_remote(B); };
   if (tid == 0) {
     if (rank == 0) cert[0] = cert[1] = cert[2] = 0.0;   // the certificate scalars inverse_residual_kernel maximises into
     for (int q = 0; q < kGjSlots; ++q) {
@@ -244,7 +240,7 @@ gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, d
     // ---- credit forwarder: block B consumed by every arithmetic warp of this CTA -> one credit to the owner of block B + 4
     for (int B = 0; B < NB; ++B) {
       const int q = B & (kGjSlots - 1);
-      gj::mbar_wait(&sm.done[q], (uint32_t)(B / kGjSlots) & 1u);
+      gj::mbar_wait(&sm.done[q], GjPhases::done_parity(B));
       if (lane == 0 && B + kGjSlots < NB)
         gj::mbar_remote_arrive(gj::mapa(gj::s32(&sm.empty[q]), (uint32_t)(4 * (B + kGjSlots) / R)));
     }
@@ -259,16 +255,11 @@ gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, d
         const bool owner = k0 == wrow;                 // this warp's four rows ARE the pivot rows
         const double* src = local ? &sm.stage[q][0][0] : &sm.rowbuf[q][0][0];
         if (owner) {
-          if (B >= kGjSlots) {   // every warp of the cluster has consumed block B - 4 out of this slot
-            int B0 = max(kGjSlots, Bs);
-            B0 += (q - B0) & (kGjSlots - 1);
-            gj::mbar_wait(&sm.empty[q], (uint32_t)((B - B0) / kGjSlots) & 1u);
-          }
+          if (B >= kGjSlots) gj::mbar_wait(&sm.empty[q], ph.empty_parity(B));   // every warp of the cluster has consumed block B - 4 out of this slot
         } else if (local) {
-          gj::mbar_wait(&sm.lfull[q], (uint32_t)(below(B, q) - below(Bs, q)) & 1u);
+          gj::mbar_wait(&sm.lfull[q], ph.lfull_parity(B));
         } else {
-          const int mine_before = B < Bs ? 0 : below(Be, q) - below(Bs, q);
-          gj::mbar_wait(&sm.rfull[q], (uint32_t)(below(B, q) - mine_before) & 1u);
+          gj::mbar_wait(&sm.rfull[q], ph.rfull_parity(B));
           if (tid == 0) {                                // this slot's next block from another CTA
             const int Bn = next_remote(B);
             if (Bn >= 0) gj::mbar_expect_tx(&sm.rfull[q], block_bytes(Bn));

@@ -230,6 +230,25 @@ def test_toy_tile_chooser_without_a_device():
     assert lib.isr_toy_tile_name(3000, 4) is None                   # ratio statistics of 3000 points do not fit
 
 
+def test_gauss_jordan_slot_protocol_on_the_cpu(tmp_path):
+    """tests/cpp/test_gj_phases.cu replays the mbarrier protocol of the cluster Gauss-Jordan inverse (four CTAs, four
+    slots: empty / lfull / rfull / done, expect_tx re-arming, credit forwarding) for every N from 1 to 240 with the
+    kernel's own phase arithmetic (csrc/gj_phases.cuh): each wait must be passed the parity of the phase that has just
+    completed for that use, and nothing may stay armed at the end."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("no nvcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "test_gj_phases")
+    subprocess.check_call([nvcc, "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a",
+                           "-I", os.path.join(root, "isrsolver_b200", "csrc"),
+                           os.path.join(root, "tests", "cpp", "test_gj_phases.cu"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "slot protocol ok" in out.stdout, out.stdout + out.stderr
+
+
 def test_philox_known_answers_on_the_cpu(tmp_path):
     """The bit source of the device toy generator (csrc/rng_device.cuh, __host__ __device__) reproduces the
     Philox4x32-10 known-answer vectors published with Random123 -- run on the host, no GPU."""
