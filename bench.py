@@ -105,15 +105,16 @@ def run_reference(args, rank, world):
     per_step = args.ref_toys
     V = O.draw_toys(vcs, err, per_step * (args.steps + args.warmup))
     for w in range(args.warmup):
-        O.chi2_test_loop(G, V[w * per_step:(w + 1) * per_step], bcs0, err)
+        loop_on_all_cores(O, G, V[w * per_step:(w + 1) * per_step], bcs0, err, cores)
     t0 = time.perf_counter()
     for k in range(args.steps):
         b = (args.warmup + k) * per_step
-        O.chi2_test_loop(G, V[b:b + per_step], bcs0, err)
+        loop_on_all_cores(O, G, V[b:b + per_step], bcs0, err, cores)
     dt = time.perf_counter() - t0
     value = per_step * args.steps / dt
     sample = (f"{per_step} toys per step of the faithful per-toy loop (COD solve + G^T W G + inverse every toy, "
-              f"src/Chi2Test.cpp:38-60; NumPy/LAPACK port, Eigen + ROOT cannot be built) at N={n}; assembly: {asm['sample']}")
+              f"src/Chi2Test.cpp:38-60; NumPy/LAPACK port, Eigen + ROOT cannot be built) at N={n}, toys dealt to {cores} threads "
+              f"with ONE BLAS thread each (fixed, so that the figure is stable from run to run); assembly: {asm['sample']}")
     line = {"impl": "reference", "metric": "toy SLE solves/s (N=200 chi2 test)", "value": value, "unit": "toys/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -122,6 +123,19 @@ def run_reference(args, rank, world):
             "e2e": {"value": value, "unit": "toys/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "assembly": asm}
     emit(line)
+
+
+def loop_on_all_cores(O, G, V, bcs0, err, cores):
+    """The reference's per-toy loop (oracle port) over a batch of toys: the toys are dealt to `cores` threads, each running
+    the loop on its slice with a single BLAS thread (LAPACK releases the GIL).  Round 1 left the BLAS thread count to
+    chance and the figure swung 7x between boxes."""
+    from concurrent.futures import ThreadPoolExecutor
+    from threadpoolctl import threadpool_limits
+    parts = [V[q::cores] for q in range(cores) if len(V[q::cores])]
+    with threadpool_limits(limits=1):
+        with ThreadPoolExecutor(max_workers=len(parts)) as ex:
+            res = list(ex.map(lambda part: O.chi2_test_loop(G, part, bcs0, err)[0], parts))
+    return res
 
 
 def reference_assembly(n, ecm, settings, cores):
@@ -154,13 +168,67 @@ def workload_config(args, world):
                         f"{args.toys} toys per GPU, full matrix assembly + factor + toy batch + histogram per step",
             "n_points": args.n, "toys_per_gpu": args.toys, "toys_total": args.toys * world,
             "l2_policy": f"inputs larger than L2 (V = {args.toys * args.n * 8 / 2**20:.0f} MiB per GPU streams through the 126 MB L2 every step)",
-            "parallelism": f"toys sharded over {world} GPU(s), matrix replicated; per step all_reduce(MIN) of (min, -max), "
-                           f"all_reduce(SUM) of the 130 histogram counters and of sum_bcs (N doubles), all device-resident"}
+            "parallelism": f"toys sharded over {world} GPU(s), matrix replicated; per step, inside the C-ABI call: ncclAllReduce(MIN) of "
+                           f"(min, -max) and ncclAllReduce(SUM) of ONE packed FP64 buffer (130 cells | sum_bcs | ratio stats | count | flag)"}
 
 
 # =====================================================================================================
 # B200 arm
 # =====================================================================================================
+class Tester:
+    """isr_chi2_test (include/isr_b200.h) with its argument block: the whole chi2 test -- assemble, factor, toys, range,
+    TH1F cells and, with a communicator, the two all-reduces -- in ONE stream-ordered C-ABI call."""
+
+    def __init__(self, L, lib, prob, n, err, bcs0, vcs, comm, nbins=128, ratio=False, sum_bcs=True):
+        self.L, self.lib, self.prob, self.n = L, lib, prob, n
+        self.err, self.bcs0, self.vcs = (np.ascontiguousarray(x, dtype=np.float64) for x in (err, bcs0, vcs))
+        self.counts = np.zeros(nbins + 2, dtype=np.int64)
+        self.lohi, self.sumb, self.rstat = np.zeros(2), np.zeros(n), np.zeros(3 * n)
+        self.total = C.c_int64()
+        a = L.Chi2TestArgs()
+        a.flags = L.ISR_TEST_ASSEMBLE | L.ISR_TEST_FACTOR | (L.ISR_TEST_RATIO if ratio else 0)
+        a.vcs_err, a.bcs0, a.vcs = L.dptr(self.err), L.dptr(self.bcs0), L.dptr(self.vcs)
+        a.nbins, a.comm = nbins, comm
+        a.chi2_lo_hi_out = L.dptr(self.lohi)
+        a.chi2_counts_out = self.counts.ctypes.data_as(C.POINTER(C.c_int64))
+        if sum_bcs:
+            a.sum_bcs_out = L.dptr(self.sumb)
+        if ratio:
+            a.ratio_stats_out = L.dptr(self.rstat)
+        a.total_toys_out = C.pointer(self.total)
+        self.a = a
+        self.ms = np.zeros(3)
+
+    def run(self, T, V_dev=None, V_host=None, chi2_host=None, seed=0, first_toy=0):
+        a = self.a
+        a.n_toys, a.V_dev, a.V, a.chi2_out = T, V_dev, V_host, chi2_host
+        a.seed, a.first_toy = seed, first_toy
+        self.L.check(self.lib.isr_chi2_test(self.prob, C.byref(a)))
+        return self.counts
+
+    def phases(self):
+        self.L.check(self.lib.isr_chi2_test_timing(self.prob, self.L.dptr(self.ms)))
+        return self.ms.copy()
+
+
+def make_comm(L, lib, ctx, rank, world, torch, dist, dev):
+    """One communicator of the C ABI per rank: rank 0's NCCL unique id travels over torch.distributed (plumbing); every
+    collective of the measured path is then issued by libisr_b200 itself, in stream."""
+    if world == 1:
+        return None
+    idbuf = torch.zeros(L.ISR_COMM_ID_BYTES, dtype=torch.uint8)
+    if rank == 0:
+        raw = (C.c_ubyte * L.ISR_COMM_ID_BYTES)()
+        L.check(lib.isr_comm_unique_id(raw))
+        idbuf = torch.tensor(list(raw), dtype=torch.uint8)
+    idbuf = idbuf.to(dev)
+    dist.broadcast(idbuf, 0)
+    raw = (C.c_ubyte * L.ISR_COMM_ID_BYTES)(*idbuf.cpu().tolist())
+    comm = C.c_void_p()
+    L.check(lib.isr_comm_init_rank(ctx, world, rank, raw, C.byref(comm)))
+    return comm
+
+
 def run_b200(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -173,7 +241,10 @@ def run_b200(args, rank, world, local_rank):
     lib = L.load()
     ctx = C.c_void_p()
     L.check(lib.isr_ctx_create(local_rank, C.byref(ctx)))
+    node = C.c_int(-1)
+    L.check(lib.isr_ctx_bind_host_thread(ctx, C.byref(node)))     # this rank's host thread next to its GPU (NUMA)
     stream = torch.cuda.ExternalStream(lib.isr_ctx_stream(ctx), device=dev)
+    comm = make_comm(L, lib, ctx, rank, world, torch, dist, dev)
 
     n, T = args.n, args.toys
     ecm = np.linspace(E_MIN, E_MAX, n)
@@ -186,113 +257,41 @@ def run_b200(args, rank, world, local_rank):
     bcs0 = bw_born(ecm)
     vcs = G @ bcs0
     err = 0.05 * vcs
-    L.check(lib.isr_factor(prob, L.dptr(err)))
 
     # toys: per-rank stream of the documented generator shape (V = vcs + err * z); device copy for `value`,
-    # pinned host copy for `e2e`
+    # page-locked host copy (isr_host_alloc: NUMA-local to this rank's GPU) for `e2e`
     gen = torch.Generator(device=dev); gen.manual_seed(20211103 + rank)
     z = torch.randn((T, n), dtype=torch.float64, device=dev, generator=gen)
     Vd = torch.from_numpy(vcs).to(dev)[None, :] + torch.from_numpy(err).to(dev)[None, :] * z
     del z
-    Vh = torch.empty((T, n), dtype=torch.float64, pin_memory=True)
-    Vh.copy_(Vd)
-    mine = torch.empty(T + 4 * n, dtype=torch.float64, device=dev)      # [chi2 | sum_bcs | ratio stats]
-    small = torch.empty(2 + n, dtype=torch.float64, device=dev)         # packed per-rank summary: min, max, sum_bcs
-    small_all = torch.empty((world, 2 + n), dtype=torch.float64, device=dev)
-    cnt_dev = torch.empty(130, dtype=torch.int64, device=dev)
-    cnt32_dev = torch.empty(130, dtype=torch.int32, device=dev)
-    range_dev = torch.empty(2, dtype=torch.float64, device=dev)
-    chi2_pin = torch.empty(T, dtype=torch.float64, pin_memory=True)     # the caller's chi2 buffer of the e2e step, pinned like V
-    chi2_host = chi2_pin.numpy()
-    sumb_host = np.zeros(n)
-    counts = np.zeros(130, dtype=np.uint32)
+    vh_ptr, c2_ptr = C.c_void_p(), C.c_void_p()
+    L.check(lib.isr_host_alloc(ctx, T * n * 8, C.byref(vh_ptr)))
+    L.check(lib.isr_host_alloc(ctx, T * 8, C.byref(c2_ptr)))
+    Vh = np.ctypeslib.as_array(C.cast(vh_ptr, C.POINTER(C.c_double)), shape=(T, n))
+    chi2_host = np.ctypeslib.as_array(C.cast(c2_ptr, C.POINTER(C.c_double)), shape=(T,))
+    torch.from_numpy(Vh).copy_(Vd)
     torch.cuda.synchronize()
+    test = Tester(L, lib, prob, n, err, bcs0, vcs, comm)
+    Vh_p, c2_p = C.cast(vh_ptr, C.POINTER(C.c_double)), C.cast(c2_ptr, C.POINTER(C.c_double))
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    asm_ev, toy_ev = [], []
-
-    def combine(lo, hi, local_counts, rehist, sum_bcs):
-        """Global TH1F over all ranks: gather (min, max | sum_bcs), bin locally against the GLOBAL range (keeps the
-        result bit-identical to one GPU), all_reduce the integer counters.  local_counts: counters already binned
-        against (lo, hi), or None; rehist(lo, hi) bins this rank's chi2 (which stays on the device); sum_bcs: this
-        rank's sum of the toy solutions (host array of the call that produced it)."""
-        if world > 1:
-            small[0], small[1] = lo, hi
-            small[2:] = torch.from_numpy(sum_bcs)       # sum of the toy solutions rides in the same gather
-            dist.all_gather_into_tensor(small_all.view(-1), small)
-            sa = small_all.cpu()
-            glo, ghi = float(sa[:, 0].min()), float(sa[:, 1].max())
-            if (glo, ghi) != (lo, hi):
-                local_counts = None
-            lo, hi = glo, ghi
-        if local_counts is None:
-            local_counts = rehist(lo, hi)
-        tot = local_counts.astype(np.int64)
-        if world > 1:
-            cnt_dev.copy_(torch.from_numpy(tot))
-            dist.all_reduce(cnt_dev)
-            tot = cnt_dev.cpu().numpy()
-        return tot
+    phase_ms = []
 
     def step_device(record):
         """One chi2 test with V resident in HBM."""
-        with torch.cuda.stream(stream):
-            a0, a1, t0, t1 = ev(), ev(), ev(), ev()
-            a0.record(stream)
-            L.check(lib.isr_assemble(prob, None, None))
-            a1.record(stream)
-            L.check(lib.isr_factor(prob, L.dptr(err)))
-            mine[T:].zero_()
-            t0.record(stream)
-            L.check(lib.isr_toy_batch_dev(prob, T, Vd.data_ptr(), L.dptr(bcs0), mine.data_ptr(),
-                                          mine[T:].data_ptr(), None, None, None))
-            t1.record(stream)
-            # chi2 histogram over ALL ranks' toys without moving them and without host round trips: {min, -max}
-            # on the device -> all_reduce(MIN) (N > 1) -> TH1F counts against the global range on the device ->
-            # all_reduce(SUM) of the 130 integer counters (N > 1) -> ONE device-to-host read of the result.
-            L.check(lib.isr_minmax_to_dev(ctx, T, mine.data_ptr(), range_dev.data_ptr()))
-            if world > 1:
-                dist.all_reduce(range_dev, op=dist.ReduceOp.MIN)
-            L.check(lib.isr_histogram_range_dev(ctx, T, mine.data_ptr(), 128, range_dev.data_ptr(), cnt32_dev.data_ptr()))
-            if world > 1:
-                dist.all_reduce(cnt32_dev)
-                dist.all_reduce(mine[T:T + n])              # sum of the toy solutions (covariance partial sums)
-            tot = cnt32_dev.cpu().numpy().astype(np.int64)   # synchronises
-            if record:
-                asm_ev.append((a0, a1)); toy_ev.append((t0, t1))
-            return tot
+        tot = test.run(T, V_dev=Vd.data_ptr())
+        if record:
+            phase_ms.append(test.phases())
+        return tot
 
     def step_e2e():
-        """The same test through the host-buffer C ABI: H2D of V and D2H of chi2 inside the call."""
-        L.check(lib.isr_assemble(prob, None, None))
-        L.check(lib.isr_factor(prob, L.dptr(err)))
-        L.check(lib.isr_toy_batch(prob, T, C.cast(Vh.data_ptr(), C.POINTER(C.c_double)), L.dptr(bcs0), L.dptr(chi2_host),
-                                  L.dptr(sumb_host), None, None, None))
-        # the chi2 values are in the caller's buffer now AND still on the device: range and TH1F from there
-        lo, hi = C.c_double(), C.c_double()
-        L.check(lib.isr_last_chi2_minmax(prob, C.byref(lo), C.byref(hi)))
-
-        def rehist(glo, ghi):
-            L.check(lib.isr_last_chi2_histogram(prob, 128, glo, ghi, L.uptr(counts)))
-            return counts
-        with torch.cuda.stream(stream):
-            return combine(lo.value, hi.value, None, rehist, sumb_host)
-
-    lohi = np.zeros(2)
+        """The same test with HOST buffers: H2D of V and D2H of chi2 inside the call."""
+        return test.run(T, V_host=Vh_p, chi2_host=c2_p)
 
     def step_campaign():
         """The same test asked for BY COUNT, as the reference's chi2Test(n, ...) is: toys drawn on the device
-        (Philox, csrc/rng.cu), chi2 histogrammed on the device; only vcs / err / bcs0 go in, 130 counters out."""
-        L.check(lib.isr_assemble(prob, None, None))
-        L.check(lib.isr_factor(prob, L.dptr(err)))
-        L.check(lib.isr_toy_campaign(prob, T, rank * T, 20211103, L.dptr(vcs), L.dptr(err), L.dptr(bcs0), None,
-                                     L.dptr(sumb_host), None, None, 128, L.dptr(lohi), L.uptr(counts)))
-
-        def rehist(glo, ghi):      # chi2 stayed on the device: re-bin it against the global range there
-            L.check(lib.isr_last_chi2_histogram(prob, 128, glo, ghi, L.uptr(counts)))
-            return counts
-        with torch.cuda.stream(stream):
-            return combine(float(lohi[0]), float(lohi[1]), counts, rehist, sumb_host)
+        (Philox, csrc/rng.cu); only vcs / err / bcs0 go in, the TH1F cells and sums come out."""
+        return test.run(T, seed=20211103, first_toy=rank * T)
 
     def barrier():
         if world > 1:
@@ -317,7 +316,7 @@ def run_b200(args, rank, world, local_rank):
         return ms
 
     for _ in range(args.warmup):
-        hist = step_device(False)
+        hist = step_device(False).copy()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start(); time.sleep(0.3)
@@ -328,17 +327,18 @@ def run_b200(args, rank, world, local_rank):
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
     ms_e2e = timed(lambda: step_e2e(), args.steps, record=None)
-    hist_c = step_campaign()
+    hist_c = step_campaign().copy()
     ms_rng = timed(lambda: step_campaign(), args.steps, record=None)
-    assert int(np.asarray(hist_c).sum()) == T * world
-
-    assert int(np.asarray(hist).sum()) == T * world, "histogram lost entries"
+    assert int(hist_c.sum()) == T * world and test.total.value == T * world
+    assert int(hist.sum()) == T * world, "histogram lost entries"
+    strong = strong_scaling(L, lib, ctx, stream, comm, torch, dist, dev, rank, world)
+    c4 = tikhonov_c4(lib, ctx, torch, comm, rank, world)
     if rank != 0:
         return
     ms_step = ms_total / args.steps
     value = T * world / (ms_step * 1e-3)
-    asm_ms = float(np.mean([a.elapsed_time(b) for a, b in asm_ev]))
-    toy_ms = float(np.mean([a.elapsed_time(b) for a, b in toy_ev]))
+    ph = np.mean(np.array(phase_ms), axis=0)
+    asm_ms, fac_ms, toy_ms = (float(x) for x in ph)
     flops = 4.0 * n * n * T          # 2N^2 for b = G^-1 v, 2N^2 for |W^(1/2) G (b - b0)|^2
     achieved = flops / (toy_ms * 1e-3) * 1e-12
     npan, nnode = C.c_int64(), C.c_int64()
@@ -348,7 +348,7 @@ def run_b200(args, rank, world, local_rank):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, world),
-        "assembly_ms": asm_ms, "toy_batch_ms": toy_ms,
+        "assembly_ms": asm_ms, "factor_ms": fac_ms, "toy_batch_ms": toy_ms,
         "assembly": {"panels": npan.value, "nodes": nnode.value, "ms": asm_ms},
         "roofline": {"bound": "tensor", "kernel": "toy_fused_kernel, tile " + (lib.isr_toy_tile_name(n, 1) or b"?").decode() +
                                " (one launch: TMA box loads -> DMMA m8n8k4 f64, pass 1 b = S v and pass 2 chi2 = |R(b-b0)|^2)",
@@ -357,23 +357,86 @@ def run_b200(args, rank, world, local_rank):
                      # in profiles/ncu_r01_toy_dense_final.txt (840.00 + 176.71 MB for 524288 toys at N=200), scaled to this T
                      "traffic": (1016.71e6 / 524288) * T if n == 200 else None,
                      "algorithmic_bytes": (8 * n + 8) * T, "flops_per_toy": 4 * n * n,
+                     "timing": "CUDA events recorded by isr_chi2_test on its own stream around the fused launch (isr_chi2_test_timing), mean over the timed steps",
                      "peak_source": "FP64 DMMA probe tools/fp64_peaks.cu -> profiles/fp64_peaks_r01.json "
                                     "(MEASURED_PEAKS.json carries no FP64 figure; bf16 peak does not apply to an FP64 kernel)"},
         "e2e": {"value": T * world / (ms_e2e / args.steps * 1e-3), "unit": "toys/s",
-                "h2d_bytes_per_step": T * n * 8, "d2h_bytes_per_step": T * 8 + n * 8 + 130 * 4, "ms_per_step": ms_e2e / args.steps},
+                "h2d_bytes_per_step": T * n * 8, "d2h_bytes_per_step": T * 8 + (130 + 4 * n + 4) * 8, "ms_per_step": ms_e2e / args.steps,
+                "h2d_gb_per_s_per_gpu": T * n * 8 / (ms_e2e / args.steps * 1e-3) * 1e-9, "numa_node_of_rank0": node.value,
+                "note": "isr_chi2_test with host buffers from isr_host_alloc (page-locked, NUMA-local to the GPU): PCIe-bound"},
         "campaign_by_count": {"value": T * world / (ms_rng / args.steps * 1e-3), "unit": "toys/s", "ms_per_step": ms_rng / args.steps,
-                              "h2d_bytes_per_step": 3 * n * 8, "d2h_bytes_per_step": n * 8 + 130 * 4 + 16,
-                              "note": "same chi2 test through isr_toy_campaign: toys drawn on the device (Philox4x32-10 + Box-Muller, "
-                                      "as the reference's chi2Test(n) draws them internally), histogram on the device; NOT the e2e "
-                                      "figure -- its toy vectors never cross PCIe"},
+                              "h2d_bytes_per_step": 3 * n * 8, "d2h_bytes_per_step": (130 + 4 * n + 4) * 8,
+                              "note": "same chi2 test with toys drawn on the device (Philox4x32-10 + Box-Muller, as the reference's "
+                                      "chi2Test(n) draws them internally); NOT the e2e figure -- its toy vectors never cross PCIe"},
         "gpu_launches": int(launches), "clocks": clocks,
+        "collectives": "none (1 GPU)" if world == 1 else "per step, inside isr_chi2_test on its stream: ncclAllReduce(MIN) of {min, -max} (2 doubles) + "
+                       "ncclAllReduce(SUM) of one packed FP64 buffer [130 cells | sum b (N) | ratio stats (3N) | toys | flag]",
+        "target_strong": strong,
     }
     line["assembly_other_configs"] = other_assemblies(lib, ctx, stream, torch)
     line["chi2_test_other_configs"] = other_chi2_tests(lib, ctx, stream, torch, dev)
-    line["tikhonov_c4"] = tikhonov_c4(lib, ctx, torch)
+    line["tikhonov_c4"] = c4
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(n, G, bcs0, vcs, err)
     emit(line)
+
+
+def _problem_for(L, lib, ctx, n, cubic):
+    ecm = np.linspace(E_MIN, E_MAX, n)
+    st = np.ascontiguousarray([[0, 0, 0], [1, 1, n - 1]] if cubic else [[0, 0, n - 1]], dtype=np.int32)
+    p = C.c_void_p()
+    L.check(lib.isr_problem_create(ctx, n, L.dptr(ecm), E_THR, len(st), L.iptr(st), None, C.byref(p)))
+    G = np.empty((n, n))
+    L.check(lib.isr_assemble(p, None, L.dptr(G)))
+    bcs0 = bw_born(ecm); vcs = G.T @ bcs0; err = 0.05 * vcs
+    return p, bcs0, vcs, err
+
+
+def strong_scaling(L, lib, ctx, stream, comm, torch, dist, dev, rank, world):
+    """STRONG scaling, every rank: the north-star target (N = 200 cubic, 2^20 toys IN TOTAL: 2^20 / world per GPU) and
+    BASELINE config C5 (N = 500 linear, 2^20 toys in total, chi2 + ratio statistics), each as one isr_chi2_test per
+    rank -- assembly + factorisation + toys + the two all-reduces + TH1F cells -- with V resident.  Time = CUDA events
+    around 5 tests after 2 warm-ups, max over ranks.  frac_of_fp64_peak = algorithmic flop of ALL toys / (world x time x
+    37.1 TFLOP/s); C5's operators are lower triangular, so its algorithmic count is 2 N^2 per toy."""
+    out = {}
+    total = 1 << 20
+    for name, n, cubic, ratio in (("target_n200_cubic_1M_toys_total", 200, True, False),
+                                  ("c5_n500_linear_1M_toys_total_ratio", 500, False, True)):
+        Tr = total // world
+        p, bcs0, vcs, err = _problem_for(L, lib, ctx, n, cubic)
+        gen = torch.Generator(device=dev); gen.manual_seed(11 + rank)
+        Vd = torch.from_numpy(vcs).to(dev)[None, :] + torch.from_numpy(err).to(dev)[None, :] * torch.randn((Tr, n), dtype=torch.float64, device=dev, generator=gen)
+        t = Tester(L, lib, p, n, err, bcs0, vcs, comm, ratio=ratio)
+        for _ in range(2):
+            t.run(Tr, V_dev=Vd.data_ptr())
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps, phases = 5, []
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+        for _ in range(reps):
+            cnt = t.run(Tr, V_dev=Vd.data_ptr())
+            phases.append(t.phases())
+        with torch.cuda.stream(stream):
+            e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        if world > 1:
+            tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        assert int(cnt.sum()) == total and t.total.value == total
+        ph = np.mean(np.array(phases), axis=0)
+        flop_per_toy = (4 if cubic else 2) * n * n
+        out[name] = {"ms_per_test": ms, "toys_total": total, "toys_per_gpu": Tr, "n_points": n, "toys_per_s": total / (ms * 1e-3),
+                     "frac_of_fp64_peak": flop_per_toy * total / world / (ms * 1e-3) * 1e-12 / FP64_PEAK_TFLOPS,
+                     "flop_per_toy": flop_per_toy, "assembly_ms": float(ph[0]), "factor_ms": float(ph[1]), "toys_ms": float(ph[2]),
+                     "toy_schedule": "dense" if cubic else "triangular"}
+        del Vd
+        lib.isr_problem_destroy(p)
+    return out
 
 
 def other_assemblies(lib, ctx, stream, torch):
@@ -412,60 +475,47 @@ def other_assemblies(lib, ctx, stream, torch):
 
 
 def other_chi2_tests(lib, ctx, stream, torch, dev):
-    """The same step (assemble + factor + toys + min/max + TH1F) at the other BASELINE.json chi2-test sizes, V resident,
-    this rank only: C2 = N 100, cubic, 100k toys (configs[1]); C5 = N 500, linear, 2^17 toys (the per-GPU share of
-    1M toys on 8 GPUs) with the ratio statistics on top -- lower-triangular operators, so the toy kernel runs its
-    triangular schedule (about 2 N^2 flop per toy executed); and the north-star target's per-GPU share: N 200, cubic,
-    2^17 toys (1M toys on 8 GPUs), with the fraction of the FP64 roofline the WHOLE test reaches (4 N^2 T flop over the
-    time of assembly + factorisation + toys + histogram).  CUDA events, mean of 5 after 2 warm-ups."""
+    """The same step (one isr_chi2_test: assemble + factor + toys + min/max + TH1F) at the other BASELINE.json chi2-test
+    sizes, V resident, this rank only: C2 = N 100, cubic, 100k toys (configs[1]); C5's per-GPU share = N 500, linear, 2^17
+    toys with the ratio statistics on top -- lower-triangular operators, so the toy kernel runs its triangular schedule
+    (about 2 N^2 flop per toy executed); and the north-star target's per-GPU share: N 200, cubic, 2^17 toys (1M toys on
+    8 GPUs), with the fraction of the FP64 roofline the WHOLE test reaches (4 N^2 T flop over the time of assembly +
+    factorisation + toys + histogram).  CUDA events, mean of 5 after 2 warm-ups."""
     from isrsolver_b200 import _lib as L
     out = {}
     for name, n, cubic, T, ratio in (("c2_n100_cubic_100k_toys", 100, True, 100000, False),
                                      ("c5_n500_linear_131072_toys_ratio", 500, False, 1 << 17, True),
                                      ("target_n200_cubic_131072_toys", 200, True, 1 << 17, False)):
-        ecm = np.linspace(E_MIN, E_MAX, n)
-        st = np.ascontiguousarray([[0, 0, 0], [1, 1, n - 1]] if cubic else [[0, 0, n - 1]], dtype=np.int32)
-        p = C.c_void_p()
-        L.check(lib.isr_problem_create(ctx, n, L.dptr(ecm), E_THR, len(st), L.iptr(st), None, C.byref(p)))
-        G = np.empty((n, n))
-        L.check(lib.isr_assemble(p, None, L.dptr(G)))
-        bcs0 = bw_born(ecm); vcs = G.T @ bcs0; err = 0.05 * vcs
+        p, bcs0, vcs, err = _problem_for(L, lib, ctx, n, cubic)
         gen = torch.Generator(device=dev); gen.manual_seed(7)
         Vd = torch.from_numpy(vcs).to(dev)[None, :] + torch.from_numpy(err).to(dev)[None, :] * torch.randn((T, n), dtype=torch.float64, device=dev, generator=gen)
-        chi2 = torch.empty(T, dtype=torch.float64, device=dev)
-        acc = torch.zeros(4 * n, dtype=torch.float64, device=dev)
-        rng2, cnt = torch.empty(2, dtype=torch.float64, device=dev), torch.empty(130, dtype=torch.int32, device=dev)
+        t = Tester(L, lib, p, n, err, bcs0, vcs, None, ratio=ratio)
         torch.cuda.synchronize()
-
-        def step():
-            L.check(lib.isr_assemble(p, None, None))
-            L.check(lib.isr_factor(p, L.dptr(err)))
-            acc.zero_()
-            L.check(lib.isr_toy_batch_dev(p, T, Vd.data_ptr(), L.dptr(bcs0), chi2.data_ptr(), acc.data_ptr(),
-                                          acc[n:].data_ptr() if ratio else None, None, None))
-            L.check(lib.isr_minmax_to_dev(ctx, T, chi2.data_ptr(), rng2.data_ptr()))
-            L.check(lib.isr_histogram_range_dev(ctx, T, chi2.data_ptr(), 128, rng2.data_ptr(), cnt.data_ptr()))
-            return cnt.cpu()
+        for _ in range(2):
+            t.run(T, V_dev=Vd.data_ptr())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        phases = []
         with torch.cuda.stream(stream):
-            for _ in range(2):
-                h = step()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            for _ in range(5):
-                h = step()
+        for _ in range(5):
+            h = t.run(T, V_dev=Vd.data_ptr())
+            phases.append(t.phases())
+        with torch.cuda.stream(stream):
             e1.record(stream)
         e1.synchronize()
         assert int(h.sum()) == T
         ms = e0.elapsed_time(e1) / 5
+        ph = np.mean(np.array(phases), axis=0)
+        flop_per_toy = (4 if cubic else 2) * n * n
         out[name] = {"ms_per_test": ms, "toys_per_s": T / (ms * 1e-3), "n_points": n, "toys": T,
-                     "toy_schedule": "dense (4 N^2 flop/toy)" if cubic else "triangular (about 2 N^2 flop/toy executed)"}
-        if cubic:
-            out[name]["whole_test_frac_of_fp64_peak"] = 4.0 * n * n * T / (ms * 1e-3) * 1e-12 / FP64_PEAK_TFLOPS
+                     "assembly_ms": float(ph[0]), "factor_ms": float(ph[1]), "toys_ms": float(ph[2]),
+                     "toy_schedule": "dense (4 N^2 flop/toy)" if cubic else "triangular (2 N^2 flop/toy algorithmic)",
+                     "whole_test_frac_of_fp64_peak": flop_per_toy * T / (ms * 1e-3) * 1e-12 / FP64_PEAK_TFLOPS}
         lib.isr_problem_destroy(p)
     return out
 
 
-def tikhonov_c4(lib, ctx, torch):
+def tikhonov_c4(lib, ctx, torch, comm=None, rank=0, world=1):
     """BASELINE config C4 on this rank: ISRSolverTikhonov, N = 200, cubic, 2 MeV energy spread, derivative regulariser;
     the generalised eigen-system once (isr_tikhonov_prepare), then the chi2 test of 10k toys for 1024 lambdas -- the
     whole grid, and the 128-lambda slice one of 8 GPUs gets -- through the host-buffer ABI with the toys in pinned
@@ -512,17 +562,18 @@ def tikhonov_c4(lib, ctx, torch):
 def cpu_baseline(n, G, bcs0, vcs, err):
     """The oracle (port of the reference's per-toy loop) on the box's host cores, bounded sample."""
     from oracle import isr_oracle as O
-    V = O.draw_toys(vcs, err, 24)
-    t0 = time.perf_counter(); O.chi2_test_loop(G, V[:8], bcs0, err); per = (time.perf_counter() - t0) / 8
-    m = int(max(16, min(400, 12.0 / per)))
+    cores = os.cpu_count() or 1
+    V = O.draw_toys(vcs, err, 4 * cores)
+    t0 = time.perf_counter(); loop_on_all_cores(O, G, V, bcs0, err, cores); per = (time.perf_counter() - t0) / len(V)
+    m = int(max(64, min(4096, 12.0 / per)))
     V = O.draw_toys(vcs, err, m)
-    t0 = time.perf_counter(); O.chi2_test_loop(G, V, bcs0, err); dt = time.perf_counter() - t0
+    t0 = time.perf_counter(); loop_on_all_cores(O, G, V, bcs0, err, cores); dt = time.perf_counter() - t0
     Vf = O.draw_toys(vcs, err, 100000)
     t1 = time.perf_counter(); O.chi2_test_fair(G, Vf, bcs0, err); dtf = time.perf_counter() - t1
     asm = reference_assembly(n, np.linspace(E_MIN, E_MAX, n), [(False, 0, 0), (True, 1, n - 1)], os.cpu_count() or 1)
     asm.pop("G")
     return {"value": m / dt, "unit": "toys/s", "cores": os.cpu_count() or 1, "kind": "port", "assembly": asm,
-            "sample": f"{m} toys of the faithful per-toy loop (COD + G^T W G + inverse per toy, src/Chi2Test.cpp:38-60) at N={n}, NumPy/LAPACK on all host cores",
+            "sample": f"{m} toys of the faithful per-toy loop (COD + G^T W G + inverse per toy, src/Chi2Test.cpp:38-60) at N={n}, NumPy/LAPACK, toys dealt to all host cores with one BLAS thread each",
             "fair_value": 100000 / dtf,
             "fair_sample": "100000 toys with the redundancy removed (factor once, two GEMMs; BASELINE.md B-fair), NumPy/OpenBLAS on all host cores"}
 
@@ -535,7 +586,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=200)
     ap.add_argument("--toys", type=int, default=1 << 20, help="toys per GPU")
-    ap.add_argument("--ref-toys", type=int, default=48, help="toys per step of the reference arm (bounded sample)")
+    ap.add_argument("--ref-toys", type=int, default=256, help="toys per step of the reference arm (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))

@@ -197,6 +197,92 @@ int isr_histogram(isr_ctx* ctx, int64_t n, const double* v, int nbins, double lo
 int isr_chi2_histogram(isr_ctx* ctx, int64_t n, const double* chi2, int nbins, double* lo_out,
                        double* hi_out, uint32_t* counts_out);
 
+/* ---- multi-GPU: communicators ------------------------------------------------------------------ */
+/* The path shards with no data-path collective (toys, lambdas, spread settings are independent); the only exchange of a
+ * chi2 test is two small all-reduces over NVLink (NCCL, loaded from libnccl.so.2 when the first communicator is made):
+ *   MIN over ranks of {min chi2, -max chi2}   -> the global TH1F range of src/Chi2Test.cpp:64-71, and
+ *   SUM over ranks of ONE packed FP64 buffer  [TH1F cells | sum of solutions (N) | ratio statistics (3N) | toy count | flag]
+ * (integer counters are exact in FP64 up to 2^53), plus the N x 1026 ratio cells when ratio_hist_out is requested.
+ * A communicator binds one context, i.e. one GPU; it can be made
+ *   - for several contexts of ONE process (isr_comm_init_all; isr_group below wraps this with one host thread per GPU), or
+ *   - one per process (isr_comm_unique_id on rank 0, distributed by the caller, then isr_comm_init_rank everywhere). */
+typedef struct isr_comm isr_comm;
+#define ISR_COMM_ID_BYTES 128
+int isr_comm_unique_id(void* id_out /* ISR_COMM_ID_BYTES */);
+int isr_comm_init_rank(isr_ctx* ctx, int nranks, int rank, const void* id, isr_comm** out);
+int isr_comm_init_all(int n, isr_ctx* const* ctxs, isr_comm** out /* n */);
+void isr_comm_destroy(isr_comm* comm);
+int isr_comm_rank(const isr_comm* comm);
+int isr_comm_size(const isr_comm* comm);
+/* In-place all-reduce of a device buffer on the context stream (asynchronous).  dtype: 0 double, 1 int32, 2 uint32,
+ * 3 int64; op: 0 sum, 1 min, 2 max. */
+int isr_comm_allreduce_dev(isr_comm* comm, void* buf_dev, int64_t count, int dtype, int op);
+/* Bind the calling host thread to the CPUs of the NUMA node the context's GPU hangs off (PCI topology from sysfs);
+ * returns the node through *node_out (-1: unknown, nothing done).  isr_host_alloc binds temporarily by itself, so that
+ * page-locked toy buffers are NUMA-local to the GPU that reads them. */
+int isr_ctx_bind_host_thread(isr_ctx* ctx, int* node_out);
+
+/* ---- a whole chi2 / ratio test in ONE call ------------------------------------------------------ */
+/* chi2TestModel / chi2Test (src/Chi2Test.cpp:113-151, 29-104) and ratioTestModel (src/RatioTest.cpp:13-62) end to end:
+ * [assemble] -> [factor] -> toys -> min / max -> TH1F cells, everything enqueued on the context stream with ONE
+ * synchronisation at the end: the certificate of the unpivoted inverse is read there (if it failed the factorisation is
+ * redone with partial pivoting and the toys are re-run; *refactored_out tells), the first toys are copied / drawn while
+ * the matrix is still being assembled, and with comm != NULL the two all-reduces above run in the same stream. */
+#define ISR_TEST_ASSEMBLE 1 /* (re)assemble the matrix first (isr_assemble with ecm_err) */
+#define ISR_TEST_FACTOR 2   /* factor for vcs_err (isr_factor); without it the currently selected solver is used */
+#define ISR_TEST_RATIO 4    /* ratio statistics (and the ratio cells if ratio_hist_out is given) */
+typedef struct {
+  int flags;
+  const double* ecm_err; /* N or NULL: beam-energy spread of the assembly */
+  const double* vcs_err; /* N: weights of the factorisation / widths of device-drawn toys */
+  const double* bcs0;    /* N: reference solution */
+  int64_t n_toys;        /* toys of THIS call (this rank's share when comm != NULL; may be 0) */
+  const double* V;       /* host toys, toy-major n_toys x N, or NULL */
+  const double* V_dev;   /* device toys, or NULL.  V == V_dev == NULL: toys first_toy .. of stream `seed` are drawn on the device */
+  const double* vcs;     /* N: centre of device-drawn toys */
+  uint64_t seed;
+  int64_t first_toy;
+  int nbins;             /* TH1F cells (128 in src/Chi2Test.cpp:72); 0: no chi2 histogram */
+  isr_comm* comm;        /* NULL: this GPU only */
+  /* outputs, host memory, any may be NULL; with comm != NULL range, cells and sums are GLOBAL (identical on every rank) */
+  double* chi2_out;          /* n_toys: chi2 of this call's toys */
+  double* chi2_lo_hi_out;    /* 2 */
+  int64_t* chi2_counts_out;  /* nbins + 2 (under / overflow cells included) */
+  double* sum_bcs_out;       /* N */
+  double* ratio_stats_out;   /* 3N: {count, sum r, sum r^2} per point */
+  uint32_t* ratio_hist_out;  /* N x 1026 */
+  int64_t* total_toys_out;   /* toys over all ranks */
+  int* refactored_out;       /* 1: certificate failed, pivoted factorisation used */
+} isr_chi2_test_args;
+int isr_chi2_test(isr_problem* p, const isr_chi2_test_args* args);
+/* CUDA-event times (ms, on the context stream) of the three phases of the last isr_chi2_test of this problem:
+ * ms_out[0] assembly, [1] factorisation (inverse + certificate + operators), [2] toy kernels. */
+int isr_chi2_test_timing(isr_problem* p, double* ms_out /* 3 */);
+
+/* ---- several GPUs of one box from ONE process ---------------------------------------------------- */
+/* What a C++ caller of chi2TestModel / ratioTestModel (include/Chi2Test.hpp:18-42, include/RatioTest.hpp:14-15) uses to
+ * spread a test over the GPUs of a box: one context, one replicated problem and one host thread per device, one
+ * communicator over all of them.  Problems are replicated (assembly + factorisation are << 1 ms and deterministic);
+ * toys are cut into contiguous slices.  Calls on one group must not run concurrently. */
+typedef struct isr_group isr_group;
+typedef struct isr_gproblem isr_gproblem;
+int isr_group_create(int ngpu, const int* devices /* NULL: 0 .. ngpu-1 */, isr_group** out);
+void isr_group_destroy(isr_group* g);
+int isr_group_size(const isr_group* g);
+isr_ctx* isr_group_ctx(isr_group* g, int rank);
+int isr_group_problem_create(isr_group* g, int n, const double* ecm, double threshold, int nranges, const int* ranges,
+                             const isr_eps_desc* eps, isr_gproblem** out);
+void isr_group_problem_destroy(isr_gproblem* gp);
+isr_problem* isr_group_problem_member(isr_gproblem* gp, int rank);
+/* Page-locked buffer for the toys of isr_group_chi2_test (toy-major n_toys x n doubles) whose slice for each GPU is
+ * first-touched by that GPU's host thread, i.e. NUMA-local to the device that will read it. */
+int isr_group_host_alloc(isr_group* g, int64_t n_toys, int n, double** out);
+void isr_group_host_free(isr_group* g, double* ptr);
+/* isr_chi2_test over all GPUs of the group: args->n_toys is the TOTAL, args->V (if given) the whole host array, args->comm
+ * and args->V_dev must be NULL; chi2_out receives all n_toys values in toy order, the other outputs are global.
+ * Histogram cells are bit-identical to the single-GPU test (every rank bins against the global range). */
+int isr_group_chi2_test(isr_gproblem* gp, const isr_chi2_test_args* args);
+
 /* ---- Tikhonov --------------------------------------------------------------------------------- */
 /* One decomposition shared by every lambda (replaces _evalProblemMatrices + two FullPivLU per lambda,
  * src/ISRSolverTikhonov.cpp:139-155): F = D^T diag(w) D (deriv_reg != 0) or diag(w);

@@ -41,6 +41,19 @@ class EpsDesc(C.Structure):
                 ("eedges", _dp), ("values", _dp)]
 
 
+class Chi2TestArgs(C.Structure):
+    """isr_chi2_test_args (include/isr_b200.h): one whole chi2 / ratio test."""
+    _fields_ = [("flags", C.c_int), ("ecm_err", _dp), ("vcs_err", _dp), ("bcs0", _dp), ("n_toys", _i64),
+                ("V", _dp), ("V_dev", _vp), ("vcs", _dp), ("seed", C.c_uint64), ("first_toy", _i64),
+                ("nbins", C.c_int), ("comm", _vp),
+                ("chi2_out", _dp), ("chi2_lo_hi_out", _dp), ("chi2_counts_out", _i64p), ("sum_bcs_out", _dp),
+                ("ratio_stats_out", _dp), ("ratio_hist_out", _up), ("total_toys_out", _i64p),
+                ("refactored_out", C.POINTER(C.c_int))]
+
+
+ISR_TEST_ASSEMBLE, ISR_TEST_FACTOR, ISR_TEST_RATIO = 1, 2, 4
+ISR_COMM_ID_BYTES = 128
+
 # name -> (restype, argtypes); every symbol include/isr_b200.h declares
 SIGNATURES = {
     "isr_ctx_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
@@ -87,6 +100,26 @@ SIGNATURES = {
     "isr_last_chi2_minmax": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "isr_histogram": (C.c_int, [_vp, _i64, _dp, C.c_int, C.c_double, C.c_double, _up]),
     "isr_chi2_histogram": (C.c_int, [_vp, _i64, _dp, C.c_int, _dp, _dp, _up]),
+    "isr_comm_unique_id": (C.c_int, [_vp]),
+    "isr_comm_init_rank": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.POINTER(_vp)]),
+    "isr_comm_init_all": (C.c_int, [C.c_int, C.POINTER(_vp), C.POINTER(_vp)]),
+    "isr_comm_destroy": (None, [_vp]),
+    "isr_comm_rank": (C.c_int, [_vp]),
+    "isr_comm_size": (C.c_int, [_vp]),
+    "isr_comm_allreduce_dev": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int]),
+    "isr_ctx_bind_host_thread": (C.c_int, [_vp, _ip]),
+    "isr_chi2_test": (C.c_int, [_vp, C.POINTER(Chi2TestArgs)]),
+    "isr_chi2_test_timing": (C.c_int, [_vp, _dp]),
+    "isr_group_create": (C.c_int, [C.c_int, _ip, C.POINTER(_vp)]),
+    "isr_group_destroy": (None, [_vp]),
+    "isr_group_size": (C.c_int, [_vp]),
+    "isr_group_ctx": (_vp, [_vp, C.c_int]),
+    "isr_group_problem_create": (C.c_int, [_vp, C.c_int, _dp, C.c_double, C.c_int, _ip, C.POINTER(EpsDesc), C.POINTER(_vp)]),
+    "isr_group_problem_destroy": (None, [_vp]),
+    "isr_group_problem_member": (_vp, [_vp, C.c_int]),
+    "isr_group_host_alloc": (C.c_int, [_vp, _i64, C.c_int, C.POINTER(_dp)]),
+    "isr_group_host_free": (None, [_vp, _dp]),
+    "isr_group_chi2_test": (C.c_int, [_vp, C.POINTER(Chi2TestArgs)]),
     "isr_tikhonov_prepare": (C.c_int, [_vp, _dp, C.c_int]),
     "isr_tikhonov_scan": (C.c_int, [_vp, _i64, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "isr_tikhonov_solve": (C.c_int, [_vp, C.c_double, _dp, _dp, _dp]),

@@ -1,0 +1,243 @@
+// A whole chi2 / ratio test in one call (isr_chi2_test): chi2TestModel / chi2Test of src/Chi2Test.cpp:29-151 and
+// ratioTestModel of src/RatioTest.cpp:13-62 end to end --
+//     [assemble G] -> [factor] -> T toys: b_k = S v_k, chi2_k = |R (b_k - b0)|^2 -> min / max -> TH1F cells
+// -- as ONE stream-ordered chain with a single host synchronisation at its end.
+//
+// Round 1 drove the same chain through separate ABI calls, each of which synchronised: the GPU idled 25-40 us per call
+// while the host woke up, and isr_factor waited for the certificate of its unpivoted inverse before the toy kernel could
+// even be enqueued (0.925 ms for the north-star target's per-GPU share against 0.65 ms of toy kernel).  Here
+//   * the certificate is DEFERRED (factor_enqueue / factor_finish, solve.cu): the toy kernels run speculatively on the
+//     unpivoted inverse; the verdict travels back with the results and, if it is negative, the factorisation is redone with
+//     partial pivoting and the toys are run again -- the call still only returns certified results;
+//   * host toys: the first two chunks are copied while the matrix is assembled and inverted; device-drawn toys: the first
+//     block is generated on a side stream meanwhile (the Gauss-Jordan cluster kernel occupies 4 of 148 SMs);
+//   * with a communicator the two all-reduces of the multi-GPU test are enqueued in the same stream: MIN of {min, -max},
+//     then SUM of one packed FP64 buffer [TH1F cells | sum b | ratio stats | toy count | certificate flag] -- the flag makes
+//     the re-run decision collective, so that no rank can leave the others waiting in an all-reduce.
+#include "comm.hpp"
+#include "problem.hpp"
+#include "solve.hpp"
+#include "toy_batch.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace isr {
+
+__global__ void empty_range_kernel(double* __restrict__ range) {
+  if (threadIdx.x < 2) range[threadIdx.x] = INFINITY;   // {min, -max} of nothing: neutral for the MIN all-reduce
+}
+
+// pack[0 .. nb) = TH1F cells, [nb .. nb + N) = sum of solutions, [nb + N .. nb + 4N) = ratio statistics,
+// pack[nb + 4N] = toys of this rank, pack[nb + 4N + 1] = 1 if this rank's factorisation failed its certificate.
+__global__ void pack_test_kernel(int nb, int n, const int* __restrict__ cells, const double* __restrict__ stat, double toys,
+                                 const double* __restrict__ cert, int assumed_lower, double tol, double* __restrict__ pack) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int len = nb + 4 * n + 2;
+  if (idx >= len) return;
+  double v;
+  if (idx < nb) v = cells ? (double)cells[idx] : 0.0;
+  else if (idx < nb + 4 * n) v = stat[idx - nb];
+  else if (idx == nb + 4 * n) v = toys;
+  else {
+    v = 0.0;
+    if (cert) {
+      const bool ok = cert[0] <= tol && (!assumed_lower || (cert[1] == 0.0 && cert[2] == 0.0));   // (a NaN residual fails)
+      v = ok ? 0.0 : 1.0;
+    }
+  }
+  pack[idx] = v;
+}
+
+static int enqueue_toys(isr_problem* p, const isr_chi2_test_args& a, const TestWants& w, bool need_chi2, bool first_attempt) {
+  const int n = p->n;
+  isr_ctx* c = p->ctx;
+  cudaStream_t st = c->stream;
+  const int64_t T = a.n_toys;
+  const bool ratio = (a.flags & ISR_TEST_RATIO) != 0;
+  ISR_CUDA(cudaMemsetAsync(p->d_stat.p, 0, sizeof(double) * 4 * n, st));
+  if (w.rhist) ISR_CUDA(cudaMemsetAsync(p->d_rhist.p, 0, sizeof(uint32_t) * (size_t)n * 1026, st));
+  if (T <= 0) return ISR_OK;
+  ToyOut o;
+  o.chi2 = need_chi2 ? p->d_chi2h.p : nullptr;
+  o.sum_bcs = (w.sum || ratio) ? p->d_stat.p : nullptr;    // (the column statistics cost the kernel 3.7 %: DESIGN K5)
+  o.ratio_stats = ratio ? p->d_stat.p + n : nullptr;
+  o.rhist = w.rhist ? p->d_rhist.p : nullptr;
+  if (a.V_dev) return toy_batch_device(p, T, a.V_dev, p->d_b0.p, o);
+  if (a.V) {
+    if (!first_attempt) ISR_TRY(host_pipe_begin(p, T, a.V));     // (the first attempt's copies were issued before the assembly)
+    return host_pipe_run(p, T, a.V, p->d_b0.p, o, a.chi2_out, nullptr);
+  }
+  // drawn on the device: blocks of 2^16 toys (105 MB at N = 200: consumed from L2 by the next launch)
+  const int64_t chunk = std::min<int64_t>(T, 1 << 16);
+  for (int64_t t0 = 0; t0 < T; t0 += chunk) {
+    const int64_t tc = std::min<int64_t>(chunk, T - t0);
+    if (t0 == 0 && first_attempt) {
+      ISR_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));      // block 0 was drawn on the side stream (see chi2_test)
+    } else {
+      ISR_TRY(draw_toys_device(c, tc, n, a.first_toy + t0, a.seed, p->d_gen.p, p->d_gen.p + n, p->d_Vh.p, st));
+    }
+    ToyOut oc = o;
+    oc.chi2 = o.chi2 ? o.chi2 + t0 : nullptr;
+    ISR_TRY(toy_batch_device(p, tc, p->d_Vh.p, p->d_b0.p, oc));
+  }
+  return ISR_OK;
+}
+
+// wants: what is COMPUTED (and reduced over the communicator) is decided by these flags, not by which output pointers a
+// rank passes -- every rank of a communicator must take the same path through the collectives.
+int chi2_test(isr_problem* p, const isr_chi2_test_args& a, TestWants w) {
+  w.rhist = w.rhist && (a.flags & ISR_TEST_RATIO) != 0;
+  const int n = p->n;
+  isr_ctx* c = p->ctx;
+  cudaStream_t st = c->stream;
+  const int64_t T = a.n_toys;
+  const bool do_asm = (a.flags & ISR_TEST_ASSEMBLE) != 0, do_fac = (a.flags & ISR_TEST_FACTOR) != 0;
+  const bool drawn = !a.V && !a.V_dev;
+  if (T < 0 || !a.bcs0) { set_error("isr_chi2_test: bad argument (n_toys < 0 or bcs0 == NULL)"); return ISR_EINVAL; }
+  if (a.V && a.V_dev) { set_error("isr_chi2_test: give V or V_dev, not both"); return ISR_EINVAL; }
+  if (do_fac && !a.vcs_err) { set_error("isr_chi2_test: ISR_TEST_FACTOR needs vcs_err"); return ISR_EINVAL; }
+  if (drawn && T > 0 && (!a.vcs || !a.vcs_err)) { set_error("isr_chi2_test: toys drawn on the device need vcs and vcs_err"); return ISR_EINVAL; }
+  if (a.nbins < 0 || a.nbins > 8190) { set_error("isr_chi2_test: nbins out of range"); return ISR_EINVAL; }
+  if (a.comm && a.comm->ctx != c) { set_error("isr_chi2_test: the communicator belongs to another context"); return ISR_EINVAL; }
+  if (!do_asm && !p->has_G) { set_error("isr_chi2_test: no matrix (set ISR_TEST_ASSEMBLE or call isr_assemble first)"); return ISR_ESTATE; }
+  if (!do_fac && !p->solver_selected) { set_error("isr_chi2_test: no solver selected (set ISR_TEST_FACTOR or select one first)"); return ISR_ESTATE; }
+  if (drawn && T > 0)
+    for (int i = 0; i < n; ++i)
+      if (!(a.vcs_err[i] >= 0.0) || !std::isfinite(a.vcs_err[i]) || !std::isfinite(a.vcs[i])) {
+        set_error("isr_chi2_test: vcs / vcs_err[%d] not finite or negative", i);
+        return ISR_EINVAL;
+      }
+  const int nb = a.nbins > 0 ? a.nbins + 2 : 0;
+  const bool need_range = a.nbins > 0 || w.range;
+  const bool need_chi2 = need_range || a.chi2_out;
+  const int plen = nb + 4 * n + 2;
+
+  // ---- workspaces
+  ISR_TRY(p->d_b0.reserve(n));
+  ISR_TRY(p->d_stat.reserve((size_t)4 * n));
+  if (need_chi2) ISR_TRY(p->d_chi2h.reserve((size_t)std::max<int64_t>(T, 1)));
+  if (w.rhist) ISR_TRY(p->d_rhist.reserve((size_t)n * 1026));
+  ISR_TRY(p->d_pack.reserve((size_t)plen + 2));          // [range (2) | pack]
+  ISR_TRY(p->d_cells.reserve((size_t)std::max(nb, 1)));
+  if ((size_t)plen + 2 > p->pin_test_n) {
+    if (p->pin_test) cudaFreeHost(p->pin_test);
+    p->pin_test = nullptr; p->pin_test_n = 0;
+    ISR_CUDA(cudaMallocHost((void**)&p->pin_test, sizeof(double) * ((size_t)plen + 2)));
+    p->pin_test_n = (size_t)plen + 2;
+  }
+  double* d_range = p->d_pack.p;
+  double* d_pack = p->d_pack.p + 2;
+
+  // ---- toys that can start before the matrix exists
+  if (a.V && T > 0) ISR_TRY(host_pipe_begin(p, T, a.V));
+  if (drawn && T > 0) {
+    const int64_t chunk = std::min<int64_t>(T, 1 << 16);
+    ISR_TRY(p->d_Vh.reserve((size_t)chunk * n));
+    ISR_TRY(p->d_gen.reserve((size_t)2 * n));
+    p->h_gen.assign(a.vcs, a.vcs + n);
+    p->h_gen.insert(p->h_gen.end(), a.vcs_err, a.vcs_err + n);
+    ISR_CUDA(cudaMemcpyAsync(p->d_gen.p, p->h_gen.data(), sizeof(double) * 2 * n, cudaMemcpyHostToDevice, st));
+    ISR_CUDA(cudaEventRecord(c->ev_fork, st));
+    ISR_CUDA(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+    ISR_TRY(draw_toys_device(c, chunk, n, a.first_toy, a.seed, p->d_gen.p, p->d_gen.p + n, p->d_Vh.p, c->aux_stream));
+    ISR_CUDA(cudaEventRecord(c->ev_join, c->aux_stream));
+  }
+  p->h_b0.assign(a.bcs0, a.bcs0 + n);
+  ISR_CUDA(cudaMemcpyAsync(p->d_b0.p, p->h_b0.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
+
+  // ---- matrix and factorisation (enqueue only)
+  int rc = ISR_OK;
+  auto drain = [&](int code) {      // a failure after the pipeline started: nothing may still read the caller's buffers
+    if (p->copy_stream) cudaStreamSynchronize(p->copy_stream);
+    cudaStreamSynchronize(c->aux_stream);
+    cudaStreamSynchronize(st);
+    p->cert_pending = false;
+    return code;
+  };
+  if (!p->ev_time[0])
+    for (int q = 0; q < 4; ++q) ISR_CUDA(cudaEventCreate(&p->ev_time[q]));
+  cudaEventRecord(p->ev_time[0], st);
+  if (do_asm && (rc = assemble(p, a.ecm_err)) != ISR_OK) return drain(rc);
+  cudaEventRecord(p->ev_time[1], st);
+  if (do_fac && (rc = factor_enqueue(p, a.vcs_err)) != ISR_OK) return drain(rc);
+
+  int refactored = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    cudaEventRecord(p->ev_time[2], st);
+    if ((rc = enqueue_toys(p, a, w, need_chi2, attempt == 0)) != ISR_OK) return drain(rc);
+    cudaEventRecord(p->ev_time[3], st);
+    // ---- range, cells, packed buffer, collectives
+    if (need_range) {
+      if (T > 0) { if ((rc = minmax_to_device(c, T, p->d_chi2h.p, d_range)) != ISR_OK) return drain(rc); }
+      else { empty_range_kernel<<<1, 32, 0, st>>>(d_range); ISR_COUNT_LAUNCH(); }
+      if (a.comm && (rc = comm_allreduce(a.comm, d_range, 2, 0, 1)) != ISR_OK) return drain(rc);
+      if (a.nbins > 0 && (rc = histogram_range_device(c, T, p->d_chi2h.p, a.nbins, d_range, p->d_cells.p)) != ISR_OK) return drain(rc);
+    }
+    const bool cert_here = do_fac && attempt == 0;
+    pack_test_kernel<<<(plen + 255) / 256, 256, 0, st>>>(nb, n, a.nbins > 0 ? p->d_cells.p : nullptr, p->d_stat.p, (double)T,
+                                                        cert_here ? p->cert_dev : nullptr, p->tri_sle[0] || p->tri_sle[1],
+                                                        1e-12 * n, d_pack); ISR_COUNT_LAUNCH();
+    if (a.comm) {
+      if ((rc = comm_allreduce(a.comm, d_pack, plen, 0, 0)) != ISR_OK) return drain(rc);
+      if (w.rhist && (rc = comm_allreduce(a.comm, p->d_rhist.p, (int64_t)n * 1026, 2, 0)) != ISR_OK) return drain(rc);
+    }
+    if (cudaMemcpyAsync(p->pin_test, p->d_pack.p, sizeof(double) * ((size_t)plen + 2), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) {
+      set_error("isr_chi2_test: CUDA error '%s'", cudaGetErrorString(cudaGetLastError()));
+      return drain(ISR_ECUDA);
+    }
+    bool redone = false;
+    if (do_fac && (rc = factor_finish(p, &redone)) != ISR_OK) return drain(rc);
+    const bool any_failed = p->pin_test[2 + nb + 4 * n + 1] > 0.0;
+    if (!redone && !any_failed) break;
+    if (attempt == 1) { set_error("isr_chi2_test: factorisation failed its certificate twice"); return drain(ISR_ENUMERIC); }
+    refactored = 1;      // this rank, or another one of the communicator, fell back to the pivoted inverse: run the toys again
+  }
+  p->last_chi2_count = need_chi2 ? T : 0;
+
+  // ---- results
+  const double* pk = p->pin_test + 2;
+  if (a.chi2_lo_hi_out) { a.chi2_lo_hi_out[0] = p->pin_test[0]; a.chi2_lo_hi_out[1] = -p->pin_test[1]; }
+  if (a.chi2_counts_out) for (int q = 0; q < nb; ++q) a.chi2_counts_out[q] = (int64_t)pk[q];
+  if (a.sum_bcs_out) std::memcpy(a.sum_bcs_out, pk + nb, sizeof(double) * n);
+  if (a.ratio_stats_out) std::memcpy(a.ratio_stats_out, pk + nb + n, sizeof(double) * 3 * n);
+  if (a.total_toys_out) *a.total_toys_out = (int64_t)pk[nb + 4 * n];
+  if (a.refactored_out) *a.refactored_out = refactored;
+  bool more = false;
+  if (a.chi2_out && T > 0 && !a.V) {      // (host toys: copied chunk by chunk inside the pipeline)
+    ISR_CUDA(cudaMemcpyAsync(a.chi2_out, p->d_chi2h.p, sizeof(double) * T, cudaMemcpyDeviceToHost, st));
+    more = true;
+  }
+  if (a.ratio_hist_out && w.rhist) {
+    ISR_CUDA(cudaMemcpyAsync(a.ratio_hist_out, p->d_rhist.p, sizeof(uint32_t) * (size_t)n * 1026, cudaMemcpyDeviceToHost, st));
+    more = true;
+  }
+  if (more) ISR_CUDA(cudaStreamSynchronize(st));
+  return ISR_OK;
+}
+
+}  // namespace isr
+
+extern "C" int isr_chi2_test_timing(isr_problem* p, double* ms_out) {
+  if (!p || !ms_out) { isr::set_error("isr_chi2_test_timing: NULL argument"); return ISR_EINVAL; }
+  if (!p->ev_time[0]) { isr::set_error("isr_chi2_test_timing: no isr_chi2_test has run on this problem"); return ISR_ESTATE; }
+  ISR_CUDA(cudaSetDevice(p->ctx->device));
+  for (int q = 0; q < 3; ++q) {
+    float ms = 0.f;
+    ISR_CUDA(cudaEventElapsedTime(&ms, p->ev_time[q], p->ev_time[q + 1]));
+    ms_out[q] = ms;
+  }
+  return ISR_OK;
+}
+
+extern "C" int isr_chi2_test(isr_problem* p, const isr_chi2_test_args* args) {
+  if (!p || !args) { isr::set_error("isr_chi2_test: NULL argument"); return ISR_EINVAL; }
+  ISR_CUDA(cudaSetDevice(p->ctx->device));
+  isr::TestWants w;
+  w.sum = args->sum_bcs_out != nullptr;
+  w.rhist = args->ratio_hist_out != nullptr;
+  w.range = args->chi2_lo_hi_out != nullptr;
+  return isr::chi2_test(p, *args, w);
+}

@@ -107,14 +107,24 @@ struct EpsDev {
 
 }  // namespace isr
 
+// Small page-locked staging area of a context: certificates, ranges, counters and other O(N) read-backs go through it,
+// so that a cudaMemcpyAsync(DeviceToHost) really is asynchronous (into pageable memory it returns only after the copy).
+constexpr size_t kPinDoubles = 1 << 16;   // 512 KB
+// slots (doubles) of a problem's page-locked certificate block: {max|AX-I|, X upper != 0, A upper != 0}, cuSOLVER info (2 ints)
+constexpr int kPinCert = 0, kPinInfo = 4;
+
 struct isr_ctx {
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t aux_stream = nullptr;     // side work that may overlap the main stream (first toy block, eigen-system)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  double* pin = nullptr;                 // kPinDoubles page-locked doubles (layout owned by the call that uses it)
   cusolverDnHandle_t solver = nullptr;
   cublasHandle_t blas = nullptr;
   // grow-only scratch for the reductions (min/max partials, histogram counters, staged chi2)
   isr::DevBuf<double> scratch_d;
   isr::DevBuf<uint32_t> scratch_u;
   isr::DevBuf<double> scratch_v;
+  isr::DevBuf<double> scratch_t;   // N x N scratch of the blocked triangular inverse
 };

@@ -344,14 +344,18 @@ gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, d
 // matrices of this problem are lower-triangular-dominated and need no row exchanges, but nothing guarantees that for
 // an injected or ill-conditioned matrix, so the fast path is CERTIFIED a posteriori: X is accepted only if
 // max |A X - I| <= 1e-12 n (then |X - A^-1| <= |A^-1| |A X - I|, i.e. 2e-10 relative at N = 200, typically 1e-13);
-// otherwise -- zero pivot, growth, NaN -- the partially pivoted factorisation is used, exactly as before.
-// lower_hint: the caller knows A to be lower triangular (used for N > 240 only).
-// enqueue_dependents: launches of the caller that only read Ainv; they are enqueued BEFORE the host waits for the
-// certificate, so that the GPU works on while the host wakes up (and once more if the pivoted fall-back replaces Ainv).
-// tri[0] / tri[1] = 1 iff Ainv / A came out exactly lower triangular (linear interpolation without energy spread: the
-// toy kernel then skips the structural zeros); read back with the certificate, no extra synchronisation.
-int lu_inverse(isr_ctx* c, int n, const double* A, double* lu, double* prod, double* Ainv, DevBuf<double>& work,
-               DevBuf<int>& ipiv, DevBuf<int>& info, bool lower_hint, int* tri, const std::function<int()>& enqueue_dependents) {
+// otherwise -- zero pivot, growth, NaN -- the partially pivoted factorisation is used.
+//
+// The certificate is DEFERRED: inverse_enqueue only enqueues (fast inverse, residual product, reduction, and the copy of
+// the three certificate scalars into the context's page-locked staging area), so that the caller can enqueue everything
+// that depends on the inverse -- the operator set-up, the toy kernels, the histogram -- behind it without a host round
+// trip; inverse_certified reads the verdict after the caller's one synchronisation, and inverse_pivoted is the
+// synchronous fall-back (after which the caller re-runs its dependents).
+// lower_hint: the caller knows A to be lower triangular (selects the triangular solve for N > kGjMaxRows).
+// cert_host: 8 page-locked doubles owned by the caller (kPinCert / kPinInfo slots); *cert_dev_out: the device copy of the
+// three scalars, for kernels that fold the verdict into a collective.
+int inverse_enqueue(isr_ctx* c, int n, const double* A, double* lu, double* prod, double* Ainv, DevBuf<double>& work,
+                    DevBuf<int>& ipiv, DevBuf<int>& info, bool lower_hint, double* cert_host, double** cert_dev_out) {
   int lwork = 0;
   const size_t bytes = sizeof(double) * (size_t)n * n;
   ISR_CUSOLVER(cusolverDnDgetrf_bufferSize(c->solver, n, n, lu, n, &lwork));
@@ -359,19 +363,18 @@ int lu_inverse(isr_ctx* c, int n, const double* A, double* lu, double* prod, dou
   ISR_TRY(ipiv.reserve(n));
   ISR_TRY(info.reserve(2));
   double* resid_dev = work.p + lwork;
-  // ---- fast path: no pivoting, certified by the residual
-  int h_info[2] = {0, 0};
+  *cert_dev_out = resid_dev;
+  int* h_info = reinterpret_cast<int*>(cert_host + kPinInfo);
+  h_info[0] = h_info[1] = 0;
   if (n <= kGjMaxRows) {
     const int warps = (n + 4 * kGjCtas - 1) / (4 * kGjCtas);   // four rows per warp, whole warps per CTA
     ISR_CUDA(cudaFuncSetAttribute(gj_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GjSmem)));   // per device
     gj_inverse_kernel<<<kGjCtas, 32 * warps + 32, sizeof(GjSmem), c->stream>>>(n, A, Ainv, resid_dev); ISR_COUNT_LAUNCH();
   } else if (lower_hint) {
-    // the caller knows A to be lower triangular (linear interpolation without spread): one triangular solve L X = I
-    // instead of getrf + two of them; a wrong hint fails the certificate below like any other bad inverse
+    // the caller knows A to be lower triangular (linear interpolation without spread): blocked triangular inverse
+    // (tri_inverse.cu); a wrong hint fails the certificate below like any other bad inverse
     ISR_CUDA(cudaMemsetAsync(resid_dev, 0, 3 * sizeof(double), c->stream));
-    set_identity_kernel<<<(n * n + 255) / 256, 256, 0, c->stream>>>(n, Ainv); ISR_COUNT_LAUNCH();
-    const double one = 1.0;
-    ISR_CUBLAS(cublasDtrsm(c->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, n, n, &one, A, n, Ainv, n));
+    ISR_TRY(tri_inverse_lower(c, n, A, Ainv));
   } else {
     ISR_CUDA(cudaMemsetAsync(resid_dev, 0, 3 * sizeof(double), c->stream));
     ISR_CUDA(cudaMemcpyAsync(lu, A, bytes, cudaMemcpyDeviceToDevice, c->stream));
@@ -380,16 +383,28 @@ int lu_inverse(isr_ctx* c, int n, const double* A, double* lu, double* prod, dou
     ISR_CUSOLVER(cusolverDnDgetrs(c->solver, CUBLAS_OP_N, n, n, lu, n, nullptr, Ainv, n, info.p + 1));
     ISR_CUDA(cudaMemcpyAsync(h_info, info.p, sizeof(int) * 2, cudaMemcpyDeviceToHost, c->stream));
   }
-  ISR_TRY(gemm(c, false, false, n, A, Ainv, prod));
+  ISR_TRY(small_gemm(c, n, lower_hint, A, Ainv, prod));   // (a wrong hint is caught by the triangularity scalars)
   inverse_residual_kernel<<<n, 256, 0, c->stream>>>(n, prod, Ainv, A, resid_dev); ISR_COUNT_LAUNCH();
-  double resid[3] = {INFINITY, INFINITY, INFINITY};
-  ISR_CUDA(cudaMemcpyAsync(resid, resid_dev, sizeof(resid), cudaMemcpyDeviceToHost, c->stream));
-  ISR_TRY(enqueue_dependents());
-  ISR_CUDA(cudaStreamSynchronize(c->stream));
+  ISR_CUDA(cudaMemcpyAsync(cert_host + kPinCert, resid_dev, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  ISR_CUDA(cudaGetLastError());
+  return ISR_OK;
+}
+// After the stream has been synchronised: did the fast inverse pass?  tri[0] / tri[1] = 1 iff Ainv / A came out exactly
+// lower triangular (linear interpolation without energy spread: the toy kernel then skips the structural zeros).
+bool inverse_certified(const double* cert_host, int n, int* tri) {
+  const double* resid = cert_host + kPinCert;
+  const int* h_info = reinterpret_cast<const int*>(cert_host + kPinInfo);
   tri[0] = resid[1] == 0.0;
   tri[1] = resid[2] == 0.0;
-  if (h_info[0] == 0 && h_info[1] == 0 && resid[0] <= 1e-12 * n) return ISR_OK;
-  // ---- certified path failed: LU with partial pivoting
+  return h_info[0] == 0 && h_info[1] == 0 && resid[0] <= 1e-12 * n;
+}
+// LU with partial pivoting (synchronous): the fall-back when the certificate fails.
+int inverse_pivoted(isr_ctx* c, int n, const double* A, double* lu, double* Ainv, DevBuf<double>& work, DevBuf<int>& ipiv,
+                    DevBuf<int>& info, double* cert_host, int* tri) {
+  const size_t bytes = sizeof(double) * (size_t)n * n;
+  int lwork = 0;
+  ISR_CUSOLVER(cusolverDnDgetrf_bufferSize(c->solver, n, n, lu, n, &lwork));
+  double* resid_dev = work.p + lwork;
   ISR_CUDA(cudaMemcpyAsync(lu, A, bytes, cudaMemcpyDeviceToDevice, c->stream));
   ISR_CUSOLVER(cusolverDnDgetrf(c->solver, n, n, lu, n, work.p, ipiv.p, info.p));
   ISR_TRY(check_info(c, info.p, "LU factorisation (getrf)"));
@@ -397,11 +412,12 @@ int lu_inverse(isr_ctx* c, int n, const double* A, double* lu, double* prod, dou
   ISR_CUSOLVER(cusolverDnDgetrs(c->solver, CUBLAS_OP_N, n, n, lu, n, ipiv.p, Ainv, n, info.p));
   ISR_CUDA(cudaMemsetAsync(resid_dev, 0, 3 * sizeof(double), c->stream));
   inverse_residual_kernel<<<n, 256, 0, c->stream>>>(n, nullptr, Ainv, A, resid_dev); ISR_COUNT_LAUNCH();
-  ISR_CUDA(cudaMemcpyAsync(resid, resid_dev, sizeof(resid), cudaMemcpyDeviceToHost, c->stream));
+  ISR_CUDA(cudaMemcpyAsync(cert_host + kPinCert, resid_dev, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   ISR_TRY(check_info(c, info.p, "LU solve (getrs)"));    // synchronises
+  const double* resid = cert_host + kPinCert;
   tri[0] = resid[1] == 0.0;     // row exchanges usually leave rounding residue above the diagonal
   tri[1] = resid[2] == 0.0;
-  return enqueue_dependents();
+  return ISR_OK;
 }
 
 // B(i, k') = A[i][n-1-k']: column-major copy of a row-major operator with its columns reversed

@@ -58,15 +58,28 @@ struct isr_problem {
   bool factored = false;
   bool cov_ready = false;      // d_Cov / d_InvCov match the current factorisation
   bool solver_selected = false;
+  int selected_kind = 0;       // whose operators d_Sop / d_Rop hold: 0 none, 1 SLE (isr_factor), 2 Tikhonov, 3 TSVD
+  bool cert_pending = false;   // factor_enqueue ran; factor_finish has not read the inverse's certificate yet
+  double* cert_dev = nullptr;  // device copy of the certificate scalars (3 doubles, owned by d_work)
+  double* pin_cert = nullptr;  // page-locked: certificate scalars + cuSOLVER info of the pending factorisation (8 doubles)
   int toy_variant = 0;
   int64_t last_chi2_count = 0;   // chi2 values the last host-API batch / campaign left in d_chi2h
 
   // ---- toy batch workspaces ------------------------------------------------------------------
   isr::DevBuf<double> d_V, d_chi2, d_acc, d_b0, d_B;
+  isr::DevBuf<double> d_vin;     // right-hand side of the single solves (isr_solve / isr_tikhonov_solve / isr_tsvd_solve): NOT d_b0, whose
+                                 // content isr_toy_batch_dev caches against h_b0
   isr::DevBuf<uint32_t> d_rhist;
+  // isr_chi2_test: [range (2) | packed result] on the device, TH1F cells, and the page-locked copy of the former
+  isr::DevBuf<double> d_pack;
+  isr::DevBuf<int> d_cells;
+  double* pin_test = nullptr;
+  cudaEvent_t ev_time[4] = {nullptr, nullptr, nullptr, nullptr};   // start | assembled | factor enqueued | toys enqueued
+  size_t pin_test_n = 0;
   // host-buffer pipeline (isr_toy_batch): two V slots, chi2 / statistics staging, copy stream
   isr::DevBuf<double> d_Vh, d_chi2h, d_stat, d_Bh;
   cudaStream_t copy_stream = nullptr;
+  int64_t pipe_slot = 0;       // toys per slot of the pipeline in flight (host_pipe_begin)
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   ~isr_problem() {
     for (int q = 0; q < 2; ++q) {
@@ -74,6 +87,9 @@ struct isr_problem {
       if (ev_done[q]) cudaEventDestroy(ev_done[q]);
     }
     if (copy_stream) cudaStreamDestroy(copy_stream);
+    for (int q = 0; q < 4; ++q) if (ev_time[q]) cudaEventDestroy(ev_time[q]);
+    if (pin_cert) cudaFreeHost(pin_cert);
+    if (pin_test) cudaFreeHost(pin_test);
   }
 
   // ---- Tikhonov ------------------------------------------------------------------------------

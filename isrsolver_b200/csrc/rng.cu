@@ -41,10 +41,10 @@ __global__ void __launch_bounds__(256) draw_toys_kernel(int64_t T, int n, int64_
 }
 
 int draw_toys_device(isr_ctx* c, int64_t T, int n, int64_t first_toy, uint64_t seed, const double* vcs_dev,
-                     const double* err_dev, double* V_dev) {
+                     const double* err_dev, double* V_dev, cudaStream_t st) {
   if (T <= 0) return ISR_OK;
   const int64_t work = T * ((n + 1) >> 1);
-  draw_toys_kernel<<<(unsigned)((work + 255) / 256), 256, 0, c->stream>>>(T, n, first_toy, seed, vcs_dev, err_dev, V_dev); ISR_COUNT_LAUNCH();
+  draw_toys_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st ? st : c->stream>>>(T, n, first_toy, seed, vcs_dev, err_dev, V_dev); ISR_COUNT_LAUNCH();
   ISR_CUDA(cudaGetLastError());
   return ISR_OK;
 }

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 
 namespace isr {
 
@@ -15,7 +16,12 @@ namespace isr {
 //   Ginv = G^-1                      (b = Ginv v  ==  COD(G).solve(v) for a full-rank G)
 //   R    = W^(1/2) G                 (Cov^-1 = G^T W G = R^T R)
 //   Cov  = (Ginv W^(-1/2)) (Ginv W^(-1/2))^T  ==  (G^T W G)^-1, symmetric by construction
-int factor(isr_problem* p, const double* vcs_err) {
+// factor_enqueue only ENQUEUES (inverse, certificate, operators) on the context stream; the certificate of the
+// unpivoted inverse is read by factor_finish after the caller's next synchronisation, so that everything downstream --
+// the toy kernels, the histogram, the collectives -- can be enqueued behind the factorisation without the GPU idling
+// through a host wake-up (25-40 us per chi2 test in round 1).  Until then the toy schedule is chosen from what the
+// host knows: a matrix known to be lower triangular (G_lower) gives exactly lower-triangular G^-1 and W^(1/2) G.
+int factor_enqueue(isr_problem* p, const double* vcs_err) {
   if (!p->has_G) { set_error("isr_factor: no matrix (call isr_assemble or isr_set_matrix first)"); return ISR_ESTATE; }
   const int n = p->n, ld = (n + 1) & ~1;
   for (int i = 0; i < n; ++i)
@@ -34,18 +40,59 @@ int factor(isr_problem* p, const double* vcs_err) {
   ISR_TRY(p->d_InvCov.reserve(nn));
   ISR_TRY(p->d_Sop.reserve((size_t)n * ld));
   ISR_TRY(p->d_Rop.reserve((size_t)n * ld));
+  // the Tikhonov eigen-system (d_mu, d_P, d_U) was built for the previous weights
+  if (p->vcs_err.size() != (size_t)n || std::memcmp(p->vcs_err.data(), vcs_err, sizeof(double) * n) != 0) p->tik_ready = false;
   p->vcs_err.assign(vcs_err, vcs_err + n);
-  ISR_CUDA(cudaMemcpyAsync(p->d_werr.p, vcs_err, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  ISR_CUDA(cudaMemcpyAsync(p->d_werr.p, p->vcs_err.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
   ISR_TRY(p->d_tmp2.reserve(nn));
-  // the operator set-up only reads G^-1: it is enqueued before the host waits for the inverse's certificate
-  ISR_TRY(lu_inverse(c, n, p->d_G.p, p->d_tmp.p, p->d_tmp2.p, p->d_Ginv.p, p->d_work, p->d_ipiv, p->d_info, p->G_lower, p->tri_sle,
-                     [p]() { return launch_sle_operators(p); }));
+  if (!p->pin_cert) ISR_CUDA(cudaMallocHost((void**)&p->pin_cert, sizeof(double) * 8));
+  ISR_TRY(inverse_enqueue(c, n, p->d_G.p, p->d_tmp.p, p->d_tmp2.p, p->d_Ginv.p, p->d_work, p->d_ipiv, p->d_info, p->G_lower,
+                          p->pin_cert, &p->cert_dev));
+  ISR_TRY(launch_sle_operators(p));
   p->factored = true;
+  p->cert_pending = true;
   p->cov_ready = false;      // Cov / G^T W G are formed on first use (ensure_cov): the toy path never reads them
+  p->tri_sle[0] = p->tri_sle[1] = p->G_lower ? 1 : 0;
   p->tri_sel[0] = p->tri_sle[0];
   p->tri_sel[1] = p->tri_sle[1];
   p->solver_selected = true;
+  p->selected_kind = 1;
   return ISR_OK;
+}
+
+// To be called after the context stream has been synchronised.  *redone = true: the unpivoted inverse failed its
+// certificate (or the triangularity the schedule assumed did not hold) and the factorisation was redone with partial
+// pivoting -- results computed from the speculative operators must be recomputed.
+int factor_finish(isr_problem* p, bool* redone) {
+  if (redone) *redone = false;
+  if (!p->cert_pending) return ISR_OK;
+  p->cert_pending = false;
+  isr_ctx* c = p->ctx;
+  int tri[2];
+  const bool ok = inverse_certified(p->pin_cert, p->n, tri);
+  const bool assumed = p->tri_sle[0] || p->tri_sle[1];
+  if (ok && (!assumed || (tri[0] && tri[1]))) {
+    // (exactly triangular factors the host did not know about -- an injected matrix -- switch the schedule from now on)
+    p->tri_sle[0] = tri[0]; p->tri_sle[1] = tri[1];
+    if (p->selected_kind == 1) { p->tri_sel[0] = tri[0]; p->tri_sel[1] = tri[1]; }
+    return ISR_OK;
+  }
+  p->factored = false;
+  ISR_TRY(inverse_pivoted(c, p->n, p->d_G.p, p->d_tmp.p, p->d_Ginv.p, p->d_work, p->d_ipiv, p->d_info, p->pin_cert, tri));
+  p->tri_sle[0] = tri[0]; p->tri_sle[1] = tri[1];
+  p->tri_sel[0] = tri[0]; p->tri_sel[1] = tri[1];
+  ISR_TRY(launch_sle_operators(p));
+  ISR_CUDA(cudaStreamSynchronize(c->stream));
+  p->factored = true;
+  if (redone) *redone = true;
+  return ISR_OK;
+}
+
+// Synchronous form (isr_factor): enqueue, wait, certify.
+int factor(isr_problem* p, const double* vcs_err) {
+  ISR_TRY(factor_enqueue(p, vcs_err));
+  ISR_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  return factor_finish(p, nullptr);
 }
 
 // Cov = (Ginv W^(-1/2)) (Ginv W^(-1/2))^T and InvCov = R^T R, once per factorisation and only when asked for.
@@ -96,6 +143,7 @@ int select_sle(isr_problem* p) {
   p->tri_sel[0] = p->tri_sle[0];
   p->tri_sel[1] = p->tri_sle[1];
   p->solver_selected = true;
+  p->selected_kind = 1;
   return ISR_OK;
 }
 
@@ -217,6 +265,70 @@ int histogram_device(isr_ctx* c, int64_t n, const double* v_dev, int nbins, doub
 // --------------------------------------------------------------------------------------------------
 // Host-buffer toy batch: H2D copies of V chunks overlap the kernels of the previous chunk.
 // --------------------------------------------------------------------------------------------------
+// Two device slots of up to 2^17 toys; the copy of chunk k + 2 is issued as soon as the kernels of chunk k have been
+// enqueued.  host_pipe_begin issues the first two copies -- behind everything the context stream holds at that moment
+// (an earlier asynchronous campaign may still read d_Vh), but BEFORE the caller enqueues more work there, so that they
+// run under a matrix assembly / factorisation enqueued next; host_pipe_run enqueues the rest.
+static int host_pipe_copy(isr_problem* p, int64_t T, const double* V, int k) {
+  const int n = p->n, q = k & 1;
+  const int64_t slot = p->pipe_slot, t0 = (int64_t)k * slot, tc = std::min<int64_t>(slot, T - t0);
+  if (k >= 2) ISR_CUDA(cudaStreamWaitEvent(p->copy_stream, p->ev_done[q], 0));   // slot free again
+  ISR_CUDA(cudaMemcpyAsync(p->d_Vh.p + (size_t)q * slot * n, V + t0 * n, sizeof(double) * tc * n, cudaMemcpyHostToDevice, p->copy_stream));
+  ISR_CUDA(cudaEventRecord(p->ev_copied[q], p->copy_stream));
+  return ISR_OK;
+}
+int host_pipe_begin(isr_problem* p, int64_t T, const double* V) {
+  const int n = p->n;
+  isr_ctx* c = p->ctx;
+  if (T <= 0) return ISR_OK;
+  p->pipe_slot = std::min<int64_t>(T, 1 << 17);
+  ISR_TRY(p->d_Vh.reserve((size_t)2 * p->pipe_slot * n));
+  if (!p->copy_stream) {
+    ISR_CUDA(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+    for (int q = 0; q < 2; ++q) {
+      ISR_CUDA(cudaEventCreateWithFlags(&p->ev_copied[q], cudaEventDisableTiming));
+      ISR_CUDA(cudaEventCreateWithFlags(&p->ev_done[q], cudaEventDisableTiming));
+    }
+  }
+  ISR_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+  ISR_CUDA(cudaStreamWaitEvent(p->copy_stream, c->ev_fork, 0));
+  const int64_t nchunks = (T + p->pipe_slot - 1) / p->pipe_slot;
+  for (int k = 0; k < 2 && k < nchunks; ++k) ISR_TRY(host_pipe_copy(p, T, V, k));
+  return ISR_OK;
+}
+// chi2_dev: T values on the device (or nullptr); chi2_out / bcs_out: host destinations copied chunk by chunk (or nullptr).
+// On failure the copy stream is drained before returning: it may still be reading the caller's V.
+int host_pipe_run(isr_problem* p, int64_t T, const double* V, const double* b0_dev, const ToyOut& base, double* chi2_out,
+                  double* bcs_out) {
+  const int n = p->n;
+  cudaStream_t st = p->ctx->stream;
+  if (T <= 0) return ISR_OK;
+  const int64_t slot = p->pipe_slot, nchunks = (T + slot - 1) / slot;
+  int rc = ISR_OK;
+  auto body = [&]() -> int {
+    if (bcs_out) ISR_TRY(p->d_Bh.reserve((size_t)2 * slot * n));
+    for (int64_t k = 0; k < nchunks; ++k) {
+      const int q = (int)(k & 1);
+      const int64_t t0 = k * slot, tc = std::min<int64_t>(slot, T - t0);
+      ISR_CUDA(cudaStreamWaitEvent(st, p->ev_copied[q], 0));
+      ToyOut o = base;
+      o.chi2 = base.chi2 ? base.chi2 + t0 : nullptr;
+      o.bcs = bcs_out ? p->d_Bh.p + (size_t)q * slot * n : nullptr;
+      ISR_TRY(toy_batch_device(p, tc, p->d_Vh.p + (size_t)q * slot * n, b0_dev, o));
+      if (bcs_out) ISR_CUDA(cudaMemcpyAsync(bcs_out + t0 * n, o.bcs, sizeof(double) * tc * n, cudaMemcpyDeviceToHost, st));
+      ISR_CUDA(cudaEventRecord(p->ev_done[q], st));
+      if (k + 2 < nchunks) ISR_TRY(host_pipe_copy(p, T, V, (int)(k + 2)));
+      // this chunk's chi2 goes back while the next chunk's toys are still coming in (the two directions have their own
+      // copy engines); the values also stay on the device for isr_last_chi2_minmax / isr_last_chi2_histogram
+      if (chi2_out && o.chi2) ISR_CUDA(cudaMemcpyAsync(chi2_out + t0, o.chi2, sizeof(double) * tc, cudaMemcpyDeviceToHost, st));
+    }
+    return ISR_OK;
+  };
+  rc = body();
+  if (rc != ISR_OK) cudaStreamSynchronize(p->copy_stream);
+  return rc;
+}
+
 int toy_batch_host(isr_problem* p, int64_t T, const double* V, const double* bcs0, double* chi2_out,
                    double* sum_bcs_out, double* ratio_stats_out, uint32_t* ratio_hist_out, double* bcs_out) {
   const int n = p->n;
@@ -227,49 +339,23 @@ int toy_batch_host(isr_problem* p, int64_t T, const double* V, const double* bcs
     return ISR_ESTATE;
   }
   if (T <= 0) return ISR_OK;
-  // two pipeline slots of up to 2^17 toys each
-  const int64_t slot = std::min<int64_t>(T, 1 << 17);
-  ISR_TRY(p->d_Vh.reserve((size_t)2 * slot * n));
   ISR_TRY(p->d_chi2h.reserve((size_t)T));
   ISR_TRY(p->d_b0.reserve(n));
   ISR_TRY(p->d_stat.reserve((size_t)4 * n));
-  ISR_CUDA(cudaMemcpyAsync(p->d_b0.p, bcs0, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  ISR_TRY(host_pipe_begin(p, T, V));
+  p->h_b0.assign(bcs0, bcs0 + n);      // d_b0 mirrors h_b0 (isr_toy_batch_dev skips its upload on a match)
+  ISR_CUDA(cudaMemcpyAsync(p->d_b0.p, p->h_b0.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
   ISR_CUDA(cudaMemsetAsync(p->d_stat.p, 0, sizeof(double) * 4 * n, st));
   if (ratio_hist_out) {
     ISR_TRY(p->d_rhist.reserve((size_t)n * 1026));
     ISR_CUDA(cudaMemsetAsync(p->d_rhist.p, 0, sizeof(uint32_t) * (size_t)n * 1026, st));
   }
-  if (bcs_out) ISR_TRY(p->d_Bh.reserve((size_t)2 * slot * n));
-  if (!p->copy_stream) {
-    ISR_CUDA(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
-    for (int q = 0; q < 2; ++q) {
-      ISR_CUDA(cudaEventCreateWithFlags(&p->ev_copied[q], cudaEventDisableTiming));
-      ISR_CUDA(cudaEventCreateWithFlags(&p->ev_done[q], cudaEventDisableTiming));
-    }
-  }
-  int k = 0;
-  for (int64_t t0 = 0; t0 < T; t0 += slot, ++k) {
-    const int q = k & 1;
-    const int64_t tc = std::min<int64_t>(slot, T - t0);
-    double* dv = p->d_Vh.p + (size_t)q * slot * n;
-    if (k >= 2) ISR_CUDA(cudaStreamWaitEvent(p->copy_stream, p->ev_done[q], 0));   // slot free again
-    ISR_CUDA(cudaMemcpyAsync(dv, V + t0 * n, sizeof(double) * tc * n, cudaMemcpyHostToDevice, p->copy_stream));
-    ISR_CUDA(cudaEventRecord(p->ev_copied[q], p->copy_stream));
-    ISR_CUDA(cudaStreamWaitEvent(st, p->ev_copied[q], 0));
-    ToyOut o;
-    o.chi2 = chi2_out ? p->d_chi2h.p + t0 : nullptr;
-    o.sum_bcs = sum_bcs_out ? p->d_stat.p : nullptr;
-    o.ratio_stats = ratio_stats_out ? p->d_stat.p + n : nullptr;
-    o.rhist = ratio_hist_out ? p->d_rhist.p : nullptr;
-    o.bcs = bcs_out ? p->d_Bh.p + (size_t)q * slot * n : nullptr;
-    ISR_TRY(toy_batch_device(p, tc, dv, p->d_b0.p, o));
-    if (bcs_out)
-      ISR_CUDA(cudaMemcpyAsync(bcs_out + t0 * n, o.bcs, sizeof(double) * tc * n, cudaMemcpyDeviceToHost, st));
-    ISR_CUDA(cudaEventRecord(p->ev_done[q], st));
-    // this chunk's chi2 goes back while the next chunk's toys are still coming in (the two directions have their own
-    // copy engines); the values also stay on the device for isr_last_chi2_minmax / isr_last_chi2_histogram
-    if (chi2_out) ISR_CUDA(cudaMemcpyAsync(chi2_out + t0, o.chi2, sizeof(double) * tc, cudaMemcpyDeviceToHost, st));
-  }
+  ToyOut o;
+  o.chi2 = chi2_out ? p->d_chi2h.p : nullptr;
+  o.sum_bcs = sum_bcs_out ? p->d_stat.p : nullptr;
+  o.ratio_stats = ratio_stats_out ? p->d_stat.p + n : nullptr;
+  o.rhist = ratio_hist_out ? p->d_rhist.p : nullptr;
+  ISR_TRY(host_pipe_run(p, T, V, p->d_b0.p, o, chi2_out, bcs_out));
   p->last_chi2_count = chi2_out ? T : 0;
   if (sum_bcs_out) ISR_CUDA(cudaMemcpyAsync(sum_bcs_out, p->d_stat.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
   if (ratio_stats_out)

@@ -194,11 +194,11 @@ int tikhonov_solve(isr_problem* p, double la, const double* vcs, double* bcs_out
   cudaStream_t st = c->stream;
   ISR_TRY(p->d_tmp.reserve(nn));
   ISR_TRY(p->d_tmp2.reserve(nn));
-  ISR_TRY(p->d_b0.reserve(n));
+  ISR_TRY(p->d_vin.reserve(n));
   ISR_TRY(p->d_stat.reserve((size_t)4 * n));
-  ISR_CUDA(cudaMemcpyAsync(p->d_b0.p, vcs, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  ISR_CUDA(cudaMemcpyAsync(p->d_vin.p, vcs, sizeof(double) * n, cudaMemcpyHostToDevice, st));
   ISR_TRY(tik_operator(p, la, p->d_tmp2.p));
-  ISR_TRY(gemv(c, false, n, p->d_tmp2.p, p->d_b0.p, p->d_stat.p));
+  ISR_TRY(gemv(c, false, n, p->d_tmp2.p, p->d_vin.p, p->d_stat.p));
   ISR_CUDA(cudaMemcpyAsync(bcs_out, p->d_stat.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
   if (cov_out) {
     scale_cols_mu_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(n, p->d_U.p, p->d_mu.p, la, 1, p->d_tmp.p); ISR_COUNT_LAUNCH();
@@ -220,6 +220,7 @@ int tikhonov_select(isr_problem* p, double la) {
   ISR_CUDA(cudaGetLastError());
   p->tri_sel[0] = p->tri_sel[1] = 0;
   p->solver_selected = true;
+  p->selected_kind = 2;
   return ISR_OK;
 }
 
@@ -481,11 +482,11 @@ int tsvd_solve(isr_problem* p, int k, int keep_one, const double* vcs, const dou
   const int n = p->n;
   isr_ctx* c = p->ctx;
   cudaStream_t st = c->stream;
-  ISR_TRY(p->d_b0.reserve(n));
+  ISR_TRY(p->d_vin.reserve(n));
   ISR_TRY(p->d_stat.reserve((size_t)4 * n));
-  ISR_CUDA(cudaMemcpyAsync(p->d_b0.p, vcs, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  ISR_CUDA(cudaMemcpyAsync(p->d_vin.p, vcs, sizeof(double) * n, cudaMemcpyHostToDevice, st));
   // b = V_s Sigma_s^-1 U_s^T v  (minimum-norm least squares of K b = v, what COD(K).solve returns)
-  ISR_TRY(gemv(c, true, n, p->d_svU.p, p->d_b0.p, p->d_stat.p));
+  ISR_TRY(gemv(c, true, n, p->d_svU.p, p->d_vin.p, p->d_stat.p));
   tsvd_filter_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, first, count, p->d_sv.p, p->d_stat.p); ISR_COUNT_LAUNCH();
   ISR_TRY(gemv(c, true, n, p->d_svVT.p, p->d_stat.p, p->d_stat.p + n));
   ISR_CUDA(cudaMemcpyAsync(bcs_out, p->d_stat.p + n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
@@ -496,7 +497,14 @@ int tsvd_solve(isr_problem* p, int k, int keep_one, const double* vcs, const dou
       return ISR_ENUMERIC;
     }
     if (!vcs_err) { set_error("isr_tsvd_solve: vcs_err needed for the covariance"); return ISR_EINVAL; }
-    ISR_TRY(factor(p, vcs_err));
+    // (K^T W K)^-1 for the full-rank K = G is the SLE covariance: it needs the SLE factorisation, whose operator set-up
+    // overwrites d_Sop / d_Rop.  A Tikhonov / TSVD selection made earlier is therefore DROPPED, explicitly: the next toy
+    // batch fails with ISR_ESTATE until the caller selects again (it used to run silently on the SLE operators).
+    const int kind_before = p->selected_kind;
+    bool same = p->factored && p->selected_kind == 1 && p->vcs_err.size() == (size_t)n;
+    if (same) for (int i = 0; i < n; ++i) same = same && p->vcs_err[i] == vcs_err[i];
+    if (!same) ISR_TRY(factor(p, vcs_err));
+    if (kind_before == 2 || kind_before == 3) { p->solver_selected = false; p->selected_kind = 0; }
     ISR_TRY(ensure_cov(p));
     ISR_CUDA(cudaMemcpyAsync(cov_out, p->d_Cov.p, sizeof(double) * n * n, cudaMemcpyDeviceToHost, st));
     ISR_CUDA(cudaStreamSynchronize(st));
@@ -530,6 +538,7 @@ int tsvd_select(isr_problem* p, int k, int keep_one, const double* vcs_err) {
   p->tri_sel[0] = p->tri_sel[1] = 0;
   p->factored = false;   // Sop/Rop no longer belong to the SLE factorisation
   p->solver_selected = true;
+  p->selected_kind = 3;
   return ISR_OK;
 }
 

@@ -254,8 +254,12 @@ int toy_batch_device(isr_problem* p, int64_t T, const double* V_dev, const doubl
   if (T <= 0) return ISR_OK;
   if (out.chi2 && p->toy_variant == 2) ISR_TRY(ensure_rop_triangular(p));
   // pass 2 is skipped when no chi2 is requested (e.g. the mean-solution loop of chi2TestData)
-  return launch_fused(p, T, V_dev, p->d_Sop.p, out.chi2 ? p->d_Rop.p : nullptr, b0_dev,
-                      out.chi2 ? nullptr : scratch_dfull(p, T), out);
+  double* dfull = nullptr;
+  if (!out.chi2) {
+    dfull = scratch_dfull(p, T);
+    if (!dfull) return ISR_ECUDA;      // (the allocation's message is in isr_last_error)
+  }
+  return launch_fused(p, T, V_dev, p->d_Sop.p, out.chi2 ? p->d_Rop.p : nullptr, b0_dev, dfull, out);
 }
 
 // pass-1-only launches still write d = b - b0 somewhere: a scratch T x ld buffer
