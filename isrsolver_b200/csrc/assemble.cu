@@ -144,6 +144,7 @@ int build_eps_rows(cudaStream_t st, int n, const double* energy, const isr_eps_d
 }
 
 int upload_eps(isr_problem* p, const isr_eps_desc* e) {
+  p->panels_ready = false;
   return build_eps_rows(p->ctx->stream, p->n, p->ext.data() + 1, e, p->d_eps_vals, p->d_eps_edges, p->eps);
 }
 
@@ -601,7 +602,12 @@ int reduce_moments(isr_problem* p) {
 }
 
 // Panel enumeration (row constants, count, scan, fill): everything before the integrand is touched.
+// The panel set depends only on the energies and on the efficiency's bin edges -- both fixed when the problem is created
+// (the interpolation ranges only enter the contraction) -- so, like the reference's Interpolator, which is built in the
+// solver's constructor and not in evalEqMatrix (src/ISRSolverSLE.cpp:54-58 vs :138-149), it is enumerated once per problem;
+// every isr_assemble still evaluates the integrand at every node and redoes the contraction.
 static int enumerate_panels(isr_problem* p) {
+  if (p->panels_ready) return ISR_OK;
   const int n = p->n;
   cudaStream_t st = p->ctx->stream;
   const int nitems = n * (n + 1) / 2;
@@ -631,6 +637,7 @@ static int enumerate_panels(isr_problem* p) {
                                                         p->d_pa.p, p->d_pb.p, p->d_pitem.p, p->d_pkind.p); ISR_COUNT_LAUNCH();
   }
   ISR_CUDA(cudaGetLastError());
+  p->panels_ready = true;
   return ISR_OK;
 }
 

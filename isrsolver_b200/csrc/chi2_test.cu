@@ -15,6 +15,7 @@
 //     then SUM of one packed FP64 buffer [TH1F cells | sum b | ratio stats | toy count | certificate flag] -- the flag makes
 //     the re-run decision collective, so that no rank can leave the others waiting in an all-reduce.
 #include "comm.hpp"
+#include "panel_device.cuh"
 #include "problem.hpp"
 #include "solve.hpp"
 #include "toy_batch.hpp"
@@ -48,6 +49,97 @@ __global__ void pack_test_kernel(int nb, int n, const int* __restrict__ cells, c
     }
   }
   pack[idx] = v;
+}
+
+// ---- fused tail of the test: two launches instead of six (min/max partials, final reduction, memset, TH1F, packing) --
+// range_kernel: per-block min / max of the chi2 values; the block that arrives LAST (fence + arrival counter) reduces the
+// partials in a fixed order to range = {min, -max} (the layout one all-reduce(MIN) over ranks needs), zeroes the TH1F
+// cells for the next kernel and re-arms the counter.
+__global__ void __launch_bounds__(256) range_kernel(int64_t n, const double* __restrict__ v, double* __restrict__ part,
+                                                     unsigned* __restrict__ counter, double* __restrict__ range,
+                                                     int* __restrict__ cells, int ncells) {
+  __shared__ double smin[8], smax[8];
+  __shared__ bool last;
+  double lo = INFINITY, hi = -INFINITY;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+    const double x = v[q];
+    lo = fmin(lo, x);
+    hi = fmax(hi, x);
+  }
+  auto block_reduce = [&]() {
+    for (int s = 16; s >= 1; s >>= 1) {
+      lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, s));
+      hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, s));
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { smin[w] = lo; smax[w] = hi; }
+    __syncthreads();
+    if (w == 0) {
+      lo = l < 8 ? smin[l] : INFINITY;
+      hi = l < 8 ? smax[l] : -INFINITY;
+      for (int s = 4; s >= 1; s >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, s));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, s));
+      }
+    }
+  };
+  block_reduce();
+  if (threadIdx.x == 0) {
+    part[2 * blockIdx.x] = lo;
+    part[2 * blockIdx.x + 1] = hi;
+    __threadfence();
+    last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  lo = INFINITY; hi = -INFINITY;
+  for (int q = threadIdx.x; q < (int)gridDim.x; q += blockDim.x) {
+    lo = fmin(lo, __ldcg(&part[2 * q]));
+    hi = fmax(hi, __ldcg(&part[2 * q + 1]));
+  }
+  __syncthreads();
+  block_reduce();
+  if (threadIdx.x == 0) { range[0] = lo; range[1] = -hi; *counter = 0u; }
+  for (int q = threadIdx.x; q < ncells; q += blockDim.x) cells[q] = 0;
+}
+
+// cells_pack_kernel: TH1F cells of the chi2 values against the (global) range (shared-memory counters, integer atomics),
+// then the block that arrives last writes the packed buffer (see pack_test_kernel for the layout).
+__global__ void __launch_bounds__(256) cells_pack_kernel(int64_t n, const double* __restrict__ v, int nbins,
+                                                          const double* __restrict__ range, int* __restrict__ cells,
+                                                          unsigned* __restrict__ counter, int npts, const double* __restrict__ stat,
+                                                          double toys, const double* __restrict__ cert, int assumed_lower, double tol,
+                                                          double* __restrict__ pack) {
+  extern __shared__ uint32_t sh[];
+  __shared__ bool last;
+  const double lo = range[0], hi = -range[1];
+  for (int q = threadIdx.x; q < nbins + 2; q += blockDim.x) sh[q] = 0;
+  __syncthreads();
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd(&sh[th1_bin(nbins, lo, hi, v[q])], 1u);
+  __syncthreads();
+  for (int q = threadIdx.x; q < nbins + 2; q += blockDim.x)
+    if (sh[q]) atomicAdd(&cells[q], (int)sh[q]);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  const int nb = nbins + 2, len = nb + 4 * npts + 2;
+  for (int idx = threadIdx.x; idx < len; idx += blockDim.x) {
+    double val;
+    if (idx < nb) val = (double)__ldcg(&cells[idx]);
+    else if (idx < nb + 4 * npts) val = stat[idx - nb];
+    else if (idx == nb + 4 * npts) val = toys;
+    else {
+      val = 0.0;
+      if (cert) val = (cert[0] <= tol && (!assumed_lower || (cert[1] == 0.0 && cert[2] == 0.0))) ? 0.0 : 1.0;
+    }
+    pack[idx] = val;
+  }
+  if (threadIdx.x == 0) *counter = 0u;
 }
 
 static int enqueue_toys(isr_problem* p, const isr_chi2_test_args& a, const TestWants& w, bool need_chi2, bool first_attempt) {
@@ -121,6 +213,11 @@ int chi2_test(isr_problem* p, const isr_chi2_test_args& a, TestWants w) {
   if (w.rhist) ISR_TRY(p->d_rhist.reserve((size_t)n * 1026));
   ISR_TRY(p->d_pack.reserve((size_t)plen + 2));          // [range (2) | pack]
   ISR_TRY(p->d_cells.reserve((size_t)std::max(nb, 1)));
+  ISR_TRY(p->d_part.reserve((size_t)4 * c->sm_count));
+  if (!p->d_arrive.p) {
+    ISR_TRY(p->d_arrive.reserve(2));
+    ISR_CUDA(cudaMemsetAsync(p->d_arrive.p, 0, 2 * sizeof(unsigned), st));     // the kernels re-arm their counters themselves
+  }
   if ((size_t)plen + 2 > p->pin_test_n) {
     if (p->pin_test) cudaFreeHost(p->pin_test);
     p->pin_test = nullptr; p->pin_test_n = 0;
@@ -169,16 +266,28 @@ int chi2_test(isr_problem* p, const isr_chi2_test_args& a, TestWants w) {
     if ((rc = enqueue_toys(p, a, w, need_chi2, attempt == 0)) != ISR_OK) return drain(rc);
     cudaEventRecord(p->ev_time[3], st);
     // ---- range, cells, packed buffer, collectives
-    if (need_range) {
-      if (T > 0) { if ((rc = minmax_to_device(c, T, p->d_chi2h.p, d_range)) != ISR_OK) return drain(rc); }
-      else { empty_range_kernel<<<1, 32, 0, st>>>(d_range); ISR_COUNT_LAUNCH(); }
-      if (a.comm && (rc = comm_allreduce(a.comm, d_range, 2, 0, 1)) != ISR_OK) return drain(rc);
-      if (a.nbins > 0 && (rc = histogram_range_device(c, T, p->d_chi2h.p, a.nbins, d_range, p->d_cells.p)) != ISR_OK) return drain(rc);
-    }
     const bool cert_here = do_fac && attempt == 0;
-    pack_test_kernel<<<(plen + 255) / 256, 256, 0, st>>>(nb, n, a.nbins > 0 ? p->d_cells.p : nullptr, p->d_stat.p, (double)T,
-                                                        cert_here ? p->cert_dev : nullptr, p->tri_sle[0] || p->tri_sle[1],
-                                                        1e-12 * n, d_pack); ISR_COUNT_LAUNCH();
+    const int assumed = (p->tri_sle[0] || p->tri_sle[1]) ? 1 : 0;
+    if (T > 0 && a.nbins > 0) {
+      // the usual case: two fused launches (the stat sums of the toy kernels are complete: same stream)
+      const int blocks = (int)std::min<int64_t>(c->sm_count * 2, (T + 255) / 256);
+      range_kernel<<<blocks, 256, 0, st>>>(T, p->d_chi2h.p, p->d_part.p, p->d_arrive.p, d_range, p->d_cells.p, nb); ISR_COUNT_LAUNCH();
+      if (a.comm && (rc = comm_allreduce(a.comm, d_range, 2, 0, 1)) != ISR_OK) return drain(rc);
+      if (cert_here) cudaStreamWaitEvent(st, c->ev_cert, 0);      // the verdict of the inverse (side stream) enters the packed buffer
+      cells_pack_kernel<<<blocks, 256, sizeof(uint32_t) * nb, st>>>(T, p->d_chi2h.p, a.nbins, d_range, p->d_cells.p, p->d_arrive.p + 1, n,
+                                                                    p->d_stat.p, (double)T, cert_here ? p->cert_dev : nullptr, assumed,
+                                                                    1e-12 * n, d_pack); ISR_COUNT_LAUNCH();
+    } else {
+      if (need_range) {
+        if (T > 0) { if ((rc = minmax_to_device(c, T, p->d_chi2h.p, d_range)) != ISR_OK) return drain(rc); }
+        else { empty_range_kernel<<<1, 32, 0, st>>>(d_range); ISR_COUNT_LAUNCH(); }
+        if (a.comm && (rc = comm_allreduce(a.comm, d_range, 2, 0, 1)) != ISR_OK) return drain(rc);
+        if (a.nbins > 0 && (rc = histogram_range_device(c, T, p->d_chi2h.p, a.nbins, d_range, p->d_cells.p)) != ISR_OK) return drain(rc);
+      }
+      if (cert_here) cudaStreamWaitEvent(st, c->ev_cert, 0);
+      pack_test_kernel<<<(plen + 255) / 256, 256, 0, st>>>(nb, n, a.nbins > 0 ? p->d_cells.p : nullptr, p->d_stat.p, (double)T,
+                                                          cert_here ? p->cert_dev : nullptr, assumed, 1e-12 * n, d_pack); ISR_COUNT_LAUNCH();
+    }
     if (a.comm) {
       if ((rc = comm_allreduce(a.comm, d_pack, plen, 0, 0)) != ISR_OK) return drain(rc);
       if (w.rhist && (rc = comm_allreduce(a.comm, p->d_rhist.p, (int64_t)n * 1026, 2, 0)) != ISR_OK) return drain(rc);

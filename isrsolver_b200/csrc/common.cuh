@@ -119,6 +119,7 @@ struct isr_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t aux_stream = nullptr;     // side work that may overlap the main stream (first toy block, eigen-system)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_inv = nullptr, ev_cert = nullptr;   // inverse enqueued (main stream) / its certificate complete (side stream)
   double* pin = nullptr;                 // kPinDoubles page-locked doubles (layout owned by the call that uses it)
   cusolverDnHandle_t solver = nullptr;
   cublasHandle_t blas = nullptr;

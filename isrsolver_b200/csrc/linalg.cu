@@ -5,6 +5,8 @@
 #include "linalg.hpp"
 #include "gj_phases.cuh"
 
+#include <cstdlib>
+
 
 namespace isr {
 
@@ -144,7 +146,8 @@ __global__ void __launch_bounds__(256) inverse_residual_kernel(int n, const doub
 // A lower-triangular A yields an exactly lower-triangular inverse (the updates above the diagonal subtract exact
 // zeros).  No pivoting: the caller certifies the result (lu_inverse) and falls back to the pivoted LU otherwise.
 // --------------------------------------------------------------------------------------------------
-constexpr int kGjCtas = 4, kGjMaxN = 256, kGjColsPerLane = kGjMaxN / 32;   // 8 columns (4 pairs) per lane
+constexpr int kGjMaxN = 256, kGjColsPerLane = kGjMaxN / 32;   // 8 columns (4 pairs) per lane
+constexpr int kGjDefaultCtas = 8;
 constexpr int kGjMaxRows = 240;   // 15 arithmetic warps + the forwarder = 512 threads per CTA: 128 registers each
 namespace gj {
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -195,7 +198,11 @@ struct GjSmem {
   uint64_t rfull[kGjSlots], lfull[kGjSlots], empty[kGjSlots], done[kGjSlots];
 };
 
-__global__ void __cluster_dims__(kGjCtas, 1, 1) __launch_bounds__(512, 1)
+// kGjCtas (template): CTAs of the cluster.  4 CTAs x 15 warps put four arithmetic warps on every SM sub-partition, where the
+// owner warp's dependent chain competes with three others for the FP64 pipe; 8 CTAs x 8 warps halve that contention (the
+// cluster size is a launch attribute: cudaLaunchKernelEx).
+template <int kGjCtas>
+__global__ void __launch_bounds__(512, 1)
 gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, double* __restrict__ cert) {
   constexpr uint32_t kRowBytes = kGjMaxN * sizeof(double);
   extern __shared__ __align__(128) unsigned char gj_smem_raw[];
@@ -337,6 +344,34 @@ gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, d
   gj::cluster_sync();   // no CTA may exit while its shared memory can still be the target of a remote copy or arrive
 }
 
+template <int CTAS>
+static int launch_gj_t(isr_ctx* c, int n, const double* A, double* X, double* cert) {
+  const int warps = (n + 4 * CTAS - 1) / (4 * CTAS);   // four rows per warp, whole warps per CTA
+  auto kernel = gj_inverse_kernel<CTAS>;
+  ISR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GjSmem)));   // per device
+  if (CTAS > 8) ISR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(CTAS);
+  cfg.blockDim = dim3(32 * warps + 32);
+  cfg.dynamicSmemBytes = sizeof(GjSmem);
+  cfg.stream = c->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  ISR_CUDA(cudaLaunchKernelEx(&cfg, kernel, n, A, X, cert)); ISR_COUNT_LAUNCH();
+  return ISR_OK;
+}
+// Cluster size: 4 CTAs hold at most 240 rows (15 arithmetic warps each), 8 and 16 CTAs spread the same rows thinner.
+static int launch_gj(isr_ctx* c, int n, const double* A, double* X, double* cert) {
+  static const int forced = [] { const char* e = std::getenv("ISR_GJ_CTAS"); return e ? std::atoi(e) : 0; }();
+  const int ctas = forced ? forced : kGjDefaultCtas;
+  if (ctas == 16) return launch_gj_t<16>(c, n, A, X, cert);
+  if (ctas == 4) return launch_gj_t<4>(c, n, A, X, cert);
+  return launch_gj_t<8>(c, n, A, X, cert);
+}
+
 // Ainv = A^-1.  A (column-major, preserved) is factored in `lu` (n x n scratch, destroyed); `prod` is n x n scratch.
 //
 // cuSOLVER's LU without pivoting is about twice as fast as the pivoted one at these sizes (N = 200: 0.26 vs 0.56 ms,
@@ -352,24 +387,21 @@ gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, d
 // trip; inverse_certified reads the verdict after the caller's one synchronisation, and inverse_pivoted is the
 // synchronous fall-back (after which the caller re-runs its dependents).
 // lower_hint: the caller knows A to be lower triangular (selects the triangular solve for N > kGjMaxRows).
-// cert_host: 8 page-locked doubles owned by the caller (kPinCert / kPinInfo slots); *cert_dev_out: the device copy of the
-// three scalars, for kernels that fold the verdict into a collective.
+// cert_host: 8 page-locked doubles owned by the caller (kPinCert / kPinInfo slots); cert_dev: 3 doubles of device memory
+// owned by the caller (kernels may fold the verdict into a collective).
 int inverse_enqueue(isr_ctx* c, int n, const double* A, double* lu, double* prod, double* Ainv, DevBuf<double>& work,
-                    DevBuf<int>& ipiv, DevBuf<int>& info, bool lower_hint, double* cert_host, double** cert_dev_out) {
+                    DevBuf<int>& ipiv, DevBuf<int>& info, bool lower_hint, double* cert_host, double* cert_dev) {
   int lwork = 0;
   const size_t bytes = sizeof(double) * (size_t)n * n;
   ISR_CUSOLVER(cusolverDnDgetrf_bufferSize(c->solver, n, n, lu, n, &lwork));
-  ISR_TRY(work.reserve((size_t)lwork + 3));      // +3: the residual and the two triangularity scalars live behind the LAPACK workspace
+  ISR_TRY(work.reserve((size_t)lwork));
   ISR_TRY(ipiv.reserve(n));
   ISR_TRY(info.reserve(2));
-  double* resid_dev = work.p + lwork;
-  *cert_dev_out = resid_dev;
+  double* resid_dev = cert_dev;
   int* h_info = reinterpret_cast<int*>(cert_host + kPinInfo);
   h_info[0] = h_info[1] = 0;
   if (n <= kGjMaxRows) {
-    const int warps = (n + 4 * kGjCtas - 1) / (4 * kGjCtas);   // four rows per warp, whole warps per CTA
-    ISR_CUDA(cudaFuncSetAttribute(gj_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GjSmem)));   // per device
-    gj_inverse_kernel<<<kGjCtas, 32 * warps + 32, sizeof(GjSmem), c->stream>>>(n, A, Ainv, resid_dev); ISR_COUNT_LAUNCH();
+    ISR_TRY(launch_gj(c, n, A, Ainv, resid_dev));
   } else if (lower_hint) {
     // the caller knows A to be lower triangular (linear interpolation without spread): blocked triangular inverse
     // (tri_inverse.cu); a wrong hint fails the certificate below like any other bad inverse
@@ -383,9 +415,16 @@ int inverse_enqueue(isr_ctx* c, int n, const double* A, double* lu, double* prod
     ISR_CUSOLVER(cusolverDnDgetrs(c->solver, CUBLAS_OP_N, n, n, lu, n, nullptr, Ainv, n, info.p + 1));
     ISR_CUDA(cudaMemcpyAsync(h_info, info.p, sizeof(int) * 2, cudaMemcpyDeviceToHost, c->stream));
   }
-  ISR_TRY(small_gemm(c, n, lower_hint, A, Ainv, prod));   // (a wrong hint is caught by the triangularity scalars)
-  inverse_residual_kernel<<<n, 256, 0, c->stream>>>(n, prod, Ainv, A, resid_dev); ISR_COUNT_LAUNCH();
-  ISR_CUDA(cudaMemcpyAsync(cert_host + kPinCert, resid_dev, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  // The certificate runs on the context's SIDE stream: nothing downstream of the inverse (operator set-up, toy kernels)
+  // waits for it; whoever reads the verdict waits for ev_cert (factor_finish's caller synchronises, chi2_test makes its
+  // packing kernel wait).  `prod` must therefore be scratch nobody else touches meanwhile.
+  cudaStream_t cs = c->aux_stream;
+  ISR_CUDA(cudaEventRecord(c->ev_inv, c->stream));
+  ISR_CUDA(cudaStreamWaitEvent(cs, c->ev_inv, 0));
+  ISR_TRY(small_gemm(c, n, lower_hint, A, Ainv, prod, cs));   // (a wrong hint is caught by the triangularity scalars)
+  inverse_residual_kernel<<<n, 256, 0, cs>>>(n, prod, Ainv, A, resid_dev); ISR_COUNT_LAUNCH();
+  ISR_CUDA(cudaMemcpyAsync(cert_host + kPinCert, resid_dev, 3 * sizeof(double), cudaMemcpyDeviceToHost, cs));
+  ISR_CUDA(cudaEventRecord(c->ev_cert, cs));
   ISR_CUDA(cudaGetLastError());
   return ISR_OK;
 }
@@ -400,11 +439,12 @@ bool inverse_certified(const double* cert_host, int n, int* tri) {
 }
 // LU with partial pivoting (synchronous): the fall-back when the certificate fails.
 int inverse_pivoted(isr_ctx* c, int n, const double* A, double* lu, double* Ainv, DevBuf<double>& work, DevBuf<int>& ipiv,
-                    DevBuf<int>& info, double* cert_host, int* tri) {
+                    DevBuf<int>& info, double* cert_host, double* cert_dev, int* tri) {
   const size_t bytes = sizeof(double) * (size_t)n * n;
   int lwork = 0;
   ISR_CUSOLVER(cusolverDnDgetrf_bufferSize(c->solver, n, n, lu, n, &lwork));
-  double* resid_dev = work.p + lwork;
+  ISR_TRY(work.reserve((size_t)lwork));
+  double* resid_dev = cert_dev;
   ISR_CUDA(cudaMemcpyAsync(lu, A, bytes, cudaMemcpyDeviceToDevice, c->stream));
   ISR_CUSOLVER(cusolverDnDgetrf(c->solver, n, n, lu, n, work.p, ipiv.p, info.p));
   ISR_TRY(check_info(c, info.p, "LU factorisation (getrf)"));

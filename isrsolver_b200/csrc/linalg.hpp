@@ -12,15 +12,15 @@ void scale_rows(cudaStream_t st, int n, const double* A, const double* s, int in
 int gemm(isr_ctx* c, bool ta, bool tb, int n, const double* A, const double* B, double* C);
 int gemv(isr_ctx* c, bool ta, int n, const double* A, const double* x, double* y);
 int inverse_enqueue(isr_ctx* c, int n, const double* A, double* lu, double* prod, double* Ainv, DevBuf<double>& work,
-                    DevBuf<int>& ipiv, DevBuf<int>& info, bool lower_hint, double* cert_host, double** cert_dev_out);
+                    DevBuf<int>& ipiv, DevBuf<int>& info, bool lower_hint, double* cert_host, double* cert_dev);
 bool inverse_certified(const double* cert_host, int n, int* tri);
 int inverse_pivoted(isr_ctx* c, int n, const double* A, double* lu, double* Ainv, DevBuf<double>& work, DevBuf<int>& ipiv,
-                    DevBuf<int>& info, double* cert_host, int* tri);
+                    DevBuf<int>& info, double* cert_host, double* cert_dev, int* tri);
 // X = L^-1 for a lower-triangular L (column-major, N x N), blocked: diagonal blocks by substitution, then the
 // off-diagonal block columns by products (tri_inverse.cu).  Entries above the diagonal of X are exact zeros.
 int tri_inverse_lower(isr_ctx* c, int n, const double* L, double* X);
 // C = A B, n x n column-major, hand-written 32 x 32 tiles; lower: both factors (hence the product) are lower triangular.
-int small_gemm(isr_ctx* c, int n, bool lower, const double* A, const double* B, double* C);
+int small_gemm(isr_ctx* c, int n, bool lower, const double* A, const double* B, double* C, cudaStream_t st = nullptr);
 int ql_factor_rowmajor(isr_ctx* c, int n, int ld, double* A, double* scratch, DevBuf<double>& work, DevBuf<int>& info);
 int svd(isr_ctx* c, int n, double* A, double* U, double* S, double* VT, DevBuf<double>& work, DevBuf<int>& info);
 int svd_values_async(cusolverDnHandle_t h, int n, double* A, double* S, DevBuf<double>& work, DevBuf<int>& info);

@@ -34,6 +34,7 @@ struct isr_problem {
   isr::DevBuf<double> d_Gpart;   // split-K partials of the contraction
   isr::DevBuf<double> d_S, d_tmp, d_sigE;
   int64_t max_panels = 0;
+  bool panels_ready = false;          // the panel set of this problem has been enumerated (it depends on energies and efficiency edges only)
   int sampled_panels = -1;            // panel count of the last isr_assemble_nodes (host-sampled efficiency)
   isr::DevBuf<double> d_node_x, d_node_eps;
   isr::DevBuf<int> d_node_row;
@@ -49,6 +50,8 @@ struct isr_problem {
   // chi2 = |Rop (b - b0)|^2).
   isr::DevBuf<double> d_Ginv, d_R, d_Cov, d_InvCov, d_Sop, d_Rop, d_werr;
   isr::DevBuf<double> d_work;
+  isr::DevBuf<double> d_cert;        // the certificate's three scalars
+  isr::DevBuf<double> d_cert_prod;   // G X of the inverse's certificate (side stream: nobody else may touch it)
   isr::DevBuf<int> d_ipiv, d_info;
   int tri_sel[2] = {0, 0};     // {S, R}: d_Sop / d_Rop of the current selection is exactly lower triangular (the toy kernel
                                // skips the zeros); known on the host without a synchronisation of its own (lu_inverse)
@@ -60,7 +63,7 @@ struct isr_problem {
   bool solver_selected = false;
   int selected_kind = 0;       // whose operators d_Sop / d_Rop hold: 0 none, 1 SLE (isr_factor), 2 Tikhonov, 3 TSVD
   bool cert_pending = false;   // factor_enqueue ran; factor_finish has not read the inverse's certificate yet
-  double* cert_dev = nullptr;  // device copy of the certificate scalars (3 doubles, owned by d_work)
+  double* cert_dev = nullptr;  // device copy of the certificate scalars (= d_cert.p once a factorisation was enqueued)
   double* pin_cert = nullptr;  // page-locked: certificate scalars + cuSOLVER info of the pending factorisation (8 doubles)
   int toy_variant = 0;
   int64_t last_chi2_count = 0;   // chi2 values the last host-API batch / campaign left in d_chi2h
@@ -73,6 +76,8 @@ struct isr_problem {
   // isr_chi2_test: [range (2) | packed result] on the device, TH1F cells, and the page-locked copy of the former
   isr::DevBuf<double> d_pack;
   isr::DevBuf<int> d_cells;
+  isr::DevBuf<double> d_part;        // per-block {min, max} partials of the range kernel
+  isr::DevBuf<unsigned> d_arrive;    // arrival counters of the two fused tail kernels
   double* pin_test = nullptr;
   cudaEvent_t ev_time[4] = {nullptr, nullptr, nullptr, nullptr};   // start | assembled | factor enqueued | toys enqueued
   size_t pin_test_n = 0;

@@ -44,10 +44,12 @@ int factor_enqueue(isr_problem* p, const double* vcs_err) {
   if (p->vcs_err.size() != (size_t)n || std::memcmp(p->vcs_err.data(), vcs_err, sizeof(double) * n) != 0) p->tik_ready = false;
   p->vcs_err.assign(vcs_err, vcs_err + n);
   ISR_CUDA(cudaMemcpyAsync(p->d_werr.p, p->vcs_err.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
-  ISR_TRY(p->d_tmp2.reserve(nn));
+  ISR_TRY(p->d_cert_prod.reserve(nn));
+  ISR_TRY(p->d_cert.reserve(4));
   if (!p->pin_cert) ISR_CUDA(cudaMallocHost((void**)&p->pin_cert, sizeof(double) * 8));
-  ISR_TRY(inverse_enqueue(c, n, p->d_G.p, p->d_tmp.p, p->d_tmp2.p, p->d_Ginv.p, p->d_work, p->d_ipiv, p->d_info, p->G_lower,
-                          p->pin_cert, &p->cert_dev));
+  ISR_TRY(inverse_enqueue(c, n, p->d_G.p, p->d_tmp.p, p->d_cert_prod.p, p->d_Ginv.p, p->d_work, p->d_ipiv, p->d_info, p->G_lower,
+                          p->pin_cert, p->d_cert.p));
+  p->cert_dev = p->d_cert.p;
   ISR_TRY(launch_sle_operators(p));
   p->factored = true;
   p->cert_pending = true;
@@ -78,7 +80,7 @@ int factor_finish(isr_problem* p, bool* redone) {
     return ISR_OK;
   }
   p->factored = false;
-  ISR_TRY(inverse_pivoted(c, p->n, p->d_G.p, p->d_tmp.p, p->d_Ginv.p, p->d_work, p->d_ipiv, p->d_info, p->pin_cert, tri));
+  ISR_TRY(inverse_pivoted(c, p->n, p->d_G.p, p->d_tmp.p, p->d_Ginv.p, p->d_work, p->d_ipiv, p->d_info, p->pin_cert, p->d_cert.p, tri));
   p->tri_sle[0] = tri[0]; p->tri_sle[1] = tri[1];
   p->tri_sel[0] = tri[0]; p->tri_sel[1] = tri[1];
   ISR_TRY(launch_sle_operators(p));
@@ -92,6 +94,7 @@ int factor_finish(isr_problem* p, bool* redone) {
 int factor(isr_problem* p, const double* vcs_err) {
   ISR_TRY(factor_enqueue(p, vcs_err));
   ISR_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  ISR_CUDA(cudaEventSynchronize(p->ctx->ev_cert));     // the certificate ran on the side stream
   return factor_finish(p, nullptr);
 }
 

@@ -140,9 +140,9 @@ __global__ void __launch_bounds__(256) small_gemm_kernel(int n, int lower, const
   const int k_lo = lower ? tc * kTb : 0, k_hi = lower ? min(n, (tr + 1) * kTb) : n;
   tile_product(jb, n, tr, tc, k_lo, k_hi, 1.0, sA, sB);
 }
-int small_gemm(isr_ctx* c, int n, bool lower, const double* A, const double* B, double* C) {
+int small_gemm(isr_ctx* c, int n, bool lower, const double* A, const double* B, double* C, cudaStream_t st) {
   const int t = (n + kTb - 1) / kTb;
-  small_gemm_kernel<<<dim3(t, t), 256, 0, c->stream>>>(n, lower ? 1 : 0, A, B, C); ISR_COUNT_LAUNCH();
+  small_gemm_kernel<<<dim3(t, t), 256, 0, st ? st : c->stream>>>(n, lower ? 1 : 0, A, B, C); ISR_COUNT_LAUNCH();
   ISR_CUDA(cudaGetLastError());
   return ISR_OK;
 }

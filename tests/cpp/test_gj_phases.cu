@@ -1,6 +1,6 @@
 // CPU replay of the slot protocol of the cluster Gauss-Jordan inverse (isrsolver_b200/csrc/linalg.cu) with the kernel's
-// own phase arithmetic (gj_phases.cuh).  For every N from 1 to 240 the pivot blocks are processed in order on four
-// simulated CTAs; every mbarrier is a counter of completed phases, and at every wait of the kernel the parity it would
+// own phase arithmetic (gj_phases.cuh).  For every N from 1 to 240 the pivot blocks are processed in order on the
+// simulated CTAs of a 4-, 8- and 16-CTA cluster; every mbarrier is a counter of completed phases, and at every wait of the kernel the parity it would
 // pass must be the parity of the phase that has just completed for that use:
 //   empty[slot]  owner of block B >= 4 waits for the four credits of block B - 4
 //   lfull[slot]  warps of the owner's CTA wait for the locally staged block
@@ -23,8 +23,9 @@ using namespace isr;
     }                                                                                    \
   } while (0)
 
-int main() {
-  constexpr int C = 4;
+// C: CTAs of the cluster (the kernel is launched with 4, 8 or 16)
+template <int C>
+static long replay() {
   long waits = 0;
   for (int n = 1; n <= 240; ++n) {
     const int R = 4 * ((n + 4 * C - 1) / (4 * C)), NB = (n + 3) / 4;
@@ -70,6 +71,11 @@ int main() {
     for (c = 0; c < C; ++c)
       for (int q = 0; q < kGjSlots; ++q) CHECK(expected[c][q] == -1 && credits[c][q] == 0);   // nothing left armed
   }
+  return waits;
+}
+
+int main() {
+  const long waits = replay<4>() + replay<8>() + replay<16>();
   std::printf("gauss-jordan slot protocol ok: %ld waits replayed\n", waits);
   return 0;
 }
