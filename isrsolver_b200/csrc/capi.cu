@@ -58,6 +58,9 @@ int isr_ctx_create(int device, isr_ctx** out) {
   ISR_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
   ISR_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   ISR_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  ISR_CUDA(cudaStreamCreateWithFlags(&c->gen_stream, cudaStreamNonBlocking));
+  ISR_CUDA(cudaEventCreateWithFlags(&c->ev_fork2, cudaEventDisableTiming));
+  ISR_CUDA(cudaEventCreateWithFlags(&c->ev_rop, cudaEventDisableTiming));
   ISR_CUDA(cudaEventCreateWithFlags(&c->ev_inv, cudaEventDisableTiming));
   ISR_CUDA(cudaEventCreateWithFlags(&c->ev_cert, cudaEventDisableTiming));
   ISR_CUDA(cudaMallocHost((void**)&c->pin, sizeof(double) * kPinDoubles));
@@ -78,6 +81,9 @@ void isr_ctx_destroy(isr_ctx* c) {
   if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->gen_stream) cudaStreamDestroy(c->gen_stream);
+  if (c->ev_fork2) cudaEventDestroy(c->ev_fork2);
+  if (c->ev_rop) cudaEventDestroy(c->ev_rop);
   if (c->ev_inv) cudaEventDestroy(c->ev_inv);
   if (c->ev_cert) cudaEventDestroy(c->ev_cert);
   if (c->pin) cudaFreeHost(c->pin);

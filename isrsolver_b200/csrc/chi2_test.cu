@@ -237,18 +237,17 @@ int chi2_test(isr_problem* p, const isr_chi2_test_args& a, TestWants w) {
     p->h_gen.insert(p->h_gen.end(), a.vcs_err, a.vcs_err + n);
     ISR_CUDA(cudaMemcpyAsync(p->d_gen.p, p->h_gen.data(), sizeof(double) * 2 * n, cudaMemcpyHostToDevice, st));
     ISR_CUDA(cudaEventRecord(c->ev_fork, st));
-    ISR_CUDA(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
-    ISR_TRY(draw_toys_device(c, chunk, n, a.first_toy, a.seed, p->d_gen.p, p->d_gen.p + n, p->d_Vh.p, c->aux_stream));
-    ISR_CUDA(cudaEventRecord(c->ev_join, c->aux_stream));
+    ISR_CUDA(cudaStreamWaitEvent(c->gen_stream, c->ev_fork, 0));
+    ISR_TRY(draw_toys_device(c, chunk, n, a.first_toy, a.seed, p->d_gen.p, p->d_gen.p + n, p->d_Vh.p, c->gen_stream));
+    ISR_CUDA(cudaEventRecord(c->ev_join, c->gen_stream));
   }
-  p->h_b0.assign(a.bcs0, a.bcs0 + n);
-  ISR_CUDA(cudaMemcpyAsync(p->d_b0.p, p->h_b0.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
 
   // ---- matrix and factorisation (enqueue only)
   int rc = ISR_OK;
   auto drain = [&](int code) {      // a failure after the pipeline started: nothing may still read the caller's buffers
     if (p->copy_stream) cudaStreamSynchronize(p->copy_stream);
     cudaStreamSynchronize(c->aux_stream);
+    cudaStreamSynchronize(c->gen_stream);
     cudaStreamSynchronize(st);
     p->cert_pending = false;
     return code;
@@ -258,6 +257,11 @@ int chi2_test(isr_problem* p, const isr_chi2_test_args& a, TestWants w) {
   cudaEventRecord(p->ev_time[0], st);
   if (do_asm && (rc = assemble(p, a.ecm_err)) != ISR_OK) return drain(rc);
   cudaEventRecord(p->ev_time[1], st);
+  p->h_b0.assign(a.bcs0, a.bcs0 + n);      // (after the assembly's launches: the GPU is already busy while the host stages this)
+  if (cudaMemcpyAsync(p->d_b0.p, p->h_b0.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+    set_error("isr_chi2_test: copy of bcs0 failed (%s)", cudaGetErrorString(cudaGetLastError()));
+    return drain(ISR_ECUDA);
+  }
   if (do_fac && (rc = factor_enqueue(p, a.vcs_err)) != ISR_OK) return drain(rc);
 
   int refactored = 0;

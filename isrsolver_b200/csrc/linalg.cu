@@ -186,6 +186,17 @@ __device__ __forceinline__ void bulk_smem_to_cluster(uint32_t dst_cluster, uint3
   asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(mbar_cluster) : "memory");
 }
+// 1 / x to full double precision without the division routine (MUFU.RCP64H seed + slow-path branch + fix-up, about 150
+// cycles on the critical chain of every pivot): hardware seed (20 bits) and two Newton steps.  Not correctly rounded
+// (<= 1 ulp); the inverse is certified a posteriori anyway.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;\n" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
 __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
@@ -203,7 +214,8 @@ struct GjSmem {
 // cluster size is a launch attribute: cudaLaunchKernelEx).
 template <int kGjCtas>
 __global__ void __launch_bounds__(512, 1)
-gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, double* __restrict__ cert) {
+gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, double* __restrict__ cert,
+                  double* __restrict__ Xrow, int ld) {
   constexpr uint32_t kRowBytes = kGjMaxN * sizeof(double);
   extern __shared__ __align__(128) unsigned char gj_smem_raw[];
   GjSmem& sm = *reinterpret_cast<GjSmem*>(gj_smem_raw);
@@ -282,7 +294,7 @@ gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, d
           if (owner) {
             // pivot row = this warp's row t: scale it (a_kj / p, a_kk <- 1 / p), eliminate it from the warp's other three
             // rows straight from registers (every lane holds the same columns of all four rows), and stage it
-            const double pinv = 1.0 / m[t];
+            const double pinv = gj::fast_rcp(m[t]);
 #pragma unroll
             for (int jj = 0; jj < kGjColsPerLane; ++jj) a[t][jj] *= pinv;
             if (lane == lk) a[t][j] = pinv;
@@ -340,12 +352,27 @@ gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, d
       for (int r = 0; r < 4; ++r)
         if (wrow + r < n && col < n) X[(size_t)(wrow + r) + (size_t)n * col] = a[r][j];
     }
+    // the same inverse ROW-major with the leading dimension the toy kernel's TMA maps want (pad column zero): the
+    // operator set-up launch disappears from the critical path between the inverse and the toy kernel
+    if (Xrow) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        if (wrow + r >= n) continue;
+#pragma unroll
+        for (int i = 0; i < kGjColsPerLane / 2; ++i) {
+          const int col = 2 * (lane + 32 * i);
+          if (col < ld)
+            *reinterpret_cast<double2*>(Xrow + (size_t)(wrow + r) * ld + col) =
+                make_double2(a[r][2 * i], col + 1 < n ? a[r][2 * i + 1] : 0.0);
+        }
+      }
+    }
   }
   gj::cluster_sync();   // no CTA may exit while its shared memory can still be the target of a remote copy or arrive
 }
 
 template <int CTAS>
-static int launch_gj_t(isr_ctx* c, int n, const double* A, double* X, double* cert) {
+static int launch_gj_t(isr_ctx* c, int n, const double* A, double* X, double* cert, double* Xrow, int ld) {
   const int warps = (n + 4 * CTAS - 1) / (4 * CTAS);   // four rows per warp, whole warps per CTA
   auto kernel = gj_inverse_kernel<CTAS>;
   ISR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GjSmem)));   // per device
@@ -360,16 +387,16 @@ static int launch_gj_t(isr_ctx* c, int n, const double* A, double* X, double* ce
   at[0].val.clusterDim.x = CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  ISR_CUDA(cudaLaunchKernelEx(&cfg, kernel, n, A, X, cert)); ISR_COUNT_LAUNCH();
+  ISR_CUDA(cudaLaunchKernelEx(&cfg, kernel, n, A, X, cert, Xrow, ld)); ISR_COUNT_LAUNCH();
   return ISR_OK;
 }
 // Cluster size: 4 CTAs hold at most 240 rows (15 arithmetic warps each), 8 and 16 CTAs spread the same rows thinner.
-static int launch_gj(isr_ctx* c, int n, const double* A, double* X, double* cert) {
+static int launch_gj(isr_ctx* c, int n, const double* A, double* X, double* cert, double* Xrow, int ld) {
   static const int forced = [] { const char* e = std::getenv("ISR_GJ_CTAS"); return e ? std::atoi(e) : 0; }();
   const int ctas = forced ? forced : kGjDefaultCtas;
-  if (ctas == 16) return launch_gj_t<16>(c, n, A, X, cert);
-  if (ctas == 4) return launch_gj_t<4>(c, n, A, X, cert);
-  return launch_gj_t<8>(c, n, A, X, cert);
+  if (ctas == 16) return launch_gj_t<16>(c, n, A, X, cert, Xrow, ld);
+  if (ctas == 4) return launch_gj_t<4>(c, n, A, X, cert, Xrow, ld);
+  return launch_gj_t<8>(c, n, A, X, cert, Xrow, ld);
 }
 
 // Ainv = A^-1.  A (column-major, preserved) is factored in `lu` (n x n scratch, destroyed); `prod` is n x n scratch.
@@ -389,8 +416,11 @@ static int launch_gj(isr_ctx* c, int n, const double* A, double* X, double* cert
 // lower_hint: the caller knows A to be lower triangular (selects the triangular solve for N > kGjMaxRows).
 // cert_host: 8 page-locked doubles owned by the caller (kPinCert / kPinInfo slots); cert_dev: 3 doubles of device memory
 // owned by the caller (kernels may fold the verdict into a collective).
+// Ainv_rowmajor (optional, [n][ld], ld = n rounded up to even): the cluster Gauss-Jordan kernel also writes the inverse in
+// the row-major padded layout of the toy kernel's operators; *wrote_rowmajor tells whether this path did.
 int inverse_enqueue(isr_ctx* c, int n, const double* A, double* lu, double* prod, double* Ainv, DevBuf<double>& work,
-                    DevBuf<int>& ipiv, DevBuf<int>& info, bool lower_hint, double* cert_host, double* cert_dev) {
+                    DevBuf<int>& ipiv, DevBuf<int>& info, bool lower_hint, double* cert_host, double* cert_dev,
+                    double* Ainv_rowmajor, int ld, bool* wrote_rowmajor) {
   int lwork = 0;
   const size_t bytes = sizeof(double) * (size_t)n * n;
   ISR_CUSOLVER(cusolverDnDgetrf_bufferSize(c->solver, n, n, lu, n, &lwork));
@@ -400,8 +430,10 @@ int inverse_enqueue(isr_ctx* c, int n, const double* A, double* lu, double* prod
   double* resid_dev = cert_dev;
   int* h_info = reinterpret_cast<int*>(cert_host + kPinInfo);
   h_info[0] = h_info[1] = 0;
+  if (wrote_rowmajor) *wrote_rowmajor = false;
   if (n <= kGjMaxRows) {
-    ISR_TRY(launch_gj(c, n, A, Ainv, resid_dev));
+    ISR_TRY(launch_gj(c, n, A, Ainv, resid_dev, Ainv_rowmajor, ld));
+    if (wrote_rowmajor) *wrote_rowmajor = Ainv_rowmajor != nullptr;
   } else if (lower_hint) {
     // the caller knows A to be lower triangular (linear interpolation without spread): blocked triangular inverse
     // (tri_inverse.cu); a wrong hint fails the certificate below like any other bad inverse

@@ -12,7 +12,8 @@ void scale_rows(cudaStream_t st, int n, const double* A, const double* s, int in
 int gemm(isr_ctx* c, bool ta, bool tb, int n, const double* A, const double* B, double* C);
 int gemv(isr_ctx* c, bool ta, int n, const double* A, const double* x, double* y);
 int inverse_enqueue(isr_ctx* c, int n, const double* A, double* lu, double* prod, double* Ainv, DevBuf<double>& work,
-                    DevBuf<int>& ipiv, DevBuf<int>& info, bool lower_hint, double* cert_host, double* cert_dev);
+                    DevBuf<int>& ipiv, DevBuf<int>& info, bool lower_hint, double* cert_host, double* cert_dev,
+                    double* Ainv_rowmajor = nullptr, int ld = 0, bool* wrote_rowmajor = nullptr);
 bool inverse_certified(const double* cert_host, int n, int* tri);
 int inverse_pivoted(isr_ctx* c, int n, const double* A, double* lu, double* Ainv, DevBuf<double>& work, DevBuf<int>& ipiv,
                     DevBuf<int>& info, double* cert_host, double* cert_dev, int* tri);

@@ -12,6 +12,10 @@
 
 namespace isr {
 
+__global__ void rop_kernel(int n, int ld, const double* __restrict__ G, const double* __restrict__ err, double* __restrict__ R,
+                           double* __restrict__ Rop);
+__global__ void sop_kernel(int n, int ld, const double* __restrict__ Ginv, double* __restrict__ Sop);
+
 // Factor for a given error vector (W = diag(err^-2), src/BaseISRSolver.cpp:355-357):
 //   Ginv = G^-1                      (b = Ginv v  ==  COD(G).solve(v) for a full-rank G)
 //   R    = W^(1/2) G                 (Cov^-1 = G^T W G = R^T R)
@@ -47,10 +51,18 @@ int factor_enqueue(isr_problem* p, const double* vcs_err) {
   ISR_TRY(p->d_cert_prod.reserve(nn));
   ISR_TRY(p->d_cert.reserve(4));
   if (!p->pin_cert) ISR_CUDA(cudaMallocHost((void**)&p->pin_cert, sizeof(double) * 8));
+  // R = W^(1/2) G and its row-major copy do not depend on the inverse: side stream, under the inverse
+  ISR_CUDA(cudaEventRecord(c->ev_fork2, st));
+  ISR_CUDA(cudaStreamWaitEvent(c->aux_stream, c->ev_fork2, 0));
+  rop_kernel<<<(n * ld + 255) / 256, 256, 0, c->aux_stream>>>(n, ld, p->d_G.p, p->d_werr.p, p->d_R.p, p->d_Rop.p); ISR_COUNT_LAUNCH();
+  ISR_CUDA(cudaEventRecord(c->ev_rop, c->aux_stream));
+  bool sop_written = false;
   ISR_TRY(inverse_enqueue(c, n, p->d_G.p, p->d_tmp.p, p->d_cert_prod.p, p->d_Ginv.p, p->d_work, p->d_ipiv, p->d_info, p->G_lower,
-                          p->pin_cert, p->d_cert.p));
+                          p->pin_cert, p->d_cert.p, p->d_Sop.p, ld, &sop_written));
   p->cert_dev = p->d_cert.p;
-  ISR_TRY(launch_sle_operators(p));
+  if (!sop_written) { sop_kernel<<<(n * ld + 255) / 256, 256, 0, st>>>(n, ld, p->d_Ginv.p, p->d_Sop.p); ISR_COUNT_LAUNCH(); }
+  ISR_CUDA(cudaStreamWaitEvent(st, c->ev_rop, 0));
+  ISR_CUDA(cudaGetLastError());
   p->factored = true;
   p->cert_pending = true;
   p->cov_ready = false;      // Cov / G^T W G are formed on first use (ensure_cov): the toy path never reads them
@@ -130,6 +142,28 @@ __global__ void sle_operators_kernel(int n, int ld, const double* __restrict__ G
   }
   Sop[idx] = sv;
   Rop[idx] = rv;
+}
+
+// The two halves of sle_operators_kernel, for the factorisation's two streams: Rop / R need only G and the errors, Sop only
+// the inverse.
+__global__ void rop_kernel(int n, int ld, const double* __restrict__ G, const double* __restrict__ err, double* __restrict__ R,
+                           double* __restrict__ Rop) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * ld) return;
+  const int i = idx / ld, j = idx % ld;
+  double rv = 0.0;
+  if (j < n) {
+    const size_t cm = (size_t)i + (size_t)n * j;
+    rv = G[cm] / err[i];
+    R[cm] = rv;
+  }
+  Rop[idx] = rv;
+}
+__global__ void sop_kernel(int n, int ld, const double* __restrict__ Ginv, double* __restrict__ Sop) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * ld) return;
+  const int i = idx / ld, j = idx % ld;
+  Sop[idx] = j < n ? Ginv[(size_t)i + (size_t)n * j] : 0.0;
 }
 
 // Operators the toy kernel consumes: row-major, leading dimension padded to even, pad column zero.
