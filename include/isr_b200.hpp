@@ -79,6 +79,17 @@ class Context {
   }
 };
 
+// One isr_group (all requested GPUs of the box, one host thread + context each, NCCL communicator) per process and size.
+class GpuGroup {
+ public:
+  static isr_group* get(int ngpu) {
+    static std::vector<isr_group*> groups(65, nullptr);
+    if (ngpu < 1 || ngpu > 64) throw std::invalid_argument("GpuGroup: ngpu out of range");
+    if (!groups[ngpu]) check(isr_group_create(ngpu, nullptr, &groups[ngpu]));
+    return groups[ngpu];
+  }
+};
+
 struct Chi2TestArgs { int n; double initialChi2Ampl; std::string outputPath; };   // include/ISRSolverStructs.hpp
 struct Chi2TestResult { std::vector<double> chi2; std::vector<float> hist; double chi2Min, chi2Max; };
 struct RatioTestResult { std::vector<double> means, meanErrors; std::vector<uint32_t> hist; };
@@ -103,6 +114,17 @@ class BaseISRSolver {   // include/BaseISRSolver.hpp:30-120
     isr_eps_desc d = _eff.desc();
     check(isr_problem_create(_ctx, (int)_n, _ecm.data(), _energyT, 0, nullptr, _eff.kind == ISR_EPS_ONE ? nullptr : &d, &_p));
   }
+  // The reference's own constructor signature (include/BaseISRSolver.hpp:33-40): the efficiency is an arbitrary callable
+  // eps(x, E).  It cannot run inside a kernel, so it is SAMPLED: evalEqMatrix asks the library for the quadrature nodes
+  // (isr_assemble_nodes), evaluates the callable there on the host and feeds the values back (isr_assemble_sampled).
+  // efficiencyBreaks: x values where the callable jumps (the panels are cut there; smooth callables need none).
+  BaseISRSolver(std::size_t numberOfPoints, const double* energy, const double* visibleCS, const double* energyErr,
+                const double* visibleCSErr, double thresholdEnergy, const std::function<double(double, double)>& efficiency,
+                const std::vector<double>& efficiencyBreaks = {}, int device = 0)
+      : BaseISRSolver(numberOfPoints, energy, visibleCS, energyErr, visibleCSErr, thresholdEnergy,
+                      breaksTable(numberOfPoints, efficiencyBreaks), device) {
+    _effFcn = efficiency;
+  }
   BaseISRSolver(const BaseISRSolver&) = delete;
   BaseISRSolver& operator=(const BaseISRSolver&) = delete;
   virtual ~BaseISRSolver() { isr_problem_destroy(_p); }
@@ -123,8 +145,27 @@ class BaseISRSolver {   // include/BaseISRSolver.hpp:30-120
   void resetVisibleCSErrors(const std::vector<double>& e) { _vcsErr = e; _factored = false; }
   void resetECMErrors(const std::vector<double>& e) { _ecmErr = e; invalidate(); }
   isr_problem* gpuProblem() { return _p; }
+  const Efficiency& efficiencyTable() const { return _eff; }
+  bool hasCallableEfficiency() const { return (bool)_effFcn; }
 
  protected:
+  // a per-point table of ones whose bin edges are the callable's declared jumps (its values are ignored in sampled mode)
+  static Efficiency breaksTable(std::size_t n, const std::vector<double>& breaks) {
+    Efficiency e;
+    if (breaks.empty()) return e;
+    std::vector<double> b(breaks);
+    std::sort(b.begin(), b.end());
+    b.erase(std::unique(b.begin(), b.end()), b.end());
+    e.kind = ISR_EPS_ROW_TABLE;
+    e.xedges.push_back(std::min(0.0, b.front()) - 1.0);
+    for (double v : b) e.xedges.push_back(v);
+    e.xedges.push_back(std::max(1.0, b.back()) + 1.0);
+    e.nx = (int)e.xedges.size() - 1;
+    e.xlo = e.xedges.front(); e.xhi = e.xedges.back();
+    e.values.assign(n * (std::size_t)(e.nx + 2), 1.0);
+    return e;
+  }
+  std::function<double(double, double)> _effFcn;
   virtual void invalidate() { _isEqMatrixPrepared = false; _factored = false; }
   std::size_t _n;
   double _energyT;
@@ -143,11 +184,24 @@ class ISRSolverSLE : public BaseISRSolver {   // include/ISRSolverSLE.hpp
     std::vector<int> flat;
     for (const auto& t : s) { flat.push_back(std::get<0>(t)); flat.push_back(std::get<1>(t)); flat.push_back(std::get<2>(t)); }
     check(isr_problem_set_ranges(_p, (int)s.size(), flat.data()));
+    _ranges = flat;
     invalidate();
   }
+  const std::vector<int>& rangeSettings() const { return _ranges; }
   void evalEqMatrix() {   // src/ISRSolverSLE.cpp:138-149
     _integralOperatorMatrix = Matrix((int)_n, (int)_n);
-    check(isr_assemble(_p, _energySpread ? _ecmErr.data() : nullptr, _integralOperatorMatrix.data()));
+    const double* spread = _energySpread ? _ecmErr.data() : nullptr;
+    if (_effFcn) {      // callable efficiency: sampled at the quadrature nodes
+      int64_t nn = 0;
+      check(isr_assemble_nodes(_p, 0, nullptr, nullptr, &nn));
+      std::vector<double> x((std::size_t)nn), eps((std::size_t)nn);
+      std::vector<int> row((std::size_t)nn);
+      check(isr_assemble_nodes(_p, nn, x.data(), row.data(), &nn));
+      for (int64_t q = 0; q < nn; ++q) eps[(std::size_t)q] = _effFcn(x[(std::size_t)q], _ecm[(std::size_t)row[(std::size_t)q]]);
+      check(isr_assemble_sampled(_p, nn, eps.data(), spread, _integralOperatorMatrix.data()));
+    } else {
+      check(isr_assemble(_p, spread, _integralOperatorMatrix.data()));
+    }
     _isEqMatrixPrepared = true;
     _factored = false;
   }
@@ -197,6 +251,15 @@ class ISRSolverSLE : public BaseISRSolver {   // include/ISRSolverSLE.hpp
     selectForToys();
     check(isr_toy_batch(_p, T, V, bcs0, chi2, sumBcs, ratioStats, ratioHist, bcsOut));
   }
+  // a whole chi2 / ratio test on the selected solver in one stream-ordered call (isr_chi2_test)
+  virtual void chi2TestCall(isr_chi2_test_args& a) {
+    selectForToys();
+    a.flags &= ~(ISR_TEST_ASSEMBLE | ISR_TEST_FACTOR);      // the solver's own state is current
+    check(isr_chi2_test(_p, &a));
+  }
+  // true if the solver is fully described by (energies, ranges, efficiency table, spread, errors): such a solver can be
+  // replicated on the GPUs of an isr_group
+  virtual bool replicable() const { return !_effFcn; }
 
  protected:
   virtual void ensureFactored() {
@@ -205,6 +268,7 @@ class ISRSolverSLE : public BaseISRSolver {   // include/ISRSolverSLE.hpp
   }
   virtual void selectForToys() { ensureFactored(); }
   Matrix _integralOperatorMatrix, _covMatrixBornCS;
+  std::vector<int> _ranges;
 };
 
 // IterISRInterpSolver (include/IterISRInterpSolver.hpp; src/IterISRInterpSolver.cpp:45-65): the iterative
@@ -267,6 +331,7 @@ class ISRSolverSLE2 : public ISRSolverSLE {
 class ISRSolverTikhonov : public ISRSolverSLE {   // include/ISRSolverTikhonov.hpp
  public:
   using ISRSolverSLE::ISRSolverSLE;
+  bool replicable() const override { return false; }      // (the selected A+_lambda lives in this problem only)
   double getLambda() const { return _lambda; }
   void setLambda(double l) { _lambda = l; }
   bool isDerivNorm2RegIsEnabled() const { return _derivReg; }
@@ -341,6 +406,10 @@ class ISRSolverTSVD : public ISRSolverSLE {   // include/ISRSolverTSVD.hpp
   ISRSolverTSVD(std::size_t n, const double* e, const double* v, const double* ee, const double* ve, double thr,
                 const Efficiency& eff = Efficiency(), int device = 0)
       : ISRSolverSLE(n, e, v, ee, ve, thr, eff, device), _upperTSVDIndex((int)n) {}
+  ISRSolverTSVD(std::size_t n, const double* e, const double* v, const double* ee, const double* ve, double thr,
+                const std::function<double(double, double)>& eff, const std::vector<double>& effBreaks = {}, int device = 0)
+      : ISRSolverSLE(n, e, v, ee, ve, thr, eff, effBreaks, device), _upperTSVDIndex((int)n) {}
+  bool replicable() const override { return false; }
   void setUpperTSVDIndex(int k) { _upperTSVDIndex = k; }
   int getUpperTSVDIndex() const { return _upperTSVDIndex; }
   void enableKeepOne() { _keepOne = true; }
@@ -434,16 +503,51 @@ inline std::vector<double> randomDrawVisCS(const std::vector<double>& vcs, const
 }
 
 // chi2Test (src/Chi2Test.cpp:29-104) on caller-supplied toys (toy-major n x N); the ROOT fit/file are left to
-// the caller.  The histogram is TH1F(128, min, max) with under/overflow cells (130 floats).
+// the caller.  The histogram is TH1F(128, min, max) with under/overflow cells (130 floats).  One isr_chi2_test call:
+// toys, range and cells in one stream-ordered chain.
 inline Chi2TestResult chi2Test(ISRSolverSLE* solver, const Chi2TestArgs& args, const std::vector<double>& toys,
                                const std::vector<double>& bcs0) {
   Chi2TestResult r;
   r.chi2.resize(args.n);
-  solver->toyBatch(args.n, toys.data(), bcs0.data(), r.chi2.data(), nullptr, nullptr, nullptr, nullptr);
-  std::vector<uint32_t> counts(130);
-  // range and TH1F from the chi2 values the batch left on the device (no second upload)
-  check(isr_last_chi2_minmax(solver->gpuProblem(), &r.chi2Min, &r.chi2Max));
-  check(isr_last_chi2_histogram(solver->gpuProblem(), 128, r.chi2Min, r.chi2Max, counts.data()));
+  std::vector<int64_t> counts(130);
+  double lohi[2] = {0, 0};
+  isr_chi2_test_args a{};
+  a.bcs0 = bcs0.data(); a.n_toys = args.n; a.V = toys.data(); a.nbins = 128;
+  a.chi2_out = r.chi2.data(); a.chi2_lo_hi_out = lohi; a.chi2_counts_out = counts.data();
+  solver->chi2TestCall(a);
+  r.chi2Min = lohi[0]; r.chi2Max = lohi[1];
+  r.hist.assign(counts.begin(), counts.end());
+  return r;
+}
+
+// The same test spread over the first `ngpu` GPUs of the box from this one process (isr_group: a context, a replicated
+// problem and a host thread per GPU; toys cut into contiguous slices; two small NCCL all-reduces in stream).  The
+// histogram is bit-identical to the single-GPU one.  Plain SLE solvers only (ISRSolverSLE / ISRSolverSLE2 with tabulated
+// efficiency): the problem is rebuilt from its description on every GPU.
+inline Chi2TestResult chi2TestMultiGPU(ISRSolverSLE* solver, const Chi2TestArgs& args, const std::vector<double>& toys,
+                                       const std::vector<double>& bcs0, int ngpu, std::vector<double>* sumBcs = nullptr) {
+  if (!solver->replicable()) throw std::invalid_argument("chi2TestMultiGPU: only plain SLE solvers with a tabulated efficiency can be replicated");
+  isr_group* g = GpuGroup::get(ngpu);
+  const std::size_t N = solver->getN();
+  isr_eps_desc d = solver->efficiencyTable().desc();
+  isr_gproblem* gp = nullptr;
+  const std::vector<int>& rg = solver->rangeSettings();
+  check(isr_group_problem_create(g, (int)N, solver->ecm().data(), solver->getThresholdEnergy(), (int)rg.size() / 3,
+                                 rg.empty() ? nullptr : rg.data(), solver->efficiencyTable().kind == ISR_EPS_ONE ? nullptr : &d, &gp));
+  struct Guard { isr_gproblem* p; ~Guard() { isr_group_problem_destroy(p); } } guard{gp};
+  Chi2TestResult r;
+  r.chi2.resize(args.n);
+  std::vector<int64_t> counts(130);
+  double lohi[2] = {0, 0};
+  isr_chi2_test_args a{};
+  a.flags = ISR_TEST_ASSEMBLE | ISR_TEST_FACTOR;
+  a.ecm_err = solver->isEnergySpreadEnabled() ? solver->ecmErr().data() : nullptr;
+  a.vcs_err = solver->vcsErr().data();
+  a.bcs0 = bcs0.data(); a.n_toys = args.n; a.V = toys.data(); a.nbins = 128;
+  a.chi2_out = r.chi2.data(); a.chi2_lo_hi_out = lohi; a.chi2_counts_out = counts.data();
+  if (sumBcs) { sumBcs->assign(N, 0.0); a.sum_bcs_out = sumBcs->data(); }
+  check(isr_group_chi2_test(gp, &a));
+  r.chi2Min = lohi[0]; r.chi2Max = lohi[1];
   r.hist.assign(counts.begin(), counts.end());
   return r;
 }
@@ -455,6 +559,14 @@ inline Chi2TestResult chi2TestModel(ISRSolverSLE* solver, const Chi2TestArgs& ar
   if (modelVCS.size() != modelBCS.size() || modelVCS.size() != solver->getN()) throw DifferentModelCrossSectionSizes();
   solver->solve();
   return chi2Test(solver, args, randomDrawVisCS(modelVCS, solver->vcsErr(), args.n, seed), modelBCS);
+}
+// chi2TestModel over `ngpu` GPUs: same toys (same seed), same histogram.
+inline Chi2TestResult chi2TestModel(ISRSolverSLE* solver, const Chi2TestArgs& args, const std::vector<double>& modelVCS,
+                                    const std::vector<double>& modelBCS, std::uint64_t seed, int ngpu) {
+  if (modelVCS.size() != modelBCS.size() || modelVCS.size() != solver->getN()) throw DifferentModelCrossSectionSizes();
+  if (ngpu <= 1) return chi2TestModel(solver, args, modelVCS, modelBCS, seed);
+  solver->solve();
+  return chi2TestMultiGPU(solver, args, randomDrawVisCS(modelVCS, solver->vcsErr(), args.n, seed), modelBCS, ngpu);
 }
 // chi2TestData (src/Chi2Test.cpp:160-195): the reference solution is the mean of the toy solutions around the data.
 inline Chi2TestResult chi2TestData(ISRSolverSLE* solver, const Chi2TestArgs& args, std::uint64_t seed = 20211103ull) {

@@ -6,8 +6,9 @@
 // include/PyKuraevFadin.hpp).  Host side: C++17 + pybind11; all numerical work goes through the C ABI.
 //
 // Differences from the reference module: files are .npz instead of .root (read / written
-// through numpy from here); `efficiency` is an isrsolver_b200.Efficiency table instead of a Python callable for
-// the solvers (a kernel cannot call the interpreter), while convolutionKuraevFadin keeps the callable form;
+// through numpy from here); `efficiency` is an isrsolver_b200.Efficiency table or, as in the reference, a Python
+// callable eps(x, energy) -- the latter is sampled at the quadrature nodes on the host (a kernel cannot call the
+// interpreter); convolutionKuraevFadin keeps the callable form;
 // getters return NumPy views that keep the solver alive (the reference's views dangle when it dies).
 #include <pybind11/functional.h>
 #include <pybind11/numpy.h>
@@ -26,8 +27,7 @@ static Efficiency to_efficiency(const py::object& o) {
   Efficiency e;
   if (o.is_none()) return e;
   if (!py::hasattr(o, "kind") || !py::hasattr(o, "values"))
-    throw py::type_error("efficiency must be an isrsolver_b200.Efficiency table (a Python callable cannot be evaluated "
-                         "inside a CUDA kernel); see INTEGRATION.md");
+    throw py::type_error("efficiency must be an isrsolver_b200.Efficiency table or a callable eps(x, energy)");
   const std::string kind = o.attr("kind").cast<std::string>();
   e.kind = kind == "one" ? ISR_EPS_ONE : kind == "row_table" ? ISR_EPS_ROW_TABLE : kind == "table_2d" ? ISR_EPS_TABLE_2D : ISR_EPS_E_ONLY;
   e.nx = o.attr("nx").cast<int>(); e.ne = o.attr("ne").cast<int>();
@@ -69,8 +69,24 @@ static std::unique_ptr<S> make_solver(int n, const py::object& energy, const py:
   auto e = vec(energy, n, "energy"), v = vec(vcs, n, "vcs"), ve = vec(vcs_err, n, "vcs_err");
   std::vector<double> ee;
   if (!energy_err.is_none()) ee = vec(energy_err, n, "energy_err");
-  auto s = std::make_unique<S>((std::size_t)n, e.data(), v.data(), ee.empty() ? nullptr : ee.data(), ve.data(), threshold,
-                               to_efficiency(efficiency));
+  // A Python callable efficiency(x, energy), as the reference's constructor takes it (include/PyISRSolver.hpp:186-197):
+  // it is wrapped into the std::function overload of the C++ mirror, which samples it at the quadrature nodes on the host
+  // (the reference calls it from inside every GSL integrand evaluation).  An optional attribute `breaks` on the callable
+  // lists the x values where it jumps.
+  std::unique_ptr<S> s;
+  if (!efficiency.is_none() && !py::hasattr(efficiency, "kind") && PyCallable_Check(efficiency.ptr())) {
+    std::vector<double> breaks;
+    if (py::hasattr(efficiency, "breaks")) breaks = efficiency.attr("breaks").cast<std::vector<double>>();
+    py::object fn = efficiency;
+    std::function<double(double, double)> f = [fn](double x, double en) {
+      py::gil_scoped_acquire gil;
+      return fn(x, en).template cast<double>();
+    };
+    s = std::make_unique<S>((std::size_t)n, e.data(), v.data(), ee.empty() ? nullptr : ee.data(), ve.data(), threshold, f, breaks);
+  } else {
+    s = std::make_unique<S>((std::size_t)n, e.data(), v.data(), ee.empty() ? nullptr : ee.data(), ve.data(), threshold,
+                            to_efficiency(efficiency));
+  }
   if (enableEnergySpread) s->enableEnergySpread(); else s->disableEnergySpread();
   return s;
 }

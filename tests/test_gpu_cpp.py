@@ -8,11 +8,11 @@ import pytest
 from conftest import ROOT, load_golden
 
 
-def _build(tmp_path):
-    exe = tmp_path / "test_classes"
+def _build(tmp_path, name="test_classes"):
+    exe = tmp_path / name
     lib_dir = os.path.join(ROOT, "isrsolver_b200")
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"),
-                           os.path.join(ROOT, "tests", "cpp", "test_classes.cpp"), "-L", lib_dir, "-lisr_b200",
+                           os.path.join(ROOT, "tests", "cpp", name + ".cpp"), "-L", lib_dir, "-lisr_b200",
                            f"-Wl,-rpath,{lib_dir}", "-Wl,-rpath,/usr/local/cuda/lib64", "-o", str(exe)])
     return exe
 
@@ -20,6 +20,34 @@ def _build(tmp_path):
 def test_cpp_mirror_compiles_and_links(tmp_path):
     """No GPU needed: the class mirror compiles against the header and links against the library."""
     assert _build(tmp_path).exists()
+    assert _build(tmp_path, "test_group").exists()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ngpu", [1, 2, 4])
+def test_cpp_chi2_test_model_on_several_gpus(tmp_path, ngpu):
+    """a C++ chi2TestModel caller spreads the test over the GPUs of the box from one process; results
+    bit-identical to one GPU.  (ngpu = 1 runs the group machinery -- threads, communicator of one -- on any box.)"""
+    import torch
+    import isrsolver_b200 as isr
+    if torch.cuda.device_count() < ngpu:
+        pytest.skip(f"needs {ngpu} GPUs")
+    g = load_golden("c2_sle_n40_cspline")
+    exe = _build(tmp_path, "test_group")
+    for k in ("ecm", "vcs", "vcs_err", "bcs0"):
+        np.ascontiguousarray(g[k], dtype=np.float64).tofile(tmp_path / f"{k}.bin")
+    out = subprocess.run([str(exe), str(tmp_path), str(ngpu)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "group ok" in out.stdout and "group_hist_sum 30011" in out.stdout
+    val = lambda key: [l for l in out.stdout.splitlines() if l.startswith(key + " ")][0].split()[1:]
+    assert float(val("callable_half")[0]) < 1e-15
+    n = len(g["ecm"])
+    Gc = np.fromfile(tmp_path / "out_G_callable.bin").reshape(n, n).T
+    m = isr.ISRSolverSLE(n, g["ecm"], g["vcs"], None, g["vcs_err"], 0.827,
+                         efficiency=lambda x, e: 0.3 + 0.5 * np.exp(-30.0 * x) * (1.0 - 0.1 * (e - 1.5)))
+    m.set_interp_settings([(False, 0, 0), (True, 1, n - 1)])
+    m.eval_equation_matrix()
+    np.testing.assert_allclose(Gc, m.intop_matrix(), rtol=1e-13, atol=1e-16)
 
 
 @pytest.mark.gpu

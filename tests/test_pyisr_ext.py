@@ -112,3 +112,43 @@ def test_compiled_pyisr_tikhonov_and_tsvd(oracle):
     v.enable_keepone(); v.solve()
     np.testing.assert_allclose(v.bcs(), g["tsvd_bcs_keepone"], rtol=1e-6, atol=1e-8 * np.abs(g["tsvd_bcs"]).max())
     assert v.upper_TSVD_index == int(g["tsvd_k"])
+
+
+@pytest.mark.gpu
+def test_compiled_pyisr_accepts_a_callable_efficiency():
+    """the reference's constructor takes efficiency as a Python callable (include/PyISRSolver.hpp:186-197);
+    the compiled module wraps it into the std::function overload of the C++ mirror (sampled at the quadrature nodes).
+    Same matrix as the ctypes mirror running the same callable, and as the compiled reference."""
+    import math
+    import isrsolver_b200 as isr
+    from isrsolver_b200 import PyISR
+    from oracle import isr_ref as R
+    n = 12
+    ecm = np.linspace(1.18, 2.0, n); thr = 0.827
+    eff = lambda x, e: 0.3 + 0.5 * math.exp(-30.0 * x) * (1.0 - 0.1 * (e - 1.5))
+    st = [(False, 0, 2), (True, 3, n - 1)]
+    s = PyISR.ISRSolverSLE(n=n, energy=ecm, vcs=np.ones(n), energy_err=None, vcs_err=np.ones(n), threshold=thr, efficiency=eff)
+    s.set_interp_settings(st)
+    s.eval_equation_matrix()
+    G = s.intop_matrix()
+    m = isr.ISRSolverSLE(n, ecm, np.ones(n), None, np.ones(n), thr, efficiency=eff)
+    m.set_interp_settings(st)
+    m.eval_equation_matrix()
+    np.testing.assert_array_equal(G, m.intop_matrix())
+    if R.available():
+        Gr = R.RefInterp(ecm, thr, st).eval_eq_matrix_callable(eff)
+        assert np.all(np.abs(G - Gr) <= 1e-9 * np.abs(Gr).max(1, keepdims=True) + 2e-12)
+    # a step efficiency with its declared jump == the two-bin table
+    class Step:
+        breaks = [0.1]
+        def __call__(self, x, e):
+            return (0.8 if x < 0.1 else 0.4) * (1.0 + 0.05 * (e - 1.5))
+    s2 = PyISR.ISRSolverSLE(n=n, energy=ecm, vcs=np.ones(n), energy_err=None, vcs_err=np.ones(n), threshold=thr, efficiency=Step())
+    s2.set_interp_settings(st)
+    s2.eval_equation_matrix()
+    vals = np.zeros((n, 4)); vals[:, 1] = 0.8 * (1.0 + 0.05 * (ecm - 1.5)); vals[:, 2] = 0.4 * (1.0 + 0.05 * (ecm - 1.5))
+    t = isr.ISRSolverSLE(n, ecm, np.ones(n), None, np.ones(n), thr,
+                         efficiency=isr.Efficiency("row_table", values=vals, nx=2, xedges=np.array([0.0, 0.1, 1.0])))
+    t.set_interp_settings(st)
+    t.eval_equation_matrix()
+    np.testing.assert_allclose(s2.intop_matrix(), t.intop_matrix(), rtol=1e-12, atol=1e-15)
