@@ -515,11 +515,12 @@ def other_chi2_tests(lib, ctx, stream, torch, dev):
 
 
 def tikhonov_c4(lib, ctx, torch, comm=None, rank=0, world=1):
-    """BASELINE config C4 on this rank: ISRSolverTikhonov, N = 200, cubic, 2 MeV energy spread, derivative regulariser;
-    the generalised eigen-system once (isr_tikhonov_prepare), then the chi2 test of 10k toys for 1024 lambdas -- the
-    whole grid, and the 128-lambda slice one of 8 GPUs gets -- through the host-buffer ABI with the toys in pinned
-    memory (H2D of V and D2H of the per-lambda summaries inside the timed call; wall clock around synchronous calls,
-    mean of 5 after 2 warm-ups)."""
+    """BASELINE config C4, every rank: ISRSolverTikhonov, N = 200, cubic, 2 MeV energy spread, derivative regulariser;
+    the generalised eigen-system once (isr_tikhonov_prepare), then the chi2 test of 10^4 toys for 1024 lambdas with the
+    TOYS sharded over the ranks (isr_tikhonov_chi2_scan: 10^4 / world toys per GPU from page-locked host memory, H2D and
+    D2H inside the call, per-lambda ranges by one all-reduce(MIN), cells and sums by one all-reduce(SUM)).  Wall clock
+    around synchronous calls, mean of 5 after 2 warm-ups, max over ranks."""
+    import torch.distributed as dist
     from isrsolver_b200 import _lib as L
     n, T, Lm = 200, 10000, 1024
     ecm = np.linspace(E_MIN, E_MAX, n)
@@ -532,30 +533,54 @@ def tikhonov_c4(lib, ctx, torch, comm=None, rank=0, world=1):
     bcs0 = bw_born(ecm); vcs = G.T @ bcs0; err = 0.05 * vcs
     lam = 1e-9 * (1e9) ** (np.arange(Lm) / (Lm - 1))          # src/isrsolver-LCurve-plot.cpp:127-132
     rng = np.random.default_rng(20211103)
-    Vp = torch.empty((T, n), dtype=torch.float64, pin_memory=True)
-    Vp.copy_(torch.from_numpy(vcs[None, :] + err[None, :] * rng.standard_normal((T, n))))
-    Vptr = C.cast(Vp.data_ptr(), C.POINTER(C.c_double))
+    Vall = vcs[None, :] + err[None, :] * rng.standard_normal((T, n))
+    t0, t1 = rank * T // world, (rank + 1) * T // world       # this rank's toys
+    vptr = C.c_void_p()
+    L.check(lib.isr_host_alloc(ctx, max(t1 - t0, 1) * n * 8, C.byref(vptr)))
+    Vp = np.ctypeslib.as_array(C.cast(vptr, C.POINTER(C.c_double)), shape=(max(t1 - t0, 1), n))
+    Vp[:t1 - t0] = Vall[t0:t1]
     stats = np.empty((Lm, 3)); counts = np.zeros((Lm, 130), dtype=np.uint32)
+    total = C.c_int64()
 
     def wall(fn, reps=5):
         for _ in range(2):
             fn()
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
+        t_0 = time.perf_counter()
         for _ in range(reps):
             fn()
         torch.cuda.synchronize()
-        return (time.perf_counter() - t0) / reps * 1e3
+        ms = (time.perf_counter() - t_0) / reps * 1e3
+        if world > 1:
+            tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        return ms
     prep = wall(lambda: L.check(lib.isr_tikhonov_prepare(p, L.dptr(err), 1)))
-    full = wall(lambda: L.check(lib.isr_tikhonov_toy_scan_hist(p, Lm, L.dptr(lam), T, Vptr, L.dptr(bcs0), 128, L.dptr(stats), L.uptr(counts))))
-    assert int(counts.sum()) == Lm * T
-    part = wall(lambda: L.check(lib.isr_tikhonov_toy_scan_hist(p, Lm // 8, L.dptr(lam), T, Vptr, L.dptr(bcs0), 128, L.dptr(stats), L.uptr(counts))))
-    lc = [np.empty(Lm) for _ in range(4)]
-    lcurve = wall(lambda: L.check(lib.isr_tikhonov_scan(p, Lm, L.dptr(lam), L.dptr(vcs), L.dptr(lc[0]), L.dptr(lc[1]), L.dptr(lc[2]), L.dptr(lc[3]), None)))
+    a = L.TikhonovScanArgs()
+    a.flags, a.deriv_reg, a.n_lambda, a.lambda_, a.n_toys = 0, 1, Lm, L.dptr(lam), t1 - t0
+    a.V, a.bcs0, a.nbins, a.comm = C.cast(vptr, C.POINTER(C.c_double)), L.dptr(bcs0), 128, comm
+    a.stats_out, a.counts_out, a.total_toys_out = L.dptr(stats), L.uptr(counts), C.pointer(total)
+    full = wall(lambda: L.check(lib.isr_tikhonov_chi2_scan(p, C.byref(a))))
+    assert int(counts.sum()) == Lm * T and total.value == T
+    a.flags, a.vcs_err = L.ISR_TEST_FACTOR, L.dptr(err)
+    both = wall(lambda: L.check(lib.isr_tikhonov_chi2_scan(p, C.byref(a))))
+    out = {"n_points": n, "lambdas": Lm, "toys_per_lambda": T, "toys_per_gpu": t1 - t0, "prepare_ms": prep,
+           "chi2_test_1024_lambdas_ms": full, "pairs_per_s": Lm * T / (full * 1e-3),
+           "eigen_system_plus_chi2_test_ms": both,
+           "note": "toys sharded over the GPUs (isr_tikhonov_chi2_scan); the eigen-system (cuSOLVER sygvd) is replicated; "
+                   "eigen_system_plus_chi2_test_ms = both in one call, the H2D of the toys under the eigen-system"}
+    if rank == 0:
+        lc = [np.empty(Lm) for _ in range(4)]
+        t_0 = time.perf_counter()
+        for _ in range(5):
+            L.check(lib.isr_tikhonov_scan(p, Lm, L.dptr(lam), L.dptr(vcs), L.dptr(lc[0]), L.dptr(lc[1]), L.dptr(lc[2]), L.dptr(lc[3]), None))
+        out["lcurve_1024_lambdas_ms"] = (time.perf_counter() - t_0) / 5 * 1e3
+    lib.isr_host_free(vptr)
     lib.isr_problem_destroy(p)
-    return {"n_points": n, "lambdas": Lm, "toys_per_lambda": T, "prepare_ms": prep, "lcurve_1024_lambdas_ms": lcurve,
-            "chi2_test_1024_lambdas_ms": full, "pairs_per_s": Lm * T / (full * 1e-3),
-            "chi2_test_128_lambdas_ms": part, "note": "128 lambdas = the slice of one of 8 GPUs (toy_scan_hist_sharded)"}
+    return out
 
 
 def cpu_baseline(n, G, bcs0, vcs, err):

@@ -307,6 +307,29 @@ int isr_tikhonov_toy_scan_dev(isr_problem* p, int64_t L, const double* lambda, i
  * TH1F(nbins, min_l, max_l) cells (under/overflow included).  The L x T chi2 matrix never leaves the GPU. */
 int isr_tikhonov_toy_scan_hist(isr_problem* p, int64_t L, const double* lambda, int64_t T, const double* V,
                                const double* bcs0, int nbins, double* stats_out, uint32_t* counts_out);
+/* The same per-lambda chi2 test with the TOYS sharded over the ranks of a communicator (BASELINE config C4 on 2/4/8 GPUs):
+ * every rank passes its slice of the toys (host V or device V_dev; n_toys may be 0); the per-lambda {min, max, mean} and
+ * TH1F cells returned are GLOBAL and identical on every rank -- one all-reduce(MIN) of 2 L doubles for the ranges, one
+ * all-reduce(SUM) of a packed FP64 buffer for cells and sums.  flags: ISR_TEST_ASSEMBLE (re-assemble with ecm_err first),
+ * ISR_TEST_FACTOR (isr_tikhonov_prepare for vcs_err / deriv_reg first; the toys are copied meanwhile). */
+typedef struct {
+  int flags;
+  const double* ecm_err;   /* N or NULL */
+  const double* vcs_err;   /* N (ISR_TEST_FACTOR) */
+  int deriv_reg;
+  int64_t n_lambda;
+  const double* lambda;
+  int64_t n_toys;          /* this rank's share */
+  const double* V;         /* host, toy-major n_toys x N, or NULL */
+  const double* V_dev;     /* device, or NULL */
+  const double* bcs0;      /* N */
+  int nbins;
+  isr_comm* comm;          /* NULL: this GPU only */
+  double* stats_out;       /* L x 3 {min, max, mean}, or NULL */
+  uint32_t* counts_out;    /* L x (nbins + 2), or NULL */
+  int64_t* total_toys_out; /* or NULL */
+} isr_tikhonov_scan_args;
+int isr_tikhonov_chi2_scan(isr_problem* p, const isr_tikhonov_scan_args* args);
 /* (lambda, toy) scan variant: 0 (default) = chi2 as a quadratic form in lambda from two dot products per toy
  * (O(1) per pair, bound by writing the output); 1 = the direct O(N)-per-pair kernel (kept as a cross-check). */
 int isr_set_scan_kernel(isr_problem* p, int variant);

@@ -51,6 +51,13 @@ class Chi2TestArgs(C.Structure):
                 ("refactored_out", C.POINTER(C.c_int))]
 
 
+class TikhonovScanArgs(C.Structure):
+    """isr_tikhonov_scan_args (include/isr_b200.h): per-lambda chi2 test, toys sharded over a communicator."""
+    _fields_ = [("flags", C.c_int), ("ecm_err", _dp), ("vcs_err", _dp), ("deriv_reg", C.c_int), ("n_lambda", _i64),
+                ("lambda_", _dp), ("n_toys", _i64), ("V", _dp), ("V_dev", _vp), ("bcs0", _dp), ("nbins", C.c_int),
+                ("comm", _vp), ("stats_out", _dp), ("counts_out", _up), ("total_toys_out", _i64p)]
+
+
 ISR_TEST_ASSEMBLE, ISR_TEST_FACTOR, ISR_TEST_RATIO = 1, 2, 4
 ISR_COMM_ID_BYTES = 128
 
@@ -126,6 +133,7 @@ SIGNATURES = {
     "isr_tikhonov_toy_scan": (C.c_int, [_vp, _i64, _dp, _i64, _dp, _dp, _dp]),
     "isr_tikhonov_toy_scan_dev": (C.c_int, [_vp, _i64, _dp, _i64, _vp, _dp, _vp]),
     "isr_tikhonov_toy_scan_hist": (C.c_int, [_vp, _i64, _dp, _i64, _dp, _dp, C.c_int, _dp, _up]),
+    "isr_tikhonov_chi2_scan": (C.c_int, [_vp, C.POINTER(TikhonovScanArgs)]),
     "isr_set_scan_kernel": (C.c_int, [_vp, C.c_int]),
     "isr_tikhonov_select": (C.c_int, [_vp, C.c_double]),
     "isr_get_regulariser": (C.c_int, [_vp, _dp]),

@@ -667,6 +667,12 @@ int isr_tikhonov_toy_scan_hist(isr_problem* p, int64_t L, const double* lambda, 
   return tikhonov_toy_scan_hist(p, L, lambda, T, V, bcs0, nbins, stats_out, counts_out);
 }
 
+int isr_tikhonov_chi2_scan(isr_problem* p, const isr_tikhonov_scan_args* args) {
+  if (!p || !args) { set_error("NULL argument"); return ISR_EINVAL; }
+  ISR_CUDA(cudaSetDevice(p->ctx->device));
+  return tikhonov_chi2_scan(p, *args);
+}
+
 int isr_set_scan_kernel(isr_problem* p, int variant) {
   if (!p || variant < 0 || variant > 2) { set_error("isr_set_scan_kernel: bad argument"); return ISR_EINVAL; }
   p->scan_variant = variant;

@@ -112,16 +112,49 @@ static bool parse_cpulist(const std::string& s, cpu_set_t* set) {
   }
   return any;
 }
+// Fall-back when sysfs does not know the node (virtual machines report numa_node = -1): NVML's ideal CPU affinity of
+// the device -- what `nvidia-smi topo -m` prints -- bound at run time like NCCL.  Returns a pseudo node id (1000 + first
+// CPU of the set) so that callers can tell devices with different affinities apart.
+static int nvml_cpu_affinity(const char* bus, cpu_set_t* cpus) {
+  static void* h = dlopen("libnvidia-ml.so.1", RTLD_NOW);
+  if (!h) return -1;
+  typedef int (*InitFn)();
+  typedef int (*ByBusFn)(const char*, void**);
+  typedef int (*AffFn)(void*, unsigned, unsigned long*);
+  static InitFn init = (InitFn)dlsym(h, "nvmlInit_v2");
+  static ByBusFn by_bus = (ByBusFn)dlsym(h, "nvmlDeviceGetHandleByPciBusId_v2");
+  static AffFn aff = (AffFn)dlsym(h, "nvmlDeviceGetCpuAffinity");
+  if (!init || !by_bus || !aff || init() != 0) return -1;
+  void* dev = nullptr;
+  if (by_bus(bus, &dev) != 0) return -1;
+  unsigned long mask[CPU_SETSIZE / (8 * sizeof(unsigned long))] = {};
+  const unsigned words = sizeof(mask) / sizeof(mask[0]);
+  if (aff(dev, words, mask) != 0) return -1;
+  CPU_ZERO(cpus);
+  int first = -1;
+  for (unsigned w = 0; w < words; ++w)
+    for (unsigned b = 0; b < 8 * sizeof(unsigned long); ++b)
+      if (mask[w] >> b & 1ul) { const int cpu = (int)(w * 8 * sizeof(unsigned long) + b); CPU_SET(cpu, cpus); if (first < 0) first = cpu; }
+  return first < 0 ? -1 : 1000 + first;
+}
 int device_numa_node(int device, cpu_set_t* cpus) {
   char bus[32] = "";
   if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) { cudaGetLastError(); return -1; }
-  for (char* q = bus; *q; ++q) *q = (char)tolower(*q);
-  std::ifstream f(std::string("/sys/bus/pci/devices/") + bus + "/numa_node");
+  char busl[32];
+  std::strcpy(busl, bus);
+  for (char* q = busl; *q; ++q) *q = (char)tolower(*q);
+  std::ifstream f(std::string("/sys/bus/pci/devices/") + busl + "/numa_node");
   int node = -1;
-  if (!(f >> node) || node < 0) return -1;
-  std::ifstream g("/sys/devices/system/node/node" + std::to_string(node) + "/cpulist");
   std::string list;
-  if (!std::getline(g, list) || !parse_cpulist(list, cpus)) return -1;
+  bool have = false;
+  if ((f >> node) && node >= 0) {
+    std::ifstream g("/sys/devices/system/node/node" + std::to_string(node) + "/cpulist");
+    have = std::getline(g, list) && parse_cpulist(list, cpus);
+  }
+  if (!have) {
+    node = nvml_cpu_affinity(bus, cpus);
+    if (node < 0) return -1;
+  }
   // keep only CPUs this process may run on (cgroup / taskset restrictions)
   cpu_set_t allowed;
   if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0) {

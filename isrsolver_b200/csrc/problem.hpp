@@ -106,6 +106,8 @@ struct isr_problem {
   // (lambda, toy) scan scratch, grow-only
   isr::DevBuf<double> d_scan_lam, d_scan_b0, d_scan_g, d_scan_Pe, d_scan_AB, d_scan_C, d_scan_V, d_scan_chi, d_scan_stats;
   isr::DevBuf<uint32_t> d_scan_cnt;
+  isr::DevBuf<double> d_scan_pack;      // isr_tikhonov_chi2_scan: [L x cells | L sums | toys]
+  std::vector<double> h_scan_pack;
 
   // ---- SVD -----------------------------------------------------------------------------------
   bool svd_ready = false;

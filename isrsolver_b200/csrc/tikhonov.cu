@@ -14,6 +14,7 @@
 //     chi2(lambda, toy k) = (b_k - b0)^T Cov_lambda^-1 (b_k - b0) = sum_m (e_km - lambda f_m)^2,
 //         e_km = (c_km - g_m mu_m) / sqrt(mu_m),  f_m = g_m / sqrt(mu_m),  g = U^T F b0
 // so every lambda is a diagonal rescaling: O(N) per lambda and per (lambda, toy) pair.
+#include "comm.hpp"
 #include "linalg.hpp"
 #include "problem.hpp"
 #include "solve.hpp"
@@ -447,6 +448,142 @@ int tikhonov_toy_scan_hist(isr_problem* p, int64_t L, const double* lambda, int6
   if (stats_out) ISR_CUDA(cudaMemcpyAsync(stats_out, dstats.p, sizeof(double) * 3 * L, cudaMemcpyDeviceToHost, st));
   if (counts_out) ISR_CUDA(cudaMemcpyAsync(counts_out, dcnt.p, sizeof(uint32_t) * L * (nbins + 2), cudaMemcpyDeviceToHost, st));
   ISR_CUDA(cudaStreamSynchronize(st));
+  return ISR_OK;
+}
+
+// ---- the same summary with the TOYS sharded over the ranks of a communicator ----------------------------------------
+// Round 1 sharded BASELINE config C4 (1024 lambdas x 10^4 toys) over the lambda grid: the H2D of the toys and the 4 N^2 T
+// projection were then replicated on every GPU and 8 GPUs bought 1.05x.  Sharding the toys cuts both 8 ways; the per-lambda
+// range needs ONE all-reduce(MIN) of {min_l, -max_l} (2 L doubles) before the cells can be filled, and cells + sums travel
+// in ONE all-reduce(SUM) of a packed FP64 buffer [L x (nbins + 2) cells | L sums | toys] (integers are exact in FP64).
+__global__ void __launch_bounds__(256) scan_stats_kernel(int64_t T, const double* __restrict__ chi2, double* __restrict__ range,
+                                                          double* __restrict__ sums) {
+  __shared__ double s_lo[8], s_hi[8], s_sum[8];
+  const double* row = chi2 + (size_t)blockIdx.x * T;
+  double lo = INFINITY, hi = -INFINITY, sum = 0.0;
+  for (int64_t k = threadIdx.x; k < T; k += blockDim.x) {
+    const double v = row[k];
+    lo = fmin(lo, v); hi = fmax(hi, v); sum += v;
+  }
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, s));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, s));
+    sum += __shfl_xor_sync(0xffffffffu, sum, s);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { s_lo[w] = lo; s_hi[w] = hi; s_sum[w] = sum; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = s_lo[0], b = s_hi[0], c = s_sum[0];
+    for (int q = 1; q < 8; ++q) { a = fmin(a, s_lo[q]); b = fmax(b, s_hi[q]); c += s_sum[q]; }
+    range[2 * blockIdx.x] = a;
+    range[2 * blockIdx.x + 1] = -b;
+    sums[blockIdx.x] = c;
+  }
+}
+// pack[l * nb + q] = cells of lambda l against range[l] = {min, -max}; pack[L nb + l] = sums[l]; pack[L nb + L] = toys
+__global__ void __launch_bounds__(256) scan_cells_kernel(int64_t T, const double* __restrict__ chi2, int nbins,
+                                                          const double* __restrict__ range, const double* __restrict__ sums,
+                                                          int64_t L, double toys, double* __restrict__ pack) {
+  extern __shared__ uint32_t sh_cnt[];
+  const int nb = nbins + 2;
+  const double a = range[2 * blockIdx.x], b = -range[2 * blockIdx.x + 1];
+  for (int q = threadIdx.x; q < nb; q += blockDim.x) sh_cnt[q] = 0;
+  __syncthreads();
+  const double* row = chi2 + (size_t)blockIdx.x * T;
+  for (int64_t k = threadIdx.x; k < T; k += blockDim.x) {
+    const double x = row[k];
+    int bin;
+    if (x < a) bin = 0;
+    else if (!(x < b)) bin = nbins + 1;
+    else bin = 1 + (int)__ddiv_rn(__dmul_rn((double)nbins, __dsub_rn(x, a)), __dsub_rn(b, a));
+    atomicAdd(&sh_cnt[bin], 1u);
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < nb; q += blockDim.x) pack[(size_t)blockIdx.x * nb + q] = (double)sh_cnt[q];
+  if (threadIdx.x == 0) {
+    pack[(size_t)L * nb + blockIdx.x] = sums[blockIdx.x];
+    if (blockIdx.x == 0) pack[(size_t)L * nb + L] = toys;
+  }
+}
+__global__ void scan_empty_stats_kernel(int64_t L, double* __restrict__ range, double* __restrict__ sums) {
+  const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (l < L) { range[2 * l] = INFINITY; range[2 * l + 1] = INFINITY; sums[l] = 0.0; }
+}
+
+int tikhonov_chi2_scan(isr_problem* p, const isr_tikhonov_scan_args& a) {
+  const int n = p->n;
+  isr_ctx* c = p->ctx;
+  cudaStream_t st = c->stream;
+  const int64_t L = a.n_lambda, T = a.n_toys;
+  if (L <= 0 || !a.lambda || T < 0 || !a.bcs0) { set_error("isr_tikhonov_chi2_scan: bad argument"); return ISR_EINVAL; }
+  if (a.V && a.V_dev) { set_error("isr_tikhonov_chi2_scan: give V or V_dev, not both"); return ISR_EINVAL; }
+  if (T > 0 && !a.V && !a.V_dev) { set_error("isr_tikhonov_chi2_scan: no toys"); return ISR_EINVAL; }
+  if (a.nbins < 1 || a.nbins > 8190) { set_error("isr_tikhonov_chi2_scan: nbins out of range"); return ISR_EINVAL; }
+  if (a.comm && a.comm->ctx != c) { set_error("isr_tikhonov_chi2_scan: the communicator belongs to another context"); return ISR_EINVAL; }
+  const int nb = a.nbins + 2;
+  const size_t plen = (size_t)L * nb + L + 1;
+  DevBuf<double>&dV = p->d_scan_V, &dchi = p->d_scan_chi, &dstats = p->d_scan_stats, &dpack = p->d_scan_pack;
+  ISR_TRY(dchi.reserve((size_t)L * std::max<int64_t>(T, 1)));
+  ISR_TRY(dstats.reserve(3 * (size_t)L));
+  ISR_TRY(dpack.reserve(plen));
+  // the toys go up on the copy stream while the eigen-system is (re)built on the main one
+  const double* Vdev = a.V_dev;
+  if (a.V && T > 0) {
+    ISR_TRY(dV.reserve((size_t)T * n));
+    if (!p->copy_stream) {
+      ISR_CUDA(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+      for (int q = 0; q < 2; ++q) {
+        ISR_CUDA(cudaEventCreateWithFlags(&p->ev_copied[q], cudaEventDisableTiming));
+        ISR_CUDA(cudaEventCreateWithFlags(&p->ev_done[q], cudaEventDisableTiming));
+      }
+    }
+    ISR_CUDA(cudaEventRecord(c->ev_fork, st));
+    ISR_CUDA(cudaStreamWaitEvent(p->copy_stream, c->ev_fork, 0));
+    ISR_CUDA(cudaMemcpyAsync(dV.p, a.V, sizeof(double) * T * n, cudaMemcpyHostToDevice, p->copy_stream));
+    ISR_CUDA(cudaEventRecord(p->ev_copied[0], p->copy_stream));
+    Vdev = dV.p;
+  }
+  int rc = ISR_OK;
+  auto drain = [&](int code) { if (p->copy_stream) cudaStreamSynchronize(p->copy_stream); cudaStreamSynchronize(st); return code; };
+  if ((a.flags & ISR_TEST_ASSEMBLE) && (rc = assemble(p, a.ecm_err)) != ISR_OK) return drain(rc);
+  if (a.flags & ISR_TEST_FACTOR) {
+    if (!a.vcs_err) { set_error("isr_tikhonov_chi2_scan: ISR_TEST_FACTOR needs vcs_err"); return drain(ISR_EINVAL); }
+    if ((rc = tikhonov_prepare(p, a.vcs_err, a.deriv_reg)) != ISR_OK) return drain(rc);
+  }
+  if (!p->tik_ready) { set_error("isr_tikhonov_chi2_scan: no eigen-system (set ISR_TEST_FACTOR or call isr_tikhonov_prepare first)"); return drain(ISR_ESTATE); }
+  if (a.V && T > 0) ISR_CUDA(cudaStreamWaitEvent(st, p->ev_copied[0], 0));
+  double* d_range = dstats.p;          // [L][2]
+  double* d_sums = dstats.p + 2 * L;   // [L]
+  if (T > 0) {
+    if ((rc = tikhonov_toy_scan_device(p, L, a.lambda, T, Vdev, a.bcs0, dchi.p)) != ISR_OK) return drain(rc);
+    scan_stats_kernel<<<(unsigned)L, 256, 0, st>>>(T, dchi.p, d_range, d_sums); ISR_COUNT_LAUNCH();
+  } else {
+    scan_empty_stats_kernel<<<(unsigned)((L + 255) / 256), 256, 0, st>>>(L, d_range, d_sums); ISR_COUNT_LAUNCH();
+  }
+  if (a.comm && (rc = comm_allreduce(a.comm, d_range, 2 * L, 0, 1)) != ISR_OK) return drain(rc);
+  scan_cells_kernel<<<(unsigned)L, 256, sizeof(uint32_t) * nb, st>>>(T, dchi.p, a.nbins, d_range, d_sums, L, (double)T, dpack.p); ISR_COUNT_LAUNCH();
+  if (a.comm && (rc = comm_allreduce(a.comm, dpack.p, (int64_t)plen, 0, 0)) != ISR_OK) return drain(rc);
+  std::vector<double>& h = p->h_scan_pack;
+  h.resize(plen + 2 * (size_t)L);
+  if (cudaMemcpyAsync(h.data(), dpack.p, sizeof(double) * plen, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+      cudaMemcpyAsync(h.data() + plen, d_range, sizeof(double) * 2 * L, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+      cudaStreamSynchronize(st) != cudaSuccess) {
+    set_error("isr_tikhonov_chi2_scan: CUDA error '%s'", cudaGetErrorString(cudaGetLastError()));
+    return drain(ISR_ECUDA);
+  }
+  const double total = h[(size_t)L * nb + L];
+  if (a.total_toys_out) *a.total_toys_out = (int64_t)total;
+  for (int64_t l = 0; l < L; ++l) {
+    if (a.stats_out) {
+      a.stats_out[3 * l + 0] = h[plen + 2 * l];
+      a.stats_out[3 * l + 1] = -h[plen + 2 * l + 1];
+      a.stats_out[3 * l + 2] = total > 0 ? h[(size_t)L * nb + l] / total : 0.0;
+    }
+    if (a.counts_out)
+      for (int q = 0; q < nb; ++q) a.counts_out[(size_t)l * nb + q] = (uint32_t)h[(size_t)l * nb + q];
+  }
   return ISR_OK;
 }
 

@@ -290,3 +290,60 @@ def test_comm_of_one_and_allreduce():
     L.check(lib.isr_ctx_bind_host_thread(ctx, C.byref(node)))
     assert node.value >= -1
     lib.isr_comm_destroy(comm)
+
+
+@pytest.mark.parametrize("ngpu", [1, 2])
+def test_tikhonov_chi2_scan_toys_sharded(ngpu):
+    """BASELINE config C4 sharded on the toy axis: per-lambda {min, max} and TH1F cells from toys spread
+    over `ngpu` contexts of one process (one host thread each, isr_comm_init_all) are bit-identical to the single-GPU
+    isr_tikhonov_toy_scan_hist; the mean agrees to rounding (the sums are re-associated)."""
+    import threading
+    if _gpu_count() < ngpu:
+        pytest.skip(f"needs {ngpu} GPUs")
+    L, lib = _lib()
+    g = load_golden("c4_tikhonov_n32_spread")
+    n, T, Lm = len(g["ecm"]), 5000, 37
+    rng = np.random.default_rng(3)
+    err = np.ascontiguousarray(g["vcs_err"]); b0 = np.ascontiguousarray(g["bcs0"])
+    V = np.ascontiguousarray(g["vcs"][None, :] + err[None, :] * rng.standard_normal((T, n)))
+    lam = np.ascontiguousarray(10.0 ** np.linspace(-8, 0, Lm))
+    # reference: one GPU, round-1 entry point
+    p1 = _problem(L, lib, _ctx(), g["ecm"], float(g["threshold"]), g["settings"], G=g["G_spread"])
+    L.check(lib.isr_tikhonov_prepare(p1, L.dptr(err), 1))
+    st1 = np.zeros((Lm, 3)); c1 = np.zeros((Lm, 130), dtype=np.uint32)
+    L.check(lib.isr_tikhonov_toy_scan_hist(p1, Lm, L.dptr(lam), T, L.dptr(V), L.dptr(b0), 128, L.dptr(st1), L.uptr(c1)))
+    # sharded
+    ctxs = (C.c_void_p * ngpu)()
+    for r in range(ngpu):
+        h = C.c_void_p(); L.check(lib.isr_ctx_create(r, C.byref(h))); ctxs[r] = h
+    comms = (C.c_void_p * ngpu)()
+    L.check(lib.isr_comm_init_all(ngpu, ctxs, comms))
+    res, errs = [None] * ngpu, []
+
+    def work(r):
+        try:
+            p = _problem(L, lib, ctxs[r], g["ecm"], float(g["threshold"]), g["settings"], G=g["G_spread"])
+            t0, t1 = r * T // ngpu, (r + 1) * T // ngpu
+            Vr = np.ascontiguousarray(V[t0:t1])
+            st = np.zeros((Lm, 3)); cn = np.zeros((Lm, 130), dtype=np.uint32); tot = C.c_int64()
+            a = L.TikhonovScanArgs()
+            a.flags, a.vcs_err, a.deriv_reg = L.ISR_TEST_FACTOR, L.dptr(err), 1
+            a.n_lambda, a.lambda_, a.n_toys, a.V, a.bcs0, a.nbins, a.comm = Lm, L.dptr(lam), t1 - t0, L.dptr(Vr), L.dptr(b0), 128, comms[r]
+            a.stats_out, a.counts_out, a.total_toys_out = L.dptr(st), L.uptr(cn), C.pointer(tot)
+            L.check(lib.isr_tikhonov_chi2_scan(p, C.byref(a)))
+            res[r] = (st, cn, tot.value)
+            lib.isr_problem_destroy(p)
+        except Exception as e:      # noqa: BLE001
+            errs.append(e)
+    th = [threading.Thread(target=work, args=(r,)) for r in range(ngpu)]
+    [t.start() for t in th]; [t.join() for t in th]
+    assert not errs, errs
+    for r in range(ngpu):
+        st, cn, tot = res[r]
+        assert tot == T
+        np.testing.assert_array_equal(cn, c1)
+        np.testing.assert_array_equal(st[:, :2], st1[:, :2])
+        np.testing.assert_allclose(st[:, 2], st1[:, 2], rtol=1e-12)
+    for r in range(ngpu):
+        lib.isr_comm_destroy(comms[r]); lib.isr_ctx_destroy(ctxs[r])
+    lib.isr_problem_destroy(p1)
