@@ -539,7 +539,10 @@ def tikhonov_c4(lib, ctx, torch, comm=None, rank=0, world=1):
     L.check(lib.isr_host_alloc(ctx, max(t1 - t0, 1) * n * 8, C.byref(vptr)))
     Vp = np.ctypeslib.as_array(C.cast(vptr, C.POINTER(C.c_double)), shape=(max(t1 - t0, 1), n))
     Vp[:t1 - t0] = Vall[t0:t1]
-    stats = np.empty((Lm, 3)); counts = np.zeros((Lm, 130), dtype=np.uint32)
+    stats = np.empty((Lm, 3))
+    cptr = C.c_void_p()
+    L.check(lib.isr_host_alloc(ctx, Lm * 130 * 4, C.byref(cptr)))        # the caller's cell buffer, page-locked like the toys
+    counts = np.ctypeslib.as_array(C.cast(cptr, C.POINTER(C.c_uint32)), shape=(Lm, 130))
     total = C.c_int64()
 
     def wall(fn, reps=5):
@@ -579,6 +582,7 @@ def tikhonov_c4(lib, ctx, torch, comm=None, rank=0, world=1):
             L.check(lib.isr_tikhonov_scan(p, Lm, L.dptr(lam), L.dptr(vcs), L.dptr(lc[0]), L.dptr(lc[1]), L.dptr(lc[2]), L.dptr(lc[3]), None))
         out["lcurve_1024_lambdas_ms"] = (time.perf_counter() - t_0) / 5 * 1e3
     lib.isr_host_free(vptr)
+    lib.isr_host_free(cptr)
     lib.isr_problem_destroy(p)
     return out
 

@@ -94,6 +94,7 @@ struct isr_problem {
     if (copy_stream) cudaStreamDestroy(copy_stream);
     for (int q = 0; q < 4; ++q) if (ev_time[q]) cudaEventDestroy(ev_time[q]);
     if (pin_cert) cudaFreeHost(pin_cert);
+    if (pin_scan) cudaFreeHost(pin_scan);
     if (pin_test) cudaFreeHost(pin_test);
   }
 
@@ -106,8 +107,8 @@ struct isr_problem {
   // (lambda, toy) scan scratch, grow-only
   isr::DevBuf<double> d_scan_lam, d_scan_b0, d_scan_g, d_scan_Pe, d_scan_AB, d_scan_C, d_scan_V, d_scan_chi, d_scan_stats;
   isr::DevBuf<uint32_t> d_scan_cnt;
-  isr::DevBuf<double> d_scan_pack;      // isr_tikhonov_chi2_scan: [L x cells | L sums | toys]
-  std::vector<double> h_scan_pack;
+  double* pin_scan = nullptr;           // isr_tikhonov_chi2_scan: page-locked [L ranges (2) | L sums | toys]
+  size_t pin_scan_n = 0;
 
   // ---- SVD -----------------------------------------------------------------------------------
   bool svd_ready = false;

@@ -482,10 +482,10 @@ __global__ void __launch_bounds__(256) scan_stats_kernel(int64_t T, const double
     sums[blockIdx.x] = c;
   }
 }
-// pack[l * nb + q] = cells of lambda l against range[l] = {min, -max}; pack[L nb + l] = sums[l]; pack[L nb + L] = toys
+// cells[l][q] = TH1F cells of lambda l against range[l] = {min, -max}; sums[L] = toys of this rank (rides in the sums' all-reduce)
 __global__ void __launch_bounds__(256) scan_cells_kernel(int64_t T, const double* __restrict__ chi2, int nbins,
-                                                          const double* __restrict__ range, const double* __restrict__ sums,
-                                                          int64_t L, double toys, double* __restrict__ pack) {
+                                                          const double* __restrict__ range, double* __restrict__ sums,
+                                                          int64_t L, double toys, uint32_t* __restrict__ cells) {
   extern __shared__ uint32_t sh_cnt[];
   const int nb = nbins + 2;
   const double a = range[2 * blockIdx.x], b = -range[2 * blockIdx.x + 1];
@@ -501,11 +501,8 @@ __global__ void __launch_bounds__(256) scan_cells_kernel(int64_t T, const double
     atomicAdd(&sh_cnt[bin], 1u);
   }
   __syncthreads();
-  for (int q = threadIdx.x; q < nb; q += blockDim.x) pack[(size_t)blockIdx.x * nb + q] = (double)sh_cnt[q];
-  if (threadIdx.x == 0) {
-    pack[(size_t)L * nb + blockIdx.x] = sums[blockIdx.x];
-    if (blockIdx.x == 0) pack[(size_t)L * nb + L] = toys;
-  }
+  for (int q = threadIdx.x; q < nb; q += blockDim.x) cells[(size_t)blockIdx.x * nb + q] = sh_cnt[q];
+  if (threadIdx.x == 0 && blockIdx.x == 0) sums[L] = toys;
 }
 __global__ void scan_empty_stats_kernel(int64_t L, double* __restrict__ range, double* __restrict__ sums) {
   const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -523,11 +520,19 @@ int tikhonov_chi2_scan(isr_problem* p, const isr_tikhonov_scan_args& a) {
   if (a.nbins < 1 || a.nbins > 8190) { set_error("isr_tikhonov_chi2_scan: nbins out of range"); return ISR_EINVAL; }
   if (a.comm && a.comm->ctx != c) { set_error("isr_tikhonov_chi2_scan: the communicator belongs to another context"); return ISR_EINVAL; }
   const int nb = a.nbins + 2;
-  const size_t plen = (size_t)L * nb + L + 1;
-  DevBuf<double>&dV = p->d_scan_V, &dchi = p->d_scan_chi, &dstats = p->d_scan_stats, &dpack = p->d_scan_pack;
+  DevBuf<double>&dV = p->d_scan_V, &dchi = p->d_scan_chi, &dstats = p->d_scan_stats;
+  DevBuf<uint32_t>& dcnt = p->d_scan_cnt;
   ISR_TRY(dchi.reserve((size_t)L * std::max<int64_t>(T, 1)));
-  ISR_TRY(dstats.reserve(3 * (size_t)L));
-  ISR_TRY(dpack.reserve(plen));
+  ISR_TRY(dstats.reserve(3 * (size_t)L + 1));
+  ISR_TRY(dcnt.reserve((size_t)L * nb));
+  // page-locked staging for the O(L) read-back (a copy into pageable memory would block the host)
+  const size_t hlen = 3 * (size_t)L + 1;
+  if (hlen > p->pin_scan_n) {
+    if (p->pin_scan) cudaFreeHost(p->pin_scan);
+    p->pin_scan = nullptr; p->pin_scan_n = 0;
+    ISR_CUDA(cudaMallocHost((void**)&p->pin_scan, sizeof(double) * hlen));
+    p->pin_scan_n = hlen;
+  }
   // the toys go up on the copy stream while the eigen-system is (re)built on the main one
   const double* Vdev = a.V_dev;
   if (a.V && T > 0) {
@@ -555,7 +560,7 @@ int tikhonov_chi2_scan(isr_problem* p, const isr_tikhonov_scan_args& a) {
   if (!p->tik_ready) { set_error("isr_tikhonov_chi2_scan: no eigen-system (set ISR_TEST_FACTOR or call isr_tikhonov_prepare first)"); return drain(ISR_ESTATE); }
   if (a.V && T > 0) ISR_CUDA(cudaStreamWaitEvent(st, p->ev_copied[0], 0));
   double* d_range = dstats.p;          // [L][2]
-  double* d_sums = dstats.p + 2 * L;   // [L]
+  double* d_sums = dstats.p + 2 * L;   // [L] + toy count
   if (T > 0) {
     if ((rc = tikhonov_toy_scan_device(p, L, a.lambda, T, Vdev, a.bcs0, dchi.p)) != ISR_OK) return drain(rc);
     scan_stats_kernel<<<(unsigned)L, 256, 0, st>>>(T, dchi.p, d_range, d_sums); ISR_COUNT_LAUNCH();
@@ -563,27 +568,26 @@ int tikhonov_chi2_scan(isr_problem* p, const isr_tikhonov_scan_args& a) {
     scan_empty_stats_kernel<<<(unsigned)((L + 255) / 256), 256, 0, st>>>(L, d_range, d_sums); ISR_COUNT_LAUNCH();
   }
   if (a.comm && (rc = comm_allreduce(a.comm, d_range, 2 * L, 0, 1)) != ISR_OK) return drain(rc);
-  scan_cells_kernel<<<(unsigned)L, 256, sizeof(uint32_t) * nb, st>>>(T, dchi.p, a.nbins, d_range, d_sums, L, (double)T, dpack.p); ISR_COUNT_LAUNCH();
-  if (a.comm && (rc = comm_allreduce(a.comm, dpack.p, (int64_t)plen, 0, 0)) != ISR_OK) return drain(rc);
-  std::vector<double>& h = p->h_scan_pack;
-  h.resize(plen + 2 * (size_t)L);
-  if (cudaMemcpyAsync(h.data(), dpack.p, sizeof(double) * plen, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-      cudaMemcpyAsync(h.data() + plen, d_range, sizeof(double) * 2 * L, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-      cudaStreamSynchronize(st) != cudaSuccess) {
+  scan_cells_kernel<<<(unsigned)L, 256, sizeof(uint32_t) * nb, st>>>(T, dchi.p, a.nbins, d_range, d_sums, L, (double)T, dcnt.p); ISR_COUNT_LAUNCH();
+  if (a.comm) {
+    if ((rc = comm_allreduce(a.comm, dcnt.p, (int64_t)L * nb, 2, 0)) != ISR_OK) return drain(rc);
+    if ((rc = comm_allreduce(a.comm, d_sums, L + 1, 0, 0)) != ISR_OK) return drain(rc);
+  }
+  bool bad = cudaMemcpyAsync(p->pin_scan, dstats.p, sizeof(double) * hlen, cudaMemcpyDeviceToHost, st) != cudaSuccess;
+  if (a.counts_out) bad = bad || cudaMemcpyAsync(a.counts_out, dcnt.p, sizeof(uint32_t) * (size_t)L * nb, cudaMemcpyDeviceToHost, st) != cudaSuccess;
+  if (bad || cudaStreamSynchronize(st) != cudaSuccess) {
     set_error("isr_tikhonov_chi2_scan: CUDA error '%s'", cudaGetErrorString(cudaGetLastError()));
     return drain(ISR_ECUDA);
   }
-  const double total = h[(size_t)L * nb + L];
+  const double* h = p->pin_scan;
+  const double total = h[3 * L];
   if (a.total_toys_out) *a.total_toys_out = (int64_t)total;
-  for (int64_t l = 0; l < L; ++l) {
-    if (a.stats_out) {
-      a.stats_out[3 * l + 0] = h[plen + 2 * l];
-      a.stats_out[3 * l + 1] = -h[plen + 2 * l + 1];
-      a.stats_out[3 * l + 2] = total > 0 ? h[(size_t)L * nb + l] / total : 0.0;
+  if (a.stats_out)
+    for (int64_t l = 0; l < L; ++l) {
+      a.stats_out[3 * l + 0] = h[2 * l];
+      a.stats_out[3 * l + 1] = -h[2 * l + 1];
+      a.stats_out[3 * l + 2] = total > 0 ? h[2 * L + l] / total : 0.0;
     }
-    if (a.counts_out)
-      for (int q = 0; q < nb; ++q) a.counts_out[(size_t)l * nb + q] = (uint32_t)h[(size_t)l * nb + q];
-  }
   return ISR_OK;
 }
 
