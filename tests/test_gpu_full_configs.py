@@ -1,5 +1,6 @@
-"""BASELINE.json configs C3-C5 at their full sizes, through size-independent properties (the oracle cannot
-finish these sizes in seconds; small-size parity is in the other test_gpu_* files)."""
+"""BASELINE.json configs C2-C5 at their full sizes: toy-level comparisons with the oracle's linear-algebra layer (which
+finishes thousands of toys at N = 100 ... 500 in seconds), matrix rows against the assembly oracle and the compiled
+reference (a whole N = 500 matrix takes the CPU minutes), and size-independent properties."""
 import time
 
 import numpy as np
@@ -33,11 +34,31 @@ def test_c4_tikhonov_1024_lambdas_10k_toys():
     chi2 = s.toy_scan(lam, V, b0)
     dt = time.perf_counter() - t0
     assert chi2.shape == (L, T) and np.all(np.isfinite(chi2)) and np.all(chi2 >= 0)
-    # the O(N)-per-pair scan against the generic operator path (A+_lambda, Cov_lambda^-1 through the tile kernel)
+    # (1) against the ORACLE at full size: 4 lambdas x 1024 toys.  The yardstick is the reference's formula
+    # (b_k - b0)^T Cov_lambda^-1 (b_k - b0), b_k = T^-1 G^T W v_k, in 80-bit long double (tests/hp_reference.py, pinned by
+    # 50-digit arithmetic at N = 32); the double-precision literal matrices of oracle.tikhonov_solve are compared too,
+    # with the slack their explicit covariance inverse needs (reported, not assumed).
+    from hp_reference import ld_tikhonov_chi2
+    from oracle import isr_oracle as O
+    F = s.regulariser()
+    Fo = O.tikhonov_F(O.Interp(ecm, 0.827, [(False, 0, 0), (True, 1, n - 1)]).deriv_projector(),
+                      O.Interp(ecm, 0.827, [(False, 0, 0), (True, 1, n - 1)]).integral_basis(), True)
+    np.testing.assert_allclose(F, Fo, rtol=1e-8, atol=1e-10 * np.abs(Fo).max())
+    worst_np = 0.0
     for q in (0, 400, 700, 1023):
+        ref, Bref = ld_tikhonov_chi2(G, err, Fo, lam[q], V[:1024], b0)
+        np.testing.assert_allclose(chi2[q, :1024], ref, rtol=RTOL)
+        t = O.tikhonov_solve(G, vcs, err, Fo, lam[q])
+        D = V[:1024] @ t["Ap"].T - b0[None, :]
+        lit = np.einsum("ij,ij->i", D, np.linalg.solve(t["cov"], D.T).T)
+        worst_np = max(worst_np, float(np.abs(lit / ref - 1).max()))
+        np.testing.assert_allclose(chi2[q, :1024], lit, rtol=max(RTOL, 10 * worst_np))
+        # (2) the O(N)-per-pair scan against the generic operator path (A+_lambda, Cov_lambda^-1 through the tile kernel)
         s.reg_param = float(lam[q])
-        r = s.toy_batch(V[:2048], b0)
-        np.testing.assert_allclose(chi2[q, :2048], r["chi2"], rtol=1e-6)
+        r = s.toy_batch(V[:2048], b0, want_bcs=True)
+        np.testing.assert_allclose(chi2[q, :2048], r["chi2"], rtol=RTOL)
+        np.testing.assert_allclose(r["bcs"][:1024], Bref, rtol=RTOL, atol=RTOL * np.abs(Bref).max())
+    print(f"\nC4: double-precision literal oracle vs long double: worst relative chi2 deviation {worst_np:.2e}")
     # L-curve over the same grid: finite, and the residual norm grows / the smoothness norm falls with lambda
     lc = s.make_LCurve(lam)
     assert np.all(np.isfinite(lc["x"])) and np.all(np.isfinite(lc["y"])) and np.all(lc["c"] >= 0)
@@ -78,6 +99,50 @@ def test_c5_sle_ratio_and_chi2_n500():
     np.testing.assert_allclose(s2["bcs"], B, rtol=RTOL, atol=1e-12)
     inr = (rr >= -2) & (rr < 2)
     np.testing.assert_allclose(s2["ratio_stats"][:, 1], np.where(inr, rr, 0).sum(0), rtol=1e-7, atol=1e-9)
+
+
+@pytest.mark.parametrize("n,cubic,T", [(100, True, 100000), (500, False, 1 << 17)])
+def test_c2_c5_sizes_toy_level_vs_oracle(n, cubic, T, oracle):
+    """BASELINE C2 (N = 100, cubic, 10^5 toys) and C5 (N = 500, linear, ratio + chi2) at their own N: the whole batch runs
+    on the GPU; 8192 toys spread over it are compared toy by toy with the oracle -- b_k and chi2_k to 1e-8, the ratio
+    histogram cells and the chi2 TH1F bit for bit."""
+    import isrsolver_b200 as isr
+    O = oracle
+    ecm = np.linspace(1.18, 2.0, n)
+    s = isr.ISRSolverSLE(n, ecm, np.ones(n), None, np.ones(n), 0.827)
+    if cubic:
+        s.set_interp_settings([(False, 0, 0), (True, 1, n - 1)])
+    s.eval_equation_matrix()
+    G = s.intop_matrix().copy()
+    b0, vcs, err = _model(ecm, G)
+    s.resetVisibleCS(vcs); s.resetVisibleCSErrors(err)
+    V = isr.draw_toys(vcs, err, T)
+    r = s.toy_batch(V, b0, want_sum=True, want_ratio=True)
+    sel = np.unique(np.concatenate([np.arange(4096), np.linspace(0, T - 1, 4096).astype(int)]))
+    c2, B = O.chi2_test_fair(G, V[sel], b0, err)
+    np.testing.assert_allclose(r["chi2"][sel], c2, rtol=RTOL)
+    # the reference's per-toy O(N^3) loop on a few of them (COD + G^T W G + inverse per toy, src/Chi2Test.cpp:38-60)
+    c2l, _ = O.chi2_test_loop(G, V[sel[:6]], b0, err)
+    np.testing.assert_allclose(r["chi2"][sel[:6]], c2l, rtol=RTOL)
+    # a batch of exactly the selected toys: solutions, ratio cells, chi2 cells
+    q = s.toy_batch(np.ascontiguousarray(V[sel]), b0, want_sum=True, want_ratio=True, want_hist=True, want_bcs=True)
+    np.testing.assert_array_equal(q["chi2"], r["chi2"][sel])                      # a toy's chi2 does not depend on its batch
+    np.testing.assert_allclose(q["bcs"], B, rtol=RTOL, atol=RTOL * np.abs(b0).max())
+    np.testing.assert_allclose(q["sum_bcs"], B.sum(0), rtol=RTOL)
+    means, errs, counts, stats = O.ratio_test(q["bcs"], b0)                       # ROOT bin arithmetic on the GPU's b_k
+    np.testing.assert_array_equal(q["ratio_hist"], counts.astype(np.uint32))
+    np.testing.assert_allclose(q["ratio_stats"], stats, rtol=1e-9, atol=1e-9)
+    # cells from the oracle's OWN b_k: identical except where a ratio sits within rounding of a cell edge
+    counts_o = O.ratio_test(B, b0)[2]
+    assert np.abs(q["ratio_hist"].astype(np.int64) - counts_o.astype(np.int64)).sum() <= 4
+    ref, _, lo, hi = O.chi2_histogram(q["chi2"])
+    import ctypes as C
+    from isrsolver_b200 import _lib as L
+    cnt = np.zeros(130, dtype=np.uint32); clo, chi = C.c_double(), C.c_double()
+    L.check(L.load().isr_last_chi2_minmax(s._p, C.byref(clo), C.byref(chi)))
+    L.check(L.load().isr_last_chi2_histogram(s._p, 128, clo.value, chi.value, L.uptr(cnt)))
+    assert (clo.value, chi.value) == (lo, hi)
+    np.testing.assert_array_equal(cnt, ref.astype(np.uint32))
 
 
 def test_c3_sle2_matrix_assembly_timing():

@@ -363,3 +363,23 @@ def test_device_quadrature_tables_against_numpy_and_scipy():
         assert abs(np.dot(wg, x ** p) - exact) < 2e-15, p
     xg, wgl = np.polynomial.legendre.leggauss(7)
     np.testing.assert_allclose(np.sort(x[wg != 0]), xg, rtol=0, atol=1e-15)
+
+
+def test_high_precision_yardsticks_agree(golden, oracle):
+    """tests/hp_reference.py: the long-double evaluation used as the gate at full size (N = 200) against the literal
+    formulas of src/ISRSolverTikhonov.cpp:61-72, 139-155 / src/Chi2Test.cpp:51-55 in 50-digit arithmetic, and both
+    against the NumPy literal-matrix oracle."""
+    from hp_reference import ld_solve, ld_tikhonov_chi2, mp_tikhonov
+    g = golden("c4_tikhonov_n32_spread")
+    G, err, F, V, b0 = g["G_spread"], g["vcs_err"], g["tik_F"], g["toys"][:5], g["bcs0"]
+    for lam in (1e-9, 1e-3, 0.3):
+        m = mp_tikhonov(G, g["vcs"], err, F, lam, V, b0)
+        c, B = ld_tikhonov_chi2(G, err, F, lam, V, b0)
+        np.testing.assert_allclose(c, m["chi2"], rtol=1e-13)
+        np.testing.assert_allclose(B, m["B"], rtol=1e-13, atol=1e-15)
+        r = oracle.tikhonov_lcurve(G, g["vcs"], err, F, lam)
+        np.testing.assert_allclose(r["bcs"], m["bcs"], rtol=1e-10)
+        assert r["y"] == pytest.approx(m["y"], rel=1e-10) and r["curv"] == pytest.approx(m["curv"], rel=1e-9)
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((40, 40)) + 5 * np.eye(40); Bm = rng.standard_normal((40, 3))
+    np.testing.assert_allclose(np.asarray(ld_solve(A, Bm), dtype=float), np.linalg.solve(A, Bm), rtol=1e-12)
