@@ -541,6 +541,34 @@ __global__ void spread_kernel(int n, const double* __restrict__ ext, const doubl
   S[(size_t)i + (size_t)n * j] = acc;
 }
 
+// The same for a batch of spread settings (condition-number scan): S_k from sigma_k (one common value per setting, or
+// one per point), matrices back to back.
+__global__ void spread_batch_kernel(int n, const double* __restrict__ ext, const double* __restrict__ invh,
+                                    const double* __restrict__ Ct, const double* __restrict__ sig, int per_point,
+                                    double* __restrict__ Sbatch) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * n) return;
+  const int k = blockIdx.y;
+  const int j = idx % n, i = idx / n;
+  const double sigma = per_point ? sig[(size_t)k * n + i] : sig[k];
+  const double e0 = ext[i + 1], sg = sigma * 1.4142135623730951;
+  double acc = 0.0;
+  if (sigma == 0.0) {
+    acc = (i == j) ? 1.0 : 0.0;      // spread disabled for this setting: S = I (the product below returns G0 itself)
+  } else {
+#pragma unroll
+    for (int m = 0; m < 6; ++m)
+      acc += kGH6_w_over_sqrtpi[m] * basis_eval_dev(n, ext, invh, Ct, j, e0 + sg * kGH6_t[m], 0);
+  }
+  Sbatch[(size_t)k * n * n + (size_t)i + (size_t)n * j] = acc;
+}
+int spread_batch(isr_problem* p, cudaStream_t st, int K, const double* sig_dev, int per_point, double* Sbatch) {
+  const int n = p->n;
+  spread_batch_kernel<<<dim3((n * n + 127) / 128, K), 128, 0, st>>>(n, p->d_ext.p, p->d_invh.p, p->d_Ct.p, sig_dev, per_point, Sbatch); ISR_COUNT_LAUNCH();
+  ISR_CUDA(cudaGetLastError());
+  return ISR_OK;
+}
+
 // C = A * B, all n x n column-major, FP64; 32x32 tiles.  Used for the one-off spread product.
 __global__ void __launch_bounds__(256) gemm_nn_kernel(int n, const double* __restrict__ A,
                                                        const double* __restrict__ B, double* __restrict__ C) {

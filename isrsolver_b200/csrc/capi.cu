@@ -393,56 +393,32 @@ int isr_cond_spread_scan(isr_problem* p, int K, const double* sigma, int per_poi
   ISR_TRY(p->d_G0.reserve(nn));
   ISR_CUDA(cudaMemcpyAsync(p->d_G0.p, p->d_G.p, sizeof(double) * nn, cudaMemcpyDeviceToDevice, st));
   p->G_lower = false;
+  // The K settings are independent: ONE batched launch each for the 6-point Gauss-Hermite spread matrices, the products
+  // S_k G0 and the singular values (one-sided Jacobi, one CTA per matrix: svd_jacobi.cu), in chunks of two waves of CTAs.
+  if (n > 512) { set_error("isr_cond_spread_scan: N = %d exceeds the batched Jacobi kernel's 512", n); return ISR_EINVAL; }
+  const int chunk = std::min(K, 2 * p->ctx->sm_count);
+  DevBuf<double> dS, dA, dsig, dsv;
+  DevBuf<int> dsw;
+  const size_t per = per_point ? (size_t)n : 1;
+  ISR_TRY(dS.reserve((size_t)chunk * nn)); ISR_TRY(dA.reserve((size_t)chunk * nn));
+  ISR_TRY(dsig.reserve((size_t)K * per)); ISR_TRY(dsv.reserve((size_t)K * n)); ISR_TRY(dsw.reserve(K));
+  ISR_CUDA(cudaMemcpyAsync(dsig.p, sigma, sizeof(double) * K * per, cudaMemcpyHostToDevice, st));
+  for (int k0 = 0; k0 < K; k0 += chunk) {
+    const int kc = std::min(chunk, K - k0);
+    ISR_TRY(spread_batch(p, st, kc, dsig.p + (size_t)k0 * per, per_point, dS.p));
+    ISR_TRY(small_gemm_batch(p->ctx, st, n, kc, dS.p, p->d_G0.p, dA.p));
+    ISR_TRY(jacobi_singular_values_batch(p->ctx, st, n, kc, dA.p, dsv.p + (size_t)k0 * n, dsw.p + k0));
+  }
+  std::vector<double> h_sv((size_t)K * n);
+  std::vector<int> h_sw(K);
+  ISR_CUDA(cudaMemcpyAsync(h_sv.data(), dsv.p, sizeof(double) * K * n, cudaMemcpyDeviceToHost, st));
+  ISR_CUDA(cudaMemcpyAsync(h_sw.data(), dsw.p, sizeof(int) * K, cudaMemcpyDeviceToHost, st));
   ISR_CUDA(cudaStreamSynchronize(st));
-  // The K decompositions are independent and each one is a chain of small latency-bound kernels, so they
-  // run on several lanes (stream + cuSOLVER handle + workspace each) at once.
-  struct Lane {
-    cudaStream_t st = nullptr;
-    cusolverDnHandle_t h = nullptr;
-    DevBuf<double> S, A, sig, sv, work;
-    DevBuf<int> info;
-    std::vector<double> h_sig, h_sv;
-    int h_info = 0, k = -1;
-    ~Lane() {
-      if (h) cusolverDnDestroy(h);
-      if (st) cudaStreamDestroy(st);
-    }
-  };
-  const int nlanes = std::min(K, 8);
-  std::vector<Lane> lanes(nlanes);
-  for (Lane& ln : lanes) {
-    ISR_CUDA(cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking));
-    ISR_CUSOLVER(cusolverDnCreate(&ln.h));
-    ISR_CUSOLVER(cusolverDnSetStream(ln.h, ln.st));
-    ISR_TRY(ln.S.reserve(nn)); ISR_TRY(ln.A.reserve(nn)); ISR_TRY(ln.sig.reserve(n)); ISR_TRY(ln.sv.reserve(n));
-    ln.h_sig.resize(n); ln.h_sv.resize(n);
-  }
-  auto collect = [&](Lane& ln) -> int {
-    if (ln.k < 0) return ISR_OK;
-    ISR_CUDA(cudaStreamSynchronize(ln.st));
-    if (ln.h_info != 0) { set_error("isr_cond_spread_scan: SVD failed for setting %d (info = %d)", ln.k, ln.h_info); return ISR_ENUMERIC; }
-    cond_out[ln.k] = ln.h_sv.front() / ln.h_sv.back();
-    if (sv_out) std::memcpy(sv_out + (size_t)ln.k * n, ln.h_sv.data(), sizeof(double) * n);
-    ln.k = -1;
-    return ISR_OK;
-  };
   for (int k = 0; k < K; ++k) {
-    Lane& ln = lanes[k % nlanes];
-    ISR_TRY(collect(ln));                               // the lane's previous setting (also frees h_sig)
-    const bool none = !per_point && sigma[k] == 0.0;    // first point of the reference's scan: spread disabled
-    if (none) {
-      ISR_CUDA(cudaMemcpyAsync(ln.A.p, p->d_G0.p, sizeof(double) * nn, cudaMemcpyDeviceToDevice, ln.st));
-    } else {
-      for (int i = 0; i < n; ++i) ln.h_sig[i] = per_point ? sigma[(size_t)k * n + i] : sigma[k];
-      ISR_CUDA(cudaMemcpyAsync(ln.sig.p, ln.h_sig.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ln.st));
-      ISR_TRY(apply_spread(p, ln.st, ln.sig.p, p->d_G0.p, ln.S.p, ln.A.p));
-    }
-    ISR_TRY(svd_values_async(ln.h, n, ln.A.p, ln.sv.p, ln.work, ln.info));
-    ISR_CUDA(cudaMemcpyAsync(ln.h_sv.data(), ln.sv.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ln.st));
-    ISR_CUDA(cudaMemcpyAsync(&ln.h_info, ln.info.p, sizeof(int), cudaMemcpyDeviceToHost, ln.st));
-    ln.k = k;
+    if (h_sw[k] <= 0) { set_error("isr_cond_spread_scan: the Jacobi sweeps of setting %d did not converge (%d sweeps)", k, -h_sw[k]); return ISR_ENUMERIC; }
+    cond_out[k] = h_sv[(size_t)k * n] / h_sv[(size_t)k * n + n - 1];
   }
-  for (Lane& ln : lanes) ISR_TRY(collect(ln));
+  if (sv_out) std::memcpy(sv_out, h_sv.data(), sizeof(double) * K * n);
   p->svd_ready = false;    // d_sv no longer belongs to the problem's own matrix
   return ISR_OK;
 }

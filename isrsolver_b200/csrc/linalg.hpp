@@ -22,6 +22,10 @@ int inverse_pivoted(isr_ctx* c, int n, const double* A, double* lu, double* Ainv
 int tri_inverse_lower(isr_ctx* c, int n, const double* L, double* X);
 // C = A B, n x n column-major, hand-written 32 x 32 tiles; lower: both factors (hence the product) are lower triangular.
 int small_gemm(isr_ctx* c, int n, bool lower, const double* A, const double* B, double* C, cudaStream_t st = nullptr);
+// C_k = A_k B for k < K (n x n column-major; A_k, C_k back to back with stride n^2, B shared): one launch
+int small_gemm_batch(isr_ctx* c, cudaStream_t st, int n, int K, const double* A_batch, const double* B, double* C_batch);
+// singular values (descending) of K n x n matrices by one-sided Jacobi, one CTA per matrix (svd_jacobi.cu); A destroyed
+int jacobi_singular_values_batch(isr_ctx* c, cudaStream_t st, int n, int K, double* A_batch, double* sv_batch, int* sweeps_dev);
 int ql_factor_rowmajor(isr_ctx* c, int n, int ld, double* A, double* scratch, DevBuf<double>& work, DevBuf<int>& info);
 int svd(isr_ctx* c, int n, double* A, double* U, double* S, double* VT, DevBuf<double>& work, DevBuf<int>& info);
 int svd_values_async(cusolverDnHandle_t h, int n, double* A, double* S, DevBuf<double>& work, DevBuf<int>& info);

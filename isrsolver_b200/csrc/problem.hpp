@@ -131,5 +131,6 @@ int assemble(isr_problem* p, const double* ecm_err);
 int reduce_moments(isr_problem* p);
 int assemble_nodes(isr_problem* p, int64_t cap, double* x_out, int* row_out, int64_t* count);
 int assemble_sampled(isr_problem* p, int64_t nn, const double* eps_values, const double* ecm_err);
+int spread_batch(isr_problem* p, cudaStream_t st, int K, const double* sig_dev, int per_point, double* Sbatch);
 int apply_spread(isr_problem* p, cudaStream_t st, const double* sigE_dev, const double* G0, double* S, double* Gout);
 }  // namespace isr

@@ -147,4 +147,20 @@ int small_gemm(isr_ctx* c, int n, bool lower, const double* A, const double* B, 
   return ISR_OK;
 }
 
+__global__ void __launch_bounds__(256) small_gemm_batch_kernel(int n, const double* __restrict__ A, const double* __restrict__ B,
+                                                                double* __restrict__ C) {
+  __shared__ double sA[kTb][kTb + 1];
+  __shared__ __align__(32) double sB[kTb][kTb + 4];
+  const size_t off = (size_t)blockIdx.z * n * n;
+  TileJob jb{A + off, B, C + off, n, n, n};
+  tile_product(jb, n, blockIdx.y, blockIdx.x, 0, n, 1.0, sA, sB);
+}
+int small_gemm_batch(isr_ctx* c, cudaStream_t st, int n, int K, const double* A_batch, const double* B, double* C_batch) {
+  if (K <= 0) return ISR_OK;
+  const int t = (n + kTb - 1) / kTb;
+  small_gemm_batch_kernel<<<dim3(t, t, K), 256, 0, st ? st : c->stream>>>(n, A_batch, B, C_batch); ISR_COUNT_LAUNCH();
+  ISR_CUDA(cudaGetLastError());
+  return ISR_OK;
+}
+
 }  // namespace isr
