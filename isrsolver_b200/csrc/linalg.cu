@@ -203,6 +203,13 @@ __device__ __forceinline__ void cluster_sync() {
 }  // namespace gj
 
 
+#ifdef ISR_GJ_TRACE
+__device__ long long* g_gj_trace = nullptr;    // [block][8] clock64 stamps of the critical chain (experiment builds only)
+#define GJ_STAMP(B, slot) do { if (lane == 0 && g_gj_trace) g_gj_trace[(B) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define GJ_STAMP(B, slot) do { } while (0)
+#endif
+
 struct GjSmem {
   double stage[kGjSlots][4][kGjMaxN];    // pivot blocks produced by this CTA (read by its own warps, source of the copies)
   double rowbuf[kGjSlots][4][kGjMaxN];   // pivot blocks received from the other CTAs
@@ -273,6 +280,8 @@ gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, d
         const bool local = owned(B);                   // produced by a warp of this CTA: read from `stage`
         const bool owner = k0 == wrow;                 // this warp's four rows ARE the pivot rows
         const double* src = local ? &sm.stage[q][0][0] : &sm.rowbuf[q][0][0];
+        const bool next_owner = k0 + 4 == wrow;        // (trace builds) this warp owns the next block: it is on the critical chain
+        if (owner) GJ_STAMP(B, 0); else if (next_owner) GJ_STAMP(B, 4);
         if (owner) {
           if (B >= kGjSlots) gj::mbar_wait(&sm.empty[q], ph.empty_parity(B));   // every warp of the cluster has consumed block B - 4 out of this slot
         } else if (local) {
@@ -284,6 +293,7 @@ gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, d
             if (Bn >= 0) gj::mbar_expect_tx(&sm.rfull[q], block_bytes(Bn));
           }
         }
+        if (owner) GJ_STAMP(B, 1); else if (next_owner) GJ_STAMP(B, 5);
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           if (k0 + t >= n) break;
@@ -325,11 +335,13 @@ gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, d
             }
           }
         }
+        if (owner) GJ_STAMP(B, 2); else if (next_owner) GJ_STAMP(B, 6);
         if (owner) {
           // the four scaled pivot rows, each as it was at its own step: first to the warps of this CTA (the next owner
           // is almost always one of them -- the critical chain never waits for a copy), then to the other CTAs
           __syncwarp();
           if (lane == 0) gj::mbar_arrive(&sm.lfull[q]);
+          GJ_STAMP(B, 3);
           asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
           __syncwarp();
           if (lane == 0) {
@@ -398,6 +410,12 @@ static int launch_gj(isr_ctx* c, int n, const double* A, double* X, double* cert
   if (ctas == 4) return launch_gj_t<4>(c, n, A, X, cert, Xrow, ld);
   return launch_gj_t<8>(c, n, A, X, cert, Xrow, ld);
 }
+
+#ifdef ISR_GJ_TRACE
+extern "C" int isr_debug_gj_trace(long long* dev) {
+  return cudaMemcpyToSymbol(g_gj_trace, &dev, sizeof(dev)) == cudaSuccess ? 0 : 3;
+}
+#endif
 
 // Ainv = A^-1.  A (column-major, preserved) is factored in `lu` (n x n scratch, destroyed); `prod` is n x n scratch.
 //

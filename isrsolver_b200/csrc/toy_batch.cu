@@ -122,6 +122,10 @@ static const std::vector<ToyCfg>& configs() {
       make_cfg<8, 2, 2, 7, 2, 40>("m128n112w16s2k40"), make_cfg<4, 4, 2, 4, 2, 40>("m64n128w16s2k40"),
       make_cfg<4, 4, 2, 4, 3, 40>("m64n128w16k40"),   make_cfg<16, 1, 1, 13, 2, 40>("m128n104w16s2k40"),
       make_cfg<16, 1, 1, 13, 3, 40>("m128n104w16k40"),
+      // column widths between 128 and 200 and 2 x 144 for N up to 288 (the N sweep of round 2 showed N = 136 ... 168
+      // paying for 200 columns: 21.7 TFLOP/s at N = 136)
+      make_cfg<4, 3, 2, 6, 2, 40>("m64n144w12s2k40"), make_cfg<4, 4, 2, 5, 2, 40>("m64n160w16s2k40"),
+      make_cfg<8, 2, 2, 11, 2, 40>("m128n176w16s2k40"), make_cfg<4, 4, 2, 6, 2, 40>("m64n192w16s2k40"),
   };
   return v;
 }
