@@ -197,7 +197,7 @@ class Tester:
             a.ratio_stats_out = L.dptr(self.rstat)
         a.total_toys_out = C.pointer(self.total)
         self.a = a
-        self.ms = np.zeros(3)
+        self.ms = np.zeros(4)
 
     def run(self, T, V_dev=None, V_host=None, chi2_host=None, seed=0, first_toy=0):
         a = self.a
@@ -338,7 +338,7 @@ def run_b200(args, rank, world, local_rank):
     ms_step = ms_total / args.steps
     value = T * world / (ms_step * 1e-3)
     ph = np.mean(np.array(phase_ms), axis=0)
-    asm_ms, fac_ms, toy_ms = (float(x) for x in ph)
+    asm_ms, fac_ms, toy_ms, tail_ms = (float(x) for x in ph)
     flops = 4.0 * n * n * T          # 2N^2 for b = G^-1 v, 2N^2 for |W^(1/2) G (b - b0)|^2
     achieved = flops / (toy_ms * 1e-3) * 1e-12
     npan, nnode = C.c_int64(), C.c_int64()
@@ -348,7 +348,7 @@ def run_b200(args, rank, world, local_rank):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, world),
-        "assembly_ms": asm_ms, "factor_ms": fac_ms, "toy_batch_ms": toy_ms,
+        "assembly_ms": asm_ms, "factor_ms": fac_ms, "toy_batch_ms": toy_ms, "tail_ms": tail_ms,
         "assembly": {"panels": npan.value, "nodes": nnode.value, "ms": asm_ms},
         "roofline": {"bound": "tensor", "kernel": "toy_fused_kernel, tile " + (lib.isr_toy_tile_name(n, 1) or b"?").decode() +
                                " (one launch: TMA box loads -> DMMA m8n8k4 f64, pass 1 b = S v and pass 2 chi2 = |R(b-b0)|^2)",
@@ -376,6 +376,7 @@ def run_b200(args, rank, world, local_rank):
     line["assembly_other_configs"] = other_assemblies(lib, ctx, stream, torch)
     line["chi2_test_other_configs"] = other_chi2_tests(lib, ctx, stream, torch, dev)
     line["tikhonov_c4"] = c4
+    line["cond_spread_scan"] = cond_scan(lib, ctx)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(n, G, bcs0, vcs, err)
     emit(line)
@@ -406,7 +407,7 @@ def strong_scaling(L, lib, ctx, stream, comm, torch, dist, dev, rank, world):
         p, bcs0, vcs, err = _problem_for(L, lib, ctx, n, cubic)
         gen = torch.Generator(device=dev); gen.manual_seed(11 + rank)
         Vd = torch.from_numpy(vcs).to(dev)[None, :] + torch.from_numpy(err).to(dev)[None, :] * torch.randn((Tr, n), dtype=torch.float64, device=dev, generator=gen)
-        t = Tester(L, lib, p, n, err, bcs0, vcs, comm, ratio=ratio)
+        t = Tester(L, lib, p, n, err, bcs0, vcs, comm, ratio=ratio, sum_bcs=ratio)
         for _ in range(2):
             t.run(Tr, V_dev=Vd.data_ptr())
         if world > 1:
@@ -433,7 +434,8 @@ def strong_scaling(L, lib, ctx, stream, comm, torch, dist, dev, rank, world):
         out[name] = {"ms_per_test": ms, "toys_total": total, "toys_per_gpu": Tr, "n_points": n, "toys_per_s": total / (ms * 1e-3),
                      "frac_of_fp64_peak": flop_per_toy * total / world / (ms * 1e-3) * 1e-12 / FP64_PEAK_TFLOPS,
                      "flop_per_toy": flop_per_toy, "assembly_ms": float(ph[0]), "factor_ms": float(ph[1]), "toys_ms": float(ph[2]),
-                     "toy_schedule": "dense" if cubic else "triangular"}
+                     "tail_ms": float(ph[3]), "toy_schedule": "dense" if cubic else "triangular",
+                     "outputs": "TH1F(128) cells and range" + (", ratio statistics, sum of solutions" if ratio else " (chi2TestModel: no column sums)")}
         del Vd
         lib.isr_problem_destroy(p)
     return out
@@ -489,7 +491,7 @@ def other_chi2_tests(lib, ctx, stream, torch, dev):
         p, bcs0, vcs, err = _problem_for(L, lib, ctx, n, cubic)
         gen = torch.Generator(device=dev); gen.manual_seed(7)
         Vd = torch.from_numpy(vcs).to(dev)[None, :] + torch.from_numpy(err).to(dev)[None, :] * torch.randn((T, n), dtype=torch.float64, device=dev, generator=gen)
-        t = Tester(L, lib, p, n, err, bcs0, vcs, None, ratio=ratio)
+        t = Tester(L, lib, p, n, err, bcs0, vcs, None, ratio=ratio, sum_bcs=ratio)      # chi2TestModel needs no column sums
         torch.cuda.synchronize()
         for _ in range(2):
             t.run(T, V_dev=Vd.data_ptr())
@@ -507,7 +509,7 @@ def other_chi2_tests(lib, ctx, stream, torch, dev):
         ph = np.mean(np.array(phases), axis=0)
         flop_per_toy = (4 if cubic else 2) * n * n
         out[name] = {"ms_per_test": ms, "toys_per_s": T / (ms * 1e-3), "n_points": n, "toys": T,
-                     "assembly_ms": float(ph[0]), "factor_ms": float(ph[1]), "toys_ms": float(ph[2]),
+                     "assembly_ms": float(ph[0]), "factor_ms": float(ph[1]), "toys_ms": float(ph[2]), "tail_ms": float(ph[3]),
                      "toy_schedule": "dense (4 N^2 flop/toy)" if cubic else "triangular (2 N^2 flop/toy algorithmic)",
                      "whole_test_frac_of_fp64_peak": flop_per_toy * T / (ms * 1e-3) * 1e-12 / FP64_PEAK_TFLOPS}
         lib.isr_problem_destroy(p)
@@ -585,6 +587,25 @@ def tikhonov_c4(lib, ctx, torch, comm=None, rank=0, world=1):
     lib.isr_host_free(cptr)
     lib.isr_problem_destroy(p)
     return out
+
+
+def cond_scan(lib, ctx):
+    """Condition number of G_spread(sigma) G for 100 beam-energy spreads at N = 200 (src/isrsolver-condnum-test.cpp:88-140,
+    notebooks/condnum_enspread.ipynb): one assembly, then batched spread matrices, products and one-sided Jacobi singular
+    values (one CTA per setting).  Wall clock of the synchronous call, best of 3."""
+    from isrsolver_b200 import _lib as L
+    n, K = 200, 100
+    p, _, _, _ = _problem_for(L, lib, ctx, n, True)
+    sig = np.ascontiguousarray(np.linspace(0.0, 0.005, K))
+    cond = np.zeros(K)
+    best = 1e9
+    for _ in range(3):
+        t0 = time.perf_counter()
+        L.check(lib.isr_cond_spread_scan(p, K, L.dptr(sig), 0, L.dptr(cond), None))
+        best = min(best, (time.perf_counter() - t0) * 1e3)
+    lib.isr_problem_destroy(p)
+    return {"n_points": n, "settings": K, "ms": best, "cond_first": float(cond[0]), "cond_last": float(cond[-1]),
+            "note": "round 1: 1.1 s (100 x cuSOLVER gesvd on 8 streams)"}
 
 
 def cpu_baseline(n, G, bcs0, vcs, err):

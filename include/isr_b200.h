@@ -255,9 +255,10 @@ typedef struct {
   int* refactored_out;       /* 1: certificate failed, pivoted factorisation used */
 } isr_chi2_test_args;
 int isr_chi2_test(isr_problem* p, const isr_chi2_test_args* args);
-/* CUDA-event times (ms, on the context stream) of the three phases of the last isr_chi2_test of this problem:
- * ms_out[0] assembly, [1] factorisation (inverse + certificate + operators), [2] toy kernels. */
-int isr_chi2_test_timing(isr_problem* p, double* ms_out /* 3 */);
+/* CUDA-event times (ms, on the context stream) of the phases of the last isr_chi2_test of this problem:
+ * ms_out[0] assembly, [1] factorisation (inverse + operators; the certificate runs on a side stream), [2] toy kernels,
+ * [3] range + collectives + TH1F cells + copy of the packed result. */
+int isr_chi2_test_timing(isr_problem* p, double* ms_out /* 4 */);
 
 /* ---- several GPUs of one box from ONE process ---------------------------------------------------- */
 /* What a C++ caller of chi2TestModel / ratioTestModel (include/Chi2Test.hpp:18-42, include/RatioTest.hpp:14-15) uses to

@@ -253,7 +253,7 @@ int chi2_test(isr_problem* p, const isr_chi2_test_args& a, TestWants w) {
     return code;
   };
   if (!p->ev_time[0])
-    for (int q = 0; q < 4; ++q) ISR_CUDA(cudaEventCreate(&p->ev_time[q]));
+    for (int q = 0; q < 5; ++q) ISR_CUDA(cudaEventCreate(&p->ev_time[q]));
   cudaEventRecord(p->ev_time[0], st);
   if (do_asm && (rc = assemble(p, a.ecm_err)) != ISR_OK) return drain(rc);
   cudaEventRecord(p->ev_time[1], st);
@@ -296,8 +296,9 @@ int chi2_test(isr_problem* p, const isr_chi2_test_args& a, TestWants w) {
       if ((rc = comm_allreduce(a.comm, d_pack, plen, 0, 0)) != ISR_OK) return drain(rc);
       if (w.rhist && (rc = comm_allreduce(a.comm, p->d_rhist.p, (int64_t)n * 1026, 2, 0)) != ISR_OK) return drain(rc);
     }
-    if (cudaMemcpyAsync(p->pin_test, p->d_pack.p, sizeof(double) * ((size_t)plen + 2), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-        cudaStreamSynchronize(st) != cudaSuccess) {
+    const bool copy_failed = cudaMemcpyAsync(p->pin_test, p->d_pack.p, sizeof(double) * ((size_t)plen + 2), cudaMemcpyDeviceToHost, st) != cudaSuccess;
+    cudaEventRecord(p->ev_time[4], st);
+    if (copy_failed || cudaStreamSynchronize(st) != cudaSuccess) {
       set_error("isr_chi2_test: CUDA error '%s'", cudaGetErrorString(cudaGetLastError()));
       return drain(ISR_ECUDA);
     }
@@ -337,7 +338,7 @@ extern "C" int isr_chi2_test_timing(isr_problem* p, double* ms_out) {
   if (!p || !ms_out) { isr::set_error("isr_chi2_test_timing: NULL argument"); return ISR_EINVAL; }
   if (!p->ev_time[0]) { isr::set_error("isr_chi2_test_timing: no isr_chi2_test has run on this problem"); return ISR_ESTATE; }
   ISR_CUDA(cudaSetDevice(p->ctx->device));
-  for (int q = 0; q < 3; ++q) {
+  for (int q = 0; q < 4; ++q) {
     float ms = 0.f;
     ISR_CUDA(cudaEventElapsedTime(&ms, p->ev_time[q], p->ev_time[q + 1]));
     ms_out[q] = ms;

@@ -79,7 +79,7 @@ struct isr_problem {
   isr::DevBuf<double> d_part;        // per-block {min, max} partials of the range kernel
   isr::DevBuf<unsigned> d_arrive;    // arrival counters of the two fused tail kernels
   double* pin_test = nullptr;
-  cudaEvent_t ev_time[4] = {nullptr, nullptr, nullptr, nullptr};   // start | assembled | factor enqueued | toys enqueued
+  cudaEvent_t ev_time[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // start | assembled | factor enqueued | toys enqueued | results copied
   size_t pin_test_n = 0;
   // host-buffer pipeline (isr_toy_batch): two V slots, chi2 / statistics staging, copy stream
   isr::DevBuf<double> d_Vh, d_chi2h, d_stat, d_Bh;
@@ -92,7 +92,7 @@ struct isr_problem {
       if (ev_done[q]) cudaEventDestroy(ev_done[q]);
     }
     if (copy_stream) cudaStreamDestroy(copy_stream);
-    for (int q = 0; q < 4; ++q) if (ev_time[q]) cudaEventDestroy(ev_time[q]);
+    for (int q = 0; q < 5; ++q) if (ev_time[q]) cudaEventDestroy(ev_time[q]);
     if (pin_cert) cudaFreeHost(pin_cert);
     if (pin_scan) cudaFreeHost(pin_scan);
     if (pin_test) cudaFreeHost(pin_test);

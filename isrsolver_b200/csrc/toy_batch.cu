@@ -150,7 +150,8 @@ static const ToyCfg* pick_cfg(int n, int nstat) {
     // plus ~0.3 k-step per chunk boundary; a mild preference for tall tiles; 8-warp tiles hide latency worse
     const int nk = (ld + c.kc - 1) / c.kc;
     double cost = (double)nblk * c.np * ((ld + 7) / 8 + 0.31 * nk) * (1.0 + 2.0 / c.tm);
-    if (c.threads < 512) cost *= 1.10;   // measured: N=100 25.8 vs 24.9 TFLOP/s
+    if (c.threads < 384) cost *= 1.10;        // 8 warps; measured: N=100 25.8 vs 24.9 TFLOP/s
+    else if (c.threads < 512) cost *= 1.04;   // 12 warps; measured: N=144 30.3 vs N=160 (16 warps) 31.7 TFLOP/s, both exact fits
     if (c.stages < 3 && c.kc == 24) cost *= 1.001;   // tie-break: the deeper ring when nothing else differs
     if (cost < best_cost) { best_cost = cost; best = &c; }
   }
