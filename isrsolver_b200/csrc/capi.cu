@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -414,6 +415,7 @@ int isr_cond_spread_scan(isr_problem* p, int K, const double* sigma, int per_poi
   ISR_CUDA(cudaMemcpyAsync(h_sv.data(), dsv.p, sizeof(double) * K * n, cudaMemcpyDeviceToHost, st));
   ISR_CUDA(cudaMemcpyAsync(h_sw.data(), dsw.p, sizeof(int) * K, cudaMemcpyDeviceToHost, st));
   ISR_CUDA(cudaStreamSynchronize(st));
+  if (std::getenv("ISR_DEBUG_SWEEPS")) { for (int k = 0; k < K; ++k) fprintf(stderr, "%d ", h_sw[k]); fprintf(stderr, "<- Jacobi sweeps per setting\n"); }
   for (int k = 0; k < K; ++k) {
     if (h_sw[k] <= 0) { set_error("isr_cond_spread_scan: the Jacobi sweeps of setting %d did not converge (%d sweeps)", k, -h_sw[k]); return ISR_ENUMERIC; }
     cond_out[k] = h_sv[(size_t)k * n] / h_sv[(size_t)k * n + n - 1];

@@ -82,7 +82,7 @@ jacobi_sv_kernel(int n, double* Abatch, double* __restrict__ svbatch, int* __res
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
         const double alpha = sm_norm[p], beta = sm_norm[q];
-        if (fabs(g) > tol * sqrt(alpha * beta) && alpha > 0.0 && beta > 0.0) {
+        if (g * g > tol * tol * alpha * beta && alpha > 0.0 && beta > 0.0) {
           const double zeta = (beta - alpha) / (2.0 * g);
           const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
           const double c = rsqrt(1.0 + t * t), s = c * t;
@@ -141,7 +141,10 @@ int jacobi_singular_values_batch(isr_ctx* c, cudaStream_t st, int n, int K, doub
   cudaStream_t s = st ? st : c->stream;
   const size_t smem = sizeof(double) * M;
   const int max_sweeps = 40;
-  const double tol = 1e-15;
+  // a pair counts as orthogonal when |a_p . a_q| <= N eps |a_p| |a_q| (LAPACK dgesvj's default CTOL = M): the dot product
+  // of two columns carries about sqrt(N) eps |a_p| |a_q| of rounding noise, so a tighter test (1e-15 was tried: twice the
+  // sweeps) keeps rotating noise
+  const double tol = n * 1.1102230246251565e-16;
   if (n <= 128) { jacobi_sv_kernel<4, 1024><<<K, 1024, smem, s>>>(n, A_batch, sv_batch, sweeps_dev, max_sweeps, tol); }
   else if (n <= 256) { jacobi_sv_kernel<8, 1024><<<K, 1024, smem, s>>>(n, A_batch, sv_batch, sweeps_dev, max_sweeps, tol); }
   else { jacobi_sv_kernel<16, 512><<<K, 512, smem, s>>>(n, A_batch, sv_batch, sweeps_dev, max_sweeps, tol); }
