@@ -55,9 +55,11 @@ __global__ void pack_test_kernel(int nb, int n, const int* __restrict__ cells, c
 // range_kernel: per-block min / max of the chi2 values; the block that arrives LAST (fence + arrival counter) reduces the
 // partials in a fixed order to range = {min, -max} (the layout one all-reduce(MIN) over ranks needs), zeroes the TH1F
 // cells for the next kernel and re-arms the counter.
+// With a peer communicator (use_peer) the last block also EXCHANGES the range with the other GPUs over NVLink mailboxes
+// (peer_device.cuh): the all-reduce(MIN) of the multi-GPU test costs no launch of its own.
 __global__ void __launch_bounds__(256) range_kernel(int64_t n, const double* __restrict__ v, double* __restrict__ part,
-                                                     unsigned* __restrict__ counter, double* __restrict__ range,
-                                                     int* __restrict__ cells, int ncells) {
+                                                     unsigned* __restrict__ counter, double* range,
+                                                     int* __restrict__ cells, int ncells, PeerComm pc, unsigned long long epoch, int use_peer) {
   __shared__ double smin[8], smax[8];
   __shared__ bool last;
   double lo = INFINITY, hi = -INFINITY;
@@ -102,6 +104,10 @@ __global__ void __launch_bounds__(256) range_kernel(int64_t n, const double* __r
   block_reduce();
   if (threadIdx.x == 0) { range[0] = lo; range[1] = -hi; *counter = 0u; }
   for (int q = threadIdx.x; q < ncells; q += blockDim.x) cells[q] = 0;
+  if (use_peer) {
+    __syncthreads();
+    peer_allreduce_block(pc, epoch, range, range, 2, 1);      // {min, -max} over all ranks
+  }
 }
 
 // cells_pack_kernel: TH1F cells of the chi2 values against the (global) range (shared-memory counters, integer atomics),
@@ -110,7 +116,7 @@ __global__ void __launch_bounds__(256) cells_pack_kernel(int64_t n, const double
                                                           const double* __restrict__ range, int* __restrict__ cells,
                                                           unsigned* __restrict__ counter, int npts, const double* __restrict__ stat,
                                                           double toys, const double* __restrict__ cert, int assumed_lower, double tol,
-                                                          double* __restrict__ pack) {
+                                                          double* pack, PeerComm pc, unsigned long long epoch, int use_peer) {
   extern __shared__ uint32_t sh[];
   __shared__ bool last;
   const double lo = range[0], hi = -range[1];
@@ -140,6 +146,10 @@ __global__ void __launch_bounds__(256) cells_pack_kernel(int64_t n, const double
     pack[idx] = val;
   }
   if (threadIdx.x == 0) *counter = 0u;
+  if (use_peer) {
+    __syncthreads();
+    peer_allreduce_block(pc, epoch, pack, pack, len, 0);      // cells, sums, toy count and certificate flag over all ranks
+  }
 }
 
 static int enqueue_toys(isr_problem* p, const isr_chi2_test_args& a, const TestWants& w, bool need_chi2, bool first_attempt) {
@@ -271,16 +281,23 @@ int chi2_test(isr_problem* p, const isr_chi2_test_args& a, TestWants w) {
     cudaEventRecord(p->ev_time[3], st);
     // ---- range, cells, packed buffer, collectives
     const bool cert_here = do_fac && attempt == 0;
+    bool packed_by_peer = false;
     const int assumed = (p->tri_sle[0] || p->tri_sle[1]) ? 1 : 0;
     if (T > 0 && a.nbins > 0) {
       // the usual case: two fused launches (the stat sums of the toy kernels are complete: same stream)
       const int blocks = (int)std::min<int64_t>(c->sm_count * 2, (T + 255) / 256);
-      range_kernel<<<blocks, 256, 0, st>>>(T, p->d_chi2h.p, p->d_part.p, p->d_arrive.p, d_range, p->d_cells.p, nb); ISR_COUNT_LAUNCH();
-      if (a.comm && (rc = comm_allreduce(a.comm, d_range, 2, 0, 1)) != ISR_OK) return drain(rc);
+      // the two exchanges ride inside the tail kernels when the ranks have NVLink mailboxes (else: two NCCL all-reduces)
+      const bool peer = a.comm && a.comm->nranks > 1 && comm_peer_fits(a.comm, plen);
+      PeerComm pc{};
+      unsigned long long e1 = 0, e2 = 0;
+      if (peer) { pc = a.comm->peer; e1 = ++a.comm->epoch; e2 = ++a.comm->epoch; }
+      range_kernel<<<blocks, 256, 0, st>>>(T, p->d_chi2h.p, p->d_part.p, p->d_arrive.p, d_range, p->d_cells.p, nb, pc, e1, peer ? 1 : 0); ISR_COUNT_LAUNCH();
+      if (a.comm && !peer && (rc = comm_allreduce(a.comm, d_range, 2, 0, 1)) != ISR_OK) return drain(rc);
       if (cert_here) cudaStreamWaitEvent(st, c->ev_cert, 0);      // the verdict of the inverse (side stream) enters the packed buffer
       cells_pack_kernel<<<blocks, 256, sizeof(uint32_t) * nb, st>>>(T, p->d_chi2h.p, a.nbins, d_range, p->d_cells.p, p->d_arrive.p + 1, n,
                                                                     p->d_stat.p, (double)T, cert_here ? p->cert_dev : nullptr, assumed,
-                                                                    1e-12 * n, d_pack); ISR_COUNT_LAUNCH();
+                                                                    1e-12 * n, d_pack, pc, e2, peer ? 1 : 0); ISR_COUNT_LAUNCH();
+      packed_by_peer = peer;
     } else {
       if (need_range) {
         if (T > 0) { if ((rc = minmax_to_device(c, T, p->d_chi2h.p, d_range)) != ISR_OK) return drain(rc); }
@@ -293,13 +310,18 @@ int chi2_test(isr_problem* p, const isr_chi2_test_args& a, TestWants w) {
                                                           cert_here ? p->cert_dev : nullptr, assumed, 1e-12 * n, d_pack); ISR_COUNT_LAUNCH();
     }
     if (a.comm) {
-      if ((rc = comm_allreduce(a.comm, d_pack, plen, 0, 0)) != ISR_OK) return drain(rc);
+      if (!packed_by_peer && (rc = comm_allreduce(a.comm, d_pack, plen, 0, 0)) != ISR_OK) return drain(rc);
       if (w.rhist && (rc = comm_allreduce(a.comm, p->d_rhist.p, (int64_t)n * 1026, 2, 0)) != ISR_OK) return drain(rc);
     }
+    if (a.comm && a.comm->peer_ok) cudaMemcpyAsync(a.comm->status_pin, a.comm->peer.status, sizeof(int), cudaMemcpyDeviceToHost, st);
     const bool copy_failed = cudaMemcpyAsync(p->pin_test, p->d_pack.p, sizeof(double) * ((size_t)plen + 2), cudaMemcpyDeviceToHost, st) != cudaSuccess;
     cudaEventRecord(p->ev_time[4], st);
     if (copy_failed || cudaStreamSynchronize(st) != cudaSuccess) {
       set_error("isr_chi2_test: CUDA error '%s'", cudaGetErrorString(cudaGetLastError()));
+      return drain(ISR_ECUDA);
+    }
+    if (a.comm && a.comm->peer_ok && *a.comm->status_pin != 0) {
+      set_error("isr_chi2_test: a rank of the communicator did not take part in the exchange (peer mailbox timed out)");
       return drain(ISR_ECUDA);
     }
     bool redone = false;

@@ -35,6 +35,7 @@ struct NcclApi {
   int (*CommInitAll)(ncclComm_t*, int, const int*);
   int (*CommDestroy)(ncclComm_t);
   int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t);
   const char* (*GetErrorString)(int);
   int (*GroupStart)();
   int (*GroupEnd)();
@@ -60,6 +61,7 @@ static NcclApi* nccl_api() {
     ISR_NCCL_SYM(CommInitAll, "ncclCommInitAll")
     ISR_NCCL_SYM(CommDestroy, "ncclCommDestroy")
     ISR_NCCL_SYM(AllReduce, "ncclAllReduce")
+    ISR_NCCL_SYM(AllGather, "ncclAllGather")
     ISR_NCCL_SYM(GetErrorString, "ncclGetErrorString")
     ISR_NCCL_SYM(GroupStart, "ncclGroupStart")
     ISR_NCCL_SYM(GroupEnd, "ncclGroupEnd")
@@ -82,9 +84,19 @@ static NcclApi* nccl_api() {
     }                                                                                                    \
   } while (0)
 
+// the mailbox exchange as a kernel of its own (callers that cannot fuse it into a producer kernel)
+__global__ void __launch_bounds__(256) peer_allreduce_kernel(PeerComm pc, unsigned long long epoch, double* buf, int len, int op) {
+  peer_allreduce_block(pc, epoch, buf, buf, len, op);
+}
+
 int comm_allreduce(isr_comm* cm, void* buf, int64_t count, int dtype, int op) {
   if (!cm || !buf || count < 0) { set_error("isr_comm_allreduce_dev: bad argument"); return ISR_EINVAL; }
   if (count == 0 || cm->nranks == 1) return ISR_OK;
+  if (dtype == 0 && op <= 1 && comm_peer_fits(cm, count)) {      // small FP64 sum / min: NVLink mailboxes, rank-ordered
+    peer_allreduce_kernel<<<1, 256, 0, cm->ctx->stream>>>(cm->peer, ++cm->epoch, static_cast<double*>(buf), (int)count, op); ISR_COUNT_LAUNCH();
+    ISR_CUDA(cudaGetLastError());
+    return ISR_OK;
+  }
   static const int dt[4] = {kNcclFloat64, kNcclInt32, kNcclUint32, kNcclInt64};
   static const int ops[3] = {kNcclSum, kNcclMin, kNcclMax};
   if (dtype < 0 || dtype > 3 || op < 0 || op > 2) { set_error("isr_comm_allreduce_dev: unknown dtype / op"); return ISR_EINVAL; }
@@ -181,6 +193,94 @@ ScopedNodeBinding::~ScopedNodeBinding() {
   if (saved_ok && node >= 0) sched_setaffinity(0, sizeof(saved), &saved);
 }
 
+// ---- NVLink mailboxes ---------------------------------------------------------------------------------------------------
+static bool peer_disabled() { const char* e = std::getenv("ISR_NO_P2P"); return e && e[0] == '1'; }
+
+static int peer_alloc(isr_comm* cm) {
+  ISR_CUDA(cudaSetDevice(cm->ctx->device));
+  ISR_CUDA(cudaMalloc((void**)&cm->my_box, kPeerBoxBytes + sizeof(int)));
+  ISR_CUDA(cudaMemset(cm->my_box, 0, kPeerBoxBytes + sizeof(int)));
+  cm->peer.rank = cm->rank; cm->peer.nranks = cm->nranks;
+  cm->peer.status = reinterpret_cast<int*>(reinterpret_cast<char*>(cm->my_box) + kPeerBoxBytes);
+  ISR_CUDA(cudaMallocHost((void**)&cm->status_pin, sizeof(int)));
+  *cm->status_pin = 0;
+  return ISR_OK;
+}
+static void peer_release(isr_comm* cm) {
+  if (!cm->my_box) return;
+  cudaSetDevice(cm->ctx->device);
+  if (cm->peer_ipc)
+    for (int r = 0; r < cm->nranks; ++r)
+      if (r != cm->rank && cm->peer.box[r]) cudaIpcCloseMemHandle(cm->peer.box[r]);
+  cudaFree(cm->my_box);
+  if (cm->status_pin) cudaFreeHost(cm->status_pin);
+  cm->my_box = nullptr; cm->peer_ok = false;
+}
+// one process per GPU: mailboxes exchanged as CUDA IPC handles through ONE ncclAllGather; agreement on success through one
+// ncclAllReduce(MIN) (a rank that cannot map a peer switches everybody back to NCCL)
+static int peer_setup_ipc(isr_comm* cm, NcclApi* api) {
+  if (cm->nranks > kPeerMaxRanks) return ISR_OK;
+  int ok = peer_disabled() ? 0 : 1;
+  if (ok && peer_alloc(cm) != ISR_OK) ok = 0;
+  cudaStream_t st = cm->ctx->stream;
+  cudaIpcMemHandle_t mine;
+  std::memset(&mine, 0, sizeof(mine));
+  if (ok && cudaIpcGetMemHandle(&mine, cm->my_box) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+  DevBuf<char> dsend, drecv;
+  DevBuf<int> dflag;
+  ISR_TRY(dsend.reserve(sizeof(mine))); ISR_TRY(drecv.reserve(sizeof(mine) * cm->nranks)); ISR_TRY(dflag.reserve(1));
+  ISR_CUDA(cudaMemcpyAsync(dsend.p, &mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+  ISR_NCCL(api, api->AllGather(dsend.p, drecv.p, sizeof(mine), /*ncclInt8*/ 0, (ncclComm_t)cm->nccl, st));
+  std::vector<cudaIpcMemHandle_t> all(cm->nranks);
+  ISR_CUDA(cudaMemcpyAsync(all.data(), drecv.p, sizeof(mine) * cm->nranks, cudaMemcpyDeviceToHost, st));
+  ISR_CUDA(cudaStreamSynchronize(st));
+  if (ok) {
+    for (int r = 0; r < cm->nranks && ok; ++r) {
+      if (r == cm->rank) { cm->peer.box[r] = cm->my_box; continue; }
+      void* ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+      cm->peer.box[r] = static_cast<double*>(ptr);
+    }
+    cm->peer_ipc = true;
+  }
+  ISR_CUDA(cudaMemcpyAsync(dflag.p, &ok, sizeof(int), cudaMemcpyHostToDevice, st));
+  ISR_NCCL(api, api->AllReduce(dflag.p, dflag.p, 1, kNcclInt32, kNcclMin, (ncclComm_t)cm->nccl, st));     // also the barrier: all mailboxes zeroed and mapped
+  int all_ok = 0;
+  ISR_CUDA(cudaMemcpyAsync(&all_ok, dflag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  ISR_CUDA(cudaStreamSynchronize(st));
+  cm->peer_ok = all_ok == 1;
+  if (!cm->peer_ok) peer_release(cm);
+  return ISR_OK;
+}
+// one process, several GPUs: peer access
+static int peer_setup_local(int n, isr_comm** cms) {
+  if (n > kPeerMaxRanks || peer_disabled()) return ISR_OK;
+  bool ok = true;
+  for (int r = 0; r < n && ok; ++r) ok = peer_alloc(cms[r]) == ISR_OK;
+  for (int r = 0; r < n && ok; ++r) {
+    cudaSetDevice(cms[r]->ctx->device);
+    for (int q = 0; q < n && ok; ++q) {
+      if (q == r) continue;
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, cms[r]->ctx->device, cms[q]->ctx->device);
+      if (!can) { ok = false; break; }
+      cudaError_t e = cudaDeviceEnablePeerAccess(cms[q]->ctx->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = false;
+      cudaGetLastError();
+    }
+  }
+  for (int r = 0; r < n; ++r) {
+    if (ok) {
+      for (int q = 0; q < n; ++q) cms[r]->peer.box[q] = cms[q]->my_box;
+      cms[r]->peer_ok = true;
+    } else {
+      peer_release(cms[r]);
+    }
+  }
+  for (int r = 0; r < n; ++r) { cudaSetDevice(cms[r]->ctx->device); cudaDeviceSynchronize(); }
+  return ISR_OK;
+}
+
 }  // namespace isr
 
 using namespace isr;
@@ -214,6 +314,8 @@ int isr_comm_init_rank(isr_ctx* ctx, int nranks, int rank, const void* id, isr_c
     int r = api->CommInitRank(&c, nranks, uid, rank);
     if (r != 0) { set_error("ncclCommInitRank failed: %s", api->GetErrorString(r)); delete cm; return ISR_ECUDA; }
     cm->nccl = c;
+    const int rc = peer_setup_ipc(cm, api);
+    if (rc != ISR_OK) { isr_comm_destroy(cm); return rc; }
   }
   *out = cm;
   return ISR_OK;
@@ -241,11 +343,13 @@ int isr_comm_init_all(int n, isr_ctx* const* ctxs, isr_comm** out) {
     cm->ctx = ctxs[r]; cm->rank = r; cm->nranks = n; cm->nccl = cs[r];
     out[r] = cm;
   }
+  if (n > 1) ISR_TRY(peer_setup_local(n, out));
   return ISR_OK;
 }
 
 void isr_comm_destroy(isr_comm* cm) {
   if (!cm) return;
+  peer_release(cm);
   if (cm->nccl) {
     NcclApi* api = nccl_api();
     if (api) { cudaSetDevice(cm->ctx->device); api->CommDestroy((ncclComm_t)cm->nccl); }
