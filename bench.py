@@ -369,8 +369,9 @@ def run_b200(args, rank, world, local_rank):
                               "note": "same chi2 test with toys drawn on the device (Philox4x32-10 + Box-Muller, as the reference's "
                                       "chi2Test(n) draws them internally); NOT the e2e figure -- its toy vectors never cross PCIe"},
         "gpu_launches": int(launches), "clocks": clocks,
-        "collectives": "none (1 GPU)" if world == 1 else "per step, inside isr_chi2_test on its stream: ncclAllReduce(MIN) of {min, -max} (2 doubles) + "
-                       "ncclAllReduce(SUM) of one packed FP64 buffer [130 cells | sum b (N) | ratio stats (3N) | toys | flag]",
+        "collectives": "none (1 GPU)" if world == 1 else "per step, inside isr_chi2_test: all-reduce(MIN) of {min, -max} (2 doubles) + all-reduce(SUM) of one "
+                       "packed FP64 buffer [130 cells | sum b (N) | ratio stats (3N) | toys | flag], via " +
+                       ("NVLink peer-memory mailboxes fused into the range / cells kernels" if lib.isr_comm_uses_peer_memory(comm) else "ncclAllReduce on the context stream"),
         "target_strong": strong,
     }
     line["assembly_other_configs"] = other_assemblies(lib, ctx, stream, torch)

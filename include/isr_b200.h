@@ -212,6 +212,10 @@ int isr_comm_unique_id(void* id_out /* ISR_COMM_ID_BYTES */);
 int isr_comm_init_rank(isr_ctx* ctx, int nranks, int rank, const void* id, isr_comm** out);
 int isr_comm_init_all(int n, isr_ctx* const* ctxs, isr_comm** out /* n */);
 void isr_comm_destroy(isr_comm* comm);
+/* 1 if the small exchanges of this communicator go over NVLink peer-memory mailboxes (fused into the kernels that
+ * produce / consume them; rank-ordered, hence bit-reproducible sums), 0 if they are NCCL all-reduces (peers not mappable,
+ * more than 16 ranks, or ISR_NO_P2P=1 in the environment). */
+int isr_comm_uses_peer_memory(const isr_comm* comm);
 int isr_comm_rank(const isr_comm* comm);
 int isr_comm_size(const isr_comm* comm);
 /* In-place all-reduce of a device buffer on the context stream (asynchronous).  dtype: 0 double, 1 int32, 2 uint32,

@@ -111,6 +111,7 @@ SIGNATURES = {
     "isr_comm_init_rank": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.POINTER(_vp)]),
     "isr_comm_init_all": (C.c_int, [C.c_int, C.POINTER(_vp), C.POINTER(_vp)]),
     "isr_comm_destroy": (None, [_vp]),
+    "isr_comm_uses_peer_memory": (C.c_int, [_vp]),
     "isr_comm_rank": (C.c_int, [_vp]),
     "isr_comm_size": (C.c_int, [_vp]),
     "isr_comm_allreduce_dev": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int]),

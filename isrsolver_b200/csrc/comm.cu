@@ -357,6 +357,7 @@ void isr_comm_destroy(isr_comm* cm) {
   delete cm;
 }
 
+int isr_comm_uses_peer_memory(const isr_comm* cm) { return (cm && cm->peer_ok) ? 1 : 0; }
 int isr_comm_rank(const isr_comm* cm) { return cm ? cm->rank : -1; }
 int isr_comm_size(const isr_comm* cm) { return cm ? cm->nranks : 0; }
 

@@ -445,29 +445,39 @@ toy_fused_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant
               }
             }
             if (stats) {
-              // fixed-order reduction over the 8 toy lanes; lane gq == 0 owns slot (wm, stat, column): no
-              // other thread of the CTA ever touches it, so the running sum needs no barrier or atomic.
+              // Fixed-order reduction over the 8 toy lanes (gq = lane bits 2..4) as a REDUCE-SCATTER: the 2 (nstat = 1) or
+              // 8 (nstat = 4) per-thread partial sums {stat, column e} are halved at every butterfly stage, so that after
+              // the xor-16 / xor-8 / xor-4 stages each of the 8 lanes holds ONE complete sum -- 7 shuffles instead of 24
+              // (3 instead of 6 for nstat = 1; the replicated all-reduce form cost the C5 test 9 %).  Lane gq owns slot
+              // (wm, stat, column) of value index gq: no other thread of the CTA ever touches it, so the running sum
+              // needs no barrier or atomic, and the summation order is fixed (bit-reproducible).
+              const bool h4 = (lane & 16) != 0, h2 = (lane & 8) != 0, h1 = (lane & 4) != 0;
+              double* pp = sAcc + (size_t)wm * g.nstat * accw;
+              const int lc0 = n0 + ctile(j) * 8 + 2 * c;
+              if (g.nstat == 4) {
+                // v[k]: k = 4 e + stat
+                double v[8] = {cs[0], cn[0], cr[0], cq[0], cs[1], cn[1], cr[1], cq[1]};
+                double w[4], x[2];
 #pragma unroll
-              for (int e = 0; e < 2; ++e) {
+                for (int k = 0; k < 4; ++k) {
+                  const double send = h4 ? v[k] : v[k + 4], keep = h4 ? v[k + 4] : v[k];
+                  w[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
 #pragma unroll
-                for (int sft = 4; sft <= 16; sft <<= 1) {
-                  cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], sft);
-                  if (g.nstat == 4) {
-                    cn[e] += __shfl_xor_sync(0xffffffffu, cn[e], sft);
-                    cr[e] += __shfl_xor_sync(0xffffffffu, cr[e], sft);
-                    cq[e] += __shfl_xor_sync(0xffffffffu, cq[e], sft);
-                  }
+                for (int k = 0; k < 2; ++k) {
+                  const double send = h2 ? w[k] : w[k + 2], keep = h2 ? w[k + 2] : w[k];
+                  x[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
                 }
-                if (gq == 0) {
-                  const int lc = n0 + ctile(j) * 8 + 2 * c + e;
-                  double* pp = sAcc + (size_t)wm * g.nstat * accw;
-                  pp[lc] += cs[e];
-                  if (g.nstat == 4) {
-                    pp[1 * accw + lc] += cn[e];
-                    pp[2 * accw + lc] += cr[e];
-                    pp[3 * accw + lc] += cq[e];
-                  }
-                }
+                const double send = h1 ? x[0] : x[1], keep = h1 ? x[1] : x[0];
+                const double y = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                const int e = h4 ? 1 : 0, stat = (h2 ? 2 : 0) + (h1 ? 1 : 0);
+                pp[stat * accw + lc0 + e] += y;
+              } else {
+                const double send = h4 ? cs[0] : cs[1], keep = h4 ? cs[1] : cs[0];
+                double y = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                y += __shfl_xor_sync(0xffffffffu, y, 8);
+                y += __shfl_xor_sync(0xffffffffu, y, 4);
+                if ((lane & 12) == 0) pp[lc0 + (h4 ? 1 : 0)] += y;
               }
             }
           }
