@@ -287,6 +287,8 @@ void isr_group_host_free(isr_group* g, double* ptr);
  * and args->V_dev must be NULL; chi2_out receives all n_toys values in toy order, the other outputs are global.
  * Histogram cells are bit-identical to the single-GPU test (every rank bins against the global range). */
 int isr_group_chi2_test(isr_gproblem* gp, const isr_chi2_test_args* args);
+/* isr_cond_spread_scan with the K spread settings cut into one contiguous slice per GPU (no exchange at all). */
+int isr_group_cond_spread_scan(isr_gproblem* gp, int K, const double* sigma, int per_point, double* cond_out, double* sv_out);
 
 /* ---- Tikhonov --------------------------------------------------------------------------------- */
 /* One decomposition shared by every lambda (replaces _evalProblemMatrices + two FullPivLU per lambda,
@@ -335,6 +337,9 @@ typedef struct {
   int64_t* total_toys_out; /* or NULL */
 } isr_tikhonov_scan_args;
 int isr_tikhonov_chi2_scan(isr_problem* p, const isr_tikhonov_scan_args* args);
+/* The same over all GPUs of an isr_group from one process: args->n_toys is the TOTAL, args->V the whole host array;
+ * args->comm and args->V_dev must be NULL. */
+int isr_group_tikhonov_chi2_scan(isr_gproblem* gp, const isr_tikhonov_scan_args* args);
 /* (lambda, toy) scan variant: 0 (default) = chi2 as a quadratic form in lambda from two dot products per toy
  * (O(1) per pair, bound by writing the output); 1 = the direct O(N)-per-pair kernel (kept as a cross-check). */
 int isr_set_scan_kernel(isr_problem* p, int variant);

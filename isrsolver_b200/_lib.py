@@ -128,6 +128,8 @@ SIGNATURES = {
     "isr_group_host_alloc": (C.c_int, [_vp, _i64, C.c_int, C.POINTER(_dp)]),
     "isr_group_host_free": (None, [_vp, _dp]),
     "isr_group_chi2_test": (C.c_int, [_vp, C.POINTER(Chi2TestArgs)]),
+    "isr_group_cond_spread_scan": (C.c_int, [_vp, C.c_int, _dp, C.c_int, _dp, _dp]),
+    "isr_group_tikhonov_chi2_scan": (C.c_int, [_vp, C.POINTER(TikhonovScanArgs)]),
     "isr_tikhonov_prepare": (C.c_int, [_vp, _dp, C.c_int]),
     "isr_tikhonov_scan": (C.c_int, [_vp, _i64, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "isr_tikhonov_solve": (C.c_int, [_vp, C.c_double, _dp, _dp, _dp]),

@@ -218,4 +218,39 @@ int isr_group_chi2_test(isr_gproblem* gp, const isr_chi2_test_args* args) {
   });
 }
 
+// Condition number versus beam-energy spread (src/isrsolver-condnum-test.cpp:88-140) with the K settings cut into
+// contiguous slices, one per GPU: no exchange at all (every GPU assembles the unspread matrix itself).
+int isr_group_cond_spread_scan(isr_gproblem* gp, int K, const double* sigma, int per_point, double* cond_out, double* sv_out) {
+  if (!gp || !sigma || !cond_out || K < 0) { set_error("isr_group_cond_spread_scan: bad argument"); return ISR_EINVAL; }
+  isr_group* g = gp->g;
+  const int n = gp->n;
+  return g->run_all([&](int r) {
+    int64_t b, e;
+    shard_bounds(K, g->n, r, &b, &e);
+    if (e == b) return (int)ISR_OK;
+    const size_t per = per_point ? (size_t)n : 1;
+    return isr_cond_spread_scan(gp->p[r], (int)(e - b), sigma + (size_t)b * per, per_point, cond_out + b,
+                                sv_out ? sv_out + (size_t)b * n : nullptr);
+  });
+}
+
+// isr_tikhonov_chi2_scan over all GPUs of the group: args->n_toys is the TOTAL and args->V the whole host array; every
+// rank takes a contiguous slice of the toys, the per-lambda summaries returned are global (written by rank 0).
+int isr_group_tikhonov_chi2_scan(isr_gproblem* gp, const isr_tikhonov_scan_args* args) {
+  if (!gp || !args) { set_error("isr_group_tikhonov_chi2_scan: NULL argument"); return ISR_EINVAL; }
+  if (args->comm || args->V_dev) { set_error("isr_group_tikhonov_chi2_scan: comm and V_dev must be NULL (the group owns the communicators)"); return ISR_EINVAL; }
+  isr_group* g = gp->g;
+  const int n = gp->n;
+  return g->run_all([&](int r) {
+    isr_tikhonov_scan_args a = *args;
+    int64_t b, e;
+    shard_bounds(args->n_toys, g->n, r, &b, &e);
+    a.n_toys = e - b;
+    if (args->V) a.V = args->V + (size_t)b * n;
+    a.comm = g->comm[r];
+    if (r != 0) { a.stats_out = nullptr; a.counts_out = nullptr; a.total_toys_out = nullptr; }
+    return isr_tikhonov_chi2_scan(gp->p[r], &a);
+  });
+}
+
 }  // extern "C"

@@ -63,21 +63,27 @@ def all_gather_results(chi2, sum_bcs, ratio_stats, total: int, device=None):
     return unpack(out.view(world, mine.numel()).cpu().numpy(), total, world, n)
 
 
-def histogram_sharded(chi2_local, sum_bcs, ratio_stats, nbins: int = 128, count_fn=None, device=None):
+def histogram_sharded(chi2_local, sum_bcs, ratio_stats, nbins: int = 128, count_fn=None, device=None, local_range=None):
     """The chi2 test over all ranks' toys without gathering them.
 
     Returns (counts[nbins + 2] int64 summed over ranks, lo, hi, sum_bcs, ratio_stats): bit-identical to the
     single-process TH1F(nbins, min, max) of the concatenated values because every rank bins against the GLOBAL
-    range and integer counters add exactly.  count_fn(lo, hi) -> counts lets the caller bin on the GPU
-    (isr_histogram_dev); the default bins `chi2_local` on the host.  Two collectives, both O(N) bytes."""
+    range and integer counters add exactly (sum_bcs / ratio_stats are float sums re-associated across ranks: equal
+    to rounding, not bit for bit).  count_fn(lo, hi) -> counts lets the caller bin on the GPU (isr_histogram_dev);
+    the default bins `chi2_local` on the host.  local_range = (lo, hi): this rank's range when the chi2 values stay
+    on the device (chi2_local may then be empty).  An EMPTY shard (fewer toys than ranks) contributes (+inf, -inf)
+    and zero counts.  Two collectives, both O(N) bytes."""
     import torch
     import torch.distributed as dist
 
     world = dist.get_world_size()
     chi2_local = np.asarray(chi2_local, dtype=np.float64)
     n = len(sum_bcs)
-    lo = chi2_local.min() if chi2_local.size else np.inf
-    hi = chi2_local.max() if chi2_local.size else -np.inf
+    if local_range is not None:
+        lo, hi = float(local_range[0]), float(local_range[1])
+    else:
+        lo = chi2_local.min() if chi2_local.size else np.inf
+        hi = chi2_local.max() if chi2_local.size else -np.inf
     mine = torch.from_numpy(np.concatenate([[lo, hi], np.asarray(sum_bcs, dtype=np.float64),
                                             np.asarray(ratio_stats, dtype=np.float64).reshape(-1)]))
     if device is not None:

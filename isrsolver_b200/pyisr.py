@@ -589,13 +589,17 @@ class ISRSolverSLE(BaseISRSolver):
         process per GPU): rank r draws and processes toys [begin_r, end_r) of the device stream `seed`
         (toy k depends only on (seed, k)), then the TH1F(nbins, min, max) is combined with two O(N)-byte
         collectives (dist.histogram_sharded) -- chi2 never leaves the GPUs.  Every rank returns the same
-        result, bit-identical to toy_campaign(n) on one GPU."""
+        result; the histogram and its range are bit-identical to toy_campaign(n) on one GPU (sum_bcs / ratio_stats agree
+        to rounding: float sums are re-associated across ranks).  Ranks without toys (n < world) are legal."""
         import torch.distributed as td
         from . import dist as D
         rank, world = td.get_rank(), td.get_world_size()
         b, e = D.shard_bounds(int(n), world, rank)
-        r = self.toy_campaign(e - b, vcs, vcs_err, bcs0, seed, first_toy=b, want_chi2=False, want_sum=True,
-                              want_ratio=True, want_chi2_hist=True, nbins=nbins)
+        if e > b:
+            r = self.toy_campaign(e - b, vcs, vcs_err, bcs0, seed, first_toy=b, want_chi2=False, want_sum=True,
+                                  want_ratio=True, want_chi2_hist=True, nbins=nbins)
+        else:
+            r = {"lo": np.inf, "hi": -np.inf, "sum_bcs": np.zeros(self._n), "ratio_stats": np.zeros((self._n, 3))}
         counts = np.zeros(nbins + 2, dtype=np.uint32)
 
         def rebin(lo, hi):
@@ -605,10 +609,9 @@ class ISRSolverSLE(BaseISRSolver):
         if td.get_backend() == "nccl":
             import torch
             dev = torch.device("cuda", torch.cuda.current_device())
-        lo = r["lo"] if e > b else np.inf
-        hi = r["hi"] if e > b else -np.inf
-        cnt, glo, ghi, sb, rs = D.histogram_sharded(np.array([lo, hi]), r["sum_bcs"], r["ratio_stats"], nbins,
-                                                    count_fn=rebin if e > b else (lambda lo, hi: counts), device=dev)
+        cnt, glo, ghi, sb, rs = D.histogram_sharded(np.empty(0), r["sum_bcs"], r["ratio_stats"], nbins,
+                                                    count_fn=rebin if e > b else (lambda lo, hi: counts), device=dev,
+                                                    local_range=(r["lo"], r["hi"]))
         return {"hist": cnt.astype(np.float32), "lo": glo, "hi": ghi, "sum_bcs": sb, "ratio_stats": rs, "n": int(n)}
 
     def chi2_test(self, n, vcs, bcs0, vcs_err, seed=TOY_SEED, toys=None, rng="host"):

@@ -347,3 +347,52 @@ def test_tikhonov_chi2_scan_toys_sharded(ngpu):
     for r in range(ngpu):
         lib.isr_comm_destroy(comms[r]); lib.isr_ctx_destroy(ctxs[r])
     lib.isr_problem_destroy(p1)
+
+
+@pytest.mark.parametrize("ngpu", [1, 2, 4])
+def test_group_scans_equal_single_gpu(ngpu):
+    """The two other sharded loops from ONE process: the condition-number-vs-spread scan (settings cut over the GPUs, no
+    exchange) and BASELINE config C4 (per-lambda chi2 test, toys cut over the GPUs) -- identical to the single-GPU calls."""
+    if _gpu_count() < ngpu:
+        pytest.skip(f"needs {ngpu} GPUs")
+    L, lib = _lib()
+    g = load_golden("c4_tikhonov_n32_spread")
+    n = len(g["ecm"])
+    st = np.ascontiguousarray(g["settings"], dtype=np.int32)
+    ecm = np.ascontiguousarray(g["ecm"])
+    grp = _group(L, lib, ngpu)
+    gp = C.c_void_p()
+    L.check(lib.isr_group_problem_create(grp, n, L.dptr(ecm), float(g["threshold"]), len(st), L.iptr(st), None, C.byref(gp)))
+    p1 = _problem(L, lib, _ctx(), ecm, float(g["threshold"]), st)
+    # --- cond scan: 11 settings (ragged slices), first one with the spread off
+    K = 11
+    sig = np.ascontiguousarray(np.linspace(0.0, 0.004, K))
+    c1, s1, cg, sg = np.zeros(K), np.zeros((K, n)), np.zeros(K), np.zeros((K, n))
+    L.check(lib.isr_cond_spread_scan(p1, K, L.dptr(sig), 0, L.dptr(c1), L.dptr(s1)))
+    L.check(lib.isr_group_cond_spread_scan(gp, K, L.dptr(sig), 0, L.dptr(cg), L.dptr(sg)))
+    np.testing.assert_array_equal(sg, s1)
+    np.testing.assert_array_equal(cg, c1)
+    # --- C4: assemble (with spread) + eigen-system + chi2 test of 3001 toys for 19 lambdas, in one call
+    T, Lm = 3001, 19
+    rng = np.random.default_rng(8)
+    err = np.ascontiguousarray(g["vcs_err"]); b0 = np.ascontiguousarray(g["bcs0"]); eerr = np.ascontiguousarray(g["ecm_err"])
+    V = np.ascontiguousarray(g["vcs"][None, :] + err[None, :] * rng.standard_normal((T, n)))
+    lam = np.ascontiguousarray(10.0 ** np.linspace(-8, 0, Lm))
+
+    def scan(call, prob):
+        stt = np.zeros((Lm, 3)); cn = np.zeros((Lm, 130), dtype=np.uint32); tot = C.c_int64()
+        a = L.TikhonovScanArgs()
+        a.flags, a.ecm_err, a.vcs_err, a.deriv_reg = L.ISR_TEST_ASSEMBLE | L.ISR_TEST_FACTOR, L.dptr(eerr), L.dptr(err), 1
+        a.n_lambda, a.lambda_, a.n_toys, a.V, a.bcs0, a.nbins = Lm, L.dptr(lam), T, L.dptr(V), L.dptr(b0), 128
+        a.stats_out, a.counts_out, a.total_toys_out = L.dptr(stt), L.uptr(cn), C.pointer(tot)
+        L.check(call(prob, C.byref(a)))
+        return stt, cn, tot.value
+    s_one, c_one, t_one = scan(lib.isr_tikhonov_chi2_scan, p1)
+    s_grp, c_grp, t_grp = scan(lib.isr_group_tikhonov_chi2_scan, gp)
+    assert t_one == T and t_grp == T and int(c_grp.sum()) == Lm * T
+    np.testing.assert_array_equal(c_grp, c_one)
+    np.testing.assert_array_equal(s_grp[:, :2], s_one[:, :2])
+    np.testing.assert_allclose(s_grp[:, 2], s_one[:, 2], rtol=1e-12)
+    lib.isr_problem_destroy(p1)
+    lib.isr_group_problem_destroy(gp)
+    lib.isr_group_destroy(grp)

@@ -357,6 +357,16 @@ assert np.array_equal(h, th1_counts(chi2_all, 128, chi2_all.min(), chi2_all.max(
 cnt, lo, hi, sb2, rs2 = histogram_sharded(chi2_all[b:e], B[b:e].sum(0), stats)
 assert (lo, hi) == (chi2_all.min(), chi2_all.max()) and np.array_equal(cnt, h.astype(np.int64))
 assert np.allclose(sb2, B.sum(0), rtol=1e-13) and np.allclose(rs2, rs, rtol=1e-13)
+# fewer values than ranks: rank 1's shard is empty -- the global range must not become (-inf, +inf)  (ADVICE r1)
+one = np.array([3.25])
+mine = one if rank == 0 else np.empty(0)
+cnt1, lo1, hi1, _, _ = histogram_sharded(mine, np.zeros(n), np.zeros((n, 3)))
+assert (lo1, hi1) == (3.25, 3.25) and cnt1.sum() == 1
+# ... and with the values on the "device": only the local range is passed
+cnt2, lo2, hi2, _, _ = histogram_sharded(np.empty(0), np.zeros(n), np.zeros((n, 3)),
+                                         count_fn=lambda lo, hi: th1_counts(mine, 128, lo, hi),
+                                         local_range=(3.25, 3.25) if rank == 0 else (np.inf, -np.inf))
+assert (lo2, hi2) == (3.25, 3.25) and np.array_equal(cnt2, cnt1)
 dist.destroy_process_group()
 print("rank", rank, "ok")
 """
