@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(256) inverse_residual_kernel(int n, const doub
 // zeros).  No pivoting: the caller certifies the result (lu_inverse) and falls back to the pivoted LU otherwise.
 // --------------------------------------------------------------------------------------------------
 constexpr int kGjMaxN = 256, kGjColsPerLane = kGjMaxN / 32;   // 8 columns (4 pairs) per lane
-constexpr int kGjDefaultCtas = 8;
+constexpr int kGjDefaultCtas = 8, kGjDefaultRows = 4;   // measured (tools/exp_factor.py, N = 200): RW 4 / 8 = 144.7 / 147.9 us with 8 CTAs, 159 / 159 us with 4
 constexpr int kGjMaxRows = 240;   // 15 arithmetic warps + the forwarder = 512 threads per CTA: 128 registers each
 namespace gj {
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -216,23 +216,32 @@ struct GjSmem {
   uint64_t rfull[kGjSlots], lfull[kGjSlots], empty[kGjSlots], done[kGjSlots];
 };
 
-// kGjCtas (template): CTAs of the cluster.  4 CTAs x 15 warps put four arithmetic warps on every SM sub-partition, where the
-// owner warp's dependent chain competes with three others for the FP64 pipe; 8 CTAs x 8 warps halve that contention (the
-// cluster size is a launch attribute: cudaLaunchKernelEx).
-template <int kGjCtas>
-__global__ void __launch_bounds__(512, 1)
+// kGjCtas (template): CTAs of the cluster; RW (template): matrix rows per warp, 4 or 8.  Pivots are always processed in
+// blocks of four (block B = rows / pivots 4 B .. 4 B + 3); a warp with RW = 8 owns TWO consecutive blocks.
+// Round-2 trace of the 4-row layout (tools/exp_gj_trace.py): per block of four pivots 3030 cycles, of which the next owner's
+// update of its rows takes 1350 (for 256 issue cycles of FMAs) and the owner's elimination 1050.  RW = 8 was built to test
+// whether shared-memory / shuffle traffic and FP64-pipe sharing explain that: the same pivot-row read serves twice the
+// rows, there is ONE arithmetic warp per sub-partition (8 CTAs x 4 warps), and every second hand-over stays inside a warp
+// (the owner eliminates block B from its other four rows in registers and goes straight on to block B + 1).  Measured:
+// within-warp transitions 2400 cycles, the others 3300 -- no net gain (N = 200: 147.9 against 144.7 us per isr_factor), so
+// RW = 4 stays the default; ISR_GJ_RW=8 selects the other layout.
+template <int J> struct GjIntC { static constexpr int value = J; };
+
+template <int kGjCtas, int RW>
+__global__ void __launch_bounds__(RW == 8 ? (kGjCtas == 4 ? 288 : (kGjCtas == 8 ? 160 : 96)) : (kGjCtas == 4 ? 512 : (kGjCtas == 8 ? 288 : 160)), 1)
 gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, double* __restrict__ cert,
                   double* __restrict__ Xrow, int ld) {
   constexpr uint32_t kRowBytes = kGjMaxN * sizeof(double);
+  constexpr int RQ = RW / 4;                                    // pivot blocks per warp
   extern __shared__ __align__(128) unsigned char gj_smem_raw[];
   GjSmem& sm = *reinterpret_cast<GjSmem*>(gj_smem_raw);
   uint32_t rank;
   asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(rank));
-  const int R = 4 * ((n + 4 * kGjCtas - 1) / (4 * kGjCtas));   // rows per CTA: whole warps
+  const int R = RW * ((n + RW * kGjCtas - 1) / (RW * kGjCtas));   // rows per CTA: whole warps
   const int NB = (n + 3) / 4;                                  // pivot blocks; block B = rows / pivots 4 B .. 4 B + 3
   const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int nwarps = (blockDim.x >> 5) - 1;   // arithmetic warps; the last warp forwards the credits
-  const int row0 = (int)rank * R, wrow = row0 + 4 * warp;      // first of this warp's four rows
+  const int row0 = (int)rank * R, wrow = row0 + RW * warp;     // first of this warp's RW rows
   const int Bs = row0 >> 2, Be = min(NB, Bs + (R >> 2));       // blocks whose pivot rows this CTA owns
   auto block_bytes = [&](int B) { return (uint32_t)min(4, n - 4 * B) * kRowBytes; };
   const GjPhases ph{NB, Bs, Be};
@@ -250,14 +259,14 @@ gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, d
       if (B >= 0 && B < NB) gj::mbar_expect_tx(&sm.rfull[q], block_bytes(B));
     }
   }
-  // a[r][2 i + e] = A(wrow + r, 2 (lane + 32 i) + e): four rows x four column pairs per lane
-  double a[4][kGjColsPerLane];
+  // a[r][2 i + e] = A(wrow + r, 2 (lane + 32 i) + e): RW rows x four column pairs per lane
+  double a[RW][kGjColsPerLane];
   if (warp < nwarps) {
 #pragma unroll
     for (int j = 0; j < kGjColsPerLane; ++j) {
       const int col = 2 * (lane + 32 * (j >> 1)) + (j & 1);
 #pragma unroll
-      for (int r = 0; r < 4; ++r) a[r][j] = (wrow + r < n && col < n) ? A[(size_t)(wrow + r) + (size_t)n * col] : 0.0;
+      for (int r = 0; r < RW; ++r) a[r][j] = (wrow + r < n && col < n) ? A[(size_t)(wrow + r) + (size_t)n * col] : 0.0;
     }
   }
   gj::cluster_sync();   // barriers initialised and every CTA resident before the first remote access
@@ -278,7 +287,8 @@ gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, d
         if (k0 >= n) break;
         const int q = B & (kGjSlots - 1);
         const bool local = owned(B);                   // produced by a warp of this CTA: read from `stage`
-        const bool owner = k0 == wrow;                 // this warp's four rows ARE the pivot rows
+        const int sb = (k0 - wrow) >> 2;               // which of this warp's blocks, if any
+        const bool owner = k0 >= wrow && sb < RQ;      // RW of this warp's rows include the four pivot rows
         const double* src = local ? &sm.stage[q][0][0] : &sm.rowbuf[q][0][0];
         const bool next_owner = k0 + 4 == wrow;        // (trace builds) this warp owns the next block: it is on the critical chain
         if (owner) GJ_STAMP(B, 0); else if (next_owner) GJ_STAMP(B, 4);
@@ -294,38 +304,54 @@ gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, d
           }
         }
         if (owner) GJ_STAMP(B, 1); else if (next_owner) GJ_STAMP(B, 5);
+        // the pivot rows are this warp's rows 4 SB .. 4 SB + 3 (SB compile time inside: register arrays need static indices)
+        auto owner_block = [&](auto sbc) {
+          constexpr int SB = decltype(sbc)::value;
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          if (k0 + t >= n) break;
-          const int j = 2 * i + (t & 1), lk = 2 * qq + (t >> 1);   // column k0 + t is element j of lane lk
-          double m[4];                                             // a_ik of the four rows, before the step
+          for (int t = 0; t < 4; ++t) {
+            if (k0 + t >= n) break;
+            const int j = 2 * i + (t & 1), lk = 2 * qq + (t >> 1);   // column k0 + t is element j of lane lk
+            constexpr int P0 = 4 * SB;
+            const int pr_ = P0 + t;                                  // (t is unrolled: pr_ is a constant)
+            double m[RW];                                            // a_ik of this warp's rows, before the step
 #pragma unroll
-          for (int r = 0; r < 4; ++r) m[r] = __shfl_sync(0xffffffffu, a[r][j], lk);
-          if (owner) {
-            // pivot row = this warp's row t: scale it (a_kj / p, a_kk <- 1 / p), eliminate it from the warp's other three
-            // rows straight from registers (every lane holds the same columns of all four rows), and stage it
-            const double pinv = gj::fast_rcp(m[t]);
+            for (int r = 0; r < RW; ++r) m[r] = __shfl_sync(0xffffffffu, a[r][j], lk);
+            // pivot row: scale it (a_kj / p, a_kk <- 1 / p), eliminate it from the warp's other rows straight from
+            // registers (every lane holds the same columns of all its rows), and stage it
+            const double pinv = gj::fast_rcp(m[pr_]);
 #pragma unroll
-            for (int jj = 0; jj < kGjColsPerLane; ++jj) a[t][jj] *= pinv;
-            if (lane == lk) a[t][j] = pinv;
+            for (int jj = 0; jj < kGjColsPerLane; ++jj) a[pr_][jj] *= pinv;
+            if (lane == lk) a[pr_][j] = pinv;
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-              if (r == t) continue;
+            for (int r = 0; r < RW; ++r) {
+              if (r == pr_) continue;
 #pragma unroll
-              for (int jj = 0; jj < kGjColsPerLane; ++jj) a[r][jj] = fma(-m[r], a[t][jj], a[r][jj]);
+              for (int jj = 0; jj < kGjColsPerLane; ++jj) a[r][jj] = fma(-m[r], a[pr_][jj], a[r][jj]);
               if (lane == lk) a[r][j] = -m[r] * pinv;
             }
             double2* dst = reinterpret_cast<double2*>(&sm.stage[q][t][0]) + lane;
 #pragma unroll
-            for (int ii = 0; ii < kGjColsPerLane / 2; ++ii) dst[32 * ii] = make_double2(a[t][2 * ii], a[t][2 * ii + 1]);
-          } else {
+            for (int ii = 0; ii < kGjColsPerLane / 2; ++ii) dst[32 * ii] = make_double2(a[pr_][2 * ii], a[pr_][2 * ii + 1]);
+          }
+        };
+        if (owner) {
+          if (RQ == 1 || sb == 0) owner_block(GjIntC<0>{});
+          else owner_block(GjIntC<RQ - 1>{});
+        } else {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            if (k0 + t >= n) break;
+            const int j = 2 * i + (t & 1), lk = 2 * qq + (t >> 1);
+            double m[RW];
+#pragma unroll
+            for (int r = 0; r < RW; ++r) m[r] = __shfl_sync(0xffffffffu, a[r][j], lk);
             // a_ij <- a_ij - a_ik a'_kj (a' the scaled pivot row), a_ik <- -a_ik / p = -a_ik a'_kk
             const double2* rk = reinterpret_cast<const double2*>(src + t * kGjMaxN) + lane;
             double2 pr[kGjColsPerLane / 2];
 #pragma unroll
             for (int ii = 0; ii < kGjColsPerLane / 2; ++ii) pr[ii] = rk[32 * ii];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
+            for (int r = 0; r < RW; ++r) {
 #pragma unroll
               for (int ii = 0; ii < kGjColsPerLane / 2; ++ii) {
                 a[r][2 * ii] = fma(-m[r], pr[ii].x, a[r][2 * ii]);
@@ -361,14 +387,14 @@ gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, d
     for (int j = 0; j < kGjColsPerLane; ++j) {
       const int col = 2 * (lane + 32 * (j >> 1)) + (j & 1);
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
+      for (int r = 0; r < RW; ++r)
         if (wrow + r < n && col < n) X[(size_t)(wrow + r) + (size_t)n * col] = a[r][j];
     }
     // the same inverse ROW-major with the leading dimension the toy kernel's TMA maps want (pad column zero): the
     // operator set-up launch disappears from the critical path between the inverse and the toy kernel
     if (Xrow) {
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
+      for (int r = 0; r < RW; ++r) {
         if (wrow + r >= n) continue;
 #pragma unroll
         for (int i = 0; i < kGjColsPerLane / 2; ++i) {
@@ -383,10 +409,16 @@ gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, d
   gj::cluster_sync();   // no CTA may exit while its shared memory can still be the target of a remote copy or arrive
 }
 
-template <int CTAS>
+#ifdef ISR_GJ_TRACE
+extern "C" int isr_debug_gj_trace(long long* dev) {
+  return cudaMemcpyToSymbol(g_gj_trace, &dev, sizeof(dev)) == cudaSuccess ? 0 : 3;
+}
+#endif
+
+template <int CTAS, int RW>
 static int launch_gj_t(isr_ctx* c, int n, const double* A, double* X, double* cert, double* Xrow, int ld) {
-  const int warps = (n + 4 * CTAS - 1) / (4 * CTAS);   // four rows per warp, whole warps per CTA
-  auto kernel = gj_inverse_kernel<CTAS>;
+  const int warps = (n + RW * CTAS - 1) / (RW * CTAS);   // RW rows per warp, whole warps per CTA
+  auto kernel = gj_inverse_kernel<CTAS, RW>;
   ISR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GjSmem)));   // per device
   if (CTAS > 8) ISR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
@@ -402,20 +434,20 @@ static int launch_gj_t(isr_ctx* c, int n, const double* A, double* X, double* ce
   ISR_CUDA(cudaLaunchKernelEx(&cfg, kernel, n, A, X, cert, Xrow, ld)); ISR_COUNT_LAUNCH();
   return ISR_OK;
 }
-// Cluster size: 4 CTAs hold at most 240 rows (15 arithmetic warps each), 8 and 16 CTAs spread the same rows thinner.
+// Cluster size and rows per warp (ISR_GJ_CTAS / ISR_GJ_RW in the environment override the default for experiments).
 static int launch_gj(isr_ctx* c, int n, const double* A, double* X, double* cert, double* Xrow, int ld) {
   static const int forced = [] { const char* e = std::getenv("ISR_GJ_CTAS"); return e ? std::atoi(e) : 0; }();
-  const int ctas = forced ? forced : kGjDefaultCtas;
-  if (ctas == 16) return launch_gj_t<16>(c, n, A, X, cert, Xrow, ld);
-  if (ctas == 4) return launch_gj_t<4>(c, n, A, X, cert, Xrow, ld);
-  return launch_gj_t<8>(c, n, A, X, cert, Xrow, ld);
+  static const int forced_rw = [] { const char* e = std::getenv("ISR_GJ_RW"); return e ? std::atoi(e) : 0; }();
+  const int ctas = forced ? forced : kGjDefaultCtas, rw = forced_rw ? forced_rw : kGjDefaultRows;
+  if (rw == 8) {
+    if (ctas == 16) return launch_gj_t<16, 8>(c, n, A, X, cert, Xrow, ld);
+    if (ctas == 4) return launch_gj_t<4, 8>(c, n, A, X, cert, Xrow, ld);
+    return launch_gj_t<8, 8>(c, n, A, X, cert, Xrow, ld);
+  }
+  if (ctas == 16) return launch_gj_t<16, 4>(c, n, A, X, cert, Xrow, ld);
+  if (ctas == 4) return launch_gj_t<4, 4>(c, n, A, X, cert, Xrow, ld);
+  return launch_gj_t<8, 4>(c, n, A, X, cert, Xrow, ld);
 }
-
-#ifdef ISR_GJ_TRACE
-extern "C" int isr_debug_gj_trace(long long* dev) {
-  return cudaMemcpyToSymbol(g_gj_trace, &dev, sizeof(dev)) == cudaSuccess ? 0 : 3;
-}
-#endif
 
 // Ainv = A^-1.  A (column-major, preserved) is factored in `lu` (n x n scratch, destroyed); `prod` is n x n scratch.
 //

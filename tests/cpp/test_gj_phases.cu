@@ -23,12 +23,12 @@ using namespace isr;
     }                                                                                    \
   } while (0)
 
-// C: CTAs of the cluster (the kernel is launched with 4, 8 or 16)
-template <int C>
+// C: CTAs of the cluster (the kernel is launched with 4, 8 or 16); RW: matrix rows per warp (4 or 8: a CTA owns whole warps)
+template <int C, int RW>
 static long replay() {
   long waits = 0;
   for (int n = 1; n <= 240; ++n) {
-    const int R = 4 * ((n + 4 * C - 1) / (4 * C)), NB = (n + 3) / 4;
+    const int R = RW * ((n + RW * C - 1) / (RW * C)), NB = (n + 3) / 4;
     GjPhases ph[C];
     int rfull[C][kGjSlots] = {}, lfull[C][kGjSlots] = {}, empty[C][kGjSlots] = {}, done[C][kGjSlots] = {};
     int credits[C][kGjSlots] = {}, expected[C][kGjSlots];
@@ -75,7 +75,7 @@ static long replay() {
 }
 
 int main() {
-  const long waits = replay<4>() + replay<8>() + replay<16>();
+  const long waits = replay<4, 4>() + replay<8, 4>() + replay<16, 4>() + replay<4, 8>() + replay<8, 8>() + replay<16, 8>();
   std::printf("gauss-jordan slot protocol ok: %ld waits replayed\n", waits);
   return 0;
 }
