@@ -293,9 +293,12 @@ int chi2_test(isr_problem* p, const isr_chi2_test_args& a, TestWants w) {
       if (peer) { pc = a.comm->peer; e1 = ++a.comm->epoch; e2 = ++a.comm->epoch; }
       range_kernel<<<blocks, 256, 0, st>>>(T, p->d_chi2h.p, p->d_part.p, p->d_arrive.p, d_range, p->d_cells.p, nb, pc, e1, peer ? 1 : 0); ISR_COUNT_LAUNCH();
       if (a.comm && !peer && (rc = comm_allreduce(a.comm, d_range, 2, 0, 1)) != ISR_OK) return drain(rc);
-      if (cert_here) cudaStreamWaitEvent(st, c->ev_cert, 0);      // the verdict of the inverse (side stream) enters the packed buffer
+      // the verdict of the inverse (side stream) enters the packed buffer only when ranks have to agree on a re-run; a
+      // single GPU reads it from page-locked memory after the final synchronisation, so the certificate (which cannot
+      // share the SMs with the persistent toy kernel and therefore runs when that ends) overlaps the tail kernels
+      if (cert_here && a.comm) cudaStreamWaitEvent(st, c->ev_cert, 0);
       cells_pack_kernel<<<blocks, 256, sizeof(uint32_t) * nb, st>>>(T, p->d_chi2h.p, a.nbins, d_range, p->d_cells.p, p->d_arrive.p + 1, n,
-                                                                    p->d_stat.p, (double)T, cert_here ? p->cert_dev : nullptr, assumed,
+                                                                    p->d_stat.p, (double)T, (cert_here && a.comm) ? p->cert_dev : nullptr, assumed,
                                                                     1e-12 * n, d_pack, pc, e2, peer ? 1 : 0); ISR_COUNT_LAUNCH();
       packed_by_peer = peer;
     } else {
@@ -305,9 +308,9 @@ int chi2_test(isr_problem* p, const isr_chi2_test_args& a, TestWants w) {
         if (a.comm && (rc = comm_allreduce(a.comm, d_range, 2, 0, 1)) != ISR_OK) return drain(rc);
         if (a.nbins > 0 && (rc = histogram_range_device(c, T, p->d_chi2h.p, a.nbins, d_range, p->d_cells.p)) != ISR_OK) return drain(rc);
       }
-      if (cert_here) cudaStreamWaitEvent(st, c->ev_cert, 0);
+      if (cert_here && a.comm) cudaStreamWaitEvent(st, c->ev_cert, 0);
       pack_test_kernel<<<(plen + 255) / 256, 256, 0, st>>>(nb, n, a.nbins > 0 ? p->d_cells.p : nullptr, p->d_stat.p, (double)T,
-                                                          cert_here ? p->cert_dev : nullptr, assumed, 1e-12 * n, d_pack); ISR_COUNT_LAUNCH();
+                                                          (cert_here && a.comm) ? p->cert_dev : nullptr, assumed, 1e-12 * n, d_pack); ISR_COUNT_LAUNCH();
     }
     if (a.comm) {
       if (!packed_by_peer && (rc = comm_allreduce(a.comm, d_pack, plen, 0, 0)) != ISR_OK) return drain(rc);
@@ -316,7 +319,7 @@ int chi2_test(isr_problem* p, const isr_chi2_test_args& a, TestWants w) {
     if (a.comm && a.comm->peer_ok) cudaMemcpyAsync(a.comm->status_pin, a.comm->peer.status, sizeof(int), cudaMemcpyDeviceToHost, st);
     const bool copy_failed = cudaMemcpyAsync(p->pin_test, p->d_pack.p, sizeof(double) * ((size_t)plen + 2), cudaMemcpyDeviceToHost, st) != cudaSuccess;
     cudaEventRecord(p->ev_time[4], st);
-    if (copy_failed || cudaStreamSynchronize(st) != cudaSuccess) {
+    if (copy_failed || cudaStreamSynchronize(st) != cudaSuccess || (cert_here && cudaEventSynchronize(c->ev_cert) != cudaSuccess)) {
       set_error("isr_chi2_test: CUDA error '%s'", cudaGetErrorString(cudaGetLastError()));
       return drain(ISR_ECUDA);
     }

@@ -83,7 +83,7 @@ static int check_info(isr_ctx* c, const int* d_info, const char* what) {
 // out[0] = max |(A X)(i, j) - delta_ij| over the n x n product P = A X (column-major); out[1] / out[2] = +inf unless
 // X / A is exactly lower triangular.  `out` is zeroed by the caller; non-negative doubles order like their bit patterns,
 // so the blocks combine with an integer atomicMax (the maximum does not depend on the order).
-__global__ void __launch_bounds__(256) inverse_residual_kernel(int n, const double* __restrict__ P, const double* __restrict__ X,
+__global__ void __launch_bounds__(256) inverse_residual_kernel(int n, const double* __restrict__ P, int nslices, const double* __restrict__ X,
                                                                const double* __restrict__ A, double* __restrict__ out) {
   __shared__ double smax[3][8];
   double m = 0.0, ux = 0.0, ua = 0.0;
@@ -91,7 +91,9 @@ __global__ void __launch_bounds__(256) inverse_residual_kernel(int n, const doub
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const size_t idx = (size_t)i + (size_t)n * j;
     if (P) {
-      const double v = P[idx] - ((i == j) ? 1.0 : 0.0);
+      double pv = P[idx];
+      for (int z = 1; z < nslices; ++z) pv += P[(size_t)z * n * n + idx];     // split-K slices of the product, in order
+      const double v = pv - ((i == j) ? 1.0 : 0.0);
       m = fmax(m, fabs(v));
       if (v != v) m = INFINITY;           // a NaN product must fail the (r <= tol) test on the host
     }
@@ -462,7 +464,7 @@ static int launch_gj(isr_ctx* c, int n, const double* A, double* X, double* cert
 // the three certificate scalars into the context's page-locked staging area), so that the caller can enqueue everything
 // that depends on the inverse -- the operator set-up, the toy kernels, the histogram -- behind it without a host round
 // trip; inverse_certified reads the verdict after the caller's one synchronisation, and inverse_pivoted is the
-// synchronous fall-back (after which the caller re-runs its dependents).
+// synchronous fall-back (after which the caller re-runs its dependents).  `prod` holds small_gemm_slices(c, n) * n^2 doubles.
 // lower_hint: the caller knows A to be lower triangular (selects the triangular solve for N > kGjMaxRows).
 // cert_host: 8 page-locked doubles owned by the caller (kPinCert / kPinInfo slots); cert_dev: 3 doubles of device memory
 // owned by the caller (kernels may fold the verdict into a collective).
@@ -503,8 +505,9 @@ int inverse_enqueue(isr_ctx* c, int n, const double* A, double* lu, double* prod
   cudaStream_t cs = c->aux_stream;
   ISR_CUDA(cudaEventRecord(c->ev_inv, c->stream));
   ISR_CUDA(cudaStreamWaitEvent(cs, c->ev_inv, 0));
-  ISR_TRY(small_gemm(c, n, lower_hint, A, Ainv, prod, cs));   // (a wrong hint is caught by the triangularity scalars)
-  inverse_residual_kernel<<<n, 256, 0, cs>>>(n, prod, Ainv, A, resid_dev); ISR_COUNT_LAUNCH();
+  int nslices = 1;
+  ISR_TRY(small_gemm(c, n, lower_hint, A, Ainv, prod, cs, &nslices));   // (a wrong hint is caught by the triangularity scalars)
+  inverse_residual_kernel<<<n, 256, 0, cs>>>(n, prod, nslices, Ainv, A, resid_dev); ISR_COUNT_LAUNCH();
   ISR_CUDA(cudaMemcpyAsync(cert_host + kPinCert, resid_dev, 3 * sizeof(double), cudaMemcpyDeviceToHost, cs));
   ISR_CUDA(cudaEventRecord(c->ev_cert, cs));
   ISR_CUDA(cudaGetLastError());
@@ -533,7 +536,7 @@ int inverse_pivoted(isr_ctx* c, int n, const double* A, double* lu, double* Ainv
   set_identity_kernel<<<(n * n + 255) / 256, 256, 0, c->stream>>>(n, Ainv); ISR_COUNT_LAUNCH();
   ISR_CUSOLVER(cusolverDnDgetrs(c->solver, CUBLAS_OP_N, n, n, lu, n, ipiv.p, Ainv, n, info.p));
   ISR_CUDA(cudaMemsetAsync(resid_dev, 0, 3 * sizeof(double), c->stream));
-  inverse_residual_kernel<<<n, 256, 0, c->stream>>>(n, nullptr, Ainv, A, resid_dev); ISR_COUNT_LAUNCH();
+  inverse_residual_kernel<<<n, 256, 0, c->stream>>>(n, nullptr, 0, Ainv, A, resid_dev); ISR_COUNT_LAUNCH();
   ISR_CUDA(cudaMemcpyAsync(cert_host + kPinCert, resid_dev, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   ISR_TRY(check_info(c, info.p, "LU solve (getrs)"));    // synchronises
   const double* resid = cert_host + kPinCert;

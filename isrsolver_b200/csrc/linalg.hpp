@@ -21,7 +21,11 @@ int inverse_pivoted(isr_ctx* c, int n, const double* A, double* lu, double* Ainv
 // off-diagonal block columns by products (tri_inverse.cu).  Entries above the diagonal of X are exact zeros.
 int tri_inverse_lower(isr_ctx* c, int n, const double* L, double* X);
 // C = A B, n x n column-major, hand-written 32 x 32 tiles; lower: both factors (hence the product) are lower triangular.
-int small_gemm(isr_ctx* c, int n, bool lower, const double* A, const double* B, double* C, cudaStream_t st = nullptr);
+// slices_out != nullptr: K is split into *slices_out slices whose partial products lie n^2 apart in C (the caller adds
+// them); C then holds small_gemm_slices(c, n) * n^2 doubles.
+int small_gemm(isr_ctx* c, int n, bool lower, const double* A, const double* B, double* C, cudaStream_t st = nullptr,
+               int* slices_out = nullptr);
+int small_gemm_slices(isr_ctx* c, int n);
 // C_k = A_k B for k < K (n x n column-major; A_k, C_k back to back with stride n^2, B shared): one launch
 int small_gemm_batch(isr_ctx* c, cudaStream_t st, int n, int K, const double* A_batch, const double* B, double* C_batch);
 // singular values (descending) of K n x n matrices by one-sided Jacobi, one CTA per matrix (svd_jacobi.cu); A destroyed

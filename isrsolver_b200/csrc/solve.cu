@@ -48,7 +48,7 @@ int factor_enqueue(isr_problem* p, const double* vcs_err) {
   if (p->vcs_err.size() != (size_t)n || std::memcmp(p->vcs_err.data(), vcs_err, sizeof(double) * n) != 0) p->tik_ready = false;
   p->vcs_err.assign(vcs_err, vcs_err + n);
   ISR_CUDA(cudaMemcpyAsync(p->d_werr.p, p->vcs_err.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
-  ISR_TRY(p->d_cert_prod.reserve(nn));
+  ISR_TRY(p->d_cert_prod.reserve(nn * small_gemm_slices(c, n)));
   ISR_TRY(p->d_cert.reserve(4));
   if (!p->pin_cert) ISR_CUDA(cudaMallocHost((void**)&p->pin_cert, sizeof(double) * 8));
   // R = W^(1/2) G and its row-major copy do not depend on the inverse: side stream, under the inverse

@@ -15,6 +15,8 @@
 // so the toy kernel's triangular schedule may be selected from the host-side knowledge alone.
 #include "linalg.hpp"
 
+#include <algorithm>
+
 namespace isr {
 
 constexpr int kTb = 32;   // block / tile edge
@@ -128,22 +130,35 @@ int tri_inverse_lower(isr_ctx* c, int n, const double* L, double* X) {
   return ISR_OK;
 }
 
-// C = A B (n x n, column-major) for the inverse's certificate.  lower != 0: both factors are lower triangular, the
-// product is too -- tiles above the diagonal are written as zeros and the others visit K in [column tile, row tile] only.
+// C = A B (n x n, column-major) for the inverse's certificate, K split into gridDim.z slices: slice z writes its partial
+// product to C + z n^2 (the consumer adds the slices in order).  A 7 x 7 grid of tiles leaves two thirds of the machine
+// idle at N = 200 and walks seven dependent K tiles per block (24 us); four slices make it 196 blocks of two.
+// lower != 0: both factors are lower triangular, the product is too -- tiles above the diagonal are written as zeros and
+// the others visit K in [column tile, row tile] only.
 __global__ void __launch_bounds__(256) small_gemm_kernel(int n, int lower, const double* __restrict__ A,
                                                           const double* __restrict__ B, double* __restrict__ C) {
   __shared__ double sA[kTb][kTb + 1];
   __shared__ __align__(32) double sB[kTb][kTb + 4];
   const int tr = blockIdx.y, tc = blockIdx.x;
-  TileJob jb{A, B, C, n, n, n};
+  TileJob jb{A, B, C + (size_t)blockIdx.z * n * n, n, n, n};
   if (lower && tc > tr) { tile_product(jb, n, tr, tc, 0, 0, 0.0, sA, sB); return; }
   const int k_lo = lower ? tc * kTb : 0, k_hi = lower ? min(n, (tr + 1) * kTb) : n;
-  tile_product(jb, n, tr, tc, k_lo, k_hi, 1.0, sA, sB);
+  // this slice's share of the K tiles [k_lo, k_hi)
+  const int tiles = (k_hi - k_lo + kTb - 1) / kTb, per = (tiles + (int)gridDim.z - 1) / (int)gridDim.z;
+  const int a = k_lo + (int)blockIdx.z * per * kTb, b = min(k_hi, a + per * kTb);
+  tile_product(jb, n, tr, tc, a, max(a, b), 1.0, sA, sB);
 }
-int small_gemm(isr_ctx* c, int n, bool lower, const double* A, const double* B, double* C, cudaStream_t st) {
+int small_gemm_slices(isr_ctx* c, int n) {
   const int t = (n + kTb - 1) / kTb;
-  small_gemm_kernel<<<dim3(t, t), 256, 0, st ? st : c->stream>>>(n, lower ? 1 : 0, A, B, C); ISR_COUNT_LAUNCH();
+  return std::max(1, std::min({8, t, (2 * c->sm_count + t * t - 1) / (t * t)}));
+}
+// C must hold small_gemm_slices(c, n) * n^2 doubles; *slices_out tells how many partial products to add.
+int small_gemm(isr_ctx* c, int n, bool lower, const double* A, const double* B, double* C, cudaStream_t st, int* slices_out) {
+  const int t = (n + kTb - 1) / kTb;
+  const int nz = slices_out ? small_gemm_slices(c, n) : 1;
+  small_gemm_kernel<<<dim3(t, t, nz), 256, 0, st ? st : c->stream>>>(n, lower ? 1 : 0, A, B, C); ISR_COUNT_LAUNCH();
   ISR_CUDA(cudaGetLastError());
+  if (slices_out) *slices_out = nz;
   return ISR_OK;
 }
 
