@@ -398,8 +398,10 @@ int isr_cond_spread_scan(isr_problem* p, int K, const double* sigma, int per_poi
   // S_k G0 and the singular values (one-sided Jacobi, one CTA per matrix: svd_jacobi.cu), in chunks of two waves of CTAs.
   if (n > 512) { set_error("isr_cond_spread_scan: N = %d exceeds the batched Jacobi kernel's 512", n); return ISR_EINVAL; }
   const int chunk = std::min(K, 2 * p->ctx->sm_count);
-  DevBuf<double> dS, dA, dsig, dsv;
-  DevBuf<int> dsw;
+  // grow-only scratch of the context: a scan allocates its 2 x K x N^2 doubles once, not per call (cudaMalloc / cudaFree of
+  // tens of MB cost more than the scan itself)
+  DevBuf<double>&dS = p->ctx->scratch_batch_a, &dA = p->ctx->scratch_batch_b, &dsig = p->ctx->scratch_batch_sig, &dsv = p->ctx->scratch_batch_sv;
+  DevBuf<int>& dsw = p->ctx->scratch_batch_i;
   const size_t per = per_point ? (size_t)n : 1;
   ISR_TRY(dS.reserve((size_t)chunk * nn)); ISR_TRY(dA.reserve((size_t)chunk * nn));
   ISR_TRY(dsig.reserve((size_t)K * per)); ISR_TRY(dsv.reserve((size_t)K * n)); ISR_TRY(dsw.reserve(K));

@@ -130,4 +130,6 @@ struct isr_ctx {
   isr::DevBuf<uint32_t> scratch_u;
   isr::DevBuf<double> scratch_v;
   isr::DevBuf<double> scratch_t;   // N x N scratch of the blocked triangular inverse
+  isr::DevBuf<double> scratch_batch_a, scratch_batch_b, scratch_batch_sig, scratch_batch_sv;   // batched spread scan
+  isr::DevBuf<int> scratch_batch_i;
 };
