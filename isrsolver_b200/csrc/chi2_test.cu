@@ -116,7 +116,8 @@ __global__ void __launch_bounds__(256) cells_pack_kernel(int64_t n, const double
                                                           const double* __restrict__ range, int* __restrict__ cells,
                                                           unsigned* __restrict__ counter, int npts, const double* __restrict__ stat,
                                                           double toys, const double* __restrict__ cert, int assumed_lower, double tol,
-                                                          double* pack, PeerComm pc, unsigned long long epoch, int use_peer) {
+                                                          double* pack, PeerComm pc, unsigned long long epoch, int use_peer,
+                                                          double* host_out) {
   extern __shared__ uint32_t sh[];
   __shared__ bool last;
   const double lo = range[0], hi = -range[1];
@@ -149,6 +150,14 @@ __global__ void __launch_bounds__(256) cells_pack_kernel(int64_t n, const double
   if (use_peer) {
     __syncthreads();
     peer_allreduce_block(pc, epoch, pack, pack, len, 0);      // cells, sums, toy count and certificate flag over all ranks
+  }
+  if (host_out) {
+    // the final result goes straight into the caller-visible page-locked buffer (zero-copy stores over PCIe): no separate
+    // device-to-host copy operation behind the kernel
+    __syncthreads();
+    if (threadIdx.x < 2) host_out[threadIdx.x] = range[threadIdx.x];
+    for (int idx = threadIdx.x; idx < len; idx += blockDim.x) host_out[2 + idx] = pack[idx];
+    __threadfence_system();
   }
 }
 
@@ -233,6 +242,8 @@ int chi2_test(isr_problem* p, const isr_chi2_test_args& a, TestWants w) {
     p->pin_test = nullptr; p->pin_test_n = 0;
     ISR_CUDA(cudaMallocHost((void**)&p->pin_test, sizeof(double) * ((size_t)plen + 2)));
     p->pin_test_n = (size_t)plen + 2;
+    p->pin_test_dev = nullptr;
+    if (cudaHostGetDevicePointer((void**)&p->pin_test_dev, p->pin_test, 0) != cudaSuccess) { cudaGetLastError(); p->pin_test_dev = nullptr; }
   }
   double* d_range = p->d_pack.p;
   double* d_pack = p->d_pack.p + 2;
@@ -281,7 +292,7 @@ int chi2_test(isr_problem* p, const isr_chi2_test_args& a, TestWants w) {
     cudaEventRecord(p->ev_time[3], st);
     // ---- range, cells, packed buffer, collectives
     const bool cert_here = do_fac && attempt == 0;
-    bool packed_by_peer = false;
+    bool packed_by_peer = false, result_on_host = false;
     const int assumed = (p->tri_sle[0] || p->tri_sle[1]) ? 1 : 0;
     if (T > 0 && a.nbins > 0) {
       // the usual case: two fused launches (the stat sums of the toy kernels are complete: same stream)
@@ -299,8 +310,10 @@ int chi2_test(isr_problem* p, const isr_chi2_test_args& a, TestWants w) {
       if (cert_here && a.comm) cudaStreamWaitEvent(st, c->ev_cert, 0);
       cells_pack_kernel<<<blocks, 256, sizeof(uint32_t) * nb, st>>>(T, p->d_chi2h.p, a.nbins, d_range, p->d_cells.p, p->d_arrive.p + 1, n,
                                                                     p->d_stat.p, (double)T, (cert_here && a.comm) ? p->cert_dev : nullptr, assumed,
-                                                                    1e-12 * n, d_pack, pc, e2, peer ? 1 : 0); ISR_COUNT_LAUNCH();
+                                                                    1e-12 * n, d_pack, pc, e2, peer ? 1 : 0,
+                                                                    (peer || !a.comm) ? p->pin_test_dev : nullptr); ISR_COUNT_LAUNCH();
       packed_by_peer = peer;
+      result_on_host = (peer || !a.comm) && p->pin_test_dev != nullptr;
     } else {
       if (need_range) {
         if (T > 0) { if ((rc = minmax_to_device(c, T, p->d_chi2h.p, d_range)) != ISR_OK) return drain(rc); }
@@ -317,7 +330,8 @@ int chi2_test(isr_problem* p, const isr_chi2_test_args& a, TestWants w) {
       if (w.rhist && (rc = comm_allreduce(a.comm, p->d_rhist.p, (int64_t)n * 1026, 2, 0)) != ISR_OK) return drain(rc);
     }
     if (a.comm && a.comm->peer_ok) cudaMemcpyAsync(a.comm->status_pin, a.comm->peer.status, sizeof(int), cudaMemcpyDeviceToHost, st);
-    const bool copy_failed = cudaMemcpyAsync(p->pin_test, p->d_pack.p, sizeof(double) * ((size_t)plen + 2), cudaMemcpyDeviceToHost, st) != cudaSuccess;
+    const bool copy_failed = !result_on_host &&
+        cudaMemcpyAsync(p->pin_test, p->d_pack.p, sizeof(double) * ((size_t)plen + 2), cudaMemcpyDeviceToHost, st) != cudaSuccess;
     cudaEventRecord(p->ev_time[4], st);
     if (copy_failed || cudaStreamSynchronize(st) != cudaSuccess || (cert_here && cudaEventSynchronize(c->ev_cert) != cudaSuccess)) {
       set_error("isr_chi2_test: CUDA error '%s'", cudaGetErrorString(cudaGetLastError()));

@@ -79,6 +79,7 @@ struct isr_problem {
   isr::DevBuf<double> d_part;        // per-block {min, max} partials of the range kernel
   isr::DevBuf<unsigned> d_arrive;    // arrival counters of the two fused tail kernels
   double* pin_test = nullptr;
+  double* pin_test_dev = nullptr;     // the same buffer as the device sees it (zero-copy result store of the last kernel)
   cudaEvent_t ev_time[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // start | assembled | factor enqueued | toys enqueued | results copied
   size_t pin_test_n = 0;
   // host-buffer pipeline (isr_toy_batch): two V slots, chi2 / statistics staging, copy stream
