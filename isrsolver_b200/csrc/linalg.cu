@@ -229,7 +229,8 @@ struct GjSmem {
 // RW = 4 stays the default; ISR_GJ_RW=8 selects the other layout.
 template <int J> struct GjIntC { static constexpr int value = J; };
 
-template <int kGjCtas, int RW>
+// CPL (template): matrix columns per lane, 8 (N <= 256) or 4 (N <= 128: half the FMAs, loads and stores per pivot).
+template <int kGjCtas, int RW, int CPL>
 __global__ void __launch_bounds__(RW == 8 ? (kGjCtas == 4 ? 288 : (kGjCtas == 8 ? 160 : 96)) : (kGjCtas == 4 ? 512 : (kGjCtas == 8 ? 288 : 160)), 1)
 gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, double* __restrict__ cert,
                   double* __restrict__ Xrow, int ld) {
@@ -262,10 +263,10 @@ gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, d
     }
   }
   // a[r][2 i + e] = A(wrow + r, 2 (lane + 32 i) + e): RW rows x four column pairs per lane
-  double a[RW][kGjColsPerLane];
+  double a[RW][CPL];
   if (warp < nwarps) {
 #pragma unroll
-    for (int j = 0; j < kGjColsPerLane; ++j) {
+    for (int j = 0; j < CPL; ++j) {
       const int col = 2 * (lane + 32 * (j >> 1)) + (j & 1);
 #pragma unroll
       for (int r = 0; r < RW; ++r) a[r][j] = (wrow + r < n && col < n) ? A[(size_t)(wrow + r) + (size_t)n * col] : 0.0;
@@ -283,7 +284,7 @@ gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, d
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < kGjColsPerLane / 2; ++i) {
+    for (int i = 0; i < CPL / 2; ++i) {
       for (int qq = 0; qq < 16; ++qq) {
         const int k0 = 64 * i + 4 * qq, B = k0 >> 2;   // pivots k0 .. k0 + 3: column pairs of lanes 2 qq and 2 qq + 1
         if (k0 >= n) break;
@@ -322,18 +323,18 @@ gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, d
             // registers (every lane holds the same columns of all its rows), and stage it
             const double pinv = gj::fast_rcp(m[pr_]);
 #pragma unroll
-            for (int jj = 0; jj < kGjColsPerLane; ++jj) a[pr_][jj] *= pinv;
+            for (int jj = 0; jj < CPL; ++jj) a[pr_][jj] *= pinv;
             if (lane == lk) a[pr_][j] = pinv;
 #pragma unroll
             for (int r = 0; r < RW; ++r) {
               if (r == pr_) continue;
 #pragma unroll
-              for (int jj = 0; jj < kGjColsPerLane; ++jj) a[r][jj] = fma(-m[r], a[pr_][jj], a[r][jj]);
+              for (int jj = 0; jj < CPL; ++jj) a[r][jj] = fma(-m[r], a[pr_][jj], a[r][jj]);
               if (lane == lk) a[r][j] = -m[r] * pinv;
             }
             double2* dst = reinterpret_cast<double2*>(&sm.stage[q][t][0]) + lane;
 #pragma unroll
-            for (int ii = 0; ii < kGjColsPerLane / 2; ++ii) dst[32 * ii] = make_double2(a[pr_][2 * ii], a[pr_][2 * ii + 1]);
+            for (int ii = 0; ii < CPL / 2; ++ii) dst[32 * ii] = make_double2(a[pr_][2 * ii], a[pr_][2 * ii + 1]);
           }
         };
         if (owner) {
@@ -349,13 +350,13 @@ gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, d
             for (int r = 0; r < RW; ++r) m[r] = __shfl_sync(0xffffffffu, a[r][j], lk);
             // a_ij <- a_ij - a_ik a'_kj (a' the scaled pivot row), a_ik <- -a_ik / p = -a_ik a'_kk
             const double2* rk = reinterpret_cast<const double2*>(src + t * kGjMaxN) + lane;
-            double2 pr[kGjColsPerLane / 2];
+            double2 pr[CPL / 2];
 #pragma unroll
-            for (int ii = 0; ii < kGjColsPerLane / 2; ++ii) pr[ii] = rk[32 * ii];
+            for (int ii = 0; ii < CPL / 2; ++ii) pr[ii] = rk[32 * ii];
 #pragma unroll
             for (int r = 0; r < RW; ++r) {
 #pragma unroll
-              for (int ii = 0; ii < kGjColsPerLane / 2; ++ii) {
+              for (int ii = 0; ii < CPL / 2; ++ii) {
                 a[r][2 * ii] = fma(-m[r], pr[ii].x, a[r][2 * ii]);
                 a[r][2 * ii + 1] = fma(-m[r], pr[ii].y, a[r][2 * ii + 1]);
               }
@@ -386,7 +387,7 @@ gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, d
       }
     }
 #pragma unroll
-    for (int j = 0; j < kGjColsPerLane; ++j) {
+    for (int j = 0; j < CPL; ++j) {
       const int col = 2 * (lane + 32 * (j >> 1)) + (j & 1);
 #pragma unroll
       for (int r = 0; r < RW; ++r)
@@ -399,7 +400,7 @@ gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, d
       for (int r = 0; r < RW; ++r) {
         if (wrow + r >= n) continue;
 #pragma unroll
-        for (int i = 0; i < kGjColsPerLane / 2; ++i) {
+        for (int i = 0; i < CPL / 2; ++i) {
           const int col = 2 * (lane + 32 * i);
           if (col < ld)
             *reinterpret_cast<double2*>(Xrow + (size_t)(wrow + r) * ld + col) =
@@ -417,10 +418,10 @@ extern "C" int isr_debug_gj_trace(long long* dev) {
 }
 #endif
 
-template <int CTAS, int RW>
-static int launch_gj_t(isr_ctx* c, int n, const double* A, double* X, double* cert, double* Xrow, int ld) {
+template <int CTAS, int RW, int CPL>
+static int launch_gj_c(isr_ctx* c, int n, const double* A, double* X, double* cert, double* Xrow, int ld) {
   const int warps = (n + RW * CTAS - 1) / (RW * CTAS);   // RW rows per warp, whole warps per CTA
-  auto kernel = gj_inverse_kernel<CTAS, RW>;
+  auto kernel = gj_inverse_kernel<CTAS, RW, CPL>;
   ISR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GjSmem)));   // per device
   if (CTAS > 8) ISR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
@@ -435,6 +436,11 @@ static int launch_gj_t(isr_ctx* c, int n, const double* A, double* X, double* ce
   cfg.numAttrs = 1;
   ISR_CUDA(cudaLaunchKernelEx(&cfg, kernel, n, A, X, cert, Xrow, ld)); ISR_COUNT_LAUNCH();
   return ISR_OK;
+}
+template <int CTAS, int RW>
+static int launch_gj_t(isr_ctx* c, int n, const double* A, double* X, double* cert, double* Xrow, int ld) {
+  if (n <= 128) return launch_gj_c<CTAS, RW, 4>(c, n, A, X, cert, Xrow, ld);
+  return launch_gj_c<CTAS, RW, 8>(c, n, A, X, cert, Xrow, ld);
 }
 // Cluster size and rows per warp (ISR_GJ_CTAS / ISR_GJ_RW in the environment override the default for experiments).
 static int launch_gj(isr_ctx* c, int n, const double* A, double* X, double* cert, double* Xrow, int ld) {
