@@ -246,7 +246,7 @@ gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, d
   const int nwarps = (blockDim.x >> 5) - 1;   // arithmetic warps; the last warp forwards the credits
   const int row0 = (int)rank * R, wrow = row0 + RW * warp;     // first of this warp's RW rows
   const int Bs = row0 >> 2, Be = min(NB, Bs + (R >> 2));       // blocks whose pivot rows this CTA owns
-  auto block_bytes = [&](int B) { return (uint32_t)min(4, n - 4 * B) * kRowBytes; };
+  auto block_bytes = [&](int) { return (uint32_t)(4 * kRowBytes); };   // always four rows (zero rows pad a ragged last block)
   const GjPhases ph{NB, Bs, Be};
   auto owned = [&](int B) { return ph.owned(B); };
   auto next_remote = [&](int B) { return ph.next_remote(B); };
@@ -312,7 +312,14 @@ gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, d
           constexpr int SB = decltype(sbc)::value;
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            if (k0 + t >= n) break;
+            if (k0 + t >= n) {
+              // ragged last block: a ZERO row is staged for the missing pivots, so that the consumers' four updates run
+              // unconditionally (their multipliers for these columns are zeros of the padding, and 0 x 0 changes nothing)
+              double2* dstz = reinterpret_cast<double2*>(&sm.stage[q][t][0]) + lane;
+#pragma unroll
+              for (int ii = 0; ii < CPL / 2; ++ii) dstz[32 * ii] = make_double2(0.0, 0.0);
+              continue;
+            }
             const int j = 2 * i + (t & 1), lk = 2 * qq + (t >> 1);   // column k0 + t is element j of lane lk
             constexpr int P0 = 4 * SB;
             const int pr_ = P0 + t;                                  // (t is unrolled: pr_ is a constant)
@@ -341,9 +348,10 @@ gj_inverse_kernel(int n, const double* __restrict__ A, double* __restrict__ X, d
           if (RQ == 1 || sb == 0) owner_block(GjIntC<0>{});
           else owner_block(GjIntC<RQ - 1>{});
         } else {
+          // (no early exit for a ragged last block -- see the owner: without control flow between the four steps the
+          // loads of pivot row t + 1 are issued under the FMAs of row t)
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            if (k0 + t >= n) break;
             const int j = 2 * i + (t & 1), lk = 2 * qq + (t >> 1);
             double m[RW];
 #pragma unroll
