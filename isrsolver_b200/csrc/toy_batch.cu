@@ -140,9 +140,12 @@ static size_t cfg_smem(const ToyCfg& c, int n, int nstat) {
   return c.smem_base + (size_t)c.wm * nstat * nblk * c.np * sizeof(double);
 }
 
-// T > 0: the batch size is known -- the cost then includes the quantisation of T / tm tiles into waves of `sms` persistent
-// CTAs (BASELINE config C2: 10^5 toys in 128-toy tiles are 5.3 waves, paid as 6).
-static const ToyCfg* pick_cfg(int n, int nstat, int64_t T = 0, int sms = 148) {
+// The choice depends on N and the requested statistics ONLY -- never on the batch size: a toy's chi2 must not depend on
+// how the campaign was chunked or over how many GPUs it was sharded (different tile shapes sum in different orders), or
+// the multi-GPU histograms would stop being bit-identical to the single-GPU one.  (A batch-size-aware chooser was tried
+// for C2 -- 10^5 toys in 128-toy tiles are 5.3 waves of CTAs, paid as 6 -- and bought nothing: the 64-toy tile that
+// quantises better is 9 % slower per tile.)
+static const ToyCfg* pick_cfg(int n, int nstat) {
   const char* force = std::getenv("ISR_TOY_CFG");
   const ToyCfg* best = nullptr;
   double best_cost = 1e300;
@@ -158,10 +161,6 @@ static const ToyCfg* pick_cfg(int n, int nstat, int64_t T = 0, int sms = 148) {
     if (c.threads < 384) cost *= 1.10;        // 8 warps; measured: N=100 25.8 vs 24.9 TFLOP/s
     else if (c.threads < 512) cost *= 1.04;   // 12 warps; measured: N=144 30.3 vs N=160 (16 warps) 31.7 TFLOP/s, both exact fits
     if (c.stages < 3 && c.kc == 24) cost *= 1.001;   // tie-break: the deeper ring when nothing else differs
-    if (T > 0) {
-      const double tiles = (double)((T + c.tm - 1) / c.tm), waves = tiles / sms;
-      cost *= std::ceil(waves) / waves;
-    }
     if (cost < best_cost) { best_cost = cost; best = &c; }
   }
   return best;
@@ -192,7 +191,7 @@ static int launch_fused(isr_problem* p, int64_t T, const double* V_dev, const do
   cudaStream_t st = p->ctx->stream;
   const bool want_stats = out.sum_bcs || out.ratio_stats || out.rhist;
   const int nstat = (out.ratio_stats || out.rhist) ? 4 : 1;
-  const ToyCfg* cfg = pick_cfg(n, want_stats ? nstat : 0, T, p->ctx->sm_count);
+  const ToyCfg* cfg = pick_cfg(n, want_stats ? nstat : 0);
   if (!cfg) { set_error("toy batch: N = %d does not fit any kernel configuration", n); return ISR_EINVAL; }
   const size_t smem = cfg_smem(*cfg, n, want_stats ? nstat : 0);
   const int nblk = (n + cfg->np - 1) / cfg->np;
