@@ -32,6 +32,18 @@ TOY_SEED = 20211103
 _CTX = {}
 
 
+_GROUPS = {}
+
+
+def _group(ngpu: int):
+    """One isr_group per (process, size): contexts, host threads and the communicator over the first `ngpu` GPUs."""
+    if ngpu not in _GROUPS:
+        g = C.c_void_p()
+        L.check(L.load().isr_group_create(int(ngpu), None, C.byref(g)))
+        _GROUPS[ngpu] = g
+    return _GROUPS[ngpu]
+
+
 def _ctx(device: int | None = None):
     """One isr_ctx per (process, device); device defaults to LOCAL_RANK (one process per GPU) or 0."""
     if device is None:
@@ -583,6 +595,71 @@ class ISRSolverSLE(BaseISRSolver):
         if want_hist: out["ratio_hist"] = rh
         if want_chi2_hist: out.update(hist=cnt.astype(np.float32), lo=float(lohi[0]), hi=float(lohi[1]))
         return out
+
+    def chi2_test_call(self, bcs0, n=None, V=None, vcs=None, vcs_err=None, seed=TOY_SEED, first_toy=0, nbins=128,
+                       want_chi2=True, want_sum=False, want_ratio=False, want_hist=False, ngpu=1):
+        """chi2Test / ratioTestModel as ONE stream-ordered C-ABI call (isr_chi2_test): toys -> range -> TH1F cells with a
+        single synchronisation.  V (host, (T, N)): the toys; or n + vcs (+ vcs_err): toys drawn on the device.
+        ngpu > 1 (plain SLE solvers with tabulated efficiency): the test is spread over the first `ngpu` GPUs of the box
+        from this process (isr_group: a thread, a context and a replicated problem per GPU, two small all-reduces); the
+        histogram is bit-identical to the single-GPU one."""
+        bcs0 = _f64(bcs0, self._n, "bcs0")
+        a = L.Chi2TestArgs()
+        keep = [bcs0]
+        if V is not None:
+            V = np.ascontiguousarray(V, dtype=np.float64)
+            if V.ndim != 2 or V.shape[1] != self._n:
+                raise ValueError(f"V must be (T, {self._n})")
+            T = V.shape[0]
+            a.V = L.dptr(V)
+        else:
+            T = int(n)
+            vcs = _f64(vcs, self._n, "vcs"); keep.append(vcs)
+            a.vcs = L.dptr(vcs)
+        err = _f64(self._vcs_err if vcs_err is None else vcs_err, self._n, "vcs_err"); keep.append(err)
+        a.vcs_err, a.bcs0, a.n_toys, a.seed, a.first_toy, a.nbins = L.dptr(err), L.dptr(bcs0), T, int(seed), int(first_toy), int(nbins)
+        a.flags = L.ISR_TEST_RATIO if (want_ratio or want_hist) else 0
+        chi2 = np.empty(T) if want_chi2 else None
+        lohi, cnt = np.zeros(2), np.zeros(nbins + 2, dtype=np.int64)
+        sb = np.zeros(self._n) if want_sum else None
+        rs = np.zeros(3 * self._n) if (want_ratio or want_hist) else None
+        rh = np.zeros((self._n, 1026), dtype=np.uint32) if want_hist else None
+        total = C.c_int64()
+        a.chi2_out, a.chi2_lo_hi_out, a.chi2_counts_out = L.dptr(chi2), L.dptr(lohi), cnt.ctypes.data_as(C.POINTER(C.c_int64))
+        a.sum_bcs_out, a.ratio_stats_out, a.ratio_hist_out, a.total_toys_out = L.dptr(sb), L.dptr(rs), L.uptr(rh), C.pointer(total)
+        if ngpu > 1:
+            gp = self._group_problem(int(ngpu))
+            a.flags |= L.ISR_TEST_ASSEMBLE | L.ISR_TEST_FACTOR
+            if self._spread:
+                ee = _f64(self._ecm_err, self._n, "energy_err"); keep.append(ee)
+                a.ecm_err = L.dptr(ee)
+            L.check(self._lib.isr_group_chi2_test(gp, C.byref(a)))
+        else:
+            self._select_for_toys()
+            L.check(self._lib.isr_chi2_test(self._p, C.byref(a)))
+        out = {"hist": cnt.astype(np.float32), "lo": float(lohi[0]), "hi": float(lohi[1]), "n": int(total.value)}
+        if want_chi2: out["chi2"] = chi2
+        if want_sum: out["sum_bcs"] = sb
+        if want_ratio or want_hist: out["ratio_stats"] = rs.reshape(self._n, 3)
+        if want_hist: out["ratio_hist"] = rh
+        return out
+
+    def _group_problem(self, ngpu):
+        """The replicated problem of this solver on an isr_group of `ngpu` GPUs (cached per solver and size)."""
+        if type(self)._select_for_toys is not ISRSolverSLE._select_for_toys or self._eff_call is not None:
+            raise ValueError("multi-GPU tests need a plain SLE solver with a tabulated efficiency (the problem is rebuilt "
+                             "from its description on every GPU)")
+        cache = self.__dict__.setdefault("_gproblems", {})
+        if ngpu not in cache:
+            grp = _group(ngpu)
+            gp = C.c_void_p()
+            st = np.ascontiguousarray(self._settings, dtype=np.int32).reshape(-1, 3) if self._settings is not None else np.zeros((0, 3), dtype=np.int32)
+            desc = self._eff.desc(self._n) if self._eff is not None and self._eff.kind != "one" else None
+            L.check(self._lib.isr_group_problem_create(grp, self._n, L.dptr(self._ecm), self._thr, len(st),
+                                                       L.iptr(st) if len(st) else None, C.byref(desc) if desc is not None else None,
+                                                       C.byref(gp)))
+            cache[ngpu] = gp
+        return cache[ngpu]
 
     def chi2_test_sharded(self, n, vcs, bcs0, vcs_err, seed=TOY_SEED, nbins=128):
         """chi2Test over `n` toys sharded across the ranks of an initialised torch.distributed group (one

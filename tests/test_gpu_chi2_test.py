@@ -396,3 +396,33 @@ def test_group_scans_equal_single_gpu(ngpu):
     lib.isr_problem_destroy(p1)
     lib.isr_group_problem_destroy(gp)
     lib.isr_group_destroy(grp)
+
+
+@pytest.mark.parametrize("ngpu", [1, 2])
+def test_python_mirror_fused_call_and_group(ngpu, oracle):
+    """The ctypes mirror's chi2_test_call: one isr_chi2_test per test (and isr_group_chi2_test for ngpu > 1), same numbers as
+    the call-by-call methods; Tikhonov solvers are refused for multi-GPU (their selected operator is not replicated)."""
+    import isrsolver_b200 as isr
+    if _gpu_count() < ngpu:
+        pytest.skip(f"needs {ngpu} GPUs")
+    g = load_golden("c2_sle_n40_cspline")
+    n = len(g["ecm"])
+    s = isr.ISRSolverSLE(n, g["ecm"], g["vcs"], None, g["vcs_err"], float(g["threshold"]))
+    s.set_interp_settings([tuple(r) for r in g["settings"]])
+    V = oracle.draw_toys(g["vcs"], g["vcs_err"], 20011)
+    r = s.chi2_test_call(g["bcs0"], V=V, want_sum=True, want_ratio=True, want_hist=True, ngpu=ngpu)
+    ref = s.toy_batch(V, g["bcs0"], want_sum=True, want_ratio=True, want_hist=True)
+    np.testing.assert_array_equal(r["chi2"], ref["chi2"])
+    np.testing.assert_array_equal(r["ratio_hist"], ref["ratio_hist"])
+    np.testing.assert_allclose(r["sum_bcs"], ref["sum_bcs"], rtol=1e-12)
+    cnt, _, lo, hi = oracle.chi2_histogram(ref["chi2"])
+    assert (r["lo"], r["hi"]) == (lo, hi) and r["n"] == len(V)
+    np.testing.assert_array_equal(r["hist"], cnt)
+    d = s.chi2_test_call(g["bcs0"], n=5000, vcs=g["vcs"], seed=3, ngpu=ngpu)
+    one = s.toy_campaign(5000, g["vcs"], g["vcs_err"], g["bcs0"], seed=3)
+    np.testing.assert_array_equal(d["chi2"], one["chi2"])
+    np.testing.assert_array_equal(d["hist"], one["hist"])
+    if ngpu > 1:
+        t = isr.ISRSolverTikhonov(n, g["ecm"], g["vcs"], None, g["vcs_err"], float(g["threshold"]))
+        with pytest.raises(ValueError):
+            t.chi2_test_call(g["bcs0"], V=V[:10], ngpu=ngpu)
