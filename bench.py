@@ -353,9 +353,9 @@ def run_b200(args, rank, world, local_rank):
         "roofline": {"bound": "tensor", "kernel": "toy_fused_kernel, tile " + (lib.isr_toy_tile_name(n, 1) or b"?").decode() +
                                " (one launch: TMA box loads -> DMMA m8n8k4 f64, pass 1 b = S v and pass 2 chi2 = |R(b-b0)|^2)",
                      "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
-                     # dram__bytes_read + dram__bytes_write of the fused launch from the ncu --set full capture
-                     # in profiles/ncu_r01_toy_dense_final.txt (840.00 + 176.71 MB for 524288 toys at N=200), scaled to this T
-                     "traffic": (1016.71e6 / 524288) * T if n == 200 else None,
+                     # dram__bytes_read + dram__bytes_write of the fused launch from the ncu --set full capture of THIS
+                     # command in profiles/ncu_r02_toy_dense.txt (1679.86 + 202.05 MB for 1048576 toys at N=200), scaled to T
+                     "traffic": (1881.91e6 / 1048576) * T if n == 200 else None,
                      "algorithmic_bytes": (8 * n + 8) * T, "flops_per_toy": 4 * n * n,
                      "timing": "CUDA events recorded by isr_chi2_test on its own stream around the fused launch (isr_chi2_test_timing), mean over the timed steps",
                      "peak_source": "FP64 DMMA probe tools/fp64_peaks.cu -> profiles/fp64_peaks_r01.json "
