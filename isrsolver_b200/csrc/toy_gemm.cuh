@@ -390,8 +390,49 @@ toy_fused_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant
             }
           }
         };
-        if (jm == 0) body(IntC<0>{});   // a dense pass of a half-triangular pair never reaches the jump table below
-        else dispatch_jmin<1, BT>(jm, body);
+        // The chunk that CROSSES the diagonal of a column tile is where chunk-granular skipping wastes work: tile j is
+        // live for the chunk's first 8 k but dead for its later ones (k > column).  For such chunks -- the first live tile
+        // differs between the chunk's first and last k-step -- the k-steps are grouped by their first live tile and each
+        // group runs the body specialised for it, over a run-time range of k-steps (round 2; round 1 executed 0.60 of the
+        // dense DMMA count at N = 200 where 0.52 is needed).  All other chunks keep the fully unrolled body above.
+        int jm_last = jm;
+        const int kt0 = (q.kc * kKC - q.cb * NP) / 8;        // first k-tile of the chunk, counted from the block's first column (multiple-of-8 arithmetic: exact)
+        if ((g.tri >> (kind == PH_P2)) & 1) jm_last = tri_first_live_tile<WN>(q.kc * kKC - q.cb * NP + 8 * (ksteps - 1), wn);
+        if (jm_last == jm) {
+          if (jm == 0) body(IntC<0>{});   // a dense pass of a half-triangular pair never reaches the jump table below
+          else dispatch_jmin<1, BT>(jm, body);
+        } else {
+          auto body_range = [&](auto jmc, int kp_lo, int kp_hi) {
+            constexpr int JM = decltype(jmc)::value;
+            for (int kp = kp_lo; kp < kp_hi; ++kp) {
+              double2 a[AT], b[BT];
+#pragma unroll
+              for (int i = 0; i < AT; ++i)
+                a[i] = *reinterpret_cast<const double2*>(sA + ((wm * AT + i) * 8 + gq) * kKC + kp * 8 + 2 * c);
+#pragma unroll
+              for (int j = JM; j < BT; ++j)
+                b[j] = *reinterpret_cast<const double2*>(sB + ((j * WN + wn) * 8 + gq) * kKC + kp * 8 + 2 * c);
+#pragma unroll
+              for (int i = 0; i < AT; ++i)
+#pragma unroll
+                for (int j = JM; j < BT; ++j) dmma884<JM + 64>(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
+#pragma unroll
+              for (int i = 0; i < AT; ++i)
+#pragma unroll
+                for (int j = JM; j < BT; ++j) dmma884<JM + 64>(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
+            }
+          };
+          int kp = 0;
+          for (int J = jm; J <= jm_last && J < BT && kp < ksteps; ++J) {
+            // k-steps whose first live tile is J: k-tile kt0 + kp needs tile index j WN + wn >= kt0 + kp
+            const int kp_hi = min(ksteps, J * WN + wn - kt0 + 1);
+            if (kp_hi > kp) {
+              if (J == 0) body_range(IntC<0>{}, kp, kp_hi);
+              else dispatch_jmin<1, BT>(J, [&](auto jc) { body_range(jc, kp, kp_hi); });
+              kp = kp_hi;
+            }
+          }
+        }
       }
 
       if (q.last_chunk()) {
