@@ -61,7 +61,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append([c.strip() for c in line.split(",")])
@@ -323,12 +323,12 @@ def run_b200(args, rank, world, local_rank):
     launches0 = lib.isr_launch_count()
     ms_total = timed(step_device, args.steps, record=True)
     launches = lib.isr_launch_count() - launches0
-    clocks = sampler.finish() if sampler else None
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
     ms_e2e = timed(lambda: step_e2e(), args.steps, record=None)
     hist_c = step_campaign().copy()
     ms_rng = timed(lambda: step_campaign(), args.steps, record=None)
+    clocks = sampler.finish() if sampler else None      # sampled every 25 ms across the three timed regions (value, e2e, campaign)
     assert int(hist_c.sum()) == T * world and test.total.value == T * world
     assert int(hist.sum()) == T * world, "histogram lost entries"
     strong = strong_scaling(L, lib, ctx, stream, comm, torch, dist, dev, rank, world)
