@@ -5,11 +5,14 @@ this module.  The product path (isrsolver_b200 -> libisr_b200.so) never touches 
 
 PINNING.  The assembly layer (isr_oracle.c) reproduces the reference's own compiled sources bit for bit
 (oracle/_ref, oracle/isr_ref.py, tests/test_ref_pin.py).  The linear-algebra layer in THIS file (solve,
-covariance, toy loops, Tikhonov, TSVD) remains PARITY UNPINNED BY THE REFERENCE: those reference files need
-Eigen's decompositions and ROOT, which are absent, and the reference ships no golden vectors (SURVEY.md
-F3, F5); it is pinned instead against the same formulas evaluated in 60-digit mpmath arithmetic
-(test_linear_algebra_layer_against_exact_arithmetic), LAPACK identities and the eigen-form identities
-(tests/test_oracle.py).
+covariance, toy loops, histograms, Tikhonov, TSVD) is pinned by RUNS OF THE REFERENCE ITSELF: its solver
+classes and toy-test drivers (BaseISRSolver{,2}, ISRSolverSLE{,2}, ISRSolverTikhonov, ISRSolverTSVD,
+Chi2Test, RatioTest, Utils) compile unmodified against oracle/ref_shim (dense Eigen stand-in, ROOT
+containers over an in-memory registry), their outputs on the fixtures' inputs are committed as
+tests/golden/refrun_*.npz (tests/golden/make_refrun_golden.py), and tests/test_refrun_pin.py requires
+this file to reproduce them to 1e-12 (histogram cells bit for bit).  Second anchor: the same formulas in
+60-digit mpmath arithmetic (test_linear_algebra_layer_against_exact_arithmetic), LAPACK identities and
+the eigen-form identities (tests/test_oracle.py).
 
 Two layers:
   * oracle/isr_oracle.c   kernel, QUADPACK QAGS/QAG61, interpolation bases, efficiency lookups and
