@@ -161,7 +161,8 @@ const char* isr_toy_tile_name(int n, int nstat);
 /* Toy campaigns by COUNT, as the reference's chi2Test / chi2TestData / ratioTestModel take them (src/Chi2Test.cpp:29-60,
  * 160-195; src/RatioTest.cpp:13-45): toys first_toy .. first_toy + T - 1 of the stream `seed` are drawn on the device,
  *   V[k][i] = vcs[i] + vcs_err[i] * z(seed, k, i)      (randomDrawVisCS, src/Utils.cpp:6-13)
- * with z from counter-based Philox4x32-10 + Box-Muller (isrsolver_b200/csrc/rng.cu) -- a toy depends only on
+ * with z from counter-based Philox4x32-10 + Box-Muller (isrsolver_b200/csrc/rng.cu; the pair is formed in single
+ * precision on the special-function unit, |z| <= 6.76, unless ISR_TOY_RNG=fp64 is set) -- a toy depends only on
  * (seed, k, i), so a campaign sharded over ranks by first_toy reproduces the single-GPU campaign exactly.
  * ROOT's unseeded global TRandom3 stream cannot be reproduced; isr_draw_toys returns the very vectors a campaign
  * uses, for checking it against any other implementation.  Outputs as isr_toy_batch; additionally the

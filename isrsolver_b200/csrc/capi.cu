@@ -59,6 +59,10 @@ int isr_ctx_create(int device, isr_ctx** out) {
   ISR_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
   ISR_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   ISR_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  for (int q = 0; q < 2; ++q) {
+    ISR_CUDA(cudaEventCreateWithFlags(&c->ev_gen[q], cudaEventDisableTiming));
+    ISR_CUDA(cudaEventCreateWithFlags(&c->ev_slot[q], cudaEventDisableTiming));
+  }
   ISR_CUDA(cudaStreamCreateWithFlags(&c->gen_stream, cudaStreamNonBlocking));
   ISR_CUDA(cudaEventCreateWithFlags(&c->ev_fork2, cudaEventDisableTiming));
   ISR_CUDA(cudaEventCreateWithFlags(&c->ev_rop, cudaEventDisableTiming));
@@ -82,6 +86,10 @@ void isr_ctx_destroy(isr_ctx* c) {
   if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
+  for (int q = 0; q < 2; ++q) {
+    if (c->ev_gen[q]) cudaEventDestroy(c->ev_gen[q]);
+    if (c->ev_slot[q]) cudaEventDestroy(c->ev_slot[q]);
+  }
   if (c->gen_stream) cudaStreamDestroy(c->gen_stream);
   if (c->ev_fork2) cudaEventDestroy(c->ev_fork2);
   if (c->ev_rop) cudaEventDestroy(c->ev_rop);

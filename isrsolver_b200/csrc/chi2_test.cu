@@ -180,20 +180,7 @@ static int enqueue_toys(isr_problem* p, const isr_chi2_test_args& a, const TestW
     if (!first_attempt) ISR_TRY(host_pipe_begin(p, T, a.V));     // (the first attempt's copies were issued before the assembly)
     return host_pipe_run(p, T, a.V, p->d_b0.p, o, a.chi2_out, nullptr);
   }
-  // drawn on the device: blocks of 2^16 toys (105 MB at N = 200: consumed from L2 by the next launch)
-  const int64_t chunk = std::min<int64_t>(T, 1 << 16);
-  for (int64_t t0 = 0; t0 < T; t0 += chunk) {
-    const int64_t tc = std::min<int64_t>(chunk, T - t0);
-    if (t0 == 0 && first_attempt) {
-      ISR_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));      // block 0 was drawn on the side stream (see chi2_test)
-    } else {
-      ISR_TRY(draw_toys_device(c, tc, n, a.first_toy + t0, a.seed, p->d_gen.p, p->d_gen.p + n, p->d_Vh.p, st));
-    }
-    ToyOut oc = o;
-    oc.chi2 = o.chi2 ? o.chi2 + t0 : nullptr;
-    ISR_TRY(toy_batch_device(p, tc, p->d_Vh.p, p->d_b0.p, oc));
-  }
-  return ISR_OK;
+  return drawn_toys_run(p, T, a.first_toy, a.seed, p->d_b0.p, o, /*block0_drawn=*/first_attempt);
 }
 
 // wants: what is COMPUTED (and reduced over the communicator) is decided by these flags, not by which output pointers a
@@ -251,8 +238,8 @@ int chi2_test(isr_problem* p, const isr_chi2_test_args& a, TestWants w) {
   // ---- toys that can start before the matrix exists
   if (a.V && T > 0) ISR_TRY(host_pipe_begin(p, T, a.V));
   if (drawn && T > 0) {
-    const int64_t chunk = std::min<int64_t>(T, 1 << 16);
-    ISR_TRY(p->d_Vh.reserve((size_t)chunk * n));
+    const int64_t chunk = std::min<int64_t>(T, gen_chunk(n));
+    ISR_TRY(p->d_Vh.reserve((size_t)(T > chunk ? 2 : 1) * chunk * n));
     ISR_TRY(p->d_gen.reserve((size_t)2 * n));
     p->h_gen.assign(a.vcs, a.vcs + n);
     p->h_gen.insert(p->h_gen.end(), a.vcs_err, a.vcs_err + n);

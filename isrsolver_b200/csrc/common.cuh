@@ -119,6 +119,7 @@ struct isr_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t aux_stream = nullptr;     // side work that may overlap the main stream (first toy block, eigen-system)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_gen[2] = {nullptr, nullptr}, ev_slot[2] = {nullptr, nullptr};   // device toy generator: block drawn / slot consumed
   cudaEvent_t ev_fork2 = nullptr, ev_rop = nullptr;  // factorisation: fork to the side stream / chi2 factor ready there
   cudaStream_t gen_stream = nullptr;                 // toy generator of the first block (chi2_test)
   cudaEvent_t ev_inv = nullptr, ev_cert = nullptr;   // inverse enqueued (main stream) / its certificate complete (side stream)

@@ -447,8 +447,63 @@ int iterative_solve(isr_problem* p, int niter, const double* vcs, double* bcs_ou
 }
 
 // --------------------------------------------------------------------------------------------------
-// Toy campaign by count: toys drawn on the device (rng.cu), chunk by chunk through the fused kernel.
+// Toys drawn on the device (rng.cu), block by block through the fused kernel.
 // --------------------------------------------------------------------------------------------------
+// Toys per generator block: the largest power of two whose block stays under 512 MiB (2^18 toys at N = 200, 2^17 at
+// N = 500).  Measured at N = 200, 2^20 toys (tools/exp_rng.py): 6.43 / 6.22 / 5.52 / 5.45 / 5.41 ms for 2^14 ... 2^18 toys per
+// block against 5.38 ms with resident toys -- every block boundary costs the toy kernel a tail and a ramp, and L2
+// residency of the block (2^15: 52 MB) buys nothing because the kernel is DMMA-bound.  ISR_GEN_CHUNK=<log2> overrides.
+int64_t gen_chunk(int n) {
+  static const int forced = [] {
+    const char* e = getenv("ISR_GEN_CHUNK");
+    const int lg = e ? atoi(e) : 0;
+    return lg >= 10 && lg <= 22 ? lg : 0;
+  }();
+  if (forced) return (int64_t)1 << forced;
+  int lg = 14;
+  while (lg < 20 && ((int64_t)2 << lg) * n * (int64_t)sizeof(double) <= ((int64_t)512 << 20)) ++lg;
+  return (int64_t)1 << lg;
+}
+
+// Blocks of gen_chunk(n) toys in two slots of d_Vh.  Block k + 1 is drawn on the generator stream while block k is being
+// consumed: the generator's thread blocks move onto the SMs as the persistent toy CTAs of block k retire, so the tail of
+// one kernel and the ramp of the next overlap instead of adding up (the two kernels never share an SM: a toy CTA takes
+// the whole register file).  d_gen = [vcs | vcs_err] must be on the device (ordered before c->ev_fork / on c->stream).
+// block0_drawn: block 0 is already in slot 0, signalled by c->ev_join on the generator stream (isr_chi2_test draws it
+// under the assembly and the factorisation).
+int drawn_toys_run(isr_problem* p, int64_t T, int64_t first_toy, uint64_t seed, const double* b0_dev, const ToyOut& o, bool block0_drawn) {
+  const int n = p->n;
+  isr_ctx* c = p->ctx;
+  cudaStream_t st = c->stream;
+  const int64_t chunk = std::min<int64_t>(T, gen_chunk(n));
+  ISR_TRY(p->d_Vh.reserve((size_t)(T > chunk ? 2 : 1) * chunk * n));
+  const double* gv = p->d_gen.p;
+  int k = 0;
+  for (int64_t t0 = 0; t0 < T; t0 += chunk, ++k) {
+    const int64_t tc = std::min<int64_t>(chunk, T - t0);
+    const int s = k & 1;
+    if (k == 0 && !block0_drawn) {                           // block 0, behind everything enqueued so far
+      ISR_CUDA(cudaEventRecord(c->ev_fork, st));
+      ISR_CUDA(cudaStreamWaitEvent(c->gen_stream, c->ev_fork, 0));
+      ISR_TRY(draw_toys_device(c, tc, n, first_toy, seed, gv, gv + n, p->d_Vh.p, c->gen_stream));
+      ISR_CUDA(cudaEventRecord(c->ev_join, c->gen_stream));
+    }
+    if (t0 + chunk < T) {                                    // block k + 1 into the other slot, once block k - 1 has left it
+      const int64_t t1 = t0 + chunk, tn = std::min<int64_t>(chunk, T - t1);
+      if (k >= 1) ISR_CUDA(cudaStreamWaitEvent(c->gen_stream, c->ev_slot[s ^ 1], 0));
+      ISR_TRY(draw_toys_device(c, tn, n, first_toy + t1, seed, gv, gv + n, p->d_Vh.p + (size_t)(s ^ 1) * chunk * n, c->gen_stream));
+      ISR_CUDA(cudaEventRecord(c->ev_gen[s ^ 1], c->gen_stream));
+    }
+    ISR_CUDA(cudaStreamWaitEvent(st, k == 0 ? c->ev_join : c->ev_gen[s], 0));
+    ToyOut oc = o;
+    oc.chi2 = o.chi2 ? o.chi2 + t0 : nullptr;
+    ISR_TRY(toy_batch_device(p, tc, p->d_Vh.p + (size_t)s * chunk * n, b0_dev, oc));
+    ISR_CUDA(cudaEventRecord(c->ev_slot[s], st));
+  }
+  return ISR_OK;
+}
+
+// Toy campaign by count (isr_toy_campaign).
 int toy_campaign_device(isr_problem* p, int64_t T, int64_t first_toy, uint64_t seed, const double* vcs,
                         const double* vcs_err, const double* bcs0, double* chi2_dev, double* sum_bcs_dev,
                         double* ratio_stats_dev, uint32_t* rhist_dev) {
@@ -462,9 +517,6 @@ int toy_campaign_device(isr_problem* p, int64_t T, int64_t first_toy, uint64_t s
       set_error("isr_toy_campaign: vcs / vcs_err[%d] not finite or negative", i);
       return ISR_EINVAL;
     }
-  // chunks of 2^16 toys: the generated block (105 MB at N = 200) is consumed from L2 by the next launch
-  const int64_t chunk = std::min<int64_t>(T, 1 << 16);
-  ISR_TRY(p->d_Vh.reserve((size_t)chunk * n));
   ISR_TRY(p->d_b0.reserve(n));
   ISR_TRY(p->d_gen.reserve((size_t)2 * n));
   p->h_b0.assign(bcs0, bcs0 + n);
@@ -472,17 +524,12 @@ int toy_campaign_device(isr_problem* p, int64_t T, int64_t first_toy, uint64_t s
   p->h_gen.insert(p->h_gen.end(), vcs_err, vcs_err + n);
   ISR_CUDA(cudaMemcpyAsync(p->d_b0.p, p->h_b0.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
   ISR_CUDA(cudaMemcpyAsync(p->d_gen.p, p->h_gen.data(), sizeof(double) * 2 * n, cudaMemcpyHostToDevice, st));
-  for (int64_t t0 = 0; t0 < T; t0 += chunk) {
-    const int64_t tc = std::min<int64_t>(chunk, T - t0);
-    ISR_TRY(draw_toys_device(c, tc, n, first_toy + t0, seed, p->d_gen.p, p->d_gen.p + n, p->d_Vh.p));
-    ToyOut o;
-    o.chi2 = chi2_dev ? chi2_dev + t0 : nullptr;
-    o.sum_bcs = sum_bcs_dev;
-    o.ratio_stats = ratio_stats_dev;
-    o.rhist = rhist_dev;
-    ISR_TRY(toy_batch_device(p, tc, p->d_Vh.p, p->d_b0.p, o));
-  }
-  return ISR_OK;
+  ToyOut o;
+  o.chi2 = chi2_dev;
+  o.sum_bcs = sum_bcs_dev;
+  o.ratio_stats = ratio_stats_dev;
+  o.rhist = rhist_dev;
+  return drawn_toys_run(p, T, first_toy, seed, p->d_b0.p, o, /*block0_drawn=*/false);
 }
 
 }  // namespace isr

@@ -24,6 +24,8 @@ int toy_campaign_device(isr_problem* p, int64_t T, int64_t first_toy, uint64_t s
                         double* ratio_stats_dev, uint32_t* rhist_dev);
 int draw_toys_device(isr_ctx* c, int64_t T, int n, int64_t first_toy, uint64_t seed, const double* vcs_dev,
                      const double* err_dev, double* V_dev, cudaStream_t st = nullptr);   // nullptr: the context stream
+int64_t gen_chunk(int n);   // toys per generator block
+int drawn_toys_run(isr_problem* p, int64_t T, int64_t first_toy, uint64_t seed, const double* b0_dev, const ToyOut& o, bool block0_drawn);
 struct TestWants { bool sum = false, rhist = false, range = false; };
 int chi2_test(isr_problem* p, const isr_chi2_test_args& a, TestWants w);
 }  // namespace isr
