@@ -21,6 +21,23 @@ b0 = 1.0 + 0.3 * np.sin(5 * ecm)
 vcs = G @ b0
 err = 0.05 * vcs
 s.resetVisibleCS(vcs); s.resetVisibleCSErrors(err)
+# the same test on resident toys (V_dev): the floor a campaign by count can reach
+import ctypes as C
+import torch
+from isrsolver_b200 import _lib as L
+lib = L.load()
+Vd = torch.from_numpy(isr.draw_toys_device(vcs, err, 1, seed=1)).cuda().repeat(T, 1).contiguous()
+a = L.Chi2TestArgs()
+lohi, cnt, total = np.zeros(2), np.zeros(130, dtype=np.int64), C.c_int64()
+errc, b0c = np.ascontiguousarray(err), np.ascontiguousarray(b0)
+a.vcs_err, a.bcs0, a.n_toys, a.nbins, a.V_dev = L.dptr(errc), L.dptr(b0c), T, 128, Vd.data_ptr()
+a.chi2_lo_hi_out, a.chi2_counts_out, a.total_toys_out = L.dptr(lohi), cnt.ctypes.data_as(C.POINTER(C.c_int64)), C.pointer(total)
+s._select_for_toys()
+for k in range(reps + 2):
+    t0 = time.perf_counter()
+    L.check(lib.isr_chi2_test(s._p, C.byref(a)))
+    dt = time.perf_counter() - t0
+print(f"resident toys: {dt * 1e3:.3f} ms  {T / dt:.4g} toys/s", flush=True)
 for k in range(reps + 2):
     t0 = time.perf_counter()
     o = s.chi2_test_call(b0, n=T, vcs=vcs, vcs_err=err, seed=7 + k, want_chi2=False)
