@@ -68,6 +68,13 @@ def test_cpp_mirror_matches_oracle(tmp_path, oracle):
     assert np.abs(cov - g["cov"]).max() <= 1e-8 * np.abs(g["cov"]).max()
     np.testing.assert_allclose(rd("out_chi2.bin"), g["chi2"], rtol=1e-7)
     np.testing.assert_allclose(rd("out_means.bin"), g["ratio_means"], rtol=1e-6, atol=1e-9)
+    # the same against what the reference's own compiled classes returned (tests/golden/make_refrun_golden.py)
+    r = load_golden("refrun_c2_sle_n40_cspline")
+    assert np.abs(G - r["ref_G_native"]).max() <= 1e-9 * np.abs(r["ref_G_native"]).max()
+    assert np.abs(rd("out_bcs.bin") - r["ref_bcs_native"]).max() <= 1e-8 * np.abs(r["ref_bcs_native"]).max()
+    assert np.abs(cov - r["ref_cov_native"]).max() <= 1e-8 * np.abs(r["ref_cov_native"]).max()
+    np.testing.assert_allclose(rd("out_chi2.bin"), r["ref_chi2"], rtol=1e-7)
+    np.testing.assert_allclose(rd("out_means.bin"), r["ref_ratio_means"], rtol=1e-6, atol=1e-9)
     I = oracle.Interp(g["ecm"], 0.827)      # the Tikhonov/TSVD solvers in the C++ test keep the default linear basis
     Gl = I.eval_eq_matrix(mode="converged")
     F = oracle.tikhonov_F(I.deriv_projector(), I.integral_basis(), True)

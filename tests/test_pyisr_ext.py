@@ -55,6 +55,10 @@ def test_compiled_pyisr_matches_golden(tmp_path):
     assert np.abs(s.bcs_cov_matrix() - g["cov"]).max() <= 1e-8 * np.abs(g["cov"]).max()
     np.testing.assert_allclose(s.bcs_inv_cov_matrix() @ g["cov"], np.eye(n), atol=1e-7)
     assert s.condnum_eval() == pytest.approx(float(g["cond"]), rel=1e-8)
+    # against the reference's own compiled classes on the same inputs, nothing injected on either side
+    r0 = load_golden("refrun_c2_sle_n40_cspline")
+    assert np.abs(s.bcs() - r0["ref_bcs_native"]).max() <= 1e-8 * np.abs(r0["ref_bcs_native"]).max()
+    assert np.abs(s.bcs_cov_matrix() - r0["ref_cov_native"]).max() <= 1e-8 * np.abs(r0["ref_cov_native"]).max()
     assert s.interp_eval(float(g["ecm"][7])) == pytest.approx(s.bcs()[7], rel=1e-12)
     # views keep the solver alive
     b = s.bcs()
@@ -112,6 +116,12 @@ def test_compiled_pyisr_tikhonov_and_tsvd(oracle):
     v.enable_keepone(); v.solve()
     np.testing.assert_allclose(v.bcs(), g["tsvd_bcs_keepone"], rtol=1e-6, atol=1e-8 * np.abs(g["tsvd_bcs"]).max())
     assert v.upper_TSVD_index == int(g["tsvd_k"])
+    # ISRSolverTSVD of the reference itself (its own assembly, spread product, JacobiSVD, minimum-norm COD solve)
+    rr = load_golden("refrun_c4_tikhonov_n32_spread")
+    scale = np.abs(rr["ref_tsvd_bcs"]).max()
+    assert np.abs(v.bcs() - rr["ref_tsvd_bcs_keepone"]).max() <= 1e-7 * scale
+    v.disable_keepone(); v.solve()
+    assert np.abs(v.bcs() - rr["ref_tsvd_bcs"]).max() <= 1e-7 * scale
 
 
 @pytest.mark.gpu
