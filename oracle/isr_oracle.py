@@ -449,6 +449,19 @@ def tsvd_solve(G, vcs, vcs_err, k, keep_one=False):
     return bcs, cov, (U, S, Vt)
 
 
+def iterative_solve(G, vcs, vcs_err, n_iter=10):
+    """IterISRInterpSolver::solve -- src/IterISRInterpSolver.cpp:45-57: b <- vcs; repeat: radcorr = (G b) / b, b = vcs / radcorr,
+    Cov = diag((vcs_err / radcorr)^2).  Returns (bcs, radcorr, cov)."""
+    vcs = np.asarray(vcs, dtype=float)
+    b, rad = vcs.copy(), np.zeros(len(vcs))
+    cov = np.zeros((len(vcs), len(vcs)))
+    for _ in range(int(n_iter)):
+        rad = (G @ b) / b
+        b = vcs / rad
+        cov = np.diag((np.asarray(vcs_err, dtype=float) / rad) ** 2)
+    return b, rad, cov
+
+
 def cond_number(G):
     """evalConditionNumber -- src/ISRSolverSLE.cpp:200-204."""
     s = np.linalg.svd(G, compute_uv=False)

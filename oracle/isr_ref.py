@@ -5,7 +5,8 @@ ORACLE / TEST INFRASTRUCTURE: only tests/, __graft_entry__.smoke() and bench.py'
 
 libisr_ref.so holds, compiled unmodified from /root/reference/src by oracle/Makefile:
     KuraevFadin.cpp, Integration.cpp, {Base,Linear,CSpline}RangeInterpolator{,2}.cpp, Interpolator{,2}.cpp   (assembly)
-    BaseISRSolver.cpp, ISRSolverSLE.cpp, ISRSolverTikhonov.cpp, ISRSolverTSVD.cpp, Chi2Test.cpp, RatioTest.cpp, Utils.cpp
+    BaseISRSolver{,2}.cpp, ISRSolverSLE{,2}.cpp, ISRSolverTikhonov.cpp, ISRSolverTSVD.cpp, IterISRInterpSolver.cpp,
+    Chi2Test.cpp, RatioTest.cpp, Utils.cpp
 linked against oracle/ref_shim (the GSL entry points they call, implemented on the QUADPACK / cspline
 restatement of oracle/isr_oracle.c; a dense Eigen stand-in with textbook decompositions; ROOT containers over an
 in-memory registry; Boost / NLopt stand-ins) and oracle/ref_glue.cpp + oracle/ref_solver_glue.cpp (extern "C" access).
@@ -106,6 +107,8 @@ def lib():
         L.refs_lambda_objective.argtypes = [vp, C.c_double, _dp]
         L.refs_tik_operators.argtypes = [vp, _dp, _dp]
         L.refs_tsvd_set.argtypes = [vp, C.c_int, C.c_int]
+        L.refs_iter_set.argtypes = [vp, C.c_int]
+        L.refs_iter_radcorr.argtypes = [vp, _dp]
         L.refs_chi2_test_model.argtypes = [vp, C.c_int, _dp, _dp, _dp, _dp, _dp, fp]
         L.refs_chi2_test_data.argtypes = [vp, C.c_int, _dp, _dp, _dp, fp]
         L.refs_ratio_test_model.argtypes = [vp, C.c_int, _dp, _dp, _dp, _dp, _dp, fp, _dp]
@@ -242,11 +245,11 @@ def _c(a):
 class RefSolver:
     """One of the reference's compiled ISRSolverSLE / ISRSolverTikhonov / ISRSolverTSVD objects.
 
-    kind: 'sle' | 'tikhonov' | 'tsvd'.  ctor 'pointers' = the constructor PyISR uses (src/BaseISRSolver.cpp:78-128),
+    kind: 'sle' | 'tikhonov' | 'tsvd' | 'iterative' (IterISRInterpSolver).  ctor 'pointers' = the constructor PyISR uses (src/BaseISRSolver.cpp:78-128),
     'graph' = the TGraphErrors (+ TEfficiency) constructor of the executables (:135-165).  Matrices cross this boundary
     row-major [i][j] like the rest of the oracle (the library is column-major inside)."""
 
-    KINDS = {"sle": 0, "tikhonov": 1, "tsvd": 2}
+    KINDS = {"sle": 0, "tikhonov": 1, "tsvd": 2, "iterative": 3}
 
     def __init__(self, kind, ecm, vcs, vcs_err, threshold, ecm_err=None, eff: O.Efficiency | None = None, settings=None,
                  lam=1.0, upper=None, ctor="graph"):
@@ -340,6 +343,15 @@ class RefSolver:
         D, w = np.empty((self.n, self.n)), np.empty(self.n)
         self._L.refs_tik_operators(self._h, _p(D), _p(w))
         return D.T.copy(), w
+
+    # ---- IterISRInterpSolver
+    def iter_set(self, n_iter):
+        self._L.refs_iter_set(self._h, int(n_iter))
+
+    def radcorr(self):
+        out = np.empty(self.n)
+        self._check(self._L.refs_iter_radcorr(self._h, _p(out)))
+        return out
 
     # ---- TSVD
     def tsvd_set(self, upper, keep_one=False):

@@ -63,6 +63,21 @@ class TGraphErrors : public TObject {
   std::vector<double> x_, y_, ex_, ey_;
 };
 
+class TGraph : public TObject {
+ public:
+  TGraph(int n, const double* x, const double* y) : x_(x, x + n), y_(y, y + n) {}
+  int GetN() const { return (int)x_.size(); }
+  double* GetX() { return x_.data(); }
+  double* GetY() { return y_.data(); }
+  int Write(const char* name = nullptr) override {
+    root_shim::registry()[name ? name : "Graph"] = std::make_shared<TGraph>(*this);
+    return 0;
+  }
+
+ private:
+  std::vector<double> x_, y_;
+};
+
 class TMatrixD : public TObject {
  public:
   TMatrixD(int r, int c) : r_(r), c_(c), v_((std::size_t)r * c, 0.0) {}

@@ -4,7 +4,8 @@
 // may load oracle/_ref/libisr_ref.so).
 //
 // oracle/Makefile compiles, unmodified and from where they lie under /root/reference/src:
-//   BaseISRSolver.cpp  ISRSolverSLE.cpp  ISRSolverTikhonov.cpp  ISRSolverTSVD.cpp  Chi2Test.cpp  RatioTest.cpp  Utils.cpp
+//   BaseISRSolver.cpp  ISRSolverSLE.cpp  ISRSolverTikhonov.cpp  ISRSolverTSVD.cpp  IterISRInterpSolver.cpp  Chi2Test.cpp
+//   RatioTest.cpp  Utils.cpp
 // against oracle/ref_shim: a dense Eigen stand-in (textbook decompositions under Eigen's class names), ROOT containers
 // backed by an in-memory registry, Boost.Format / Boost.Accumulators stand-ins, an empty nlopt.hpp.  Everything between
 // the constructor and the numbers -- sorting the points, the efficiency adaptor, evalEqMatrix with the energy-spread
@@ -24,6 +25,7 @@
 #include "ISRSolverSLE.hpp"
 #include "ISRSolverTSVD.hpp"
 #include "ISRSolverTikhonov.hpp"
+#include "IterISRInterpSolver.hpp"
 #include "RatioTest.hpp"
 #include "Utils.hpp"
 #include "root_shim.h"
@@ -74,9 +76,16 @@ struct TikX : ISRSolverTikhonov {
 struct TsvdX : ISRSolverTSVD {
   using ISRSolverTSVD::ISRSolverTSVD;
 };
+struct IterX : IterISRInterpSolver {
+  using IterISRInterpSolver::IterISRInterpSolver;
+  void inject(const Eigen::MatrixXd& G) {
+    _getIntegralOperatorMatrix() = G;
+    _isEqMatrixPrepared = true;
+  }
+};
 
 struct Handle {
-  int kind;  // 0 SLE, 1 Tikhonov, 2 TSVD
+  int kind;  // 0 SLE, 1 Tikhonov, 2 TSVD, 3 iterative
   std::unique_ptr<ISRSolverSLE> s;
   std::string error;
 };
@@ -109,7 +118,7 @@ extern "C" {
 
 const char* refs_last_error() { return g_error.c_str(); }
 
-// kind: 0 ISRSolverSLE, 1 ISRSolverTikhonov (lambda), 2 ISRSolverTSVD (upper index).
+// kind: 0 ISRSolverSLE, 1 ISRSolverTikhonov (lambda), 2 ISRSolverTSVD (upper index), 3 IterISRInterpSolver (upper = iterations).
 // ctor 0: the pointer constructor PyISR uses (include/PyISRSolver.hpp; src/BaseISRSolver.cpp:78-128; ecm_err == NULL
 //         switches the energy spread off, efficiency = 1);
 // ctor 1: the TGraphErrors (+ TEfficiency) constructor of the executables (src/BaseISRSolver.cpp:31-76, 135-165, 232-258);
@@ -136,6 +145,7 @@ void* refs_create(int kind, int ctor, int n, const double* ecm, const double* vc
         t->setUpperTSVDIndex(upper);
         h->s.reset(t);
       }
+      if (kind == 3) h->s.reset(new IterX((std::size_t)n, e, v, ee, ve, threshold, one));
     } else {
       TGraphErrors g(n, ecm, vcs, ecm_err, vcs_err);
       std::unique_ptr<TEfficiency> te;
@@ -146,6 +156,7 @@ void* refs_create(int kind, int ctor, int n, const double* ecm, const double* vc
       if (kind == 0) h->s.reset(te ? new SleX(&g, te.get(), threshold) : new SleX(&g, threshold));
       if (kind == 1) h->s.reset(te ? new TikX(&g, te.get(), threshold, lambda) : new TikX(&g, threshold, lambda));
       if (kind == 2) h->s.reset(te ? new TsvdX(&g, te.get(), threshold, upper) : new TsvdX(&g, threshold, upper));
+      if (kind == 3) h->s.reset(te ? new IterX(&g, te.get(), threshold) : new IterX(&g, threshold));
       if (ecm_err) h->s->enableEnergySpread();
     }
   });
@@ -176,6 +187,7 @@ int refs_inject_matrix(void* vh, const double* G) {
   for (int q = 0; q < n * n; ++q) M.data()[q] = G[q];
   if (h->kind == 0) { static_cast<SleX*>(h->s.get())->inject(M); return 0; }
   if (h->kind == 1) return guarded([&]() { static_cast<TikX*>(h->s.get())->inject(M); });
+  if (h->kind == 3) { static_cast<IterX*>(h->s.get())->inject(M); return 0; }
   g_error = "refs_inject_matrix: not available for ISRSolverTSVD";
   return 1;
 }
@@ -248,6 +260,22 @@ void refs_tik_operators(void* vh, double* D, double* w) {   // D column-major
   const int n = (int)t->getN();
   for (int q = 0; q < n * n; ++q) D[q] = t->D().data()[q];
   for (int i = 0; i < n; ++i) w[i] = t->w()(i);
+}
+
+// IterISRInterpSolver (src/IterISRInterpSolver.cpp:45-57): number of iterations; the radiative correction is private and
+// leaves the object only through save() (:67-93, the "radiative_correction" graph), which is how it is read here
+void refs_iter_set(void* vh, int n_iter) { static_cast<IterX*>(static_cast<Handle*>(vh)->s.get())->setNumOfIters((std::size_t)n_iter); }
+int refs_iter_radcorr(void* vh, double* out) {
+  auto* h = static_cast<Handle*>(vh);
+  return guarded([&]() {
+    root_shim::registry().clear();
+    OutputOptions o;
+    o.visibleCSGraphName = "vcs";
+    o.bornCSGraphName = "bcs";
+    h->s->save("out.root", o);
+    auto* g = dynamic_cast<TGraph*>(root_shim::registry().at("radiative_correction").get());
+    for (int i = 0; i < g->GetN(); ++i) out[i] = g->GetY()[i];
+  });
 }
 
 // TSVD

@@ -2,13 +2,13 @@
 """Generate tests/golden/refrun_*.npz: outputs of the REFERENCE'S OWN solver classes and toy-test drivers.
 
 oracle/_ref/libisr_ref.so holds src/BaseISRSolver{,2}.cpp, ISRSolverSLE{,2}.cpp, ISRSolverTikhonov.cpp, ISRSolverTSVD.cpp,
-Chi2Test.cpp, RatioTest.cpp and Utils.cpp compiled unmodified from /root/reference against oracle/ref_shim (dense Eigen
+IterISRInterpSolver.cpp, Chi2Test.cpp, RatioTest.cpp and Utils.cpp compiled unmodified from /root/reference against oracle/ref_shim (dense Eigen
 stand-in, ROOT containers over an in-memory registry; oracle/Makefile).  This script runs them on the inputs of the
 existing fixtures (tests/golden/c*.npz: same points, errors, toys, model) and stores what they return under ref_* keys:
 
   injected   the solver is handed the fixture's operator matrix (G_converged / G_spread), so that only the linear-algebra
              layer differs from the restatement: solve(), save(), evalConditionNumber, chi2TestModel, chi2TestData,
-             ratioTestModel; for c4 also ISRSolverTikhonov (12 lambda, both regularisers, the L-curve functionals,
+             ratioTestModel, IterISRInterpSolver::solve (10 and 3 iterations); for c4 also ISRSolverTikhonov (12 lambda, both regularisers, the L-curve functionals,
              lambdaObjective, chi2TestModel with the Tikhonov covariance)
   native     the solver runs its own evalEqMatrix (N^2 adaptive integrations, the efficiency adaptor, the energy-spread
              product) and then solve(); for c4 also ISRSolverTSVD (whose SVD cannot be separated from evalEqMatrix)
@@ -66,6 +66,14 @@ def run_v1(g):
     S.reset_vcs(g["vcs"])
     chi2d, cd, lod, hid = S.chi2_test_data(g["toys"])
     out.update(ref_chi2_data=chi2d, ref_chi2_data_hist=cd, ref_chi2_data_lo=lod, ref_chi2_data_hi=hid)
+    # IterISRInterpSolver on the same operator: default 10 iterations, and 3
+    It = R.RefSolver("iterative", g["ecm"], g["vcs"], g["vcs_err"], thr, ecm_err=ee, settings=st)
+    It.inject_matrix(G)
+    for tag, n_iter in (("", 10), ("3", 3)):
+        It.iter_set(n_iter)
+        bi, ci = It.solve()
+        assert np.count_nonzero(ci - np.diag(np.diag(ci))) == 0
+        out.update({"ref_iter%s_bcs" % tag: bi, "ref_iter%s_radcorr" % tag: It.radcorr(), "ref_iter%s_cov_diag" % tag: np.diag(ci).copy()})
     # native: both constructors, nothing injected
     for ctor in ("graph", "pointers"):
         Sn = R.RefSolver("sle", g["ecm"], g["vcs"], g["vcs_err"], thr, ecm_err=ee, settings=st, ctor=ctor)

@@ -70,6 +70,22 @@ def test_chi2_and_ratio_tests(name):
 
 
 @pytest.mark.parametrize("name", V1)
+def test_iterative_solver(name):
+    """isr_iterative_solve against IterISRInterpSolver::solve of the reference itself (10 and 3 iterations)."""
+    import isrsolver_b200 as isr
+    g, r = load_golden(name), load_golden("refrun_" + name)
+    for tag, n_iter in (("", 10), ("3", 3)):
+        s = make_solver(g, cls=isr.IterISRInterpSolver, spread="ecm_err" in g)
+        s.setNumOfIters(n_iter)
+        s.set_matrix(fixture_matrix(g))
+        s.solve()
+        close(s.bcs(), r["ref_iter%s_bcs" % tag])
+        close(s.radcorr(), r["ref_iter%s_radcorr" % tag])
+        close(np.diag(s.bcs_cov_matrix()), r["ref_iter%s_cov_diag" % tag])
+        assert np.count_nonzero(s.bcs_cov_matrix() - np.diag(np.diag(s.bcs_cov_matrix()))) == 0
+
+
+@pytest.mark.parametrize("name", V1)
 def test_native_assembly_and_solve(name):
     """Nothing injected on either side: the reference's evalEqMatrix + solve() against isr_assemble + isr_factor + isr_solve."""
     g, r = load_golden(name), load_golden("refrun_" + name)

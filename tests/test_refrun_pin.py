@@ -90,6 +90,16 @@ def test_ratio_test_model(name):
     np.testing.assert_allclose(errs, r["ref_ratio_mean_errors"], rtol=1e-10, atol=1e-15)
 
 
+@pytest.mark.parametrize("name", V1)
+def test_iterative_solver(name):
+    """IterISRInterpSolver::solve (src/IterISRInterpSolver.cpp:45-57): radiative-correction iteration, diagonal covariance."""
+    g, r = load_golden(name), load_golden("refrun_" + name)
+    for tag, n_iter in (("", 10), ("3", 3)):
+        b, rad, cov = O.iterative_solve(fixture_matrix(g), g["vcs"], g["vcs_err"], n_iter)
+        assert rel(b, r["ref_iter%s_bcs" % tag]) < RT and rel(rad, r["ref_iter%s_radcorr" % tag]) < RT
+        assert rel(np.diag(cov), r["ref_iter%s_cov_diag" % tag]) < RT
+
+
 @pytest.mark.parametrize("name", V1 + ["c3_sle2_n24_eps64"])
 def test_native_run_matrix_and_solution(name):
     """Nothing injected: the reference's own constructor (sorting, efficiency adaptor), evalEqMatrix and solve()."""
