@@ -462,6 +462,51 @@ def iterative_solve(G, vcs, vcs_err, n_iter=10):
     return b, rad, cov
 
 
+_FN = C.CFUNCTYPE(C.c_double, C.c_double, C.c_void_p)
+
+
+def convolution_kf(energy, fcn, min_x, max_x):
+    """convolutionKuraevFadin (src/KuraevFadin.cpp:56-73) of a Python callable of the energy, efficiency = 1."""
+    L = lib()
+    L.orc_convolution_kf.restype = C.c_double
+    L.orc_convolution_kf.argtypes = [C.c_double, _FN, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int]
+    cb = _FN(lambda e, ctx: float(fcn(e)))
+    return L.orc_convolution_kf(float(energy), cb, None, float(min_x), float(max_x), None, 0)
+
+
+def gaussian_conv(energy, sigma2, fcn):
+    """gaussian_conv (src/Integration.cpp:86-100): 6-point Gauss-Hermite average of fcn around `energy`."""
+    L = lib()
+    L.orc_gaussian_conv.restype = C.c_double
+    L.orc_gaussian_conv.argtypes = [C.c_double, C.c_double, _FN, C.c_void_p]
+    cb = _FN(lambda e, ctx: float(fcn(e)))
+    return L.orc_gaussian_conv(float(energy), float(sigma2), cb, None)
+
+
+def vcs_fit_model(ecm, threshold, born, ecm_err=None):
+    """The model side of ISRSolverVCSFitFunction (src/ISRSolverVCSFitter.cpp:64-88, 122-150): sigma_vis of the Born
+    function `born(E)` at every energy -- 0 at or below threshold, convolutionKuraevFadin over [0, 1 - thr^2 / E^2], and
+    its Gaussian average over the beam-energy spread when `ecm_err` is given."""
+    def vis(e):
+        if e * e <= threshold * threshold:
+            return 0.0
+        return convolution_kf(e, born, 0.0, 1.0 - threshold * threshold / (e * e))
+    if ecm_err is None:
+        return np.array([vis(float(e)) for e in ecm])
+    return np.array([gaussian_conv(float(e), float(s) ** 2, vis) for e, s in zip(ecm, ecm_err)])
+
+
+def vcs_fit_chi2(ecm, vcs, vcs_err, threshold, born, ecm_err=None):
+    """ISRSolverVCSFitFunction::operator() (src/ISRSolverVCSFitter.cpp:64-93): sum of ((model - vcs) / vcs_err)^2 in point
+    order."""
+    m = vcs_fit_model(ecm, threshold, born, ecm_err)
+    chi2 = 0.0
+    for mi, vi, ei in zip(m, vcs, vcs_err):
+        d = mi - vi
+        chi2 += d * d / ei / ei
+    return chi2
+
+
 def cond_number(G):
     """evalConditionNumber -- src/ISRSolverSLE.cpp:200-204."""
     s = np.linalg.svd(G, compute_uv=False)

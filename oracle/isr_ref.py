@@ -36,6 +36,7 @@ _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
 CALLBACK = C.CFUNCTYPE(C.c_double, C.c_double, C.c_void_p)
 EFF_CALLBACK = C.CFUNCTYPE(C.c_double, C.c_double, C.c_double, C.c_void_p)
+FIT_CALLBACK = C.CFUNCTYPE(C.c_double, C.c_double, _dp, C.c_int, C.c_void_p)
 
 
 def build() -> bool:
@@ -113,6 +114,13 @@ def lib():
         L.refs_chi2_test_data.argtypes = [vp, C.c_int, _dp, _dp, _dp, fp]
         L.refs_ratio_test_model.argtypes = [vp, C.c_int, _dp, _dp, _dp, _dp, _dp, fp, _dp]
         L.refs_save.argtypes = [vp, _dp, _dp, _dp, _dp, _dp]
+        L.reff_last_error.restype = C.c_char_p
+        L.reff_create.restype = vp
+        L.reff_create.argtypes = [C.c_int, C.c_double, _dp, _dp, _dp, _dp, FIT_CALLBACK, vp]
+        L.reff_free.argtypes = [vp]
+        L.reff_set_spread.argtypes = [vp, C.c_int]
+        L.reff_chi2.argtypes = [vp, _dp, C.c_int, _dp]
+        L.reff_save.argtypes = [vp, _dp, C.c_int, C.c_int, _dp]
         L.refs2_last_error.restype = C.c_char_p
         L.refs2_create.restype = vp
         L.refs2_create.argtypes = [C.c_int, _dp, _dp, _dp, _dp, C.c_double, vp]
@@ -436,3 +444,41 @@ class RefSolver2:
 
     def cond(self):
         return self._L.refs2_cond(self._h)
+
+
+class RefVCSFitFunction:
+    """The reference's compiled ISRSolverVCSFitFunction (src/ISRSolverVCSFitter.cpp): chi2 of a parametrised Born cross
+    section `fcn(energy, par)` against the visible data through N forward convolutions (blurred by the energy spread when
+    `ecm_err` is given), and what saveResults writes at given parameters."""
+
+    def __init__(self, ecm, vcs, vcs_err, threshold, fcn, ecm_err=None):
+        self._L = lib()
+        self.n = len(ecm)
+        self._cb = FIT_CALLBACK(lambda en, par, npar, ctx: float(fcn(en, [par[i] for i in range(npar)])))
+        ee = None if ecm_err is None else _c(ecm_err)
+        self._h = self._L.reff_create(self.n, float(threshold), _p(_c(ecm)), _p(_c(vcs)), None if ee is None else _p(ee),
+                                      _p(_c(vcs_err)), self._cb, None)
+        if not self._h:
+            raise RuntimeError("reference constructor failed: " + self._L.reff_last_error().decode())
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.reff_free(self._h)
+            self._h = None
+
+    def set_spread(self, on):
+        self._L.reff_set_spread(self._h, int(bool(on)))
+
+    def chi2(self, par):
+        par = _c(par)
+        out = C.c_double(0.0)
+        if self._L.reff_chi2(self._h, _p(par), len(par), C.byref(out)):
+            raise RuntimeError(self._L.reff_last_error().decode())
+        return out.value
+
+    def save_results(self, par):
+        par = _c(par)
+        out = np.empty((4, self.n))
+        if self._L.reff_save(self._h, _p(par), len(par), self.n, _p(out)):
+            raise RuntimeError(self._L.reff_last_error().decode())
+        return dict(vcs_gauss_conv=out[0], rad_delta=out[1], bcs=out[2], bcs_err=out[3])

@@ -53,6 +53,7 @@ class TGraphErrors : public TObject {
   double* GetY() { return y_.data(); }
   double* GetEX() { return ex_.data(); }
   double* GetEY() { return ey_.data(); }
+  void SetMarkerStyle(int) {}
   TObject* Clone(const char* = "") const override { return new TGraphErrors(*this); }
   int Write(const char* name = nullptr) override {
     root_shim::registry()[name ? name : "Graph"] = std::make_shared<TGraphErrors>(*this);
@@ -69,6 +70,7 @@ class TGraph : public TObject {
   int GetN() const { return (int)x_.size(); }
   double* GetX() { return x_.data(); }
   double* GetY() { return y_.data(); }
+  void SetMarkerStyle(int) {}
   int Write(const char* name = nullptr) override {
     root_shim::registry()[name ? name : "Graph"] = std::make_shared<TGraph>(*this);
     return 0;

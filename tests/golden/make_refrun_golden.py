@@ -12,6 +12,8 @@ existing fixtures (tests/golden/c*.npz: same points, errors, toys, model) and st
              lambdaObjective, chi2TestModel with the Tikhonov covariance)
   native     the solver runs its own evalEqMatrix (N^2 adaptive integrations, the efficiency adaptor, the energy-spread
              product) and then solve(); for c4 also ISRSolverTSVD (whose SVD cannot be separated from evalEqMatrix)
+  vcsfit     ISRSolverVCSFitFunction (src/ISRSolverVCSFitter.cpp): the chi2 objective of the visible-cross-section fit at four
+             parameter sets (N forward convolutions each, with and without energy spread) and saveResults
   e2e        two full-size runs with nothing injected: N = 200 cubic spline, chi2TestModel + ratioTestModel on 32 toys
              (BASELINE configs[1] geometry), and N = 200 cubic spline with energy spread, ISRSolverTikhonov at 4 lambda
              with chi2TestModel on 16 toys each (configs[3] geometry).
@@ -183,6 +185,37 @@ def run_e2e_tikhonov(n=200, toys=16, lam=(1e-6, 1e-4, 1e-2, 1.0)):
     return g
 
 
+VCSFIT_PARS = np.array([[4.2, 1.52, 0.26], [3.7, 1.47, 0.22], [4.0, 1.50, 0.30], [4.4, 1.55, 0.25]])
+
+
+def bw_model(e, par, thr=O.E_THR):
+    """The parametrised Born cross section of the fit: relativistic Breit-Wigner x threshold factor, par = (sigma0, M, Gamma)."""
+    s0, M, Gm = par
+    if e <= thr:
+        return 0.0
+    return s0 * M * M * Gm * Gm / ((e * e - M * M) ** 2 + M * M * Gm * Gm) * (1.0 - thr * thr / (e * e)) ** 1.5
+
+
+def run_vcsfit(n=24):
+    """ISRSolverVCSFitFunction of the reference: chi2 at four parameter sets away from the truth, without and with a 2 MeV
+    energy spread, and saveResults (blurred model, radiative correction, Born points) at the first set."""
+    ecm = np.linspace(O.E_MIN, O.E_MAX, n)
+    vcs = O.bw_visible(ecm)
+    vcs_err = 0.05 * vcs
+    ee = np.full(n, 0.002)
+    out = dict(ecm=ecm, threshold=O.E_THR, vcs=vcs, vcs_err=vcs_err, ecm_err=ee, pars=VCSFIT_PARS)
+    F = R.RefVCSFitFunction(ecm, vcs, vcs_err, O.E_THR, bw_model)
+    out["ref_chi2"] = np.array([F.chi2(p) for p in VCSFIT_PARS])
+    out["ref_chi2_true"] = F.chi2([O.BW_S0, O.BW_M, O.BW_G])
+    sv = F.save_results(VCSFIT_PARS[0])
+    out.update({"ref_save_" + k: v for k, v in sv.items()})
+    Fs = R.RefVCSFitFunction(ecm, vcs, vcs_err, O.E_THR, bw_model, ecm_err=ee)
+    out["ref_chi2_spread"] = np.array([Fs.chi2(p) for p in VCSFIT_PARS])
+    sv = Fs.save_results(VCSFIT_PARS[0])
+    out.update({"ref_save_spread_" + k: v for k, v in sv.items()})
+    return out
+
+
 def save(name, out):
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
     print(name, "written:", os.path.getsize(os.path.join(HERE, name + ".npz")) // 1024, "kB", flush=True)
@@ -205,6 +238,7 @@ if __name__ == "__main__":
     t0 = time.time()
     for name in SMALL:
         save("refrun_" + name, small_case(name))
+    save("refrun_vcsfit_n24", run_vcsfit())
     save("refrun_e2e_sle_n200_cspline", run_e2e_sle())
     save("refrun_e2e_tikhonov_n200_spread", run_e2e_tikhonov())
     print("done in %.0f s" % (time.time() - t0))

@@ -176,6 +176,40 @@ def test_tsvd():
     close(s.bcs_cov_matrix(), r["ref_tsvd_cov_full"])
 
 
+def test_vcs_fit_objective_through_the_convolution_service():
+    """The chi2 objective of the reference's visible-cross-section fit (ISRSolverVCSFitFunction::operator(): N forward
+    convolutions of a parametrised Born function, optionally blurred) and what its saveResults writes, against the GPU
+    convolution service -- one plan per data set, one convolve() per parameter set."""
+    import isrsolver_b200 as isr
+    r = load_golden("refrun_vcsfit_n24")
+    thr, ecm = float(r["threshold"]), r["ecm"]
+
+    def bw(par):
+        s0, M, Gm = par
+        def f(e):
+            e = np.asarray(e, dtype=np.float64)
+            tf = np.where(e > thr, 1.0 - thr * thr / (e * e), 0.0)
+            return np.where(e > thr, s0 * M * M * Gm * Gm / ((e * e - M * M) ** 2 + M * M * Gm * Gm) * tf ** 1.5, 0.0)
+        return f
+    plan = isr.ConvolutionPlan(ecm, threshold=thr)
+    for k, par in enumerate(r["pars"]):
+        vis, _ = plan.convolve(bw(par))
+        chi2 = float((((vis - r["vcs"]) / r["vcs_err"]) ** 2).sum())
+        assert chi2 == pytest.approx(float(r["ref_chi2"][k]), rel=RT)
+        blurred = isr.convolutionKuraevFadinBlurred(ecm, bw(par), thr, r["ecm_err"])
+        chi2s = float((((blurred - r["vcs"]) / r["vcs_err"]) ** 2).sum())
+        assert chi2s == pytest.approx(float(r["ref_chi2_spread"][k]), rel=RT)
+        if k == 0:
+            born = bw(par)(ecm)
+            np.testing.assert_allclose(vis, r["ref_save_vcs_gauss_conv"], rtol=1e-10)
+            np.testing.assert_allclose(blurred, r["ref_save_spread_vcs_gauss_conv"], rtol=1e-10)
+            np.testing.assert_allclose(vis / born - 1.0, r["ref_save_rad_delta"], rtol=RT, atol=1e-11)
+            np.testing.assert_allclose(r["vcs"] / (blurred / born), r["ref_save_spread_bcs"], rtol=1e-10)
+    # at the true parameters the data ARE the model: chi2 collapses to rounding
+    vis, _ = plan.convolve(bw((4.0, 1.50, 0.25)))
+    assert float((((vis - r["vcs"]) / r["vcs_err"]) ** 2).sum()) < 1e-12
+
+
 def test_full_size_sle_run_n200():
     """BASELINE configs[1] geometry end to end: the reference assembled N = 200 (cubic spline) with its 40 000 adaptive
     integrations, solved, and ran chi2TestModel + ratioTestModel on 32 toys; the GPU does the same from the same inputs."""

@@ -161,6 +161,37 @@ def test_tsvd():
     assert rel(b, r["ref_tsvd_bcs_full"]) < 1e-11 and rel(cov, r["ref_tsvd_cov_full"]) < 1e-11
 
 
+def _bw(par, thr):
+    s0, M, Gm = par
+    def f(e):
+        if e <= thr:
+            return 0.0
+        return s0 * M * M * Gm * Gm / ((e * e - M * M) ** 2 + M * M * Gm * Gm) * (1.0 - thr * thr / (e * e)) ** 1.5
+    return f
+
+
+def test_vcs_fit_function():
+    """ISRSolverVCSFitFunction (src/ISRSolverVCSFitter.cpp:64-93, 107-177) run by the reference itself: the restated forward
+    convolution + Gauss-Hermite blur + chi2 sum reproduces its objective BIT FOR BIT, with and without energy spread, and
+    what saveResults writes (blurred model, radiative correction delta = model / Born - 1, Born points vcs / (1 + delta))."""
+    r = load_golden("refrun_vcsfit_n24")
+    thr = float(r["threshold"])
+    for k, par in enumerate(r["pars"]):
+        assert O.vcs_fit_chi2(r["ecm"], r["vcs"], r["vcs_err"], thr, _bw(par, thr)) == r["ref_chi2"][k]
+        if k < 2:
+            assert O.vcs_fit_chi2(r["ecm"], r["vcs"], r["vcs_err"], thr, _bw(par, thr), r["ecm_err"]) == r["ref_chi2_spread"][k]
+    assert float(r["ref_chi2_true"]) < 1e-18                              # the data are the model at the true parameters
+    f = _bw(r["pars"][0], thr)
+    born = np.array([f(float(e)) for e in r["ecm"]])
+    for tag, ee in (("", None), ("spread_", r["ecm_err"])):
+        m = O.vcs_fit_model(r["ecm"], thr, f, ee)
+        np.testing.assert_allclose(m, r["ref_save_%svcs_gauss_conv" % tag], rtol=1e-10)   # (TF1::Eval in the unblurred branch)
+        delta = m / born - 1.0
+        np.testing.assert_allclose(delta, r["ref_save_%srad_delta" % tag], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(r["vcs"] / (delta + 1.0), r["ref_save_%sbcs" % tag], rtol=1e-10)
+        np.testing.assert_allclose(r["vcs_err"] / (delta + 1.0), r["ref_save_%sbcs_err" % tag], rtol=1e-10)
+
+
 def test_full_size_tikhonov_run_against_long_double():
     """The N = 200 reference run (cubic spline + energy spread, 4 lambda, 16 toys each): its per-toy chi2 against the
     80-bit evaluation of the same formula on the same operator -- how much of the reference's own double-precision route
@@ -192,6 +223,16 @@ def test_refrun_fixtures_are_reference_output(name):
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
     import make_refrun_golden as M
     fresh, stored = M.small_case(name), load_golden("refrun_" + name)
+    assert set(fresh) == set(stored)
+    for k in stored:
+        np.testing.assert_array_equal(np.asarray(fresh[k]), stored[k], err_msg=k)
+
+
+@needs_ref
+def test_refrun_vcsfit_fixture_is_reference_output():
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_refrun_golden as M
+    fresh, stored = M.run_vcsfit(), load_golden("refrun_vcsfit_n24")
     assert set(fresh) == set(stored)
     for k in stored:
         np.testing.assert_array_equal(np.asarray(fresh[k]), stored[k], err_msg=k)
