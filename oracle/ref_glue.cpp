@@ -12,10 +12,12 @@
 // (efficiency(x, energyIndex), BaseISRSolver2) -- the two headers define the same exception type and
 // cannot share a translation unit.
 //
-// What cannot be compiled (ROOT / Eigen linear algebra inside) and is therefore restated here, each with
-// its reference line: the efficiency adaptors (src/BaseISRSolver.cpp:232-258, src/BaseISRSolver2.cpp:231-236,
-// ROOT bin arithmetic = orc_find_bin), the N x N fill loop of ISRSolverSLE::evalEqMatrix
-// (src/ISRSolverSLE.cpp:138-145; SLE2: src/ISRSolverSLE2.cpp:142-149) and _energySpreadMatrix (:177-193).
+// Restated here, each with its reference line, because this file serves the multi-threaded row evaluation that the
+// fixtures and the CPU baseline use (the reference's own versions of the same snippets run unmodified through
+// ref_solver_glue.cpp / ref_solver2_glue.cpp since round 2, and tests/test_refrun_pin.py checks that both give the same
+// matrices bit for bit): the efficiency adaptors (src/BaseISRSolver.cpp:232-258, src/BaseISRSolver2.cpp:231-236, ROOT bin
+// arithmetic = orc_find_bin), the N x N fill loop of ISRSolverSLE::evalEqMatrix (src/ISRSolverSLE.cpp:138-145; SLE2:
+// src/ISRSolverSLE2.cpp:142-149) and _energySpreadMatrix (:177-193).
 #include <cmath>
 #include <cstddef>
 #include <cstdio>

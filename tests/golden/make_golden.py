@@ -9,7 +9,8 @@ carry that library's outputs under *_ref keys:
     vcs_ref    the reference's convolutionKuraevFadin of the Breit-Wigner Born model
     w_ref, D_ref   Interpolator::evalIntegralBasis / basisDerivEval
 Everything else (solve, covariance, toys, Tikhonov, TSVD) is output of the restatement in oracle/
-(NumPy/LAPACK in place of Eigen; ROOT and Eigen's decompositions cannot be compiled here).  This script
+(NumPy/LAPACK in place of Eigen); since round 2 the reference's own solver classes run here as well, and their outputs on
+these fixtures' inputs live in refrun_*.npz (make_refrun_golden.py), which tests/test_refrun_pin.py compares with these numbers.  This script
 asserts that the restatement's faithful back-end reproduces the compiled reference BIT FOR BIT before
 writing anything.  Run in the container that has /root/reference:
     python tests/golden/make_golden.py   (about a minute on 8 cores).
