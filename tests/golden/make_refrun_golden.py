@@ -14,13 +14,15 @@ existing fixtures (tests/golden/c*.npz: same points, errors, toys, model) and st
              product) and then solve(); for c4 also ISRSolverTSVD (whose SVD cannot be separated from evalEqMatrix)
   vcsfit     ISRSolverVCSFitFunction (src/ISRSolverVCSFitter.cpp): the chi2 objective of the visible-cross-section fit at four
              parameter sets (N forward convolutions each, with and without energy spread) and saveResults
-  e2e        two full-size runs with nothing injected: N = 200 cubic spline, chi2TestModel + ratioTestModel on 32 toys
-             (BASELINE configs[1] geometry), and N = 200 cubic spline with energy spread, ISRSolverTikhonov at 4 lambda
+  e2e        full-size runs with nothing injected: chi2TestModel + ratioTestModel at N = 200 cubic spline on 32 toys
+             (the north-star geometry), N = 100 cubic spline on 64 toys (C2) and N = 500 linear on 16 toys (C5: a
+             triangular operator), ISRSolverSLE2 at N = 200 with 512-bin efficiency histograms (C3), and N = 200 cubic spline with energy spread, ISRSolverTikhonov at 4 lambda
              with chi2TestModel on 16 toys each (configs[3] geometry).
 
 tests/test_ref_pin.py checks that oracle/isr_oracle.py reproduces these numbers (the pin of its linear-algebra layer) and
 that a fresh run reproduces the files; tests/test_gpu_refrun.py compares the CUDA path with them through the C ABI.
-Run in the container that has /root/reference:  python tests/golden/make_refrun_golden.py   (about two minutes).
+Run in the container that has /root/reference:  python tests/golden/make_refrun_golden.py   (about ten minutes, most of
+it the N = 500 run: 125 000 adaptive integrations and an O(N^3) solve per toy on one core).
 """
 import os
 import sys
@@ -142,19 +144,20 @@ def run_v2(g):
     return dict(ref_G_native=S.matrix(), ref_bcs_native=b, ref_cov_native=cov, ref_cond_native=S.cond())
 
 
-def e2e_inputs(n, toys, spread):
+def e2e_inputs(n, toys, spread, cubic=True):
     ecm = np.linspace(O.E_MIN, O.E_MAX, n)
     vcs = O.bw_visible(ecm)
     vcs_err = 0.05 * vcs
-    out = dict(ecm=ecm, threshold=O.E_THR, settings=np.array([(0, 0, 0), (1, 1, n - 1)], dtype=np.int32), vcs=vcs, vcs_err=vcs_err,
+    settings = [(0, 0, 0), (1, 1, n - 1)] if cubic else [(0, 0, n - 1)]
+    out = dict(ecm=ecm, threshold=O.E_THR, settings=np.array(settings, dtype=np.int32), vcs=vcs, vcs_err=vcs_err,
                bcs0=O.bw_born(ecm), toys=O.draw_toys(vcs, vcs_err, toys))
     if spread:
         out["ecm_err"] = np.full(n, 0.002)
     return out
 
 
-def run_e2e_sle(n=200, toys=32):
-    g = e2e_inputs(n, toys, False)
+def run_e2e_sle(n=200, toys=32, cubic=True):
+    g = e2e_inputs(n, toys, False, cubic)
     S = R.RefSolver("sle", g["ecm"], g["vcs"], g["vcs_err"], float(g["threshold"]), settings=g["settings"])
     chi2, counts, lo, hi = S.chi2_test_model(g["toys"], g["vcs"], g["bcs0"])      # runs evalEqMatrix + solve() itself
     S.reset_vcs(g["vcs"])
@@ -165,6 +168,25 @@ def run_e2e_sle(n=200, toys=32):
              ref_chi2_hist=counts, ref_chi2_lo=lo, ref_chi2_hi=hi, ref_ratio_means=means, ref_ratio_mean_errors=errs,
              ref_ratio_counts=rc.astype(np.uint16), ref_ratio_stats=stats, ref_G_rows=S.matrix()[rows])
     return g
+
+
+def run_e2e_sle2(n=200, nbins=512):
+    """BASELINE configs C3 geometry: ISRSolverSLE2, linear interpolation, one 512-bin efficiency histogram per energy point.
+    The reference's adaptive quadrature meets the bin edges inside its integration ranges and its retry loop
+    (src/Integration.cpp:28-42) ends at epsrel up to 1e-3 there: G_err_rows carries the error estimates it returned."""
+    ecm = np.linspace(O.E_MIN, O.E_MAX, n)
+    eff = O.row_table_efficiency(ecm, nbins)
+    vcs = O.bw_visible(ecm, eff=eff)
+    vcs_err = 0.05 * vcs
+    S = R.RefSolver2(ecm, vcs, vcs_err, O.E_THR, eff=eff)
+    b, cov = S.solve()
+    rows = np.array([0, n // 2, n - 1])
+    I = O.Interp(ecm, O.E_THR)
+    Gf, Ef, Rf = I.eval_eq_matrix(eff=eff, with_errors=True)
+    assert np.array_equal(Gf, S.matrix()), "the faithful restatement differs from the compiled ISRSolverSLE2"
+    return dict(ecm=ecm, threshold=O.E_THR, settings=np.array([(0, 0, n - 1)], dtype=np.int32), eff_nbins=nbins, vcs=vcs, vcs_err=vcs_err,
+                ref_bcs=b, ref_cov_diag=np.diag(cov).copy(), ref_cond=S.cond(), ref_G_rows_at=rows, ref_G_rows=S.matrix()[rows],
+                ref_G_err_rows=Ef[rows], ref_G_relerr_max=Rf.max())
 
 
 def run_e2e_tikhonov(n=200, toys=16, lam=(1e-6, 1e-4, 1e-2, 1.0)):
@@ -240,5 +262,8 @@ if __name__ == "__main__":
         save("refrun_" + name, small_case(name))
     save("refrun_vcsfit_n24", run_vcsfit())
     save("refrun_e2e_sle_n200_cspline", run_e2e_sle())
+    save("refrun_e2e_sle_n100_cspline", run_e2e_sle(100, 64))                  # BASELINE configs C2 geometry
+    save("refrun_e2e_sle_n500_linear", run_e2e_sle(500, 16, cubic=False))      # C5 geometry: triangular operator, ratio + chi2
+    save("refrun_e2e_sle2_n200_eps512", run_e2e_sle2())                        # C3 geometry
     save("refrun_e2e_tikhonov_n200_spread", run_e2e_tikhonov())
     print("done in %.0f s" % (time.time() - t0))

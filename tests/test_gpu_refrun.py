@@ -210,11 +210,14 @@ def test_vcs_fit_objective_through_the_convolution_service():
     assert float((((vis - r["vcs"]) / r["vcs_err"]) ** 2).sum()) < 1e-12
 
 
-def test_full_size_sle_run_n200():
-    """BASELINE configs[1] geometry end to end: the reference assembled N = 200 (cubic spline) with its 40 000 adaptive
-    integrations, solved, and ran chi2TestModel + ratioTestModel on 32 toys; the GPU does the same from the same inputs."""
+@pytest.mark.parametrize("name", ["refrun_e2e_sle_n200_cspline", "refrun_e2e_sle_n100_cspline", "refrun_e2e_sle_n500_linear"])
+def test_full_size_sle_runs(name):
+    """BASELINE geometries end to end, nothing injected on either side: the reference assembled the matrix with its N^2
+    adaptive integrations, solved, and ran chi2TestModel + ratioTestModel (a full O(N^3) solve per toy); the GPU does the
+    same from the same inputs.  N = 200 cubic spline (the north-star geometry), N = 100 cubic spline (C2), N = 500 linear
+    (C5: a lower-triangular operator -- the blocked triangular inverse and the triangular toy schedule)."""
     import isrsolver_b200 as isr
-    r = load_golden("refrun_e2e_sle_n200_cspline")
+    r = load_golden(name)
     n, T = len(r["ecm"]), len(r["toys"])
     s = isr.ISRSolverSLE(n, r["ecm"], r["vcs"], None, r["vcs_err"], float(r["threshold"]))
     s.set_interp_settings([tuple(x) for x in r["settings"]])
@@ -223,6 +226,8 @@ def test_full_size_sle_run_n200():
     G = s.intop_matrix()
     scale = np.abs(r["ref_G_rows"]).max(axis=1, keepdims=True)
     assert np.all(np.abs(G[rows] - r["ref_G_rows"]) <= 1e-9 * scale + 2e-12)
+    if "linear" in name:
+        assert np.all(np.triu(G, 1) == 0) and np.all(np.triu(r["ref_G_rows"][0:1], 1) == 0)
     s.solve()
     close(s.bcs(), r["ref_bcs"])
     cov = s.bcs_cov_matrix()
@@ -237,6 +242,39 @@ def test_full_size_sle_run_n200():
     cnt, sx, sx2 = o["ratio_stats"].T
     # a ratio (b - b0) / b0 inherits the 1e-9 relative difference of the two assemblies as an ABSOLUTE 1e-9 (b / b0 ~ 1)
     np.testing.assert_allclose(sx / cnt, r["ref_ratio_means"], rtol=RT, atol=RT)
+
+
+def test_full_size_sle2_run_n200_eps512(oracle):
+    """BASELINE configs C3 end to end: ISRSolverSLE2 at N = 200 with one 512-bin efficiency histogram per energy point, run
+    by the reference itself (its TH1D adaptor, its adaptive quadrature across the bin edges).  Here the REFERENCE is the
+    less accurate side -- its retry loop ends at epsrel up to 1e-3 on these piecewise integrands (the fixture records the
+    error estimates it returned; the converged oracle differs from it by up to 9e-6) -- so the matrix gate is the
+    reference's own error estimate, and the solution is gated at 1e-8 against the converged oracle, at the matrix
+    difference against the reference."""
+    import isrsolver_b200 as isr
+    r = load_golden("refrun_e2e_sle2_n200_eps512")
+    n, nb = len(r["ecm"]), int(r["eff_nbins"])
+    effo = oracle.row_table_efficiency(r["ecm"], nb)
+    s = isr.ISRSolverSLE2(n, r["ecm"], r["vcs"], None, r["vcs_err"], float(r["threshold"]), eff_hists=effo.values, xlo=0.0, xhi=1.0)
+    s.eval_equation_matrix()
+    G = s.intop_matrix()
+    rows = list(r["ref_G_rows_at"])
+    scale = np.abs(r["ref_G_rows"]).max(axis=1, keepdims=True)
+    assert np.all(np.abs(G[rows] - r["ref_G_rows"]) <= 3 * r["ref_G_err_rows"] + 1e-9 * scale + 2e-12)
+    assert np.all(np.triu(G, 1) == 0)
+    Gc, Ec = oracle.Interp(r["ecm"], float(r["threshold"])).eval_rows(rows, eff=effo, mode="converged")
+    assert np.all(np.abs(G[rows] - Gc) <= 1e-9 * np.abs(Gc).max(axis=1, keepdims=True) + Ec + 2e-12)
+    s.solve()
+    # against the reference: its matrix is up to 9e-6 of the row scale away from the converged integrals (measured when the
+    # fixture was made: max |G_faithful - G_converged| = 8.8e-6), and the solution inherits that
+    close(s.bcs(), r["ref_bcs"], 2e-5)
+    close(np.diag(s.bcs_cov_matrix()), r["ref_cov_diag"], 2e-5)
+    assert s.condnum_eval() == pytest.approx(float(r["ref_cond"]), rel=2e-5)
+    # against the converged oracle (the exact value of the integrals the reference approximates): the 1e-8 gate
+    Gfull = oracle.Interp(r["ecm"], float(r["threshold"])).eval_eq_matrix(eff=effo, mode="converged")
+    b, cov = oracle.sle_solve(Gfull, r["vcs"], r["vcs_err"])
+    close(s.bcs(), b)
+    close(np.diag(s.bcs_cov_matrix()), np.diag(cov))
 
 
 def test_full_size_tikhonov_run_n200():

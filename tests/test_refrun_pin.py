@@ -192,6 +192,30 @@ def test_vcs_fit_function():
         np.testing.assert_allclose(r["vcs_err"] / (delta + 1.0), r["ref_save_%sbcs_err" % tag], rtol=1e-10)
 
 
+@pytest.mark.parametrize("name", ["refrun_e2e_sle_n100_cspline", "refrun_e2e_sle_n200_cspline", "refrun_e2e_sle_n500_linear"])
+def test_full_size_sle_runs_end_to_end(name):
+    """BASELINE geometries (C2: N = 100 cubic; north star: N = 200 cubic; C5: N = 500 linear) run by the reference itself
+    with nothing injected -- its own N^2 adaptive integrations, solve(), chi2TestModel, ratioTestModel.  The oracle from the
+    same inputs: matrix rows bit for bit (faithful back-end), everything downstream to 1e-12, histograms bit for bit."""
+    r = load_golden(name)
+    I = O.Interp(r["ecm"], float(r["threshold"]), [tuple(s) for s in r["settings"]])
+    G = I.eval_eq_matrix(mode="faithful")
+    rows = list(r["ref_cov_rows_at"])
+    np.testing.assert_array_equal(G[rows], r["ref_G_rows"])
+    b, cov = O.sle_solve(G, r["vcs"], r["vcs_err"])
+    assert rel(b, r["ref_bcs"]) < RT and rel(np.diag(cov), r["ref_cov_diag"]) < RT and rel(cov[rows], r["ref_cov_rows"]) < RT
+    assert abs(O.cond_number(G) / float(r["ref_cond"]) - 1.0) < RT
+    chi2, B = O.chi2_test_fair(G, r["toys"], r["bcs0"], r["vcs_err"])
+    assert rel(chi2, r["ref_chi2"]) < RT
+    counts, _, lo, hi = O.chi2_histogram(r["ref_chi2"])
+    assert (lo, hi) == (float(r["ref_chi2_lo"]), float(r["ref_chi2_hi"]))
+    np.testing.assert_array_equal(counts, r["ref_chi2_hist"])
+    means, errs, rc, stats = O.ratio_test(B, r["bcs0"])
+    np.testing.assert_array_equal(rc.astype(np.uint16), r["ref_ratio_counts"])
+    np.testing.assert_allclose(means, r["ref_ratio_means"], rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(errs, r["ref_ratio_mean_errors"], rtol=1e-9, atol=1e-14)
+
+
 def test_full_size_tikhonov_run_against_long_double():
     """The N = 200 reference run (cubic spline + energy spread, 4 lambda, 16 toys each): its per-toy chi2 against the
     80-bit evaluation of the same formula on the same operator -- how much of the reference's own double-precision route
