@@ -106,7 +106,9 @@ static std::pair<std::vector<double>, std::vector<double>> load_model(const std:
 
 template <typename S, typename C>
 static void bind_common(C& c) {
-  c.def("solve", [](S& s) { s.solve(); return 0; }, "Find solution")
+  // the long GPU calls run with the GIL released (the reference never releases it; other Python threads -- one
+  // per GPU, say -- can then run); a callable efficiency re-acquires it for the duration of each call-back
+  c.def("solve", [](S& s) { py::gil_scoped_release nogil; s.solve(); return 0; }, "Find solution")
       .def("bcs", [](S& s) { return view1(s.bcs(), s); }, "Get numerical solution (Born cross section)")
       .def("ecm", [](S& s) { return view1(s.ecm(), s); }, "Get center-of-mass energy")
       .def("ecm_err", [](S& s) { return view1(s.ecmErr(), s); }, "Get center-of-mass energy errors")
@@ -151,12 +153,16 @@ static void bind_common(C& c) {
 
 template <typename S, typename C>
 static void bind_tests(C& c) {
-  c.def("eval_equation_matrix", [](S& s) { s.evalEqMatrix(); return 0; }, "Eval equation matrix")
+  c.def("eval_equation_matrix", [](S& s) { py::gil_scoped_release nogil; s.evalEqMatrix(); return 0; }, "Eval equation matrix")
       .def("chi2_test_model",
            [](S& s, int n, double initial_ampl, const std::string& model_path, const std::string& model_visible_cs_name,
               const std::string& model_born_cs_name, const py::object& output_path) {
              auto m = load_model(model_path, model_visible_cs_name, model_born_cs_name, s.getN());
-             Chi2TestResult r = chi2TestModel(&s, {n, initial_ampl, ""}, m.first, m.second);
+             Chi2TestResult r;
+             {
+               py::gil_scoped_release nogil;
+               r = chi2TestModel(&s, {n, initial_ampl, ""}, m.first, m.second);
+             }
              py::dict out;
              out["chi2"] = py::array_t<double>(r.chi2.size(), r.chi2.data());
              out["hist"] = py::array_t<float>(r.hist.size(), r.hist.data());
@@ -173,8 +179,12 @@ static void bind_tests(C& c) {
            [](S& s, int n, const std::string& model_path, const std::string& model_visible_cs_name,
               const std::string& model_born_cs_name, const py::object& output_path) {
              auto m = load_model(model_path, model_visible_cs_name, model_born_cs_name, s.getN());
-             s.solve();
-             RatioTestResult r = ratioTestModel(&s, n, randomDrawVisCS(m.first, s.vcsErr(), n), m.second);
+             RatioTestResult r;
+             {
+               py::gil_scoped_release nogil;
+               s.solve();
+               r = ratioTestModel(&s, n, randomDrawVisCS(m.first, s.vcsErr(), n), m.second);
+             }
              py::dict out;
              out["means"] = py::array_t<double>(r.means.size(), r.means.data());
              out["mean_errors"] = py::array_t<double>(r.meanErrors.size(), r.meanErrors.data());
@@ -290,7 +300,7 @@ PYBIND11_MODULE(PyISR, m) {
   py::class_<IterISRInterpSolver> iter(m, "IterISRInterpSolver", kCtorDoc);   // include/PyIterISRInterpSolver.hpp
   iter.def(py::init(&make_solver<IterISRInterpSolver>), CTOR_ARGS);
   bind_common<IterISRInterpSolver>(iter);
-  iter.def("eval_equation_matrix", [](IterISRInterpSolver& s) { s.evalEqMatrix(); return 0; }, "Eval equation matrix")
+  iter.def("eval_equation_matrix", [](IterISRInterpSolver& s) { py::gil_scoped_release nogil; s.evalEqMatrix(); return 0; }, "Eval equation matrix")
       .def_property("n_iter", [](IterISRInterpSolver& s) { return s.getNumOfIters(); },
                     [](IterISRInterpSolver& s, std::size_t n) { s.setNumOfIters(n); }, "Number of iterations")
       .def("radcorr", [](IterISRInterpSolver& s) { return view1(s.getRadCorr(), s); }, "Radiative correction 1 + delta");

@@ -162,3 +162,32 @@ def test_compiled_pyisr_accepts_a_callable_efficiency():
     t.set_interp_settings(st)
     t.eval_equation_matrix()
     np.testing.assert_allclose(s2.intop_matrix(), t.intop_matrix(), rtol=1e-12, atol=1e-15)
+
+
+@pytest.mark.gpu
+def test_compiled_pyisr_releases_the_gil_during_long_calls(tmp_path):
+    """long GPU calls of the compiled module run with the GIL released -- another Python thread makes progress
+    while a toy campaign of 4 million toys is under way (the reference's PyISR holds the GIL throughout)."""
+    import threading
+    from isrsolver_b200 import PyISR
+    g = load_golden("c2_sle_n40_cspline")
+    n = len(g["ecm"])
+    s = PyISR.ISRSolverSLE(n=n, energy=g["ecm"], vcs=g["vcs"], energy_err=None, vcs_err=g["vcs_err"], threshold=float(g["threshold"]))
+    s.solve()
+    model = tmp_path / "model.npz"
+    np.savez(model, vcs=np.stack([g["ecm"], g["vcs"], 0 * g["ecm"], g["vcs_err"]]), bcs=g["bcs0"])
+    done = threading.Event()
+    out = {}
+
+    def work():
+        out["r"] = s.chi2_test_model(n=1 << 22, initial_ampl=1e4, model_path=str(model), model_visible_cs_name="vcs", model_born_cs_name="bcs")
+        done.set()
+    s.chi2_test_model(n=1024, initial_ampl=1e4, model_path=str(model), model_visible_cs_name="vcs", model_born_cs_name="bcs")   # warm-up
+    th = threading.Thread(target=work)
+    ticks = 0
+    th.start()
+    while not done.is_set():
+        ticks += 1
+    th.join()
+    assert out["r"]["hist"].sum() == 1 << 22
+    assert ticks > 1000, ticks
