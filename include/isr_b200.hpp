@@ -32,6 +32,9 @@ struct EfficiencyDimensionException : std::exception {  // include/BaseISRSolver
 struct DifferentModelCrossSectionSizes : std::exception {  // include/Chi2Test.hpp:47-52
   const char* what() const noexcept override { return "[!] Model visible and Born cross sections have different sizes.\n"; }
 };
+struct InterpSettingsSizeException : std::exception {  // include/ISRSolverStructs.hpp:170-174 (declared there, thrown nowhere)
+  const char* what() const noexcept override { return "[!] Wrong size of interpolation settings vector.\n"; }
+};
 struct IsrGpuError : std::runtime_error { using std::runtime_error::runtime_error; };
 
 inline void check(int rc) {
