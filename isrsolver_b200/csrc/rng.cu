@@ -94,33 +94,36 @@ __global__ void __launch_bounds__(256) draw_toys_fast_kernel(int64_t T, int n, i
   // Thread q of a toy owns the column pairs q and q + nquad (columns 2q, 2q+1 and 2(q+nquad), 2(q+nquad)+1), so that each
   // of its two 16-byte stores is contiguous across the lanes of the warp (one pair per lane: 512 B per store instruction;
   // adjacent pairs per thread made every store instruction touch twice the L1 wavefronts: 82 % L1 throughput at 33 % issue).
-  const unsigned lt = (threadIdx.x * magic) >> 16, q = threadIdx.x - lt * nquad;
+  // N > 1024 (nquad > 256): tpb = 1 and the thread walks the quads tid, tid + 256, ...
+  const unsigned lt = (threadIdx.x * magic) >> 16, q0 = threadIdx.x - lt * nquad;
   if (lt >= tpb) return;
-  const int col[4] = {2 * (int)q, 2 * (int)q + 1, 2 * (int)(q + nquad), 2 * (int)(q + nquad) + 1};
-  double e[4], c[4];
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const bool in = col[a] < n;
-    e[a] = in ? err[col[a]] : 0.0;
-    c[a] = in ? vcs[col[a]] : 0.0;
-  }
   const bool even = (n & 1) == 0;                          // even N: every pair is 16-byte aligned
   const int64_t tb = (int64_t)blockIdx.x * kFastIters * tpb + lt;
-#pragma unroll 1
-  for (int it = 0; it < kFastIters; ++it) {
-    const int64_t t = tb + (int64_t)it * tpb;
-    if (t >= T) break;
-    double z[4];
-    fast_normals((uint64_t)(first_toy + t), q, seed, z);
-    double* row = V + t * n;
+  for (unsigned q = q0; q < nquad; q += 256) {
+    const int col[4] = {2 * (int)q, 2 * (int)q + 1, 2 * (int)(q + nquad), 2 * (int)(q + nquad) + 1};
+    double e[4], c[4];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const double v0 = fma(e[2 * h], z[2 * h], c[2 * h]), v1 = fma(e[2 * h + 1], z[2 * h + 1], c[2 * h + 1]);
-      if (even && col[2 * h + 1] < n) {
-        *reinterpret_cast<double2*>(row + col[2 * h]) = make_double2(v0, v1);
-      } else {
-        if (col[2 * h] < n) row[col[2 * h]] = v0;
-        if (col[2 * h + 1] < n) row[col[2 * h + 1]] = v1;
+    for (int a = 0; a < 4; ++a) {
+      const bool in = col[a] < n;
+      e[a] = in ? err[col[a]] : 0.0;
+      c[a] = in ? vcs[col[a]] : 0.0;
+    }
+#pragma unroll 1
+    for (int it = 0; it < kFastIters; ++it) {
+      const int64_t t = tb + (int64_t)it * tpb;
+      if (t >= T) break;
+      double z[4];
+      fast_normals((uint64_t)(first_toy + t), q, seed, z);
+      double* row = V + t * n;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const double v0 = fma(e[2 * h], z[2 * h], c[2 * h]), v1 = fma(e[2 * h + 1], z[2 * h + 1], c[2 * h + 1]);
+        if (even && col[2 * h + 1] < n) {
+          *reinterpret_cast<double2*>(row + col[2 * h]) = make_double2(v0, v1);
+        } else {
+          if (col[2 * h] < n) row[col[2 * h]] = v0;
+          if (col[2 * h + 1] < n) row[col[2 * h + 1]] = v1;
+        }
       }
     }
   }
@@ -138,8 +141,7 @@ int draw_toys_device(isr_ctx* c, int64_t T, int n, int64_t first_toy, uint64_t s
                      const double* err_dev, double* V_dev, cudaStream_t st) {
   if (T <= 0) return ISR_OK;
   if (!rng_fp64()) {
-    if (n > 1024) { set_error("device toy generator: N = %d exceeds 1024", n); return ISR_EINVAL; }
-    const unsigned nquad = (unsigned)(n + 3) >> 2, tpb = 256u / nquad, magic = (65536u + nquad - 1) / nquad;
+    const unsigned nquad = (unsigned)(n + 3) >> 2, tpb = nquad < 256u ? 256u / nquad : 1u, magic = (65536u + nquad - 1) / nquad;
     draw_toys_fast_kernel<<<(unsigned)((T + (int64_t)tpb * kFastIters - 1) / ((int64_t)tpb * kFastIters)), 256, 0, st ? st : c->stream>>>(T, n, first_toy, seed, vcs_dev, err_dev, V_dev, nquad, tpb, magic); ISR_COUNT_LAUNCH();
     ISR_CUDA(cudaGetLastError());
     return ISR_OK;

@@ -348,6 +348,25 @@ def test_device_toys_are_standard_normal():
     np.testing.assert_allclose(v, np.arange(n)[None, :] + 0.5 * z[:16], rtol=0, atol=1e-15 * n)
 
 
+def test_device_toys_over_many_sizes():
+    """The generator's thread mapping (column quads, several toys per block, quads walked in strides for N > 1024) at sizes
+    around every boundary: finite, standard normal, independent columns, and identical however the campaign is chunked."""
+    import isrsolver_b200 as isr
+    for n in (1, 2, 3, 5, 7, 8, 63, 64, 65, 127, 128, 129, 255, 256, 257, 258, 500, 513, 1000, 1023, 1024, 1025, 1100, 2050):
+        vcs, err = np.linspace(1, 2, n), np.linspace(0.1, 0.3, n)
+        T = 4096 if n < 300 else 512
+        full = isr.draw_toys_device(vcs, err, T, seed=99)
+        parts = np.concatenate([isr.draw_toys_device(vcs, err, c, seed=99, first_toy=f) for f, c in ((0, 17), (17, 1), (18, T - 18))])
+        np.testing.assert_array_equal(full, parts, err_msg=str(n))
+        z = (full - vcs) / err
+        assert np.all(np.isfinite(full)) and np.abs(z).max() < 6.8, n
+        assert abs(z.mean()) < 5 / np.sqrt(z.size) and abs(z.var() - 1) < 6 * np.sqrt(2 / z.size), (n, z.mean(), z.var())
+        assert len(np.unique(z[:, 0])) > 0.99 * T, n
+        if n > 1:
+            assert abs(np.corrcoef(z[:, 0], z[:, -1])[0, 1]) < 6 / np.sqrt(T), n
+            assert abs(np.corrcoef(z[:, 0], z[:, n // 2])[0, 1]) < 6 / np.sqrt(T) or n // 2 == 0, n
+
+
 @pytest.mark.parametrize("n", [36, 37])
 def test_device_toys_depend_only_on_seed_and_index(n):
     """Sharding by first_toy reproduces the unsharded stream bit for bit (odd N included)."""
