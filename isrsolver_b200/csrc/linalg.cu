@@ -149,7 +149,11 @@ __global__ void __launch_bounds__(256) inverse_residual_kernel(int n, const doub
 // zeros).  No pivoting: the caller certifies the result (lu_inverse) and falls back to the pivoted LU otherwise.
 // --------------------------------------------------------------------------------------------------
 constexpr int kGjMaxN = 256, kGjColsPerLane = kGjMaxN / 32;   // 8 columns (4 pairs) per lane
-constexpr int kGjDefaultCtas = 8, kGjDefaultRows = 4;   // measured (tools/exp_factor.py, N = 200): RW 4 / 8 = 144.7 / 147.9 us with 8 CTAs, 159 / 159 us with 4
+constexpr int kGjDefaultRows = 4;   // measured (tools/exp_factor.py, N = 200): RW 4 / 8 = 144.7 / 147.9 us with 8 CTAs, 159 / 159 us with 4
+// Cluster size by N (isr_factor, synchronous, tools/exp_factor.py; 8 / 4 CTAs): N = 30 58.6 / 50.8 us, 50 66.7 / 57.5, 100 84.9 / 74.4,
+// 128 95.5 / 84.2, 136 98.7 / 98.8, 168 111.0 / 115.8, 200 126.0 / 139.4, 240 141.1 / 165.4 -- up to 128 points (four columns per
+// lane) the seven hand-overs between CTAs cost more than the lighter FP64 load per SM sub-partition saves.
+__host__ __device__ constexpr int gj_default_ctas(int n) { return n <= 128 ? 4 : 8; }
 constexpr int kGjMaxRows = 240;   // 15 arithmetic warps + the forwarder = 512 threads per CTA: 128 registers each
 namespace gj {
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -454,7 +458,7 @@ static int launch_gj_t(isr_ctx* c, int n, const double* A, double* X, double* ce
 static int launch_gj(isr_ctx* c, int n, const double* A, double* X, double* cert, double* Xrow, int ld) {
   static const int forced = [] { const char* e = std::getenv("ISR_GJ_CTAS"); return e ? std::atoi(e) : 0; }();
   static const int forced_rw = [] { const char* e = std::getenv("ISR_GJ_RW"); return e ? std::atoi(e) : 0; }();
-  const int ctas = forced ? forced : kGjDefaultCtas, rw = forced_rw ? forced_rw : kGjDefaultRows;
+  const int ctas = forced ? forced : gj_default_ctas(n), rw = forced_rw ? forced_rw : kGjDefaultRows;
   if (rw == 8) {
     if (ctas == 16) return launch_gj_t<16, 8>(c, n, A, X, cert, Xrow, ld);
     if (ctas == 4) return launch_gj_t<4, 8>(c, n, A, X, cert, Xrow, ld);
