@@ -11,7 +11,7 @@ for n in [int(a) for a in os.environ.get("N", "200").split(",")]:
     G = np.empty((n,n)); L.check(lib.isr_assemble(p, None, L.dptr(G))); G = G.T.copy()
     bcs0 = np.ones(n); vcs = G @ bcs0; err = 0.05*vcs
     L.check(lib.isr_factor(p, L.dptr(err)))
-    T = 1 << 20
+    T = int(os.environ.get("T", 1 << 20))
     Vd = torch.from_numpy(vcs)[None,:].cuda() + torch.from_numpy(err)[None,:].cuda()*torch.randn(T, n, dtype=torch.float64, device='cuda')
     chi2d = torch.empty(T, dtype=torch.float64, device='cuda')
     sbd = torch.zeros(n, dtype=torch.float64, device='cuda')
