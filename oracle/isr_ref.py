@@ -97,6 +97,7 @@ def lib():
         L.refs_eval_eq_matrix.argtypes = [vp]
         L.refs_solve.argtypes = [vp]
         L.refs_reset_vcs.argtypes = [vp, _dp]
+        L.refs_reset_ecm_err.argtypes = [vp, _dp, C.c_int]
         for nm in ("refs_get_points", "refs_get_bcs", "refs_get_cov", "refs_get_matrix", "refs_tik_functionals"):
             getattr(L, nm).argtypes = [vp, _dp]
         L.refs_cond.restype = C.c_double
@@ -302,6 +303,16 @@ class RefSolver:
     def solve(self):
         self._check(self._L.refs_solve(self._h))
         return self.bcs(), self.cov()
+
+    def cond_spread_scan(self, sigmas):
+        """The loop of src/isrsolver-condnum-test.cpp:84-128: per spread setting resetECMErrors(sigma * ones), evalEqMatrix,
+        JacobiSVD -> sigma_max / sigma_min (sigma = 0: the spread switched off)."""
+        out = []
+        for sg in sigmas:
+            self._L.refs_reset_ecm_err(self._h, _p(_c(np.full(self.n, float(sg)))), int(sg > 0))
+            self._check(self._L.refs_eval_eq_matrix(self._h))
+            out.append(self.cond())
+        return np.array(out)
 
     def reset_vcs(self, v):
         self._L.refs_reset_vcs(self._h, _p(_c(v)))

@@ -200,6 +200,13 @@ int refs_solve(void* vh) {
   auto* h = static_cast<Handle*>(vh);
   return guarded([&]() { h->s->solve(); });
 }
+// resetECMErrors + enable / disableEnergySpread (src/BaseISRSolver.cpp:428-459): what src/isrsolver-condnum-test.cpp:120-128
+// does per spread setting before it re-assembles the matrix and takes its condition number
+void refs_reset_ecm_err(void* vh, const double* e, int enable_spread) {
+  auto* h = static_cast<Handle*>(vh);
+  h->s->resetECMErrors(vec(e, (int)h->s->getN()));
+  if (enable_spread) h->s->enableEnergySpread(); else h->s->disableEnergySpread();
+}
 void refs_reset_vcs(void* vh, const double* v) {
   auto* h = static_cast<Handle*>(vh);
   h->s->resetVisibleCS(vec(v, (int)h->s->getN()));

@@ -123,6 +123,10 @@ def run_tikhonov(g):
                ref_tik_cov=np.array(covs), ref_tik_cov_at=np.array(TIK_COV_AT), ref_tik_chi2=np.array(chi2s), ref_tik_chi2_at=np.array(TIK_CHI2_AT),
                ref_tik_noreg_at=np.array(TIK_NOREG_AT), ref_tik_noreg_bcs=np.array([r[0] for r in noreg]),
                ref_tik_noreg_xycd=np.array([r[1:] for r in noreg]), ref_lambda_objective=np.array(obj), ref_lambda_objective_at=np.array([2, 7]))
+    # condition number versus beam-energy spread (src/isrsolver-condnum-test.cpp:84-128), the reference's own re-assembly per setting
+    sig = np.array([0.0, 0.0005, 0.001, 0.002, 0.004, 0.008, 0.016])
+    Sc = R.RefSolver("sle", g["ecm"], g["vcs"], g["vcs_err"], thr, settings=st)
+    out.update(ref_condscan_sigma=sig, ref_condscan_cond=Sc.cond_spread_scan(sig))
     # TSVD: native only
     k = int(g["tsvd_k"])
     n = len(g["ecm"])

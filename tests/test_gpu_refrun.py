@@ -157,6 +157,15 @@ def test_tikhonov_scan_solve_and_toys():
     np.testing.assert_allclose(dc, ref[:, 3], rtol=RT)
 
 
+def test_condition_number_versus_spread_scan():
+    """isr_cond_spread_scan (one assembly, batched spread products and Jacobi singular values) against the reference's own
+    loop, which re-assembles the matrix and runs a JacobiSVD per setting (src/isrsolver-condnum-test.cpp:84-128)."""
+    g, r = load_golden("c4_tikhonov_n32_spread"), load_golden("refrun_c4_tikhonov_n32_spread")
+    s = make_solver(g, spread=False)
+    cond = s.condnum_spread_scan(r["ref_condscan_sigma"])
+    np.testing.assert_allclose(cond, r["ref_condscan_cond"], rtol=RT)
+
+
 def test_tsvd():
     import isrsolver_b200 as isr
     g, r = load_golden("c4_tikhonov_n32_spread"), load_golden("refrun_c4_tikhonov_n32_spread")

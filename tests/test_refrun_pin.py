@@ -151,6 +151,19 @@ def test_tikhonov_solve_and_lcurve():
         assert rel(chi2, r["ref_tik_chi2"][q]) < 1e-10
 
 
+def test_condition_number_versus_spread():
+    """The loop of src/isrsolver-condnum-test.cpp:84-128 run on the reference's own classes (resetECMErrors, evalEqMatrix,
+    JacobiSVD per setting) against the restated spread product and LAPACK singular values."""
+    g, r = load_golden("c4_tikhonov_n32_spread"), load_golden("refrun_c4_tikhonov_n32_spread")
+    I = O.Interp(g["ecm"], float(g["threshold"]), [tuple(s) for s in g["settings"]])
+    G = I.eval_eq_matrix(mode="faithful")
+    n = len(g["ecm"])
+    for sg, ref in zip(r["ref_condscan_sigma"], r["ref_condscan_cond"]):
+        c = O.cond_number(G if sg == 0 else I.energy_spread_matrix(np.full(n, sg)) @ G)
+        assert abs(c / ref - 1.0) < RT
+    assert np.all(np.diff(r["ref_condscan_cond"]) > 0)
+
+
 def test_tsvd():
     """ISRSolverTSVD::solve: JacobiSVD, truncation to k, keep-one, full rank; minimum-norm COD solve of the rank-k matrix."""
     g, r = load_golden("c4_tikhonov_n32_spread"), load_golden("refrun_c4_tikhonov_n32_spread")
