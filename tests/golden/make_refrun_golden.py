@@ -61,6 +61,9 @@ def run_v1(g):
     out.update(ref_bcs=b, ref_cov=cov, ref_cond=S.cond())
     sv = S.save()
     out.update(ref_bcs_err=sv["bcs_err"], ref_inv_cov=sv["inv_cov"])
+    # interpEval (src/ISRSolverSLE.cpp:195-198 -> Interpolator::eval): below threshold, inside every range, between nodes, beyond E_max
+    ei = np.concatenate([[thr - 0.01, thr, thr + 1e-3], np.linspace(thr, g["ecm"][-1], 41)[1:-1] + 1e-4, g["ecm"][[0, 5, -1]], [g["ecm"][-1] + 0.3]])
+    out.update(ref_interp_E=ei, ref_interp_val=np.array([S.interp_eval(b, float(e)) for e in ei]))
     assert np.array_equal(sv["bcs"], b) and np.array_equal(sv["cov"], cov) and np.array_equal(sv["G"], G)
     chi2, counts, lo, hi = S.chi2_test_model(g["toys"], g["vcs"], g["bcs0"])
     out.update(ref_chi2=chi2, ref_chi2_hist=counts, ref_chi2_lo=lo, ref_chi2_hi=hi)

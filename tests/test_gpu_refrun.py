@@ -40,6 +40,10 @@ def test_sle_solution_covariance_condition_number(name):
     close(s.bcs_err(), r["ref_bcs_err"])
     close(s.bcs_inv_cov_matrix(), r["ref_inv_cov"])
     assert s.condnum_eval() == pytest.approx(float(r["ref_cond"]), rel=RT)
+    # interpEval of the reference at 47 energies: 0 at and below threshold, every range type, the clamp beyond E_max
+    got = s.interp_eval(r["ref_interp_E"])
+    np.testing.assert_allclose(got, r["ref_interp_val"], rtol=RT, atol=RT * np.abs(r["ref_bcs"]).max())
+    assert got[0] == 0.0 and got[1] == 0.0 and got[-1] == s.bcs()[-1]
 
 
 @pytest.mark.parametrize("name", V1)

@@ -41,6 +41,8 @@ def test_sle_solve_covariance_condition_number(name):
     assert rel(np.sqrt(np.diag(cov)), r["ref_bcs_err"]) < RT
     assert rel(np.linalg.inv(cov), r["ref_inv_cov"]) < 1e-11          # save() inverts the covariance once more
     assert abs(O.cond_number(G) / float(r["ref_cond"]) - 1.0) < RT
+    I = O.Interp(g["ecm"], float(g["threshold"]), [tuple(x) for x in g["settings"]])
+    np.testing.assert_array_equal([I.eval(r["ref_bcs"], float(e)) for e in r["ref_interp_E"]], r["ref_interp_val"])   # interpEval
     # the fixtures the GPU tests use carry the restatement's numbers: the same
     assert rel(g["bcs"], r["ref_bcs"]) < RT and rel(g["cov"], r["ref_cov"]) < RT and abs(g["cond"] / r["ref_cond"] - 1) < RT
 
