@@ -170,6 +170,48 @@ def test_blocked_triangular_inverse(n):
     lib.isr_problem_destroy(p)
 
 
+@pytest.mark.parametrize("n", [241, 242, 255, 256, 257, 300, 333, 400, 479, 480, 481, 500, 600, 721, 960, 961, 1000])
+def test_dense_inverse_beyond_240(n):
+    """240 < N <= 960, dense matrix: block elimination on the cluster Gauss-Jordan kernel (two inverses of the parts + six
+    products per level, linalg.cu::dense_inverse; two levels above 480); beyond 960 cuSOLVER's unpivoted LU.  Both behind
+    the certificate."""
+    L, lib = _lib()
+    rng = np.random.default_rng(1000 + n)
+    G = rng.uniform(-0.2, 0.2, (n, n)) / np.sqrt(n) * 4 + np.diag(rng.uniform(0.8, 1.2, n))     # cond ~ 10
+    ecm = np.linspace(1.2, 2.0, n)
+    p = _problem(L, lib, _ctx(), ecm, 0.827, [[0, 0, 0], [1, 1, n - 1]], G=G)
+    err = rng.uniform(0.5, 1.5, n)
+    L.check(lib.isr_factor(p, L.dptr(err)))
+    X = np.zeros((n, n))
+    L.check(lib.isr_get_inverse(p, L.dptr(X)))
+    ref = np.linalg.inv(G)
+    assert np.abs(X.T - ref).max() <= 1e-10 * np.abs(ref).max()
+    vcs = G @ np.linspace(1.0, 2.0, n)
+    b, cov = np.zeros(n), np.zeros((n, n))
+    L.check(lib.isr_solve(p, L.dptr(vcs), L.dptr(b), L.dptr(cov)))
+    np.testing.assert_allclose(b, np.linspace(1.0, 2.0, n), rtol=1e-10)
+    lib.isr_problem_destroy(p)
+
+
+def test_dense_inverse_beyond_240_falls_back_to_pivoting():
+    """A matrix whose leading half is singular: the unpivoted block elimination cannot invert it, the certificate says so and
+    the partially pivoted LU takes over."""
+    L, lib = _lib()
+    n = 300
+    rng = np.random.default_rng(7)
+    G = rng.uniform(-1, 1, (n, n))
+    G[:150, :150] = 0.0                              # A11 = 0: no block elimination without pivoting
+    G += 0.0
+    ecm = np.linspace(1.2, 2.0, n)
+    p = _problem(L, lib, _ctx(), ecm, 0.827, [[0, 0, 0], [1, 1, n - 1]], G=G)
+    L.check(lib.isr_factor(p, L.dptr(np.ones(n))))
+    X = np.zeros((n, n))
+    L.check(lib.isr_get_inverse(p, L.dptr(X)))
+    ref = np.linalg.inv(G)
+    assert np.abs(X.T - ref).max() <= 1e-8 * np.abs(ref).max()
+    lib.isr_problem_destroy(p)
+
+
 def test_batch_dev_solve_batch_dev_sequence(oracle):
     """isr_solve / isr_tikhonov_solve / isr_tsvd_solve used to write their right-hand side into the buffer
     isr_toy_batch_dev caches the reference solution in; the second batch then computed d = b - vcs."""
